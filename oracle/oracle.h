@@ -1,0 +1,118 @@
+/* oracle/oracle.h — C API of the CPU parity oracle.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing in the product (ur-mvo_b200/, include/) may
+ * include, link or call this.  Only tests/, __graft_entry__.smoke() and the
+ * cpu_baseline / --impl reference legs of bench.py use it, as the checker.
+ *
+ * PARITY UNPINNED: the reference (be2rlab/UR-MVO) ships no tests, golden vectors
+ * or fixtures for this path and its arithmetic lives in g2o / Eigen / OpenCV,
+ * none of which is vendored or installable here.  This oracle is
+ * a restatement of src/g2o_optimization.cc and src/epipolar_geometry.cc plus the
+ * published g2o Levenberg-Marquardt semantics; it is cross-checked in tests/
+ * against scipy / numpy / cv2 and against the glibc rand() known answers.
+ */
+#ifndef URMVO_ORACLE_H_
+#define URMVO_ORACLE_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define URMVO_ORACLE_TRACE_MAX 64
+
+/* One row per outer LM iteration (one g2o OptimizationAlgorithmLevenberg::solve call). */
+typedef struct {
+  double chi2_before;   /* activeRobustChi2 at the start of the iteration */
+  double chi2_after;    /* currentChi when the iteration returns */
+  double lambda_after;  /* _currentLambda when the iteration returns */
+  int32_t trials;       /* damped solves tried (qmax) */
+  int32_t accepted;     /* 1 if the last trial was accepted */
+} urmvo_oracle_trace_row;
+
+typedef struct {
+  int32_t n_rows;              /* rows used in trace */
+  int32_t iters[4];            /* outer iterations run per optimize() call (BA: 2 calls, pose-only: 4 rounds) */
+  double chi2_final[4];        /* currentChi after each optimize() call */
+  double lambda_final[4];
+  urmvo_oracle_trace_row trace[URMVO_ORACLE_TRACE_MAX];
+} urmvo_oracle_stats;
+
+/* LocalmapOptimization (reference src/g2o_optimization.cc:20-177), mono edges only.
+ * poses: Nc*7 doubles, T_wc as (qx,qy,qz,qw,px,py,pz), updated in place.
+ * fixed: Nc bytes.  pts: Np*3 doubles, updated in place.
+ * uv: No*2, cam/pt: dense indices into poses/pts.  intr = fx,fy,cx,cy.
+ * chi2_thr = cfg.mono_point; huber delta = (double)(float)sqrt(chi2_thr).
+ * it0/it1 = 10/5 in the reference.  inlier: No bytes out.  Returns 0. */
+int urmvo_oracle_local_ba(int Nc, double* poses, const uint8_t* fixed, int Np, double* pts,
+                          int No, const double* uv, const int32_t* cam, const int32_t* pt,
+                          const double* intr, double chi2_thr, int it0, int it1,
+                          uint8_t* inlier, urmvo_oracle_stats* stats);
+
+/* FrameOptimization (reference src/g2o_optimization.cc:179-321), mono edges only, one frame.
+ * pose: 7 doubles T_wc in/out.  Xw: No*3 world points, uv: No*2.
+ * inlier: No bytes in/out (the reference reads the incoming flag at :273).
+ * Returns No - num_outlier of the last round run. */
+int urmvo_oracle_pose_only(double* pose, int No, const double* uv, const double* Xw,
+                           const double* intr, double chi2_thr, int rounds, int its_per_round,
+                           uint8_t* inlier, urmvo_oracle_stats* stats);
+
+/* Batched wrapper: B independent frames, obs_offset has B+1 entries. n_threads<=1: serial. */
+int urmvo_oracle_pose_only_batch(int B, const int32_t* obs_offset, double* poses,
+                                 const double* uv, const double* Xw, const double* intr,
+                                 double chi2_thr, int rounds, int its_per_round,
+                                 uint8_t* inlier, int32_t* n_inlier, int n_threads);
+
+/* Pieces exposed for unit tests. */
+/* Residual e(2), J_pose(2x6 row-major, rotation first), J_point(2x3) of EdgeSE3ProjectXYZ.
+ * T_cw given as (qx,qy,qz,qw,tx,ty,tz). Returns 1 if depth > 0. */
+int urmvo_oracle_edge(const double* Tcw, const double* X, const double* uv, const double* intr,
+                      double* e, double* Jpose, double* Jpoint);
+/* rho[3] of g2o RobustKernelHuber::robustify(e2) with the given delta. */
+void urmvo_oracle_huber(double e2, double delta, double* rho);
+/* T <- exp(update) * T (VertexSE3Expmap::oplusImpl). update = (omega, upsilon). */
+void urmvo_oracle_se3_oplus(double* Tcw, const double* update);
+/* T_wc <-> T_cw (SE3Quat(q,t).inverse(), normalising q and forcing w>=0). */
+void urmvo_oracle_se3_inverse(const double* Tin, double* Tout);
+
+/* ------------------------------------------------------------------ two-view (fp32) */
+
+typedef struct {
+  float SH, SF;            /* best scores */
+  int32_t best_H, best_F;  /* hypothesis index of the best model (-1: none scored > 0) */
+  float H21[9], F21[9];    /* row-major best models (de-normalised) */
+  int32_t used_H;          /* 1: reconstructed from H, 0: from F, -1: SH+SF==0 */
+  int32_t n_good[8];       /* nGood of each motion hypothesis tested (4 for F, 8 for H) */
+  float parallax[8];
+  int32_t best_motion;     /* index of the accepted motion hypothesis or -1 */
+} urmvo_oracle_tv_stats;
+
+/* EpipolarGeometry::reconstruct (reference src/epipolar_geometry.cc:18-98) with the
+ * 8-point sets supplied by the caller (n_hyp*8 indices into the match list).
+ * keys1/keys2: n1*2 / n2*2 pixel coordinates, matches12: n1 ints (-1 = unmatched).
+ * mask_H/mask_F: N bytes (N = number of valid matches, in order) or NULL.
+ * Returns 1 on success (T21 row-major 4x4, P3D n1*3, triangulated n1 bytes). */
+int urmvo_oracle_two_view(int n1, const float* keys1, int n2, const float* keys2,
+                          const int32_t* matches12, const float* K, float sigma, int n_hyp,
+                          const int32_t* sets, float* T21, float* P3D, uint8_t* triangulated,
+                          uint8_t* mask_H, uint8_t* mask_F, urmvo_oracle_tv_stats* stats);
+
+/* Score every hypothesis (no arg-max): scores n_hyp floats, masks n_hyp*ceil(N/32) words,
+ * models n_hyp*9 floats.  model: 0 = F, 1 = H.  For parity tests of the RANSAC kernel. */
+int urmvo_oracle_score_all(int n1, const float* keys1, int n2, const float* keys2,
+                           const int32_t* matches12, float sigma, int n_hyp, const int32_t* sets,
+                           int model, float* scores, uint32_t* masks, float* models);
+
+/* Draw n_hyp x 8 index sets exactly as reconstruct() does (:53-71) with glibc rand().
+ * reseed != 0 calls srand(seed) first (Random::seed_rand). */
+void urmvo_oracle_draw_sets(int N, int n_hyp, int reseed, int seed, int32_t* sets);
+
+/* One-sided Jacobi SVD used by the oracle (fp32). A is m x n row-major (m<=16, n<=9).
+ * Outputs: sigma[n] (descending), V n x n row-major (columns are right singular vectors),
+ * U m x n row-major (may be NULL). */
+void urmvo_oracle_svd(int m, int n, const float* A, float* sigma, float* U, float* V);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,179 @@
+"""ctypes wrapper of the CPU parity oracle (oracle/liburmvo_oracle.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product (ur-mvo_b200/) never imports this.
+PARITY UNPINNED — see oracle/oracle.h.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+TRACE_MAX = 64
+
+
+class TraceRow(C.Structure):
+    _fields_ = [("chi2_before", C.c_double), ("chi2_after", C.c_double), ("lambda_after", C.c_double),
+                ("trials", C.c_int32), ("accepted", C.c_int32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("n_rows", C.c_int32), ("iters", C.c_int32 * 4), ("chi2_final", C.c_double * 4),
+                ("lambda_final", C.c_double * 4), ("trace", TraceRow * TRACE_MAX)]
+
+    def rows(self):
+        return [(r.chi2_before, r.chi2_after, r.lambda_after, r.trials, r.accepted)
+                for r in self.trace[:self.n_rows]]
+
+
+class TVStats(C.Structure):
+    _fields_ = [("SH", C.c_float), ("SF", C.c_float), ("best_H", C.c_int32), ("best_F", C.c_int32),
+                ("H21", C.c_float * 9), ("F21", C.c_float * 9), ("used_H", C.c_int32),
+                ("n_good", C.c_int32 * 8), ("parallax", C.c_float * 8), ("best_motion", C.c_int32)]
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "liburmvo_oracle.so")
+    if force or not os.path.exists(so):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        _LIB.urmvo_oracle_local_ba.restype = C.c_int
+        _LIB.urmvo_oracle_pose_only.restype = C.c_int
+        _LIB.urmvo_oracle_two_view.restype = C.c_int
+        _LIB.urmvo_oracle_score_all.restype = C.c_int
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def local_ba(prob, chi2_thr=10.0, it0=10, it1=5):
+    """Returns (poses, pts, inlier, Stats). Inputs are not modified."""
+    poses = np.ascontiguousarray(prob["poses"], dtype=np.float64).copy()
+    pts = np.ascontiguousarray(prob["pts"], dtype=np.float64).copy()
+    fixed = np.ascontiguousarray(prob["fixed"], dtype=np.uint8)
+    uv = np.ascontiguousarray(prob["uv"], dtype=np.float64)
+    cam = np.ascontiguousarray(prob["obs_cam"], dtype=np.int32)
+    pt = np.ascontiguousarray(prob["obs_pt"], dtype=np.int32)
+    intr = np.ascontiguousarray(prob["intr"], dtype=np.float64)
+    inl = np.zeros(uv.shape[0], dtype=np.uint8)
+    st = Stats()
+    lib().urmvo_oracle_local_ba(C.c_int(poses.shape[0]), _p(poses), _p(fixed), C.c_int(pts.shape[0]), _p(pts),
+                                C.c_int(uv.shape[0]), _p(uv), _p(cam), _p(pt), _p(intr), C.c_double(chi2_thr),
+                                C.c_int(it0), C.c_int(it1), _p(inl), C.byref(st))
+    return poses, pts, inl, st
+
+
+def pose_only(pose, uv, Xw, intr, chi2_thr=10.0, rounds=4, its=10, inlier=None):
+    pose = np.ascontiguousarray(pose, dtype=np.float64).copy()
+    uv = np.ascontiguousarray(uv, dtype=np.float64)
+    Xw = np.ascontiguousarray(Xw, dtype=np.float64)
+    intr = np.ascontiguousarray(intr, dtype=np.float64)
+    inl = np.ones(uv.shape[0], dtype=np.uint8) if inlier is None else np.ascontiguousarray(inlier, dtype=np.uint8).copy()
+    st = Stats()
+    n = lib().urmvo_oracle_pose_only(_p(pose), C.c_int(uv.shape[0]), _p(uv), _p(Xw), _p(intr), C.c_double(chi2_thr),
+                                     C.c_int(rounds), C.c_int(its), _p(inl), C.byref(st))
+    return pose, inl, n, st
+
+
+def pose_only_batch(batch, chi2_thr=10.0, rounds=4, its=10, n_threads=1):
+    poses = np.ascontiguousarray(batch["poses"], dtype=np.float64).copy()
+    off = np.ascontiguousarray(batch["obs_offset"], dtype=np.int32)
+    uv = np.ascontiguousarray(batch["uv"], dtype=np.float64)
+    Xw = np.ascontiguousarray(batch["Xw"], dtype=np.float64)
+    intr = np.ascontiguousarray(batch["intr"], dtype=np.float64)
+    inl = np.ones(uv.shape[0], dtype=np.uint8)
+    B = poses.shape[0]
+    n_inl = np.zeros(B, dtype=np.int32)
+    lib().urmvo_oracle_pose_only_batch(C.c_int(B), _p(off), _p(poses), _p(uv), _p(Xw), _p(intr), C.c_double(chi2_thr),
+                                       C.c_int(rounds), C.c_int(its), _p(inl), _p(n_inl), C.c_int(n_threads))
+    return poses, inl, n_inl
+
+
+def two_view(tv, sets=None):
+    k1 = np.ascontiguousarray(tv["keys1"], dtype=np.float32)
+    k2 = np.ascontiguousarray(tv["keys2"], dtype=np.float32)
+    m = np.ascontiguousarray(tv["matches12"], dtype=np.int32)
+    K = np.ascontiguousarray(tv["K"], dtype=np.float32)
+    sets = np.ascontiguousarray(tv["sets"] if sets is None else sets, dtype=np.int32)
+    N = int((m >= 0).sum())
+    T21 = np.zeros((4, 4), dtype=np.float32)
+    P3D = np.zeros((k1.shape[0], 3), dtype=np.float32)
+    tri = np.zeros(k1.shape[0], dtype=np.uint8)
+    mH = np.zeros(N, dtype=np.uint8)
+    mF = np.zeros(N, dtype=np.uint8)
+    st = TVStats()
+    ok = lib().urmvo_oracle_two_view(C.c_int(k1.shape[0]), _p(k1), C.c_int(k2.shape[0]), _p(k2), _p(m), _p(K),
+                                     C.c_float(tv.get("sigma", 1.0)), C.c_int(sets.shape[0]), _p(sets), _p(T21),
+                                     _p(P3D), _p(tri), _p(mH), _p(mF), C.byref(st))
+    return dict(ok=bool(ok), T21=T21, P3D=P3D, triangulated=tri, mask_H=mH, mask_F=mF, stats=st)
+
+
+def score_all(tv, model, sets=None):
+    """model 0 = F, 1 = H. Returns scores[n_hyp], masks[n_hyp, words], models[n_hyp, 9]."""
+    k1 = np.ascontiguousarray(tv["keys1"], dtype=np.float32)
+    k2 = np.ascontiguousarray(tv["keys2"], dtype=np.float32)
+    m = np.ascontiguousarray(tv["matches12"], dtype=np.int32)
+    sets = np.ascontiguousarray(tv["sets"] if sets is None else sets, dtype=np.int32)
+    N = int((m >= 0).sum())
+    words = (N + 31) // 32
+    scores = np.zeros(sets.shape[0], dtype=np.float32)
+    masks = np.zeros((sets.shape[0], words), dtype=np.uint32)
+    models = np.zeros((sets.shape[0], 9), dtype=np.float32)
+    lib().urmvo_oracle_score_all(C.c_int(k1.shape[0]), _p(k1), C.c_int(k2.shape[0]), _p(k2), _p(m),
+                                 C.c_float(tv.get("sigma", 1.0)), C.c_int(sets.shape[0]), _p(sets), C.c_int(model),
+                                 _p(scores), _p(masks), _p(models))
+    return scores, masks, models
+
+
+def draw_sets(N, n_hyp, seed=0):
+    sets = np.zeros((n_hyp, 8), dtype=np.int32)
+    lib().urmvo_oracle_draw_sets(C.c_int(N), C.c_int(n_hyp), C.c_int(1), C.c_int(seed), _p(sets))
+    return sets
+
+
+def svd(A):
+    A = np.ascontiguousarray(A, dtype=np.float32)
+    m, n = A.shape
+    s = np.zeros(n, dtype=np.float32)
+    U = np.zeros((m, n), dtype=np.float32)
+    V = np.zeros((n, n), dtype=np.float32)
+    lib().urmvo_oracle_svd(C.c_int(m), C.c_int(n), _p(A), _p(s), _p(U), _p(V))
+    return U, s, V
+
+
+def edge(Tcw, X, uv, intr):
+    e = np.zeros(2); Jp = np.zeros((2, 6)); Jx = np.zeros((2, 3))
+    Tcw = np.ascontiguousarray(Tcw, dtype=np.float64); X = np.ascontiguousarray(X, dtype=np.float64)
+    uv = np.ascontiguousarray(uv, dtype=np.float64); intr = np.ascontiguousarray(intr, dtype=np.float64)
+    pos = lib().urmvo_oracle_edge(_p(Tcw), _p(X), _p(uv), _p(intr), _p(e), _p(Jp), _p(Jx))
+    return e, Jp, Jx, bool(pos)
+
+
+def huber(e2, delta):
+    rho = np.zeros(3)
+    lib().urmvo_oracle_huber(C.c_double(e2), C.c_double(delta), _p(rho))
+    return rho
+
+
+def se3_oplus(Tcw, upd):
+    T = np.ascontiguousarray(Tcw, dtype=np.float64).copy()
+    upd = np.ascontiguousarray(upd, dtype=np.float64)
+    lib().urmvo_oracle_se3_oplus(_p(T), _p(upd))
+    return T
+
+
+def se3_inverse(T):
+    T = np.ascontiguousarray(T, dtype=np.float64)
+    out = np.zeros(7)
+    lib().urmvo_oracle_se3_inverse(_p(T), _p(out))
+    return out
