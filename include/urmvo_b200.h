@@ -1,0 +1,163 @@
+/* include/urmvo_b200.h — C ABI of the B200-native geometric back-end for UR-MVO.
+ *
+ * Drop-in boundary for the reference's hot path:
+ *   LocalmapOptimization   /root/reference/include/g2o_optimization.h:13-15  (src/g2o_optimization.cc:20-177)
+ *   FrameOptimization      /root/reference/include/g2o_optimization.h:17-19  (src/g2o_optimization.cc:179-321)
+ *   EpipolarGeometry::reconstruct  /root/reference/include/epipolar_geometry.h:31-35 (src/epipolar_geometry.cc:18-98)
+ * The C++ adapters in ur-mvo_b200/adapter/ keep those signatures and flatten the reference's
+ * MapOfPoses / MapOfPoints3d / constraint vectors / cv::KeyPoint into the SoA arrays below.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is a HOST pointer unless the name says _dev.
+ *  - every function returns 0 on success, <0 (urmvo_status) on error; nothing throws or aborts;
+ *    urmvo_last_error() describes the last failure on the calling thread.
+ *  - a context owns one CUDA device, one non-blocking stream and its device workspaces.  Calls on
+ *    one context must not overlap; different contexts are independent (re-entrant per handle).
+ *    The legacy default stream is never used and cudaDeviceSynchronize is never called.
+ *  - there is NO CPU fallback: without a usable sm_100 device every entry point fails loudly.
+ *  - poses are T_wc as (qx,qy,qz,qw,px,py,pz) doubles — the reference's Pose3d (include/types.h:18-31).
+ */
+#ifndef URMVO_B200_H_
+#define URMVO_B200_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct urmvo_ctx urmvo_ctx;
+typedef struct urmvo_ba_plan urmvo_ba_plan;       /* device-resident batch of BA windows */
+typedef struct urmvo_pose_plan urmvo_pose_plan;   /* device-resident batch of pose-only frames */
+typedef struct urmvo_tv_plan urmvo_tv_plan;       /* device-resident two-view problem */
+
+typedef enum {
+  URMVO_OK = 0,
+  URMVO_ERR_NO_DEVICE = -1,   /* no CUDA device / not sm_100 / driver failure */
+  URMVO_ERR_CUDA = -2,        /* a CUDA runtime call failed */
+  URMVO_ERR_ARG = -3,         /* invalid argument */
+  URMVO_ERR_NCCL = -4,        /* NCCL unavailable or a collective failed */
+  URMVO_ERR_UNSUPPORTED = -5
+} urmvo_status;
+
+int urmvo_version(void);
+const char* urmvo_last_error(void);
+
+int urmvo_create(urmvo_ctx** ctx, int device);
+void urmvo_destroy(urmvo_ctx* ctx);
+/* The context's cudaStream_t (as void*), so that callers can record CUDA events around plan runs. */
+void* urmvo_stream(urmvo_ctx* ctx);
+int urmvo_sync(urmvo_ctx* ctx);
+/* Number of kernels launched by this context since creation (bench.py's gpu_launches). */
+int64_t urmvo_launch_count(urmvo_ctx* ctx);
+
+/* ------------------------------------------------------------------ local BA (B1-B6) */
+
+typedef struct {
+  double pcg_tol;        /* relative tolerance on sqrt(r^T M^-1 r); 0 -> 1e-10 */
+  int32_t pcg_max_iter;  /* 0 -> max(60, 2*6*Ncf) capped at 1000 */
+  int32_t cluster_size;  /* CTAs cooperating on one window in batch mode (1,2,4,8,16); 0 -> auto */
+  int32_t threads;       /* threads per CTA; 0 -> auto */
+  int32_t reserved;
+} urmvo_ba_options;
+
+typedef struct {
+  int32_t iters[2];          /* outer LM iterations run by optimize(it0) / optimize(it1) */
+  int32_t trials[2];         /* damped solves (trial steps) in each call */
+  int32_t pcg_iters[2];      /* PCG iterations summed over the trials of each call */
+  int32_t n_level1;          /* observations excluded from the second optimisation */
+  double chi2_initial;       /* robust chi2 at the input estimate */
+  double chi2_final[2];      /* currentChi after each optimize() call */
+  double lambda_final[2];
+} urmvo_ba_stats;
+
+/* One-shot LocalmapOptimization on host buffers (mono edges).
+ *  poses  Nc*7 in/out (T_wc), fixed Nc bytes, pts Np*3 in/out,
+ *  uv No*2, cam / pt: No dense indices (into poses / pts).  Observations may be in any order.
+ *  intr = fx,fy,cx,cy.  chi2_thr = cfg.mono_point (Huber delta = (double)(float)sqrt(chi2_thr)).
+ *  it0 / it1 = 10 / 5 in the reference.  inlier: No bytes out.  stats may be NULL. */
+int urmvo_local_ba(urmvo_ctx* ctx, int Nc, double* poses, const uint8_t* fixed, int Np, double* pts,
+                   int No, const double* uv, const int32_t* cam, const int32_t* pt,
+                   const double* intr, double chi2_thr, int it0, int it1, uint8_t* inlier,
+                   urmvo_ba_stats* stats, const urmvo_ba_options* opts);
+
+/* Batch of B independent windows, concatenated: window w owns cams [cam_off[w],cam_off[w+1]),
+ * points [pt_off[w],pt_off[w+1]) and observations [obs_off[w],obs_off[w+1]); cam/pt indices are
+ * LOCAL to the window.  stats: B entries or NULL. */
+int urmvo_local_ba_batch(urmvo_ctx* ctx, int B, const int32_t* cam_off, const int32_t* pt_off,
+                         const int32_t* obs_off, double* poses, const uint8_t* fixed, double* pts,
+                         const double* uv, const int32_t* cam, const int32_t* pt, const double* intr,
+                         double chi2_thr, int it0, int it1, uint8_t* inlier, urmvo_ba_stats* stats,
+                         const urmvo_ba_options* opts);
+
+/* Plan API: upload once, run many times from HBM-resident inputs (each run restarts from the
+ * uploaded initial estimate), download when wanted. */
+int urmvo_ba_plan_create(urmvo_ctx* ctx, urmvo_ba_plan** plan, int B, const int32_t* cam_off,
+                         const int32_t* pt_off, const int32_t* obs_off, const double* poses,
+                         const uint8_t* fixed, const double* pts, const double* uv,
+                         const int32_t* cam, const int32_t* pt, const double* intr,
+                         double chi2_thr, int it0, int it1, const urmvo_ba_options* opts);
+int urmvo_ba_plan_run(urmvo_ba_plan* plan);            /* asynchronous on the context stream */
+int urmvo_ba_plan_download(urmvo_ba_plan* plan, double* poses, double* pts, uint8_t* inlier,
+                           urmvo_ba_stats* stats);    /* synchronises the stream */
+void urmvo_ba_plan_destroy(urmvo_ba_plan* plan);
+
+/* ------------------------------------------------------------------ pose-only (B7-B8) */
+
+/* Batched FrameOptimization: frame f owns observations [obs_off[f], obs_off[f+1]).
+ * poses B*7 in/out (T_wc); uv No*2; Xw No*3 (world points, constants); inlier No bytes in/out
+ * (the reference reads the incoming flag, src/g2o_optimization.cc:273); n_inlier B ints out
+ * (= #constraints - #outliers of the last round, :319-320). rounds / its = 4 / 10. */
+int urmvo_pose_only_batch(urmvo_ctx* ctx, int B, const int32_t* obs_off, double* poses,
+                          const double* uv, const double* Xw, const double* intr, double chi2_thr,
+                          int rounds, int its_per_round, uint8_t* inlier, int32_t* n_inlier);
+
+int urmvo_pose_plan_create(urmvo_ctx* ctx, urmvo_pose_plan** plan, int B, const int32_t* obs_off,
+                           const double* poses, const double* uv, const double* Xw,
+                           const double* intr, double chi2_thr, int rounds, int its_per_round,
+                           const uint8_t* inlier);
+int urmvo_pose_plan_run(urmvo_pose_plan* plan);
+int urmvo_pose_plan_download(urmvo_pose_plan* plan, double* poses, uint8_t* inlier, int32_t* n_inlier,
+                             int32_t* lm_iters /* B, total outer iterations, may be NULL */);
+void urmvo_pose_plan_destroy(urmvo_pose_plan* plan);
+
+/* ------------------------------------------------------------------ two-view RANSAC (R1-R8) */
+
+typedef struct {
+  float SH, SF;            /* best homography / fundamental scores */
+  int32_t best_H, best_F;  /* hypothesis index of the best model, -1 if no score > 0 */
+  float H21[9], F21[9];    /* best models, row-major */
+  int32_t used_H;          /* 1: reconstructed from H, 0: from F, -1: SH+SF == 0 */
+  int32_t n_good[8];       /* nGood per motion hypothesis (4 for F, 8 for H) */
+  float parallax[8];       /* degrees */
+  int32_t best_motion;     /* accepted motion hypothesis or -1 */
+} urmvo_tv_stats;
+
+/* EpipolarGeometry::reconstruct on host buffers.
+ *  keys1 n1*2, keys2 n2*2 pixel coordinates; matches12 n1 ints (index into keys2 or -1);
+ *  K 3x3 row-major; sets n_hyp*8 indices into the list of valid matches (host-generated with the
+ *  reference's Random::RandomInt so that "same seeds" means the same array).
+ *  Outputs: T21 4x4 row-major, P3D n1*3, triangulated n1 bytes; mask_H / mask_F: N bytes each
+ *  (N = number of valid matches) or NULL.  *success = 1 if the reference would return true. */
+int urmvo_two_view(urmvo_ctx* ctx, int n1, const float* keys1, int n2, const float* keys2,
+                   const int32_t* matches12, const float* K, float sigma, int n_hyp,
+                   const int32_t* sets, float* T21, float* P3D, uint8_t* triangulated,
+                   uint8_t* mask_H, uint8_t* mask_F, urmvo_tv_stats* stats, int* success);
+
+int urmvo_tv_plan_create(urmvo_ctx* ctx, urmvo_tv_plan** plan, int n1, const float* keys1, int n2,
+                         const float* keys2, const int32_t* matches12, const float* K, float sigma,
+                         int n_hyp, const int32_t* sets);
+/* Fit + score + arg-max of all hypotheses of both models (asynchronous). */
+int urmvo_tv_plan_run_ransac(urmvo_tv_plan* plan);
+/* Per-hypothesis results for parity tests: model 0 = F, 1 = H.
+ * scores n_hyp floats, masks n_hyp*ceil(N/32) words, models n_hyp*9 floats (any may be NULL). */
+int urmvo_tv_plan_download_hyps(urmvo_tv_plan* plan, int model, float* scores, uint32_t* masks,
+                                float* models);
+/* Model selection + motion recovery + triangulation; synchronises and fills the outputs. */
+int urmvo_tv_plan_reconstruct(urmvo_tv_plan* plan, float* T21, float* P3D, uint8_t* triangulated,
+                              uint8_t* mask_H, uint8_t* mask_F, urmvo_tv_stats* stats, int* success);
+void urmvo_tv_plan_destroy(urmvo_tv_plan* plan);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* URMVO_B200_H_ */

@@ -1,0 +1,859 @@
+// csrc/ba_kernels.cu — sliding-window bundle adjustment on sm_100a: the whole g2o-style
+// Levenberg-Marquardt loop of one LocalmapOptimization call runs inside ONE persistent kernel.
+//
+// Reference behaviour reproduced:
+//   /root/reference/src/g2o_optimization.cc:20-177 (LocalmapOptimization call sequence)
+//   g2o EdgeSE3ProjectXYZ / RobustKernelHuber / BlockSolver Schur / OptimizationAlgorithmLevenberg
+//   (upstream g2o, not vendored by the reference; semantics in SURVEY.md §8c.1).
+//
+// Formulation: matrix-free in the observations.  Nothing per-observation is ever
+// written to HBM: each phase re-derives residual / Huber weight / 2x6 and 2x3 Jacobians from the
+// 24 B/observation SoA input (uv + camera index), because on B200 the fp64 flops to recompute are
+// cheaper than the 144 B/observation an explicit Hpl block would cost to write and re-read twice.
+//   phase LIN      warp per point: residuals, Hll/bl (warp-shuffle reduction), Dinv, and the Schur
+//                  complement contributions J_i^T (w_i I - A_i B_j^T) J_j accumulated into the
+//                  block-sparse reduced camera system S, right-hand side b_s
+//   phase PCG      block-Jacobi preconditioned conjugate gradients on S x_p = b_s
+//   phase BACKSUB  warp per point: x_l = Dinv (b_l - W^T x_p), trial state, trial robust chi2
+//   decide         gain ratio, lambda update, accept / reject — on device, uniform over the scope
+
+#include "ba_types.h"
+#include "common.cuh"
+#include "kernels.h"
+#include "../../include/urmvo_b200.h"
+
+namespace urmvo {
+
+// ------------------------------------------------------------------------------- edge math
+
+struct EdgeLin {
+  double e0, e1, w, rho0;
+  double Jx[6];   // 2x3 d e / d X
+  double Jp[12];  // 2x6 d e / d xi (rotation first)
+};
+
+// pc = R X + t
+__device__ __forceinline__ void map_point(const double* __restrict__ Rt, const double* X, double* pc) {
+  pc[0] = Rt[0] * X[0] + Rt[1] * X[1] + Rt[2] * X[2] + Rt[9];
+  pc[1] = Rt[3] * X[0] + Rt[4] * X[1] + Rt[5] * X[2] + Rt[10];
+  pc[2] = Rt[6] * X[0] + Rt[7] * X[1] + Rt[8] * X[2] + Rt[11];
+}
+
+// EdgeSE3ProjectXYZ::computeError: e = z - (x/z*fx + cx, y/z*fy + cy); returns chi2.
+__device__ __forceinline__ double edge_error(const double* pc, double u, double v, const double* K,
+                                             double& e0, double& e1) {
+  e0 = u - (pc[0] / pc[2] * K[0] + K[2]);
+  e1 = v - (pc[1] / pc[2] * K[1] + K[3]);
+  return e0 * e0 + e1 * e1;
+}
+
+// EdgeSE3ProjectXYZ::linearizeOplus pose part (2x6).
+__device__ __forceinline__ void edge_jac_pose(const double* pc, const double* K, double* Jp) {
+  const double x = pc[0], y = pc[1], z = pc[2], z2 = z * z;
+  Jp[0] = x * y / z2 * K[0];
+  Jp[1] = -(1 + (x * x / z2)) * K[0];
+  Jp[2] = y / z * K[0];
+  Jp[3] = -1. / z * K[0];
+  Jp[4] = 0;
+  Jp[5] = x / z2 * K[0];
+  Jp[6] = (1 + y * y / z2) * K[1];
+  Jp[7] = -x * y / z2 * K[1];
+  Jp[8] = -x / z * K[1];
+  Jp[9] = 0;
+  Jp[10] = -1. / z * K[1];
+  Jp[11] = y / z2 * K[1];
+}
+
+// EdgeSE3ProjectXYZ::linearizeOplus point part (2x3) = -1/z * [[fx,0,-x/z fx],[0,fy,-y/z fy]] * R
+__device__ __forceinline__ void edge_jac_point(const double* __restrict__ Rt, const double* pc,
+                                               const double* K, double* Jx) {
+  const double x = pc[0], y = pc[1], z = pc[2];
+  const double t02 = -x / z * K[0], t12 = -y / z * K[1];
+  const double miz = -1. / z;
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    Jx[c] = miz * (K[0] * Rt[c] + t02 * Rt[6 + c]);
+    Jx[3 + c] = miz * (K[1] * Rt[3 + c] + t12 * Rt[6 + c]);
+  }
+}
+
+// Symmetric 3x3 inverse, packed (00 01 02 11 12 22), cofactor formula like Eigen's fixed-size inverse.
+__device__ __forceinline__ void sym3_inverse(const double* h, double* r) {
+  const double a00 = h[0], a01 = h[1], a02 = h[2], a11 = h[3], a12 = h[4], a22 = h[5];
+  const double c00 = a11 * a22 - a12 * a12;
+  const double c01 = a12 * a02 - a01 * a22;
+  const double c02 = a01 * a12 - a11 * a02;
+  const double det = a00 * c00 + a01 * c01 + a02 * c02;
+  const double id = 1.0 / det;
+  r[0] = c00 * id;
+  r[1] = c01 * id;
+  r[2] = c02 * id;
+  r[3] = (a00 * a22 - a02 * a02) * id;
+  r[4] = (a01 * a02 - a00 * a12) * id;
+  r[5] = (a00 * a11 - a01 * a01) * id;
+}
+
+// Block (ci,cj) of S, ci <= cj, by binary search in the BSR row; -1 if absent.
+__device__ __forceinline__ int find_block(const BAWin& W, int ci, int cj) {
+  int lo = W.row_ptr[ci], hi = W.row_ptr[ci + 1] - 1;
+  while (lo <= hi) {
+    const int mid = (lo + hi) >> 1;
+    const int c = W.col[mid];
+    if (c == cj) return mid;
+    if (c < cj) lo = mid + 1; else hi = mid - 1;
+  }
+  return -1;
+}
+
+// Per-warp staging area, structure-of-arrays over the observations of one point.
+struct WarpStage {
+  double* f;  // 27 fields x kmax: Jp[12] | B[6] | A[6] | we[2] | w
+  int* cf;    // kmax
+  int kmax;
+  __device__ __forceinline__ double& Jp(int a, int i) { return f[a * kmax + i]; }
+  __device__ __forceinline__ double& B(int a, int i) { return f[(12 + a) * kmax + i]; }
+  __device__ __forceinline__ double& A(int a, int i) { return f[(18 + a) * kmax + i]; }
+  __device__ __forceinline__ double& we(int a, int i) { return f[(24 + a) * kmax + i]; }
+  __device__ __forceinline__ double& w(int i) { return f[26 * kmax + i]; }
+};
+constexpr int kStageFields = 27;
+
+__host__ __device__ inline size_t warp_stage_bytes(int kmax) {
+  return (size_t)kmax * (kStageFields * sizeof(double) + sizeof(int));
+}
+
+// ------------------------------------------------------------------------------- phase LIN
+
+// DIAG = true: only diag(Hpp) (atomics into hdiag), max diag(Hll) and the robust chi2 — the
+// quantities OptimizationAlgorithmLevenberg::computeLambdaInit needs at iteration 0.
+template <bool DIAG, class Scope>
+__device__ void lin_phase(const Scope& sc, const BAWin& W, int cur, double lambda, bool robust,
+                          double delta, WarpStage st, double& chi_acc, double& maxdiag_acc) {
+  const int lane = threadIdx.x & 31;
+  const int wpc = blockDim.x >> 5;
+  const int gw = sc.blk() * wpc + (threadIdx.x >> 5);
+  const int gstride = sc.nblk() * wpc;
+  const double* __restrict__ camRt = W.camRt[cur];
+  const double* __restrict__ pts = W.pts[cur];
+  const double K[4] = {W.intr[0], W.intr[1], W.intr[2], W.intr[3]};
+
+  for (int l = gw; l < W.Np; l += gstride) {
+    const int ps = W.pt_start[l], k = W.pt_start[l + 1] - ps;
+    const double X[3] = {pts[l * 3], pts[l * 3 + 1], pts[l * 3 + 2]};
+    double h[6] = {0, 0, 0, 0, 0, 0}, bl[3] = {0, 0, 0};
+    for (int i = lane; i < k; i += 32) {
+      const int o = ps + i;
+      int cf = -1;
+      if (!W.level[o]) {
+        const int c = W.ocam[o];
+        const double* Rt = camRt + (size_t)c * 12;
+        double pc[3], e0, e1, w;
+        map_point(Rt, X, pc);
+        const double2 uv = *reinterpret_cast<const double2*>(W.uv + (size_t)o * 2);
+        const double e2 = edge_error(pc, uv.x, uv.y, K, e0, e1);
+        chi_acc += huber_rho(e2, delta, robust, w);
+        double Jx[6], B[6];
+        edge_jac_point(Rt, pc, K, Jx);
+#pragma unroll
+        for (int a = 0; a < 6; a++) B[a] = w * Jx[a];
+        h[0] += B[0] * Jx[0] + B[3] * Jx[3];
+        h[1] += B[0] * Jx[1] + B[3] * Jx[4];
+        h[2] += B[0] * Jx[2] + B[3] * Jx[5];
+        h[3] += B[1] * Jx[1] + B[4] * Jx[4];
+        h[4] += B[1] * Jx[2] + B[4] * Jx[5];
+        h[5] += B[2] * Jx[2] + B[5] * Jx[5];
+#pragma unroll
+        for (int a = 0; a < 3; a++) bl[a] -= B[a] * e0 + B[3 + a] * e1;
+        cf = W.cam_free[c];
+        if (cf >= 0) {
+          double Jp[12];
+          edge_jac_pose(pc, K, Jp);
+          if (DIAG) {
+#pragma unroll
+            for (int a = 0; a < 6; a++)
+              atomicAdd(&W.hdiag[cf * 6 + a], w * (Jp[a] * Jp[a] + Jp[6 + a] * Jp[6 + a]));
+          } else {
+#pragma unroll
+            for (int a = 0; a < 12; a++) st.Jp(a, i) = Jp[a];
+#pragma unroll
+            for (int a = 0; a < 6; a++) st.B(a, i) = B[a];
+            st.we(0, i) = w * e0;
+            st.we(1, i) = w * e1;
+            st.w(i) = w;
+          }
+        }
+      }
+      if (!DIAG) st.cf[i] = cf;
+    }
+#pragma unroll
+    for (int a = 0; a < 6; a++) h[a] = warp_sum(h[a]);
+    if (DIAG) {
+      maxdiag_acc = fmax(maxdiag_acc, fmax(fabs(h[0]), fmax(fabs(h[3]), fabs(h[5]))));
+      continue;
+    }
+#pragma unroll
+    for (int a = 0; a < 3; a++) bl[a] = warp_sum(bl[a]);
+    // (Hll + lambda I)^-1 — BlockSolver::setLambda adds lambda to every diagonal block
+    double Di[6];
+    {
+      const double hl[6] = {h[0] + lambda, h[1], h[2], h[3] + lambda, h[4], h[5] + lambda};
+      sym3_inverse(hl, Di);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int a = 0; a < 6; a++) W.Dinv[(size_t)l * 6 + a] = Di[a];
+#pragma unroll
+      for (int a = 0; a < 3; a++) W.bl[(size_t)l * 3 + a] = bl[a];
+    }
+    __syncwarp();
+    // A_i = B_i Dinv (2x3), gradient terms: b_s += -J^T (w e + A b_l), b_p += -J^T w e
+    for (int i = lane; i < k; i += 32) {
+      const int cf = st.cf[i];
+      if (cf < 0) continue;
+      double A[6];
+#pragma unroll
+      for (int r = 0; r < 2; r++) {
+        const double b0 = st.B(r * 3, i), b1 = st.B(r * 3 + 1, i), b2 = st.B(r * 3 + 2, i);
+        A[r * 3 + 0] = b0 * Di[0] + b1 * Di[1] + b2 * Di[2];
+        A[r * 3 + 1] = b0 * Di[1] + b1 * Di[3] + b2 * Di[4];
+        A[r * 3 + 2] = b0 * Di[2] + b1 * Di[4] + b2 * Di[5];
+      }
+#pragma unroll
+      for (int a = 0; a < 6; a++) st.A(a, i) = A[a];
+      const double we0 = st.we(0, i), we1 = st.we(1, i);
+      const double g0 = we0 + (A[0] * bl[0] + A[1] * bl[1] + A[2] * bl[2]);
+      const double g1 = we1 + (A[3] * bl[0] + A[4] * bl[1] + A[5] * bl[2]);
+#pragma unroll
+      for (int a = 0; a < 6; a++) {
+        const double j0 = st.Jp(a, i), j1 = st.Jp(6 + a, i);
+        atomicAdd(&W.bs[cf * 6 + a], -(j0 * g0 + j1 * g1));
+        atomicAdd(&W.bp[cf * 6 + a], -(j0 * we0 + j1 * we1));
+      }
+    }
+    __syncwarp();
+    // Schur pairs (i <= j): one lane per pair, 6x6 block = J_i^T M J_j,
+    //   M = w_i I - A_i B_i^T (i == j: Hpp term and its Schur correction), M = -A_i B_j^T otherwise.
+    const int npairs = k * (k + 1) / 2;
+    for (int pi = lane; pi < npairs; pi += 32) {
+      const int kk = 2 * k + 1;
+      int i = (int)(((float)kk - sqrtf((float)(kk * kk - 8 * pi))) * 0.5f);
+      i = max(0, min(i, k - 1));
+      while (i > 0 && i * k - i * (i - 1) / 2 > pi) i--;
+      while ((i + 1) * k - (i + 1) * i / 2 <= pi) i++;
+      const int j = i + (pi - (i * k - i * (i - 1) / 2));
+      const int ci = st.cf[i], cj = st.cf[j];
+      if (ci < 0 || cj < 0) continue;
+      double M[4];
+      {
+        const double a0 = st.A(0, i), a1 = st.A(1, i), a2 = st.A(2, i);
+        const double a3 = st.A(3, i), a4 = st.A(4, i), a5 = st.A(5, i);
+        const double b0 = st.B(0, j), b1 = st.B(1, j), b2 = st.B(2, j);
+        const double b3 = st.B(3, j), b4 = st.B(4, j), b5 = st.B(5, j);
+        M[0] = -(a0 * b0 + a1 * b1 + a2 * b2);
+        M[1] = -(a0 * b3 + a1 * b4 + a2 * b5);
+        M[2] = -(a3 * b0 + a4 * b1 + a5 * b2);
+        M[3] = -(a3 * b3 + a4 * b4 + a5 * b5);
+        if (i == j) { const double w = st.w(i); M[0] += w; M[3] += w; }
+      }
+      double T[12];  // T = M J_j (2x6)
+#pragma unroll
+      for (int b = 0; b < 6; b++) {
+        const double j0 = st.Jp(b, j), j1 = st.Jp(6 + b, j);
+        T[b] = M[0] * j0 + M[1] * j1;
+        T[6 + b] = M[2] * j0 + M[3] * j1;
+      }
+      const bool swap = ci > cj;
+      const int blk = swap ? find_block(W, cj, ci) : find_block(W, ci, cj);
+      if (blk < 0) continue;  // cannot happen for a structure built from the same observations
+      double* Sb = W.S + (size_t)blk * 36;
+      const bool same_cam_twice = (ci == cj) && (i != j);
+#pragma unroll
+      for (int a = 0; a < 6; a++) {
+        const double j0 = st.Jp(a, i), j1 = st.Jp(6 + a, i);
+#pragma unroll
+        for (int b = 0; b < 6; b++) {
+          const double v = j0 * T[b] + j1 * T[6 + b];
+          if (!swap) atomicAdd(&Sb[a * 6 + b], v); else atomicAdd(&Sb[b * 6 + a], v);
+          if (same_cam_twice) atomicAdd(&Sb[b * 6 + a], v);
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------- phase PCG
+
+// 6x6 SPD inverse by Cholesky (block-Jacobi preconditioner). Returns false if not positive definite.
+__device__ __forceinline__ bool spd6_inverse(const double* __restrict__ A, double* __restrict__ Ainv) {
+  double L[36];
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+#pragma unroll
+    for (int j = 0; j <= i; j++) {
+      double s = A[i * 6 + j];
+#pragma unroll
+      for (int k = 0; k < j; k++) s -= L[i * 6 + k] * L[j * 6 + k];
+      if (j < i) L[i * 6 + j] = s / L[j * 6 + j];
+      else {
+        if (!(s > 0.0)) return false;
+        L[i * 6 + i] = sqrt(s);
+      }
+    }
+  }
+  // columns of the inverse: solve L L^T x = e_c
+#pragma unroll
+  for (int c = 0; c < 6; c++) {
+    double y[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+      double s = (i == c) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k = 0; k < i; k++) s -= L[i * 6 + k] * y[k];
+      y[i] = s / L[i * 6 + i];
+    }
+#pragma unroll
+    for (int i = 5; i >= 0; i--) {
+      double s = y[i];
+#pragma unroll
+      for (int k = i + 1; k < 6; k++) s -= L[k * 6 + i] * y[k];
+      y[i] = s / L[i * 6 + i];
+    }
+#pragma unroll
+    for (int i = 0; i < 6; i++) Ainv[i * 6 + c] = y[i];
+  }
+  return true;
+}
+
+// Solves S xp = bs. Rows (6 per free camera) are distributed over the threads of the scope.
+// Returns false when S is not positive definite (=> g2o's "ok2 == false").
+template <class Scope>
+__device__ bool pcg_phase(const Scope& sc, const BAWin& W, double tol, int max_iter, double* part,
+                          int& parity, double* red, int& iters_out) {
+  const int n = W.Ncf * 6;
+  const int gt = sc.blk() * blockDim.x + threadIdx.x;
+  const int gstride = sc.nblk() * blockDim.x;
+  iters_out = 0;
+  if (n == 0) return true;
+  // preconditioner: Minv_i = S_ii^-1
+  double bad = 0.0;
+  for (int i = gt; i < W.Ncf; i += gstride) {
+    if (!spd6_inverse(W.S + (size_t)W.row_ptr[i] * 36, W.Minv + (size_t)i * 36)) bad = 1.0;
+  }
+  sc.sync();
+  // x = 0, r = b, z = Minv r, p = z
+  double acc[2] = {0.0, 0.0};
+  for (int row = gt; row < n; row += gstride) {
+    const int i = row / 6, a = row - i * 6;
+    const double* Mi = W.Minv + (size_t)i * 36 + a * 6;
+    const double* bi = W.bs + i * 6;
+    double zz = 0.0;
+#pragma unroll
+    for (int b = 0; b < 6; b++) zz += Mi[b] * __ldcg(bi + b);
+    const double rr = __ldcg(W.bs + row);
+    W.xp[row] = 0.0;
+    W.r[row] = rr;
+    W.z[row] = zz;
+    W.p[row] = zz;
+    acc[0] += rr * zz;
+  }
+  acc[1] = bad;
+  double dummy[1];
+  scope_reduce<2, 0>(sc, acc, dummy, part, parity, red);
+  if (acc[1] > 0.0) return false;
+  double rz = acc[0];
+  const double rz0 = rz;
+  if (!(rz0 > 0.0)) return rz0 == 0.0;  // b == 0 -> x = 0;  negative / NaN -> failure
+  const double stop = tol * tol * rz0;
+  bool ok = true;
+  int it = 0;
+  for (; it < max_iter; it++) {
+    // Ap = S p (upper blocks + mirrored transposes), pAp
+    double pap[1] = {0.0};
+    for (int row = gt; row < n; row += gstride) {
+      const int i = row / 6, a = row - i * 6;
+      double s = 0.0;
+      for (int e = W.row_ptr[i]; e < W.row_ptr[i + 1]; e++) {
+        const double* Sb = W.S + (size_t)e * 36 + a * 6;
+        const double* pj = W.p + W.col[e] * 6;
+#pragma unroll
+        for (int b = 0; b < 6; b++) s += __ldcg(Sb + b) * __ldcg(pj + b);
+      }
+      for (int e = W.lrow_ptr[i]; e < W.lrow_ptr[i + 1]; e++) {
+        const double* Sb = W.S + (size_t)W.lblk[e] * 36 + a;
+        const double* pj = W.p + W.lcol[e] * 6;
+#pragma unroll
+        for (int b = 0; b < 6; b++) s += __ldcg(Sb + b * 6) * __ldcg(pj + b);
+      }
+      W.Ap[row] = s;
+      pap[0] += __ldcg(W.p + row) * s;
+    }
+    scope_reduce<1, 0>(sc, pap, dummy, part, parity, red);
+    if (!(pap[0] > 0.0)) { ok = false; break; }
+    const double alpha = rz / pap[0];
+    // x += alpha p ; r -= alpha Ap  (own rows), then z = Minv r needs the whole 6-block of r
+    for (int row = gt; row < n; row += gstride) {
+      W.xp[row] += alpha * __ldcg(W.p + row);
+      W.r[row] -= alpha * W.Ap[row];
+    }
+    sc.sync();
+    double rzn[1] = {0.0};
+    for (int row = gt; row < n; row += gstride) {
+      const int i = row / 6, a = row - i * 6;
+      const double* Mi = W.Minv + (size_t)i * 36 + a * 6;
+      const double* ri = W.r + i * 6;
+      double zz = 0.0;
+#pragma unroll
+      for (int b = 0; b < 6; b++) zz += Mi[b] * __ldcg(ri + b);
+      W.z[row] = zz;
+      rzn[0] += __ldcg(W.r + row) * zz;
+    }
+    scope_reduce<1, 0>(sc, rzn, dummy, part, parity, red);
+    if (!(rzn[0] > stop)) { it++; break; }
+    const double beta = rzn[0] / rz;
+    rz = rzn[0];
+    for (int row = gt; row < n; row += gstride) W.p[row] = W.z[row] + beta * W.p[row];
+    sc.sync();
+  }
+  iters_out = it;
+  return ok;
+}
+
+// ------------------------------------------------------------------------------- cameras
+
+template <class Scope>
+__device__ void refresh_camRt(const Scope& sc, const BAWin& W, int buf) {
+  const int gt = sc.blk() * blockDim.x + threadIdx.x, gstride = sc.nblk() * blockDim.x;
+  for (int c = gt; c < W.Nc; c += gstride) {
+    const double* q = W.cam[buf] + (size_t)c * 7;
+    double R[9];
+    quat_to_R(q, R);
+    double* o = W.camRt[buf] + (size_t)c * 12;
+#pragma unroll
+    for (int a = 0; a < 9; a++) o[a] = R[a];
+    o[9] = q[4]; o[10] = q[5]; o[11] = q[6];
+  }
+}
+
+// trial cameras = exp(x_c) * current (free cameras), copy (fixed cameras)
+template <class Scope>
+__device__ void cam_update(const Scope& sc, const BAWin& W, int cur) {
+  const int gt = sc.blk() * blockDim.x + threadIdx.x, gstride = sc.nblk() * blockDim.x;
+  const int tr = cur ^ 1;
+  for (int c = gt; c < W.Nc; c += gstride) {
+    const double* q = W.cam[cur] + (size_t)c * 7;
+    double* qo = W.cam[tr] + (size_t)c * 7;
+    const int cf = W.cam_free[c];
+    if (cf >= 0) {
+      double u[6];
+#pragma unroll
+      for (int a = 0; a < 6; a++) u[a] = __ldcg(W.xp + cf * 6 + a);
+      double qn[4], tn[3];
+      se3_oplus(u, q, q + 4, qn, tn);
+      qo[0] = qn[0]; qo[1] = qn[1]; qo[2] = qn[2]; qo[3] = qn[3];
+      qo[4] = tn[0]; qo[5] = tn[1]; qo[6] = tn[2];
+    } else {
+#pragma unroll
+      for (int a = 0; a < 7; a++) qo[a] = q[a];
+    }
+    double R[9];
+    quat_to_R(qo, R);
+    double* o = W.camRt[tr] + (size_t)c * 12;
+#pragma unroll
+    for (int a = 0; a < 9; a++) o[a] = R[a];
+    o[9] = qo[4]; o[10] = qo[5]; o[11] = qo[6];
+  }
+}
+
+// ------------------------------------------------------------------------------- phase BACKSUB
+
+// x_l = Dinv (b_l - sum_i B_i^T (J_i x_ci)); X' = X + x_l; trial robust chi2; landmark part of
+// computeScale: sum x_l (lambda x_l + b_l).
+template <class Scope>
+__device__ void backsub_phase(const Scope& sc, const BAWin& W, int cur, double lambda, bool robust,
+                              double delta, double& chi_acc, double& scale_acc) {
+  const int lane = threadIdx.x & 31;
+  const int wpc = blockDim.x >> 5;
+  const int gw = sc.blk() * wpc + (threadIdx.x >> 5);
+  const int gstride = sc.nblk() * wpc;
+  const int tr = cur ^ 1;
+  const double* __restrict__ camRt = W.camRt[cur];
+  const double* __restrict__ camRtT = W.camRt[tr];
+  const double K[4] = {W.intr[0], W.intr[1], W.intr[2], W.intr[3]};
+  for (int l = gw; l < W.Np; l += gstride) {
+    const int ps = W.pt_start[l], k = W.pt_start[l + 1] - ps;
+    const double X[3] = {W.pts[cur][l * 3], W.pts[cur][l * 3 + 1], W.pts[cur][l * 3 + 2]};
+    double c3[3] = {0, 0, 0};
+    for (int i = lane; i < k; i += 32) {
+      const int o = ps + i;
+      if (W.level[o]) continue;
+      const int c = W.ocam[o];
+      const int cf = W.cam_free[c];
+      if (cf < 0) continue;
+      const double* Rt = camRt + (size_t)c * 12;
+      double pc[3], e0, e1, w, Jp[12], Jx[6];
+      map_point(Rt, X, pc);
+      const double2 uv = *reinterpret_cast<const double2*>(W.uv + (size_t)o * 2);
+      const double e2 = edge_error(pc, uv.x, uv.y, K, e0, e1);
+      huber_rho(e2, delta, robust, w);
+      edge_jac_pose(pc, K, Jp);
+      edge_jac_point(Rt, pc, K, Jx);
+      double s0 = 0, s1 = 0;
+#pragma unroll
+      for (int a = 0; a < 6; a++) {
+        const double xa = __ldcg(W.xp + cf * 6 + a);
+        s0 += Jp[a] * xa;
+        s1 += Jp[6 + a] * xa;
+      }
+      s0 *= w; s1 *= w;
+#pragma unroll
+      for (int a = 0; a < 3; a++) c3[a] += Jx[a] * s0 + Jx[3 + a] * s1;
+    }
+#pragma unroll
+    for (int a = 0; a < 3; a++) c3[a] = warp_sum(c3[a]);
+    const double* Di = W.Dinv + (size_t)l * 6;
+    const double b0 = W.bl[(size_t)l * 3], b1 = W.bl[(size_t)l * 3 + 1], b2 = W.bl[(size_t)l * 3 + 2];
+    const double r0 = b0 - c3[0], r1 = b1 - c3[1], r2 = b2 - c3[2];
+    const double x0 = Di[0] * r0 + Di[1] * r1 + Di[2] * r2;
+    const double x1 = Di[1] * r0 + Di[3] * r1 + Di[4] * r2;
+    const double x2 = Di[2] * r0 + Di[4] * r1 + Di[5] * r2;
+    const double Xn[3] = {X[0] + x0, X[1] + x1, X[2] + x2};
+    if (lane == 0) {
+      W.pts[tr][l * 3] = Xn[0]; W.pts[tr][l * 3 + 1] = Xn[1]; W.pts[tr][l * 3 + 2] = Xn[2];
+      scale_acc += x0 * (lambda * x0 + b0) + x1 * (lambda * x1 + b1) + x2 * (lambda * x2 + b2);
+    }
+    for (int i = lane; i < k; i += 32) {
+      const int o = ps + i;
+      if (W.level[o]) continue;
+      const double* Rt = camRtT + (size_t)W.ocam[o] * 12;
+      double pc[3], e0, e1, w;
+      map_point(Rt, Xn, pc);
+      const double2 uv = *reinterpret_cast<const double2*>(W.uv + (size_t)o * 2);
+      const double e2 = edge_error(pc, uv.x, uv.y, K, e0, e1);
+      chi_acc += huber_rho(e2, delta, robust, w);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------- LM driver
+
+constexpr int kPartWidth = kBAPartWidth;
+
+struct LMResult { int iters, trials, pcg_iters; double chi, lambda; };
+
+template <class Scope>
+__device__ void zero_system(const Scope& sc, const BAWin& W, bool diag_only, double lambda) {
+  const int gt = sc.blk() * blockDim.x + threadIdx.x, gstride = sc.nblk() * blockDim.x;
+  if (diag_only) {
+    for (int i = gt; i < W.Ncf * 6; i += gstride) W.hdiag[i] = 0.0;
+    return;
+  }
+  for (int i = gt; i < W.nblk * 36; i += gstride) W.S[i] = 0.0;
+  // BlockSolver::setLambda: + lambda on the diagonal of every pose block (col[row_ptr[i]] == i);
+  // disjoint from the zeroing above only after a barrier, so do it in the same thread ordering
+  for (int i = gt; i < W.Ncf * 6; i += gstride) { W.bs[i] = 0.0; W.bp[i] = 0.0; }
+  (void)lambda;
+}
+
+// S_ii += lambda I. Must run after zero_system is visible (the caller syncs in between).
+template <class Scope>
+__device__ void damp_diagonal(const Scope& sc, const BAWin& W, double lambda) {
+  const int gt = sc.blk() * blockDim.x + threadIdx.x, gstride = sc.nblk() * blockDim.x;
+  for (int i = gt; i < W.Ncf * 6; i += gstride) {
+    const int c = i / 6, a = i - c * 6;
+    atomicAdd(&W.S[(size_t)W.row_ptr[c] * 36 + a * 7], lambda);
+  }
+}
+
+// SparseOptimizer::optimize(n_iter) with OptimizationAlgorithmLevenberg.
+// `cur` is the buffer holding the current estimate (updated on accept); `have_trial` tells the
+// caller whether buffer cur^1 / `last_eval` holds the state of the last computeActiveErrors().
+template <class Scope>
+__device__ LMResult lm_optimize(const Scope& sc, const BAWin& W, const BARun& run, int n_iter,
+                                bool robust, int& cur, int& last_eval, WarpStage st, int& parity,
+                                double* red, double* chi_initial) {
+  LMResult res = {0, 0, 0, 0.0, 0.0};
+  double lambda = 0.0, ni = 2.0;
+  double currentChi = 0.0;
+  double dummy[1];
+  const int use_single_cta_pcg = (W.Ncf * 6 <= 4 * (int)blockDim.x);
+  double* flags = W.part + (size_t)2 * sc.nblk() * kPartWidth;  // behind the two reduction buffers
+  for (int it = 0; it < n_iter; it++) {
+    if (it == 0) {
+      // computeLambdaInit: tau * max diagonal entry of the (undamped) Hessian
+      zero_system(sc, W, true, 0.0);
+      sc.sync();
+      double chi = 0.0, mx = 0.0;
+      lin_phase<true>(sc, W, cur, 0.0, robust, run.delta, st, chi, mx);
+      double s1[1] = {chi}, m1[1] = {mx};
+      scope_reduce<1, 1>(sc, s1, m1, W.part, parity, red);
+      double mp = 0.0;
+      for (int i = threadIdx.x; i < W.Ncf * 6; i += blockDim.x) mp = fmax(mp, fabs(__ldcg(W.hdiag + i)));
+      double z1[1] = {0.0}, m2[1] = {mp};
+      {  // CTA-local max (every CTA sees the same hdiag)
+        CtaScope cs;
+        int par2 = 0;
+        scope_reduce<1, 1>(cs, z1, m2, nullptr, par2, red);
+      }
+      lambda = 1e-5 * fmax(m1[0], m2[0]);
+      ni = 2.0;
+      if (chi_initial) *chi_initial = s1[0];
+    }
+    double rho = 0.0;
+    int qmax = 0;
+    bool lambda_bad = false;
+    do {
+      zero_system(sc, W, false, lambda);
+      sc.sync();
+      damp_diagonal(sc, W, lambda);
+      double chi = 0.0, mx = 0.0;
+      lin_phase<false>(sc, W, cur, lambda, robust, run.delta, st, chi, mx);
+      double s1[1] = {chi};
+      scope_reduce<1, 0>(sc, s1, dummy, W.part, parity, red);  // also publishes S, bs, bp
+      currentChi = s1[0];
+      int pcg_it = 0;
+      bool ok2;
+      if (use_single_cta_pcg) {
+        // small reduced system: one CTA iterates with __syncthreads only, the others wait
+        if (sc.blk() == 0) {
+          CtaScope cs;
+          int par2 = 0;
+          ok2 = pcg_phase(cs, W, run.pcg_tol, run.pcg_max_iter, nullptr, par2, red, pcg_it);
+          if (threadIdx.x == 0) { __stcg(flags, ok2 ? 1.0 : 0.0); __stcg(flags + 1, (double)pcg_it); }
+        }
+        sc.sync();
+        ok2 = __ldcg(flags) > 0.5;
+        pcg_it = (int)__ldcg(flags + 1);
+      } else {
+        ok2 = pcg_phase(sc, W, run.pcg_tol, run.pcg_max_iter, W.part, parity, red, pcg_it);
+        sc.sync();
+      }
+      res.pcg_iters += pcg_it;
+      double tempChi = 1.7976931348623157e308;
+      double scale = 0.0;
+      if (ok2) {
+        cam_update(sc, W, cur);
+        sc.sync();
+        double tchi = 0.0, sc_l = 0.0;
+        backsub_phase(sc, W, cur, lambda, robust, run.delta, tchi, sc_l);
+        {  // pose part of computeScale: sum x (lambda x + b)
+          const int gt = sc.blk() * blockDim.x + threadIdx.x, gstride = sc.nblk() * blockDim.x;
+          for (int i = gt; i < W.Ncf * 6; i += gstride) {
+            const double x = __ldcg(W.xp + i);
+            sc_l += x * (lambda * x + __ldcg(W.bp + i));
+          }
+        }
+        double s2[2] = {tchi, sc_l};
+        scope_reduce<2, 0>(sc, s2, dummy, W.part, parity, red);
+        tempChi = s2[0];
+        scale = s2[1];
+        last_eval = cur ^ 1;
+      }
+      rho = (currentChi - tempChi) / (scale + 1e-3);
+      if (rho > 0 && isfinite(tempChi)) {
+        double alpha = 1. - pow((2 * rho - 1), 3);
+        alpha = fmin(alpha, 2. / 3.);
+        lambda *= fmax(1. / 3., alpha);
+        ni = 2;
+        currentChi = tempChi;
+        cur ^= 1;  // discardTop(): the trial state becomes the estimate
+      } else {
+        lambda *= ni;
+        ni *= 2;  // pop(): keep `cur`
+        if (!isfinite(lambda)) { lambda_bad = true; qmax++; break; }
+      }
+      qmax++;
+    } while (rho < 0 && qmax < 10);
+    res.trials += qmax;
+    res.iters = it + 1;
+    if (qmax == 10 || rho == 0 || lambda_bad || !isfinite(lambda)) break;
+  }
+  res.chi = currentChi;
+  res.lambda = lambda;
+  return res;
+}
+
+// ------------------------------------------------------------------------------- whole window
+
+template <class Scope>
+__device__ void solve_window(const Scope& sc, const BAWin& W, const BARun& run, WarpStage st,
+                             double* red) {
+  const int gt = sc.blk() * blockDim.x + threadIdx.x, gstride = sc.nblk() * blockDim.x;
+  // setEstimate(SE3Quat(q, p).inverse()) (src/g2o_optimization.cc:45), points, levels
+  for (int c = gt; c < W.Nc; c += gstride) {
+    double q[4], t[3], qi[4], ti[3];
+    const double* in = W.pose_in + (size_t)c * 7;
+    q[0] = in[0]; q[1] = in[1]; q[2] = in[2]; q[3] = in[3];
+    t[0] = in[4]; t[1] = in[5]; t[2] = in[6];
+    quat_normalize_w(q);
+    se3_inverse(q, t, qi, ti);
+    double* o = W.cam[0] + (size_t)c * 7;
+    o[0] = qi[0]; o[1] = qi[1]; o[2] = qi[2]; o[3] = qi[3];
+    o[4] = ti[0]; o[5] = ti[1]; o[6] = ti[2];
+  }
+  for (int i = gt; i < W.Np * 3; i += gstride) W.pts[0][i] = W.pts_in[i];
+  for (int o = gt; o < W.No; o += gstride) W.level[o] = 0;
+  sc.sync();
+  refresh_camRt(sc, W, 0);
+  sc.sync();
+
+  int cur = 0, last_eval = 0, parity = 0;
+  urmvo_ba_stats* stats = reinterpret_cast<urmvo_ba_stats*>(W.stats);
+  const bool writer = (sc.blk() == 0 && threadIdx.x == 0);
+  for (int pass = 0; pass < 2; pass++) {
+    const bool robust = (pass == 0);
+    double chi_init = 0.0;
+    LMResult r = lm_optimize(sc, W, run, pass == 0 ? run.it0 : run.it1, robust, cur, last_eval, st,
+                             parity, red, &chi_init);
+    if (writer && stats) {
+      stats->iters[pass] = r.iters;
+      stats->trials[pass] = r.trials;
+      stats->pcg_iters[pass] = r.pcg_iters;
+      stats->chi2_final[pass] = r.chi;
+      stats->lambda_final[pass] = r.lambda;
+      if (pass == 0) stats->chi2_initial = chi_init;
+    }
+    // src/g2o_optimization.cc:129-135 / :150-154.  e->chi2() reads the error cached by the last
+    // computeActiveErrors() (state `last_eval`, which is the rejected trial when the final trial
+    // was rejected); isDepthPositive() re-maps with the CURRENT estimate.  Level-1 edges keep the
+    // classification error of the first pass.
+    const double K[4] = {W.intr[0], W.intr[1], W.intr[2], W.intr[3]};
+    double n_l1 = 0.0;
+    for (int l = gt; l < W.Np; l += gstride) {
+      for (int o = W.pt_start[l]; o < W.pt_start[l + 1]; o++) {
+        const int c = W.ocam[o];
+        double pc[3], e0, e1;
+        const double2 uv = *reinterpret_cast<const double2*>(W.uv + (size_t)o * 2);
+        const int lev = W.level[o];
+        if (pass == 1 && lev == 1) continue;  // cached chi2 > thr: inlier[] already 0 from pass 0
+        map_point(W.camRt[last_eval] + (size_t)c * 12, W.pts[last_eval] + (size_t)l * 3, pc);
+        const double e2 = edge_error(pc, uv.x, uv.y, K, e0, e1);
+        map_point(W.camRt[cur] + (size_t)c * 12, W.pts[cur] + (size_t)l * 3, pc);
+        const bool depth_pos = pc[2] > 0.0;
+        if (pass == 0) {
+          // level 1: chi2 test failed; level 2: only the depth test failed (its cached chi2 stays
+          // <= thr, so the final flag depends on the depth at the final estimate)
+          const int nl = (e2 > run.chi2_thr) ? 1 : (!depth_pos ? 2 : 0);
+          W.level[o] = (uint8_t)nl;
+          W.inlier[o] = 0;
+          n_l1 += nl ? 1.0 : 0.0;
+        } else if (lev == 2) {
+          W.inlier[o] = depth_pos ? 1 : 0;
+        } else {
+          W.inlier[o] = (e2 <= run.chi2_thr && depth_pos) ? 1 : 0;
+        }
+      }
+    }
+    if (pass == 0) {
+      double s1[1] = {n_l1}, dummy[1];
+      scope_reduce<1, 0>(sc, s1, dummy, W.part, parity, red);
+      if (writer && stats) stats->n_level1 = (int)s1[0];
+    }
+    sc.sync();
+  }
+  // write back T_wc = estimate().inverse() and the points (:164-176)
+  for (int c = gt; c < W.Nc; c += gstride) {
+    const double* in = W.cam[cur] + (size_t)c * 7;
+    double qi[4], ti[3];
+    se3_inverse(in, in + 4, qi, ti);
+    double* o = W.pose_out + (size_t)c * 7;
+    o[0] = qi[0]; o[1] = qi[1]; o[2] = qi[2]; o[3] = qi[3];
+    o[4] = ti[0]; o[5] = ti[1]; o[6] = ti[2];
+  }
+  for (int i = gt; i < W.Np * 3; i += gstride) W.pts_out[i] = W.pts[cur][i];
+}
+
+__device__ __forceinline__ WarpStage make_stage(unsigned char* smem, int kmax, double** red_out) {
+  const int nw = blockDim.x >> 5, wid = threadIdx.x >> 5;
+  // layout: [red: 16*32+16 doubles] [per warp: 27*kmax doubles] [per warp: kmax ints]
+  double* red = reinterpret_cast<double*>(smem);
+  double* f0 = red + (16 * 32 + 16);
+  int* c0 = reinterpret_cast<int*>(f0 + (size_t)nw * kStageFields * kmax);
+  WarpStage st;
+  st.kmax = kmax;
+  st.f = f0 + (size_t)wid * kStageFields * kmax;
+  st.cf = c0 + (size_t)wid * kmax;
+  *red_out = red;
+  return st;
+}
+
+// Batched windows: one thread-block cluster per window (cluster dims set at launch).
+__global__ void __launch_bounds__(256, 1)
+ba_window_cluster_kernel(const BAWin* __restrict__ wins, BARun run, int kmax_all) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  ClusterScope sc;
+  double* red;
+  WarpStage st = make_stage(smem, kmax_all, &red);
+  const int n_clusters = gridDim.x / sc.nblk();
+  const int cid = blockIdx.x / sc.nblk();
+  for (int w = cid; w < run.n_win; w += n_clusters) {
+    solve_window(sc, wins[w], run, st, red);
+    sc.sync();
+  }
+}
+
+// One large problem on the whole (cooperative) grid.
+__global__ void __launch_bounds__(256, 1)
+ba_window_grid_kernel(const BAWin* __restrict__ wins, BARun run, int kmax_all) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  GridScope sc;
+  double* red;
+  WarpStage st = make_stage(smem, kmax_all, &red);
+  for (int w = 0; w < run.n_win; w++) {
+    solve_window(sc, wins[w], run, st, red);
+    sc.sync();
+  }
+}
+
+size_t ba_smem_bytes(int threads, int kmax) {
+  const int nw = threads / 32;
+  return (16 * 32 + 16) * sizeof(double) + (size_t)nw * warp_stage_bytes(kmax);
+}
+
+cudaError_t launch_ba_cluster(const BAWin* wins_dev, const BARun& run, int kmax, int n_clusters,
+                              int cluster_size, int threads, cudaStream_t stream) {
+  const size_t smem = ba_smem_bytes(threads, kmax);
+  cudaError_t e = cudaFuncSetAttribute(ba_window_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  if (cluster_size > 8) {
+    e = cudaFuncSetAttribute(ba_window_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return e;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(n_clusters * cluster_size));
+  cfg.blockDim = dim3((unsigned)threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cluster_size;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, ba_window_cluster_kernel, wins_dev, run, kmax);
+}
+
+int ba_grid_capacity(int threads, int kmax) {
+  const size_t smem = ba_smem_bytes(threads, kmax);
+  if (cudaFuncSetAttribute(ba_window_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+  int per_sm = 0, dev = 0, sms = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ba_window_grid_kernel, threads, smem) != cudaSuccess) return 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return per_sm * sms;
+}
+
+cudaError_t launch_ba_grid(const BAWin* wins_dev, const BARun& run, int kmax, int grid_blocks,
+                           int threads, cudaStream_t stream) {
+  const size_t smem = ba_smem_bytes(threads, kmax);
+  cudaError_t e = cudaFuncSetAttribute(ba_window_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  BARun r = run;
+  int km = kmax;
+  void* args[] = {(void*)&wins_dev, (void*)&r, (void*)&km};
+  return cudaLaunchCooperativeKernel((const void*)ba_window_grid_kernel, dim3((unsigned)grid_blocks),
+                                     dim3((unsigned)threads), args, smem, stream);
+}
+
+}  // namespace urmvo

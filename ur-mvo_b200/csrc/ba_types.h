@@ -1,0 +1,68 @@
+// csrc/ba_types.h — device-side problem descriptors shared by the kernels and the C-ABI layer.
+#pragma once
+#include <stdint.h>
+
+namespace urmvo {
+
+// One BA window (one LocalmapOptimization call), all pointers are device pointers.
+// HBM layout: SoA, fp64; observations sorted point-major so that one point's
+// observations are contiguous; cameras as 7-double (q,t) T_cw state + a derived 12-double (R|t).
+struct BAWin {
+  int Nc, Ncf, Np, No;
+  int nblk;         // stored 6x6 blocks of the reduced camera system (upper triangle, BSR)
+  int kmax;         // max observations of one point (sizes the per-warp staging area)
+  double intr[4];   // fx fy cx cy
+  // ---- inputs (immutable during a run)
+  const double* pose_in;   // Nc*7   T_wc initial estimate
+  const double* pts_in;    // Np*3
+  const double* uv;        // No*2
+  const int* ocam;         // No     camera index
+  const int* pt_start;     // Np+1   CSR over observations
+  const int* cam_free;     // Nc     dense index among free cameras or -1
+  const int* row_ptr;      // Ncf+1  upper BSR of S: block row i -> [row_ptr[i], row_ptr[i+1])
+  const int* col;          // nblk   block column (>= row), ascending inside a row, col[row_ptr[i]] == i
+  const int* lrow_ptr;     // Ncf+1  mirror lists: block row i -> blocks (k,i) with k < i
+  const int* lcol;         // k
+  const int* lblk;         // index of block (k,i) in S
+  // ---- state
+  double* cam[2];          // Nc*7   T_cw (q,t): current / trial (roles swap on accept)
+  double* camRt[2];        // Nc*12  R (row-major 9) | t (3) derived from cam[]
+  double* pts[2];          // Np*3
+  uint8_t* level;          // No     0 active, 1 excluded (g2o edge level)
+  // ---- linear system
+  double* S;               // nblk*36 row-major blocks
+  double* bs;              // Ncf*6  Schur right-hand side
+  double* bp;              // Ncf*6  raw pose gradient b_p (for computeScale)
+  double* hdiag;           // Ncf*6  raw diag(Hpp) (for computeLambdaInit)
+  double* Minv;            // Ncf*36 block-Jacobi preconditioner
+  double* xp;              // Ncf*6
+  double* r;               // Ncf*6
+  double* z;               // Ncf*6
+  double* p;               // Ncf*6
+  double* Ap;              // Ncf*6
+  double* Dinv;            // Np*6   (Hll + lambda I)^-1, symmetric packed 00 01 02 11 12 22
+  double* bl;              // Np*3
+  double* part;            // scope reduction scratch: 2 * nblk_scope * 8
+  // ---- outputs
+  double* pose_out;        // Nc*7 T_wc
+  double* pts_out;         // Np*3
+  uint8_t* inlier;         // No
+  void* stats;             // urmvo_ba_stats*
+};
+
+struct BARun {
+  double chi2_thr;
+  double delta;        // (double)(float)sqrt(chi2_thr)
+  double pcg_tol;
+  int pcg_max_iter;
+  int it0, it1;
+  int n_win;
+};
+
+// One pose-only frame.
+struct PoseFrame {
+  int No;
+  int obs0;            // first observation in the concatenated arrays
+};
+
+}  // namespace urmvo

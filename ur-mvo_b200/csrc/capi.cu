@@ -1,0 +1,808 @@
+// csrc/capi.cu — the C ABI declared in include/urmvo_b200.h: contexts, device-resident plans,
+// host-buffer entry points.  Host code here only flattens / validates inputs, builds the sparsity
+// structure of the reduced camera system, moves bytes and takes the final scalar accept/reject
+// decisions of EpipolarGeometry::reconstruct; all arithmetic of the path runs in the kernels.
+// There is no CPU fallback: every entry point needs a live sm_100 device.
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/urmvo_b200.h"
+#include "ba_types.h"
+#include "kernels.h"
+
+using namespace urmvo;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CU_TRY(expr)                                                                        \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess)                                                                  \
+      return fail(URMVO_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));      \
+  } while (0)
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// Bump allocator over one device allocation (and a mirrored pinned host staging area).
+struct Arena {
+  size_t size = 0;
+  size_t off = 0;
+  template <class T>
+  size_t take(size_t n) {
+    size_t o = off;
+    off = align_up(off + n * sizeof(T));
+    return o;
+  }
+};
+
+}  // namespace
+
+struct urmvo_ctx {
+  int device = 0;
+  int n_sm = 0;
+  cudaStream_t stream = nullptr;
+  int64_t launches = 0;
+  // reusable pinned staging buffer for the one-shot entry points
+  void* pinned = nullptr;
+  size_t pinned_size = 0;
+  int ensure_pinned(size_t n) {
+    if (n <= pinned_size) return 0;
+    if (pinned) cudaFreeHost(pinned);
+    pinned = nullptr;
+    pinned_size = 0;
+    size_t want = std::max(n, (size_t)1 << 20);
+    if (cudaMallocHost(&pinned, want) != cudaSuccess) return -1;
+    pinned_size = want;
+    return 0;
+  }
+};
+
+extern "C" int urmvo_version(void) { return 100; }
+extern "C" const char* urmvo_last_error(void) { return g_err.c_str(); }
+
+extern "C" int urmvo_create(urmvo_ctx** out, int device) {
+  if (!out) return fail(URMVO_ERR_ARG, "urmvo_create: null out pointer");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(URMVO_ERR_NO_DEVICE, std::string("urmvo_create: no CUDA device (") +
+                                         (e != cudaSuccess ? cudaGetErrorString(e) : "count 0") +
+                                         "); this library has no CPU fallback");
+  if (device < 0 || device >= n) return fail(URMVO_ERR_ARG, "urmvo_create: device index out of range");
+  cudaDeviceProp prop;
+  CU_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(URMVO_ERR_NO_DEVICE, "urmvo_create: device is sm_" + std::to_string(prop.major) +
+                                         std::to_string(prop.minor) + ", kernels are built for sm_100a only");
+  CU_TRY(cudaSetDevice(device));
+  urmvo_ctx* c = new urmvo_ctx();
+  c->device = device;
+  c->n_sm = prop.multiProcessorCount;
+  e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    delete c;
+    return fail(URMVO_ERR_CUDA, std::string("cudaStreamCreateWithFlags: ") + cudaGetErrorString(e));
+  }
+  *out = c;
+  return URMVO_OK;
+}
+
+extern "C" void urmvo_destroy(urmvo_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+  if (c->pinned) cudaFreeHost(c->pinned);
+  delete c;
+}
+
+extern "C" void* urmvo_stream(urmvo_ctx* c) { return c ? (void*)c->stream : nullptr; }
+extern "C" int urmvo_sync(urmvo_ctx* c) {
+  if (!c) return fail(URMVO_ERR_ARG, "urmvo_sync: null context");
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  return URMVO_OK;
+}
+extern "C" int64_t urmvo_launch_count(urmvo_ctx* c) { return c ? c->launches : 0; }
+
+// =====================================================================================  BA
+
+struct urmvo_ba_plan {
+  urmvo_ctx* ctx = nullptr;
+  int B = 0;
+  int total_c = 0, total_p = 0, total_o = 0;
+  int kmax = 1;
+  int cluster_size = 1, threads = 256, n_clusters = 0;
+  bool use_grid = false;
+  int grid_blocks = 0;
+  BARun run{};
+  unsigned char* dev = nullptr;  // one allocation
+  size_t dev_bytes = 0;
+  // offsets of the pieces the host reads back
+  size_t off_wins = 0, off_pose_out = 0, off_pts_out = 0, off_inlier = 0, off_stats = 0;
+  // observation permutation (point-major sort) when the caller's order was not sorted
+  std::vector<int> perm;  // sorted position -> caller index (empty = identity)
+};
+
+namespace {
+
+struct WinHost {
+  int Nc, Ncf, Np, No, nblk, kmax;
+  std::vector<int> pt_start, cam_free, row_ptr, col, lrow_ptr, lcol, lblk;
+};
+
+// Builds CSR over points, free-camera indices and the upper-BSR structure of S for one window.
+// obs_pt / obs_cam are window-local; `order` (size No) receives the point-major permutation
+// (sorted position -> original index), `sorted` tells whether it is the identity.
+int build_window(int Nc, const uint8_t* fixed, int Np, int No, const int32_t* obs_cam,
+                 const int32_t* obs_pt, WinHost& w, std::vector<int>& order, bool& sorted) {
+  w.Nc = Nc; w.Np = Np; w.No = No;
+  w.cam_free.assign(Nc, -1);
+  w.Ncf = 0;
+  for (int c = 0; c < Nc; c++)
+    if (!fixed[c]) w.cam_free[c] = w.Ncf++;
+  w.pt_start.assign(Np + 1, 0);
+  sorted = true;
+  for (int o = 0; o < No; o++) {
+    const int p = obs_pt[o], c = obs_cam[o];
+    if (p < 0 || p >= Np || c < 0 || c >= Nc) return fail(URMVO_ERR_ARG, "local_ba: observation index out of range");
+    if (o > 0 && obs_pt[o - 1] > p) sorted = false;
+    w.pt_start[p + 1]++;
+  }
+  w.kmax = 1;
+  for (int l = 0; l < Np; l++) {
+    w.kmax = std::max(w.kmax, w.pt_start[l + 1]);
+    w.pt_start[l + 1] += w.pt_start[l];
+  }
+  order.resize(No);
+  if (sorted) {
+    for (int o = 0; o < No; o++) order[o] = o;
+  } else {
+    std::vector<int> fill(w.pt_start.begin(), w.pt_start.end() - 1);
+    for (int o = 0; o < No; o++) order[fill[obs_pt[o]]++] = o;  // stable
+  }
+  // structure of S: block (a,b), a <= b, present iff some point is seen by free cameras a and b
+  const int n = w.Ncf;
+  std::vector<std::vector<int>> rows(n);
+  for (int i = 0; i < n; i++) rows[i].push_back(i);
+  if (n <= 64) {
+    for (int i = 0; i < n; i++) {  // dense upper triangle: no scan of the observations needed
+      rows[i].resize(n - i);
+      for (int j = i; j < n; j++) rows[i][j - i] = j;
+    }
+  } else {
+    std::vector<int> cfs;
+    for (int l = 0; l < Np; l++) {
+      cfs.clear();
+      for (int s = w.pt_start[l]; s < w.pt_start[l + 1]; s++) {
+        const int cf = w.cam_free[obs_cam[order[s]]];
+        if (cf >= 0) cfs.push_back(cf);
+      }
+      std::sort(cfs.begin(), cfs.end());
+      cfs.erase(std::unique(cfs.begin(), cfs.end()), cfs.end());
+      for (size_t a = 0; a < cfs.size(); a++) {
+        std::vector<int>& r = rows[cfs[a]];
+        for (size_t b = a + 1; b < cfs.size(); b++) {
+          auto it = std::lower_bound(r.begin(), r.end(), cfs[b]);
+          if (it == r.end() || *it != cfs[b]) r.insert(it, cfs[b]);
+        }
+      }
+    }
+  }
+  w.row_ptr.assign(n + 1, 0);
+  for (int i = 0; i < n; i++) w.row_ptr[i + 1] = w.row_ptr[i] + (int)rows[i].size();
+  w.nblk = w.row_ptr[n];
+  w.col.resize(w.nblk);
+  std::vector<int> lcount(n + 1, 0);
+  for (int i = 0; i < n; i++)
+    for (size_t k = 0; k < rows[i].size(); k++) {
+      w.col[w.row_ptr[i] + k] = rows[i][k];
+      if (rows[i][k] > i) lcount[rows[i][k] + 1]++;
+    }
+  w.lrow_ptr.assign(n + 1, 0);
+  for (int i = 0; i < n; i++) w.lrow_ptr[i + 1] = w.lrow_ptr[i] + lcount[i + 1];
+  w.lcol.resize(w.lrow_ptr[n]);
+  w.lblk.resize(w.lrow_ptr[n]);
+  std::vector<int> lfill(w.lrow_ptr.begin(), w.lrow_ptr.end() - 1);
+  for (int i = 0; i < n; i++)
+    for (int e = w.row_ptr[i]; e < w.row_ptr[i + 1]; e++) {
+      const int j = w.col[e];
+      if (j > i) { w.lcol[lfill[j]] = i; w.lblk[lfill[j]] = e; lfill[j]++; }
+    }
+  return URMVO_OK;
+}
+
+}  // namespace
+
+extern "C" void urmvo_ba_plan_destroy(urmvo_ba_plan* p) {
+  if (!p) return;
+  if (p->dev) { cudaSetDevice(p->ctx->device); cudaFree(p->dev); }
+  delete p;
+}
+
+extern "C" int urmvo_ba_plan_create(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, const int32_t* cam_off,
+                                    const int32_t* pt_off, const int32_t* obs_off, const double* poses,
+                                    const uint8_t* fixed, const double* pts, const double* uv,
+                                    const int32_t* cam, const int32_t* pt, const double* intr,
+                                    double chi2_thr, int it0, int it1, const urmvo_ba_options* opts) {
+  if (!ctx || !out) return fail(URMVO_ERR_ARG, "ba_plan_create: null context / out");
+  *out = nullptr;
+  if (B <= 0 || !cam_off || !pt_off || !obs_off || !poses || !fixed || !pts || !uv || !cam || !pt || !intr)
+    return fail(URMVO_ERR_ARG, "ba_plan_create: null or empty input");
+  if (it0 < 0 || it1 < 0 || !(chi2_thr > 0)) return fail(URMVO_ERR_ARG, "ba_plan_create: bad iteration counts / threshold");
+  CU_TRY(cudaSetDevice(ctx->device));
+  std::vector<WinHost> wh(B);
+  urmvo_ba_plan* p = new urmvo_ba_plan();
+  p->ctx = ctx;
+  p->B = B;
+  p->total_c = cam_off[B]; p->total_p = pt_off[B]; p->total_o = obs_off[B];
+  bool all_sorted = true;
+  std::vector<int> perm(p->total_o);
+  std::vector<int> order;
+  int max_ncf = 0;
+  long long sum_blk = 0, sum_ncf = 0;
+  for (int w = 0; w < B; w++) {
+    const int Nc = cam_off[w + 1] - cam_off[w], Np = pt_off[w + 1] - pt_off[w], No = obs_off[w + 1] - obs_off[w];
+    if (Nc <= 0 || Np < 0 || No < 0) { delete p; return fail(URMVO_ERR_ARG, "ba_plan_create: bad window offsets"); }
+    bool sorted = true;
+    int rc = build_window(Nc, fixed + cam_off[w], Np, No, cam + obs_off[w], pt + obs_off[w], wh[w], order, sorted);
+    if (rc != URMVO_OK) { delete p; return rc; }
+    all_sorted = all_sorted && sorted;
+    for (int o = 0; o < No; o++) perm[obs_off[w] + o] = obs_off[w] + order[o];
+    p->kmax = std::max(p->kmax, wh[w].kmax);
+    max_ncf = std::max(max_ncf, wh[w].Ncf);
+    sum_blk += wh[w].nblk;
+    sum_ncf += wh[w].Ncf;
+  }
+  if (!all_sorted) p->perm = perm;
+  // ---- launch shape
+  p->threads = (opts && opts->threads > 0) ? opts->threads : 256;
+  if (p->threads % 32 != 0 || p->threads < 64 || p->threads > 256) { delete p; return fail(URMVO_ERR_ARG, "ba options: threads must be 64..256 and a multiple of 32"); }
+  while (p->threads > 64 && ba_smem_bytes(p->threads, p->kmax) > 200 * 1024) p->threads -= 32;
+  if (ba_smem_bytes(p->threads, p->kmax) > 220 * 1024) { delete p; return fail(URMVO_ERR_UNSUPPORTED, "local_ba: a point has too many observations for the per-warp staging area"); }
+  const int max_np = [&] { int m = 0; for (auto& w : wh) m = std::max(m, w.Np); return m; }();
+  const long long max_no = [&] { long long m = 0; for (auto& w : wh) m = std::max<long long>(m, w.No); return m; }();
+  p->use_grid = (B == 1 && max_no >= 100000);
+  int cs = (opts && opts->cluster_size > 0) ? opts->cluster_size : 0;
+  if (cs == 0) {
+    const int warps = p->threads / 32;
+    cs = 1;
+    while (cs < 8 && max_np > cs * warps * 16) cs *= 2;
+  }
+  if (cs != 1 && cs != 2 && cs != 4 && cs != 8 && cs != 16) { delete p; return fail(URMVO_ERR_ARG, "ba options: cluster_size must be 1,2,4,8 or 16"); }
+  p->cluster_size = cs;
+  p->n_clusters = B;
+  int nblk_scope = cs;
+  if (p->use_grid) {
+    p->grid_blocks = ba_grid_capacity(p->threads, p->kmax);
+    if (p->grid_blocks <= 0) { delete p; return fail(URMVO_ERR_CUDA, "ba_plan_create: occupancy query failed"); }
+    nblk_scope = p->grid_blocks;
+  }
+  p->run.chi2_thr = chi2_thr;
+  p->run.delta = (double)(float)std::sqrt(chi2_thr);  // const float thHuberMonoPoint = sqrt(cfg.mono_point)
+  p->run.pcg_tol = (opts && opts->pcg_tol > 0) ? opts->pcg_tol : 1e-10;
+  p->run.pcg_max_iter = (opts && opts->pcg_max_iter > 0) ? opts->pcg_max_iter : std::min(1000, std::max(60, 12 * max_ncf));
+  p->run.it0 = it0; p->run.it1 = it1; p->run.n_win = B;
+
+  // ---- device layout
+  Arena A;
+  const size_t TC = p->total_c, TP = p->total_p, TO = p->total_o;
+  const size_t o_pose_in = A.take<double>(TC * 7), o_pts_in = A.take<double>(TP * 3), o_uv = A.take<double>(TO * 2);
+  const size_t o_ocam = A.take<int>(TO), o_pt_start = A.take<int>(TP + B), o_cam_free = A.take<int>(TC);
+  const size_t o_row_ptr = A.take<int>(sum_ncf + B), o_col = A.take<int>(sum_blk);
+  const size_t o_lrow_ptr = A.take<int>(sum_ncf + B), o_lcol = A.take<int>(sum_blk), o_lblk = A.take<int>(sum_blk);
+  p->off_wins = A.take<BAWin>(B);
+  const size_t upload_end = A.off;  // everything above is filled from the host
+  size_t o_cam[2], o_camRt[2], o_pts[2];
+  for (int k = 0; k < 2; k++) { o_cam[k] = A.take<double>(TC * 7); o_camRt[k] = A.take<double>(TC * 12); o_pts[k] = A.take<double>(TP * 3); }
+  const size_t o_level = A.take<uint8_t>(TO);
+  const size_t o_S = A.take<double>((size_t)sum_blk * 36);
+  const size_t o_vec = A.take<double>((size_t)sum_ncf * 6 * 8);  // bs bp hdiag xp r z p Ap
+  const size_t o_Minv = A.take<double>((size_t)sum_ncf * 36);
+  const size_t o_Dinv = A.take<double>(TP * 6), o_bl = A.take<double>(TP * 3);
+  const size_t part_per_win = (size_t)2 * nblk_scope * kBAPartWidth + 8;
+  const size_t o_part = A.take<double>(part_per_win * B);
+  p->off_pose_out = A.take<double>(TC * 7);
+  p->off_pts_out = A.take<double>(TP * 3);
+  p->off_inlier = A.take<uint8_t>(TO);
+  p->off_stats = A.take<urmvo_ba_stats>(B);
+  p->dev_bytes = A.off;
+  cudaError_t ce = cudaMalloc(&p->dev, p->dev_bytes);
+  if (ce != cudaSuccess) { delete p; return fail(URMVO_ERR_CUDA, std::string("cudaMalloc BA plan: ") + cudaGetErrorString(ce)); }
+  unsigned char* D = p->dev;
+
+  // ---- host staging of the small index arrays + descriptors (pinned), big arrays copied directly
+  const size_t idx_bytes = upload_end - o_pt_start;
+  if (ctx->ensure_pinned(idx_bytes + (all_sorted ? 0 : TO * (sizeof(double) * 2 + sizeof(int))))) {
+    urmvo_ba_plan_destroy(p);
+    return fail(URMVO_ERR_CUDA, "cudaMallocHost failed");
+  }
+  unsigned char* H = (unsigned char*)ctx->pinned;  // mirrors [o_pt_start, upload_end)
+  auto hp = [&](size_t off) { return H + (off - o_pt_start); };
+  size_t c_pt = 0, c_ncf = 0, c_blk = 0;
+  BAWin* hw = (BAWin*)hp(p->off_wins);
+  for (int w = 0; w < B; w++) {
+    const WinHost& W = wh[w];
+    const size_t c0 = cam_off[w], p0 = pt_off[w], ob0 = obs_off[w];
+    int* h_pt_start = (int*)hp(o_pt_start) + c_pt;
+    std::memcpy(h_pt_start, W.pt_start.data(), (W.Np + 1) * sizeof(int));
+    std::memcpy((int*)hp(o_cam_free) + c0, W.cam_free.data(), W.Nc * sizeof(int));
+    std::memcpy((int*)hp(o_row_ptr) + c_ncf, W.row_ptr.data(), (W.Ncf + 1) * sizeof(int));
+    std::memcpy((int*)hp(o_lrow_ptr) + c_ncf, W.lrow_ptr.data(), (W.Ncf + 1) * sizeof(int));
+    if (W.nblk) std::memcpy((int*)hp(o_col) + c_blk, W.col.data(), W.nblk * sizeof(int));
+    if (!W.lcol.empty()) {
+      std::memcpy((int*)hp(o_lcol) + c_blk, W.lcol.data(), W.lcol.size() * sizeof(int));
+      std::memcpy((int*)hp(o_lblk) + c_blk, W.lblk.data(), W.lblk.size() * sizeof(int));
+    }
+    BAWin& d = hw[w];
+    std::memset(&d, 0, sizeof(d));
+    d.Nc = W.Nc; d.Ncf = W.Ncf; d.Np = W.Np; d.No = W.No; d.nblk = W.nblk; d.kmax = W.kmax;
+    for (int k = 0; k < 4; k++) d.intr[k] = intr[k];
+    d.pose_in = (const double*)(D + o_pose_in) + c0 * 7;
+    d.pts_in = (const double*)(D + o_pts_in) + p0 * 3;
+    d.uv = (const double*)(D + o_uv) + ob0 * 2;
+    d.ocam = (const int*)(D + o_ocam) + ob0;
+    d.pt_start = (const int*)(D + o_pt_start) + c_pt;
+    d.cam_free = (const int*)(D + o_cam_free) + c0;
+    d.row_ptr = (const int*)(D + o_row_ptr) + c_ncf;
+    d.col = (const int*)(D + o_col) + c_blk;
+    d.lrow_ptr = (const int*)(D + o_lrow_ptr) + c_ncf;
+    d.lcol = (const int*)(D + o_lcol) + c_blk;
+    d.lblk = (const int*)(D + o_lblk) + c_blk;
+    for (int k = 0; k < 2; k++) {
+      d.cam[k] = (double*)(D + o_cam[k]) + c0 * 7;
+      d.camRt[k] = (double*)(D + o_camRt[k]) + c0 * 12;
+      d.pts[k] = (double*)(D + o_pts[k]) + p0 * 3;
+    }
+    d.level = D + o_level + ob0;
+    d.S = (double*)(D + o_S) + c_blk * 36;
+    double* vec = (double*)(D + o_vec) + c_ncf * 6 * 8;
+    const size_t n6 = (size_t)W.Ncf * 6;
+    d.bs = vec; d.bp = vec + n6; d.hdiag = vec + 2 * n6; d.xp = vec + 3 * n6;
+    d.r = vec + 4 * n6; d.z = vec + 5 * n6; d.p = vec + 6 * n6; d.Ap = vec + 7 * n6;
+    d.Minv = (double*)(D + o_Minv) + c_ncf * 36;
+    d.Dinv = (double*)(D + o_Dinv) + p0 * 6;
+    d.bl = (double*)(D + o_bl) + p0 * 3;
+    d.part = (double*)(D + o_part) + part_per_win * w;
+    d.pose_out = (double*)(D + p->off_pose_out) + c0 * 7;
+    d.pts_out = (double*)(D + p->off_pts_out) + p0 * 3;
+    d.inlier = D + p->off_inlier + ob0;
+    d.stats = (urmvo_ba_stats*)(D + p->off_stats) + w;
+    c_pt += W.Np + 1;
+    c_ncf += W.Ncf + 1;
+    c_blk += W.nblk;
+  }
+  cudaStream_t s = ctx->stream;
+  auto up = [&](size_t off, const void* src, size_t bytes) {
+    return bytes ? cudaMemcpyAsync(D + off, src, bytes, cudaMemcpyHostToDevice, s) : cudaSuccess;
+  };
+  cudaError_t e1 = up(o_pt_start, H, idx_bytes);
+  cudaError_t e2 = up(o_pose_in, poses, TC * 7 * sizeof(double));
+  cudaError_t e3 = up(o_pts_in, pts, TP * 3 * sizeof(double));
+  cudaError_t e4, e5;
+  if (all_sorted) {
+    e4 = up(o_uv, uv, TO * 2 * sizeof(double));
+    e5 = up(o_ocam, cam, TO * sizeof(int));
+  } else {
+    double* huv = (double*)(H + idx_bytes);
+    int* hcam = (int*)(huv + TO * 2);
+    for (size_t o = 0; o < TO; o++) {
+      huv[o * 2] = uv[(size_t)perm[o] * 2];
+      huv[o * 2 + 1] = uv[(size_t)perm[o] * 2 + 1];
+      hcam[o] = cam[perm[o]];
+    }
+    e4 = up(o_uv, huv, TO * 2 * sizeof(double));
+    e5 = up(o_ocam, hcam, TO * sizeof(int));
+  }
+  cudaError_t e6 = cudaMemsetAsync(D + p->off_stats, 0, sizeof(urmvo_ba_stats) * B, s);
+  // the pinned staging buffer is reused by later calls: wait for the copies that read it
+  cudaError_t e7 = cudaStreamSynchronize(s);
+  for (cudaError_t e : {e1, e2, e3, e4, e5, e6, e7})
+    if (e != cudaSuccess) {
+      urmvo_ba_plan_destroy(p);
+      return fail(URMVO_ERR_CUDA, std::string("ba_plan_create upload: ") + cudaGetErrorString(e));
+    }
+  *out = p;
+  return URMVO_OK;
+}
+
+extern "C" int urmvo_ba_plan_run(urmvo_ba_plan* p) {
+  if (!p) return fail(URMVO_ERR_ARG, "ba_plan_run: null plan");
+  CU_TRY(cudaSetDevice(p->ctx->device));
+  const BAWin* wins = (const BAWin*)(p->dev + p->off_wins);
+  cudaError_t e;
+  if (p->use_grid) e = launch_ba_grid(wins, p->run, p->kmax, p->grid_blocks, p->threads, p->ctx->stream);
+  else e = launch_ba_cluster(wins, p->run, p->kmax, p->n_clusters, p->cluster_size, p->threads, p->ctx->stream);
+  if (e != cudaSuccess) return fail(URMVO_ERR_CUDA, std::string("BA kernel launch: ") + cudaGetErrorString(e));
+  p->ctx->launches++;
+  return URMVO_OK;
+}
+
+extern "C" int urmvo_ba_plan_download(urmvo_ba_plan* p, double* poses, double* pts, uint8_t* inlier,
+                                      urmvo_ba_stats* stats) {
+  if (!p) return fail(URMVO_ERR_ARG, "ba_plan_download: null plan");
+  CU_TRY(cudaSetDevice(p->ctx->device));
+  cudaStream_t s = p->ctx->stream;
+  if (poses) CU_TRY(cudaMemcpyAsync(poses, p->dev + p->off_pose_out, (size_t)p->total_c * 7 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (pts) CU_TRY(cudaMemcpyAsync(pts, p->dev + p->off_pts_out, (size_t)p->total_p * 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  std::vector<uint8_t> tmp;
+  if (inlier) {
+    if (p->perm.empty()) {
+      CU_TRY(cudaMemcpyAsync(inlier, p->dev + p->off_inlier, (size_t)p->total_o, cudaMemcpyDeviceToHost, s));
+    } else {
+      tmp.resize(p->total_o);
+      CU_TRY(cudaMemcpyAsync(tmp.data(), p->dev + p->off_inlier, (size_t)p->total_o, cudaMemcpyDeviceToHost, s));
+    }
+  }
+  if (stats) CU_TRY(cudaMemcpyAsync(stats, p->dev + p->off_stats, sizeof(urmvo_ba_stats) * p->B, cudaMemcpyDeviceToHost, s));
+  CU_TRY(cudaStreamSynchronize(s));
+  if (inlier && !p->perm.empty())
+    for (int o = 0; o < p->total_o; o++) inlier[p->perm[o]] = tmp[o];
+  return URMVO_OK;
+}
+
+extern "C" int urmvo_local_ba_batch(urmvo_ctx* ctx, int B, const int32_t* cam_off, const int32_t* pt_off,
+                                    const int32_t* obs_off, double* poses, const uint8_t* fixed, double* pts,
+                                    const double* uv, const int32_t* cam, const int32_t* pt, const double* intr,
+                                    double chi2_thr, int it0, int it1, uint8_t* inlier, urmvo_ba_stats* stats,
+                                    const urmvo_ba_options* opts) {
+  urmvo_ba_plan* p = nullptr;
+  int rc = urmvo_ba_plan_create(ctx, &p, B, cam_off, pt_off, obs_off, poses, fixed, pts, uv, cam, pt, intr,
+                                chi2_thr, it0, it1, opts);
+  if (rc != URMVO_OK) return rc;
+  rc = urmvo_ba_plan_run(p);
+  if (rc == URMVO_OK) rc = urmvo_ba_plan_download(p, poses, pts, inlier, stats);
+  urmvo_ba_plan_destroy(p);
+  return rc;
+}
+
+extern "C" int urmvo_local_ba(urmvo_ctx* ctx, int Nc, double* poses, const uint8_t* fixed, int Np, double* pts,
+                              int No, const double* uv, const int32_t* cam, const int32_t* pt,
+                              const double* intr, double chi2_thr, int it0, int it1, uint8_t* inlier,
+                              urmvo_ba_stats* stats, const urmvo_ba_options* opts) {
+  const int32_t co[2] = {0, Nc}, po[2] = {0, Np}, oo[2] = {0, No};
+  return urmvo_local_ba_batch(ctx, 1, co, po, oo, poses, fixed, pts, uv, cam, pt, intr, chi2_thr, it0, it1,
+                              inlier, stats, opts);
+}
+
+// =====================================================================================  pose-only
+
+struct urmvo_pose_plan {
+  urmvo_ctx* ctx = nullptr;
+  int B = 0, total_o = 0;
+  double intr[4];
+  double chi2_thr = 0, delta = 0;
+  int rounds = 4, its = 10;
+  unsigned char* dev = nullptr;
+  size_t o_off = 0, o_pose_in = 0, o_uv = 0, o_X = 0, o_inl_in = 0, o_inl = 0, o_level = 0, o_pose_out = 0,
+         o_ninl = 0, o_iters = 0;
+};
+
+extern "C" void urmvo_pose_plan_destroy(urmvo_pose_plan* p) {
+  if (!p) return;
+  if (p->dev) { cudaSetDevice(p->ctx->device); cudaFree(p->dev); }
+  delete p;
+}
+
+extern "C" int urmvo_pose_plan_create(urmvo_ctx* ctx, urmvo_pose_plan** out, int B, const int32_t* obs_off,
+                                      const double* poses, const double* uv, const double* Xw,
+                                      const double* intr, double chi2_thr, int rounds, int its_per_round,
+                                      const uint8_t* inlier) {
+  if (!ctx || !out) return fail(URMVO_ERR_ARG, "pose_plan_create: null context / out");
+  *out = nullptr;
+  if (B <= 0 || !obs_off || !poses || !uv || !Xw || !intr) return fail(URMVO_ERR_ARG, "pose_plan_create: null or empty input");
+  if (rounds < 0 || its_per_round < 0 || !(chi2_thr > 0)) return fail(URMVO_ERR_ARG, "pose_plan_create: bad rounds / threshold");
+  for (int f = 0; f < B; f++)
+    if (obs_off[f + 1] < obs_off[f]) return fail(URMVO_ERR_ARG, "pose_plan_create: obs_off must be non-decreasing");
+  CU_TRY(cudaSetDevice(ctx->device));
+  urmvo_pose_plan* p = new urmvo_pose_plan();
+  p->ctx = ctx; p->B = B; p->total_o = obs_off[B] - obs_off[0];
+  for (int k = 0; k < 4; k++) p->intr[k] = intr[k];
+  p->chi2_thr = chi2_thr;
+  p->delta = (double)(float)std::sqrt(chi2_thr);  // src/g2o_optimization.cc:205
+  p->rounds = rounds; p->its = its_per_round;
+  const size_t TO = p->total_o;
+  Arena A;
+  p->o_off = A.take<int>(B + 1); p->o_pose_in = A.take<double>((size_t)B * 7);
+  p->o_uv = A.take<double>(TO * 2); p->o_X = A.take<double>(TO * 3);
+  p->o_inl_in = A.take<uint8_t>(TO); p->o_inl = A.take<uint8_t>(TO); p->o_level = A.take<uint8_t>(TO);
+  p->o_pose_out = A.take<double>((size_t)B * 7); p->o_ninl = A.take<int>(B); p->o_iters = A.take<int>(B);
+  cudaError_t ce = cudaMalloc(&p->dev, A.off);
+  if (ce != cudaSuccess) { delete p; return fail(URMVO_ERR_CUDA, std::string("cudaMalloc pose plan: ") + cudaGetErrorString(ce)); }
+  cudaStream_t s = ctx->stream;
+  std::vector<int> off(B + 1);
+  for (int f = 0; f <= B; f++) off[f] = obs_off[f] - obs_off[0];
+  const size_t o0 = obs_off[0];
+  cudaError_t e[6];
+  e[0] = cudaMemcpyAsync(p->dev + p->o_off, off.data(), (B + 1) * sizeof(int), cudaMemcpyHostToDevice, s);
+  e[1] = cudaMemcpyAsync(p->dev + p->o_pose_in, poses, (size_t)B * 7 * sizeof(double), cudaMemcpyHostToDevice, s);
+  e[2] = TO ? cudaMemcpyAsync(p->dev + p->o_uv, uv + o0 * 2, TO * 2 * sizeof(double), cudaMemcpyHostToDevice, s) : cudaSuccess;
+  e[3] = TO ? cudaMemcpyAsync(p->dev + p->o_X, Xw + o0 * 3, TO * 3 * sizeof(double), cudaMemcpyHostToDevice, s) : cudaSuccess;
+  if (inlier) e[4] = TO ? cudaMemcpyAsync(p->dev + p->o_inl_in, inlier + o0, TO, cudaMemcpyHostToDevice, s) : cudaSuccess;
+  else e[4] = TO ? cudaMemsetAsync(p->dev + p->o_inl_in, 1, TO, s) : cudaSuccess;
+  e[5] = cudaStreamSynchronize(s);  // `off` is a stack-lifetime staging vector
+  for (cudaError_t x : e)
+    if (x != cudaSuccess) { urmvo_pose_plan_destroy(p); return fail(URMVO_ERR_CUDA, std::string("pose_plan_create upload: ") + cudaGetErrorString(x)); }
+  *out = p;
+  return URMVO_OK;
+}
+
+extern "C" int urmvo_pose_plan_run(urmvo_pose_plan* p) {
+  if (!p) return fail(URMVO_ERR_ARG, "pose_plan_run: null plan");
+  CU_TRY(cudaSetDevice(p->ctx->device));
+  cudaStream_t s = p->ctx->stream;
+  if (p->total_o) CU_TRY(cudaMemcpyAsync(p->dev + p->o_inl, p->dev + p->o_inl_in, p->total_o, cudaMemcpyDeviceToDevice, s));
+  cudaError_t e = launch_pose_only(p->B, (const int*)(p->dev + p->o_off), (const double*)(p->dev + p->o_pose_in),
+                                   (const double*)(p->dev + p->o_uv), (const double*)(p->dev + p->o_X), p->intr,
+                                   p->chi2_thr, p->delta, p->rounds, p->its, p->dev + p->o_inl, p->dev + p->o_level,
+                                   (double*)(p->dev + p->o_pose_out), (int*)(p->dev + p->o_ninl),
+                                   (int*)(p->dev + p->o_iters), s);
+  if (e != cudaSuccess) return fail(URMVO_ERR_CUDA, std::string("pose kernel launch: ") + cudaGetErrorString(e));
+  p->ctx->launches++;
+  return URMVO_OK;
+}
+
+extern "C" int urmvo_pose_plan_download(urmvo_pose_plan* p, double* poses, uint8_t* inlier, int32_t* n_inlier,
+                                        int32_t* lm_iters) {
+  if (!p) return fail(URMVO_ERR_ARG, "pose_plan_download: null plan");
+  CU_TRY(cudaSetDevice(p->ctx->device));
+  cudaStream_t s = p->ctx->stream;
+  if (poses) CU_TRY(cudaMemcpyAsync(poses, p->dev + p->o_pose_out, (size_t)p->B * 7 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (inlier && p->total_o) CU_TRY(cudaMemcpyAsync(inlier, p->dev + p->o_inl, p->total_o, cudaMemcpyDeviceToHost, s));
+  if (n_inlier) CU_TRY(cudaMemcpyAsync(n_inlier, p->dev + p->o_ninl, p->B * sizeof(int), cudaMemcpyDeviceToHost, s));
+  if (lm_iters) CU_TRY(cudaMemcpyAsync(lm_iters, p->dev + p->o_iters, p->B * sizeof(int), cudaMemcpyDeviceToHost, s));
+  CU_TRY(cudaStreamSynchronize(s));
+  return URMVO_OK;
+}
+
+extern "C" int urmvo_pose_only_batch(urmvo_ctx* ctx, int B, const int32_t* obs_off, double* poses,
+                                     const double* uv, const double* Xw, const double* intr, double chi2_thr,
+                                     int rounds, int its_per_round, uint8_t* inlier, int32_t* n_inlier) {
+  urmvo_pose_plan* p = nullptr;
+  int rc = urmvo_pose_plan_create(ctx, &p, B, obs_off, poses, uv, Xw, intr, chi2_thr, rounds, its_per_round, inlier);
+  if (rc != URMVO_OK) return rc;
+  rc = urmvo_pose_plan_run(p);
+  if (rc == URMVO_OK) rc = urmvo_pose_plan_download(p, poses, inlier ? inlier + obs_off[0] : nullptr, n_inlier, nullptr);
+  urmvo_pose_plan_destroy(p);
+  return rc;
+}
+
+// =====================================================================================  two-view
+
+struct urmvo_tv_plan {
+  urmvo_ctx* ctx = nullptr;
+  TVBuffers b{};
+  float sigma = 1.0f;
+  float Kh[9];
+  std::vector<int> m1, m2;
+  unsigned char* dev = nullptr;
+  bool ransac_done = false;
+};
+
+extern "C" void urmvo_tv_plan_destroy(urmvo_tv_plan* p) {
+  if (!p) return;
+  if (p->dev) { cudaSetDevice(p->ctx->device); cudaFree(p->dev); }
+  delete p;
+}
+
+extern "C" int urmvo_tv_plan_create(urmvo_ctx* ctx, urmvo_tv_plan** out, int n1, const float* keys1, int n2,
+                                    const float* keys2, const int32_t* matches12, const float* K, float sigma,
+                                    int n_hyp, const int32_t* sets) {
+  if (!ctx || !out) return fail(URMVO_ERR_ARG, "tv_plan_create: null context / out");
+  *out = nullptr;
+  if (n1 <= 0 || n2 <= 0 || !keys1 || !keys2 || !matches12 || !K || n_hyp <= 0 || !sets || !(sigma > 0))
+    return fail(URMVO_ERR_ARG, "tv_plan_create: null or empty input");
+  CU_TRY(cudaSetDevice(ctx->device));
+  urmvo_tv_plan* p = new urmvo_tv_plan();
+  p->ctx = ctx;
+  p->sigma = sigma;
+  std::memcpy(p->Kh, K, sizeof(p->Kh));
+  for (int i = 0; i < n1; i++) {  // src/epipolar_geometry.cc:34-40
+    if (matches12[i] >= 0) {
+      if (matches12[i] >= n2) { delete p; return fail(URMVO_ERR_ARG, "tv_plan_create: match index out of range"); }
+      p->m1.push_back(i);
+      p->m2.push_back(matches12[i]);
+    }
+  }
+  const int N = (int)p->m1.size();
+  if (N < 8) { delete p; return fail(URMVO_ERR_ARG, "tv_plan_create: fewer than 8 matches"); }
+  for (size_t i = 0; i < (size_t)n_hyp * 8; i++)
+    if (sets[i] < 0 || sets[i] >= N) { delete p; return fail(URMVO_ERR_ARG, "tv_plan_create: sample index out of range"); }
+  TVBuffers& b = p->b;
+  b.n1 = n1; b.n2 = n2; b.N = N; b.n_hyp = n_hyp; b.words = (N + 31) / 32;
+  Arena A;
+  const size_t o_k1 = A.take<float>((size_t)n1 * 2), o_k2 = A.take<float>((size_t)n2 * 2);
+  const size_t o_m1 = A.take<int>(N), o_m2 = A.take<int>(N), o_sets = A.take<int>((size_t)n_hyp * 8), o_K = A.take<float>(9);
+  const size_t o_pn1 = A.take<float>((size_t)n1 * 2), o_pn2 = A.take<float>((size_t)n2 * 2), o_T1 = A.take<float>(9), o_T2 = A.take<float>(9);
+  const size_t o_uv = A.take<float4>(N), o_pnm = A.take<float4>(N);
+  const size_t o_models = A.take<float>((size_t)2 * n_hyp * 18), o_scores = A.take<float>((size_t)2 * n_hyp);
+  const size_t o_masks = A.take<uint32_t>((size_t)2 * n_hyp * b.words);
+  const size_t o_bi = A.take<int>(2), o_bs = A.take<float>(2);
+  const size_t o_P3D = A.take<float>((size_t)8 * n1 * 3), o_good = A.take<uint8_t>((size_t)8 * n1), o_cos = A.take<float>(N);
+  const size_t o_motion = A.take<TVMotionOut>(1);
+  cudaError_t ce = cudaMalloc(&p->dev, A.off);
+  if (ce != cudaSuccess) { delete p; return fail(URMVO_ERR_CUDA, std::string("cudaMalloc tv plan: ") + cudaGetErrorString(ce)); }
+  unsigned char* D = p->dev;
+  b.keys1 = (float*)(D + o_k1); b.keys2 = (float*)(D + o_k2);
+  b.m1 = (int*)(D + o_m1); b.m2 = (int*)(D + o_m2); b.sets = (int*)(D + o_sets); b.K = (float*)(D + o_K);
+  b.pn1 = (float*)(D + o_pn1); b.pn2 = (float*)(D + o_pn2); b.T1 = (float*)(D + o_T1); b.T2 = (float*)(D + o_T2);
+  b.uv = (float4*)(D + o_uv); b.pnm = (float4*)(D + o_pnm);
+  b.models = (float*)(D + o_models); b.scores = (float*)(D + o_scores); b.masks = (uint32_t*)(D + o_masks);
+  b.best_idx = (int*)(D + o_bi); b.best_score = (float*)(D + o_bs);
+  b.P3D = (float*)(D + o_P3D); b.good = D + o_good; b.cosbuf = (float*)(D + o_cos);
+  b.motion = (TVMotionOut*)(D + o_motion);
+  cudaStream_t s = ctx->stream;
+  cudaError_t e[7];
+  e[0] = cudaMemcpyAsync(D + o_k1, keys1, (size_t)n1 * 2 * sizeof(float), cudaMemcpyHostToDevice, s);
+  e[1] = cudaMemcpyAsync(D + o_k2, keys2, (size_t)n2 * 2 * sizeof(float), cudaMemcpyHostToDevice, s);
+  e[2] = cudaMemcpyAsync(D + o_m1, p->m1.data(), N * sizeof(int), cudaMemcpyHostToDevice, s);
+  e[3] = cudaMemcpyAsync(D + o_m2, p->m2.data(), N * sizeof(int), cudaMemcpyHostToDevice, s);
+  e[4] = cudaMemcpyAsync(D + o_sets, sets, (size_t)n_hyp * 8 * sizeof(int), cudaMemcpyHostToDevice, s);
+  e[5] = cudaMemcpyAsync(D + o_K, K, 9 * sizeof(float), cudaMemcpyHostToDevice, s);
+  e[6] = cudaStreamSynchronize(s);
+  for (cudaError_t x : e)
+    if (x != cudaSuccess) { urmvo_tv_plan_destroy(p); return fail(URMVO_ERR_CUDA, std::string("tv_plan_create upload: ") + cudaGetErrorString(x)); }
+  *out = p;
+  return URMVO_OK;
+}
+
+extern "C" int urmvo_tv_plan_run_ransac(urmvo_tv_plan* p) {
+  if (!p) return fail(URMVO_ERR_ARG, "tv_plan_run_ransac: null plan");
+  CU_TRY(cudaSetDevice(p->ctx->device));
+  int nl = 0;
+  cudaError_t e = launch_tv_ransac(p->b, p->sigma, p->ctx->n_sm, p->ctx->stream, &nl);
+  if (e != cudaSuccess) return fail(URMVO_ERR_CUDA, std::string("two-view RANSAC launch: ") + cudaGetErrorString(e));
+  p->ctx->launches += nl;
+  p->ransac_done = true;
+  return URMVO_OK;
+}
+
+extern "C" int urmvo_tv_plan_download_hyps(urmvo_tv_plan* p, int model, float* scores, uint32_t* masks, float* models) {
+  if (!p || model < 0 || model > 1) return fail(URMVO_ERR_ARG, "tv_plan_download_hyps: bad plan / model");
+  CU_TRY(cudaSetDevice(p->ctx->device));
+  cudaStream_t s = p->ctx->stream;
+  const TVBuffers& b = p->b;
+  const size_t nh = b.n_hyp;
+  if (scores) CU_TRY(cudaMemcpyAsync(scores, b.scores + model * nh, nh * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (masks) CU_TRY(cudaMemcpyAsync(masks, b.masks + model * nh * b.words, nh * b.words * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  std::vector<float> tmp;
+  if (models) {
+    tmp.resize(nh * 18);
+    CU_TRY(cudaMemcpyAsync(tmp.data(), b.models + model * nh * 18, nh * 18 * sizeof(float), cudaMemcpyDeviceToHost, s));
+  }
+  CU_TRY(cudaStreamSynchronize(s));
+  if (models)
+    for (size_t h = 0; h < nh; h++) std::memcpy(models + h * 9, tmp.data() + h * 18, 9 * sizeof(float));
+  return URMVO_OK;
+}
+
+extern "C" int urmvo_tv_plan_reconstruct(urmvo_tv_plan* p, float* T21, float* P3D, uint8_t* triangulated,
+                                         uint8_t* mask_H, uint8_t* mask_F, urmvo_tv_stats* stats, int* success) {
+  if (!p || !T21 || !P3D || !triangulated || !success) return fail(URMVO_ERR_ARG, "tv_plan_reconstruct: null argument");
+  if (!p->ransac_done) return fail(URMVO_ERR_ARG, "tv_plan_reconstruct: run_ransac has not been called");
+  CU_TRY(cudaSetDevice(p->ctx->device));
+  cudaStream_t s = p->ctx->stream;
+  const TVBuffers& b = p->b;
+  const float sigma2 = p->sigma * p->sigma;
+  const float th2 = 4.0 * sigma2;  // src/epipolar_geometry.cc:489
+  cudaError_t e = launch_tv_motion(b, th2, s);
+  if (e != cudaSuccess) return fail(URMVO_ERR_CUDA, std::string("two-view motion launch: ") + cudaGetErrorString(e));
+  p->ctx->launches++;
+  TVMotionOut mo;
+  int best_idx[2];
+  float best_score[2];
+  CU_TRY(cudaMemcpyAsync(&mo, b.motion, sizeof(mo), cudaMemcpyDeviceToHost, s));
+  CU_TRY(cudaMemcpyAsync(best_idx, b.best_idx, sizeof(best_idx), cudaMemcpyDeviceToHost, s));
+  CU_TRY(cudaMemcpyAsync(best_score, b.best_score, sizeof(best_score), cudaMemcpyDeviceToHost, s));
+  CU_TRY(cudaStreamSynchronize(s));
+  urmvo_tv_stats st;
+  std::memset(&st, 0, sizeof(st));
+  st.SF = best_score[0]; st.SH = best_score[1];
+  st.best_F = best_idx[0]; st.best_H = best_idx[1];
+  st.used_H = mo.used_H;
+  st.best_motion = -1;
+  std::vector<uint32_t> mw(b.words);
+  for (int model = 0; model < 2; model++) {
+    uint8_t* mout = model == 0 ? mask_F : mask_H;
+    float* Mout = model == 0 ? st.F21 : st.H21;
+    if (best_idx[model] >= 0) {
+      CU_TRY(cudaMemcpyAsync(Mout, b.models + ((size_t)model * b.n_hyp + best_idx[model]) * 18, 9 * sizeof(float), cudaMemcpyDeviceToHost, s));
+      if (mout) {
+        CU_TRY(cudaMemcpyAsync(mw.data(), b.masks + ((size_t)model * b.n_hyp + best_idx[model]) * b.words, b.words * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        CU_TRY(cudaStreamSynchronize(s));
+        for (int i = 0; i < b.N; i++) mout[i] = (mw[i >> 5] >> (i & 31)) & 1u;
+      }
+    } else if (mout) {
+      std::memset(mout, 0, b.N);
+    }
+  }
+  CU_TRY(cudaStreamSynchronize(s));
+  std::memset(T21, 0, 16 * sizeof(float));
+  std::memset(P3D, 0, (size_t)b.n1 * 3 * sizeof(float));
+  std::memset(triangulated, 0, (size_t)b.n1);
+  *success = 0;
+  int winner = -1;
+  float parallax[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int h = 0; h < mo.n_motion; h++) {
+    st.n_good[h] = mo.n_good[h];
+    // :889-895  parallax = acos(vCosParallax[idx]) * 180 / CV_PI  (float acos, double division)
+    if (mo.n_good[h] > 0) parallax[h] = std::acos(mo.cos_kth[h]) * 180 / 3.1415926535897932384626433832795;
+    else parallax[h] = 0;
+    st.parallax[h] = parallax[h];
+  }
+  const float minParallax = 1.0;
+  const int minTriangulated = 50;
+  const int Ninl = mo.n_inl;
+  if (mo.used_H == 0 && mo.n_motion == 4) {
+    // _reconstruct_F acceptance, src/epipolar_geometry.cc:500-561
+    const int* g = mo.n_good;
+    const int maxGood = std::max(g[0], std::max(g[1], std::max(g[2], g[3])));
+    const int nMinGood = std::max(static_cast<int>(0.9 * Ninl), minTriangulated);
+    int nsimilar = 0;
+    for (int h = 0; h < 4; h++)
+      if (g[h] > 0.7 * maxGood) nsimilar++;
+    if (!(maxGood < nMinGood || nsimilar > 1)) {
+      for (int h = 0; h < 4; h++)
+        if (maxGood == g[h]) {
+          if (parallax[h] > minParallax) winner = h;
+          break;
+        }
+    }
+  } else if (mo.used_H == 1 && mo.n_motion == 8) {
+    // _reconstruct_H acceptance, :695-732
+    int bestGood = 0, secondBestGood = 0, bestIdx = -1;
+    float bestParallax = -1;
+    for (int h = 0; h < 8; h++) {
+      const int nGood = mo.n_good[h];
+      if (nGood > bestGood) {
+        secondBestGood = bestGood;
+        bestGood = nGood;
+        bestIdx = h;
+        bestParallax = parallax[h];
+      } else if (nGood > secondBestGood) {
+        secondBestGood = nGood;
+      }
+    }
+    if (secondBestGood < 0.75 * bestGood && bestParallax >= minParallax && bestGood > minTriangulated &&
+        bestGood > 0.9 * Ninl)
+      winner = bestIdx;
+  }
+  if (winner >= 0) {
+    for (int i = 0; i < 16; i++) T21[i] = (i % 5 == 0) ? 1.0f : 0.0f;
+    for (int i = 0; i < 3; i++) {
+      for (int j = 0; j < 3; j++) T21[i * 4 + j] = mo.R[winner][i * 3 + j];
+      T21[i * 4 + 3] = mo.t[winner][i];
+    }
+    CU_TRY(cudaMemcpyAsync(P3D, b.P3D + (size_t)winner * b.n1 * 3, (size_t)b.n1 * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaMemcpyAsync(triangulated, b.good + (size_t)winner * b.n1, (size_t)b.n1, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    st.best_motion = winner;
+    *success = 1;
+  }
+  if (stats) *stats = st;
+  return URMVO_OK;
+}
+
+extern "C" int urmvo_two_view(urmvo_ctx* ctx, int n1, const float* keys1, int n2, const float* keys2,
+                              const int32_t* matches12, const float* K, float sigma, int n_hyp,
+                              const int32_t* sets, float* T21, float* P3D, uint8_t* triangulated,
+                              uint8_t* mask_H, uint8_t* mask_F, urmvo_tv_stats* stats, int* success) {
+  urmvo_tv_plan* p = nullptr;
+  int rc = urmvo_tv_plan_create(ctx, &p, n1, keys1, n2, keys2, matches12, K, sigma, n_hyp, sets);
+  if (rc != URMVO_OK) return rc;
+  rc = urmvo_tv_plan_run_ransac(p);
+  if (rc == URMVO_OK) rc = urmvo_tv_plan_reconstruct(p, T21, P3D, triangulated, mask_H, mask_F, stats, success);
+  urmvo_tv_plan_destroy(p);
+  return rc;
+}

@@ -1,0 +1,59 @@
+// csrc/kernels.h — host-side launchers exported by the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ba_types.h"
+
+namespace urmvo {
+
+// ---- ba_kernels.cu
+size_t ba_smem_bytes(int threads, int kmax);
+// Batched windows: grid = n_clusters * cluster_size CTAs, one cluster per window.
+cudaError_t launch_ba_cluster(const BAWin* wins_dev, const BARun& run, int kmax, int n_clusters,
+                              int cluster_size, int threads, cudaStream_t stream);
+// One (or a few) large problems on a cooperative grid. grid_blocks <= co-resident capacity.
+cudaError_t launch_ba_grid(const BAWin* wins_dev, const BARun& run, int kmax, int grid_blocks,
+                           int threads, cudaStream_t stream);
+// Max co-resident CTAs of the grid kernel on the current device for this configuration.
+int ba_grid_capacity(int threads, int kmax);
+constexpr int kBAPartWidth = 8;  // doubles per CTA and buffer in BAWin::part (+8 flag doubles)
+
+// ---- pose_kernels.cu
+cudaError_t launch_pose_only(int B, const int* obs_off, const double* pose_in, const double* uv,
+                             const double* Xw, const double* intr, double chi2_thr, double delta,
+                             int rounds, int its_per_round, uint8_t* inlier, uint8_t* level,
+                             double* pose_out, int* n_inlier, int* lm_iters, cudaStream_t stream);
+
+// ---- twoview_kernels.cu
+struct TVMotionOut {
+  int used_H;
+  int n_motion;
+  int n_inl;
+  int n_good[8];
+  float cos_kth[8];
+  float R[8][9];
+  float t[8][3];
+};
+struct TVBuffers {
+  int n1, n2, N, n_hyp, words;
+  const float *keys1, *keys2;
+  const int *m1, *m2, *sets;
+  const float* K;
+  float *pn1, *pn2, *T1, *T2;
+  float4 *uv, *pnm;
+  float* models;      // [2][n_hyp][18]
+  float* scores;      // [2][n_hyp]
+  uint32_t* masks;    // [2][n_hyp][words]
+  int* best_idx;      // [2]
+  float* best_score;  // [2]
+  float* P3D;         // [8][n1*3]
+  uint8_t* good;      // [8][n1]
+  float* cosbuf;      // [N]
+  TVMotionOut* motion;
+};
+// normalise + gather + fit + score + arg-max: 5 launches. Returns launches made in *n_launch.
+cudaError_t launch_tv_ransac(const TVBuffers& b, float sigma, int n_sm, cudaStream_t stream, int* n_launch);
+cudaError_t launch_tv_motion(const TVBuffers& b, float th2, cudaStream_t stream);
+
+}  // namespace urmvo

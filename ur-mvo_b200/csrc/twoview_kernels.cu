@@ -1,0 +1,650 @@
+// csrc/twoview_kernels.cu — two-view RANSAC (fundamental + homography) and motion recovery on sm_100a.
+//
+// Reference behaviour reproduced, /root/reference/src/epipolar_geometry.cc:
+//   _normalize :735-780, _compute_F21 :247-283, _compute_H21 :207-245, _check_F :372-449,
+//   _check_H :285-370, _find_F/_find_H arg-max :153-157/:199-203, _decompose_E :900-926,
+//   _reconstruct_F :451-562, _reconstruct_H :564-733, _check_R_T :782-898, _triangulate :928-950.
+//
+// Everything is fp32 like the reference.  THIS FILE MUST BE COMPILED WITH -fmad=false (and the
+// default IEEE -prec-div=true -prec-sqrt=true): the parity contract is bit-exact scores and inlier
+// masks for identical 8-point sets, which needs the same operation sequence with no contraction.
+// Eigen::JacobiSVD is replaced by a fully specified one-sided Jacobi SVD (cyclic pair order,
+// threshold 5e-7, <= 30 sweeps) — see DESIGN.md §6.
+//
+//   tv_normalize_kernel   one CTA per image; the running sums are sequential like the reference's
+//   tv_fit_kernel         one thread per (model, hypothesis): 8-point DLT + Jacobi SVD
+//   tv_score_kernel       one warp per (model, hypothesis): lanes stride over the matches,
+//                         __ballot_sync builds the inlier mask words, the score is accumulated in
+//                         match order (the reference's summation order) by a lane-ordered chain
+//   tv_argmax_kernel      deterministic arg-max: highest score, earliest hypothesis on ties
+//   tv_motion_kernel      model selection, E / H decomposition, per-match DLT triangulation and
+//                         cheirality vote for the 4 (F) or 8 (H) motion hypotheses
+
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "kernels.h"
+
+namespace urmvo {
+
+namespace {
+
+constexpr int kMaxSweeps = 30;
+constexpr float kJacobiTol = 5e-7f;
+
+// One-sided (Hestenes) Jacobi on an m x n row-major matrix; V (n x n) accumulates the rotations.
+// Deliberately a real (non-inlined) function with run-time sizes: one copy of the loop nest serves
+// the 8x9, 16x9, 4x4 and 3x3 uses, and the operation order is literally the restatement's.
+__device__ __noinline__ void jacobi_onesided(int m, int n, float* A, float* V) {
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < n; j++) V[i * n + j] = (i == j) ? 1.0f : 0.0f;
+  for (int sweep = 0; sweep < kMaxSweeps; sweep++) {
+    bool rotated = false;
+    for (int p = 0; p < n - 1; p++) {
+      for (int q = p + 1; q < n; q++) {
+        float alpha = 0.0f, beta = 0.0f, gamma = 0.0f;
+        for (int k = 0; k < m; k++) {
+          const float ap = A[k * n + p], aq = A[k * n + q];
+          alpha += ap * ap;
+          beta += aq * aq;
+          gamma += ap * aq;
+        }
+        if (fabsf(gamma) <= kJacobiTol * sqrtf(alpha * beta)) continue;
+        rotated = true;
+        const float zeta = (beta - alpha) / (2.0f * gamma);
+        float t = 1.0f / (fabsf(zeta) + sqrtf(1.0f + zeta * zeta));
+        if (zeta < 0.0f) t = -t;
+        const float c = 1.0f / sqrtf(1.0f + t * t);
+        const float s = c * t;
+        for (int k = 0; k < m; k++) {
+          const float ap = A[k * n + p], aq = A[k * n + q];
+          A[k * n + p] = c * ap - s * aq;
+          A[k * n + q] = s * ap + c * aq;
+        }
+        for (int k = 0; k < n; k++) {
+          const float vp = V[k * n + p], vq = V[k * n + q];
+          V[k * n + p] = c * vp - s * vq;
+          V[k * n + q] = s * vp + c * vq;
+        }
+      }
+    }
+    if (!rotated) break;
+  }
+}
+
+__device__ __forceinline__ float col_norm(int m, int n, const float* A, int j) {
+  float s = 0.0f;
+  for (int k = 0; k < m; k++) s += A[k * n + j] * A[k * n + j];
+  return sqrtf(s);
+}
+
+// Right singular vector of the smallest singular value (first index on ties). n <= 9.
+__device__ __noinline__ void null_vector(int m, int n, float* A, float* v) {
+  float V[81];
+  jacobi_onesided(m, n, A, V);
+  int best = 0;
+  float bn = col_norm(m, n, A, 0);
+  for (int j = 1; j < n; j++) {
+    const float nj = col_norm(m, n, A, j);
+    if (nj < bn) { bn = nj; best = j; }
+  }
+  for (int k = 0; k < n; k++) v[k] = V[k * n + best];
+}
+
+// 3x3 SVD, singular values descending; U.col(2) = +-(u0 x u1) such that U diag(w) V^T = A.
+__device__ __noinline__ void svd3(const float* Ain, float* U, float* w, float* V) {
+  float A[9], Vt[9];
+  for (int i = 0; i < 9; i++) A[i] = Ain[i];
+  jacobi_onesided(3, 3, A, Vt);
+  float nrm[3];
+  int idx[3] = {0, 1, 2};
+  for (int j = 0; j < 3; j++) nrm[j] = col_norm(3, 3, A, j);
+  for (int i = 0; i < 2; i++) {
+    int b = i;
+    for (int j = i + 1; j < 3; j++)
+      if (nrm[idx[j]] > nrm[idx[b]]) b = j;
+    const int tmp = idx[i]; idx[i] = idx[b]; idx[b] = tmp;
+  }
+  for (int j = 0; j < 3; j++) {
+    const int s = idx[j];
+    w[j] = nrm[s];
+    for (int k = 0; k < 3; k++) V[k * 3 + j] = Vt[k * 3 + s];
+    if (j < 2) {
+      for (int k = 0; k < 3; k++) U[k * 3 + j] = (nrm[s] > 0.0f) ? A[k * 3 + s] / nrm[s] : 0.0f;
+    }
+  }
+  float c0 = U[3 + 0] * U[6 + 1] - U[6 + 0] * U[3 + 1];
+  float c1 = U[6 + 0] * U[0 + 1] - U[0 + 0] * U[6 + 1];
+  float c2 = U[0 + 0] * U[3 + 1] - U[3 + 0] * U[0 + 1];
+  const int s2 = idx[2];
+  const float d = c0 * A[0 + s2] + c1 * A[3 + s2] + c2 * A[6 + s2];
+  if (d < 0.0f) { c0 = -c0; c1 = -c1; c2 = -c2; }
+  U[2] = c0; U[5] = c1; U[8] = c2;
+}
+
+__device__ __forceinline__ void mat3_mul(const float* A, const float* B, float* C) {
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++)
+      C[i * 3 + j] = A[i * 3] * B[j] + A[i * 3 + 1] * B[3 + j] + A[i * 3 + 2] * B[6 + j];
+}
+__device__ __forceinline__ void mat3_T(const float* A, float* B) {
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) B[i * 3 + j] = A[j * 3 + i];
+}
+__device__ __forceinline__ float det3(const float* a) {
+  return a[0] * (a[4] * a[8] - a[5] * a[7]) - a[1] * (a[3] * a[8] - a[5] * a[6]) +
+         a[2] * (a[3] * a[7] - a[4] * a[6]);
+}
+__device__ __forceinline__ void inv3f(const float* a, float* r) {
+  const float c00 = a[4] * a[8] - a[5] * a[7];
+  const float c01 = a[5] * a[6] - a[3] * a[8];
+  const float c02 = a[3] * a[7] - a[4] * a[6];
+  const float det = a[0] * c00 + a[1] * c01 + a[2] * c02;
+  const float id = 1.0f / det;
+  r[0] = c00 * id;
+  r[1] = (a[2] * a[7] - a[1] * a[8]) * id;
+  r[2] = (a[1] * a[5] - a[2] * a[4]) * id;
+  r[3] = c01 * id;
+  r[4] = (a[0] * a[8] - a[2] * a[6]) * id;
+  r[5] = (a[2] * a[3] - a[0] * a[5]) * id;
+  r[6] = c02 * id;
+  r[7] = (a[1] * a[6] - a[0] * a[7]) * id;
+  r[8] = (a[0] * a[4] - a[1] * a[3]) * id;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------- normalisation
+
+// grid = 2 (image 1, image 2). keys: n*2, pn: n*2 out, T: 9 out.
+__global__ void tv_normalize_kernel(int n1, const float* __restrict__ keys1, float* __restrict__ pn1,
+                                    float* __restrict__ T1, int n2, const float* __restrict__ keys2,
+                                    float* __restrict__ pn2, float* __restrict__ T2) {
+  const int n = blockIdx.x == 0 ? n1 : n2;
+  const float* keys = blockIdx.x == 0 ? keys1 : keys2;
+  float* pn = blockIdx.x == 0 ? pn1 : pn2;
+  float* T = blockIdx.x == 0 ? T1 : T2;
+  __shared__ float sh[4];
+  if (threadIdx.x == 0) {
+    float meanX = 0, meanY = 0;
+    for (int i = 0; i < n; i++) { meanX += keys[i * 2]; meanY += keys[i * 2 + 1]; }
+    meanX = meanX / n;
+    meanY = meanY / n;
+    float meanDevX = 0, meanDevY = 0;
+    for (int i = 0; i < n; i++) {
+      meanDevX += fabsf(keys[i * 2] - meanX);
+      meanDevY += fabsf(keys[i * 2 + 1] - meanY);
+    }
+    meanDevX = meanDevX / n;
+    meanDevY = meanDevY / n;
+    const float sX = 1.0f / meanDevX, sY = 1.0f / meanDevY;
+    sh[0] = meanX; sh[1] = meanY; sh[2] = sX; sh[3] = sY;
+    for (int i = 0; i < 9; i++) T[i] = 0.0f;
+    T[0] = sX; T[4] = sY; T[2] = -meanX * sX; T[5] = -meanY * sY; T[8] = 1.0f;
+  }
+  __syncthreads();
+  const float meanX = sh[0], meanY = sh[1], sX = sh[2], sY = sh[3];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    pn[i * 2] = (keys[i * 2] - meanX) * sX;
+    pn[i * 2 + 1] = (keys[i * 2 + 1] - meanY) * sY;
+  }
+}
+
+// Packs the valid matches: uv[i] = (u1, v1, u2, v2) in pixels, pnm likewise in normalised coords.
+__global__ void tv_gather_kernel(int N, const int* __restrict__ m1, const int* __restrict__ m2,
+                                 const float* __restrict__ keys1, const float* __restrict__ keys2,
+                                 const float* __restrict__ pn1, const float* __restrict__ pn2,
+                                 float4* __restrict__ uv, float4* __restrict__ pnm) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const int a = m1[i], b = m2[i];
+  uv[i] = make_float4(keys1[a * 2], keys1[a * 2 + 1], keys2[b * 2], keys2[b * 2 + 1]);
+  pnm[i] = make_float4(pn1[a * 2], pn1[a * 2 + 1], pn2[b * 2], pn2[b * 2 + 1]);
+}
+
+// ------------------------------------------------------------------------------- model fitting
+
+// Thread t < n_hyp fits F for hypothesis t; thread n_hyp + t fits H.  models: [2][n_hyp][18]
+// (F: 9 used; H: H21 | H12).
+__global__ void __launch_bounds__(64)
+tv_fit_kernel(int n_hyp, const int* __restrict__ sets, const float4* __restrict__ pnm,
+              const float* __restrict__ T1, const float* __restrict__ T2, float* __restrict__ models) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= 2 * n_hyp) return;
+  const int model = g / n_hyp, hyp = g - model * n_hyp;
+  const int* set = sets + (size_t)hyp * 8;
+  float t1[9], t2[9];
+  for (int i = 0; i < 9; i++) { t1[i] = T1[i]; t2[i] = T2[i]; }
+  float* out = models + ((size_t)model * n_hyp + hyp) * 18;
+  if (model == 0) {
+    float A[8 * 9];
+    for (int j = 0; j < 8; j++) {
+      const float4 m = pnm[set[j]];
+      const float u1 = m.x, v1 = m.y, u2 = m.z, v2 = m.w;
+      float* r = A + j * 9;
+      r[0] = u2 * u1; r[1] = u2 * v1; r[2] = u2;
+      r[3] = v2 * u1; r[4] = v2 * v1; r[5] = v2;
+      r[6] = u1; r[7] = v1; r[8] = 1.0f;
+    }
+    float Fpre[9];
+    null_vector(8, 9, A, Fpre);
+    float U[9], w[3], V[9];
+    svd3(Fpre, U, w, V);
+    w[2] = 0.0f;
+    float Fn[9];
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++)
+        Fn[i * 3 + j] = (U[i * 3] * w[0]) * V[j * 3] + (U[i * 3 + 1] * w[1]) * V[j * 3 + 1] +
+                        (U[i * 3 + 2] * w[2]) * V[j * 3 + 2];
+    float T2t[9], tmp[9], F21[9];
+    mat3_T(t2, T2t);
+    mat3_mul(T2t, Fn, tmp);
+    mat3_mul(tmp, t1, F21);
+    for (int i = 0; i < 9; i++) { out[i] = F21[i]; out[9 + i] = 0.0f; }
+  } else {
+    float A[16 * 9];
+    for (int j = 0; j < 8; j++) {
+      const float4 m = pnm[set[j]];
+      const float u1 = m.x, v1 = m.y, u2 = m.z, v2 = m.w;
+      float* r0 = A + (2 * j) * 9;
+      float* r1 = A + (2 * j + 1) * 9;
+      r0[0] = 0.0f; r0[1] = 0.0f; r0[2] = 0.0f;
+      r0[3] = -u1; r0[4] = -v1; r0[5] = -1.0f;
+      r0[6] = v2 * u1; r0[7] = v2 * v1; r0[8] = v2;
+      r1[0] = u1; r1[1] = v1; r1[2] = 1.0f;
+      r1[3] = 0.0f; r1[4] = 0.0f; r1[5] = 0.0f;
+      r1[6] = -u2 * u1; r1[7] = -u2 * v1; r1[8] = -u2;
+    }
+    float Hn[9];
+    null_vector(16, 9, A, Hn);
+    float T2inv[9], tmp[9], H21[9], H12[9];
+    inv3f(t2, T2inv);
+    mat3_mul(T2inv, Hn, tmp);
+    mat3_mul(tmp, t1, H21);
+    inv3f(H21, H12);
+    for (int i = 0; i < 9; i++) { out[i] = H21[i]; out[9 + i] = H12[i]; }
+  }
+}
+
+// ------------------------------------------------------------------------------- scoring
+
+// One warp per (model, hypothesis).  uv staged in shared memory when it fits.
+// scores: [2][n_hyp], masks: [2][n_hyp][words].
+__global__ void __launch_bounds__(256)
+tv_score_kernel(int N, int n_hyp, const float4* __restrict__ uv_g, const float* __restrict__ models,
+                float inv_sigma2, int stage_uv, float* __restrict__ scores,
+                uint32_t* __restrict__ masks) {
+  extern __shared__ float4 uv_s[];
+  if (stage_uv) {
+    for (int i = threadIdx.x; i < N; i += blockDim.x) uv_s[i] = uv_g[i];
+    __syncthreads();
+  }
+  const float4* uvp = stage_uv ? uv_s : uv_g;
+  const int lane = threadIdx.x & 31;
+  const int wpc = blockDim.x >> 5;
+  const int words = (N + 31) >> 5;
+  const float thF = (float)3.841, thScore = (float)5.991, thH = (float)5.991;
+  for (int g = blockIdx.x * wpc + (threadIdx.x >> 5); g < 2 * n_hyp; g += gridDim.x * wpc) {
+    const int model = g / n_hyp;
+    const float* Mp = models + (size_t)g * 18;
+    float m[18];
+#pragma unroll
+    for (int i = 0; i < 18; i++) m[i] = Mp[i];
+    float score = 0.0f;
+    uint32_t* mw = masks + (size_t)g * words;
+    for (int base = 0; base < N; base += 32) {
+      const int i = base + lane;
+      float c1 = 0.0f, c2 = 0.0f;
+      bool bIn = false;
+      if (i < N) {
+        const float4 p = uvp[i];
+        const float u1 = p.x, v1 = p.y, u2 = p.z, v2 = p.w;
+        bIn = true;
+        if (model == 0) {
+          const float a2 = m[0] * u1 + m[1] * v1 + m[2];
+          const float b2 = m[3] * u1 + m[4] * v1 + m[5];
+          const float cc2 = m[6] * u1 + m[7] * v1 + m[8];
+          const float num2 = a2 * u2 + b2 * v2 + cc2;
+          const float squareDist1 = num2 * num2 / (a2 * a2 + b2 * b2);
+          const float chiSquare1 = squareDist1 * inv_sigma2;
+          if (chiSquare1 > thF) bIn = false; else c1 = thScore - chiSquare1;
+          const float a1 = m[0] * u2 + m[3] * v2 + m[6];
+          const float b1 = m[1] * u2 + m[4] * v2 + m[7];
+          const float cc1 = m[2] * u2 + m[5] * v2 + m[8];
+          const float num1 = a1 * u1 + b1 * v1 + cc1;
+          const float squareDist2 = num1 * num1 / (a1 * a1 + b1 * b1);
+          const float chiSquare2 = squareDist2 * inv_sigma2;
+          if (chiSquare2 > thF) bIn = false; else c2 = thScore - chiSquare2;
+        } else {
+          const float w2in1inv = 1.0f / (m[15] * u2 + m[16] * v2 + m[17]);
+          const float u2in1 = (m[9] * u2 + m[10] * v2 + m[11]) * w2in1inv;
+          const float v2in1 = (m[12] * u2 + m[13] * v2 + m[14]) * w2in1inv;
+          const float squareDist1 = (u1 - u2in1) * (u1 - u2in1) + (v1 - v2in1) * (v1 - v2in1);
+          const float chiSquare1 = squareDist1 * inv_sigma2;
+          if (chiSquare1 > thH) bIn = false; else c1 = thH - chiSquare1;
+          const float w1in2inv = 1.0f / (m[6] * u1 + m[7] * v1 + m[8]);
+          const float u1in2 = (m[0] * u1 + m[1] * v1 + m[2]) * w1in2inv;
+          const float v1in2 = (m[3] * u1 + m[4] * v1 + m[5]) * w1in2inv;
+          const float squareDist2 = (u2 - u1in2) * (u2 - u1in2) + (v2 - v1in2) * (v2 - v1in2);
+          const float chiSquare2 = squareDist2 * inv_sigma2;
+          if (chiSquare2 > thH) bIn = false; else c2 = thH - chiSquare2;
+        }
+      }
+      const uint32_t word = __ballot_sync(0xffffffffu, bIn);
+      if (lane == 0) mw[base >> 5] = word;
+      // the reference adds in match order (score += ... twice per match): replay that order
+      const int cnt = min(32, N - base);
+      for (int l = 0; l < cnt; l++) {
+        score += __shfl_sync(0xffffffffu, c1, l);
+        score += __shfl_sync(0xffffffffu, c2, l);
+      }
+    }
+    if (lane == 0) scores[g] = score;
+  }
+}
+
+// grid = 2 (F, H). best[model] = index of the highest score > 0 (earliest on ties) or -1.
+__global__ void tv_argmax_kernel(int n_hyp, const float* __restrict__ scores, int* __restrict__ best_idx,
+                                 float* __restrict__ best_score) {
+  const int model = blockIdx.x;
+  const float* s = scores + (size_t)model * n_hyp;
+  __shared__ float ss[256];
+  __shared__ int si[256];
+  float bs = 0.0f;
+  int bi = -1;
+  for (int i = threadIdx.x; i < n_hyp; i += blockDim.x) {
+    const float v = s[i];
+    if (v > bs) { bs = v; bi = i; }  // ascending i per thread: earliest wins inside a thread
+  }
+  ss[threadIdx.x] = bs;
+  si[threadIdx.x] = bi;
+  __syncthreads();
+  for (int off = blockDim.x >> 1; off > 0; off >>= 1) {
+    if ((int)threadIdx.x < off) {
+      const float v = ss[threadIdx.x + off];
+      const int j = si[threadIdx.x + off];
+      const float cur = ss[threadIdx.x];
+      const int ci = si[threadIdx.x];
+      if (j >= 0 && (v > cur || (v == cur && (ci < 0 || j < ci)))) { ss[threadIdx.x] = v; si[threadIdx.x] = j; }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { best_idx[model] = si[0]; best_score[model] = ss[0]; }
+}
+
+// ------------------------------------------------------------------------------- motion recovery
+
+
+// Single CTA.  P3D: [8][n1*3], good: [8][n1], cosbuf: [N] scratch.
+__global__ void __launch_bounds__(256)
+tv_motion_kernel(int N, int n1, int n_hyp, const float4* __restrict__ uv, const int* __restrict__ m1,
+                 const float* __restrict__ Kg, float th2, const float* __restrict__ models,
+                 const uint32_t* __restrict__ masks, const int* __restrict__ best_idx,
+                 const float* __restrict__ best_score, float* __restrict__ P3D,
+                 uint8_t* __restrict__ good, float* __restrict__ cosbuf, TVMotionOut* __restrict__ out) {
+  __shared__ float sR[8][9], st[8][3], sK[9];
+  __shared__ int s_nm, s_model, s_cnt[8];
+  __shared__ int s_red[256];
+  const int words = (N + 31) >> 5;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 9; i++) sK[i] = Kg[i];
+    const float SH = best_score[1], SF = best_score[0];
+    int nm = 0, used = -1;
+    if (SH + SF == 0.f) {
+      used = -1;
+    } else {
+      const float RH = SH / (SH + SF);
+      used = (RH > (float)0.50) ? 1 : 0;
+      if (used == 0) {
+        // _reconstruct_F: E = K^T F K, _decompose_E
+        const float* F21 = models + ((size_t)0 * n_hyp + best_idx[0]) * 18;
+        float Kt[9], tmp[9], E[9], Fl[9];
+        for (int i = 0; i < 9; i++) Fl[i] = F21[i];
+        mat3_T(sK, Kt);
+        mat3_mul(Kt, Fl, tmp);
+        mat3_mul(tmp, sK, E);
+        float U[9], w[3], V[9], Vt[9];
+        svd3(E, U, w, V);
+        mat3_T(V, Vt);
+        float t[3] = {U[2], U[5], U[8]};
+        const float tn = sqrtf(t[0] * t[0] + t[1] * t[1] + t[2] * t[2]);
+        for (int i = 0; i < 3; i++) t[i] = t[i] / tn;
+        const float W[9] = {0, -1, 0, 1, 0, 0, 0, 0, 1};
+        float Wt[9], R1[9], R2[9];
+        mat3_T(W, Wt);
+        mat3_mul(U, W, tmp);
+        mat3_mul(tmp, Vt, R1);
+        if (det3(R1) < 0) for (int i = 0; i < 9; i++) R1[i] = -R1[i];
+        mat3_mul(U, Wt, tmp);
+        mat3_mul(tmp, Vt, R2);
+        if (det3(R2) < 0) for (int i = 0; i < 9; i++) R2[i] = -R2[i];
+        for (int h = 0; h < 4; h++) {
+          const float* Rs = (h & 1) ? R2 : R1;
+          for (int i = 0; i < 9; i++) sR[h][i] = Rs[i];
+          for (int i = 0; i < 3; i++) st[h][i] = (h < 2) ? t[i] : -t[i];
+        }
+        nm = 4;
+      } else {
+        // _reconstruct_H: Faugeras' 8 hypotheses
+        const float* H21 = models + ((size_t)1 * n_hyp + best_idx[1]) * 18;
+        float invK[9], tmp[9], A[9], Hl[9];
+        for (int i = 0; i < 9; i++) Hl[i] = H21[i];
+        inv3f(sK, invK);
+        mat3_mul(invK, Hl, tmp);
+        mat3_mul(tmp, sK, A);
+        float U[9], w[3], V[9], Vt[9];
+        svd3(A, U, w, V);
+        mat3_T(V, Vt);
+        const float s = det3(U) * det3(Vt);
+        const float d1 = w[0], d2 = w[1], d3 = w[2];
+        if ((double)(d1 / d2) < 1.00001 || (double)(d2 / d3) < 1.00001) {
+          nm = 0;
+        } else {
+          const float aux1 = sqrtf((d1 * d1 - d2 * d2) / (d1 * d1 - d3 * d3));
+          const float aux3 = sqrtf((d2 * d2 - d3 * d3) / (d1 * d1 - d3 * d3));
+          const float x1[4] = {aux1, aux1, -aux1, -aux1};
+          const float x3[4] = {aux3, -aux3, aux3, -aux3};
+          const float aux_stheta = sqrtf((d1 * d1 - d2 * d2) * (d2 * d2 - d3 * d3)) / ((d1 + d3) * d2);
+          const float ctheta = (d2 * d2 + d1 * d3) / ((d1 + d3) * d2);
+          const float stheta[4] = {aux_stheta, -aux_stheta, -aux_stheta, aux_stheta};
+          float sU[9];
+          for (int i = 0; i < 9; i++) sU[i] = s * U[i];
+          for (int i = 0; i < 4; i++) {
+            const float Rp[9] = {ctheta, 0, -stheta[i], 0, 1.f, 0, stheta[i], 0, ctheta};
+            float Rr[9];
+            mat3_mul(sU, Rp, tmp);
+            mat3_mul(tmp, Vt, Rr);
+            for (int k = 0; k < 9; k++) sR[i][k] = Rr[k];
+            float tp[3] = {x1[i], 0, -x3[i]};
+            for (int k = 0; k < 3; k++) tp[k] *= d1 - d3;
+            float t[3];
+            for (int r = 0; r < 3; r++) t[r] = U[r * 3] * tp[0] + U[r * 3 + 1] * tp[1] + U[r * 3 + 2] * tp[2];
+            const float tn = sqrtf(t[0] * t[0] + t[1] * t[1] + t[2] * t[2]);
+            for (int r = 0; r < 3; r++) st[i][r] = t[r] / tn;
+          }
+          const float aux_sphi = sqrtf((d1 * d1 - d2 * d2) * (d2 * d2 - d3 * d3)) / ((d1 - d3) * d2);
+          const float cphi = (d1 * d3 - d2 * d2) / ((d1 - d3) * d2);
+          const float sphi[4] = {aux_sphi, -aux_sphi, -aux_sphi, aux_sphi};
+          for (int i = 0; i < 4; i++) {
+            const float Rp[9] = {cphi, 0, sphi[i], 0, -1, 0, sphi[i], 0, -cphi};
+            float Rr[9];
+            mat3_mul(sU, Rp, tmp);
+            mat3_mul(tmp, Vt, Rr);
+            for (int k = 0; k < 9; k++) sR[4 + i][k] = Rr[k];
+            float tp[3] = {x1[i], 0, x3[i]};
+            for (int k = 0; k < 3; k++) tp[k] *= d1 + d3;
+            float t[3];
+            for (int r = 0; r < 3; r++) t[r] = U[r * 3] * tp[0] + U[r * 3 + 1] * tp[1] + U[r * 3 + 2] * tp[2];
+            const float tn = sqrtf(t[0] * t[0] + t[1] * t[1] + t[2] * t[2]);
+            for (int r = 0; r < 3; r++) st[4 + i][r] = t[r] / tn;
+          }
+          nm = 8;
+        }
+      }
+    }
+    s_nm = nm;
+    s_model = used;
+    out->used_H = used;
+    out->n_motion = nm;
+    for (int h = 0; h < 8; h++) {
+      out->n_good[h] = 0;
+      out->cos_kth[h] = 1.0f;
+      for (int i = 0; i < 9; i++) out->R[h][i] = (h < nm) ? sR[h][i] : 0.0f;
+      for (int i = 0; i < 3; i++) out->t[h][i] = (h < nm) ? st[h][i] : 0.0f;
+    }
+  }
+  __syncthreads();
+  const int nm = s_nm, model = s_model;
+  if (model < 0) return;
+  const uint32_t* mask = masks + ((size_t)model * n_hyp + best_idx[model]) * words;
+  {  // N inliers of the selected model
+    int c = 0;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) c += (mask[i >> 5] >> (i & 31)) & 1u;
+    s_red[threadIdx.x] = c;
+    __syncthreads();
+    for (int off = blockDim.x >> 1; off > 0; off >>= 1) {
+      if ((int)threadIdx.x < off) s_red[threadIdx.x] += s_red[threadIdx.x + off];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) out->n_inl = s_red[0];
+    __syncthreads();
+  }
+  const float fx = sK[0], fy = sK[4], cx = sK[2], cy = sK[5];
+  for (int h = 0; h < nm; h++) {
+    // _check_R_T for motion hypothesis h
+    float R[9], t[3], P1[12], P2[12], O2[3];
+    for (int i = 0; i < 9; i++) R[i] = sR[h][i];
+    for (int i = 0; i < 3; i++) t[i] = st[h][i];
+    {
+      float Rt[12];
+      for (int i = 0; i < 3; i++) {
+        for (int j = 0; j < 3; j++) { P1[i * 4 + j] = sK[i * 3 + j]; Rt[i * 4 + j] = R[i * 3 + j]; }
+        P1[i * 4 + 3] = 0.0f;
+        Rt[i * 4 + 3] = t[i];
+      }
+      for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 4; j++)
+          P2[i * 4 + j] = sK[i * 3] * Rt[j] + sK[i * 3 + 1] * Rt[4 + j] + sK[i * 3 + 2] * Rt[8 + j];
+      for (int i = 0; i < 3; i++)
+        O2[i] = (-R[0 * 3 + i]) * t[0] + (-R[1 * 3 + i]) * t[1] + (-R[2 * 3 + i]) * t[2];
+    }
+    float* P3Dh = P3D + (size_t)h * n1 * 3;
+    uint8_t* goodh = good + (size_t)h * n1;
+    for (int i = threadIdx.x; i < n1; i += blockDim.x) {
+      goodh[i] = 0;
+      P3Dh[i * 3] = 0.0f; P3Dh[i * 3 + 1] = 0.0f; P3Dh[i * 3 + 2] = 0.0f;
+    }
+    __syncthreads();
+    int my_good = 0;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+      float cosv = 2.0f;  // marker: not counted
+      if ((mask[i >> 5] >> (i & 31)) & 1u) {
+        const float4 m = uv[i];
+        // _triangulate: null vector of the 4x4 DLT system
+        float A[16];
+        for (int j = 0; j < 4; j++) {
+          A[0 * 4 + j] = m.x * P1[2 * 4 + j] - P1[0 * 4 + j];
+          A[1 * 4 + j] = m.y * P1[2 * 4 + j] - P1[1 * 4 + j];
+          A[2 * 4 + j] = m.z * P2[2 * 4 + j] - P2[0 * 4 + j];
+          A[3 * 4 + j] = m.w * P2[2 * 4 + j] - P2[1 * 4 + j];
+        }
+        float v[4];
+        null_vector(4, 4, A, v);
+        float p[3] = {v[0] / v[3], v[1] / v[3], v[2] / v[3]};
+        if (isfinite(p[0]) && isfinite(p[1]) && isfinite(p[2])) {
+          const float dist1 = sqrtf(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
+          const float n2[3] = {p[0] - O2[0], p[1] - O2[1], p[2] - O2[2]};
+          const float dist2 = sqrtf(n2[0] * n2[0] + n2[1] * n2[1] + n2[2] * n2[2]);
+          const float cosParallax = (p[0] * n2[0] + p[1] * n2[1] + p[2] * n2[2]) / (dist1 * dist2);
+          const bool lowpar = (double)cosParallax < 0.99998;
+          bool ok = !(p[2] <= 0 && lowpar);
+          float p2[3];
+          for (int r = 0; r < 3; r++) p2[r] = (R[r * 3] * p[0] + R[r * 3 + 1] * p[1] + R[r * 3 + 2] * p[2]) + t[r];
+          if (ok && p2[2] <= 0 && lowpar) ok = false;
+          if (ok) {
+            const float invZ1 = 1.0f / p[2];
+            const float im1x = fx * p[0] * invZ1 + cx;
+            const float im1y = fy * p[1] * invZ1 + cy;
+            const float squareError1 = (im1x - m.x) * (im1x - m.x) + (im1y - m.y) * (im1y - m.y);
+            if (squareError1 > th2) ok = false;
+          }
+          if (ok) {
+            const float invZ2 = 1.0f / p2[2];
+            const float im2x = fx * p2[0] * invZ2 + cx;
+            const float im2y = fy * p2[1] * invZ2 + cy;
+            const float squareError2 = (im2x - m.z) * (im2x - m.z) + (im2y - m.w) * (im2y - m.w);
+            if (squareError2 > th2) ok = false;
+          }
+          if (ok) {
+            cosv = cosParallax;
+            const int k1 = m1[i];
+            P3Dh[k1 * 3] = p[0]; P3Dh[k1 * 3 + 1] = p[1]; P3Dh[k1 * 3 + 2] = p[2];
+            my_good++;
+            if (lowpar) goodh[k1] = 1;
+          }
+        }
+      }
+      cosbuf[i] = cosv;
+    }
+    s_red[threadIdx.x] = my_good;
+    __syncthreads();
+    for (int off = blockDim.x >> 1; off > 0; off >>= 1) {
+      if ((int)threadIdx.x < off) s_red[threadIdx.x] += s_red[threadIdx.x + off];
+      __syncthreads();
+    }
+    const int nGood = s_red[0];
+    __syncthreads();
+    if (threadIdx.x == 0) { out->n_good[h] = nGood; s_cnt[h] = nGood; }
+    if (nGood > 0) {
+      // element of rank min(50, nGood-1) of the sorted cosines, by rank counting
+      const int kth = min(50, nGood - 1);
+      for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        const float ci = cosbuf[i];
+        if (ci > 1.5f) continue;
+        int rank = 0;
+        for (int j = 0; j < N; j++) {
+          const float cj = cosbuf[j];
+          rank += (cj < ci || (cj == ci && j < i)) ? 1 : 0;
+        }
+        if (rank == kth) out->cos_kth[h] = ci;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+cudaError_t launch_tv_ransac(const TVBuffers& b, float sigma, int n_sm, cudaStream_t stream, int* n_launch) {
+  int nl = 0;
+  tv_normalize_kernel<<<2, 256, 0, stream>>>(b.n1, b.keys1, b.pn1, b.T1, b.n2, b.keys2, b.pn2, b.T2);
+  nl++;
+  tv_gather_kernel<<<(b.N + 255) / 256, 256, 0, stream>>>(b.N, b.m1, b.m2, b.keys1, b.keys2, b.pn1, b.pn2, b.uv, b.pnm);
+  nl++;
+  tv_fit_kernel<<<(2 * b.n_hyp + 63) / 64, 64, 0, stream>>>(b.n_hyp, b.sets, b.pnm, b.T1, b.T2, b.models);
+  nl++;
+  const float inv_sigma2 = 1.0f / (sigma * sigma);
+  const size_t smem = (size_t)b.N * sizeof(float4);
+  const int stage = smem <= 160 * 1024 ? 1 : 0;
+  if (stage && smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(tv_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  const int wpc = 8;
+  int grid = (2 * b.n_hyp + wpc - 1) / wpc;
+  const int cap = n_sm * 8;
+  if (grid > cap) grid = cap;
+  tv_score_kernel<<<grid, wpc * 32, stage ? smem : 0, stream>>>(b.N, b.n_hyp, b.uv, b.models, inv_sigma2, stage, b.scores, b.masks);
+  nl++;
+  tv_argmax_kernel<<<2, 256, 0, stream>>>(b.n_hyp, b.scores, b.best_idx, b.best_score);
+  nl++;
+  if (n_launch) *n_launch = nl;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_tv_motion(const TVBuffers& b, float th2, cudaStream_t stream) {
+  tv_motion_kernel<<<1, 256, 0, stream>>>(b.N, b.n1, b.n_hyp, b.uv, b.m1, b.K, th2, b.models, b.masks,
+                                          b.best_idx, b.best_score, b.P3D, b.good, b.cosbuf, b.motion);
+  return cudaGetLastError();
+}
+
+}  // namespace urmvo

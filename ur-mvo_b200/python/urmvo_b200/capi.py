@@ -1,0 +1,309 @@
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_PKG_ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), "..", ".."))  # ur-mvo_b200/
+_LIB = None
+
+EXPORTED_SYMBOLS = [
+    "urmvo_version", "urmvo_last_error", "urmvo_create", "urmvo_destroy", "urmvo_stream", "urmvo_sync",
+    "urmvo_launch_count", "urmvo_local_ba", "urmvo_local_ba_batch", "urmvo_ba_plan_create",
+    "urmvo_ba_plan_run", "urmvo_ba_plan_download", "urmvo_ba_plan_destroy", "urmvo_pose_only_batch",
+    "urmvo_pose_plan_create", "urmvo_pose_plan_run", "urmvo_pose_plan_download", "urmvo_pose_plan_destroy",
+    "urmvo_two_view", "urmvo_tv_plan_create", "urmvo_tv_plan_run_ransac", "urmvo_tv_plan_download_hyps",
+    "urmvo_tv_plan_reconstruct", "urmvo_tv_plan_destroy",
+]
+
+
+class UrmvoError(RuntimeError):
+    pass
+
+
+class BAOptions(C.Structure):
+    _fields_ = [("pcg_tol", C.c_double), ("pcg_max_iter", C.c_int32), ("cluster_size", C.c_int32),
+                ("threads", C.c_int32), ("reserved", C.c_int32)]
+
+
+class BAStats(C.Structure):
+    _fields_ = [("iters", C.c_int32 * 2), ("trials", C.c_int32 * 2), ("pcg_iters", C.c_int32 * 2),
+                ("n_level1", C.c_int32), ("chi2_initial", C.c_double), ("chi2_final", C.c_double * 2),
+                ("lambda_final", C.c_double * 2)]
+
+
+class TVStats(C.Structure):
+    _fields_ = [("SH", C.c_float), ("SF", C.c_float), ("best_H", C.c_int32), ("best_F", C.c_int32),
+                ("H21", C.c_float * 9), ("F21", C.c_float * 9), ("used_H", C.c_int32),
+                ("n_good", C.c_int32 * 8), ("parallax", C.c_float * 8), ("best_motion", C.c_int32)]
+
+
+def lib_path():
+    return os.path.join(_PKG_ROOT, "lib", "liburmvo_b200.so")
+
+
+def build_library():
+    subprocess.check_call(["make", "-C", _PKG_ROOT, "-s"])
+    return lib_path()
+
+
+def load_library():
+    """Loads liburmvo_b200.so. Raises (never falls back) when the CUDA extension is missing."""
+    global _LIB
+    if _LIB is None:
+        path = lib_path()
+        if not os.path.exists(path):
+            raise UrmvoError(f"{path} is missing: build it with `make -C {_PKG_ROOT}` "
+                             "(python __graft_entry__.py build). There is no CPU fallback.")
+        L = C.CDLL(path)
+        L.urmvo_last_error.restype = C.c_char_p
+        L.urmvo_stream.restype = C.c_void_p
+        L.urmvo_launch_count.restype = C.c_int64
+        for name in EXPORTED_SYMBOLS:
+            f = getattr(L, name)
+            if name not in ("urmvo_last_error", "urmvo_stream", "urmvo_launch_count", "urmvo_destroy",
+                            "urmvo_ba_plan_destroy", "urmvo_pose_plan_destroy", "urmvo_tv_plan_destroy"):
+                f.restype = C.c_int
+        for name in ("urmvo_destroy", "urmvo_ba_plan_destroy", "urmvo_pose_plan_destroy", "urmvo_tv_plan_destroy"):
+            getattr(L, name).restype = None
+        _LIB = L
+    return _LIB
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise UrmvoError(f"{what} failed ({rc}): {load_library().urmvo_last_error().decode()}")
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _u8(a):
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+class Context:
+    def __init__(self, device=0):
+        self._L = load_library()
+        self._h = C.c_void_p()
+        _check(self._L.urmvo_create(C.byref(self._h), C.c_int(device)), "urmvo_create")
+
+    def close(self):
+        if self._h:
+            self._L.urmvo_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def stream(self):
+        return self._L.urmvo_stream(self._h)
+
+    def sync(self):
+        _check(self._L.urmvo_sync(self._h), "urmvo_sync")
+
+    @property
+    def launches(self):
+        return int(self._L.urmvo_launch_count(self._h))
+
+    # ---- one-shot, host buffers in / out (the reference-facing calls)
+    def local_ba(self, prob, chi2_thr=10.0, it0=10, it1=5, opts=None):
+        poses = _f64(prob["poses"]).copy(); pts = _f64(prob["pts"]).copy()
+        fixed = _u8(prob["fixed"]); uv = _f64(prob["uv"]); cam = _i32(prob["obs_cam"]); pt = _i32(prob["obs_pt"])
+        intr = _f64(prob["intr"])
+        inl = np.zeros(uv.shape[0], dtype=np.uint8)
+        st = BAStats()
+        _check(self._L.urmvo_local_ba(self._h, C.c_int(poses.shape[0]), _p(poses), _p(fixed), C.c_int(pts.shape[0]),
+                                      _p(pts), C.c_int(uv.shape[0]), _p(uv), _p(cam), _p(pt), _p(intr),
+                                      C.c_double(chi2_thr), C.c_int(it0), C.c_int(it1), _p(inl), C.byref(st),
+                                      C.byref(opts) if opts is not None else None), "urmvo_local_ba")
+        return poses, pts, inl, st
+
+    def local_ba_batch(self, batch, chi2_thr=10.0, it0=10, it1=5, opts=None, out=None):
+        """batch: dict from pack_ba_batch(). Returns (poses, pts, inlier, [BAStats])."""
+        B = len(batch["cam_off"]) - 1
+        poses = batch["poses"].copy() if out is None else out["poses"]
+        pts = batch["pts"].copy() if out is None else out["pts"]
+        if out is not None:
+            poses[...] = batch["poses"]; pts[...] = batch["pts"]
+        inl = np.zeros(batch["uv"].shape[0], dtype=np.uint8) if out is None else out["inlier"]
+        st = (BAStats * B)()
+        _check(self._L.urmvo_local_ba_batch(self._h, C.c_int(B), _p(batch["cam_off"]), _p(batch["pt_off"]),
+                                            _p(batch["obs_off"]), _p(poses), _p(batch["fixed"]), _p(pts),
+                                            _p(batch["uv"]), _p(batch["obs_cam"]), _p(batch["obs_pt"]),
+                                            _p(batch["intr"]), C.c_double(chi2_thr), C.c_int(it0), C.c_int(it1),
+                                            _p(inl), st, C.byref(opts) if opts is not None else None),
+               "urmvo_local_ba_batch")
+        return poses, pts, inl, list(st)
+
+    def pose_only_batch(self, batch, chi2_thr=10.0, rounds=4, its=10, inlier=None):
+        poses = _f64(batch["poses"]).copy()
+        off = _i32(batch["obs_offset"]); uv = _f64(batch["uv"]); Xw = _f64(batch["Xw"]); intr = _f64(batch["intr"])
+        inl = np.ones(uv.shape[0], dtype=np.uint8) if inlier is None else _u8(inlier).copy()
+        n_inl = np.zeros(poses.shape[0], dtype=np.int32)
+        _check(self._L.urmvo_pose_only_batch(self._h, C.c_int(poses.shape[0]), _p(off), _p(poses), _p(uv), _p(Xw),
+                                             _p(intr), C.c_double(chi2_thr), C.c_int(rounds), C.c_int(its),
+                                             _p(inl), _p(n_inl)), "urmvo_pose_only_batch")
+        return poses, inl, n_inl
+
+    def two_view(self, tv, sets=None):
+        k1 = _f32(tv["keys1"]); k2 = _f32(tv["keys2"]); m = _i32(tv["matches12"]); K = _f32(tv["K"])
+        sets = _i32(tv["sets"] if sets is None else sets)
+        N = int((m >= 0).sum())
+        T21 = np.zeros((4, 4), dtype=np.float32); P3D = np.zeros((k1.shape[0], 3), dtype=np.float32)
+        tri = np.zeros(k1.shape[0], dtype=np.uint8)
+        mH = np.zeros(N, dtype=np.uint8); mF = np.zeros(N, dtype=np.uint8)
+        st = TVStats(); ok = C.c_int(0)
+        _check(self._L.urmvo_two_view(self._h, C.c_int(k1.shape[0]), _p(k1), C.c_int(k2.shape[0]), _p(k2), _p(m),
+                                      _p(K), C.c_float(tv.get("sigma", 1.0)), C.c_int(sets.shape[0]), _p(sets),
+                                      _p(T21), _p(P3D), _p(tri), _p(mH), _p(mF), C.byref(st), C.byref(ok)),
+               "urmvo_two_view")
+        return dict(ok=bool(ok.value), T21=T21, P3D=P3D, triangulated=tri, mask_H=mH, mask_F=mF, stats=st)
+
+
+def pack_ba_batch(probs):
+    """Concatenates BA problems (dicts like synth.make_ba) into the batch layout of the C ABI."""
+    cam_off = np.zeros(len(probs) + 1, dtype=np.int32)
+    pt_off = np.zeros(len(probs) + 1, dtype=np.int32)
+    obs_off = np.zeros(len(probs) + 1, dtype=np.int32)
+    for i, p in enumerate(probs):
+        cam_off[i + 1] = cam_off[i] + p["poses"].shape[0]
+        pt_off[i + 1] = pt_off[i] + p["pts"].shape[0]
+        obs_off[i + 1] = obs_off[i] + p["uv"].shape[0]
+    cat = lambda k, dt: np.ascontiguousarray(np.concatenate([np.asarray(p[k]) for p in probs], axis=0), dtype=dt)
+    return dict(cam_off=cam_off, pt_off=pt_off, obs_off=obs_off, poses=cat("poses", np.float64),
+                fixed=cat("fixed", np.uint8), pts=cat("pts", np.float64), uv=cat("uv", np.float64),
+                obs_cam=cat("obs_cam", np.int32), obs_pt=cat("obs_pt", np.int32), intr=_f64(probs[0]["intr"]))
+
+
+class BAPlan:
+    """Device-resident batch of BA windows: upload once, run() many times, download()."""
+
+    def __init__(self, ctx, batch, chi2_thr=10.0, it0=10, it1=5, opts=None):
+        self._L = ctx._L
+        self.ctx = ctx
+        self.B = len(batch["cam_off"]) - 1
+        self.shapes = (batch["poses"].shape, batch["pts"].shape, batch["uv"].shape[0])
+        self._h = C.c_void_p()
+        _check(self._L.urmvo_ba_plan_create(ctx._h, C.byref(self._h), C.c_int(self.B), _p(batch["cam_off"]),
+                                            _p(batch["pt_off"]), _p(batch["obs_off"]), _p(batch["poses"]),
+                                            _p(batch["fixed"]), _p(batch["pts"]), _p(batch["uv"]),
+                                            _p(batch["obs_cam"]), _p(batch["obs_pt"]), _p(batch["intr"]),
+                                            C.c_double(chi2_thr), C.c_int(it0), C.c_int(it1),
+                                            C.byref(opts) if opts is not None else None), "urmvo_ba_plan_create")
+
+    def run(self):
+        _check(self._L.urmvo_ba_plan_run(self._h), "urmvo_ba_plan_run")
+
+    def download(self):
+        poses = np.zeros(self.shapes[0]); pts = np.zeros(self.shapes[1]); inl = np.zeros(self.shapes[2], dtype=np.uint8)
+        st = (BAStats * self.B)()
+        _check(self._L.urmvo_ba_plan_download(self._h, _p(poses), _p(pts), _p(inl), st), "urmvo_ba_plan_download")
+        return poses, pts, inl, list(st)
+
+    def close(self):
+        if self._h:
+            self._L.urmvo_ba_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class PosePlan:
+    def __init__(self, ctx, batch, chi2_thr=10.0, rounds=4, its=10, inlier=None):
+        self._L = ctx._L
+        self.ctx = ctx
+        self.B = batch["poses"].shape[0]
+        self.No = batch["uv"].shape[0]
+        self._keep = [_i32(batch["obs_offset"]), _f64(batch["poses"]), _f64(batch["uv"]), _f64(batch["Xw"]), _f64(batch["intr"])]
+        inl = None if inlier is None else _u8(inlier)
+        self._h = C.c_void_p()
+        k = self._keep
+        _check(self._L.urmvo_pose_plan_create(ctx._h, C.byref(self._h), C.c_int(self.B), _p(k[0]), _p(k[1]), _p(k[2]),
+                                              _p(k[3]), _p(k[4]), C.c_double(chi2_thr), C.c_int(rounds), C.c_int(its),
+                                              _p(inl)), "urmvo_pose_plan_create")
+
+    def run(self):
+        _check(self._L.urmvo_pose_plan_run(self._h), "urmvo_pose_plan_run")
+
+    def download(self):
+        poses = np.zeros((self.B, 7)); inl = np.zeros(self.No, dtype=np.uint8)
+        n_inl = np.zeros(self.B, dtype=np.int32); iters = np.zeros(self.B, dtype=np.int32)
+        _check(self._L.urmvo_pose_plan_download(self._h, _p(poses), _p(inl), _p(n_inl), _p(iters)), "urmvo_pose_plan_download")
+        return poses, inl, n_inl, iters
+
+    def close(self):
+        if self._h:
+            self._L.urmvo_pose_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class TVPlan:
+    def __init__(self, ctx, tv, sets=None):
+        self._L = ctx._L
+        self.ctx = ctx
+        k1 = _f32(tv["keys1"]); k2 = _f32(tv["keys2"]); m = _i32(tv["matches12"]); K = _f32(tv["K"])
+        sets = _i32(tv["sets"] if sets is None else sets)
+        self.n1 = k1.shape[0]; self.N = int((m >= 0).sum()); self.n_hyp = sets.shape[0]
+        self.words = (self.N + 31) // 32
+        self._h = C.c_void_p()
+        _check(self._L.urmvo_tv_plan_create(ctx._h, C.byref(self._h), C.c_int(k1.shape[0]), _p(k1), C.c_int(k2.shape[0]),
+                                            _p(k2), _p(m), _p(K), C.c_float(tv.get("sigma", 1.0)), C.c_int(self.n_hyp),
+                                            _p(sets)), "urmvo_tv_plan_create")
+
+    def run_ransac(self):
+        _check(self._L.urmvo_tv_plan_run_ransac(self._h), "urmvo_tv_plan_run_ransac")
+
+    def download_hyps(self, model):
+        scores = np.zeros(self.n_hyp, dtype=np.float32)
+        masks = np.zeros((self.n_hyp, self.words), dtype=np.uint32)
+        models = np.zeros((self.n_hyp, 9), dtype=np.float32)
+        _check(self._L.urmvo_tv_plan_download_hyps(self._h, C.c_int(model), _p(scores), _p(masks), _p(models)),
+               "urmvo_tv_plan_download_hyps")
+        return scores, masks, models
+
+    def reconstruct(self):
+        T21 = np.zeros((4, 4), dtype=np.float32); P3D = np.zeros((self.n1, 3), dtype=np.float32)
+        tri = np.zeros(self.n1, dtype=np.uint8)
+        mH = np.zeros(self.N, dtype=np.uint8); mF = np.zeros(self.N, dtype=np.uint8)
+        st = TVStats(); ok = C.c_int(0)
+        _check(self._L.urmvo_tv_plan_reconstruct(self._h, _p(T21), _p(P3D), _p(tri), _p(mH), _p(mF), C.byref(st),
+                                                 C.byref(ok)), "urmvo_tv_plan_reconstruct")
+        return dict(ok=bool(ok.value), T21=T21, P3D=P3D, triangulated=tri, mask_H=mH, mask_F=mF, stats=st)
+
+    def close(self):
+        if self._h:
+            self._L.urmvo_tv_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
