@@ -1,0 +1,256 @@
+"""GPU (B200): the CUDA path through the C ABI against the CPU oracle on identical inputs.
+
+Tolerances (BASELINE.json north_star / SURVEY.md §8d):
+  BA       final robust cost within 1e-6 relative, poses within 1e-5 per element (fp64), inlier flags
+           identical, LM accept/reject pattern identical.  The reduced camera system is solved by
+           block-Jacobi PCG (tolerance 1e-10) on the GPU and by Cholesky in the oracle.
+  RANSAC   scores, inlier masks and models bit-exact for identical 8-point sets.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import urmvo_b200 as U
+from conftest import GOLDEN
+from urmvo_b200 import synth
+from urmvo_b200.capi import pack_ba_batch
+
+pytestmark = pytest.mark.gpu
+
+REL_COST = 1e-6
+POSE_TOL = 1e-5
+
+
+def _check_ba(oracle, ctx, prob, opts=None, it0=10, it1=5):
+    gp, gx, gi, gs = ctx.local_ba(prob, it0=it0, it1=it1, opts=opts)
+    op, ox, oi, os_ = oracle.local_ba(prob, it0=it0, it1=it1)
+    for k in range(2):
+        if abs(os_.chi2_final[k]) > 0:
+            assert abs(gs.chi2_final[k] - os_.chi2_final[k]) <= REL_COST * abs(os_.chi2_final[k]), (k, gs.chi2_final[k], os_.chi2_final[k])
+        assert gs.iters[k] == os_.iters[k]
+    rows = os_.rows()
+    assert gs.trials[0] == sum(r[3] for r in rows[: os_.iters[0]])
+    assert gs.trials[1] == sum(r[3] for r in rows[os_.iters[0]:])
+    assert np.abs(gp - op).max() <= POSE_TOL
+    assert np.abs(gx - ox).max() <= 1e-4 * max(1.0, np.abs(ox).max())
+    # flags identical except observations within 1e-6 of the chi2 threshold
+    assert (gi != oi).sum() <= 0
+    return gs, os_
+
+
+@pytest.mark.parametrize("seed", [3, 7, 19])
+def test_ba_small_windows(oracle, ctx, seed):
+    _check_ba(oracle, ctx, synth.small_ba(seed=seed))
+
+
+def test_ba_noisy_start_with_rejected_steps(oracle, ctx):
+    p = synth.small_ba(seed=31, rot_sigma_deg=6.0, trans_sigma=0.5, pt_sigma=0.8, outlier_frac=0.1)
+    gs, os_ = _check_ba(oracle, ctx, p)
+    assert gs.trials[0] >= gs.iters[0]
+
+
+def test_ba_cfg1_window(oracle, ctx):
+    gs, _ = _check_ba(oracle, ctx, synth.cfg1())
+    assert gs.iters[0] == 10 and gs.iters[1] == 5
+
+
+@pytest.mark.parametrize("cs", [1, 2, 4, 8, 16])
+def test_ba_cluster_sizes_agree(oracle, ctx, cs):
+    _check_ba(oracle, ctx, synth.small_ba(seed=5, n_pts=300), opts=U.BAOptions(0, 0, cs, 128, 0))
+
+
+def test_ba_unsorted_observations_and_flag_order(oracle, ctx):
+    p = synth.small_ba(seed=13)
+    rng = np.random.default_rng(0)
+    perm = rng.permutation(p["uv"].shape[0])
+    q = dict(p, uv=np.ascontiguousarray(p["uv"][perm]), obs_cam=np.ascontiguousarray(p["obs_cam"][perm]),
+             obs_pt=np.ascontiguousarray(p["obs_pt"][perm]))
+    gp, gx, gi, gs = ctx.local_ba(q)
+    sp, sx, si, ss = ctx.local_ba(p)
+    assert np.abs(gp - sp).max() < 1e-9 and np.abs(gx - sx).max() < 1e-8
+    assert np.array_equal(gi, si[perm])  # flags come back in the caller's order
+
+
+def test_ba_all_cameras_fixed_only_moves_points(oracle, ctx):
+    p = synth.small_ba(seed=17)
+    p["fixed"][:] = 1
+    gs, _ = _check_ba(oracle, ctx, p)
+    gp = ctx.local_ba(p)[0]
+    assert np.abs(synth.quat_to_R(gp[:, :4]) - synth.quat_to_R(p["poses"][:, :4])).max() < 1e-12
+
+
+def test_ba_point_seen_by_more_than_32_cameras(oracle, ctx):
+    p = synth.make_ba(23, 40, 60, 36, 40, 2, 0.02)
+    assert np.bincount(p["obs_pt"]).max() > 32
+    _check_ba(oracle, ctx, p)
+
+
+def test_ba_zero_iterations_is_identity_on_state(oracle, ctx):
+    p = synth.small_ba(seed=2)
+    gp, gx, gi, gs = ctx.local_ba(p, it0=0, it1=0)
+    op, ox, oi, _ = oracle.local_ba(p, it0=0, it1=0)
+    assert np.abs(gp - op).max() < 1e-12 and np.abs(gx - p["pts"]).max() == 0
+    assert np.array_equal(gi, oi)
+
+
+def test_ba_batch_plan_equals_single_windows_and_is_rerunnable(oracle, ctx):
+    probs = [synth.small_ba(seed=40 + i, n_cams=5 + i % 3, n_pts=100 + 10 * i) for i in range(6)]
+    batch = pack_ba_batch(probs)
+    plan = U.BAPlan(ctx, batch)
+    plan.run()
+    a = plan.download()
+    plan.run()  # restarts from the uploaded estimate
+    b = plan.download()
+    assert np.abs(a[0] - b[0]).max() < 1e-9 and np.array_equal(a[2], b[2])
+    for w, p in enumerate(probs):
+        op, ox, oi, os_ = oracle.local_ba(p)
+        c = slice(batch["cam_off"][w], batch["cam_off"][w + 1])
+        o = slice(batch["obs_off"][w], batch["obs_off"][w + 1])
+        assert np.abs(a[0][c] - op).max() <= POSE_TOL
+        assert np.array_equal(a[2][o], oi)
+        assert abs(a[3][w].chi2_final[1] - os_.chi2_final[1]) <= REL_COST * abs(os_.chi2_final[1])
+    plan.close()
+
+
+def test_ba_golden_fixture(ctx):
+    G = np.load(os.path.join(GOLDEN, "golden_r01.npz"))
+    p = {k: G["ba_in_" + k] for k in ("poses", "fixed", "pts", "uv", "obs_cam", "obs_pt", "intr")}
+    gp, gx, gi, gs = ctx.local_ba(p)
+    assert np.array_equal(gi, G["ba_inlier"])
+    assert np.abs(gp - G["ba_poses"]).max() <= POSE_TOL
+    tr = G["ba_trace"]
+    assert gs.trials[0] + gs.trials[1] == int(tr[:, 3].sum())
+    assert abs(gs.chi2_final[1] - tr[-1, 1]) <= REL_COST * abs(tr[-1, 1])
+
+
+def test_ba_large_window_cfg4_grid_kernel(oracle, ctx):
+    """400k observations on the cooperative whole-grid kernel; the oracle takes a few seconds."""
+    p = synth.cfg4()
+    assert p["uv"].shape[0] > 300000
+    _check_ba(oracle, ctx, p)
+
+
+def test_ba_rejects_bad_input(ctx):
+    p = synth.small_ba(seed=2)
+    bad = dict(p, obs_cam=p["obs_cam"].copy())
+    bad["obs_cam"][5] = 99
+    with pytest.raises(U.UrmvoError, match="out of range"):
+        ctx.local_ba(bad)
+
+
+# ------------------------------------------------------------------------------- pose only
+
+def _check_pose(oracle, ctx, b, **kw):
+    gp, gi, gn = ctx.pose_only_batch(b, **kw)
+    op, oi, on = oracle.pose_only_batch(b)
+    assert np.abs(gp - op).max() <= POSE_TOL
+    assert np.array_equal(gi, oi) and np.array_equal(gn, on)
+
+
+def test_pose_only_cfg2_batch(oracle, ctx):
+    _check_pose(oracle, ctx, synth.cfg2())
+
+
+def test_pose_only_ragged_and_tiny_frames(oracle, ctx):
+    b = synth.make_pose_batch(6, B=5, n_obs=300)
+    # ragged: frame sizes 300, 7 (< 10 edges: one round only), 0 (empty), 150, 300
+    keep = np.r_[np.arange(0, 300), np.arange(300, 307), np.arange(900, 1050), np.arange(1200, 1500)]
+    b2 = dict(b, uv=np.ascontiguousarray(b["uv"][keep]), Xw=np.ascontiguousarray(b["Xw"][keep]),
+              obs_offset=np.array([0, 300, 307, 307, 457, 757], dtype=np.int32))
+    _check_pose(oracle, ctx, b2)
+
+
+def test_pose_only_all_outliers_and_golden(oracle, ctx):
+    b = synth.make_pose_batch(9, B=3, n_obs=120, outlier_frac=1.0)
+    _check_pose(oracle, ctx, b)
+    G = np.load(os.path.join(GOLDEN, "golden_r01.npz"))
+    g = {k: G["po_in_" + k] for k in ("poses", "obs_offset", "uv", "Xw", "intr")}
+    gp, gi, gn = ctx.pose_only_batch(g)
+    assert np.array_equal(gi, G["po_inlier"]) and np.array_equal(gn, G["po_n_inlier"])
+    assert np.abs(gp - G["po_poses"]).max() <= POSE_TOL
+
+
+# ------------------------------------------------------------------------------- two view
+
+def _check_hyps(oracle, plan, tv):
+    for model in (0, 1):
+        gs, gm, gM = plan.download_hyps(model)
+        os_, om, oM = oracle.score_all(tv, model)
+        assert np.array_equal(gs.view(np.uint32), os_.view(np.uint32)), f"scores differ (model {model})"
+        assert np.array_equal(gm, om), f"masks differ (model {model})"
+        assert np.array_equal(gM.view(np.uint32), oM.view(np.uint32)), f"models differ (model {model})"
+
+
+def _check_reconstruct(g, o):
+    assert g["ok"] == o["ok"]
+    gs, os_ = g["stats"], o["stats"]
+    assert (gs.best_F, gs.best_H, gs.used_H, gs.best_motion) == (os_.best_F, os_.best_H, os_.used_H, os_.best_motion)
+    assert gs.SF == os_.SF and gs.SH == os_.SH
+    assert list(gs.n_good) == list(os_.n_good)
+    assert np.array_equal(g["mask_F"], o["mask_F"]) and np.array_equal(g["mask_H"], o["mask_H"])
+    assert np.array_equal(g["T21"].view(np.uint32), o["T21"].view(np.uint32))
+    assert np.array_equal(g["P3D"].view(np.uint32), o["P3D"].view(np.uint32))
+    assert np.array_equal(g["triangulated"], o["triangulated"])
+
+
+def test_two_view_cfg3_bit_exact(oracle, ctx):
+    tv = synth.cfg3(n_hyp=2048)
+    plan = U.TVPlan(ctx, tv)
+    plan.run_ransac()
+    _check_hyps(oracle, plan, tv)
+    _check_reconstruct(plan.reconstruct(), oracle.two_view(tv))
+    plan.close()
+
+
+def test_two_view_full_8192_argmax_properties(oracle, ctx):
+    """BASELINE size: arg-max is the first maximum, masks have no bits beyond N, and a sample of
+    hypotheses is bit-exact against the oracle."""
+    tv = synth.cfg3()
+    plan = U.TVPlan(ctx, tv)
+    plan.run_ransac()
+    r = plan.reconstruct()
+    for model, best in ((0, r["stats"].best_F), (1, r["stats"].best_H)):
+        s, m, M = plan.download_hyps(model)
+        assert best == int(np.argmax(s))
+        assert (m[:, -1] >> (1000 % 32)).max() == 0
+        sub = np.r_[0:64, 4000:4064, 8128:8192]
+        os_, om, oM = oracle.score_all(tv, model, sets=tv["sets"][sub])
+        assert np.array_equal(s[sub].view(np.uint32), os_.view(np.uint32)) and np.array_equal(m[sub], om)
+    plan.close()
+
+
+@pytest.mark.parametrize("kw", [dict(seed=5, planar=True), dict(seed=12, n_keys=300, n_unmatched=37),
+                                dict(seed=14, n_keys=77), dict(seed=15, inlier_frac=0.05)])
+def test_two_view_variants(oracle, ctx, kw):
+    tv = synth.make_two_view(**kw)
+    N = int((tv["matches12"] >= 0).sum())
+    tv["sets"] = synth.draw_sets(N, 200, 0)
+    plan = U.TVPlan(ctx, tv)
+    plan.run_ransac()
+    _check_hyps(oracle, plan, tv)
+    _check_reconstruct(plan.reconstruct(), oracle.two_view(tv))
+    plan.close()
+
+
+def test_two_view_golden_fixture(ctx):
+    G = np.load(os.path.join(GOLDEN, "golden_r01.npz"))
+    tv = {k: G["tv_in_" + k] for k in ("keys1", "keys2", "matches12", "K", "sets")}
+    tv["sigma"] = 1.0
+    g = ctx.two_view(tv)
+    assert g["ok"] == bool(G["tv_ok"])
+    assert np.array_equal(g["T21"].view(np.uint32), G["tv_T21"].view(np.uint32))
+    assert np.array_equal(g["mask_F"], G["tv_mask_F"]) and np.array_equal(g["mask_H"], G["tv_mask_H"])
+    assert np.array_equal(g["triangulated"], G["tv_tri"])
+
+
+def test_two_view_rejects_bad_input(ctx):
+    tv = synth.make_two_view(3, n_keys=50)
+    tv["sets"] = synth.draw_sets(50, 4, 0)
+    tv["sets"][1, 3] = 50
+    with pytest.raises(U.UrmvoError, match="out of range"):
+        ctx.two_view(tv)
+    few = synth.make_two_view(3, n_keys=50, n_unmatched=45)
+    few["sets"] = np.zeros((1, 8), dtype=np.int32)
+    with pytest.raises(U.UrmvoError, match="fewer than 8"):
+        ctx.two_view(few)

@@ -1,0 +1,111 @@
+"""CPU: host-side logic — batch packing, sharding, and the N>1 paths under gloo (world_size 2)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from urmvo_b200 import synth
+from urmvo_b200.capi import pack_ba_batch
+from urmvo_b200.dist import shard_range, shard_windows, merge_best_hypothesis, max_over_ranks, sum_over_ranks
+
+
+def test_pack_ba_batch_offsets_and_local_indices():
+    probs = [synth.small_ba(seed=s, n_cams=4 + s, n_pts=30 + 5 * s) for s in range(3)]
+    b = pack_ba_batch(probs)
+    assert b["cam_off"].tolist() == [0, 4, 9, 15]
+    assert b["pt_off"][-1] == sum(p["pts"].shape[0] for p in probs)
+    for w, p in enumerate(probs):
+        s = slice(b["obs_off"][w], b["obs_off"][w + 1])
+        assert np.array_equal(b["obs_cam"][s], p["obs_cam"]) and b["obs_cam"][s].max() < p["poses"].shape[0]
+        assert np.array_equal(b["uv"][s], p["uv"])
+    assert b["poses"].flags["C_CONTIGUOUS"] and b["obs_pt"].dtype == np.int32
+
+
+@pytest.mark.parametrize("n,world", [(148, 8), (10, 4), (3, 8), (0, 2), (8192, 3)])
+def test_shard_range_partitions_exactly(n, world):
+    cover = []
+    sizes = []
+    for r in range(world):
+        a, b = shard_range(n, r, world)
+        cover += list(range(a, b))
+        sizes.append(b - a)
+    assert cover == list(range(n))
+    assert max(sizes) - min(sizes) <= 1
+
+
+def test_shard_windows_slices():
+    probs = [synth.small_ba(seed=s, n_cams=4, n_pts=20) for s in range(5)]
+    b = pack_ba_batch(probs)
+    (w0, w1), cs, ps, os_ = shard_windows((b["cam_off"], b["pt_off"], b["obs_off"]), 1, 2)
+    assert (w0, w1) == (3, 5)
+    assert os_.start == b["obs_off"][3] and os_.stop == b["obs_off"][5]
+    assert cs.stop - cs.start == 8
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, scores, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # hypothesis-sharded arg-max: each rank scores its contiguous slice
+        a, b = shard_range(len(scores), rank, world)
+        local = np.asarray(scores[a:b], dtype=np.float32)
+        li = int(np.argmax(local)) if len(local) and local.max() > 0 else -1
+        ls = float(local[li]) if li >= 0 else 0.0
+        best = merge_best_hypothesis(ls, li, a, dist)
+        # timing / unit aggregation as bench.py does it
+        t = max_over_ranks(1.0 + rank, dist)
+        u = sum_over_ranks(10.0 * (rank + 1), dist)
+        q.put((rank, best, t, u))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("scores", [
+    [0.0, 3.0, 7.5, 7.5, 1.0, 7.5, 2.0, 0.0],      # tie across ranks: earliest index (2) wins
+    [0.0, 0.0, 0.0, 0.0],                          # nothing scores > 0
+    [1.0, 0.5, 0.25, 9.0, 9.0],                    # tie inside the last rank
+])
+def test_gloo_world2_argmax_and_reductions(scores):
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, scores, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    s = np.asarray(scores, dtype=np.float32)
+    want_idx = int(np.argmax(s)) if s.max() > 0 else -1
+    for rank, best, t, u in res:
+        assert best[1] == want_idx
+        if want_idx >= 0:
+            assert best[0] == float(s[want_idx])
+            assert best[2] == (0 if want_idx < shard_range(len(scores), 0, world)[1] else 1)
+        assert t == 2.0 and u == 30.0
+
+
+def test_reference_arm_non_zero_ranks_do_no_work():
+    """bench.py --impl reference under torchrun: only rank 0 runs and prints."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                          "--warmup", "1"], env=env, capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and out.stdout.strip() == ""

@@ -1,0 +1,110 @@
+"""CPU: the BA / pose-only oracle against known answers and scipy."""
+import numpy as np
+from scipy.optimize import least_squares
+from scipy.spatial.transform import Rotation
+
+from urmvo_b200 import synth
+
+
+def _noise_free(seed=21):
+    p = synth.small_ba(seed=seed, outlier_frac=0.0, rot_sigma_deg=0.3, trans_sigma=0.01, pt_sigma=0.02)
+    uv, _ = synth.project(p["gt_poses"], p["obs_cam"], p["gt_pts"][p["obs_pt"]])
+    p["uv"] = np.ascontiguousarray(uv)  # exact, un-rounded projections of the ground truth
+    return p
+
+
+def test_noise_free_scene_returns_ground_truth(oracle):
+    p = _noise_free()
+    poses, pts, inl, st = oracle.local_ba(p, it0=15, it1=15)
+    assert inl.all()
+    assert st.chi2_final[1] < 1e-16
+    assert np.abs(pts - p["gt_pts"]).max() < 1e-7
+    # quaternion sign convention: compare rotation matrices
+    assert np.abs(synth.quat_to_R(poses[:, :4]) - synth.quat_to_R(p["gt_poses"][:, :4])).max() < 1e-8
+    assert np.abs(poses[:, 4:] - p["gt_poses"][:, 4:]).max() < 1e-8
+
+
+def test_fixed_cameras_do_not_move(oracle):
+    p = synth.small_ba(seed=5)
+    poses, _, _, _ = oracle.local_ba(p)
+    fx = p["fixed"] == 1
+    assert np.abs(synth.quat_to_R(poses[fx, :4]) - synth.quat_to_R(p["poses"][fx, :4])).max() < 1e-12
+    assert np.abs(poses[fx, 4:] - p["poses"][fx, 4:]).max() < 1e-12
+    assert np.abs(poses[~fx] - p["poses"][~fx]).max() > 1e-4
+
+
+def test_lm_trace_is_monotone_and_matches_g2o_lambda_rule(oracle):
+    p = synth.small_ba(seed=11, rot_sigma_deg=4.0, trans_sigma=0.3, pt_sigma=0.5)
+    _, _, _, st = oracle.local_ba(p)
+    rows = st.rows()
+    assert len(rows) == st.iters[0] + st.iters[1]
+    for before, after, lam, trials, accepted in rows:
+        assert after <= before + 1e-9
+        assert 1 <= trials <= 10
+        assert lam > 0
+    # accepted first-try steps shrink lambda by at most 3x (alpha clamp 1/3 .. 2/3)
+    first = rows[: st.iters[0]]
+    for (b0, a0, l0, t0, acc0), (b1, a1, l1, t1, acc1) in zip(first, first[1:]):
+        if t1 == 1 and acc1:
+            assert l0 / 3 - 1e-12 <= l1 <= l0 * 2 / 3 + 1e-12
+
+
+def test_second_pass_minimum_matches_scipy_least_squares(oracle):
+    """it0 = 0 leaves every edge at level 0 with no kernel, so the second optimize() is plain
+    non-linear least squares; scipy's trust-region solver must find the same minimum."""
+    p = synth.small_ba(seed=9, n_cams=4, n_pts=40, outlier_frac=0.0)
+    poses, pts, inl, st = oracle.local_ba(p, it0=0, it1=40)
+    Nc, Np = p["poses"].shape[0], p["pts"].shape[0]
+    free = np.where(p["fixed"] == 0)[0]
+
+    def unpack(x):
+        P = p["poses"].copy()
+        for k, c in enumerate(free):
+            r = Rotation.from_rotvec(x[k * 6:k * 6 + 3]) * Rotation.from_quat(p["poses"][c, :4])
+            P[c, :4] = r.as_quat()
+            P[c, 4:] = p["poses"][c, 4:] + x[k * 6 + 3:k * 6 + 6]
+        X = p["pts"] + x[len(free) * 6:].reshape(Np, 3)
+        return P, X
+
+    def resid(x):
+        P, X = unpack(x)
+        uv, _ = synth.project(P, p["obs_cam"], X[p["obs_pt"]])
+        return (p["uv"] - uv).ravel()
+
+    sol = least_squares(resid, np.zeros(len(free) * 6 + Np * 3), method="trf", xtol=1e-15, ftol=1e-15, gtol=1e-12, max_nfev=400)
+    assert abs(st.chi2_final[1] - 2 * sol.cost) / (2 * sol.cost) < 1e-6
+    _, X = unpack(sol.x)
+    assert np.abs(X - pts).max() < 1e-4
+
+
+def test_outliers_are_flagged(oracle):
+    p = synth.cfg1()
+    _, _, inl, st = oracle.local_ba(p)
+    agree = ((inl == 0) == p["is_outlier"]).mean()
+    assert agree > 0.99
+    assert st.chi2_final[1] < st.chi2_final[0]
+
+
+def test_pose_only_recovers_pose_and_counts_inliers(oracle):
+    b = synth.make_pose_batch(3, B=6, n_obs=400)
+    poses, inl, n_inl = oracle.pose_only_batch(b)
+    for f in range(6):
+        s = slice(b["obs_offset"][f], b["obs_offset"][f + 1])
+        assert n_inl[f] == inl[s].sum()
+        assert ((inl[s] == 0) == b["is_outlier"][s]).mean() > 0.98
+    assert np.abs(synth.quat_to_R(poses[:, :4]) - synth.quat_to_R(b["gt_poses"][:, :4])).max() < 2e-3
+    assert np.abs(poses[:, 4:] - b["gt_poses"][:, 4:]).max() < 2e-2
+
+
+def test_pose_only_less_than_ten_edges_stops_after_first_round(oracle):
+    """src/g2o_optimization.cc:310-311."""
+    b = synth.make_pose_batch(4, B=1, n_obs=9, outlier_frac=0.0)
+    pose, inl, n, st = oracle.pose_only(b["poses"][0], b["uv"], b["Xw"], b["intr"])
+    assert st.iters[0] > 0 and st.iters[1] == 0 and st.iters[2] == 0 and st.iters[3] == 0
+
+
+def test_pose_only_threads_match_serial(oracle):
+    b = synth.make_pose_batch(8, B=12, n_obs=150)
+    a = oracle.pose_only_batch(b, n_threads=1)
+    c = oracle.pose_only_batch(b, n_threads=4)
+    assert all(np.array_equal(x, y) for x, y in zip(a, c))

@@ -1,0 +1,117 @@
+"""CPU: analytic pins of the oracle's building blocks."""
+import numpy as np
+import pytest
+from scipy.linalg import expm
+from scipy.spatial.transform import Rotation
+
+from urmvo_b200 import synth
+
+
+def _rand_T(rng):
+    q = Rotation.from_rotvec(0.4 * rng.standard_normal(3)).as_quat()  # x y z w
+    if q[3] < 0:
+        q = -q
+    return np.concatenate([q, rng.standard_normal(3)])
+
+
+def _T_to_mat(T):
+    M = np.eye(4)
+    M[:3, :3] = Rotation.from_quat(T[:4]).as_matrix()
+    M[:3, 3] = T[4:]
+    return M
+
+
+def test_edge_residual_matches_pinhole_projection(oracle):
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        T = _rand_T(rng)
+        X = rng.standard_normal(3) + np.array([0, 0, 5.0])
+        uv = rng.uniform(0, 500, 2)
+        e, Jp, Jx, pos = oracle.edge(T, X, uv, synth.INTR)
+        pc = _T_to_mat(T)[:3, :3] @ X + T[4:]
+        proj = np.array([pc[0] / pc[2] * synth.FX + synth.CX, pc[1] / pc[2] * synth.FY + synth.CY])
+        assert np.allclose(e, uv - proj, rtol=0, atol=1e-10)
+        assert pos == (pc[2] > 0)
+
+
+def test_edge_jacobians_match_finite_differences(oracle):
+    """g2o EdgeSE3ProjectXYZ::linearizeOplus: J_point wrt X, J_pose wrt a LEFT se3 perturbation
+    exp(d) * T with d = (omega, upsilon) — rotation first."""
+    rng = np.random.default_rng(1)
+    h = 1e-6
+    for _ in range(10):
+        T = _rand_T(rng)
+        X = rng.standard_normal(3) + np.array([0, 0, 6.0])
+        uv = rng.uniform(0, 500, 2)
+        e0, Jp, Jx, _ = oracle.edge(T, X, uv, synth.INTR)
+        for a in range(3):
+            d = np.zeros(3); d[a] = h
+            ep = oracle.edge(T, X + d, uv, synth.INTR)[0]
+            em = oracle.edge(T, X - d, uv, synth.INTR)[0]
+            assert np.allclose((ep - em) / (2 * h), Jx[:, a], rtol=1e-5, atol=1e-5)
+        for a in range(6):
+            d = np.zeros(6); d[a] = h
+            ep = oracle.edge(oracle.se3_oplus(T, d), X, uv, synth.INTR)[0]
+            em = oracle.edge(oracle.se3_oplus(T, -d), X, uv, synth.INTR)[0]
+            assert np.allclose((ep - em) / (2 * h), Jp[:, a], rtol=1e-5, atol=1e-4)
+
+
+def test_jacobian_closed_form_table(oracle):
+    """the literal row formulas."""
+    T = np.array([0, 0, 0, 1.0, 0, 0, 0])
+    X = np.array([0.5, -0.25, 4.0])
+    _, Jp, Jx, _ = oracle.edge(T, X, np.zeros(2), synth.INTR)
+    x, y, z = X
+    fx, fy = synth.FX, synth.FY
+    row0 = [fx * x * y / z**2, -fx * (1 + x * x / z**2), fx * y / z, -fx / z, 0, fx * x / z**2]
+    row1 = [fy * (1 + y * y / z**2), -fy * x * y / z**2, -fy * x / z, 0, -fy / z, fy * y / z**2]
+    assert np.allclose(Jp, [row0, row1], rtol=1e-14)
+    assert np.allclose(Jx, -1 / z * np.array([[fx, 0, -fx * x / z], [0, fy, -fy * y / z]]), rtol=1e-14)
+
+
+def test_se3_oplus_is_left_multiplication_by_matrix_exponential(oracle):
+    rng = np.random.default_rng(2)
+    for scale in (1e-7, 1e-3, 0.3):
+        T = _rand_T(rng)
+        d = scale * rng.standard_normal(6)
+        om, up = d[:3], d[3:]
+        xi = np.zeros((4, 4))
+        xi[:3, :3] = [[0, -om[2], om[1]], [om[2], 0, -om[0]], [-om[1], om[0], 0]]
+        xi[:3, 3] = up
+        want = expm(xi) @ _T_to_mat(T)
+        got = oracle.se3_oplus(T, d)
+        assert np.allclose(_T_to_mat(got), want, atol=1e-12)
+        assert got[3] >= 0 and abs(np.linalg.norm(got[:4]) - 1) < 1e-14  # normalised, w >= 0
+
+
+def test_se3_inverse_roundtrip(oracle):
+    rng = np.random.default_rng(3)
+    T = _rand_T(rng)
+    T[:4] *= -2.5  # un-normalised, negative w: SE3Quat(q, t) normalises
+    Ti = oracle.se3_inverse(T)
+    assert np.allclose(_T_to_mat(Ti) @ _T_to_mat(np.concatenate([T[:4] / np.linalg.norm(T[:4]), T[4:]])), np.eye(4), atol=1e-12)
+    assert Ti[3] >= 0
+
+
+@pytest.mark.parametrize("e2", [0.0, 1.0, 9.999, 10.0000003, 10.1, 400.0])
+def test_huber_table(oracle, e2):
+    """g2o RobustKernelHuber::robustify; delta rounded through float like the reference
+    (src/g2o_optimization.cc:71)."""
+    delta = float(np.float32(np.sqrt(10.0)))
+    assert delta == 3.1622776985168457
+    rho = oracle.huber(e2, delta)
+    if e2 <= delta * delta:
+        assert tuple(rho) == (e2, 1.0, 0.0)
+    else:
+        s = np.sqrt(e2)
+        assert np.allclose(rho, [2 * s * delta - delta * delta, delta / s, -0.5 * (delta / s) / e2], rtol=1e-15)
+
+
+def test_rand_sets_known_answers(oracle):
+    """glibc srand(0) — first 8-point sets for N=1000."""
+    sets = oracle.draw_sets(1000, 2, 0)
+    assert sets[0].tolist() == [840, 393, 781, 796, 908, 196, 333, 762]
+    assert sets[1].tolist() == [277, 553, 476, 626, 363, 510, 946, 909]
+    assert np.array_equal(synth.draw_sets(1000, 50, 0), oracle.draw_sets(1000, 50, 0))
+    for s in oracle.draw_sets(40, 200, 0):
+        assert len(set(s.tolist())) == 8  # swap-with-back sampling never repeats an index

@@ -698,6 +698,7 @@ __device__ void solve_window(const Scope& sc, const BAWin& W, const BARun& run, 
   sc.sync();
 
   int cur = 0, last_eval = 0, parity = 0;
+  bool have_eval = false;  // has any computeActiveErrors() run? (g2o's cached _error is zero before)
   urmvo_ba_stats* stats = reinterpret_cast<urmvo_ba_stats*>(W.stats);
   const bool writer = (sc.blk() == 0 && threadIdx.x == 0);
   for (int pass = 0; pass < 2; pass++) {
@@ -705,6 +706,7 @@ __device__ void solve_window(const Scope& sc, const BAWin& W, const BARun& run, 
     double chi_init = 0.0;
     LMResult r = lm_optimize(sc, W, run, pass == 0 ? run.it0 : run.it1, robust, cur, last_eval, st,
                              parity, red, &chi_init);
+    if (r.iters > 0) have_eval = true;
     if (writer && stats) {
       stats->iters[pass] = r.iters;
       stats->trials[pass] = r.trials;
@@ -727,7 +729,7 @@ __device__ void solve_window(const Scope& sc, const BAWin& W, const BARun& run, 
         const int lev = W.level[o];
         if (pass == 1 && lev == 1) continue;  // cached chi2 > thr: inlier[] already 0 from pass 0
         map_point(W.camRt[last_eval] + (size_t)c * 12, W.pts[last_eval] + (size_t)l * 3, pc);
-        const double e2 = edge_error(pc, uv.x, uv.y, K, e0, e1);
+        const double e2 = have_eval ? edge_error(pc, uv.x, uv.y, K, e0, e1) : 0.0;
         map_point(W.camRt[cur] + (size_t)c * 12, W.pts[cur] + (size_t)l * 3, pc);
         const bool depth_pos = pc[2] > 0.0;
         if (pass == 0) {

@@ -308,8 +308,8 @@ extern "C" int urmvo_ba_plan_create(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, 
   for (int k = 0; k < 2; k++) { o_cam[k] = A.take<double>(TC * 7); o_camRt[k] = A.take<double>(TC * 12); o_pts[k] = A.take<double>(TP * 3); }
   const size_t o_level = A.take<uint8_t>(TO);
   const size_t o_S = A.take<double>((size_t)sum_blk * 36);
-  const size_t o_vec = A.take<double>((size_t)sum_ncf * 6 * 8);  // bs bp hdiag xp r z p Ap
-  const size_t o_Minv = A.take<double>((size_t)sum_ncf * 36);
+  const size_t o_vec = A.take<double>((size_t)(sum_ncf + B) * 6 * 8);  // bs bp hdiag xp r z p Ap (indexed by c_ncf, which counts Ncf+1 per window)
+  const size_t o_Minv = A.take<double>((size_t)(sum_ncf + B) * 36);
   const size_t o_Dinv = A.take<double>(TP * 6), o_bl = A.take<double>(TP * 3);
   const size_t part_per_win = (size_t)2 * nblk_scope * kBAPartWidth + 8;
   const size_t o_part = A.take<double>(part_per_win * B);

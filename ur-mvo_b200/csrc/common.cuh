@@ -79,6 +79,8 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double* red) {
   }
 }
 
+constexpr int kScopePartWidth = 8;  // doubles per CTA in each of the two scratch buffers
+
 // Scope-wide reduction of NV sums and NM maxima.  part: 2 * nblk * (NV+NM) doubles of global
 // memory (double-buffered by `parity`, which the caller flips after every call).  Fixed order:
 // per-CTA tree, then lane-strided partials + butterfly, so the result is run-to-run reproducible.
@@ -86,6 +88,7 @@ template <int NV, int NM, class Scope>
 __device__ __forceinline__ void scope_reduce(const Scope& sc, double (&sum)[NV], double (&mx)[NM == 0 ? 1 : NM],
                                              double* part, int& parity, double* red) {
   constexpr int NT = NV + NM;
+  static_assert(NT <= kScopePartWidth, "scope_reduce: too many values");
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
 #pragma unroll
   for (int k = 0; k < NV; k++) sum[k] = warp_sum(sum[k]);
@@ -100,7 +103,7 @@ __device__ __forceinline__ void scope_reduce(const Scope& sc, double (&sum)[NV],
   }
   __syncthreads();
   const int nb = sc.nblk();
-  double* buf = part + (size_t)parity * nb * NT;
+  double* buf = part + (size_t)parity * nb * kScopePartWidth;
   if ((int)threadIdx.x < NT) {
     const int k = threadIdx.x;
     double s = red[k * 32];
