@@ -57,7 +57,7 @@ typedef struct {
   int32_t pcg_max_iter;  /* 0 -> max(60, 2*6*Ncf) capped at 1000 */
   int32_t cluster_size;  /* CTAs cooperating on one window in batch mode (1,2,4,8,16); 0 -> auto */
   int32_t threads;       /* threads per CTA; 0 -> auto */
-  int32_t reserved;
+  int32_t force_atomic;  /* 1: always accumulate S with global fp64 atomics (default: shared-memory copies when they fit) */
 } urmvo_ba_options;
 
 typedef struct {

@@ -50,14 +50,35 @@ def test_ba_noisy_start_with_rejected_steps(oracle, ctx):
     assert gs.trials[0] >= gs.iters[0]
 
 
-def test_ba_cfg1_window(oracle, ctx):
-    gs, _ = _check_ba(oracle, ctx, synth.cfg1())
+@pytest.mark.parametrize("atomic", [0, 1])
+def test_ba_cfg1_window(oracle, ctx, atomic):
+    gs, _ = _check_ba(oracle, ctx, synth.cfg1(), opts=U.BAOptions(0, 0, 0, 0, atomic))
     assert gs.iters[0] == 10 and gs.iters[1] == 5
 
 
+def test_ba_smem_path_is_bit_reproducible(ctx):
+    """The shared-memory accumulation path has no atomics: two runs are bit-identical."""
+    p = synth.cfg1()
+    a = ctx.local_ba(p)
+    b = ctx.local_ba(p)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    assert a[3].chi2_final[1] == b[3].chi2_final[1]
+
+
+def test_ba_sixteen_free_cameras_and_duplicate_camera_fallback(oracle, ctx):
+    _check_ba(oracle, ctx, synth.make_ba(29, 18, 400, 7.0, 18, 2, 0.03))   # Ncf = 16: largest smem system
+    _check_ba(oracle, ctx, synth.make_ba(30, 24, 400, 7.0, 24, 2, 0.03))   # Ncf = 22: atomic path
+    p = synth.small_ba(seed=8)
+    dup = dict(p, uv=np.vstack([p["uv"], p["uv"][:1] + 1.0]), obs_cam=np.r_[p["obs_cam"], p["obs_cam"][:1]],
+               obs_pt=np.r_[p["obs_pt"], p["obs_pt"][:1]])
+    _check_ba(oracle, ctx, dup)  # same camera sees a point twice -> atomic path, still correct
+
+
+@pytest.mark.parametrize("atomic", [0, 1])
 @pytest.mark.parametrize("cs", [1, 2, 4, 8, 16])
-def test_ba_cluster_sizes_agree(oracle, ctx, cs):
-    _check_ba(oracle, ctx, synth.small_ba(seed=5, n_pts=300), opts=U.BAOptions(0, 0, cs, 128, 0))
+def test_ba_cluster_sizes_and_accumulation_modes_agree(oracle, ctx, cs, atomic):
+    """acc mode 0: global fp64 atomics + BSR PCG; 1 (default): shared-memory copies + dense PCG."""
+    _check_ba(oracle, ctx, synth.small_ba(seed=5, n_pts=300), opts=U.BAOptions(0, 0, cs, 128, atomic))
 
 
 def test_ba_unsorted_observations_and_flag_order(oracle, ctx):

@@ -126,9 +126,20 @@ __host__ __device__ inline size_t warp_stage_bytes(int kmax) {
 
 // DIAG = true: only diag(Hpp) (atomics into hdiag), max diag(Hll) and the robust chi2 — the
 // quantities OptimizationAlgorithmLevenberg::computeLambdaInit needs at iteration 0.
-template <bool DIAG, class Scope>
+//
+// SMEM = true (small windows, BAWin::acc_mode 1): every warp accumulates S / b_s / b_p into its own
+// shared-memory copy with plain adds (one lane per camera pair => no two lanes touch the same
+// block), the copies are summed in warp order per CTA and stored as one partial per CTA in
+// BAWin::Spart; the consumer sums the CTA partials in CTA order.  No atomics, bit-reproducible.
+// SMEM = false: fp64 atomics into the global block-sparse S (large / sparse reduced systems).
+template <bool SMEM>
+__device__ __forceinline__ void acc_add(double* p, double v) {
+  if (SMEM) *p += v; else atomicAdd(p, v);
+}
+
+template <bool DIAG, bool SMEM, class Scope>
 __device__ void lin_phase(const Scope& sc, const BAWin& W, int cur, double lambda, bool robust,
-                          double delta, WarpStage st, double& chi_acc, double& maxdiag_acc) {
+                          double delta, WarpStage st, double* acc_all, double& chi_acc, double& maxdiag_acc) {
   const int lane = threadIdx.x & 31;
   const int wpc = blockDim.x >> 5;
   const int gw = sc.blk() * wpc + (threadIdx.x >> 5);
@@ -136,6 +147,16 @@ __device__ void lin_phase(const Scope& sc, const BAWin& W, int cur, double lambd
   const double* __restrict__ camRt = W.camRt[cur];
   const double* __restrict__ pts = W.pts[cur];
   const double K[4] = {W.intr[0], W.intr[1], W.intr[2], W.intr[3]};
+  const int acc_len = DIAG ? W.Ncf * 6 : W.acc_len;
+  double* acc = acc_all + (size_t)(threadIdx.x >> 5) * W.acc_len;  // this warp's copy
+  double* accS = SMEM ? acc : W.S;
+  double* accbs = SMEM ? acc + (size_t)W.nblk * 36 : W.bs;
+  double* accbp = SMEM ? acc + (size_t)W.nblk * 36 + W.Ncf * 6 : W.bp;
+  double* acchd = SMEM ? acc : W.hdiag;
+  if (SMEM) {
+    for (int e = lane; e < acc_len; e += 32) acc[e] = 0.0;
+    __syncwarp();
+  }
 
   for (int l = gw; l < W.Np; l += gstride) {
     const int ps = W.pt_start[l], k = W.pt_start[l + 1] - ps;
@@ -171,7 +192,7 @@ __device__ void lin_phase(const Scope& sc, const BAWin& W, int cur, double lambd
           if (DIAG) {
 #pragma unroll
             for (int a = 0; a < 6; a++)
-              atomicAdd(&W.hdiag[cf * 6 + a], w * (Jp[a] * Jp[a] + Jp[6 + a] * Jp[6 + a]));
+              acc_add<SMEM>(&acchd[cf * 6 + a], w * (Jp[a] * Jp[a] + Jp[6 + a] * Jp[6 + a]));
           } else {
 #pragma unroll
             for (int a = 0; a < 12; a++) st.Jp(a, i) = Jp[a];
@@ -226,8 +247,8 @@ __device__ void lin_phase(const Scope& sc, const BAWin& W, int cur, double lambd
 #pragma unroll
       for (int a = 0; a < 6; a++) {
         const double j0 = st.Jp(a, i), j1 = st.Jp(6 + a, i);
-        atomicAdd(&W.bs[cf * 6 + a], -(j0 * g0 + j1 * g1));
-        atomicAdd(&W.bp[cf * 6 + a], -(j0 * we0 + j1 * we1));
+        acc_add<SMEM>(&accbs[cf * 6 + a], -(j0 * g0 + j1 * g1));
+        acc_add<SMEM>(&accbp[cf * 6 + a], -(j0 * we0 + j1 * we1));
       }
     }
     __syncwarp();
@@ -263,22 +284,35 @@ __device__ void lin_phase(const Scope& sc, const BAWin& W, int cur, double lambd
         T[6 + b] = M[2] * j0 + M[3] * j1;
       }
       const bool swap = ci > cj;
-      const int blk = swap ? find_block(W, cj, ci) : find_block(W, ci, cj);
+      // acc_mode 1 implies the dense upper-triangular block layout: block (a,b) = row_ptr[a] + b - a
+      const int blk = SMEM ? (swap ? W.row_ptr[cj] + ci - cj : W.row_ptr[ci] + cj - ci)
+                           : (swap ? find_block(W, cj, ci) : find_block(W, ci, cj));
       if (blk < 0) continue;  // cannot happen for a structure built from the same observations
-      double* Sb = W.S + (size_t)blk * 36;
-      const bool same_cam_twice = (ci == cj) && (i != j);
+      double* Sb = accS + (size_t)blk * 36;
+      const bool same_cam_twice = !SMEM && (ci == cj) && (i != j);  // excluded on the host in acc_mode 1
 #pragma unroll
       for (int a = 0; a < 6; a++) {
         const double j0 = st.Jp(a, i), j1 = st.Jp(6 + a, i);
 #pragma unroll
         for (int b = 0; b < 6; b++) {
           const double v = j0 * T[b] + j1 * T[6 + b];
-          if (!swap) atomicAdd(&Sb[a * 6 + b], v); else atomicAdd(&Sb[b * 6 + a], v);
+          if (!swap) acc_add<SMEM>(&Sb[a * 6 + b], v); else acc_add<SMEM>(&Sb[b * 6 + a], v);
           if (same_cam_twice) atomicAdd(&Sb[b * 6 + a], v);
         }
       }
     }
     __syncwarp();
+  }
+  if (SMEM) {
+    // fixed-order sum of the warp copies -> this CTA's partial
+    __syncthreads();
+    double* out = W.Spart + (size_t)sc.blk() * W.acc_len;
+    for (int e = threadIdx.x; e < acc_len; e += blockDim.x) {
+      double v = acc_all[e];
+      for (int w = 1; w < wpc; w++) v += acc_all[(size_t)w * W.acc_len + e];
+      __stcg(out + e, v);
+    }
+    __syncthreads();
   }
 }
 
@@ -417,6 +451,154 @@ __device__ bool pcg_phase(const Scope& sc, const BAWin& W, double tol, int max_i
   }
   iters_out = it;
   return ok;
+}
+
+// Small windows (acc_mode 1): CTA 0 of the scope gathers the per-CTA partials of S / b_s / b_p,
+// builds the damped dense reduced camera system in shared memory (n = 6*Ncf <= 96) and warp 0
+// runs block-Jacobi PCG on it with shuffles only.  sm: >= n*n + 4*n + 36*Ncf doubles.
+// Writes x_p and the summed raw gradient b_p to global memory for the other CTAs.
+template <class Scope>
+__device__ bool pcg_dense_smem(const Scope& sc, const BAWin& W, double lambda, double tol, int max_iter,
+                               double* sm, int& iters_out) {
+  const int n = W.Ncf * 6, nb = sc.nblk();
+  double* Sd = sm;               // n x n, symmetric
+  double* bsv = Sd + n * n;      // n
+  double* pv = bsv + n;          // n
+  double* rv = pv + n;           // n
+  double* Mi = rv + n;           // Ncf x 36
+  __shared__ int s_ok, s_it;
+  iters_out = 0;
+  if (n == 0) return true;
+  const int n_s = W.nblk * 36;
+  for (int e = threadIdx.x; e < n_s; e += blockDim.x) {
+    double v = 0.0;
+    for (int b = 0; b < nb; b++) v += __ldcg(W.Spart + (size_t)b * W.acc_len + e);
+    const int blk = e / 36, ab = e - blk * 36, a = ab / 6, c = ab - a * 6;
+    // dense upper layout: block index -> (ci, cj)
+    int ci = 0;
+    while (W.row_ptr[ci + 1] <= blk) ci++;
+    const int cj = ci + (blk - W.row_ptr[ci]);
+    const int r = ci * 6 + a, q = cj * 6 + c;
+    if (ci == cj) {
+      if (a <= c) {  // the diagonal block is taken from its upper triangle
+        const double d = (a == c) ? v + lambda : v;
+        Sd[r * n + q] = d;
+        Sd[q * n + r] = d;
+      }
+    } else {
+      Sd[r * n + q] = v;
+      Sd[q * n + r] = v;
+    }
+  }
+  for (int e = threadIdx.x; e < 2 * n; e += blockDim.x) {
+    double v = 0.0;
+    for (int b = 0; b < nb; b++) v += __ldcg(W.Spart + (size_t)b * W.acc_len + n_s + e);
+    if (e < n) bsv[e] = v; else __stcg(W.bp + (e - n), v);
+  }
+  if (threadIdx.x == 0) { s_ok = 1; s_it = 0; }
+  __syncthreads();
+  for (int i = threadIdx.x; i < W.Ncf; i += blockDim.x) {
+    double A[36];
+#pragma unroll
+    for (int a = 0; a < 6; a++)
+#pragma unroll
+      for (int c = 0; c < 6; c++) A[a * 6 + c] = Sd[(i * 6 + a) * n + i * 6 + c];
+    if (!spd6_inverse(A, Mi + i * 36)) s_ok = 0;
+  }
+  __syncthreads();
+  if (s_ok && threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    constexpr int R = 3;  // rows per lane: n <= 96
+    double x[R], r[R], z[R], pp[R];
+    double rz = 0.0;
+#pragma unroll
+    for (int k = 0; k < R; k++) {
+      const int row = lane + 32 * k;
+      x[k] = 0.0; r[k] = 0.0; z[k] = 0.0; pp[k] = 0.0;
+      if (row < n) {
+        const int i = row / 6, a = row - i * 6;
+        double zz = 0.0;
+#pragma unroll
+        for (int c = 0; c < 6; c++) zz += Mi[i * 36 + a * 6 + c] * bsv[i * 6 + c];
+        r[k] = bsv[row]; z[k] = zz; pp[k] = zz;
+        pv[row] = zz;
+        rz += r[k] * zz;
+      }
+    }
+    rz = warp_sum(rz);
+    __syncwarp();
+    bool ok = true;
+    int it = 0;
+    if (!(rz > 0.0)) {
+      ok = (rz == 0.0);
+    } else {
+      const double stop = tol * tol * rz;
+      for (; it < max_iter; it++) {
+        double ap[R], pap = 0.0;
+#pragma unroll
+        for (int k = 0; k < R; k++) {
+          const int row = lane + 32 * k;
+          ap[k] = 0.0;
+          if (row < n) {
+            double s0 = 0.0, s1 = 0.0;
+            int c = 0;
+            for (; c + 1 < n; c += 2) {
+              s0 += Sd[c * n + row] * pv[c];
+              s1 += Sd[(c + 1) * n + row] * pv[c + 1];
+            }
+            if (c < n) s0 += Sd[c * n + row] * pv[c];
+            ap[k] = s0 + s1;
+            pap += pp[k] * ap[k];
+          }
+        }
+        pap = warp_sum(pap);
+        if (!(pap > 0.0)) { ok = false; break; }
+        const double alpha = rz / pap;
+#pragma unroll
+        for (int k = 0; k < R; k++) {
+          const int row = lane + 32 * k;
+          if (row < n) {
+            x[k] += alpha * pp[k];
+            r[k] -= alpha * ap[k];
+            rv[row] = r[k];
+          }
+        }
+        __syncwarp();
+        double rzn = 0.0;
+#pragma unroll
+        for (int k = 0; k < R; k++) {
+          const int row = lane + 32 * k;
+          if (row < n) {
+            const int i = row / 6, a = row - i * 6;
+            double zz = 0.0;
+#pragma unroll
+            for (int c = 0; c < 6; c++) zz += Mi[i * 36 + a * 6 + c] * rv[i * 6 + c];
+            z[k] = zz;
+            rzn += r[k] * zz;
+          }
+        }
+        rzn = warp_sum(rzn);
+        if (!(rzn > stop)) { it++; break; }
+        const double beta = rzn / rz;
+        rz = rzn;
+#pragma unroll
+        for (int k = 0; k < R; k++) {
+          const int row = lane + 32 * k;
+          if (row < n) { pp[k] = z[k] + beta * pp[k]; pv[row] = pp[k]; }
+        }
+        __syncwarp();
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < R; k++) {
+      const int row = lane + 32 * k;
+      if (row < n) __stcg(W.xp + row, ok ? x[k] : 0.0);
+    }
+    if (lane == 0) { s_ok = ok ? 1 : 0; s_it = it; }
+  }
+  __syncthreads();
+  iters_out = s_it;
+  return s_ok != 0;
 }
 
 // ------------------------------------------------------------------------------- cameras
@@ -568,10 +750,10 @@ __device__ void damp_diagonal(const Scope& sc, const BAWin& W, double lambda) {
 // SparseOptimizer::optimize(n_iter) with OptimizationAlgorithmLevenberg.
 // `cur` is the buffer holding the current estimate (updated on accept); `have_trial` tells the
 // caller whether buffer cur^1 / `last_eval` holds the state of the last computeActiveErrors().
-template <class Scope>
+template <bool SMEM, class Scope>
 __device__ LMResult lm_optimize(const Scope& sc, const BAWin& W, const BARun& run, int n_iter,
-                                bool robust, int& cur, int& last_eval, WarpStage st, int& parity,
-                                double* red, double* chi_initial) {
+                                bool robust, int& cur, int& last_eval, WarpStage st, double* acc_all,
+                                double* pcg_sm, int& parity, double* red, double* chi_initial) {
   LMResult res = {0, 0, 0, 0.0, 0.0};
   double lambda = 0.0, ni = 2.0;
   double currentChi = 0.0;
@@ -581,14 +763,25 @@ __device__ LMResult lm_optimize(const Scope& sc, const BAWin& W, const BARun& ru
   for (int it = 0; it < n_iter; it++) {
     if (it == 0) {
       // computeLambdaInit: tau * max diagonal entry of the (undamped) Hessian
-      zero_system(sc, W, true, 0.0);
-      sc.sync();
+      if (!SMEM) {
+        zero_system(sc, W, true, 0.0);
+        sc.sync();
+      }
       double chi = 0.0, mx = 0.0;
-      lin_phase<true>(sc, W, cur, 0.0, robust, run.delta, st, chi, mx);
+      lin_phase<true, SMEM>(sc, W, cur, 0.0, robust, run.delta, st, acc_all, chi, mx);
       double s1[1] = {chi}, m1[1] = {mx};
       scope_reduce<1, 1>(sc, s1, m1, W.part, parity, red);
       double mp = 0.0;
-      for (int i = threadIdx.x; i < W.Ncf * 6; i += blockDim.x) mp = fmax(mp, fabs(__ldcg(W.hdiag + i)));
+      for (int i = threadIdx.x; i < W.Ncf * 6; i += blockDim.x) {
+        double hd;
+        if (SMEM) {
+          hd = 0.0;
+          for (int b = 0; b < sc.nblk(); b++) hd += __ldcg(W.Spart + (size_t)b * W.acc_len + i);
+        } else {
+          hd = __ldcg(W.hdiag + i);
+        }
+        mp = fmax(mp, fabs(hd));
+      }
       double z1[1] = {0.0}, m2[1] = {mp};
       {  // CTA-local max (every CTA sees the same hdiag)
         CtaScope cs;
@@ -603,17 +796,29 @@ __device__ LMResult lm_optimize(const Scope& sc, const BAWin& W, const BARun& ru
     int qmax = 0;
     bool lambda_bad = false;
     do {
-      zero_system(sc, W, false, lambda);
-      sc.sync();
-      damp_diagonal(sc, W, lambda);
+      if (!SMEM) {
+        zero_system(sc, W, false, lambda);
+        sc.sync();
+        damp_diagonal(sc, W, lambda);
+      } else if (it == 0 && qmax == 0) {
+        sc.sync();  // every CTA has read the DIAG partials before Spart is overwritten
+      }
       double chi = 0.0, mx = 0.0;
-      lin_phase<false>(sc, W, cur, lambda, robust, run.delta, st, chi, mx);
+      lin_phase<false, SMEM>(sc, W, cur, lambda, robust, run.delta, st, acc_all, chi, mx);
       double s1[1] = {chi};
       scope_reduce<1, 0>(sc, s1, dummy, W.part, parity, red);  // also publishes S, bs, bp
       currentChi = s1[0];
       int pcg_it = 0;
       bool ok2;
-      if (use_single_cta_pcg) {
+      if (SMEM) {
+        if (sc.blk() == 0) {
+          ok2 = pcg_dense_smem(sc, W, lambda, run.pcg_tol, run.pcg_max_iter, pcg_sm, pcg_it);
+          if (threadIdx.x == 0) { __stcg(flags, ok2 ? 1.0 : 0.0); __stcg(flags + 1, (double)pcg_it); }
+        }
+        sc.sync();
+        ok2 = __ldcg(flags) > 0.5;
+        pcg_it = (int)__ldcg(flags + 1);
+      } else if (use_single_cta_pcg) {
         // small reduced system: one CTA iterates with __syncthreads only, the others wait
         if (sc.blk() == 0) {
           CtaScope cs;
@@ -675,9 +880,9 @@ __device__ LMResult lm_optimize(const Scope& sc, const BAWin& W, const BARun& ru
 
 // ------------------------------------------------------------------------------- whole window
 
-template <class Scope>
+template <bool SMEM, class Scope>
 __device__ void solve_window(const Scope& sc, const BAWin& W, const BARun& run, WarpStage st,
-                             double* red) {
+                             double* acc_all, double* pcg_sm, double* red) {
   const int gt = sc.blk() * blockDim.x + threadIdx.x, gstride = sc.nblk() * blockDim.x;
   // setEstimate(SE3Quat(q, p).inverse()) (src/g2o_optimization.cc:45), points, levels
   for (int c = gt; c < W.Nc; c += gstride) {
@@ -704,8 +909,8 @@ __device__ void solve_window(const Scope& sc, const BAWin& W, const BARun& run, 
   for (int pass = 0; pass < 2; pass++) {
     const bool robust = (pass == 0);
     double chi_init = 0.0;
-    LMResult r = lm_optimize(sc, W, run, pass == 0 ? run.it0 : run.it1, robust, cur, last_eval, st,
-                             parity, red, &chi_init);
+    LMResult r = lm_optimize<SMEM>(sc, W, run, pass == 0 ? run.it0 : run.it1, robust, cur, last_eval, st,
+                                   acc_all, pcg_sm, parity, red, &chi_init);
     if (r.iters > 0) have_eval = true;
     if (writer && stats) {
       stats->iters[pass] = r.iters;
@@ -765,56 +970,66 @@ __device__ void solve_window(const Scope& sc, const BAWin& W, const BARun& run, 
   for (int i = gt; i < W.Np * 3; i += gstride) W.pts_out[i] = W.pts[cur][i];
 }
 
-__device__ __forceinline__ WarpStage make_stage(unsigned char* smem, int kmax, double** red_out) {
+// Dynamic shared memory layout of one CTA:
+//   [red: 16*32+16 doubles][stage doubles: nw*27*kmax][accumulators: nw*acc_len_max][stage ints: nw*kmax]
+// The dense PCG of acc_mode 1 aliases the stage + accumulator doubles (idle during the solve).
+__device__ __forceinline__ WarpStage make_stage(unsigned char* smem, int kmax, int acc_len_max,
+                                                double** red_out, double** acc_out, double** pcg_out) {
   const int nw = blockDim.x >> 5, wid = threadIdx.x >> 5;
-  // layout: [red: 16*32+16 doubles] [per warp: 27*kmax doubles] [per warp: kmax ints]
   double* red = reinterpret_cast<double*>(smem);
   double* f0 = red + (16 * 32 + 16);
-  int* c0 = reinterpret_cast<int*>(f0 + (size_t)nw * kStageFields * kmax);
+  double* acc0 = f0 + (size_t)nw * kStageFields * kmax;
+  int* c0 = reinterpret_cast<int*>(acc0 + (size_t)nw * acc_len_max);
   WarpStage st;
   st.kmax = kmax;
   st.f = f0 + (size_t)wid * kStageFields * kmax;
   st.cf = c0 + (size_t)wid * kmax;
   *red_out = red;
+  *acc_out = acc0;
+  *pcg_out = f0;
   return st;
 }
 
 // Batched windows: one thread-block cluster per window (cluster dims set at launch).
 __global__ void __launch_bounds__(256, 1)
-ba_window_cluster_kernel(const BAWin* __restrict__ wins, BARun run, int kmax_all) {
+ba_window_cluster_kernel(const BAWin* __restrict__ wins, BARun run, int kmax_all, int acc_len_max) {
   extern __shared__ __align__(16) unsigned char smem[];
   ClusterScope sc;
-  double* red;
-  WarpStage st = make_stage(smem, kmax_all, &red);
+  double *red, *acc, *pcg;
+  WarpStage st = make_stage(smem, kmax_all, acc_len_max, &red, &acc, &pcg);
   const int n_clusters = gridDim.x / sc.nblk();
   const int cid = blockIdx.x / sc.nblk();
   for (int w = cid; w < run.n_win; w += n_clusters) {
-    solve_window(sc, wins[w], run, st, red);
+    if (wins[w].acc_mode) solve_window<true>(sc, wins[w], run, st, acc, pcg, red);
+    else solve_window<false>(sc, wins[w], run, st, acc, pcg, red);
     sc.sync();
   }
 }
 
 // One large problem on the whole (cooperative) grid.
 __global__ void __launch_bounds__(256, 1)
-ba_window_grid_kernel(const BAWin* __restrict__ wins, BARun run, int kmax_all) {
+ba_window_grid_kernel(const BAWin* __restrict__ wins, BARun run, int kmax_all, int acc_len_max) {
   extern __shared__ __align__(16) unsigned char smem[];
   GridScope sc;
-  double* red;
-  WarpStage st = make_stage(smem, kmax_all, &red);
+  double *red, *acc, *pcg;
+  WarpStage st = make_stage(smem, kmax_all, acc_len_max, &red, &acc, &pcg);
   for (int w = 0; w < run.n_win; w++) {
-    solve_window(sc, wins[w], run, st, red);
+    solve_window<false>(sc, wins[w], run, st, acc, pcg, red);
     sc.sync();
   }
 }
 
-size_t ba_smem_bytes(int threads, int kmax) {
+size_t ba_smem_bytes(int threads, int kmax, int acc_len_max, int pcg_doubles) {
   const int nw = threads / 32;
-  return (16 * 32 + 16) * sizeof(double) + (size_t)nw * warp_stage_bytes(kmax);
+  size_t work = (size_t)nw * ((size_t)kStageFields * kmax + acc_len_max);
+  if (work < (size_t)pcg_doubles) work = pcg_doubles;  // dense PCG aliases stage + accumulators
+  // the int staging arrays follow nw*(27*kmax + acc_len_max) doubles; keep room for them after `work`
+  return (16 * 32 + 16) * sizeof(double) + work * sizeof(double) + (size_t)nw * kmax * sizeof(int);
 }
 
-cudaError_t launch_ba_cluster(const BAWin* wins_dev, const BARun& run, int kmax, int n_clusters,
-                              int cluster_size, int threads, cudaStream_t stream) {
-  const size_t smem = ba_smem_bytes(threads, kmax);
+cudaError_t launch_ba_cluster(const BAWin* wins_dev, const BARun& run, int kmax, int acc_len_max,
+                              size_t smem, int n_clusters, int cluster_size, int threads,
+                              cudaStream_t stream) {
   cudaError_t e = cudaFuncSetAttribute(ba_window_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   if (cluster_size > 8) {
@@ -833,11 +1048,11 @@ cudaError_t launch_ba_cluster(const BAWin* wins_dev, const BARun& run, int kmax,
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, ba_window_cluster_kernel, wins_dev, run, kmax);
+  return cudaLaunchKernelEx(&cfg, ba_window_cluster_kernel, wins_dev, run, kmax, acc_len_max);
 }
 
 int ba_grid_capacity(int threads, int kmax) {
-  const size_t smem = ba_smem_bytes(threads, kmax);
+  const size_t smem = ba_smem_bytes(threads, kmax, 0, 0);
   if (cudaFuncSetAttribute(ba_window_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
   int per_sm = 0, dev = 0, sms = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ba_window_grid_kernel, threads, smem) != cudaSuccess) return 0;
@@ -848,12 +1063,12 @@ int ba_grid_capacity(int threads, int kmax) {
 
 cudaError_t launch_ba_grid(const BAWin* wins_dev, const BARun& run, int kmax, int grid_blocks,
                            int threads, cudaStream_t stream) {
-  const size_t smem = ba_smem_bytes(threads, kmax);
+  const size_t smem = ba_smem_bytes(threads, kmax, 0, 0);
   cudaError_t e = cudaFuncSetAttribute(ba_window_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   BARun r = run;
-  int km = kmax;
-  void* args[] = {(void*)&wins_dev, (void*)&r, (void*)&km};
+  int km = kmax, al = 0;
+  void* args[] = {(void*)&wins_dev, (void*)&r, (void*)&km, (void*)&al};
   return cudaLaunchCooperativeKernel((const void*)ba_window_grid_kernel, dim3((unsigned)grid_blocks),
                                      dim3((unsigned)threads), args, smem, stream);
 }

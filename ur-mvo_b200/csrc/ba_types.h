@@ -11,6 +11,9 @@ struct BAWin {
   int Nc, Ncf, Np, No;
   int nblk;         // stored 6x6 blocks of the reduced camera system (upper triangle, BSR)
   int kmax;         // max observations of one point (sizes the per-warp staging area)
+  int acc_mode;     // 1: warp-private shared-memory accumulation + dense in-smem PCG (small windows)
+                    // 0: fp64 atomics into the global block-sparse S + BSR PCG
+  int acc_len;      // acc_mode 1: doubles per accumulator copy = nblk*36 + Ncf*12
   double intr[4];   // fx fy cx cy
   // ---- inputs (immutable during a run)
   const double* pose_in;   // Nc*7   T_wc initial estimate
@@ -43,6 +46,7 @@ struct BAWin {
   double* Dinv;            // Np*6   (Hll + lambda I)^-1, symmetric packed 00 01 02 11 12 22
   double* bl;              // Np*3
   double* part;            // scope reduction scratch: 2 * nblk_scope * 8
+  double* Spart;           // acc_mode 1: one accumulator copy per CTA of the scope (nblk_scope * acc_len)
   // ---- outputs
   double* pose_out;        // Nc*7 T_wc
   double* pts_out;         // Np*3

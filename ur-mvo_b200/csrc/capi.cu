@@ -123,6 +123,8 @@ struct urmvo_ba_plan {
   int B = 0;
   int total_c = 0, total_p = 0, total_o = 0;
   int kmax = 1;
+  int acc_len_max = 0;
+  size_t smem = 0;
   int cluster_size = 1, threads = 256, n_clusters = 0;
   bool use_grid = false;
   int grid_blocks = 0;
@@ -139,6 +141,8 @@ namespace {
 
 struct WinHost {
   int Nc, Ncf, Np, No, nblk, kmax;
+  bool dup_cam = false;  // some point is observed twice by the same camera
+  int acc_mode = 0, acc_len = 0;
   std::vector<int> pt_start, cam_free, row_ptr, col, lrow_ptr, lcol, lblk;
 };
 
@@ -171,6 +175,16 @@ int build_window(int Nc, const uint8_t* fixed, int Np, int No, const int32_t* ob
   } else {
     std::vector<int> fill(w.pt_start.begin(), w.pt_start.end() - 1);
     for (int o = 0; o < No; o++) order[fill[obs_pt[o]]++] = o;  // stable
+  }
+  {  // a camera seeing the same point twice forces the atomic accumulation path
+    std::vector<int> seen(Nc, -1);
+    w.dup_cam = false;
+    for (int l = 0; l < Np && !w.dup_cam; l++)
+      for (int s = w.pt_start[l]; s < w.pt_start[l + 1]; s++) {
+        const int c = obs_cam[order[s]];
+        if (seen[c] == l) { w.dup_cam = true; break; }
+        seen[c] = l;
+      }
   }
   // structure of S: block (a,b), a <= b, present iff some point is seen by free cameras a and b
   const int n = w.Ncf;
@@ -269,11 +283,37 @@ extern "C" int urmvo_ba_plan_create(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, 
   // ---- launch shape
   p->threads = (opts && opts->threads > 0) ? opts->threads : 256;
   if (p->threads % 32 != 0 || p->threads < 64 || p->threads > 256) { delete p; return fail(URMVO_ERR_ARG, "ba options: threads must be 64..256 and a multiple of 32"); }
-  while (p->threads > 64 && ba_smem_bytes(p->threads, p->kmax) > 200 * 1024) p->threads -= 32;
-  if (ba_smem_bytes(p->threads, p->kmax) > 220 * 1024) { delete p; return fail(URMVO_ERR_UNSUPPORTED, "local_ba: a point has too many observations for the per-warp staging area"); }
   const int max_np = [&] { int m = 0; for (auto& w : wh) m = std::max(m, w.Np); return m; }();
   const long long max_no = [&] { long long m = 0; for (auto& w : wh) m = std::max<long long>(m, w.No); return m; }();
   p->use_grid = (B == 1 && max_no >= 100000);
+  // accumulation mode per window: shared-memory copies + dense in-smem PCG when the reduced system
+  // is small (<= 16 free cameras) and fits, else global fp64 atomics + BSR PCG
+  const bool force_atomic = opts && opts->force_atomic == 1;
+  for (auto& w : wh) {
+    w.acc_len = w.nblk * 36 + w.Ncf * 12;
+    w.acc_mode = (!p->use_grid && !force_atomic && !w.dup_cam && w.Ncf <= 16) ? 1 : 0;
+  }
+  const size_t smem_budget = 200 * 1024;
+  for (;;) {
+    int acc_max = 0, pcg_d = 0;
+    for (auto& w : wh)
+      if (w.acc_mode) {
+        acc_max = std::max(acc_max, w.acc_len);
+        const int n = w.Ncf * 6;
+        pcg_d = std::max(pcg_d, n * n + 4 * n + 36 * w.Ncf);
+      }
+    p->acc_len_max = acc_max;
+    p->smem = ba_smem_bytes(p->threads, p->kmax, acc_max, pcg_d);
+    if (p->smem <= smem_budget) break;
+    if (p->threads > 128 || (acc_max == 0 && p->threads > 64)) { p->threads -= 32; continue; }
+    if (acc_max > 0) {  // drop the largest accumulators to the atomic path
+      for (auto& w : wh)
+        if (w.acc_mode && w.acc_len == acc_max) w.acc_mode = 0;
+      continue;
+    }
+    delete p;
+    return fail(URMVO_ERR_UNSUPPORTED, "local_ba: a point has too many observations for the per-warp staging area");
+  }
   int cs = (opts && opts->cluster_size > 0) ? opts->cluster_size : 0;
   if (cs == 0) {
     const int warps = p->threads / 32;
@@ -313,6 +353,13 @@ extern "C" int urmvo_ba_plan_create(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, 
   const size_t o_Dinv = A.take<double>(TP * 6), o_bl = A.take<double>(TP * 3);
   const size_t part_per_win = (size_t)2 * nblk_scope * kBAPartWidth + 8;
   const size_t o_part = A.take<double>(part_per_win * B);
+  size_t spart_total = 0;
+  std::vector<size_t> spart_off(B, 0);
+  for (int w = 0; w < B; w++) {
+    spart_off[w] = spart_total;
+    if (wh[w].acc_mode) spart_total += (size_t)nblk_scope * wh[w].acc_len;
+  }
+  const size_t o_spart = A.take<double>(spart_total);
   p->off_pose_out = A.take<double>(TC * 7);
   p->off_pts_out = A.take<double>(TP * 3);
   p->off_inlier = A.take<uint8_t>(TO);
@@ -348,6 +395,8 @@ extern "C" int urmvo_ba_plan_create(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, 
     BAWin& d = hw[w];
     std::memset(&d, 0, sizeof(d));
     d.Nc = W.Nc; d.Ncf = W.Ncf; d.Np = W.Np; d.No = W.No; d.nblk = W.nblk; d.kmax = W.kmax;
+    d.acc_mode = W.acc_mode; d.acc_len = W.acc_len;
+    d.Spart = (double*)(D + o_spart) + spart_off[w];
     for (int k = 0; k < 4; k++) d.intr[k] = intr[k];
     d.pose_in = (const double*)(D + o_pose_in) + c0 * 7;
     d.pts_in = (const double*)(D + o_pts_in) + p0 * 3;
@@ -423,7 +472,7 @@ extern "C" int urmvo_ba_plan_run(urmvo_ba_plan* p) {
   const BAWin* wins = (const BAWin*)(p->dev + p->off_wins);
   cudaError_t e;
   if (p->use_grid) e = launch_ba_grid(wins, p->run, p->kmax, p->grid_blocks, p->threads, p->ctx->stream);
-  else e = launch_ba_cluster(wins, p->run, p->kmax, p->n_clusters, p->cluster_size, p->threads, p->ctx->stream);
+  else e = launch_ba_cluster(wins, p->run, p->kmax, p->acc_len_max, p->smem, p->n_clusters, p->cluster_size, p->threads, p->ctx->stream);
   if (e != cudaSuccess) return fail(URMVO_ERR_CUDA, std::string("BA kernel launch: ") + cudaGetErrorString(e));
   p->ctx->launches++;
   return URMVO_OK;

@@ -22,7 +22,7 @@ class UrmvoError(RuntimeError):
 
 class BAOptions(C.Structure):
     _fields_ = [("pcg_tol", C.c_double), ("pcg_max_iter", C.c_int32), ("cluster_size", C.c_int32),
-                ("threads", C.c_int32), ("reserved", C.c_int32)]
+                ("threads", C.c_int32), ("force_atomic", C.c_int32)]
 
 
 class BAStats(C.Structure):
