@@ -1,0 +1,90 @@
+"""The C++ drop-in adapters (ur-mvo_b200/adapter/*.cc) keep the reference's signatures
+(include/g2o_optimization.h:13-19, include/epipolar_geometry.h:20-48).  CPU: they compile and link
+against the C ABI using stand-in headers (tests/shim — Eigen / OpenCV / g2o are not installed).
+GPU: driven through LocalmapOptimization / FrameOptimization / EpipolarGeometry::reconstruct they
+give the oracle's results, including the id -> dense index mapping and the in-place conventions."""
+import os
+import struct
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from urmvo_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DRIVER = os.path.join(ROOT, "tests", "shim", "adapter_driver")
+
+
+def build_driver():
+    import urmvo_b200
+    urmvo_b200.load_library()
+    cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-I", os.path.join(ROOT, "tests", "shim"), "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "shim", "adapter_driver.cc"), os.path.join(ROOT, "ur-mvo_b200", "adapter", "g2o_optimization.cc"),
+           os.path.join(ROOT, "ur-mvo_b200", "adapter", "epipolar_geometry.cc"), "-L", os.path.join(ROOT, "ur-mvo_b200", "lib"),
+           "-lurmvo_b200", "-Wl,-rpath," + os.path.join(ROOT, "ur-mvo_b200", "lib"), "-o", DRIVER]
+    subprocess.check_call(cmd)
+
+
+def test_adapters_compile_and_link_against_the_c_abi():
+    build_driver()
+    assert os.path.exists(DRIVER)
+    syms = subprocess.run(["nm", "-C", DRIVER], capture_output=True, text=True).stdout
+    for s in ("LocalmapOptimization(", "FrameOptimization(", "EpipolarGeometry::reconstruct(", "EpipolarGeometry::Random::RandomInt("):
+        assert s in syms, s
+
+
+def _run(mode, payload):
+    if not os.path.exists(DRIVER):
+        build_driver()
+    with tempfile.TemporaryDirectory() as d:
+        fi, fo = os.path.join(d, "in.bin"), os.path.join(d, "out.bin")
+        open(fi, "wb").write(payload)
+        subprocess.check_call([DRIVER, mode, fi, fo])
+        return open(fo, "rb").read()
+
+
+@pytest.mark.gpu
+def test_localmap_optimization_through_the_adapter(oracle):
+    p = synth.small_ba(seed=7)
+    Nc, Np, No = p["poses"].shape[0], p["pts"].shape[0], p["uv"].shape[0]
+    frame_ids = (np.arange(Nc) * 3 + 11).astype(np.int32)      # sparse, ascending ids like frame ids
+    point_ids = (np.arange(Np) * 7 + 5).astype(np.int32)
+    buf = struct.pack("3i", Nc, Np, No) + p["intr"].tobytes() + frame_ids.tobytes() + p["poses"].tobytes() + p["fixed"].tobytes() \
+        + point_ids.tobytes() + p["pts"].tobytes() + p["uv"].tobytes() + p["obs_cam"].tobytes() + p["obs_pt"].tobytes()
+    out = _run("ba", buf)
+    poses = np.frombuffer(out[:Nc * 56], dtype=np.float64).reshape(Nc, 7)
+    pts = np.frombuffer(out[Nc * 56:Nc * 56 + Np * 24], dtype=np.float64).reshape(Np, 3)
+    inl = np.frombuffer(out[Nc * 56 + Np * 24:], dtype=np.uint8)
+    op, ox, oi, _ = oracle.local_ba(p)
+    assert np.abs(poses - op).max() < 1e-5 and np.abs(pts - ox).max() < 1e-4 and np.array_equal(inl, oi)
+
+
+@pytest.mark.gpu
+def test_frame_optimization_through_the_adapter(oracle):
+    b = synth.make_pose_batch(5, B=1, n_obs=250)
+    buf = struct.pack("i", 250) + b["intr"].tobytes() + b["poses"][0].tobytes() + b["uv"].tobytes() + b["Xw"].tobytes()
+    out = _run("pose", buf)
+    pose = np.frombuffer(out[:56], dtype=np.float64)
+    inl = np.frombuffer(out[56:56 + 250], dtype=np.uint8)
+    n = struct.unpack("i", out[56 + 250:])[0]
+    op, oi, on, _ = oracle.pose_only(b["poses"][0], b["uv"], b["Xw"], b["intr"])
+    assert np.abs(pose - op).max() < 1e-5 and np.array_equal(inl, oi) and n == on
+
+
+@pytest.mark.gpu
+def test_reconstruct_through_the_adapter_uses_glibc_rand_sets(oracle):
+    tv = synth.make_two_view(1003, n_keys=400)
+    its = 64
+    buf = struct.pack("3i", 400, 400, its) + tv["K"].tobytes() + tv["keys1"].tobytes() + tv["keys2"].tobytes() + tv["matches12"].tobytes()
+    out = _run("tv", buf)
+    ok = struct.unpack("i", out[:4])[0]
+    T = np.frombuffer(out[4:68], dtype=np.float32).reshape(4, 4)
+    P = np.frombuffer(out[68:68 + 400 * 12], dtype=np.float32).reshape(400, 3)
+    tri = np.frombuffer(out[68 + 400 * 12:], dtype=np.uint8)
+    tv["sets"] = synth.draw_sets(400, its, 0)   # a fresh process seeds rand() once with 0 (:56)
+    o = oracle.two_view(tv)
+    assert bool(ok) == o["ok"]
+    assert np.array_equal(T.view(np.uint32), o["T21"].view(np.uint32))
+    assert np.array_equal(P.view(np.uint32), o["P3D"].view(np.uint32)) and np.array_equal(tri, o["triangulated"])

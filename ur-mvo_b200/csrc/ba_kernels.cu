@@ -39,37 +39,47 @@ __device__ __forceinline__ void map_point(const double* __restrict__ Rt, const d
   pc[2] = Rt[6] * X[0] + Rt[7] * X[1] + Rt[8] * X[2] + Rt[11];
 }
 
-// EdgeSE3ProjectXYZ::computeError: e = z - (x/z*fx + cx, y/z*fy + cy); returns chi2.
+// fp64 division costs ~10x a multiply on the SM (software Newton iteration), so every edge takes ONE
+// reciprocal iz = 1/z and forms x/z, y/z, x/z^2 ... by multiplication.  The results differ from the
+// literal g2o expressions (x*y/z2*fx ...) by a few ulp, far inside the 1e-6 parity tolerance.
+
+// EdgeSE3ProjectXYZ::computeError: e = z - (x/z*fx + cx, y/z*fy + cy); returns chi2. pz[0..2] = x/z, y/z, 1/z.
 __device__ __forceinline__ double edge_error(const double* pc, double u, double v, const double* K,
-                                             double& e0, double& e1) {
-  e0 = u - (pc[0] / pc[2] * K[0] + K[2]);
-  e1 = v - (pc[1] / pc[2] * K[1] + K[3]);
+                                             double& e0, double& e1, double* pz) {
+  const double iz = 1.0 / pc[2];
+  pz[0] = pc[0] * iz; pz[1] = pc[1] * iz; pz[2] = iz;
+  e0 = u - (pz[0] * K[0] + K[2]);
+  e1 = v - (pz[1] * K[1] + K[3]);
   return e0 * e0 + e1 * e1;
 }
+__device__ __forceinline__ double edge_error(const double* pc, double u, double v, const double* K,
+                                             double& e0, double& e1) {
+  double pz[3];
+  return edge_error(pc, u, v, K, e0, e1, pz);
+}
 
-// EdgeSE3ProjectXYZ::linearizeOplus pose part (2x6).
-__device__ __forceinline__ void edge_jac_pose(const double* pc, const double* K, double* Jp) {
-  const double x = pc[0], y = pc[1], z = pc[2], z2 = z * z;
-  Jp[0] = x * y / z2 * K[0];
-  Jp[1] = -(1 + (x * x / z2)) * K[0];
-  Jp[2] = y / z * K[0];
-  Jp[3] = -1. / z * K[0];
+// EdgeSE3ProjectXYZ::linearizeOplus pose part (2x6), from pz = (x/z, y/z, 1/z).
+__device__ __forceinline__ void edge_jac_pose(const double* pz, const double* K, double* Jp) {
+  const double xz = pz[0], yz = pz[1], iz = pz[2];
+  Jp[0] = xz * yz * K[0];
+  Jp[1] = -(1 + xz * xz) * K[0];
+  Jp[2] = yz * K[0];
+  Jp[3] = -iz * K[0];
   Jp[4] = 0;
-  Jp[5] = x / z2 * K[0];
-  Jp[6] = (1 + y * y / z2) * K[1];
-  Jp[7] = -x * y / z2 * K[1];
-  Jp[8] = -x / z * K[1];
+  Jp[5] = xz * iz * K[0];
+  Jp[6] = (1 + yz * yz) * K[1];
+  Jp[7] = -xz * yz * K[1];
+  Jp[8] = -xz * K[1];
   Jp[9] = 0;
-  Jp[10] = -1. / z * K[1];
-  Jp[11] = y / z2 * K[1];
+  Jp[10] = -iz * K[1];
+  Jp[11] = yz * iz * K[1];
 }
 
 // EdgeSE3ProjectXYZ::linearizeOplus point part (2x3) = -1/z * [[fx,0,-x/z fx],[0,fy,-y/z fy]] * R
-__device__ __forceinline__ void edge_jac_point(const double* __restrict__ Rt, const double* pc,
+__device__ __forceinline__ void edge_jac_point(const double* __restrict__ Rt, const double* pz,
                                                const double* K, double* Jx) {
-  const double x = pc[0], y = pc[1], z = pc[2];
-  const double t02 = -x / z * K[0], t12 = -y / z * K[1];
-  const double miz = -1. / z;
+  const double t02 = -pz[0] * K[0], t12 = -pz[1] * K[1];
+  const double miz = -pz[2];
 #pragma unroll
   for (int c = 0; c < 3; c++) {
     Jx[c] = miz * (K[0] * Rt[c] + t02 * Rt[6 + c]);
@@ -168,13 +178,13 @@ __device__ void lin_phase(const Scope& sc, const BAWin& W, int cur, double lambd
       if (!W.level[o]) {
         const int c = W.ocam[o];
         const double* Rt = camRt + (size_t)c * 12;
-        double pc[3], e0, e1, w;
+        double pc[3], pz[3], e0, e1, w;
         map_point(Rt, X, pc);
         const double2 uv = *reinterpret_cast<const double2*>(W.uv + (size_t)o * 2);
-        const double e2 = edge_error(pc, uv.x, uv.y, K, e0, e1);
+        const double e2 = edge_error(pc, uv.x, uv.y, K, e0, e1, pz);
         chi_acc += huber_rho(e2, delta, robust, w);
         double Jx[6], B[6];
-        edge_jac_point(Rt, pc, K, Jx);
+        edge_jac_point(Rt, pz, K, Jx);
 #pragma unroll
         for (int a = 0; a < 6; a++) B[a] = w * Jx[a];
         h[0] += B[0] * Jx[0] + B[3] * Jx[3];
@@ -188,7 +198,7 @@ __device__ void lin_phase(const Scope& sc, const BAWin& W, int cur, double lambd
         cf = W.cam_free[c];
         if (cf >= 0) {
           double Jp[12];
-          edge_jac_pose(pc, K, Jp);
+          edge_jac_pose(pz, K, Jp);
           if (DIAG) {
 #pragma unroll
             for (int a = 0; a < 6; a++)
@@ -673,13 +683,13 @@ __device__ void backsub_phase(const Scope& sc, const BAWin& W, int cur, double l
       const int cf = W.cam_free[c];
       if (cf < 0) continue;
       const double* Rt = camRt + (size_t)c * 12;
-      double pc[3], e0, e1, w, Jp[12], Jx[6];
+      double pc[3], pz[3], e0, e1, w, Jp[12], Jx[6];
       map_point(Rt, X, pc);
       const double2 uv = *reinterpret_cast<const double2*>(W.uv + (size_t)o * 2);
-      const double e2 = edge_error(pc, uv.x, uv.y, K, e0, e1);
+      const double e2 = edge_error(pc, uv.x, uv.y, K, e0, e1, pz);
       huber_rho(e2, delta, robust, w);
-      edge_jac_pose(pc, K, Jp);
-      edge_jac_point(Rt, pc, K, Jx);
+      edge_jac_pose(pz, K, Jp);
+      edge_jac_point(Rt, pz, K, Jx);
       double s0 = 0, s1 = 0;
 #pragma unroll
       for (int a = 0; a < 6; a++) {

@@ -141,8 +141,8 @@ __device__ __forceinline__ void scope_reduce(const Scope& sc, double (&sum)[NV],
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void quat_normalize_w(double* q) {
   if (q[3] < 0) { q[0] = -q[0]; q[1] = -q[1]; q[2] = -q[2]; q[3] = -q[3]; }
-  const double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
-  q[0] /= n; q[1] /= n; q[2] /= n; q[3] /= n;
+  const double n = 1.0 / sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  q[0] *= n; q[1] *= n; q[2] *= n; q[3] *= n;
 }
 
 __device__ __forceinline__ void quat_to_R(const double* q, double* R) {

@@ -26,10 +26,12 @@ __device__ __forceinline__ void pose_map(const double* R, const double* t, const
   pc[2] = R[6] * X[0] + R[7] * X[1] + R[8] * X[2] + t[2];
 }
 
+// One reciprocal per edge (fp64 division is a software routine on the SM); see ba_kernels.cu.
 __device__ __forceinline__ double pose_err(const double* pc, double u, double v, const double* K,
                                            double& e0, double& e1) {
-  e0 = u - (pc[0] / pc[2] * K[0] + K[2]);
-  e1 = v - (pc[1] / pc[2] * K[1] + K[3]);
+  const double iz = 1.0 / pc[2];
+  e0 = u - (pc[0] * iz * K[0] + K[2]);
+  e1 = v - (pc[1] * iz * K[1] + K[3]);
   return e0 * e0 + e1 * e1;
 }
 
