@@ -50,14 +50,23 @@ def test_ba_noisy_start_with_rejected_steps(oracle, ctx):
     assert gs.trials[0] >= gs.iters[0]
 
 
-@pytest.mark.parametrize("atomic", [0, 1])
+@pytest.mark.parametrize("atomic", [0, 1, 2])
 def test_ba_cfg1_window(oracle, ctx, atomic):
     gs, _ = _check_ba(oracle, ctx, synth.cfg1(), opts=U.BAOptions(0, 0, 0, 0, atomic))
     assert gs.iters[0] == 10 and gs.iters[1] == 5
 
 
+def test_ba_points_without_observations(oracle, ctx):
+    p = synth.small_ba(seed=6)
+    q = dict(p, pts=np.vstack([p["pts"], [[9.0, 9.0, 9.0], [1.0, 2.0, 3.0]]]))  # two points nobody observes
+    gp, gx, gi, gs = ctx.local_ba(q)
+    op, ox, oi, os_ = oracle.local_ba(q)
+    assert np.abs(gp - op).max() < 1e-5 and np.array_equal(gi, oi)
+    assert np.array_equal(gx[-2:], q["pts"][-2:])
+
+
 def test_ba_smem_path_is_bit_reproducible(ctx):
-    """The shared-memory accumulation path has no atomics: two runs are bit-identical."""
+    """The small-window paths have no atomics: two runs are bit-identical."""
     p = synth.cfg1()
     a = ctx.local_ba(p)
     b = ctx.local_ba(p)
@@ -66,6 +75,8 @@ def test_ba_smem_path_is_bit_reproducible(ctx):
 
 
 def test_ba_sixteen_free_cameras_and_duplicate_camera_fallback(oracle, ctx):
+    _check_ba(oracle, ctx, synth.make_ba(27, 12, 400, 7.0, 12, 2, 0.03))   # Ncf = 10: 55 blocks, 2 per lane
+    _check_ba(oracle, ctx, synth.make_ba(28, 13, 400, 7.0, 13, 2, 0.03))   # Ncf = 11: 66 blocks -> smem RMW
     _check_ba(oracle, ctx, synth.make_ba(29, 18, 400, 7.0, 18, 2, 0.03))   # Ncf = 16: largest smem system
     _check_ba(oracle, ctx, synth.make_ba(30, 24, 400, 7.0, 24, 2, 0.03))   # Ncf = 22: atomic path
     p = synth.small_ba(seed=8)
@@ -74,10 +85,11 @@ def test_ba_sixteen_free_cameras_and_duplicate_camera_fallback(oracle, ctx):
     _check_ba(oracle, ctx, dup)  # same camera sees a point twice -> atomic path, still correct
 
 
-@pytest.mark.parametrize("atomic", [0, 1])
+@pytest.mark.parametrize("atomic", [0, 1, 2])
 @pytest.mark.parametrize("cs", [1, 2, 4, 8, 16])
 def test_ba_cluster_sizes_and_accumulation_modes_agree(oracle, ctx, cs, atomic):
-    """acc mode 0: global fp64 atomics + BSR PCG; 1 (default): shared-memory copies + dense PCG."""
+    """force_atomic 0: packed groups + register-resident Schur blocks (default for small windows);
+    1: global fp64 atomics + BSR PCG; 2: shared-memory read-modify-write copies + dense PCG."""
     _check_ba(oracle, ctx, synth.small_ba(seed=5, n_pts=300), opts=U.BAOptions(0, 0, cs, 128, atomic))
 
 

@@ -132,6 +132,27 @@ __host__ __device__ inline size_t warp_stage_bytes(int kmax) {
   return (size_t)kmax * (kStageFields * sizeof(double) + sizeof(int));
 }
 
+// Per-warp work areas in dynamic shared memory: warp w owns [base + w*stride, base + (w+1)*stride).
+struct WorkArea {
+  double* base;
+  int stride;
+};
+
+// Fixed-order sum of the warps' accumulator copies (at `off` inside each work area) -> this CTA's
+// partial in BAWin::Spart.
+template <class Scope>
+__device__ __forceinline__ void cta_reduce_copies(const Scope& sc, const BAWin& W, WorkArea wa, int off, int len) {
+  const int wpc = blockDim.x >> 5;
+  __syncthreads();
+  double* out = W.Spart + (size_t)sc.blk() * W.acc_len;
+  for (int e = threadIdx.x; e < len; e += blockDim.x) {
+    double v = wa.base[off + e];
+    for (int w = 1; w < wpc; w++) v += wa.base[(size_t)w * wa.stride + off + e];
+    __stcg(out + e, v);
+  }
+  __syncthreads();
+}
+
 // ------------------------------------------------------------------------------- phase LIN
 
 // DIAG = true: only diag(Hpp) (atomics into hdiag), max diag(Hll) and the robust chi2 — the
@@ -149,7 +170,7 @@ __device__ __forceinline__ void acc_add(double* p, double v) {
 
 template <bool DIAG, bool SMEM, class Scope>
 __device__ void lin_phase(const Scope& sc, const BAWin& W, int cur, double lambda, bool robust,
-                          double delta, WarpStage st, double* acc_all, double& chi_acc, double& maxdiag_acc) {
+                          double delta, WarpStage st, WorkArea wa, double& chi_acc, double& maxdiag_acc) {
   const int lane = threadIdx.x & 31;
   const int wpc = blockDim.x >> 5;
   const int gw = sc.blk() * wpc + (threadIdx.x >> 5);
@@ -158,7 +179,8 @@ __device__ void lin_phase(const Scope& sc, const BAWin& W, int cur, double lambd
   const double* __restrict__ pts = W.pts[cur];
   const double K[4] = {W.intr[0], W.intr[1], W.intr[2], W.intr[3]};
   const int acc_len = DIAG ? W.Ncf * 6 : W.acc_len;
-  double* acc = acc_all + (size_t)(threadIdx.x >> 5) * W.acc_len;  // this warp's copy
+  const int acc_off = kStageFields * st.kmax;  // the accumulator copy follows the staging fields
+  double* acc = wa.base + (size_t)(threadIdx.x >> 5) * wa.stride + acc_off;  // this warp's copy
   double* accS = SMEM ? acc : W.S;
   double* accbs = SMEM ? acc + (size_t)W.nblk * 36 : W.bs;
   double* accbp = SMEM ? acc + (size_t)W.nblk * 36 + W.Ncf * 6 : W.bp;
@@ -316,13 +338,7 @@ __device__ void lin_phase(const Scope& sc, const BAWin& W, int cur, double lambd
   if (SMEM) {
     // fixed-order sum of the warp copies -> this CTA's partial
     __syncthreads();
-    double* out = W.Spart + (size_t)sc.blk() * W.acc_len;
-    for (int e = threadIdx.x; e < acc_len; e += blockDim.x) {
-      double v = acc_all[e];
-      for (int w = 1; w < wpc; w++) v += acc_all[(size_t)w * W.acc_len + e];
-      __stcg(out + e, v);
-    }
-    __syncthreads();
+    cta_reduce_copies(sc, W, wa, acc_off, acc_len);
   }
 }
 
@@ -727,6 +743,343 @@ __device__ void backsub_phase(const Scope& sc, const BAWin& W, int cur, double l
   }
 }
 
+// ------------------------------------------------------------------------------- packed phases
+//
+// acc_mode 2/3 (every point has <= 32 observations, <= 64 stored blocks, <= 16 free cameras — every
+// window the reference can produce): a warp takes a GROUP of consecutive points whose observations
+// fill its 32 lanes (lane = observation, so uv / camera index / level loads are coalesced and ~95 %
+// of the lanes work, against ~25 % with one point per warp), per-point sums are formed in shared
+// memory in observation order, and the Schur complement is accumulated S-STATIONARY: lane b owns
+// reduced-system block b (and b+32) in REGISTERS for all the groups of the warp and visits, per
+// point, the two observation slots of its camera pair.  No read-modify-write traffic, no atomics;
+// the register blocks are flushed once per phase and summed in warp order, then CTA order.
+
+constexpr int kPackSlots = 32;
+constexpr int kPackCam = 16;     // width of the (point-in-group, free camera) -> slot table
+constexpr int kPackFields = 38;  // Jp[12] | B[6] | A[6] | we[2] | w | h[6] | bl[3] | g[2]
+
+struct PackStage {
+  double* f;          // kPackFields x 32
+  signed char* slot;  // 32 x kPackCam
+  __device__ __forceinline__ double& Jp(int a, int s) { return f[a * 32 + s]; }
+  __device__ __forceinline__ double& B(int a, int s) { return f[(12 + a) * 32 + s]; }
+  __device__ __forceinline__ double& A(int a, int s) { return f[(18 + a) * 32 + s]; }
+  __device__ __forceinline__ double& we(int a, int s) { return f[(24 + a) * 32 + s]; }
+  __device__ __forceinline__ double& w(int s) { return f[26 * 32 + s]; }
+  __device__ __forceinline__ double& h(int a, int s) { return f[(27 + a) * 32 + s]; }
+  __device__ __forceinline__ double& bl(int a, int s) { return f[(33 + a) * 32 + s]; }
+  __device__ __forceinline__ double& g(int a, int s) { return f[(36 + a) * 32 + s]; }
+};
+
+template <bool DIAG, int NB, class Scope>
+__device__ void lin_phase_packed(const Scope& sc, const BAWin& W, int cur, double lambda, bool robust,
+                                 double delta, PackStage st, WorkArea wa, double& chi_acc,
+                                 double& maxdiag_acc) {
+  const int lane = threadIdx.x & 31;
+  const int wpc = blockDim.x >> 5;
+  const int gw = sc.blk() * wpc + (threadIdx.x >> 5);
+  const int gstride = sc.nblk() * wpc;
+  const double* __restrict__ camRt = W.camRt[cur];
+  const double* __restrict__ pts = W.pts[cur];
+  const double K[4] = {W.intr[0], W.intr[1], W.intr[2], W.intr[3]};
+  // blocks owned by this lane: dense upper layout, block b = row_ptr[ci] + (cj - ci)
+  int bci[NB], bcj[NB];
+#pragma unroll
+  for (int nb = 0; nb < NB; nb++) {
+    const int blk = lane + 32 * nb;
+    bci[nb] = -1; bcj[nb] = -1;
+    if (blk < W.nblk) {
+      int ci = 0;
+      while (W.row_ptr[ci + 1] <= blk) ci++;
+      bci[nb] = ci;
+      bcj[nb] = ci + (blk - W.row_ptr[ci]);
+    }
+  }
+  double accS[NB][36];
+#pragma unroll
+  for (int nb = 0; nb < NB; nb++)
+#pragma unroll
+    for (int e = 0; e < 36; e++) accS[nb][e] = 0.0;
+  double accb[12];  // b_s | b_p of camera `lane` (DIAG: diag(Hpp) in the first 6)
+#pragma unroll
+  for (int e = 0; e < 12; e++) accb[e] = 0.0;
+
+  for (int g = gw; g < W.n_grp; g += gstride) {
+    const int p0 = W.grp_pt[g], np = W.grp_pt[g + 1] - p0;
+    const int o0 = W.pt_start[p0], nobs = W.pt_start[p0 + np] - o0;
+    reinterpret_cast<int*>(st.slot)[lane] = -1;       // 32 * 16 bytes = 128 ints of 0xFF
+    reinterpret_cast<int*>(st.slot)[lane + 32] = -1;
+    reinterpret_cast<int*>(st.slot)[lane + 64] = -1;
+    reinterpret_cast<int*>(st.slot)[lane + 96] = -1;
+    __syncwarp();
+    const bool valid = lane < nobs;
+    const int o = o0 + lane;
+    const int pl = valid ? W.opt[o] : p0;
+    const int pi = pl - p0;
+    const int s0 = W.pt_start[pl] - o0, s1 = W.pt_start[pl + 1] - o0;
+    double hc[6] = {0, 0, 0, 0, 0, 0}, blc[3] = {0, 0, 0};
+    int cf = -1;
+    double B[6];
+    if (valid && !W.level[o]) {
+      const int c = W.ocam[o];
+      const double* Rt = camRt + (size_t)c * 12;
+      const double X[3] = {pts[pl * 3], pts[pl * 3 + 1], pts[pl * 3 + 2]};
+      double pc[3], pz[3], e0, e1, w;
+      map_point(Rt, X, pc);
+      const double2 uv = *reinterpret_cast<const double2*>(W.uv + (size_t)o * 2);
+      const double e2 = edge_error(pc, uv.x, uv.y, K, e0, e1, pz);
+      chi_acc += huber_rho(e2, delta, robust, w);
+      double Jx[6];
+      edge_jac_point(Rt, pz, K, Jx);
+#pragma unroll
+      for (int a = 0; a < 6; a++) B[a] = w * Jx[a];
+      hc[0] = B[0] * Jx[0] + B[3] * Jx[3];
+      hc[1] = B[0] * Jx[1] + B[3] * Jx[4];
+      hc[2] = B[0] * Jx[2] + B[3] * Jx[5];
+      hc[3] = B[1] * Jx[1] + B[4] * Jx[4];
+      hc[4] = B[1] * Jx[2] + B[4] * Jx[5];
+      hc[5] = B[2] * Jx[2] + B[5] * Jx[5];
+#pragma unroll
+      for (int a = 0; a < 3; a++) blc[a] = -(B[a] * e0 + B[3 + a] * e1);
+      cf = W.cam_free[c];
+      if (cf >= 0) {
+        double Jp[12];
+        edge_jac_pose(pz, K, Jp);
+#pragma unroll
+        for (int a = 0; a < 12; a++) st.Jp(a, lane) = Jp[a];
+        st.w(lane) = w;
+        if (!DIAG) {
+#pragma unroll
+          for (int a = 0; a < 6; a++) st.B(a, lane) = B[a];
+          st.we(0, lane) = w * e0;
+          st.we(1, lane) = w * e1;
+        }
+        st.slot[pi * kPackCam + cf] = (signed char)lane;
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 6; a++) st.h(a, lane) = hc[a];
+    if (!DIAG) {
+#pragma unroll
+      for (int a = 0; a < 3; a++) st.bl(a, lane) = blc[a];
+    }
+    __syncwarp();
+    // per-point sums in observation order (every lane for its own point)
+    double h[6] = {0, 0, 0, 0, 0, 0}, bl[3] = {0, 0, 0};
+    if (valid) {
+      for (int s = s0; s < s1; s++) {
+#pragma unroll
+        for (int a = 0; a < 6; a++) h[a] += st.h(a, s);
+        if (!DIAG) {
+#pragma unroll
+          for (int a = 0; a < 3; a++) bl[a] += st.bl(a, s);
+        }
+      }
+    }
+    if (DIAG) {
+      if (valid) maxdiag_acc = fmax(maxdiag_acc, fmax(fabs(h[0]), fmax(fabs(h[3]), fabs(h[5]))));
+      __syncwarp();
+      if (lane < W.Ncf) {
+        for (int q = 0; q < np; q++) {
+          const int s = st.slot[q * kPackCam + lane];
+          if (s < 0) continue;
+          const double w = st.w(s);
+#pragma unroll
+          for (int a = 0; a < 6; a++) {
+            const double j0 = st.Jp(a, s), j1 = st.Jp(6 + a, s);
+            accb[a] += w * (j0 * j0 + j1 * j1);
+          }
+        }
+      }
+      __syncwarp();
+      continue;
+    }
+    if (valid) {
+      double Di[6];
+      const double hl[6] = {h[0] + lambda, h[1], h[2], h[3] + lambda, h[4], h[5] + lambda};
+      sym3_inverse(hl, Di);
+      if (lane == s0) {
+#pragma unroll
+        for (int a = 0; a < 6; a++) W.Dinv[(size_t)pl * 6 + a] = Di[a];
+#pragma unroll
+        for (int a = 0; a < 3; a++) W.bl[(size_t)pl * 3 + a] = bl[a];
+      }
+      if (cf >= 0) {
+        double A[6];
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+          const double b0 = B[r * 3], b1 = B[r * 3 + 1], b2 = B[r * 3 + 2];
+          A[r * 3 + 0] = b0 * Di[0] + b1 * Di[1] + b2 * Di[2];
+          A[r * 3 + 1] = b0 * Di[1] + b1 * Di[3] + b2 * Di[4];
+          A[r * 3 + 2] = b0 * Di[2] + b1 * Di[4] + b2 * Di[5];
+        }
+#pragma unroll
+        for (int a = 0; a < 6; a++) st.A(a, lane) = A[a];
+        st.g(0, lane) = st.we(0, lane) + (A[0] * bl[0] + A[1] * bl[1] + A[2] * bl[2]);
+        st.g(1, lane) = st.we(1, lane) + (A[3] * bl[0] + A[4] * bl[1] + A[5] * bl[2]);
+      }
+    }
+    __syncwarp();
+    // S-stationary accumulation: for every point of the group, the lane's camera pair(s)
+    for (int q = 0; q < np; q++) {
+      const signed char* sl = st.slot + q * kPackCam;
+#pragma unroll
+      for (int nb = 0; nb < NB; nb++) {
+        if (bci[nb] < 0) continue;
+        const int si = sl[bci[nb]], sj = sl[bcj[nb]];
+        if (si < 0 || sj < 0) continue;
+        double M[4];
+        {
+          const double a0 = st.A(0, si), a1 = st.A(1, si), a2 = st.A(2, si);
+          const double a3 = st.A(3, si), a4 = st.A(4, si), a5 = st.A(5, si);
+          const double b0 = st.B(0, sj), b1 = st.B(1, sj), b2 = st.B(2, sj);
+          const double b3 = st.B(3, sj), b4 = st.B(4, sj), b5 = st.B(5, sj);
+          M[0] = -(a0 * b0 + a1 * b1 + a2 * b2);
+          M[1] = -(a0 * b3 + a1 * b4 + a2 * b5);
+          M[2] = -(a3 * b0 + a4 * b1 + a5 * b2);
+          M[3] = -(a3 * b3 + a4 * b4 + a5 * b5);
+          if (si == sj) { const double w = st.w(si); M[0] += w; M[3] += w; }
+        }
+        double T[12];
+#pragma unroll
+        for (int b = 0; b < 6; b++) {
+          const double j0 = st.Jp(b, sj), j1 = st.Jp(6 + b, sj);
+          T[b] = M[0] * j0 + M[1] * j1;
+          T[6 + b] = M[2] * j0 + M[3] * j1;
+        }
+#pragma unroll
+        for (int a = 0; a < 6; a++) {
+          const double j0 = st.Jp(a, si), j1 = st.Jp(6 + a, si);
+#pragma unroll
+          for (int b = 0; b < 6; b++) accS[nb][a * 6 + b] += j0 * T[b] + j1 * T[6 + b];
+        }
+      }
+      if (lane < W.Ncf) {
+        const int s = sl[lane];
+        if (s >= 0) {
+          const double g0 = st.g(0, s), g1 = st.g(1, s), w0 = st.we(0, s), w1 = st.we(1, s);
+#pragma unroll
+          for (int a = 0; a < 6; a++) {
+            const double j0 = st.Jp(a, s), j1 = st.Jp(6 + a, s);
+            accb[a] -= j0 * g0 + j1 * g1;
+            accb[6 + a] -= j0 * w0 + j1 * w1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+  // flush the register accumulators into this warp's work area (aliases the staging fields)
+  double* acc = wa.base + (size_t)(threadIdx.x >> 5) * wa.stride;
+  __syncwarp();
+  if (DIAG) {
+    if (lane < W.Ncf) {
+#pragma unroll
+      for (int a = 0; a < 6; a++) acc[lane * 6 + a] = accb[a];
+    }
+    cta_reduce_copies(sc, W, wa, 0, W.Ncf * 6);
+    return;
+  }
+#pragma unroll
+  for (int nb = 0; nb < NB; nb++) {
+    const int blk = lane + 32 * nb;
+    if (blk < W.nblk) {
+#pragma unroll
+      for (int e = 0; e < 36; e++) acc[(size_t)blk * 36 + e] = accS[nb][e];
+    }
+  }
+  if (lane < W.Ncf) {
+#pragma unroll
+    for (int a = 0; a < 6; a++) {
+      acc[(size_t)W.nblk * 36 + lane * 6 + a] = accb[a];
+      acc[(size_t)W.nblk * 36 + W.Ncf * 6 + lane * 6 + a] = accb[6 + a];
+    }
+  }
+  cta_reduce_copies(sc, W, wa, 0, W.acc_len);
+}
+
+template <class Scope>
+__device__ void backsub_phase_packed(const Scope& sc, const BAWin& W, int cur, double lambda, bool robust,
+                                     double delta, PackStage st, double& chi_acc, double& scale_acc) {
+  const int lane = threadIdx.x & 31;
+  const int wpc = blockDim.x >> 5;
+  const int gw = sc.blk() * wpc + (threadIdx.x >> 5);
+  const int gstride = sc.nblk() * wpc;
+  const int tr = cur ^ 1;
+  const double* __restrict__ camRt = W.camRt[cur];
+  const double* __restrict__ camRtT = W.camRt[tr];
+  const double K[4] = {W.intr[0], W.intr[1], W.intr[2], W.intr[3]};
+  for (int g = gw; g < W.n_grp; g += gstride) {
+    const int p0 = W.grp_pt[g], np = W.grp_pt[g + 1] - p0;
+    const int o0 = W.pt_start[p0], nobs = W.pt_start[p0 + np] - o0;
+    const bool valid = lane < nobs;
+    const int o = o0 + lane;
+    const int pl = valid ? W.opt[o] : p0;
+    const int s0 = W.pt_start[pl] - o0, s1 = W.pt_start[pl + 1] - o0;
+    const double X[3] = {W.pts[cur][pl * 3], W.pts[cur][pl * 3 + 1], W.pts[cur][pl * 3 + 2]};
+    double c3[3] = {0, 0, 0};
+    int c = 0;
+    double2 uv = make_double2(0.0, 0.0);
+    bool active = false;
+    if (valid && !W.level[o]) {
+      active = true;
+      c = W.ocam[o];
+      uv = *reinterpret_cast<const double2*>(W.uv + (size_t)o * 2);
+      const int cf = W.cam_free[c];
+      if (cf >= 0) {
+        const double* Rt = camRt + (size_t)c * 12;
+        double pc[3], pz[3], e0, e1, w, Jp[12], Jx[6];
+        map_point(Rt, X, pc);
+        const double e2 = edge_error(pc, uv.x, uv.y, K, e0, e1, pz);
+        huber_rho(e2, delta, robust, w);
+        edge_jac_pose(pz, K, Jp);
+        edge_jac_point(Rt, pz, K, Jx);
+        double t0 = 0, t1 = 0;
+#pragma unroll
+        for (int a = 0; a < 6; a++) {
+          const double xa = __ldcg(W.xp + cf * 6 + a);
+          t0 += Jp[a] * xa;
+          t1 += Jp[6 + a] * xa;
+        }
+        t0 *= w; t1 *= w;
+#pragma unroll
+        for (int a = 0; a < 3; a++) c3[a] = Jx[a] * t0 + Jx[3 + a] * t1;
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int a = 0; a < 3; a++) st.h(a, lane) = c3[a];
+    __syncwarp();
+    double Xn[3] = {X[0], X[1], X[2]};
+    if (valid) {
+      double cs[3] = {0, 0, 0};
+      for (int s = s0; s < s1; s++) {
+#pragma unroll
+        for (int a = 0; a < 3; a++) cs[a] += st.h(a, s);
+      }
+      const double* Di = W.Dinv + (size_t)pl * 6;
+      const double b0 = W.bl[(size_t)pl * 3], b1 = W.bl[(size_t)pl * 3 + 1], b2 = W.bl[(size_t)pl * 3 + 2];
+      const double r0 = b0 - cs[0], r1 = b1 - cs[1], r2 = b2 - cs[2];
+      const double x0 = Di[0] * r0 + Di[1] * r1 + Di[2] * r2;
+      const double x1 = Di[1] * r0 + Di[3] * r1 + Di[4] * r2;
+      const double x2 = Di[2] * r0 + Di[4] * r1 + Di[5] * r2;
+      Xn[0] += x0; Xn[1] += x1; Xn[2] += x2;
+      if (lane == s0) {
+        W.pts[tr][pl * 3] = Xn[0]; W.pts[tr][pl * 3 + 1] = Xn[1]; W.pts[tr][pl * 3 + 2] = Xn[2];
+        scale_acc += x0 * (lambda * x0 + b0) + x1 * (lambda * x1 + b1) + x2 * (lambda * x2 + b2);
+      }
+    }
+    if (active) {
+      const double* Rt = camRtT + (size_t)c * 12;
+      double pc[3], e0, e1, w;
+      map_point(Rt, Xn, pc);
+      const double e2 = edge_error(pc, uv.x, uv.y, K, e0, e1);
+      chi_acc += huber_rho(e2, delta, robust, w);
+    }
+    __syncwarp();
+  }
+}
+
 // ------------------------------------------------------------------------------- LM driver
 
 constexpr int kPartWidth = kBAPartWidth;
@@ -760,10 +1113,16 @@ __device__ void damp_diagonal(const Scope& sc, const BAWin& W, double lambda) {
 // SparseOptimizer::optimize(n_iter) with OptimizationAlgorithmLevenberg.
 // `cur` is the buffer holding the current estimate (updated on accept); `have_trial` tells the
 // caller whether buffer cur^1 / `last_eval` holds the state of the last computeActiveErrors().
-template <bool SMEM, class Scope>
+// MODE = BAWin::acc_mode: 0 global atomics, 1 shared-memory RMW copies, 2 / 3 packed groups with
+// 1 / 2 register-resident blocks per lane.
+template <int MODE, class Scope>
 __device__ LMResult lm_optimize(const Scope& sc, const BAWin& W, const BARun& run, int n_iter,
-                                bool robust, int& cur, int& last_eval, WarpStage st, double* acc_all,
-                                double* pcg_sm, int& parity, double* red, double* chi_initial) {
+                                bool robust, int& cur, int& last_eval, WarpStage st, PackStage pst,
+                                WorkArea wa, double* pcg_sm, int& parity, double* red,
+                                double* chi_initial) {
+  constexpr bool SMEM = MODE >= 1;
+  constexpr bool PACKED = MODE >= 2;
+  constexpr int NB = MODE == 3 ? 2 : 1;
   LMResult res = {0, 0, 0, 0.0, 0.0};
   double lambda = 0.0, ni = 2.0;
   double currentChi = 0.0;
@@ -778,7 +1137,8 @@ __device__ LMResult lm_optimize(const Scope& sc, const BAWin& W, const BARun& ru
         sc.sync();
       }
       double chi = 0.0, mx = 0.0;
-      lin_phase<true, SMEM>(sc, W, cur, 0.0, robust, run.delta, st, acc_all, chi, mx);
+      if (PACKED) lin_phase_packed<true, NB>(sc, W, cur, 0.0, robust, run.delta, pst, wa, chi, mx);
+      else lin_phase<true, SMEM>(sc, W, cur, 0.0, robust, run.delta, st, wa, chi, mx);
       double s1[1] = {chi}, m1[1] = {mx};
       scope_reduce<1, 1>(sc, s1, m1, W.part, parity, red);
       double mp = 0.0;
@@ -814,7 +1174,8 @@ __device__ LMResult lm_optimize(const Scope& sc, const BAWin& W, const BARun& ru
         sc.sync();  // every CTA has read the DIAG partials before Spart is overwritten
       }
       double chi = 0.0, mx = 0.0;
-      lin_phase<false, SMEM>(sc, W, cur, lambda, robust, run.delta, st, acc_all, chi, mx);
+      if (PACKED) lin_phase_packed<false, NB>(sc, W, cur, lambda, robust, run.delta, pst, wa, chi, mx);
+      else lin_phase<false, SMEM>(sc, W, cur, lambda, robust, run.delta, st, wa, chi, mx);
       double s1[1] = {chi};
       scope_reduce<1, 0>(sc, s1, dummy, W.part, parity, red);  // also publishes S, bs, bp
       currentChi = s1[0];
@@ -850,7 +1211,8 @@ __device__ LMResult lm_optimize(const Scope& sc, const BAWin& W, const BARun& ru
         cam_update(sc, W, cur);
         sc.sync();
         double tchi = 0.0, sc_l = 0.0;
-        backsub_phase(sc, W, cur, lambda, robust, run.delta, tchi, sc_l);
+        if (PACKED) backsub_phase_packed(sc, W, cur, lambda, robust, run.delta, pst, tchi, sc_l);
+        else backsub_phase(sc, W, cur, lambda, robust, run.delta, tchi, sc_l);
         {  // pose part of computeScale: sum x (lambda x + b)
           const int gt = sc.blk() * blockDim.x + threadIdx.x, gstride = sc.nblk() * blockDim.x;
           for (int i = gt; i < W.Ncf * 6; i += gstride) {
@@ -890,9 +1252,9 @@ __device__ LMResult lm_optimize(const Scope& sc, const BAWin& W, const BARun& ru
 
 // ------------------------------------------------------------------------------- whole window
 
-template <bool SMEM, class Scope>
+template <int MODE, class Scope>
 __device__ void solve_window(const Scope& sc, const BAWin& W, const BARun& run, WarpStage st,
-                             double* acc_all, double* pcg_sm, double* red) {
+                             PackStage pst, WorkArea wa, double* pcg_sm, double* red) {
   const int gt = sc.blk() * blockDim.x + threadIdx.x, gstride = sc.nblk() * blockDim.x;
   // setEstimate(SE3Quat(q, p).inverse()) (src/g2o_optimization.cc:45), points, levels
   for (int c = gt; c < W.Nc; c += gstride) {
@@ -906,7 +1268,11 @@ __device__ void solve_window(const Scope& sc, const BAWin& W, const BARun& run, 
     o[0] = qi[0]; o[1] = qi[1]; o[2] = qi[2]; o[3] = qi[3];
     o[4] = ti[0]; o[5] = ti[1]; o[6] = ti[2];
   }
-  for (int i = gt; i < W.Np * 3; i += gstride) W.pts[0][i] = W.pts_in[i];
+  for (int i = gt; i < W.Np * 3; i += gstride) {
+    const double v = W.pts_in[i];
+    W.pts[0][i] = v;
+    W.pts[1][i] = v;  // points without observations are never rewritten by the packed BACKSUB
+  }
   for (int o = gt; o < W.No; o += gstride) W.level[o] = 0;
   sc.sync();
   refresh_camRt(sc, W, 0);
@@ -919,8 +1285,8 @@ __device__ void solve_window(const Scope& sc, const BAWin& W, const BARun& run, 
   for (int pass = 0; pass < 2; pass++) {
     const bool robust = (pass == 0);
     double chi_init = 0.0;
-    LMResult r = lm_optimize<SMEM>(sc, W, run, pass == 0 ? run.it0 : run.it1, robust, cur, last_eval, st,
-                                   acc_all, pcg_sm, parity, red, &chi_init);
+    LMResult r = lm_optimize<MODE>(sc, W, run, pass == 0 ? run.it0 : run.it1, robust, cur, last_eval, st,
+                                   pst, wa, pcg_sm, parity, red, &chi_init);
     if (r.iters > 0) have_eval = true;
     if (writer && stats) {
       stats->iters[pass] = r.iters;
@@ -981,65 +1347,86 @@ __device__ void solve_window(const Scope& sc, const BAWin& W, const BARun& run, 
 }
 
 // Dynamic shared memory layout of one CTA:
-//   [red: 16*32+16 doubles][stage doubles: nw*27*kmax][accumulators: nw*acc_len_max][stage ints: nw*kmax]
-// The dense PCG of acc_mode 1 aliases the stage + accumulator doubles (idle during the solve).
-__device__ __forceinline__ WarpStage make_stage(unsigned char* smem, int kmax, int acc_len_max,
-                                                double** red_out, double** acc_out, double** pcg_out) {
-  const int nw = blockDim.x >> 5, wid = threadIdx.x >> 5;
-  double* red = reinterpret_cast<double*>(smem);
-  double* f0 = red + (16 * 32 + 16);
-  double* acc0 = f0 + (size_t)nw * kStageFields * kmax;
-  int* c0 = reinterpret_cast<int*>(acc0 + (size_t)nw * acc_len_max);
+//   [red: 16*32+16 doubles][work areas: nw * work_stride doubles][ints: nw * ints_per_warp]
+// A warp's work area holds its staging fields and its accumulator copy (the packed modes alias the
+// two); the dense PCG of the small-window modes aliases all work areas (idle during the solve).
+struct SmemViews {
+  double* red;
   WarpStage st;
-  st.kmax = kmax;
-  st.f = f0 + (size_t)wid * kStageFields * kmax;
-  st.cf = c0 + (size_t)wid * kmax;
-  *red_out = red;
-  *acc_out = acc0;
-  *pcg_out = f0;
-  return st;
+  PackStage pst;
+  WorkArea wa;
+  double* pcg;
+};
+
+__device__ __forceinline__ SmemViews make_views(unsigned char* smem, int kmax, int work_stride, int ints_per_warp) {
+  const int nw = blockDim.x >> 5, wid = threadIdx.x >> 5;
+  SmemViews v;
+  v.red = reinterpret_cast<double*>(smem);
+  double* work0 = v.red + (16 * 32 + 16);
+  int* ints0 = reinterpret_cast<int*>(work0 + (size_t)nw * work_stride);
+  v.st.kmax = kmax;
+  v.st.f = work0 + (size_t)wid * work_stride;
+  v.st.cf = ints0 + (size_t)wid * ints_per_warp;
+  v.pst.f = v.st.f;
+  v.pst.slot = reinterpret_cast<signed char*>(v.st.cf);
+  v.wa.base = work0;
+  v.wa.stride = work_stride;
+  v.pcg = work0;
+  return v;
+}
+
+template <class Scope>
+__device__ __forceinline__ void solve_window_dispatch(const Scope& sc, const BAWin& W, const BARun& run,
+                                                      const SmemViews& v) {
+  switch (W.acc_mode) {
+    case 3: solve_window<3>(sc, W, run, v.st, v.pst, v.wa, v.pcg, v.red); break;
+    case 2: solve_window<2>(sc, W, run, v.st, v.pst, v.wa, v.pcg, v.red); break;
+    case 1: solve_window<1>(sc, W, run, v.st, v.pst, v.wa, v.pcg, v.red); break;
+    default: solve_window<0>(sc, W, run, v.st, v.pst, v.wa, v.pcg, v.red); break;
+  }
 }
 
 // Batched windows: one thread-block cluster per window (cluster dims set at launch).
 __global__ void __launch_bounds__(256, 1)
-ba_window_cluster_kernel(const BAWin* __restrict__ wins, BARun run, int kmax_all, int acc_len_max) {
+ba_window_cluster_kernel(const BAWin* __restrict__ wins, BARun run, int kmax_all, int work_stride,
+                         int ints_per_warp) {
   extern __shared__ __align__(16) unsigned char smem[];
   ClusterScope sc;
-  double *red, *acc, *pcg;
-  WarpStage st = make_stage(smem, kmax_all, acc_len_max, &red, &acc, &pcg);
+  const SmemViews v = make_views(smem, kmax_all, work_stride, ints_per_warp);
   const int n_clusters = gridDim.x / sc.nblk();
   const int cid = blockIdx.x / sc.nblk();
   for (int w = cid; w < run.n_win; w += n_clusters) {
-    if (wins[w].acc_mode) solve_window<true>(sc, wins[w], run, st, acc, pcg, red);
-    else solve_window<false>(sc, wins[w], run, st, acc, pcg, red);
+    solve_window_dispatch(sc, wins[w], run, v);
     sc.sync();
   }
 }
 
 // One large problem on the whole (cooperative) grid.
 __global__ void __launch_bounds__(256, 1)
-ba_window_grid_kernel(const BAWin* __restrict__ wins, BARun run, int kmax_all, int acc_len_max) {
+ba_window_grid_kernel(const BAWin* __restrict__ wins, BARun run, int kmax_all, int work_stride,
+                      int ints_per_warp) {
   extern __shared__ __align__(16) unsigned char smem[];
   GridScope sc;
-  double *red, *acc, *pcg;
-  WarpStage st = make_stage(smem, kmax_all, acc_len_max, &red, &acc, &pcg);
+  const SmemViews v = make_views(smem, kmax_all, work_stride, ints_per_warp);
   for (int w = 0; w < run.n_win; w++) {
-    solve_window<false>(sc, wins[w], run, st, acc, pcg, red);
+    solve_window<0>(sc, wins[w], run, v.st, v.pst, v.wa, v.pcg, v.red);
     sc.sync();
   }
 }
 
-size_t ba_smem_bytes(int threads, int kmax, int acc_len_max, int pcg_doubles) {
+size_t ba_smem_bytes(int threads, int work_stride, int ints_per_warp) {
   const int nw = threads / 32;
-  size_t work = (size_t)nw * ((size_t)kStageFields * kmax + acc_len_max);
-  if (work < (size_t)pcg_doubles) work = pcg_doubles;  // dense PCG aliases stage + accumulators
-  // the int staging arrays follow nw*(27*kmax + acc_len_max) doubles; keep room for them after `work`
-  return (16 * 32 + 16) * sizeof(double) + work * sizeof(double) + (size_t)nw * kmax * sizeof(int);
+  return (16 * 32 + 16) * sizeof(double) + (size_t)nw * work_stride * sizeof(double) +
+         (size_t)nw * ints_per_warp * sizeof(int);
 }
 
-cudaError_t launch_ba_cluster(const BAWin* wins_dev, const BARun& run, int kmax, int acc_len_max,
-                              size_t smem, int n_clusters, int cluster_size, int threads,
+int ba_stage_doubles(int kmax) { return kStageFields * kmax; }
+int ba_pack_doubles() { return kPackFields * kPackSlots; }
+
+cudaError_t launch_ba_cluster(const BAWin* wins_dev, const BARun& run, int kmax, int work_stride,
+                              int ints_per_warp, int n_clusters, int cluster_size, int threads,
                               cudaStream_t stream) {
+  const size_t smem = ba_smem_bytes(threads, work_stride, ints_per_warp);
   cudaError_t e = cudaFuncSetAttribute(ba_window_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   if (cluster_size > 8) {
@@ -1058,11 +1445,11 @@ cudaError_t launch_ba_cluster(const BAWin* wins_dev, const BARun& run, int kmax,
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, ba_window_cluster_kernel, wins_dev, run, kmax, acc_len_max);
+  return cudaLaunchKernelEx(&cfg, ba_window_cluster_kernel, wins_dev, run, kmax, work_stride, ints_per_warp);
 }
 
 int ba_grid_capacity(int threads, int kmax) {
-  const size_t smem = ba_smem_bytes(threads, kmax, 0, 0);
+  const size_t smem = ba_smem_bytes(threads, ba_stage_doubles(kmax), kmax);
   if (cudaFuncSetAttribute(ba_window_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
   int per_sm = 0, dev = 0, sms = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ba_window_grid_kernel, threads, smem) != cudaSuccess) return 0;
@@ -1073,12 +1460,13 @@ int ba_grid_capacity(int threads, int kmax) {
 
 cudaError_t launch_ba_grid(const BAWin* wins_dev, const BARun& run, int kmax, int grid_blocks,
                            int threads, cudaStream_t stream) {
-  const size_t smem = ba_smem_bytes(threads, kmax, 0, 0);
+  const int ws = ba_stage_doubles(kmax);
+  const size_t smem = ba_smem_bytes(threads, ws, kmax);
   cudaError_t e = cudaFuncSetAttribute(ba_window_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   BARun r = run;
-  int km = kmax, al = 0;
-  void* args[] = {(void*)&wins_dev, (void*)&r, (void*)&km, (void*)&al};
+  int km = kmax, w2 = ws, ip = kmax;
+  void* args[] = {(void*)&wins_dev, (void*)&r, (void*)&km, (void*)&w2, (void*)&ip};
   return cudaLaunchCooperativeKernel((const void*)ba_window_grid_kernel, dim3((unsigned)grid_blocks),
                                      dim3((unsigned)threads), args, smem, stream);
 }

@@ -11,8 +11,10 @@ struct BAWin {
   int Nc, Ncf, Np, No;
   int nblk;         // stored 6x6 blocks of the reduced camera system (upper triangle, BSR)
   int kmax;         // max observations of one point (sizes the per-warp staging area)
-  int acc_mode;     // 1: warp-private shared-memory accumulation + dense in-smem PCG (small windows)
-                    // 0: fp64 atomics into the global block-sparse S + BSR PCG
+  int acc_mode;     // 0: fp64 atomics into the global block-sparse S + BSR PCG (large systems)
+                    // 1: warp-private shared-memory copies + dense in-smem PCG (<= 16 free cameras)
+                    // 2/3: packed groups, 1/2 register-resident blocks per lane (+ dense PCG)
+  int n_grp;        // packed modes: number of point groups
   int acc_len;      // acc_mode 1: doubles per accumulator copy = nblk*36 + Ncf*12
   double intr[4];   // fx fy cx cy
   // ---- inputs (immutable during a run)
@@ -21,6 +23,8 @@ struct BAWin {
   const double* uv;        // No*2
   const int* ocam;         // No     camera index
   const int* pt_start;     // Np+1   CSR over observations
+  const int* opt;          // No     point index of each observation (packed modes)
+  const int* grp_pt;       // n_grp+1 first point of each group: <= 32 observations and points per group
   const int* cam_free;     // Nc     dense index among free cameras or -1
   const int* row_ptr;      // Ncf+1  upper BSR of S: block row i -> [row_ptr[i], row_ptr[i+1])
   const int* col;          // nblk   block column (>= row), ascending inside a row, col[row_ptr[i]] == i

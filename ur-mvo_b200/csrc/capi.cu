@@ -123,8 +123,7 @@ struct urmvo_ba_plan {
   int B = 0;
   int total_c = 0, total_p = 0, total_o = 0;
   int kmax = 1;
-  int acc_len_max = 0;
-  size_t smem = 0;
+  int work_stride = 0, ints_per_warp = 0;
   int cluster_size = 1, threads = 256, n_clusters = 0;
   bool use_grid = false;
   int grid_blocks = 0;
@@ -143,6 +142,7 @@ struct WinHost {
   int Nc, Ncf, Np, No, nblk, kmax;
   bool dup_cam = false;  // some point is observed twice by the same camera
   int acc_mode = 0, acc_len = 0;
+  std::vector<int> grp_pt;  // packed modes: point groups with <= 32 observations and <= 32 points
   std::vector<int> pt_start, cam_free, row_ptr, col, lrow_ptr, lcol, lblk;
 };
 
@@ -286,39 +286,71 @@ extern "C" int urmvo_ba_plan_create(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, 
   const int max_np = [&] { int m = 0; for (auto& w : wh) m = std::max(m, w.Np); return m; }();
   const long long max_no = [&] { long long m = 0; for (auto& w : wh) m = std::max<long long>(m, w.No); return m; }();
   p->use_grid = (B == 1 && max_no >= 100000);
-  // accumulation mode per window: shared-memory copies + dense in-smem PCG when the reduced system
-  // is small (<= 16 free cameras) and fits, else global fp64 atomics + BSR PCG
-  const bool force_atomic = opts && opts->force_atomic == 1;
+  // accumulation mode per window (BAWin::acc_mode): packed groups + register-resident blocks when
+  // every point has <= 32 observations and S has <= 64 blocks; shared-memory RMW copies up to 16
+  // free cameras; global fp64 atomics + BSR PCG otherwise
+  const int force = opts ? opts->force_atomic : 0;  // 1: mode 0, 2: mode <= 1
   for (auto& w : wh) {
     w.acc_len = w.nblk * 36 + w.Ncf * 12;
-    w.acc_mode = (!p->use_grid && !force_atomic && !w.dup_cam && w.Ncf <= 16) ? 1 : 0;
+    w.acc_mode = 0;
+    if (!p->use_grid && force != 1 && !w.dup_cam && w.Ncf <= 16) {
+      w.acc_mode = 1;
+      if (force != 2 && w.kmax <= 32 && w.nblk <= 64) w.acc_mode = w.nblk <= 32 ? 2 : 3;
+    }
+    if (w.acc_mode >= 2) {
+      w.grp_pt.clear();
+      w.grp_pt.push_back(0);
+      int obs = 0, pts_in = 0;
+      for (int l = 0; l < w.Np; l++) {
+        const int k = w.pt_start[l + 1] - w.pt_start[l];
+        if (obs + k > 32 || pts_in == 32) { w.grp_pt.push_back(l); obs = 0; pts_in = 0; }
+        obs += k;
+        pts_in++;
+      }
+      w.grp_pt.push_back(w.Np);
+    }
   }
   const size_t smem_budget = 200 * 1024;
   for (;;) {
-    int acc_max = 0, pcg_d = 0;
-    for (auto& w : wh)
-      if (w.acc_mode) {
-        acc_max = std::max(acc_max, w.acc_len);
+    const int nw = p->threads / 32;
+    int stride = 0, pcg_d = 0, ints = p->kmax;
+    for (auto& w : wh) {
+      int need = 0;
+      if (w.acc_mode == 0) need = ba_stage_doubles(p->kmax);
+      else if (w.acc_mode == 1) need = ba_stage_doubles(p->kmax) + w.acc_len;
+      else { need = std::max(ba_pack_doubles(), w.acc_len); ints = std::max(ints, 128); }
+      stride = std::max(stride, need);
+      if (w.acc_mode >= 1) {
         const int n = w.Ncf * 6;
         pcg_d = std::max(pcg_d, n * n + 4 * n + 36 * w.Ncf);
       }
-    p->acc_len_max = acc_max;
-    p->smem = ba_smem_bytes(p->threads, p->kmax, acc_max, pcg_d);
-    if (p->smem <= smem_budget) break;
-    if (p->threads > 128 || (acc_max == 0 && p->threads > 64)) { p->threads -= 32; continue; }
-    if (acc_max > 0) {  // drop the largest accumulators to the atomic path
-      for (auto& w : wh)
-        if (w.acc_mode && w.acc_len == acc_max) w.acc_mode = 0;
-      continue;
     }
-    delete p;
-    return fail(URMVO_ERR_UNSUPPORTED, "local_ba: a point has too many observations for the per-warp staging area");
+    stride = std::max(stride, (pcg_d + nw - 1) / nw);
+    stride = (stride + 1) & ~1;  // keep the int area 16-byte aligned
+    p->work_stride = stride;
+    p->ints_per_warp = ints;
+    if (ba_smem_bytes(p->threads, stride, ints) <= smem_budget) break;
+    if (p->threads > 64) { p->threads -= 32; continue; }
+    // drop the most expensive small-window mode to the next cheaper one and retry
+    bool changed = false;
+    int worst = 0;
+    for (auto& w : wh) if (w.acc_mode == 1) worst = std::max(worst, w.acc_len);
+    for (auto& w : wh)
+      if (w.acc_mode == 1 && w.acc_len == worst) { w.acc_mode = 0; changed = true; }
+    if (!changed) {
+      delete p;
+      return fail(URMVO_ERR_UNSUPPORTED, "local_ba: a point has too many observations for the per-warp staging area");
+    }
+    p->threads = (opts && opts->threads > 0) ? opts->threads : 256;
   }
   int cs = (opts && opts->cluster_size > 0) ? opts->cluster_size : 0;
   if (cs == 0) {
+    // one CTA per SM is resident (register budget): give every window as many SMs as the batch
+    // leaves free, but at least ~128 points per CTA; a full batch (B >= #SMs) runs one window per SM,
+    // which avoids all cluster barriers and the idle time during the single-CTA PCG
     const int warps = p->threads / 32;
     cs = 1;
-    while (cs < 8 && max_np > cs * warps * 16) cs *= 2;
+    while (cs < 16 && cs * 2 * B <= ctx->n_sm && max_np > cs * warps * 16) cs *= 2;
   }
   if (cs != 1 && cs != 2 && cs != 4 && cs != 8 && cs != 16) { delete p; return fail(URMVO_ERR_ARG, "ba options: cluster_size must be 1,2,4,8 or 16"); }
   p->cluster_size = cs;
@@ -339,7 +371,10 @@ extern "C" int urmvo_ba_plan_create(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, 
   Arena A;
   const size_t TC = p->total_c, TP = p->total_p, TO = p->total_o;
   const size_t o_pose_in = A.take<double>(TC * 7), o_pts_in = A.take<double>(TP * 3), o_uv = A.take<double>(TO * 2);
-  const size_t o_ocam = A.take<int>(TO), o_pt_start = A.take<int>(TP + B), o_cam_free = A.take<int>(TC);
+  size_t sum_grp = 0;
+  for (auto& w : wh) sum_grp += w.grp_pt.size();
+  const size_t o_ocam = A.take<int>(TO), o_opt = A.take<int>(TO);
+  const size_t o_pt_start = A.take<int>(TP + B), o_cam_free = A.take<int>(TC), o_grp = A.take<int>(sum_grp + 1);
   const size_t o_row_ptr = A.take<int>(sum_ncf + B), o_col = A.take<int>(sum_blk);
   const size_t o_lrow_ptr = A.take<int>(sum_ncf + B), o_lcol = A.take<int>(sum_blk), o_lblk = A.take<int>(sum_blk);
   p->off_wins = A.take<BAWin>(B);
@@ -371,13 +406,13 @@ extern "C" int urmvo_ba_plan_create(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, 
 
   // ---- host staging of the small index arrays + descriptors (pinned), big arrays copied directly
   const size_t idx_bytes = upload_end - o_pt_start;
-  if (ctx->ensure_pinned(idx_bytes + (all_sorted ? 0 : TO * (sizeof(double) * 2 + sizeof(int))))) {
+  if (ctx->ensure_pinned(idx_bytes + (all_sorted ? 0 : TO * (sizeof(double) * 2 + 2 * sizeof(int))))) {
     urmvo_ba_plan_destroy(p);
     return fail(URMVO_ERR_CUDA, "cudaMallocHost failed");
   }
   unsigned char* H = (unsigned char*)ctx->pinned;  // mirrors [o_pt_start, upload_end)
   auto hp = [&](size_t off) { return H + (off - o_pt_start); };
-  size_t c_pt = 0, c_ncf = 0, c_blk = 0;
+  size_t c_pt = 0, c_ncf = 0, c_blk = 0, c_grp = 0;
   BAWin* hw = (BAWin*)hp(p->off_wins);
   for (int w = 0; w < B; w++) {
     const WinHost& W = wh[w];
@@ -385,6 +420,7 @@ extern "C" int urmvo_ba_plan_create(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, 
     int* h_pt_start = (int*)hp(o_pt_start) + c_pt;
     std::memcpy(h_pt_start, W.pt_start.data(), (W.Np + 1) * sizeof(int));
     std::memcpy((int*)hp(o_cam_free) + c0, W.cam_free.data(), W.Nc * sizeof(int));
+    if (!W.grp_pt.empty()) std::memcpy((int*)hp(o_grp) + c_grp, W.grp_pt.data(), W.grp_pt.size() * sizeof(int));
     std::memcpy((int*)hp(o_row_ptr) + c_ncf, W.row_ptr.data(), (W.Ncf + 1) * sizeof(int));
     std::memcpy((int*)hp(o_lrow_ptr) + c_ncf, W.lrow_ptr.data(), (W.Ncf + 1) * sizeof(int));
     if (W.nblk) std::memcpy((int*)hp(o_col) + c_blk, W.col.data(), W.nblk * sizeof(int));
@@ -403,6 +439,9 @@ extern "C" int urmvo_ba_plan_create(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, 
     d.uv = (const double*)(D + o_uv) + ob0 * 2;
     d.ocam = (const int*)(D + o_ocam) + ob0;
     d.pt_start = (const int*)(D + o_pt_start) + c_pt;
+    d.opt = (const int*)(D + o_opt) + ob0;
+    d.grp_pt = (const int*)(D + o_grp) + c_grp;
+    d.n_grp = W.grp_pt.empty() ? 0 : (int)W.grp_pt.size() - 1;
     d.cam_free = (const int*)(D + o_cam_free) + c0;
     d.row_ptr = (const int*)(D + o_row_ptr) + c_ncf;
     d.col = (const int*)(D + o_col) + c_blk;
@@ -431,6 +470,7 @@ extern "C" int urmvo_ba_plan_create(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, 
     c_pt += W.Np + 1;
     c_ncf += W.Ncf + 1;
     c_blk += W.nblk;
+    c_grp += W.grp_pt.size();
   }
   cudaStream_t s = ctx->stream;
   auto up = [&](size_t off, const void* src, size_t bytes) {
@@ -440,24 +480,29 @@ extern "C" int urmvo_ba_plan_create(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, 
   cudaError_t e2 = up(o_pose_in, poses, TC * 7 * sizeof(double));
   cudaError_t e3 = up(o_pts_in, pts, TP * 3 * sizeof(double));
   cudaError_t e4, e5;
+  cudaError_t e8 = cudaSuccess;
   if (all_sorted) {
     e4 = up(o_uv, uv, TO * 2 * sizeof(double));
     e5 = up(o_ocam, cam, TO * sizeof(int));
+    e8 = up(o_opt, pt, TO * sizeof(int));
   } else {
     double* huv = (double*)(H + idx_bytes);
     int* hcam = (int*)(huv + TO * 2);
+    int* hpt = hcam + TO;
     for (size_t o = 0; o < TO; o++) {
       huv[o * 2] = uv[(size_t)perm[o] * 2];
       huv[o * 2 + 1] = uv[(size_t)perm[o] * 2 + 1];
       hcam[o] = cam[perm[o]];
+      hpt[o] = pt[perm[o]];
     }
     e4 = up(o_uv, huv, TO * 2 * sizeof(double));
     e5 = up(o_ocam, hcam, TO * sizeof(int));
+    e8 = up(o_opt, hpt, TO * sizeof(int));
   }
   cudaError_t e6 = cudaMemsetAsync(D + p->off_stats, 0, sizeof(urmvo_ba_stats) * B, s);
   // the pinned staging buffer is reused by later calls: wait for the copies that read it
   cudaError_t e7 = cudaStreamSynchronize(s);
-  for (cudaError_t e : {e1, e2, e3, e4, e5, e6, e7})
+  for (cudaError_t e : {e1, e2, e3, e4, e5, e6, e7, e8})
     if (e != cudaSuccess) {
       urmvo_ba_plan_destroy(p);
       return fail(URMVO_ERR_CUDA, std::string("ba_plan_create upload: ") + cudaGetErrorString(e));
@@ -472,7 +517,7 @@ extern "C" int urmvo_ba_plan_run(urmvo_ba_plan* p) {
   const BAWin* wins = (const BAWin*)(p->dev + p->off_wins);
   cudaError_t e;
   if (p->use_grid) e = launch_ba_grid(wins, p->run, p->kmax, p->grid_blocks, p->threads, p->ctx->stream);
-  else e = launch_ba_cluster(wins, p->run, p->kmax, p->acc_len_max, p->smem, p->n_clusters, p->cluster_size, p->threads, p->ctx->stream);
+  else e = launch_ba_cluster(wins, p->run, p->kmax, p->work_stride, p->ints_per_warp, p->n_clusters, p->cluster_size, p->threads, p->ctx->stream);
   if (e != cudaSuccess) return fail(URMVO_ERR_CUDA, std::string("BA kernel launch: ") + cudaGetErrorString(e));
   p->ctx->launches++;
   return URMVO_OK;

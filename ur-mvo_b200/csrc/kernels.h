@@ -8,12 +8,13 @@
 namespace urmvo {
 
 // ---- ba_kernels.cu
-// Dynamic shared memory of the BA kernels: acc_len_max doubles of accumulators per warp (0 when no
-// window uses acc_mode 1), pcg_doubles for the dense in-smem PCG (aliases the work area).
-size_t ba_smem_bytes(int threads, int kmax, int acc_len_max, int pcg_doubles);
+// Dynamic shared memory of the BA kernels: work_stride doubles + ints_per_warp ints per warp.
+size_t ba_smem_bytes(int threads, int work_stride, int ints_per_warp);
+int ba_stage_doubles(int kmax);  // staging fields of the one-point-per-warp modes
+int ba_pack_doubles();           // staging fields of the packed modes
 // Batched windows: grid = n_clusters * cluster_size CTAs, one cluster per window.
-cudaError_t launch_ba_cluster(const BAWin* wins_dev, const BARun& run, int kmax, int acc_len_max,
-                              size_t smem, int n_clusters, int cluster_size, int threads,
+cudaError_t launch_ba_cluster(const BAWin* wins_dev, const BARun& run, int kmax, int work_stride,
+                              int ints_per_warp, int n_clusters, int cluster_size, int threads,
                               cudaStream_t stream);
 // One (or a few) large problems on a cooperative grid. grid_blocks <= co-resident capacity.
 cudaError_t launch_ba_grid(const BAWin* wins_dev, const BARun& run, int kmax, int grid_blocks,
