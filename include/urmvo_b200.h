@@ -101,6 +101,10 @@ int urmvo_ba_plan_download(urmvo_ba_plan* plan, double* poses, double* pts, uint
                            urmvo_ba_stats* stats);    /* synchronises the stream */
 void urmvo_ba_plan_destroy(urmvo_ba_plan* plan);
 
+/* Development aid: SM cycles spent per phase by window 0 of the BA launches since the last reset
+ * (0 LIN diag, 1 LIN, 2 reduce, 3 PCG, 4 camera update, 5 BACKSUB, 6 reduce, 7 unused). */
+int urmvo_debug_ba_timing(uint64_t* cycles8, int reset);
+
 /* ------------------------------------------------------------------ pose-only (B7-B8) */
 
 /* Batched FrameOptimization: frame f owns observations [obs_off[f], obs_off[f+1]).

@@ -24,6 +24,13 @@
 
 namespace urmvo {
 
+// Phase timing (SM cycles) of window 0 as seen by thread 0 of its first CTA: a development aid read
+// back by urmvo_debug_ba_timing().  0 LIN(diag) 1 LIN 2 reduce 3 PCG 4 cam update 5 BACKSUB
+// 6 reduce/decide 7 classify
+__device__ unsigned long long g_ba_timing[8];
+#define BA_T0() const long long _t0 = clock64()
+#define BA_T1(slot) do { if (timer) g_ba_timing[slot] += (unsigned long long)(clock64() - _t0); } while (0)
+
 // ------------------------------------------------------------------------------- edge math
 
 struct EdgeLin {
@@ -782,13 +789,24 @@ __device__ void lin_phase_packed(const Scope& sc, const BAWin& W, int cur, doubl
   const double* __restrict__ camRt = W.camRt[cur];
   const double* __restrict__ pts = W.pts[cur];
   const double K[4] = {W.intr[0], W.intr[1], W.intr[2], W.intr[3]};
+  // the descriptor lives in global memory: take its fields into registers once
+  const int* __restrict__ grp_pt = W.grp_pt;
+  const int* __restrict__ pt_start = W.pt_start;
+  const int* __restrict__ opt = W.opt;
+  const int* __restrict__ ocam = W.ocam;
+  const int* __restrict__ cam_free = W.cam_free;
+  const uint8_t* __restrict__ level = W.level;
+  const double2* __restrict__ uvp = reinterpret_cast<const double2*>(W.uv);
+  double* __restrict__ Dinv_out = W.Dinv;
+  double* __restrict__ bl_out = W.bl;
+  const int Ncf = W.Ncf, n_grp = W.n_grp, nblk = W.nblk;
   // blocks owned by this lane: dense upper layout, block b = row_ptr[ci] + (cj - ci)
   int bci[NB], bcj[NB];
 #pragma unroll
   for (int nb = 0; nb < NB; nb++) {
     const int blk = lane + 32 * nb;
     bci[nb] = -1; bcj[nb] = -1;
-    if (blk < W.nblk) {
+    if (blk < nblk) {
       int ci = 0;
       while (W.row_ptr[ci + 1] <= blk) ci++;
       bci[nb] = ci;
@@ -804,29 +822,47 @@ __device__ void lin_phase_packed(const Scope& sc, const BAWin& W, int cur, doubl
 #pragma unroll
   for (int e = 0; e < 12; e++) accb[e] = 0.0;
 
-  for (int g = gw; g < W.n_grp; g += gstride) {
-    const int p0 = W.grp_pt[g], np = W.grp_pt[g + 1] - p0;
-    const int o0 = W.pt_start[p0], nobs = W.pt_start[p0 + np] - o0;
+  // software pipeline: the header and the per-lane observation record of the NEXT group are
+  // fetched while the current group is processed, so the L2 round trips overlap the arithmetic
+  int n_p0 = 0, n_np = 0, n_o0 = 0, n_nobs = 0, n_pl = 0, n_c = 0, n_lev = 1;
+  double2 n_uv = make_double2(0.0, 0.0);
+  auto fetch = [&](int g) {
+    n_p0 = grp_pt[g];
+    n_np = grp_pt[g + 1] - n_p0;
+    n_o0 = pt_start[n_p0];
+    n_nobs = pt_start[n_p0 + n_np] - n_o0;
+    n_pl = n_p0; n_c = 0; n_lev = 1;
+    if (lane < n_nobs) {
+      const int o = n_o0 + lane;
+      n_pl = opt[o];
+      n_lev = level[o];
+      n_c = ocam[o];
+      n_uv = uvp[o];
+    }
+  };
+  if (gw < n_grp) fetch(gw);
+  for (int g = gw; g < n_grp; g += gstride) {
+    const int p0 = n_p0, np = n_np, o0 = n_o0, nobs = n_nobs;
+    const int pl = n_pl, c = n_c, lev = n_lev;
+    const double2 uv = n_uv;
     reinterpret_cast<int*>(st.slot)[lane] = -1;       // 32 * 16 bytes = 128 ints of 0xFF
     reinterpret_cast<int*>(st.slot)[lane + 32] = -1;
     reinterpret_cast<int*>(st.slot)[lane + 64] = -1;
     reinterpret_cast<int*>(st.slot)[lane + 96] = -1;
     __syncwarp();
     const bool valid = lane < nobs;
-    const int o = o0 + lane;
-    const int pl = valid ? W.opt[o] : p0;
     const int pi = pl - p0;
-    const int s0 = W.pt_start[pl] - o0, s1 = W.pt_start[pl + 1] - o0;
+    const int s0 = pt_start[pl] - o0, s1 = pt_start[pl + 1] - o0;
+    const double X[3] = {pts[pl * 3], pts[pl * 3 + 1], pts[pl * 3 + 2]};
+    const int cf_ld = cam_free[c];
+    if (g + gstride < n_grp) fetch(g + gstride);
     double hc[6] = {0, 0, 0, 0, 0, 0}, blc[3] = {0, 0, 0};
     int cf = -1;
     double B[6];
-    if (valid && !W.level[o]) {
-      const int c = W.ocam[o];
+    if (valid && !lev) {
       const double* Rt = camRt + (size_t)c * 12;
-      const double X[3] = {pts[pl * 3], pts[pl * 3 + 1], pts[pl * 3 + 2]};
       double pc[3], pz[3], e0, e1, w;
       map_point(Rt, X, pc);
-      const double2 uv = *reinterpret_cast<const double2*>(W.uv + (size_t)o * 2);
       const double e2 = edge_error(pc, uv.x, uv.y, K, e0, e1, pz);
       chi_acc += huber_rho(e2, delta, robust, w);
       double Jx[6];
@@ -841,7 +877,7 @@ __device__ void lin_phase_packed(const Scope& sc, const BAWin& W, int cur, doubl
       hc[5] = B[2] * Jx[2] + B[5] * Jx[5];
 #pragma unroll
       for (int a = 0; a < 3; a++) blc[a] = -(B[a] * e0 + B[3 + a] * e1);
-      cf = W.cam_free[c];
+      cf = cf_ld;
       if (cf >= 0) {
         double Jp[12];
         edge_jac_pose(pz, K, Jp);
@@ -879,7 +915,7 @@ __device__ void lin_phase_packed(const Scope& sc, const BAWin& W, int cur, doubl
     if (DIAG) {
       if (valid) maxdiag_acc = fmax(maxdiag_acc, fmax(fabs(h[0]), fmax(fabs(h[3]), fabs(h[5]))));
       __syncwarp();
-      if (lane < W.Ncf) {
+      if (lane < Ncf) {
         for (int q = 0; q < np; q++) {
           const int s = st.slot[q * kPackCam + lane];
           if (s < 0) continue;
@@ -900,9 +936,9 @@ __device__ void lin_phase_packed(const Scope& sc, const BAWin& W, int cur, doubl
       sym3_inverse(hl, Di);
       if (lane == s0) {
 #pragma unroll
-        for (int a = 0; a < 6; a++) W.Dinv[(size_t)pl * 6 + a] = Di[a];
+        for (int a = 0; a < 6; a++) Dinv_out[(size_t)pl * 6 + a] = Di[a];
 #pragma unroll
-        for (int a = 0; a < 3; a++) W.bl[(size_t)pl * 3 + a] = bl[a];
+        for (int a = 0; a < 3; a++) bl_out[(size_t)pl * 3 + a] = bl[a];
       }
       if (cf >= 0) {
         double A[6];
@@ -951,18 +987,19 @@ __device__ void lin_phase_packed(const Scope& sc, const BAWin& W, int cur, doubl
         for (int a = 0; a < 6; a++) {
           const double j0 = st.Jp(a, si), j1 = st.Jp(6 + a, si);
 #pragma unroll
-          for (int b = 0; b < 6; b++) accS[nb][a * 6 + b] += j0 * T[b] + j1 * T[6 + b];
+          for (int b = 0; b < 6; b++)  // two chained FMAs per element (not mul + fma + add)
+            accS[nb][a * 6 + b] = fma(j1, T[6 + b], fma(j0, T[b], accS[nb][a * 6 + b]));
         }
       }
-      if (lane < W.Ncf) {
+      if (lane < Ncf) {
         const int s = sl[lane];
         if (s >= 0) {
           const double g0 = st.g(0, s), g1 = st.g(1, s), w0 = st.we(0, s), w1 = st.we(1, s);
 #pragma unroll
           for (int a = 0; a < 6; a++) {
             const double j0 = st.Jp(a, s), j1 = st.Jp(6 + a, s);
-            accb[a] -= j0 * g0 + j1 * g1;
-            accb[6 + a] -= j0 * w0 + j1 * w1;
+            accb[a] = fma(-j1, g1, fma(-j0, g0, accb[a]));
+            accb[6 + a] = fma(-j1, w1, fma(-j0, w0, accb[6 + a]));
           }
         }
       }
@@ -1009,23 +1046,55 @@ __device__ void backsub_phase_packed(const Scope& sc, const BAWin& W, int cur, d
   const double* __restrict__ camRt = W.camRt[cur];
   const double* __restrict__ camRtT = W.camRt[tr];
   const double K[4] = {W.intr[0], W.intr[1], W.intr[2], W.intr[3]};
-  for (int g = gw; g < W.n_grp; g += gstride) {
-    const int p0 = W.grp_pt[g], np = W.grp_pt[g + 1] - p0;
-    const int o0 = W.pt_start[p0], nobs = W.pt_start[p0 + np] - o0;
+  const int* __restrict__ grp_pt = W.grp_pt;
+  const int* __restrict__ pt_start = W.pt_start;
+  const int* __restrict__ opt = W.opt;
+  const int* __restrict__ ocam = W.ocam;
+  const int* __restrict__ cam_free = W.cam_free;
+  const uint8_t* __restrict__ level = W.level;
+  const double2* __restrict__ uvp = reinterpret_cast<const double2*>(W.uv);
+  const double* __restrict__ pts_cur = W.pts[cur];
+  double* __restrict__ pts_tr = W.pts[tr];
+  const double* __restrict__ Dinv_in = W.Dinv;
+  const double* __restrict__ bl_in = W.bl;
+  const double* __restrict__ xp = W.xp;
+  const int n_grp = W.n_grp;
+  int n_p0 = 0, n_np = 0, n_o0 = 0, n_nobs = 0, n_pl = 0, n_c = 0, n_lev = 1;
+  double2 n_uv = make_double2(0.0, 0.0);
+  auto fetch = [&](int g) {
+    n_p0 = grp_pt[g];
+    n_np = grp_pt[g + 1] - n_p0;
+    n_o0 = pt_start[n_p0];
+    n_nobs = pt_start[n_p0 + n_np] - n_o0;
+    n_pl = n_p0; n_c = 0; n_lev = 1;
+    if (lane < n_nobs) {
+      const int o = n_o0 + lane;
+      n_pl = opt[o];
+      n_lev = level[o];
+      n_c = ocam[o];
+      n_uv = uvp[o];
+    }
+  };
+  if (gw < n_grp) fetch(gw);
+  for (int g = gw; g < n_grp; g += gstride) {
+    const int o0 = n_o0, nobs = n_nobs;
     const bool valid = lane < nobs;
-    const int o = o0 + lane;
-    const int pl = valid ? W.opt[o] : p0;
-    const int s0 = W.pt_start[pl] - o0, s1 = W.pt_start[pl + 1] - o0;
-    const double X[3] = {W.pts[cur][pl * 3], W.pts[cur][pl * 3 + 1], W.pts[cur][pl * 3 + 2]};
+    const int pl = n_pl;
+    const int c = n_c;
+    const double2 uv = n_uv;
+    const bool active = valid && !n_lev;
+    const int s0 = pt_start[pl] - o0, s1 = pt_start[pl + 1] - o0;
+    const double X[3] = {pts_cur[pl * 3], pts_cur[pl * 3 + 1], pts_cur[pl * 3 + 2]};
+    const int cf_ld = cam_free[c];
+    double Di[6], bb[3];
+#pragma unroll
+    for (int a = 0; a < 6; a++) Di[a] = Dinv_in[(size_t)pl * 6 + a];
+#pragma unroll
+    for (int a = 0; a < 3; a++) bb[a] = bl_in[(size_t)pl * 3 + a];
+    if (g + gstride < n_grp) fetch(g + gstride);
     double c3[3] = {0, 0, 0};
-    int c = 0;
-    double2 uv = make_double2(0.0, 0.0);
-    bool active = false;
-    if (valid && !W.level[o]) {
-      active = true;
-      c = W.ocam[o];
-      uv = *reinterpret_cast<const double2*>(W.uv + (size_t)o * 2);
-      const int cf = W.cam_free[c];
+    if (active) {
+      const int cf = cf_ld;
       if (cf >= 0) {
         const double* Rt = camRt + (size_t)c * 12;
         double pc[3], pz[3], e0, e1, w, Jp[12], Jx[6];
@@ -1037,7 +1106,7 @@ __device__ void backsub_phase_packed(const Scope& sc, const BAWin& W, int cur, d
         double t0 = 0, t1 = 0;
 #pragma unroll
         for (int a = 0; a < 6; a++) {
-          const double xa = __ldcg(W.xp + cf * 6 + a);
+          const double xa = __ldcg(xp + cf * 6 + a);
           t0 += Jp[a] * xa;
           t1 += Jp[6 + a] * xa;
         }
@@ -1057,15 +1126,14 @@ __device__ void backsub_phase_packed(const Scope& sc, const BAWin& W, int cur, d
 #pragma unroll
         for (int a = 0; a < 3; a++) cs[a] += st.h(a, s);
       }
-      const double* Di = W.Dinv + (size_t)pl * 6;
-      const double b0 = W.bl[(size_t)pl * 3], b1 = W.bl[(size_t)pl * 3 + 1], b2 = W.bl[(size_t)pl * 3 + 2];
+      const double b0 = bb[0], b1 = bb[1], b2 = bb[2];
       const double r0 = b0 - cs[0], r1 = b1 - cs[1], r2 = b2 - cs[2];
       const double x0 = Di[0] * r0 + Di[1] * r1 + Di[2] * r2;
       const double x1 = Di[1] * r0 + Di[3] * r1 + Di[4] * r2;
       const double x2 = Di[2] * r0 + Di[4] * r1 + Di[5] * r2;
       Xn[0] += x0; Xn[1] += x1; Xn[2] += x2;
       if (lane == s0) {
-        W.pts[tr][pl * 3] = Xn[0]; W.pts[tr][pl * 3 + 1] = Xn[1]; W.pts[tr][pl * 3 + 2] = Xn[2];
+        pts_tr[pl * 3] = Xn[0]; pts_tr[pl * 3 + 1] = Xn[1]; pts_tr[pl * 3 + 2] = Xn[2];
         scale_acc += x0 * (lambda * x0 + b0) + x1 * (lambda * x1 + b1) + x2 * (lambda * x2 + b2);
       }
     }
@@ -1123,6 +1191,7 @@ __device__ LMResult lm_optimize(const Scope& sc, const BAWin& W, const BARun& ru
   constexpr bool SMEM = MODE >= 1;
   constexpr bool PACKED = MODE >= 2;
   constexpr int NB = MODE == 3 ? 2 : 1;
+  const bool timer = W.stats == run.timing_stats && sc.blk() == 0 && threadIdx.x == 0;
   LMResult res = {0, 0, 0, 0.0, 0.0};
   double lambda = 0.0, ni = 2.0;
   double currentChi = 0.0;
@@ -1137,8 +1206,12 @@ __device__ LMResult lm_optimize(const Scope& sc, const BAWin& W, const BARun& ru
         sc.sync();
       }
       double chi = 0.0, mx = 0.0;
-      if (PACKED) lin_phase_packed<true, NB>(sc, W, cur, 0.0, robust, run.delta, pst, wa, chi, mx);
-      else lin_phase<true, SMEM>(sc, W, cur, 0.0, robust, run.delta, st, wa, chi, mx);
+      {
+        BA_T0();
+        if (PACKED) lin_phase_packed<true, NB>(sc, W, cur, 0.0, robust, run.delta, pst, wa, chi, mx);
+        else lin_phase<true, SMEM>(sc, W, cur, 0.0, robust, run.delta, st, wa, chi, mx);
+        BA_T1(0);
+      }
       double s1[1] = {chi}, m1[1] = {mx};
       scope_reduce<1, 1>(sc, s1, m1, W.part, parity, red);
       double mp = 0.0;
@@ -1174,13 +1247,22 @@ __device__ LMResult lm_optimize(const Scope& sc, const BAWin& W, const BARun& ru
         sc.sync();  // every CTA has read the DIAG partials before Spart is overwritten
       }
       double chi = 0.0, mx = 0.0;
-      if (PACKED) lin_phase_packed<false, NB>(sc, W, cur, lambda, robust, run.delta, pst, wa, chi, mx);
-      else lin_phase<false, SMEM>(sc, W, cur, lambda, robust, run.delta, st, wa, chi, mx);
+      {
+        BA_T0();
+        if (PACKED) lin_phase_packed<false, NB>(sc, W, cur, lambda, robust, run.delta, pst, wa, chi, mx);
+        else lin_phase<false, SMEM>(sc, W, cur, lambda, robust, run.delta, st, wa, chi, mx);
+        BA_T1(1);
+      }
       double s1[1] = {chi};
-      scope_reduce<1, 0>(sc, s1, dummy, W.part, parity, red);  // also publishes S, bs, bp
+      {
+        BA_T0();
+        scope_reduce<1, 0>(sc, s1, dummy, W.part, parity, red);  // also publishes S, bs, bp
+        BA_T1(2);
+      }
       currentChi = s1[0];
       int pcg_it = 0;
       bool ok2;
+      const long long _tp = clock64();
       if (SMEM) {
         if (sc.blk() == 0) {
           ok2 = pcg_dense_smem(sc, W, lambda, run.pcg_tol, run.pcg_max_iter, pcg_sm, pcg_it);
@@ -1205,14 +1287,24 @@ __device__ LMResult lm_optimize(const Scope& sc, const BAWin& W, const BARun& ru
         sc.sync();
       }
       res.pcg_iters += pcg_it;
+      if (timer) g_ba_timing[3] += (unsigned long long)(clock64() - _tp);
       double tempChi = 1.7976931348623157e308;
       double scale = 0.0;
       if (ok2) {
-        cam_update(sc, W, cur);
-        sc.sync();
+        {
+          BA_T0();
+          cam_update(sc, W, cur);
+          sc.sync();
+          BA_T1(4);
+        }
         double tchi = 0.0, sc_l = 0.0;
-        if (PACKED) backsub_phase_packed(sc, W, cur, lambda, robust, run.delta, pst, tchi, sc_l);
-        else backsub_phase(sc, W, cur, lambda, robust, run.delta, tchi, sc_l);
+        {
+          BA_T0();
+          if (PACKED) backsub_phase_packed(sc, W, cur, lambda, robust, run.delta, pst, tchi, sc_l);
+          else backsub_phase(sc, W, cur, lambda, robust, run.delta, tchi, sc_l);
+          BA_T1(5);
+        }
+        const long long _t6 = clock64();
         {  // pose part of computeScale: sum x (lambda x + b)
           const int gt = sc.blk() * blockDim.x + threadIdx.x, gstride = sc.nblk() * blockDim.x;
           for (int i = gt; i < W.Ncf * 6; i += gstride) {
@@ -1225,6 +1317,7 @@ __device__ LMResult lm_optimize(const Scope& sc, const BAWin& W, const BARun& ru
         tempChi = s2[0];
         scale = s2[1];
         last_eval = cur ^ 1;
+        if (timer) g_ba_timing[6] += (unsigned long long)(clock64() - _t6);
       }
       rho = (currentChi - tempChi) / (scale + 1e-3);
       if (rho > 0 && isfinite(tempChi)) {
@@ -1469,6 +1562,15 @@ cudaError_t launch_ba_grid(const BAWin* wins_dev, const BARun& run, int kmax, in
   void* args[] = {(void*)&wins_dev, (void*)&r, (void*)&km, (void*)&w2, (void*)&ip};
   return cudaLaunchCooperativeKernel((const void*)ba_window_grid_kernel, dim3((unsigned)grid_blocks),
                                      dim3((unsigned)threads), args, smem, stream);
+}
+
+cudaError_t ba_timing_read(unsigned long long* out, bool reset) {
+  cudaError_t e = cudaMemcpyFromSymbol(out, g_ba_timing, sizeof(unsigned long long) * 8);
+  if (e == cudaSuccess && reset) {
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    e = cudaMemcpyToSymbol(g_ba_timing, z, sizeof(z));
+  }
+  return e;
 }
 
 }  // namespace urmvo

@@ -65,6 +65,7 @@ struct BARun {
   int pcg_max_iter;
   int it0, it1;
   int n_win;
+  const void* timing_stats;  // the window whose stats pointer equals this records phase cycles
 };
 
 // One pose-only frame.

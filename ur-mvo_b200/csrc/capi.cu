@@ -366,6 +366,7 @@ extern "C" int urmvo_ba_plan_create(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, 
   p->run.pcg_tol = (opts && opts->pcg_tol > 0) ? opts->pcg_tol : 1e-10;
   p->run.pcg_max_iter = (opts && opts->pcg_max_iter > 0) ? opts->pcg_max_iter : std::min(1000, std::max(60, 12 * max_ncf));
   p->run.it0 = it0; p->run.it1 = it1; p->run.n_win = B;
+  p->run.timing_stats = nullptr;
 
   // ---- device layout
   Arena A;
@@ -467,6 +468,7 @@ extern "C" int urmvo_ba_plan_create(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, 
     d.pts_out = (double*)(D + p->off_pts_out) + p0 * 3;
     d.inlier = D + p->off_inlier + ob0;
     d.stats = (urmvo_ba_stats*)(D + p->off_stats) + w;
+    if (w == 0) p->run.timing_stats = d.stats;
     c_pt += W.Np + 1;
     c_ncf += W.Ncf + 1;
     c_blk += W.nblk;
@@ -543,6 +545,13 @@ extern "C" int urmvo_ba_plan_download(urmvo_ba_plan* p, double* poses, double* p
   CU_TRY(cudaStreamSynchronize(s));
   if (inlier && !p->perm.empty())
     for (int o = 0; o < p->total_o; o++) inlier[p->perm[o]] = tmp[o];
+  return URMVO_OK;
+}
+
+extern "C" int urmvo_debug_ba_timing(uint64_t* cycles8, int reset) {
+  unsigned long long t[8];
+  CU_TRY(ba_timing_read(t, reset != 0));
+  for (int i = 0; i < 8; i++) cycles8[i] = t[i];
   return URMVO_OK;
 }
 

@@ -21,6 +21,7 @@ cudaError_t launch_ba_grid(const BAWin* wins_dev, const BARun& run, int kmax, in
                            int threads, cudaStream_t stream);
 // Max co-resident CTAs of the grid kernel on the current device for this configuration.
 int ba_grid_capacity(int threads, int kmax);
+cudaError_t ba_timing_read(unsigned long long* out, bool reset);
 constexpr int kBAPartWidth = 8;  // doubles per CTA and buffer in BAWin::part (+8 flag doubles)
 
 // ---- pose_kernels.cu

@@ -9,7 +9,7 @@ _LIB = None
 EXPORTED_SYMBOLS = [
     "urmvo_version", "urmvo_last_error", "urmvo_create", "urmvo_destroy", "urmvo_stream", "urmvo_sync",
     "urmvo_launch_count", "urmvo_local_ba", "urmvo_local_ba_batch", "urmvo_ba_plan_create",
-    "urmvo_ba_plan_run", "urmvo_ba_plan_download", "urmvo_ba_plan_destroy", "urmvo_pose_only_batch",
+    "urmvo_ba_plan_run", "urmvo_ba_plan_download", "urmvo_ba_plan_destroy", "urmvo_debug_ba_timing", "urmvo_pose_only_batch",
     "urmvo_pose_plan_create", "urmvo_pose_plan_run", "urmvo_pose_plan_download", "urmvo_pose_plan_destroy",
     "urmvo_two_view", "urmvo_tv_plan_create", "urmvo_tv_plan_run_ransac", "urmvo_tv_plan_download_hyps",
     "urmvo_tv_plan_reconstruct", "urmvo_tv_plan_destroy",
@@ -117,6 +117,12 @@ class Context:
 
     def sync(self):
         _check(self._L.urmvo_sync(self._h), "urmvo_sync")
+
+    def ba_timing(self, reset=True):
+        """SM cycles per BA phase of window 0 since the last reset (development aid)."""
+        out = (C.c_uint64 * 8)()
+        _check(self._L.urmvo_debug_ba_timing(out, C.c_int(1 if reset else 0)), "urmvo_debug_ba_timing")
+        return list(out)
 
     @property
     def launches(self):
