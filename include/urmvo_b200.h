@@ -101,6 +101,27 @@ int urmvo_ba_plan_download(urmvo_ba_plan* plan, double* poses, double* pts, uint
                            urmvo_ba_stats* stats);    /* synchronises the stream */
 void urmvo_ba_plan_destroy(urmvo_ba_plan* plan);
 
+/* ---- point-sharded large BA over NCCL (one process per GPU) ----
+ * Every rank passes ALL cameras (replicated) and ITS OWN contiguous range of points with their
+ * observations (pt indices local to the range).  Per damped trial the ranks all-reduce the reduced
+ * camera system [S | b_s | b_p | chi2] and the trial cost over NCCL/NVLink; everything else is local.
+ *   rank 0: urmvo_nccl_unique_id(id) -> broadcast the 128 bytes (torch.distributed, MPI, ...) ->
+ *   every rank: urmvo_comm_init(ctx, rank, world, id).  Without a communicator the plan runs alone.
+ *   urmvo_ba_covisibility fills the upper-triangular free-camera co-visibility of the local
+ *   observations (returns Ncf); OR the matrices of all ranks and pass the result as `covis` so that
+ *   every rank builds the same block structure of S (NULL: the local structure, world size 1 only).
+ *   Run with urmvo_ba_plan_run (synchronous here), read back with urmvo_ba_plan_download
+ *   (poses: all cameras, identical on every rank; pts / inlier: the rank's own). */
+int urmvo_nccl_unique_id(uint8_t* id128);
+int urmvo_comm_init(urmvo_ctx* ctx, int rank, int world, const uint8_t* id128);
+int urmvo_ba_covisibility(int Nc, const uint8_t* fixed, int Np, int No, const int32_t* cam, const int32_t* pt,
+                          uint8_t* upper /* Ncf*Ncf */);
+int urmvo_sharded_ba_create(urmvo_ctx* ctx, urmvo_ba_plan** plan, int Nc, const double* poses,
+                            const uint8_t* fixed, int Np, const double* pts, int No, const double* uv,
+                            const int32_t* cam, const int32_t* pt, const double* intr, double chi2_thr,
+                            int it0, int it1, const uint8_t* covis, const urmvo_ba_options* opts);
+int urmvo_sharded_ba_run(urmvo_ba_plan* plan);
+
 /* Development aid: SM cycles spent per phase by window 0 of the BA launches since the last reset
  * (0 LIN diag, 1 LIN, 2 reduce, 3 PCG, 4 camera update, 5 BACKSUB, 6 reduce, 7 unused). */
 int urmvo_debug_ba_timing(uint64_t* cycles8, int reset);

@@ -287,3 +287,35 @@ def test_two_view_rejects_bad_input(ctx):
     few["sets"] = np.zeros((1, 8), dtype=np.int32)
     with pytest.raises(U.UrmvoError, match="fewer than 8"):
         ctx.two_view(few)
+
+
+# ------------------------------------------------------------------------------- point-sharded BA
+
+def test_sharded_ba_single_rank_matches_oracle(oracle, ctx):
+    """The NCCL-sharded phase-kernel path with a world of one rank (all-reduces are identities)."""
+    p = synth.make_ba(77, 40, 1500, 8.0, 14, 2, 0.02)
+    plan = U.ShardedBAPlan(ctx, U.shard_points(p, 0, 1), covis=U.ba_covisibility(p))
+    plan.run()
+    gp, gx, gi, gs = plan.download()
+    op, ox, oi, os_ = oracle.local_ba(p)
+    assert abs(gs.chi2_final[1] - os_.chi2_final[1]) <= REL_COST * abs(os_.chi2_final[1])
+    assert np.abs(gp - op).max() <= POSE_TOL and np.array_equal(gi, oi)
+    assert list(gs.iters) == list(os_.iters)[:2]
+    plan.close()
+
+
+def test_sharded_ba_two_ranks_over_nccl(oracle):
+    """Two GPUs, one process each (torchrun): skipped on a single-GPU box."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                          "127.0.0.1", "--master-port", "29533", os.path.join(root, "scripts", "sharded_ba.py"), "small", "--check"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = [l for l in out.stdout.splitlines() if "rel cost diff" in l][0]
+    rel = float(line.split("rel cost diff")[1].split(";")[0])
+    assert rel < REL_COST and "inlier mismatches 0" in line

@@ -109,3 +109,31 @@ def test_reference_arm_non_zero_ranks_do_no_work():
     out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
                           "--warmup", "1"], env=env, capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_shard_points_covers_every_point_and_observation_once(world):
+    from urmvo_b200.capi import shard_points
+    prob = synth.make_ba(5, 30, 800, 6.0, 10, 2, 0.02)
+    seen_p, seen_o, sizes = [], [], []
+    for r in range(world):
+        loc = shard_points(prob, r, world)
+        p0, p1 = loc["point_range"]; o0, o1 = loc["obs_range"]
+        seen_p += list(range(p0, p1)); seen_o += list(range(o0, o1)); sizes.append(o1 - o0)
+        assert loc["poses"].shape == prob["poses"].shape            # cameras replicated
+        assert loc["obs_pt"].min(initial=0) >= 0 and loc["obs_pt"].max(initial=0) < max(p1 - p0, 1)
+        assert np.array_equal(prob["obs_pt"][o0:o1] - p0, loc["obs_pt"])
+        assert np.array_equal(prob["uv"][o0:o1], loc["uv"])
+    assert seen_p == list(range(prob["pts"].shape[0])) and seen_o == list(range(prob["uv"].shape[0]))
+    assert max(sizes) - min(sizes) <= 2 * np.bincount(prob["obs_pt"]).max()   # balanced by observations
+
+
+def test_covisibility_union_over_shards_equals_global():
+    from urmvo_b200.capi import shard_points, ba_covisibility
+    prob = synth.make_ba(6, 24, 500, 5.0, 8, 2, 0.0)
+    full = ba_covisibility(prob)
+    acc = np.zeros_like(full)
+    for r in range(3):
+        acc |= ba_covisibility(shard_points(prob, r, 3))
+    assert np.array_equal(acc, full)
+    assert np.array_equal(full, np.triu(full)) and full.diagonal().all()

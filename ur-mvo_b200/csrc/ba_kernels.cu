@@ -1345,11 +1345,10 @@ __device__ LMResult lm_optimize(const Scope& sc, const BAWin& W, const BARun& ru
 
 // ------------------------------------------------------------------------------- whole window
 
-template <int MODE, class Scope>
-__device__ void solve_window(const Scope& sc, const BAWin& W, const BARun& run, WarpStage st,
-                             PackStage pst, WorkArea wa, double* pcg_sm, double* red) {
+// setEstimate(SE3Quat(q, p).inverse()) (src/g2o_optimization.cc:45), points, levels, derived R|t.
+template <class Scope>
+__device__ void window_init(const Scope& sc, const BAWin& W) {
   const int gt = sc.blk() * blockDim.x + threadIdx.x, gstride = sc.nblk() * blockDim.x;
-  // setEstimate(SE3Quat(q, p).inverse()) (src/g2o_optimization.cc:45), points, levels
   for (int c = gt; c < W.Nc; c += gstride) {
     double q[4], t[3], qi[4], ti[3];
     const double* in = W.pose_in + (size_t)c * 7;
@@ -1370,7 +1369,65 @@ __device__ void solve_window(const Scope& sc, const BAWin& W, const BARun& run, 
   sc.sync();
   refresh_camRt(sc, W, 0);
   sc.sync();
+}
 
+// src/g2o_optimization.cc:129-135 (pass 0) / :150-154 (pass 1).  e->chi2() reads the error cached by
+// the last computeActiveErrors() (state `last_eval`, which is the rejected trial when the final
+// trial was rejected); isDepthPositive() re-maps with the CURRENT estimate.  Level-1 edges keep the
+// classification error of the first pass.  Returns this thread's count of newly excluded edges.
+template <class Scope>
+__device__ double window_classify(const Scope& sc, const BAWin& W, double chi2_thr, int pass, int cur,
+                                  int last_eval, bool have_eval) {
+  const int gt = sc.blk() * blockDim.x + threadIdx.x, gstride = sc.nblk() * blockDim.x;
+  const double K[4] = {W.intr[0], W.intr[1], W.intr[2], W.intr[3]};
+  double n_l1 = 0.0;
+  for (int l = gt; l < W.Np; l += gstride) {
+    for (int o = W.pt_start[l]; o < W.pt_start[l + 1]; o++) {
+      const int c = W.ocam[o];
+      double pc[3], e0, e1;
+      const double2 uv = *reinterpret_cast<const double2*>(W.uv + (size_t)o * 2);
+      const int lev = W.level[o];
+      if (pass == 1 && lev == 1) continue;  // cached chi2 > thr: inlier[] already 0 from pass 0
+      map_point(W.camRt[last_eval] + (size_t)c * 12, W.pts[last_eval] + (size_t)l * 3, pc);
+      const double e2 = have_eval ? edge_error(pc, uv.x, uv.y, K, e0, e1) : 0.0;
+      map_point(W.camRt[cur] + (size_t)c * 12, W.pts[cur] + (size_t)l * 3, pc);
+      const bool depth_pos = pc[2] > 0.0;
+      if (pass == 0) {
+        // level 1: chi2 test failed; level 2: only the depth test failed (its cached chi2 stays
+        // <= thr, so the final flag depends on the depth at the final estimate)
+        const int nl = (e2 > chi2_thr) ? 1 : (!depth_pos ? 2 : 0);
+        W.level[o] = (uint8_t)nl;
+        W.inlier[o] = 0;
+        n_l1 += nl ? 1.0 : 0.0;
+      } else if (lev == 2) {
+        W.inlier[o] = depth_pos ? 1 : 0;
+      } else {
+        W.inlier[o] = (e2 <= chi2_thr && depth_pos) ? 1 : 0;
+      }
+    }
+  }
+  return n_l1;
+}
+
+// write back T_wc = estimate().inverse() and the points (:164-176)
+template <class Scope>
+__device__ void window_finish(const Scope& sc, const BAWin& W, int cur) {
+  const int gt = sc.blk() * blockDim.x + threadIdx.x, gstride = sc.nblk() * blockDim.x;
+  for (int c = gt; c < W.Nc; c += gstride) {
+    const double* in = W.cam[cur] + (size_t)c * 7;
+    double qi[4], ti[3];
+    se3_inverse(in, in + 4, qi, ti);
+    double* o = W.pose_out + (size_t)c * 7;
+    o[0] = qi[0]; o[1] = qi[1]; o[2] = qi[2]; o[3] = qi[3];
+    o[4] = ti[0]; o[5] = ti[1]; o[6] = ti[2];
+  }
+  for (int i = gt; i < W.Np * 3; i += gstride) W.pts_out[i] = W.pts[cur][i];
+}
+
+template <int MODE, class Scope>
+__device__ void solve_window(const Scope& sc, const BAWin& W, const BARun& run, WarpStage st,
+                             PackStage pst, WorkArea wa, double* pcg_sm, double* red) {
+  window_init(sc, W);
   int cur = 0, last_eval = 0, parity = 0;
   bool have_eval = false;  // has any computeActiveErrors() run? (g2o's cached _error is zero before)
   urmvo_ba_stats* stats = reinterpret_cast<urmvo_ba_stats*>(W.stats);
@@ -1389,37 +1446,7 @@ __device__ void solve_window(const Scope& sc, const BAWin& W, const BARun& run, 
       stats->lambda_final[pass] = r.lambda;
       if (pass == 0) stats->chi2_initial = chi_init;
     }
-    // src/g2o_optimization.cc:129-135 / :150-154.  e->chi2() reads the error cached by the last
-    // computeActiveErrors() (state `last_eval`, which is the rejected trial when the final trial
-    // was rejected); isDepthPositive() re-maps with the CURRENT estimate.  Level-1 edges keep the
-    // classification error of the first pass.
-    const double K[4] = {W.intr[0], W.intr[1], W.intr[2], W.intr[3]};
-    double n_l1 = 0.0;
-    for (int l = gt; l < W.Np; l += gstride) {
-      for (int o = W.pt_start[l]; o < W.pt_start[l + 1]; o++) {
-        const int c = W.ocam[o];
-        double pc[3], e0, e1;
-        const double2 uv = *reinterpret_cast<const double2*>(W.uv + (size_t)o * 2);
-        const int lev = W.level[o];
-        if (pass == 1 && lev == 1) continue;  // cached chi2 > thr: inlier[] already 0 from pass 0
-        map_point(W.camRt[last_eval] + (size_t)c * 12, W.pts[last_eval] + (size_t)l * 3, pc);
-        const double e2 = have_eval ? edge_error(pc, uv.x, uv.y, K, e0, e1) : 0.0;
-        map_point(W.camRt[cur] + (size_t)c * 12, W.pts[cur] + (size_t)l * 3, pc);
-        const bool depth_pos = pc[2] > 0.0;
-        if (pass == 0) {
-          // level 1: chi2 test failed; level 2: only the depth test failed (its cached chi2 stays
-          // <= thr, so the final flag depends on the depth at the final estimate)
-          const int nl = (e2 > run.chi2_thr) ? 1 : (!depth_pos ? 2 : 0);
-          W.level[o] = (uint8_t)nl;
-          W.inlier[o] = 0;
-          n_l1 += nl ? 1.0 : 0.0;
-        } else if (lev == 2) {
-          W.inlier[o] = depth_pos ? 1 : 0;
-        } else {
-          W.inlier[o] = (e2 <= run.chi2_thr && depth_pos) ? 1 : 0;
-        }
-      }
-    }
+    const double n_l1 = window_classify(sc, W, run.chi2_thr, pass, cur, last_eval, have_eval);
     if (pass == 0) {
       double s1[1] = {n_l1}, dummy[1];
       scope_reduce<1, 0>(sc, s1, dummy, W.part, parity, red);
@@ -1427,16 +1454,7 @@ __device__ void solve_window(const Scope& sc, const BAWin& W, const BARun& run, 
     }
     sc.sync();
   }
-  // write back T_wc = estimate().inverse() and the points (:164-176)
-  for (int c = gt; c < W.Nc; c += gstride) {
-    const double* in = W.cam[cur] + (size_t)c * 7;
-    double qi[4], ti[3];
-    se3_inverse(in, in + 4, qi, ti);
-    double* o = W.pose_out + (size_t)c * 7;
-    o[0] = qi[0]; o[1] = qi[1]; o[2] = qi[2]; o[3] = qi[3];
-    o[4] = ti[0]; o[5] = ti[1]; o[6] = ti[2];
-  }
-  for (int i = gt; i < W.Np * 3; i += gstride) W.pts_out[i] = W.pts[cur][i];
+  window_finish(sc, W, cur);
 }
 
 // Dynamic shared memory layout of one CTA:
@@ -1515,6 +1533,251 @@ size_t ba_smem_bytes(int threads, int work_stride, int ints_per_warp) {
 
 int ba_stage_doubles(int kmax) { return kStageFields * kmax; }
 int ba_pack_doubles() { return kPackFields * kPackSlots; }
+
+// ------------------------------------------------------------------------------- point-sharded BA
+//
+// One large problem sharded by POINT over the ranks of one node: every rank holds
+// all cameras and a contiguous range of points with their observations.  The persistent kernel is
+// cut at the two places where ranks must agree — the reduced camera system [S | b_s | b_p | chi2]
+// and the trial cost [chi2', scale] — and NCCL sums those buffers over NVLink between the phase
+// kernels (csrc/capi.cu drives the loop; every rank takes identical decisions from identical
+// reduced values, so no decision is ever broadcast).  Each phase is the same device code as the
+// persistent kernel, on the whole cooperative grid.
+struct ShardState {
+  double lambda, ni, currentChi, rho, chi_initial;
+  int cur, last_eval, have_eval, parity;
+  int robust, it, qmax, ok2;
+  int iters, trials, pcg_iters, n_level1;
+  // decisions for the host loop
+  int cont_trials, terminate;
+};
+
+// scal layout inside the reduce buffer: [0] chi2 (LIN) [1] max diag(Hll) [2] trial chi2 [3] scale
+__global__ void __launch_bounds__(256, 1)
+k_sh_init(const BAWin* __restrict__ wins, ShardState* stt) {
+  GridScope sc;
+  window_init(sc, wins[0]);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    ShardState z = {};
+    z.ni = 2.0;
+    *stt = z;
+  }
+}
+
+__global__ void __launch_bounds__(256, 1)
+k_sh_begin_pass(ShardState* stt, int robust) {
+  stt->robust = robust; stt->it = 0; stt->iters = 0; stt->trials = 0; stt->pcg_iters = 0;
+  stt->cont_trials = 0; stt->terminate = 0; stt->qmax = 0;
+}
+
+__global__ void __launch_bounds__(256, 1)
+k_sh_lin(const BAWin* __restrict__ wins, BARun run, ShardState* stt, double* scal, int kmax, int diag) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  GridScope sc;
+  const BAWin& W = wins[0];
+  const SmemViews v = make_views(smem, kmax, kStageFields * kmax, kmax);
+  int parity = stt->parity;
+  zero_system(sc, W, diag != 0, 0.0);
+  sc.sync();
+  double chi = 0.0, mx = 0.0;
+  if (diag) lin_phase<true, false>(sc, W, stt->cur, 0.0, stt->robust != 0, run.delta, v.st, v.wa, chi, mx);
+  else lin_phase<false, false>(sc, W, stt->cur, stt->lambda, stt->robust != 0, run.delta, v.st, v.wa, chi, mx);
+  double s1[1] = {chi}, m1[1] = {mx};
+  scope_reduce<1, 1>(sc, s1, m1, W.part, parity, v.red);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    scal[0] = s1[0];
+    scal[1] = m1[0];
+    stt->parity = parity;
+  }
+}
+
+// after the DIAG all-reduce: lambda = tau * max |H_jj| (computeLambdaInit)
+__global__ void k_sh_lambda(const BAWin* __restrict__ wins, ShardState* stt, const double* scal) {
+  const BAWin& W = wins[0];
+  __shared__ double sm[256];
+  double m = 0.0;
+  for (int i = threadIdx.x; i < W.Ncf * 6; i += blockDim.x) m = fmax(m, fabs(W.hdiag[i]));
+  sm[threadIdx.x] = m;
+  __syncthreads();
+  for (int off = blockDim.x >> 1; off > 0; off >>= 1) {
+    if ((int)threadIdx.x < off) sm[threadIdx.x] = fmax(sm[threadIdx.x], sm[threadIdx.x + off]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    stt->lambda = 1e-5 * fmax(sm[0], scal[1]);
+    stt->ni = 2.0;
+    if (stt->robust) stt->chi_initial = scal[0];
+  }
+}
+
+// after the [S | b_s | b_p | chi2] all-reduce: damp, PCG, trial cameras, back-substitution, trial cost
+__global__ void __launch_bounds__(256, 1)
+k_sh_solve(const BAWin* __restrict__ wins, BARun run, ShardState* stt, double* scal, int kmax, int rank) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  GridScope sc;
+  const BAWin& W = wins[0];
+  const SmemViews v = make_views(smem, kmax, kStageFields * kmax, kmax);
+  int parity = stt->parity;
+  const int cur = stt->cur;
+  const double lambda = stt->lambda;
+  damp_diagonal(sc, W, lambda);
+  sc.sync();
+  int pcg_it = 0;
+  const bool ok2 = pcg_phase(sc, W, run.pcg_tol, run.pcg_max_iter, W.part, parity, v.red, pcg_it);
+  sc.sync();
+  double tchi = 0.0, sc_l = 0.0;
+  if (ok2) {
+    cam_update(sc, W, cur);
+    sc.sync();
+    backsub_phase(sc, W, cur, lambda, stt->robust != 0, run.delta, tchi, sc_l);
+    if (rank == 0) {  // the pose part of computeScale is counted once
+      const int gt = blockIdx.x * blockDim.x + threadIdx.x, gstride = gridDim.x * blockDim.x;
+      for (int i = gt; i < W.Ncf * 6; i += gstride) {
+        const double x = __ldcg(W.xp + i);
+        sc_l += x * (lambda * x + __ldcg(W.bp + i));
+      }
+    }
+  }
+  double s2[2] = {tchi, sc_l}, dummy[1];
+  scope_reduce<2, 0>(sc, s2, dummy, W.part, parity, v.red);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    scal[2] = s2[0];
+    scal[3] = s2[1];
+    stt->ok2 = ok2 ? 1 : 0;
+    stt->pcg_iters += pcg_it;
+    stt->parity = parity;
+  }
+}
+
+// after the [chi2', scale] all-reduce: gain ratio, damping update, accept / reject (one thread)
+__global__ void k_sh_decide(ShardState* stt, const double* scal, ShardState* host_copy) {
+  ShardState s = *stt;
+  const double currentChi = scal[0];
+  const double tempChi = s.ok2 ? scal[2] : 1.7976931348623157e308;
+  const double scale = s.ok2 ? scal[3] : 0.0;
+  if (s.ok2) { s.last_eval = s.cur ^ 1; s.have_eval = 1; }
+  const double rho = (currentChi - tempChi) / (scale + 1e-3);
+  bool lambda_bad = false;
+  s.currentChi = currentChi;
+  if (rho > 0 && isfinite(tempChi)) {
+    double alpha = 1. - pow((2 * rho - 1), 3);
+    alpha = fmin(alpha, 2. / 3.);
+    s.lambda *= fmax(1. / 3., alpha);
+    s.ni = 2;
+    s.currentChi = tempChi;
+    s.cur ^= 1;
+  } else {
+    s.lambda *= s.ni;
+    s.ni *= 2;
+    if (!isfinite(s.lambda)) lambda_bad = true;
+  }
+  s.qmax++;
+  s.trials++;
+  s.rho = rho;
+  s.cont_trials = (!lambda_bad && rho < 0 && s.qmax < 10) ? 1 : 0;
+  if (!s.cont_trials) {
+    s.iters = s.it + 1;
+    s.terminate = (s.qmax == 10 || rho == 0 || lambda_bad || !isfinite(s.lambda)) ? 1 : 0;
+    s.it++;
+    s.qmax = 0;
+  }
+  *stt = s;
+  *host_copy = s;
+}
+
+__global__ void __launch_bounds__(256, 1)
+k_sh_classify(const BAWin* __restrict__ wins, BARun run, ShardState* stt, int pass) {
+  __shared__ double red[16 * 32 + 16];
+  GridScope sc;
+  const BAWin& W = wins[0];
+  int parity = stt->parity;
+  const double n_l1 = window_classify(sc, W, run.chi2_thr, pass, stt->cur, stt->last_eval, stt->have_eval != 0);
+  double s1[1] = {n_l1}, dummy[1];
+  scope_reduce<1, 0>(sc, s1, dummy, W.part, parity, red);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (pass == 0) stt->n_level1 = (int)s1[0];
+    stt->parity = parity;
+    urmvo_ba_stats* st = reinterpret_cast<urmvo_ba_stats*>(W.stats);
+    st->iters[pass] = stt->iters;
+    st->trials[pass] = stt->trials;
+    st->pcg_iters[pass] = stt->pcg_iters;
+    st->chi2_final[pass] = stt->currentChi;
+    st->lambda_final[pass] = stt->lambda;
+    if (pass == 0) { st->chi2_initial = stt->chi_initial; st->n_level1 = (int)s1[0]; }
+  }
+}
+
+__global__ void __launch_bounds__(256, 1)
+k_sh_finish(const BAWin* __restrict__ wins, ShardState* stt) {
+  GridScope sc;
+  window_finish(sc, wins[0], stt->cur);
+}
+
+size_t shard_state_bytes() { return sizeof(ShardState); }
+
+static cudaError_t coop(const void* k, int grid, int threads, void** args, size_t smem, cudaStream_t s) {
+  return cudaLaunchCooperativeKernel(k, dim3((unsigned)grid), dim3((unsigned)threads), args, smem, s);
+}
+
+int shard_grid_capacity(int threads, int kmax) {
+  const size_t smem = ba_smem_bytes(threads, kStageFields * kmax, kmax);
+  int dev = 0, sms = 0, best = 1 << 30;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const void* ks[2] = {(const void*)k_sh_lin, (const void*)k_sh_solve};
+  for (const void* k : ks) {
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, threads, smem) != cudaSuccess) return 0;
+    best = per_sm * sms < best ? per_sm * sms : best;
+  }
+  return best;
+}
+
+cudaError_t launch_sh_init(const BAWin* w, void* stt, int grid, int threads, cudaStream_t s) {
+  void* args[] = {(void*)&w, (void*)&stt};
+  return coop((const void*)k_sh_init, grid, threads, args, 0, s);
+}
+cudaError_t launch_sh_begin_pass(void* stt, int robust, cudaStream_t s) {
+  k_sh_begin_pass<<<1, 1, 0, s>>>((ShardState*)stt, robust);
+  return cudaGetLastError();
+}
+cudaError_t launch_sh_lin(const BAWin* w, const BARun& run, void* stt, double* scal, int kmax, int diag,
+                          int grid, int threads, cudaStream_t s) {
+  BARun r = run;
+  void* args[] = {(void*)&w, (void*)&r, (void*)&stt, (void*)&scal, (void*)&kmax, (void*)&diag};
+  return coop((const void*)k_sh_lin, grid, threads, args, ba_smem_bytes(threads, kStageFields * kmax, kmax), s);
+}
+cudaError_t launch_sh_lambda(const BAWin* w, void* stt, const double* scal, cudaStream_t s) {
+  k_sh_lambda<<<1, 256, 0, s>>>(w, (ShardState*)stt, scal);
+  return cudaGetLastError();
+}
+cudaError_t launch_sh_solve(const BAWin* w, const BARun& run, void* stt, double* scal, int kmax, int rank,
+                            int grid, int threads, cudaStream_t s) {
+  BARun r = run;
+  void* args[] = {(void*)&w, (void*)&r, (void*)&stt, (void*)&scal, (void*)&kmax, (void*)&rank};
+  return coop((const void*)k_sh_solve, grid, threads, args, ba_smem_bytes(threads, kStageFields * kmax, kmax), s);
+}
+cudaError_t launch_sh_decide(void* stt, const double* scal, void* host_copy, cudaStream_t s) {
+  k_sh_decide<<<1, 1, 0, s>>>((ShardState*)stt, scal, (ShardState*)host_copy);
+  return cudaGetLastError();
+}
+cudaError_t launch_sh_classify(const BAWin* w, const BARun& run, void* stt, int pass, int grid, int threads,
+                               cudaStream_t s) {
+  BARun r = run;
+  void* args[] = {(void*)&w, (void*)&r, (void*)&stt, (void*)&pass};
+  return coop((const void*)k_sh_classify, grid, threads, args, 0, s);
+}
+cudaError_t launch_sh_finish(const BAWin* w, void* stt, int grid, int threads, cudaStream_t s) {
+  void* args[] = {(void*)&w, (void*)&stt};
+  return coop((const void*)k_sh_finish, grid, threads, args, 0, s);
+}
+// the host reads these two fields of the mirrored ShardState after every trial
+void shard_flags(const void* host_copy, int* cont_trials, int* terminate) {
+  const ShardState* s = (const ShardState*)host_copy;
+  *cont_trials = s->cont_trials;
+  *terminate = s->terminate;
+}
 
 cudaError_t launch_ba_cluster(const BAWin* wins_dev, const BARun& run, int kmax, int work_stride,
                               int ints_per_warp, int n_clusters, int cluster_size, int threads,

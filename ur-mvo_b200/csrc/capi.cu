@@ -4,6 +4,8 @@
 // decisions of EpipolarGeometry::reconstruct; all arithmetic of the path runs in the kernels.
 // There is no CPU fallback: every entry point needs a live sm_100 device.
 
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -35,6 +37,38 @@ int fail(int code, const std::string& msg) {
 
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
+// NCCL is loaded lazily with dlopen so that the single-GPU path has no NCCL dependency; inside a
+// torch process this resolves to the libnccl.so.2 torch already loaded.
+struct NcclApi {
+  void* handle = nullptr;
+  struct UniqueId { char internal[128]; };
+  int (*GetUniqueId)(UniqueId*) = nullptr;
+  int (*CommInitRank)(void**, int, UniqueId, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  static constexpr int kFloat64 = 8, kSum = 0, kMax = 2;
+  bool load(std::string& err) {
+    if (handle) return true;
+    for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+      handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+      if (handle) break;
+    }
+    if (!handle) { err = std::string("dlopen(libnccl.so.2) failed: ") + dlerror(); return false; }
+    GetUniqueId = (decltype(GetUniqueId))dlsym(handle, "ncclGetUniqueId");
+    CommInitRank = (decltype(CommInitRank))dlsym(handle, "ncclCommInitRank");
+    AllReduce = (decltype(AllReduce))dlsym(handle, "ncclAllReduce");
+    CommDestroy = (decltype(CommDestroy))dlsym(handle, "ncclCommDestroy");
+    GetErrorString = (decltype(GetErrorString))dlsym(handle, "ncclGetErrorString");
+    if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy || !GetErrorString) {
+      err = "libnccl.so.2 lacks an expected symbol";
+      return false;
+    }
+    return true;
+  }
+};
+NcclApi g_nccl;
+
 // Bump allocator over one device allocation (and a mirrored pinned host staging area).
 struct Arena {
   size_t size = 0;
@@ -54,6 +88,9 @@ struct urmvo_ctx {
   int n_sm = 0;
   cudaStream_t stream = nullptr;
   int64_t launches = 0;
+  // optional NCCL communicator for the point-sharded BA (urmvo_comm_init)
+  void* comm = nullptr;
+  int rank = 0, world = 1;
   // reusable pinned staging buffer for the one-shot entry points
   void* pinned = nullptr;
   size_t pinned_size = 0;
@@ -103,7 +140,9 @@ extern "C" int urmvo_create(urmvo_ctx** out, int device) {
 extern "C" void urmvo_destroy(urmvo_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
-  if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+  if (c->stream) cudaStreamDestroy(c->stream);
   if (c->pinned) cudaFreeHost(c->pinned);
   delete c;
 }
@@ -134,6 +173,13 @@ struct urmvo_ba_plan {
   size_t off_wins = 0, off_pose_out = 0, off_pts_out = 0, off_inlier = 0, off_stats = 0;
   // observation permutation (point-major sort) when the caller's order was not sorted
   std::vector<int> perm;  // sorted position -> caller index (empty = identity)
+  // point-sharded mode: [scal(8) | S | pad | b_s | b_p | hdiag] is one contiguous all-reduce buffer
+  bool sharded = false;
+  size_t off_scal = 0, off_hdiag = 0;
+  size_t n_reduce_main = 0;   // doubles from scal through b_p
+  int n6 = 0;
+  void* shard_state = nullptr;       // device
+  void* shard_state_host = nullptr;  // pinned + mapped mirror written by k_sh_decide
 };
 
 namespace {
@@ -150,7 +196,8 @@ struct WinHost {
 // obs_pt / obs_cam are window-local; `order` (size No) receives the point-major permutation
 // (sorted position -> original index), `sorted` tells whether it is the identity.
 int build_window(int Nc, const uint8_t* fixed, int Np, int No, const int32_t* obs_cam,
-                 const int32_t* obs_pt, WinHost& w, std::vector<int>& order, bool& sorted) {
+                 const int32_t* obs_pt, WinHost& w, std::vector<int>& order, bool& sorted,
+                 const uint8_t* covis = nullptr) {
   w.Nc = Nc; w.Np = Np; w.No = No;
   w.cam_free.assign(Nc, -1);
   w.Ncf = 0;
@@ -190,7 +237,14 @@ int build_window(int Nc, const uint8_t* fixed, int Np, int No, const int32_t* ob
   const int n = w.Ncf;
   std::vector<std::vector<int>> rows(n);
   for (int i = 0; i < n; i++) rows[i].push_back(i);
-  if (n <= 64) {
+  if (covis) {  // structure agreed between the ranks of a point-sharded problem (Ncf x Ncf, upper)
+    for (int i = 0; i < n; i++) {
+      rows[i].clear();
+      rows[i].push_back(i);
+      for (int j = i + 1; j < n; j++)
+        if (covis[(size_t)i * n + j]) rows[i].push_back(j);
+    }
+  } else if (n <= 64) {
     for (int i = 0; i < n; i++) {  // dense upper triangle: no scan of the observations needed
       rows[i].resize(n - i);
       for (int j = i; j < n; j++) rows[i][j - i] = j;
@@ -241,15 +295,19 @@ int build_window(int Nc, const uint8_t* fixed, int Np, int No, const int32_t* ob
 
 extern "C" void urmvo_ba_plan_destroy(urmvo_ba_plan* p) {
   if (!p) return;
-  if (p->dev) { cudaSetDevice(p->ctx->device); cudaFree(p->dev); }
+  cudaSetDevice(p->ctx->device);
+  if (p->dev) cudaFree(p->dev);
+  if (p->shard_state) cudaFree(p->shard_state);
+  if (p->shard_state_host) cudaFreeHost(p->shard_state_host);
   delete p;
 }
 
-extern "C" int urmvo_ba_plan_create(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, const int32_t* cam_off,
-                                    const int32_t* pt_off, const int32_t* obs_off, const double* poses,
-                                    const uint8_t* fixed, const double* pts, const double* uv,
-                                    const int32_t* cam, const int32_t* pt, const double* intr,
-                                    double chi2_thr, int it0, int it1, const urmvo_ba_options* opts) {
+static int ba_plan_create_impl(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, const int32_t* cam_off,
+                               const int32_t* pt_off, const int32_t* obs_off, const double* poses,
+                               const uint8_t* fixed, const double* pts, const double* uv,
+                               const int32_t* cam, const int32_t* pt, const double* intr,
+                               double chi2_thr, int it0, int it1, const urmvo_ba_options* opts,
+                               bool sharded, const uint8_t* covis) {
   if (!ctx || !out) return fail(URMVO_ERR_ARG, "ba_plan_create: null context / out");
   *out = nullptr;
   if (B <= 0 || !cam_off || !pt_off || !obs_off || !poses || !fixed || !pts || !uv || !cam || !pt || !intr)
@@ -270,7 +328,7 @@ extern "C" int urmvo_ba_plan_create(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, 
     const int Nc = cam_off[w + 1] - cam_off[w], Np = pt_off[w + 1] - pt_off[w], No = obs_off[w + 1] - obs_off[w];
     if (Nc <= 0 || Np < 0 || No < 0) { delete p; return fail(URMVO_ERR_ARG, "ba_plan_create: bad window offsets"); }
     bool sorted = true;
-    int rc = build_window(Nc, fixed + cam_off[w], Np, No, cam + obs_off[w], pt + obs_off[w], wh[w], order, sorted);
+    int rc = build_window(Nc, fixed + cam_off[w], Np, No, cam + obs_off[w], pt + obs_off[w], wh[w], order, sorted, covis);
     if (rc != URMVO_OK) { delete p; return rc; }
     all_sorted = all_sorted && sorted;
     for (int o = 0; o < No; o++) perm[obs_off[w] + o] = obs_off[w] + order[o];
@@ -285,7 +343,8 @@ extern "C" int urmvo_ba_plan_create(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, 
   if (p->threads % 32 != 0 || p->threads < 64 || p->threads > 256) { delete p; return fail(URMVO_ERR_ARG, "ba options: threads must be 64..256 and a multiple of 32"); }
   const int max_np = [&] { int m = 0; for (auto& w : wh) m = std::max(m, w.Np); return m; }();
   const long long max_no = [&] { long long m = 0; for (auto& w : wh) m = std::max<long long>(m, w.No); return m; }();
-  p->use_grid = (B == 1 && max_no >= 100000);
+  p->use_grid = (B == 1 && max_no >= 100000) || sharded;
+  p->sharded = sharded;
   // accumulation mode per window (BAWin::acc_mode): packed groups + register-resident blocks when
   // every point has <= 32 observations and S has <= 64 blocks; shared-memory RMW copies up to 16
   // free cameras; global fp64 atomics + BSR PCG otherwise
@@ -357,7 +416,7 @@ extern "C" int urmvo_ba_plan_create(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, 
   p->n_clusters = B;
   int nblk_scope = cs;
   if (p->use_grid) {
-    p->grid_blocks = ba_grid_capacity(p->threads, p->kmax);
+    p->grid_blocks = sharded ? shard_grid_capacity(p->threads, p->kmax) : ba_grid_capacity(p->threads, p->kmax);
     if (p->grid_blocks <= 0) { delete p; return fail(URMVO_ERR_CUDA, "ba_plan_create: occupancy query failed"); }
     nblk_scope = p->grid_blocks;
   }
@@ -383,8 +442,15 @@ extern "C" int urmvo_ba_plan_create(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, 
   size_t o_cam[2], o_camRt[2], o_pts[2];
   for (int k = 0; k < 2; k++) { o_cam[k] = A.take<double>(TC * 7); o_camRt[k] = A.take<double>(TC * 12); o_pts[k] = A.take<double>(TP * 3); }
   const size_t o_level = A.take<uint8_t>(TO);
+  const size_t o_scal = A.take<double>(32);  // sharded: head of the contiguous all-reduce buffer
   const size_t o_S = A.take<double>((size_t)sum_blk * 36);
   const size_t o_vec = A.take<double>((size_t)(sum_ncf + B) * 6 * 8);  // bs bp hdiag xp r z p Ap (indexed by c_ncf, which counts Ncf+1 per window)
+  if (sharded) {
+    p->off_scal = o_scal;
+    p->n6 = wh[0].Ncf * 6;
+    p->n_reduce_main = (o_vec - o_scal) / sizeof(double) + (size_t)2 * p->n6;  // scal | S | pad | b_s | b_p
+    p->off_hdiag = o_vec + (size_t)2 * p->n6 * sizeof(double);
+  }
   const size_t o_Minv = A.take<double>((size_t)(sum_ncf + B) * 36);
   const size_t o_Dinv = A.take<double>(TP * 6), o_bl = A.take<double>(TP * 3);
   const size_t part_per_win = (size_t)2 * nblk_scope * kBAPartWidth + 8;
@@ -502,6 +568,9 @@ extern "C" int urmvo_ba_plan_create(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, 
     e8 = up(o_opt, hpt, TO * sizeof(int));
   }
   cudaError_t e6 = cudaMemsetAsync(D + p->off_stats, 0, sizeof(urmvo_ba_stats) * B, s);
+  if (sharded && e6 == cudaSuccess) e6 = cudaMemsetAsync(D + o_scal, 0, o_vec - o_scal + (size_t)8 * p->n6 * sizeof(double), s);
+  if (sharded && e6 == cudaSuccess) e6 = cudaMalloc(&p->shard_state, shard_state_bytes());
+  if (sharded && e6 == cudaSuccess) e6 = cudaHostAlloc(&p->shard_state_host, shard_state_bytes(), cudaHostAllocMapped);
   // the pinned staging buffer is reused by later calls: wait for the copies that read it
   cudaError_t e7 = cudaStreamSynchronize(s);
   for (cudaError_t e : {e1, e2, e3, e4, e5, e6, e7, e8})
@@ -513,8 +582,128 @@ extern "C" int urmvo_ba_plan_create(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, 
   return URMVO_OK;
 }
 
+extern "C" int urmvo_ba_plan_create(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, const int32_t* cam_off,
+                                    const int32_t* pt_off, const int32_t* obs_off, const double* poses,
+                                    const uint8_t* fixed, const double* pts, const double* uv,
+                                    const int32_t* cam, const int32_t* pt, const double* intr,
+                                    double chi2_thr, int it0, int it1, const urmvo_ba_options* opts) {
+  return ba_plan_create_impl(ctx, out, B, cam_off, pt_off, obs_off, poses, fixed, pts, uv, cam, pt, intr, chi2_thr,
+                             it0, it1, opts, false, nullptr);
+}
+
+// ------------------------------------------------------------------ point-sharded BA over NCCL
+
+extern "C" int urmvo_nccl_unique_id(uint8_t* id128) {
+  std::string err;
+  if (!id128) return fail(URMVO_ERR_ARG, "nccl_unique_id: null");
+  if (!g_nccl.load(err)) return fail(URMVO_ERR_NCCL, err);
+  NcclApi::UniqueId id;
+  const int rc = g_nccl.GetUniqueId(&id);
+  if (rc != 0) return fail(URMVO_ERR_NCCL, std::string("ncclGetUniqueId: ") + g_nccl.GetErrorString(rc));
+  std::memcpy(id128, id.internal, 128);
+  return URMVO_OK;
+}
+
+extern "C" int urmvo_comm_init(urmvo_ctx* ctx, int rank, int world, const uint8_t* id128) {
+  if (!ctx || !id128 || world < 1 || rank < 0 || rank >= world) return fail(URMVO_ERR_ARG, "comm_init: bad arguments");
+  std::string err;
+  if (!g_nccl.load(err)) return fail(URMVO_ERR_NCCL, err);
+  CU_TRY(cudaSetDevice(ctx->device));
+  NcclApi::UniqueId id;
+  std::memcpy(id.internal, id128, 128);
+  void* comm = nullptr;
+  const int rc = g_nccl.CommInitRank(&comm, world, id, rank);
+  if (rc != 0) return fail(URMVO_ERR_NCCL, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(rc));
+  ctx->comm = comm; ctx->rank = rank; ctx->world = world;
+  return URMVO_OK;
+}
+
+extern "C" int urmvo_ba_covisibility(int Nc, const uint8_t* fixed, int Np, int No, const int32_t* cam,
+                                     const int32_t* pt, uint8_t* upper) {
+  if (Nc <= 0 || !fixed || !cam || !pt || !upper) return fail(URMVO_ERR_ARG, "ba_covisibility: null input");
+  std::vector<int> cf(Nc, -1);
+  int n = 0;
+  for (int c = 0; c < Nc; c++) if (!fixed[c]) cf[c] = n++;
+  std::memset(upper, 0, (size_t)n * n);
+  std::vector<std::vector<int>> per_pt(Np);
+  for (int o = 0; o < No; o++) {
+    if (pt[o] < 0 || pt[o] >= Np || cam[o] < 0 || cam[o] >= Nc) return fail(URMVO_ERR_ARG, "ba_covisibility: index out of range");
+    if (cf[cam[o]] >= 0) per_pt[pt[o]].push_back(cf[cam[o]]);
+  }
+  for (auto& v : per_pt)
+    for (size_t a = 0; a < v.size(); a++)
+      for (size_t b = 0; b < v.size(); b++)
+        if (v[a] <= v[b]) upper[(size_t)v[a] * n + v[b]] = 1;
+  return n;
+}
+
+extern "C" int urmvo_sharded_ba_create(urmvo_ctx* ctx, urmvo_ba_plan** plan, int Nc, const double* poses,
+                                       const uint8_t* fixed, int Np, const double* pts, int No, const double* uv,
+                                       const int32_t* cam, const int32_t* pt, const double* intr, double chi2_thr,
+                                       int it0, int it1, const uint8_t* covis, const urmvo_ba_options* opts) {
+  const int32_t co[2] = {0, Nc}, po[2] = {0, Np}, oo[2] = {0, No};
+  urmvo_ba_options o = {};
+  if (opts) o = *opts;
+  o.force_atomic = 1;
+  return ba_plan_create_impl(ctx, plan, 1, co, po, oo, poses, fixed, pts, uv, cam, pt, intr, chi2_thr, it0, it1, &o,
+                             true, covis);
+}
+
+// Host-driven LM loop of the sharded problem: identical control flow on every rank, the decisions
+// come back from the device after each trial (one small pinned read per trial).
+extern "C" int urmvo_sharded_ba_run(urmvo_ba_plan* p) {
+  if (!p || !p->sharded) return fail(URMVO_ERR_ARG, "sharded_ba_run: not a sharded plan");
+  urmvo_ctx* ctx = p->ctx;
+  CU_TRY(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  const BAWin* wins = (const BAWin*)(p->dev + p->off_wins);
+  double* scal = (double*)(p->dev + p->off_scal);
+  double* hdiag = (double*)(p->dev + p->off_hdiag);
+  const int G = p->grid_blocks, T = p->threads;
+  auto allreduce = [&](double* buf, size_t n, int op) -> int {
+    if (!ctx->comm || ctx->world == 1) return 0;
+    const int rc = g_nccl.AllReduce(buf, buf, n, NcclApi::kFloat64, op, ctx->comm, s);
+    if (rc != 0) return fail(URMVO_ERR_NCCL, std::string("ncclAllReduce: ") + g_nccl.GetErrorString(rc));
+    return 0;
+  };
+#define SH_TRY(expr) do { cudaError_t _e = (expr); ctx->launches++; if (_e != cudaSuccess) return fail(URMVO_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); } while (0)
+  SH_TRY(launch_sh_init(wins, p->shard_state, G, T, s));
+  for (int pass = 0; pass < 2; pass++) {
+    const int n_iter = pass == 0 ? p->run.it0 : p->run.it1;
+    SH_TRY(launch_sh_begin_pass(p->shard_state, pass == 0 ? 1 : 0, s));
+    bool terminated = false;
+    for (int it = 0; it < n_iter && !terminated; it++) {
+      if (it == 0) {
+        SH_TRY(launch_sh_lin(wins, p->run, p->shard_state, scal, p->kmax, 1, G, T, s));
+        if (allreduce(hdiag, p->n6, NcclApi::kSum)) return URMVO_ERR_NCCL;
+        if (allreduce(scal, 1, NcclApi::kSum)) return URMVO_ERR_NCCL;
+        if (allreduce(scal + 1, 1, NcclApi::kMax)) return URMVO_ERR_NCCL;
+        SH_TRY(launch_sh_lambda(wins, p->shard_state, scal, s));
+      }
+      int cont = 1;
+      while (cont) {
+        SH_TRY(launch_sh_lin(wins, p->run, p->shard_state, scal, p->kmax, 0, G, T, s));
+        if (allreduce(scal, p->n_reduce_main, NcclApi::kSum)) return URMVO_ERR_NCCL;
+        SH_TRY(launch_sh_solve(wins, p->run, p->shard_state, scal, p->kmax, ctx->rank, G, T, s));
+        if (allreduce(scal + 2, 2, NcclApi::kSum)) return URMVO_ERR_NCCL;
+        SH_TRY(launch_sh_decide(p->shard_state, scal, p->shard_state_host, s));
+        CU_TRY(cudaStreamSynchronize(s));
+        int term = 0;
+        shard_flags(p->shard_state_host, &cont, &term);
+        if (!cont && term) terminated = true;
+      }
+    }
+    SH_TRY(launch_sh_classify(wins, p->run, p->shard_state, pass, G, T, s));
+  }
+  SH_TRY(launch_sh_finish(wins, p->shard_state, G, T, s));
+#undef SH_TRY
+  CU_TRY(cudaStreamSynchronize(s));
+  return URMVO_OK;
+}
+
 extern "C" int urmvo_ba_plan_run(urmvo_ba_plan* p) {
   if (!p) return fail(URMVO_ERR_ARG, "ba_plan_run: null plan");
+  if (p->sharded) return urmvo_sharded_ba_run(p);
   CU_TRY(cudaSetDevice(p->ctx->device));
   const BAWin* wins = (const BAWin*)(p->dev + p->off_wins);
   cudaError_t e;

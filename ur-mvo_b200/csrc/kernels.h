@@ -22,6 +22,21 @@ cudaError_t launch_ba_grid(const BAWin* wins_dev, const BARun& run, int kmax, in
 // Max co-resident CTAs of the grid kernel on the current device for this configuration.
 int ba_grid_capacity(int threads, int kmax);
 cudaError_t ba_timing_read(unsigned long long* out, bool reset);
+// point-sharded BA: phase kernels on a cooperative grid, NCCL all-reduces in between (capi.cu)
+size_t shard_state_bytes();
+int shard_grid_capacity(int threads, int kmax);
+cudaError_t launch_sh_init(const BAWin* w, void* stt, int grid, int threads, cudaStream_t s);
+cudaError_t launch_sh_begin_pass(void* stt, int robust, cudaStream_t s);
+cudaError_t launch_sh_lin(const BAWin* w, const BARun& run, void* stt, double* scal, int kmax, int diag,
+                          int grid, int threads, cudaStream_t s);
+cudaError_t launch_sh_lambda(const BAWin* w, void* stt, const double* scal, cudaStream_t s);
+cudaError_t launch_sh_solve(const BAWin* w, const BARun& run, void* stt, double* scal, int kmax, int rank,
+                            int grid, int threads, cudaStream_t s);
+cudaError_t launch_sh_decide(void* stt, const double* scal, void* host_copy, cudaStream_t s);
+cudaError_t launch_sh_classify(const BAWin* w, const BARun& run, void* stt, int pass, int grid, int threads,
+                               cudaStream_t s);
+cudaError_t launch_sh_finish(const BAWin* w, void* stt, int grid, int threads, cudaStream_t s);
+void shard_flags(const void* host_copy, int* cont_trials, int* terminate);
 constexpr int kBAPartWidth = 8;  // doubles per CTA and buffer in BAWin::part (+8 flag doubles)
 
 // ---- pose_kernels.cu

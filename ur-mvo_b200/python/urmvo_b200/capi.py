@@ -9,7 +9,8 @@ _LIB = None
 EXPORTED_SYMBOLS = [
     "urmvo_version", "urmvo_last_error", "urmvo_create", "urmvo_destroy", "urmvo_stream", "urmvo_sync",
     "urmvo_launch_count", "urmvo_local_ba", "urmvo_local_ba_batch", "urmvo_ba_plan_create",
-    "urmvo_ba_plan_run", "urmvo_ba_plan_download", "urmvo_ba_plan_destroy", "urmvo_debug_ba_timing", "urmvo_pose_only_batch",
+    "urmvo_ba_plan_run", "urmvo_ba_plan_download", "urmvo_ba_plan_destroy", "urmvo_debug_ba_timing", "urmvo_nccl_unique_id", "urmvo_comm_init", "urmvo_ba_covisibility",
+    "urmvo_sharded_ba_create", "urmvo_sharded_ba_run", "urmvo_pose_only_batch",
     "urmvo_pose_plan_create", "urmvo_pose_plan_run", "urmvo_pose_plan_download", "urmvo_pose_plan_destroy",
     "urmvo_two_view", "urmvo_tv_plan_create", "urmvo_tv_plan_run_ransac", "urmvo_tv_plan_download_hyps",
     "urmvo_tv_plan_reconstruct", "urmvo_tv_plan_destroy",
@@ -118,6 +119,13 @@ class Context:
     def sync(self):
         _check(self._L.urmvo_sync(self._h), "urmvo_sync")
 
+    def comm_init(self, rank, world, unique_id):
+        """Joins the NCCL communicator used by the point-sharded BA (one process per GPU)."""
+        uid = np.ascontiguousarray(unique_id, dtype=np.uint8)
+        assert uid.size == 128
+        _check(self._L.urmvo_comm_init(self._h, C.c_int(rank), C.c_int(world), _p(uid)), "urmvo_comm_init")
+        self.rank, self.world = rank, world
+
     def ba_timing(self, reset=True):
         """SM cycles per BA phase of window 0 since the last reset (development aid)."""
         out = (C.c_uint64 * 8)()
@@ -181,6 +189,79 @@ class Context:
                                       _p(T21), _p(P3D), _p(tri), _p(mH), _p(mF), C.byref(st), C.byref(ok)),
                "urmvo_two_view")
         return dict(ok=bool(ok.value), T21=T21, P3D=P3D, triangulated=tri, mask_H=mH, mask_F=mF, stats=st)
+
+
+def nccl_unique_id():
+    uid = np.zeros(128, dtype=np.uint8)
+    _check(load_library().urmvo_nccl_unique_id(_p(uid)), "urmvo_nccl_unique_id")
+    return uid
+
+
+def ba_covisibility(prob):
+    """Upper-triangular co-visibility of the free cameras through the observations of `prob`."""
+    fixed = _u8(prob["fixed"]); cam = _i32(prob["obs_cam"]); pt = _i32(prob["obs_pt"])
+    ncf = int((fixed == 0).sum())
+    upper = np.zeros((ncf, ncf), dtype=np.uint8)
+    rc = load_library().urmvo_ba_covisibility(C.c_int(fixed.shape[0]), _p(fixed), C.c_int(prob["pts"].shape[0]),
+                                              C.c_int(cam.shape[0]), _p(cam), _p(pt), _p(upper))
+    if rc < 0:
+        _check(rc, "urmvo_ba_covisibility")
+    return upper
+
+
+def shard_points(prob, rank, world):
+    """This rank's share of a BA problem sharded by point: a contiguous range of points balanced by
+    observation count (observations are point-major sorted), all cameras replicated."""
+    obs_pt = np.asarray(prob["obs_pt"])
+    Np, No = prob["pts"].shape[0], obs_pt.shape[0]
+    start = np.searchsorted(obs_pt, np.arange(Np + 1), side="left")  # CSR over points
+    cuts = [int(np.searchsorted(start, No * r / world, side="left")) for r in range(world)] + [Np]
+    cuts[0] = 0
+    p0, p1 = cuts[rank], max(cuts[rank + 1], cuts[rank])
+    o0, o1 = int(start[p0]), int(start[p1])
+    loc = dict(prob)
+    loc.update(pts=np.ascontiguousarray(prob["pts"][p0:p1]), uv=np.ascontiguousarray(prob["uv"][o0:o1]),
+               obs_cam=np.ascontiguousarray(prob["obs_cam"][o0:o1]),
+               obs_pt=np.ascontiguousarray(obs_pt[o0:o1] - p0, dtype=np.int32), point_range=(p0, p1), obs_range=(o0, o1))
+    return loc
+
+
+class ShardedBAPlan:
+    """One large BA sharded by point over the ranks of ctx's NCCL communicator (or alone)."""
+
+    def __init__(self, ctx, local_prob, covis=None, chi2_thr=10.0, it0=10, it1=5, opts=None):
+        self._L = ctx._L
+        self.ctx = ctx
+        self._keep = [_f64(local_prob["poses"]), _u8(local_prob["fixed"]), _f64(local_prob["pts"]), _f64(local_prob["uv"]),
+                      _i32(local_prob["obs_cam"]), _i32(local_prob["obs_pt"]), _f64(local_prob["intr"])]
+        k = self._keep
+        cv = None if covis is None else _u8(covis)
+        self.shapes = (k[0].shape, k[2].shape, k[3].shape[0])
+        self._h = C.c_void_p()
+        _check(self._L.urmvo_sharded_ba_create(ctx._h, C.byref(self._h), C.c_int(k[0].shape[0]), _p(k[0]), _p(k[1]),
+                                               C.c_int(k[2].shape[0]), _p(k[2]), C.c_int(k[3].shape[0]), _p(k[3]),
+                                               _p(k[4]), _p(k[5]), _p(k[6]), C.c_double(chi2_thr), C.c_int(it0), C.c_int(it1),
+                                               _p(cv), C.byref(opts) if opts is not None else None), "urmvo_sharded_ba_create")
+
+    def run(self):
+        _check(self._L.urmvo_sharded_ba_run(self._h), "urmvo_sharded_ba_run")
+
+    def download(self):
+        poses = np.zeros(self.shapes[0]); pts = np.zeros(self.shapes[1]); inl = np.zeros(self.shapes[2], dtype=np.uint8)
+        st = (BAStats * 1)()
+        _check(self._L.urmvo_ba_plan_download(self._h, _p(poses), _p(pts), _p(inl), st), "urmvo_ba_plan_download")
+        return poses, pts, inl, st[0]
+
+    def close(self):
+        if self._h:
+            self._L.urmvo_ba_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def pack_ba_batch(probs):
