@@ -293,51 +293,82 @@ __device__ void lin_phase(const Scope& sc, const BAWin& W, int cur, double lambd
     __syncwarp();
     // Schur pairs (i <= j): one lane per pair, 6x6 block = J_i^T M J_j,
     //   M = w_i I - A_i B_i^T (i == j: Hpp term and its Schur correction), M = -A_i B_j^T otherwise.
+    // SMEM: the lane adds its block into the warp's shared-memory copy.  Atomic mode: the 32 blocks
+    // of a round are transposed through shared memory so that each RED instruction covers 32
+    // CONSECUTIVE doubles of one block (2 instructions per block) — the L2 atomic units work per
+    // 32-byte sector, so this is ~4x fewer atomic transactions than 36 scattered REDs per lane.
     const int npairs = k * (k + 1) / 2;
-    for (int pi = lane; pi < npairs; pi += 32) {
-      const int kk = 2 * k + 1;
-      int i = (int)(((float)kk - sqrtf((float)(kk * kk - 8 * pi))) * 0.5f);
-      i = max(0, min(i, k - 1));
-      while (i > 0 && i * k - i * (i - 1) / 2 > pi) i--;
-      while ((i + 1) * k - (i + 1) * i / 2 <= pi) i++;
-      const int j = i + (pi - (i * k - i * (i - 1) / 2));
-      const int ci = st.cf[i], cj = st.cf[j];
-      if (ci < 0 || cj < 0) continue;
-      double M[4];
-      {
-        const double a0 = st.A(0, i), a1 = st.A(1, i), a2 = st.A(2, i);
-        const double a3 = st.A(3, i), a4 = st.A(4, i), a5 = st.A(5, i);
-        const double b0 = st.B(0, j), b1 = st.B(1, j), b2 = st.B(2, j);
-        const double b3 = st.B(3, j), b4 = st.B(4, j), b5 = st.B(5, j);
-        M[0] = -(a0 * b0 + a1 * b1 + a2 * b2);
-        M[1] = -(a0 * b3 + a1 * b4 + a2 * b5);
-        M[2] = -(a3 * b0 + a4 * b1 + a5 * b2);
-        M[3] = -(a3 * b3 + a4 * b4 + a5 * b5);
-        if (i == j) { const double w = st.w(i); M[0] += w; M[3] += w; }
-      }
-      double T[12];  // T = M J_j (2x6)
+    double* tile = wa.base + (size_t)(threadIdx.x >> 5) * wa.stride + acc_off;  // 32 x 37 doubles
+    for (int pbase = 0; pbase < npairs; pbase += 32) {
+      const int pi = pbase + lane;
+      int my_blk = -1;
+      if (pi < npairs) {
+        const int kk = 2 * k + 1;
+        int i = (int)(((float)kk - sqrtf((float)(kk * kk - 8 * pi))) * 0.5f);
+        i = max(0, min(i, k - 1));
+        while (i > 0 && i * k - i * (i - 1) / 2 > pi) i--;
+        while ((i + 1) * k - (i + 1) * i / 2 <= pi) i++;
+        const int j = i + (pi - (i * k - i * (i - 1) / 2));
+        const int ci = st.cf[i], cj = st.cf[j];
+        if (ci >= 0 && cj >= 0) {
+          double M[4];
+          {
+            const double a0 = st.A(0, i), a1 = st.A(1, i), a2 = st.A(2, i);
+            const double a3 = st.A(3, i), a4 = st.A(4, i), a5 = st.A(5, i);
+            const double b0 = st.B(0, j), b1 = st.B(1, j), b2 = st.B(2, j);
+            const double b3 = st.B(3, j), b4 = st.B(4, j), b5 = st.B(5, j);
+            M[0] = -(a0 * b0 + a1 * b1 + a2 * b2);
+            M[1] = -(a0 * b3 + a1 * b4 + a2 * b5);
+            M[2] = -(a3 * b0 + a4 * b1 + a5 * b2);
+            M[3] = -(a3 * b3 + a4 * b4 + a5 * b5);
+            if (i == j) { const double w = st.w(i); M[0] += w; M[3] += w; }
+          }
+          double T[12];  // T = M J_j (2x6)
 #pragma unroll
-      for (int b = 0; b < 6; b++) {
-        const double j0 = st.Jp(b, j), j1 = st.Jp(6 + b, j);
-        T[b] = M[0] * j0 + M[1] * j1;
-        T[6 + b] = M[2] * j0 + M[3] * j1;
-      }
-      const bool swap = ci > cj;
-      // acc_mode 1 implies the dense upper-triangular block layout: block (a,b) = row_ptr[a] + b - a
-      const int blk = SMEM ? (swap ? W.row_ptr[cj] + ci - cj : W.row_ptr[ci] + cj - ci)
-                           : (swap ? find_block(W, cj, ci) : find_block(W, ci, cj));
-      if (blk < 0) continue;  // cannot happen for a structure built from the same observations
-      double* Sb = accS + (size_t)blk * 36;
-      const bool same_cam_twice = !SMEM && (ci == cj) && (i != j);  // excluded on the host in acc_mode 1
+          for (int b = 0; b < 6; b++) {
+            const double j0 = st.Jp(b, j), j1 = st.Jp(6 + b, j);
+            T[b] = M[0] * j0 + M[1] * j1;
+            T[6 + b] = M[2] * j0 + M[3] * j1;
+          }
+          const bool swap = ci > cj;
+          // acc_mode 1 implies the dense upper-triangular block layout: block (a,b) = row_ptr[a] + b - a
+          const int blk = SMEM ? (swap ? W.row_ptr[cj] + ci - cj : W.row_ptr[ci] + cj - ci)
+                               : (swap ? find_block(W, cj, ci) : find_block(W, ci, cj));
+          if (blk >= 0) {  // always, for a structure built from the same observations
+            const bool same_cam_twice = !SMEM && (ci == cj) && (i != j);  // excluded on the host in acc_mode 1
+            double* Sb = accS + (size_t)blk * 36;
+            double* tl = tile + lane * 37;
 #pragma unroll
-      for (int a = 0; a < 6; a++) {
-        const double j0 = st.Jp(a, i), j1 = st.Jp(6 + a, i);
+            for (int a = 0; a < 6; a++) {
+              const double j0 = st.Jp(a, i), j1 = st.Jp(6 + a, i);
 #pragma unroll
-        for (int b = 0; b < 6; b++) {
-          const double v = j0 * T[b] + j1 * T[6 + b];
-          if (!swap) acc_add<SMEM>(&Sb[a * 6 + b], v); else acc_add<SMEM>(&Sb[b * 6 + a], v);
-          if (same_cam_twice) atomicAdd(&Sb[b * 6 + a], v);
+              for (int b = 0; b < 6; b++) {
+                const double v = j0 * T[b] + j1 * T[6 + b];
+                if (SMEM) {
+                  if (!swap) Sb[a * 6 + b] += v; else Sb[b * 6 + a] += v;
+                } else if (same_cam_twice) {
+                  atomicAdd(&Sb[a * 6 + b], v);
+                  atomicAdd(&Sb[b * 6 + a], v);
+                } else {
+                  tl[swap ? b * 6 + a : a * 6 + b] = v;
+                }
+              }
+            }
+            if (!SMEM && !same_cam_twice) my_blk = blk;
+          }
         }
+      }
+      if (!SMEM) {
+        __syncwarp();
+        const int cnt = min(32, npairs - pbase);
+        for (int q = 0; q < cnt; q++) {
+          const int b = __shfl_sync(0xffffffffu, my_blk, q);
+          if (b < 0) continue;
+          double* Sb = W.S + (size_t)b * 36;
+          atomicAdd(&Sb[lane], tile[q * 37 + lane]);
+          if (lane < 4) atomicAdd(&Sb[32 + lane], tile[q * 37 + 32 + lane]);
+        }
+        __syncwarp();
       }
     }
     __syncwarp();
@@ -392,95 +423,200 @@ __device__ __forceinline__ bool spd6_inverse(const double* __restrict__ A, doubl
   return true;
 }
 
-// Solves S xp = bs. Rows (6 per free camera) are distributed over the threads of the scope.
+constexpr int kPcgRowsPerWarp = 8;
+
+// Solves S xp = bs on the block-sparse S with block-Jacobi preconditioned conjugate gradients in
+// the Chronopoulos-Gear form: ONE scope-wide reduction (gamma = r.z and delta = z.Sz together) and
+// one barrier (z visible) per iteration instead of two reductions and two barriers.
+// Mapping: one WARP per camera block row; lane = (g, a) with g = lane / 6 in 0..4 striding over the
+// blocks of the row (5 blocks in flight per warp, the row's list is latency-bound otherwise) and
+// a = lane % 6 the scalar row; the five partial sums are combined by shuffles in fixed order.
+// x, r, p, s of the row stay in registers (replicated over g), only z lives in global memory.
 // Returns false when S is not positive definite (=> g2o's "ok2 == false").
+// wsm / wcap: this warp's shared-memory work area (doubles), idle during the solve: the blocks of the
+// warp's rows are copied there once (a-major, lower blocks transposed) and reused by every
+// iteration; what does not fit is read from L2.
 template <class Scope>
 __device__ bool pcg_phase(const Scope& sc, const BAWin& W, double tol, int max_iter, double* part,
-                          int& parity, double* red, int& iters_out) {
-  const int n = W.Ncf * 6;
-  const int gt = sc.blk() * blockDim.x + threadIdx.x;
-  const int gstride = sc.nblk() * blockDim.x;
+                          int& parity, double* red, int& iters_out, double* wsm, int wcap) {
+  const int Ncf = W.Ncf;
+  const int lane = threadIdx.x & 31;
+  const int wpc = blockDim.x >> 5;
+  const int gwarp = sc.blk() * wpc + (threadIdx.x >> 5);
+  const int nwarp = sc.nblk() * wpc;
+  const int grp = lane / 6, a = lane - grp * 6;       // lanes 30, 31: grp 5, idle in the products
   iters_out = 0;
-  if (n == 0) return true;
+  if (Ncf == 0) return true;
   // preconditioner: Minv_i = S_ii^-1
   double bad = 0.0;
-  for (int i = gt; i < W.Ncf; i += gstride) {
-    if (!spd6_inverse(W.S + (size_t)W.row_ptr[i] * 36, W.Minv + (size_t)i * 36)) bad = 1.0;
+  {
+    const int gt = sc.blk() * blockDim.x + threadIdx.x, gstride = sc.nblk() * blockDim.x;
+    for (int i = gt; i < Ncf; i += gstride)
+      if (!spd6_inverse(W.S + (size_t)W.row_ptr[i] * 36, W.Minv + (size_t)i * 36)) bad = 1.0;
   }
   sc.sync();
-  // x = 0, r = b, z = Minv r, p = z
-  double acc[2] = {0.0, 0.0};
-  for (int row = gt; row < n; row += gstride) {
-    const int i = row / 6, a = row - i * 6;
-    const double* Mi = W.Minv + (size_t)i * 36 + a * 6;
-    const double* bi = W.bs + i * 6;
+  constexpr int RMAX = kPcgRowsPerWarp;  // block rows per warp, state kept in registers
+  const int n_slots = (Ncf + nwarp - 1) / nwarp;
+  if (n_slots > RMAX) return false;  // excluded on the host: scopes are sized so that this cannot happen
+  double x[RMAX], r[RMAX], pv[RMAX], sv[RMAX], z[RMAX];
+  const double* __restrict__ S = W.S;
+  const double* __restrict__ Minv = W.Minv;
+  const int* __restrict__ row_ptr = W.row_ptr;
+  const int* __restrict__ col = W.col;
+  const int* __restrict__ lrow_ptr = W.lrow_ptr;
+  const int* __restrict__ lcol = W.lcol;
+  const int* __restrict__ lblk = W.lblk;
+  double* __restrict__ zg = W.z;
+  auto precond = [&](int i, double rr) {  // z_a = sum_b Minv[a][b] r_b, r_b from lanes 0..5
     double zz = 0.0;
 #pragma unroll
-    for (int b = 0; b < 6; b++) zz += Mi[b] * __ldcg(bi + b);
-    const double rr = __ldcg(W.bs + row);
-    W.xp[row] = 0.0;
-    W.r[row] = rr;
-    W.z[row] = zz;
-    W.p[row] = zz;
-    acc[0] += rr * zz;
+    for (int b2 = 0; b2 < 6; b2++) {
+      const double rb = __shfl_sync(0xffffffffu, rr, b2);
+      if (i < Ncf && a < 6) zz += Minv[(size_t)i * 36 + a * 6 + b2] * rb;
+    }
+    return zz;
+  };
+  // cache the blocks of the owned rows in shared memory (as many as fit): per cached block 36 doubles
+  // of S (a-major, lower blocks transposed), 6 doubles of staging for z_j and the column index
+  int c_off[RMAX], c_cnt[RMAX];
+  {
+    int used = 0;
+#pragma unroll
+    for (int k = 0; k < RMAX; k++) {
+      c_off[k] = used; c_cnt[k] = 0;
+      const int i = gwarp + k * nwarp;
+      if (k < n_slots && i < Ncf && wsm) {
+        const int u0 = row_ptr[i], nu = row_ptr[i + 1] - u0;
+        const int l0 = lrow_ptr[i], nl = lrow_ptr[i + 1] - l0;
+        const int fit = min(nu + nl, (wcap - used) / 43);
+        int* cc = reinterpret_cast<int*>(wsm + used + fit * 42);
+        for (int e = 0; e < fit; e++) {
+          for (int q = lane; q < 36; q += 32) {
+            const int qa = q / 6, qb = q - qa * 6;
+            const double v = (e < nu) ? __ldcg(S + (size_t)(u0 + e) * 36 + q)
+                                      : __ldcg(S + (size_t)lblk[l0 + e - nu] * 36 + qb * 6 + qa);
+            wsm[used + e * 36 + q] = v;
+          }
+          if (lane == 0) cc[e] = (e < nu) ? col[u0 + e] : lcol[l0 + e - nu];
+        }
+        c_cnt[k] = fit;
+        used += fit * 43;
+      }
+    }
+    __syncwarp();
   }
-  acc[1] = bad;
-  double dummy[1];
-  scope_reduce<2, 0>(sc, acc, dummy, part, parity, red);
-  if (acc[1] > 0.0) return false;
-  double rz = acc[0];
-  const double rz0 = rz;
-  if (!(rz0 > 0.0)) return rz0 == 0.0;  // b == 0 -> x = 0;  negative / NaN -> failure
-  const double stop = tol * tol * rz0;
+  auto matvec_row = [&](int i, int k) {  // (S z)_{i,a}, identical in every lane with the same a
+    double acc = 0.0;
+    const int nc = c_cnt[k];
+    double* cs = wsm + c_off[k];
+    double* zs = cs + nc * 36;
+    const int* cc = reinterpret_cast<const int*>(cs + nc * 42);
+    // stage z of the cached neighbours: independent loads, one L2 round trip for the whole row
+    for (int q = lane; q < nc * 6; q += 32) {
+      const int e = q / 6;
+      zs[q] = __ldcg(zg + cc[e] * 6 + (q - e * 6));
+    }
+    __syncwarp();
+    if (i < Ncf && grp < 5) {
+      const int u0 = row_ptr[i], nu = row_ptr[i + 1] - u0;
+      const int l0 = lrow_ptr[i], nl = lrow_ptr[i + 1] - l0;
+#pragma unroll 2
+      for (int e = grp; e < nc; e += 5) {  // cached blocks: S and z from shared memory
+        const double* Sb = cs + e * 36 + a * 6;
+        const double* zj = zs + e * 6;
+#pragma unroll
+        for (int b2 = 0; b2 < 6; b2++) acc += Sb[b2] * zj[b2];
+      }
+#pragma unroll 2
+      for (int e = nc + grp; e < nu + nl; e += 5) {
+        if (e < nu) {
+          const double* Sb = S + (size_t)(u0 + e) * 36 + a * 6;
+          const double* zj = zg + col[u0 + e] * 6;
+#pragma unroll
+          for (int b2 = 0; b2 < 6; b2++) acc += __ldcg(Sb + b2) * __ldcg(zj + b2);
+        } else {
+          const int le = l0 + (e - nu);
+          const double* Sb = S + (size_t)lblk[le] * 36 + a;
+          const double* zj = zg + lcol[le] * 6;
+#pragma unroll
+          for (int b2 = 0; b2 < 6; b2++) acc += __ldcg(Sb + b2 * 6) * __ldcg(zj + b2);
+        }
+      }
+    }
+    // combine the five block groups in fixed order; every lane ends with the total of its a
+    const int al = (grp < 5) ? a : 0;
+    double tot = __shfl_sync(0xffffffffu, acc, al);
+#pragma unroll
+    for (int g2 = 1; g2 < 5; g2++) tot += __shfl_sync(0xffffffffu, acc, g2 * 6 + al);
+    return tot;
+  };
+  // r = b, z = Minv r
+#pragma unroll
+  for (int k = 0; k < RMAX; k++) {
+    x[k] = 0.0; pv[k] = 0.0; sv[k] = 0.0; r[k] = 0.0; z[k] = 0.0;
+    if (k < n_slots) {
+      const int i = gwarp + k * nwarp;
+      if (i < Ncf && grp < 5) r[k] = __ldcg(W.bs + i * 6 + a);
+      z[k] = precond(i, r[k]);
+      if (i < Ncf && grp == 0) zg[i * 6 + a] = z[k];
+    }
+  }
+  sc.sync();
+  double gamma = 0.0, alpha = 0.0, stop = 0.0;
   bool ok = true;
   int it = 0;
-  for (; it < max_iter; it++) {
-    // Ap = S p (upper blocks + mirrored transposes), pAp
-    double pap[1] = {0.0};
-    for (int row = gt; row < n; row += gstride) {
-      const int i = row / 6, a = row - i * 6;
-      double s = 0.0;
-      for (int e = W.row_ptr[i]; e < W.row_ptr[i + 1]; e++) {
-        const double* Sb = W.S + (size_t)e * 36 + a * 6;
-        const double* pj = W.p + W.col[e] * 6;
+  for (;; it++) {
+    // w = S z ; gamma_new = r.z ; delta = z.w  (one reduction)
+    double w[RMAX];
+    double acc[3] = {0.0, 0.0, bad};
 #pragma unroll
-        for (int b = 0; b < 6; b++) s += __ldcg(Sb + b) * __ldcg(pj + b);
+    for (int k = 0; k < RMAX; k++) {
+      w[k] = 0.0;
+      if (k < n_slots) {
+        const int i = gwarp + k * nwarp;
+        w[k] = matvec_row(i, k);
+        if (i < Ncf && grp == 0) {
+          acc[0] += r[k] * z[k];
+          acc[1] += z[k] * w[k];
+        }
       }
-      for (int e = W.lrow_ptr[i]; e < W.lrow_ptr[i + 1]; e++) {
-        const double* Sb = W.S + (size_t)W.lblk[e] * 36 + a;
-        const double* pj = W.p + W.lcol[e] * 6;
-#pragma unroll
-        for (int b = 0; b < 6; b++) s += __ldcg(Sb + b * 6) * __ldcg(pj + b);
-      }
-      W.Ap[row] = s;
-      pap[0] += __ldcg(W.p + row) * s;
     }
-    scope_reduce<1, 0>(sc, pap, dummy, part, parity, red);
-    if (!(pap[0] > 0.0)) { ok = false; break; }
-    const double alpha = rz / pap[0];
-    // x += alpha p ; r -= alpha Ap  (own rows), then z = Minv r needs the whole 6-block of r
-    for (int row = gt; row < n; row += gstride) {
-      W.xp[row] += alpha * __ldcg(W.p + row);
-      W.r[row] -= alpha * W.Ap[row];
+    double dummy[1];
+    scope_reduce<3, 0>(sc, acc, dummy, part, parity, red);  // its barrier also orders the z reads/writes
+    if (acc[2] > 0.0) { ok = false; break; }
+    const double gamma_new = acc[0], delta = acc[1];
+    if (it == 0) {
+      if (!(gamma_new > 0.0)) { ok = (gamma_new == 0.0); break; }  // b == 0 -> x = 0
+      stop = tol * tol * gamma_new;
+    } else if (!(gamma_new > stop)) {
+      break;
+    }
+    if (it >= max_iter) break;
+    const double beta = (it == 0) ? 0.0 : gamma_new / gamma;
+    const double denom = (it == 0) ? delta : delta - beta * gamma_new / alpha;
+    if (!(denom > 0.0)) { ok = false; break; }
+    alpha = gamma_new / denom;
+    gamma = gamma_new;
+#pragma unroll
+    for (int k = 0; k < RMAX; k++) {
+      if (k < n_slots) {
+        const int i = gwarp + k * nwarp;
+        pv[k] = z[k] + beta * pv[k];
+        sv[k] = w[k] + beta * sv[k];
+        x[k] += alpha * pv[k];
+        r[k] -= alpha * sv[k];
+        z[k] = precond(i, r[k]);
+        if (i < Ncf && grp == 0) zg[i * 6 + a] = z[k];
+      }
     }
     sc.sync();
-    double rzn[1] = {0.0};
-    for (int row = gt; row < n; row += gstride) {
-      const int i = row / 6, a = row - i * 6;
-      const double* Mi = W.Minv + (size_t)i * 36 + a * 6;
-      const double* ri = W.r + i * 6;
-      double zz = 0.0;
+  }
 #pragma unroll
-      for (int b = 0; b < 6; b++) zz += Mi[b] * __ldcg(ri + b);
-      W.z[row] = zz;
-      rzn[0] += __ldcg(W.r + row) * zz;
+  for (int k = 0; k < RMAX; k++) {
+    if (k < n_slots) {
+      const int i = gwarp + k * nwarp;
+      if (i < Ncf && grp == 0) W.xp[i * 6 + a] = ok ? x[k] : 0.0;
     }
-    scope_reduce<1, 0>(sc, rzn, dummy, part, parity, red);
-    if (!(rzn[0] > stop)) { it++; break; }
-    const double beta = rzn[0] / rz;
-    rz = rzn[0];
-    for (int row = gt; row < n; row += gstride) W.p[row] = W.z[row] + beta * W.p[row];
-    sc.sync();
   }
   iters_out = it;
   return ok;
@@ -1196,7 +1332,9 @@ __device__ LMResult lm_optimize(const Scope& sc, const BAWin& W, const BARun& ru
   double lambda = 0.0, ni = 2.0;
   double currentChi = 0.0;
   double dummy[1];
-  const int use_single_cta_pcg = (W.Ncf * 6 <= 4 * (int)blockDim.x);
+  // one CTA (no scope barriers) only while its rows' blocks fit the shared-memory cache
+  const int use_single_cta_pcg = (W.Ncf <= (int)(blockDim.x >> 5) * kPcgRowsPerWarp) &&
+                                 ((long long)(2 * W.nblk - W.Ncf) * 36 <= (long long)(blockDim.x >> 5) * wa.stride);
   double* flags = W.part + (size_t)2 * sc.nblk() * kPartWidth;  // behind the two reduction buffers
   for (int it = 0; it < n_iter; it++) {
     if (it == 0) {
@@ -1276,14 +1414,16 @@ __device__ LMResult lm_optimize(const Scope& sc, const BAWin& W, const BARun& ru
         if (sc.blk() == 0) {
           CtaScope cs;
           int par2 = 0;
-          ok2 = pcg_phase(cs, W, run.pcg_tol, run.pcg_max_iter, nullptr, par2, red, pcg_it);
+          ok2 = pcg_phase(cs, W, run.pcg_tol, run.pcg_max_iter, nullptr, par2, red, pcg_it,
+                          wa.base + (size_t)(threadIdx.x >> 5) * wa.stride, wa.stride);
           if (threadIdx.x == 0) { __stcg(flags, ok2 ? 1.0 : 0.0); __stcg(flags + 1, (double)pcg_it); }
         }
         sc.sync();
         ok2 = __ldcg(flags) > 0.5;
         pcg_it = (int)__ldcg(flags + 1);
       } else {
-        ok2 = pcg_phase(sc, W, run.pcg_tol, run.pcg_max_iter, W.part, parity, red, pcg_it);
+        ok2 = pcg_phase(sc, W, run.pcg_tol, run.pcg_max_iter, W.part, parity, red, pcg_it,
+                        wa.base + (size_t)(threadIdx.x >> 5) * wa.stride, wa.stride);
         sc.sync();
       }
       res.pcg_iters += pcg_it;
@@ -1532,6 +1672,9 @@ size_t ba_smem_bytes(int threads, int work_stride, int ints_per_warp) {
 }
 
 int ba_stage_doubles(int kmax) { return kStageFields * kmax; }
+int ba_tile_doubles() { return 32 * 37; }
+// grid kernels: at least 23 KB per warp so that a ~60-neighbour block row fits the PCG cache
+static __host__ __device__ int grid_work_stride(int kmax) { const int n = kStageFields * kmax + 32 * 37; return n > 2944 ? n : 2944; }
 int ba_pack_doubles() { return kPackFields * kPackSlots; }
 
 // ------------------------------------------------------------------------------- point-sharded BA
@@ -1575,7 +1718,7 @@ k_sh_lin(const BAWin* __restrict__ wins, BARun run, ShardState* stt, double* sca
   extern __shared__ __align__(16) unsigned char smem[];
   GridScope sc;
   const BAWin& W = wins[0];
-  const SmemViews v = make_views(smem, kmax, kStageFields * kmax, kmax);
+  const SmemViews v = make_views(smem, kmax, grid_work_stride(kmax), kmax);
   int parity = stt->parity;
   zero_system(sc, W, diag != 0, 0.0);
   sc.sync();
@@ -1616,14 +1759,15 @@ k_sh_solve(const BAWin* __restrict__ wins, BARun run, ShardState* stt, double* s
   extern __shared__ __align__(16) unsigned char smem[];
   GridScope sc;
   const BAWin& W = wins[0];
-  const SmemViews v = make_views(smem, kmax, kStageFields * kmax, kmax);
+  const SmemViews v = make_views(smem, kmax, grid_work_stride(kmax), kmax);
   int parity = stt->parity;
   const int cur = stt->cur;
   const double lambda = stt->lambda;
   damp_diagonal(sc, W, lambda);
   sc.sync();
   int pcg_it = 0;
-  const bool ok2 = pcg_phase(sc, W, run.pcg_tol, run.pcg_max_iter, W.part, parity, v.red, pcg_it);
+  const bool ok2 = pcg_phase(sc, W, run.pcg_tol, run.pcg_max_iter, W.part, parity, v.red, pcg_it,
+                             v.wa.base + (size_t)(threadIdx.x >> 5) * v.wa.stride, v.wa.stride);
   sc.sync();
   double tchi = 0.0, sc_l = 0.0;
   if (ok2) {
@@ -1720,7 +1864,7 @@ static cudaError_t coop(const void* k, int grid, int threads, void** args, size_
 }
 
 int shard_grid_capacity(int threads, int kmax) {
-  const size_t smem = ba_smem_bytes(threads, kStageFields * kmax, kmax);
+  const size_t smem = ba_smem_bytes(threads, grid_work_stride(kmax), kmax);
   int dev = 0, sms = 0, best = 1 << 30;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1746,7 +1890,7 @@ cudaError_t launch_sh_lin(const BAWin* w, const BARun& run, void* stt, double* s
                           int grid, int threads, cudaStream_t s) {
   BARun r = run;
   void* args[] = {(void*)&w, (void*)&r, (void*)&stt, (void*)&scal, (void*)&kmax, (void*)&diag};
-  return coop((const void*)k_sh_lin, grid, threads, args, ba_smem_bytes(threads, kStageFields * kmax, kmax), s);
+  return coop((const void*)k_sh_lin, grid, threads, args, ba_smem_bytes(threads, grid_work_stride(kmax), kmax), s);
 }
 cudaError_t launch_sh_lambda(const BAWin* w, void* stt, const double* scal, cudaStream_t s) {
   k_sh_lambda<<<1, 256, 0, s>>>(w, (ShardState*)stt, scal);
@@ -1756,7 +1900,7 @@ cudaError_t launch_sh_solve(const BAWin* w, const BARun& run, void* stt, double*
                             int grid, int threads, cudaStream_t s) {
   BARun r = run;
   void* args[] = {(void*)&w, (void*)&r, (void*)&stt, (void*)&scal, (void*)&kmax, (void*)&rank};
-  return coop((const void*)k_sh_solve, grid, threads, args, ba_smem_bytes(threads, kStageFields * kmax, kmax), s);
+  return coop((const void*)k_sh_solve, grid, threads, args, ba_smem_bytes(threads, grid_work_stride(kmax), kmax), s);
 }
 cudaError_t launch_sh_decide(void* stt, const double* scal, void* host_copy, cudaStream_t s) {
   k_sh_decide<<<1, 1, 0, s>>>((ShardState*)stt, scal, (ShardState*)host_copy);
@@ -1805,7 +1949,7 @@ cudaError_t launch_ba_cluster(const BAWin* wins_dev, const BARun& run, int kmax,
 }
 
 int ba_grid_capacity(int threads, int kmax) {
-  const size_t smem = ba_smem_bytes(threads, ba_stage_doubles(kmax), kmax);
+  const size_t smem = ba_smem_bytes(threads, grid_work_stride(kmax), kmax);
   if (cudaFuncSetAttribute(ba_window_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
   int per_sm = 0, dev = 0, sms = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ba_window_grid_kernel, threads, smem) != cudaSuccess) return 0;
@@ -1816,7 +1960,7 @@ int ba_grid_capacity(int threads, int kmax) {
 
 cudaError_t launch_ba_grid(const BAWin* wins_dev, const BARun& run, int kmax, int grid_blocks,
                            int threads, cudaStream_t stream) {
-  const int ws = ba_stage_doubles(kmax);
+  const int ws = grid_work_stride(kmax);
   const size_t smem = ba_smem_bytes(threads, ws, kmax);
   cudaError_t e = cudaFuncSetAttribute(ba_window_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;

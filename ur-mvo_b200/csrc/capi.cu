@@ -375,7 +375,7 @@ static int ba_plan_create_impl(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, const
     int stride = 0, pcg_d = 0, ints = p->kmax;
     for (auto& w : wh) {
       int need = 0;
-      if (w.acc_mode == 0) need = ba_stage_doubles(p->kmax);
+      if (w.acc_mode == 0) need = ba_stage_doubles(p->kmax) + ba_tile_doubles();
       else if (w.acc_mode == 1) need = ba_stage_doubles(p->kmax) + w.acc_len;
       else { need = std::max(ba_pack_doubles(), w.acc_len); ints = std::max(ints, 128); }
       stride = std::max(stride, need);
@@ -412,6 +412,12 @@ static int ba_plan_create_impl(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, const
     while (cs < 16 && cs * 2 * B <= ctx->n_sm && max_np > cs * warps * 16) cs *= 2;
   }
   if (cs != 1 && cs != 2 && cs != 4 && cs != 8 && cs != 16) { delete p; return fail(URMVO_ERR_ARG, "ba options: cluster_size must be 1,2,4,8 or 16"); }
+  // the BSR PCG keeps at most 8 block rows per warp in registers: a window with more free cameras
+  // than the warps of its cluster can hold runs on the whole grid instead
+  if (!p->use_grid && max_ncf > (p->threads / 32) * cs * 8) {
+    if (B != 1) { delete p; return fail(URMVO_ERR_UNSUPPORTED, "local_ba_batch: a window has too many free cameras for a cluster; solve it alone"); }
+    p->use_grid = true;
+  }
   p->cluster_size = cs;
   p->n_clusters = B;
   int nblk_scope = cs;

@@ -115,13 +115,21 @@ __device__ __forceinline__ void scope_reduce(const Scope& sc, double (&sum)[NV],
   if (nb > 1) {
     sc.sync();
     if (wid == 0) {
+      // lane-strided partial sums; all loads of one stride step are independent (one L2 round trip)
+      double acc[NT];
+#pragma unroll
+      for (int k = 0; k < NT; k++) acc[k] = (k < NV) ? 0.0 : -1.0e300;
+#pragma unroll 2
+      for (int b = lane; b < nb; b += 32) {
+        double x[NT];
+#pragma unroll
+        for (int k = 0; k < NT; k++) x[k] = __ldcg(&buf[(size_t)b * NT + k]);
+#pragma unroll
+        for (int k = 0; k < NT; k++) acc[k] = (k < NV) ? acc[k] + x[k] : fmax(acc[k], x[k]);
+      }
+#pragma unroll
       for (int k = 0; k < NT; k++) {
-        double s = (k < NV) ? 0.0 : -1.0e300;
-        for (int b = lane; b < nb; b += 32) {
-          double x = __ldcg(&buf[(size_t)b * NT + k]);
-          s = (k < NV) ? s + x : fmax(s, x);
-        }
-        s = (k < NV) ? warp_sum(s) : warp_max(s);
+        const double s = (k < NV) ? warp_sum(acc[k]) : warp_max(acc[k]);
         if (lane == 0) red[NT * 32 + k] = s;
       }
     }
