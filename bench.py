@@ -37,7 +37,7 @@ UNIT = "LM iterations/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--windows", type=int, default=148, help="BA windows per GPU per step")
@@ -100,7 +100,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -405,6 +405,17 @@ def side_measurements(ctx, stream, torch):
     extra["pose_only_cfg2"] = {"lm_iters_per_s": its / dt, "ms": dt * 1e3, "frames": 256,
                                "cpu_lm_iters_per_s": (its * 16.0 / 256.0) / tc, "cpu_sample": "16 frames, 1 thread"}
     pplan.close()
+    # cfg4: one large window (50 keyframes, 50k points, ~400k observations) on the cooperative grid kernel
+    from urmvo_b200.capi import pack_ba_batch
+    big = synth.cfg4()
+    bplan = U.BAPlan(ctx, pack_ba_batch([big]))
+    dt = timed(bplan.run, 2)
+    bst = bplan.download()[3][0]
+    extra["ba_large_cfg4"] = {"lm_iters_per_s": (bst.iters[0] + bst.iters[1]) / dt, "ms": dt * 1e3,
+                              "obs": int(big["uv"].shape[0]), "trials": int(bst.trials[0] + bst.trials[1]),
+                              "pcg_iters": int(bst.pcg_iters[0] + bst.pcg_iters[1]),
+                              "linearise_bytes_survey_8d": int(168 * big["uv"].shape[0] + 96 * big["pts"].shape[0] + 272 * 50)}
+    bplan.close()
     return extra
 
 

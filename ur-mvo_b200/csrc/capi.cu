@@ -10,7 +10,9 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/urmvo_b200.h"
@@ -91,6 +93,10 @@ struct urmvo_ctx {
   // optional NCCL communicator for the point-sharded BA (urmvo_comm_init)
   void* comm = nullptr;
   int rank = 0, world = 1;
+  // grow-only device workspace lent to the one-shot BA calls (no cudaMalloc / cudaFree per call)
+  unsigned char* ws_dev = nullptr;
+  size_t ws_bytes = 0;
+  bool ws_in_use = false;
   // reusable pinned staging buffer for the one-shot entry points
   void* pinned = nullptr;
   size_t pinned_size = 0;
@@ -144,6 +150,7 @@ extern "C" void urmvo_destroy(urmvo_ctx* c) {
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->pinned) cudaFreeHost(c->pinned);
+  if (c->ws_dev) cudaFree(c->ws_dev);
   delete c;
 }
 
@@ -174,6 +181,7 @@ struct urmvo_ba_plan {
   // observation permutation (point-major sort) when the caller's order was not sorted
   std::vector<int> perm;  // sorted position -> caller index (empty = identity)
   // point-sharded mode: [scal(8) | S | pad | b_s | b_p | hdiag] is one contiguous all-reduce buffer
+  bool borrowed_dev = false;  // dev is the context's workspace
   bool sharded = false;
   size_t off_scal = 0, off_hdiag = 0;
   size_t n_reduce_main = 0;   // doubles from scal through b_p
@@ -205,30 +213,36 @@ int build_window(int Nc, const uint8_t* fixed, int Np, int No, const int32_t* ob
     if (!fixed[c]) w.cam_free[c] = w.Ncf++;
   w.pt_start.assign(Np + 1, 0);
   sorted = true;
-  for (int o = 0; o < No; o++) {
-    const int p = obs_pt[o], c = obs_cam[o];
-    if (p < 0 || p >= Np || c < 0 || c >= Nc) return fail(URMVO_ERR_ARG, "local_ba: observation index out of range");
-    if (o > 0 && obs_pt[o - 1] > p) sorted = false;
-    w.pt_start[p + 1]++;
+  bool cams_increasing = true;  // inside every point (what the reference emits): then no duplicates
+  {
+    int prev_p = -1, prev_c = -1;
+    for (int o = 0; o < No; o++) {
+      const int p = obs_pt[o], c = obs_cam[o];
+      if ((unsigned)p >= (unsigned)Np || (unsigned)c >= (unsigned)Nc)
+        return fail(URMVO_ERR_ARG, "local_ba: observation index out of range");
+      if (p < prev_p) sorted = false;
+      if (p == prev_p && c <= prev_c) cams_increasing = false;
+      prev_p = p; prev_c = c;
+      w.pt_start[p + 1]++;
+    }
   }
   w.kmax = 1;
   for (int l = 0; l < Np; l++) {
     w.kmax = std::max(w.kmax, w.pt_start[l + 1]);
     w.pt_start[l + 1] += w.pt_start[l];
   }
-  order.resize(No);
-  if (sorted) {
-    for (int o = 0; o < No; o++) order[o] = o;
-  } else {
+  order.clear();  // empty = identity (already point-major sorted)
+  if (!sorted) {
+    order.resize(No);
     std::vector<int> fill(w.pt_start.begin(), w.pt_start.end() - 1);
     for (int o = 0; o < No; o++) order[fill[obs_pt[o]]++] = o;  // stable
   }
-  {  // a camera seeing the same point twice forces the atomic accumulation path
+  w.dup_cam = false;
+  if (!sorted || !cams_increasing) {  // a camera seeing the same point twice forces the atomic path
     std::vector<int> seen(Nc, -1);
-    w.dup_cam = false;
     for (int l = 0; l < Np && !w.dup_cam; l++)
       for (int s = w.pt_start[l]; s < w.pt_start[l + 1]; s++) {
-        const int c = obs_cam[order[s]];
+        const int c = obs_cam[sorted ? s : order[s]];
         if (seen[c] == l) { w.dup_cam = true; break; }
         seen[c] = l;
       }
@@ -254,7 +268,7 @@ int build_window(int Nc, const uint8_t* fixed, int Np, int No, const int32_t* ob
     for (int l = 0; l < Np; l++) {
       cfs.clear();
       for (int s = w.pt_start[l]; s < w.pt_start[l + 1]; s++) {
-        const int cf = w.cam_free[obs_cam[order[s]]];
+        const int cf = w.cam_free[obs_cam[order.empty() ? s : order[s]]];
         if (cf >= 0) cfs.push_back(cf);
       }
       std::sort(cfs.begin(), cfs.end());
@@ -296,7 +310,8 @@ int build_window(int Nc, const uint8_t* fixed, int Np, int No, const int32_t* ob
 extern "C" void urmvo_ba_plan_destroy(urmvo_ba_plan* p) {
   if (!p) return;
   cudaSetDevice(p->ctx->device);
-  if (p->dev) cudaFree(p->dev);
+  if (p->dev && p->borrowed_dev) p->ctx->ws_in_use = false;
+  else if (p->dev) cudaFree(p->dev);
   if (p->shard_state) cudaFree(p->shard_state);
   if (p->shard_state_host) cudaFreeHost(p->shard_state_host);
   delete p;
@@ -307,7 +322,7 @@ static int ba_plan_create_impl(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, const
                                const uint8_t* fixed, const double* pts, const double* uv,
                                const int32_t* cam, const int32_t* pt, const double* intr,
                                double chi2_thr, int it0, int it1, const urmvo_ba_options* opts,
-                               bool sharded, const uint8_t* covis) {
+                               bool sharded, const uint8_t* covis, bool borrow_ws = false) {
   if (!ctx || !out) return fail(URMVO_ERR_ARG, "ba_plan_create: null context / out");
   *out = nullptr;
   if (B <= 0 || !cam_off || !pt_off || !obs_off || !poses || !fixed || !pts || !uv || !cam || !pt || !intr)
@@ -320,22 +335,51 @@ static int ba_plan_create_impl(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, const
   p->B = B;
   p->total_c = cam_off[B]; p->total_p = pt_off[B]; p->total_o = obs_off[B];
   bool all_sorted = true;
-  std::vector<int> perm(p->total_o);
-  std::vector<int> order;
-  int max_ncf = 0;
-  long long sum_blk = 0, sum_ncf = 0;
+  std::vector<std::vector<int>> orders(B);
+  std::vector<int> rcs(B, URMVO_OK);
+  std::vector<char> sorted_w(B, 1);
+  std::vector<std::string> errs(B);
   for (int w = 0; w < B; w++) {
     const int Nc = cam_off[w + 1] - cam_off[w], Np = pt_off[w + 1] - pt_off[w], No = obs_off[w + 1] - obs_off[w];
     if (Nc <= 0 || Np < 0 || No < 0) { delete p; return fail(URMVO_ERR_ARG, "ba_plan_create: bad window offsets"); }
-    bool sorted = true;
-    int rc = build_window(Nc, fixed + cam_off[w], Np, No, cam + obs_off[w], pt + obs_off[w], wh[w], order, sorted, covis);
-    if (rc != URMVO_OK) { delete p; return rc; }
-    all_sorted = all_sorted && sorted;
-    for (int o = 0; o < No; o++) perm[obs_off[w] + o] = obs_off[w] + order[o];
+  }
+  {  // windows are independent: flatten them on all host threads
+    const int nt = std::max(1, std::min({(int)std::thread::hardware_concurrency(), 16, B / 4}));
+    std::atomic<int> next(0);
+    auto work = [&]() {
+      for (int w = next++; w < B; w = next++) {
+        const int Nc = cam_off[w + 1] - cam_off[w], Np = pt_off[w + 1] - pt_off[w], No = obs_off[w + 1] - obs_off[w];
+        bool sorted = true;
+        rcs[w] = build_window(Nc, fixed + cam_off[w], Np, No, cam + obs_off[w], pt + obs_off[w], wh[w], orders[w], sorted, covis);
+        if (rcs[w] != URMVO_OK) errs[w] = g_err;  // thread-local message of the worker
+        sorted_w[w] = sorted ? 1 : 0;
+      }
+    };
+    if (nt == 1) {
+      work();
+    } else {
+      std::vector<std::thread> th;
+      for (int t = 0; t < nt; t++) th.emplace_back(work);
+      for (auto& t : th) t.join();
+    }
+  }
+  int max_ncf = 0;
+  long long sum_blk = 0, sum_ncf = 0;
+  for (int w = 0; w < B; w++) {
+    if (rcs[w] != URMVO_OK) { delete p; return fail(rcs[w], errs[w]); }
+    all_sorted = all_sorted && sorted_w[w];
     p->kmax = std::max(p->kmax, wh[w].kmax);
     max_ncf = std::max(max_ncf, wh[w].Ncf);
     sum_blk += wh[w].nblk;
     sum_ncf += wh[w].Ncf;
+  }
+  std::vector<int> perm;
+  if (!all_sorted) {
+    perm.resize(p->total_o);
+    for (int w = 0; w < B; w++) {
+      const int No = obs_off[w + 1] - obs_off[w];
+      for (int o = 0; o < No; o++) perm[obs_off[w] + o] = obs_off[w] + (orders[w].empty() ? o : orders[w][o]);
+    }
   }
   if (!all_sorted) p->perm = perm;
   // ---- launch shape
@@ -473,7 +517,19 @@ static int ba_plan_create_impl(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, const
   p->off_inlier = A.take<uint8_t>(TO);
   p->off_stats = A.take<urmvo_ba_stats>(B);
   p->dev_bytes = A.off;
-  cudaError_t ce = cudaMalloc(&p->dev, p->dev_bytes);
+  cudaError_t ce = cudaSuccess;
+  if (borrow_ws && !ctx->ws_in_use) {
+    if (ctx->ws_bytes < p->dev_bytes) {
+      if (ctx->ws_dev) cudaFree(ctx->ws_dev);
+      ctx->ws_dev = nullptr; ctx->ws_bytes = 0;
+      const size_t want = p->dev_bytes + p->dev_bytes / 4;
+      ce = cudaMalloc(&ctx->ws_dev, want);
+      if (ce == cudaSuccess) ctx->ws_bytes = want;
+    }
+    if (ce == cudaSuccess) { p->dev = ctx->ws_dev; p->borrowed_dev = true; ctx->ws_in_use = true; }
+  } else {
+    ce = cudaMalloc(&p->dev, p->dev_bytes);
+  }
   if (ce != cudaSuccess) { delete p; return fail(URMVO_ERR_CUDA, std::string("cudaMalloc BA plan: ") + cudaGetErrorString(ce)); }
   unsigned char* D = p->dev;
 
@@ -756,8 +812,8 @@ extern "C" int urmvo_local_ba_batch(urmvo_ctx* ctx, int B, const int32_t* cam_of
                                     double chi2_thr, int it0, int it1, uint8_t* inlier, urmvo_ba_stats* stats,
                                     const urmvo_ba_options* opts) {
   urmvo_ba_plan* p = nullptr;
-  int rc = urmvo_ba_plan_create(ctx, &p, B, cam_off, pt_off, obs_off, poses, fixed, pts, uv, cam, pt, intr,
-                                chi2_thr, it0, it1, opts);
+  int rc = ba_plan_create_impl(ctx, &p, B, cam_off, pt_off, obs_off, poses, fixed, pts, uv, cam, pt, intr,
+                               chi2_thr, it0, it1, opts, false, nullptr, /*borrow_ws=*/true);
   if (rc != URMVO_OK) return rc;
   rc = urmvo_ba_plan_run(p);
   if (rc == URMVO_OK) rc = urmvo_ba_plan_download(p, poses, pts, inlier, stats);
