@@ -24,11 +24,22 @@ namespace {
 
 constexpr int kMaxSweeps = 30;
 constexpr float kJacobiTol = 5e-7f;
+// A column whose squared norm is below kJacobiTiny * ||A||_F^2 is numerically zero (the null column
+// of a rank-deficient DLT system reaches ~1e-20 after a few sweeps); rotating it against the other
+// columns only chases round-off and would keep every solve at the sweep limit.
+constexpr float kJacobiTiny = 1e-14f;
 
 // One-sided Jacobi: A (m x n, row-major, leading dim n) becomes U*Sigma, V (n x n) accumulates.
 void jacobi_onesided(int m, int n, float* A, float* V) {
   for (int i = 0; i < n; i++)
     for (int j = 0; j < n; j++) V[i * n + j] = (i == j) ? 1.0f : 0.0f;
+  float fro2 = 0.0f;  // sum over rows of the row sums (this order is part of the specification)
+  for (int k = 0; k < m; k++) {
+    float row = 0.0f;
+    for (int j = 0; j < n; j++) row += A[k * n + j] * A[k * n + j];
+    fro2 = (k == 0) ? row : fro2 + row;
+  }
+  const float tiny = kJacobiTiny * fro2;
   for (int sweep = 0; sweep < kMaxSweeps; sweep++) {
     bool rotated = false;
     for (int p = 0; p < n - 1; p++) {
@@ -40,6 +51,7 @@ void jacobi_onesided(int m, int n, float* A, float* V) {
           beta += aq * aq;
           gamma += ap * aq;
         }
+        if (alpha <= tiny || beta <= tiny) continue;
         if (std::fabs(gamma) <= kJacobiTol * std::sqrt(alpha * beta)) continue;
         rotated = true;
         float zeta = (beta - alpha) / (2.0f * gamma);

@@ -675,7 +675,9 @@ __device__ bool pcg_dense_smem(const Scope& sc, const BAWin& W, double lambda, d
     if (!spd6_inverse(A, Mi + i * 36)) s_ok = 0;
   }
   __syncthreads();
-  if (s_ok && threadIdx.x < 32) {
+  const int spd_ok = s_ok;
+  __syncthreads();  // warp 0 rewrites s_ok below: every warp has read it
+  if (spd_ok && threadIdx.x < 32) {
     const int lane = threadIdx.x;
     constexpr int R = 3;  // rows per lane: n <= 96
     double x[R], r[R], z[R], pp[R];
@@ -767,7 +769,9 @@ __device__ bool pcg_dense_smem(const Scope& sc, const BAWin& W, double lambda, d
   }
   __syncthreads();
   iters_out = s_it;
-  return s_ok != 0;
+  const bool result = s_ok != 0;
+  __syncthreads();  // the next call re-initialises s_ok / s_it
+  return result;
 }
 
 // ------------------------------------------------------------------------------- cameras

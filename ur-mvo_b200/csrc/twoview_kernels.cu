@@ -32,6 +32,9 @@ namespace {
 
 constexpr int kMaxSweeps = 30;
 constexpr float kJacobiTol = 5e-7f;
+// columns with squared norm <= kJacobiTiny * ||A||_F^2 are numerically zero and are not rotated
+// (otherwise the null column of a rank-deficient system keeps every solve at the sweep limit)
+constexpr float kJacobiTiny = 1e-14f;
 
 // One-sided (Hestenes) Jacobi on an m x n row-major matrix; V (n x n) accumulates the rotations.
 // Deliberately a real (non-inlined) function with run-time sizes: one copy of the loop nest serves
@@ -39,6 +42,13 @@ constexpr float kJacobiTol = 5e-7f;
 __device__ __noinline__ void jacobi_onesided(int m, int n, float* A, float* V) {
   for (int i = 0; i < n; i++)
     for (int j = 0; j < n; j++) V[i * n + j] = (i == j) ? 1.0f : 0.0f;
+  float fro2 = 0.0f;  // sum over rows of the row sums
+  for (int k = 0; k < m; k++) {
+    float row = 0.0f;
+    for (int j = 0; j < n; j++) row += A[k * n + j] * A[k * n + j];
+    fro2 = (k == 0) ? row : fro2 + row;
+  }
+  const float tiny = kJacobiTiny * fro2;
   for (int sweep = 0; sweep < kMaxSweeps; sweep++) {
     bool rotated = false;
     for (int p = 0; p < n - 1; p++) {
@@ -50,6 +60,7 @@ __device__ __noinline__ void jacobi_onesided(int m, int n, float* A, float* V) {
           beta += aq * aq;
           gamma += ap * aq;
         }
+        if (alpha <= tiny || beta <= tiny) continue;
         if (fabsf(gamma) <= kJacobiTol * sqrtf(alpha * beta)) continue;
         rotated = true;
         const float zeta = (beta - alpha) / (2.0f * gamma);
@@ -92,33 +103,99 @@ __device__ __noinline__ void null_vector(int m, int n, float* A, float* v) {
   for (int k = 0; k < n; k++) v[k] = V[k * n + best];
 }
 
+// One Jacobi pair (P,Q) of the 3x3 problem with compile-time column indices: the matrices stay in
+// registers.  Same operations in the same order as jacobi_onesided(3, 3, ...).
+template <int P, int Q>
+__device__ __forceinline__ bool jacobi3_pair(float (&A)[9], float (&V)[9], float tiny) {
+  float alpha = 0.0f, beta = 0.0f, gamma = 0.0f;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const float ap = A[k * 3 + P], aq = A[k * 3 + Q];
+    alpha += ap * ap;
+    beta += aq * aq;
+    gamma += ap * aq;
+  }
+  if (alpha <= tiny || beta <= tiny) return false;
+  if (fabsf(gamma) <= kJacobiTol * sqrtf(alpha * beta)) return false;
+  const float zeta = (beta - alpha) / (2.0f * gamma);
+  float t = 1.0f / (fabsf(zeta) + sqrtf(1.0f + zeta * zeta));
+  if (zeta < 0.0f) t = -t;
+  const float c = 1.0f / sqrtf(1.0f + t * t);
+  const float s = c * t;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const float ap = A[k * 3 + P], aq = A[k * 3 + Q];
+    A[k * 3 + P] = c * ap - s * aq;
+    A[k * 3 + Q] = s * ap + c * aq;
+  }
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const float vp = V[k * 3 + P], vq = V[k * 3 + Q];
+    V[k * 3 + P] = c * vp - s * vq;
+    V[k * 3 + Q] = s * vp + c * vq;
+  }
+  return true;
+}
+
 // 3x3 SVD, singular values descending; U.col(2) = +-(u0 x u1) such that U diag(w) V^T = A.
 __device__ __noinline__ void svd3(const float* Ain, float* U, float* w, float* V) {
   float A[9], Vt[9];
-  for (int i = 0; i < 9; i++) A[i] = Ain[i];
-  jacobi_onesided(3, 3, A, Vt);
-  float nrm[3];
-  int idx[3] = {0, 1, 2};
-  for (int j = 0; j < 3; j++) nrm[j] = col_norm(3, 3, A, j);
-  for (int i = 0; i < 2; i++) {
-    int b = i;
-    for (int j = i + 1; j < 3; j++)
-      if (nrm[idx[j]] > nrm[idx[b]]) b = j;
-    const int tmp = idx[i]; idx[i] = idx[b]; idx[b] = tmp;
+#pragma unroll
+  for (int i = 0; i < 9; i++) { A[i] = Ain[i]; Vt[i] = (i % 4 == 0) ? 1.0f : 0.0f; }
+  float fro2 = 0.0f;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    float row = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 3; j++) row += A[k * 3 + j] * A[k * 3 + j];
+    fro2 = (k == 0) ? row : fro2 + row;
   }
+  const float tiny = kJacobiTiny * fro2;
+  for (int sweep = 0; sweep < kMaxSweeps; sweep++) {
+    bool rotated = jacobi3_pair<0, 1>(A, Vt, tiny);
+    rotated = jacobi3_pair<0, 2>(A, Vt, tiny) || rotated;
+    rotated = jacobi3_pair<1, 2>(A, Vt, tiny) || rotated;
+    if (!rotated) break;
+  }
+  float nrm[3];
+#pragma unroll
   for (int j = 0; j < 3; j++) {
-    const int s = idx[j];
-    w[j] = nrm[s];
-    for (int k = 0; k < 3; k++) V[k * 3 + j] = Vt[k * 3 + s];
+    float sq = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 3; k++) sq += A[k * 3 + j] * A[k * 3 + j];
+    nrm[j] = sqrtf(sq);
+  }
+  // selection sort, descending, first index wins ties (indices kept in registers)
+  int i0 = 0, i1 = 1, i2 = 2;
+  {
+    int bsel = 0;
+    if (nrm[1] > nrm[0]) bsel = 1;
+    if (nrm[2] > nrm[bsel]) bsel = 2;
+    if (bsel == 1) { i0 = 1; i1 = 0; }
+    else if (bsel == 2) { i0 = 2; i2 = 0; }
+    auto nv = [&](int idx) { return idx == 0 ? nrm[0] : (idx == 1 ? nrm[1] : nrm[2]); };
+    if (nv(i2) > nv(i1)) { const int tmp = i1; i1 = i2; i2 = tmp; }
+  }
+  auto colA = [&](int k, int idx) { return idx == 0 ? A[k * 3] : (idx == 1 ? A[k * 3 + 1] : A[k * 3 + 2]); };
+  auto colV = [&](int k, int idx) { return idx == 0 ? Vt[k * 3] : (idx == 1 ? Vt[k * 3 + 1] : Vt[k * 3 + 2]); };
+  auto nsel = [&](int idx) { return idx == 0 ? nrm[0] : (idx == 1 ? nrm[1] : nrm[2]); };
+  const int idx[3] = {i0, i1, i2};
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    const int sidx = idx[j];
+    const float nj = nsel(sidx);
+    w[j] = nj;
+#pragma unroll
+    for (int k = 0; k < 3; k++) V[k * 3 + j] = colV(k, sidx);
     if (j < 2) {
-      for (int k = 0; k < 3; k++) U[k * 3 + j] = (nrm[s] > 0.0f) ? A[k * 3 + s] / nrm[s] : 0.0f;
+#pragma unroll
+      for (int k = 0; k < 3; k++) U[k * 3 + j] = (nj > 0.0f) ? colA(k, sidx) / nj : 0.0f;
     }
   }
   float c0 = U[3 + 0] * U[6 + 1] - U[6 + 0] * U[3 + 1];
   float c1 = U[6 + 0] * U[0 + 1] - U[0 + 0] * U[6 + 1];
   float c2 = U[0 + 0] * U[3 + 1] - U[3 + 0] * U[0 + 1];
-  const int s2 = idx[2];
-  const float d = c0 * A[0 + s2] + c1 * A[3 + s2] + c2 * A[6 + s2];
+  const float d = c0 * colA(0, i2) + c1 * colA(1, i2) + c2 * colA(2, i2);
   if (d < 0.0f) { c0 = -c0; c1 = -c1; c2 = -c2; }
   U[2] = c0; U[5] = c1; U[8] = c2;
 }
@@ -165,26 +242,45 @@ __global__ void tv_normalize_kernel(int n1, const float* __restrict__ keys1, flo
   const float* keys = blockIdx.x == 0 ? keys1 : keys2;
   float* pn = blockIdx.x == 0 ? pn1 : pn2;
   float* T = blockIdx.x == 0 ? T1 : T2;
+  constexpr int CH = 2048;  // keypoints staged per chunk (16 KB)
+  __shared__ float buf[CH * 2];
   __shared__ float sh[4];
+  // the reference's running sums are sequential (src/epipolar_geometry.cc:744-761): one thread adds
+  // in keypoint order, the others only stage the data into shared memory
+  float meanX = 0, meanY = 0;
+  for (int c0 = 0; c0 < n; c0 += CH) {
+    const int m = min(CH, n - c0);
+    for (int i = threadIdx.x; i < m * 2; i += blockDim.x) buf[i] = keys[(size_t)c0 * 2 + i];
+    __syncthreads();
+    if (threadIdx.x == 0)
+      for (int i = 0; i < m; i++) { meanX += buf[i * 2]; meanY += buf[i * 2 + 1]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { sh[0] = meanX / n; sh[1] = meanY / n; }
+  __syncthreads();
+  meanX = sh[0]; meanY = sh[1];
+  float meanDevX = 0, meanDevY = 0;
+  for (int c0 = 0; c0 < n; c0 += CH) {
+    const int m = min(CH, n - c0);
+    for (int i = threadIdx.x; i < m * 2; i += blockDim.x) buf[i] = keys[(size_t)c0 * 2 + i];
+    __syncthreads();
+    if (threadIdx.x == 0)
+      for (int i = 0; i < m; i++) {
+        meanDevX += fabsf(buf[i * 2] - meanX);
+        meanDevY += fabsf(buf[i * 2 + 1] - meanY);
+      }
+    __syncthreads();
+  }
   if (threadIdx.x == 0) {
-    float meanX = 0, meanY = 0;
-    for (int i = 0; i < n; i++) { meanX += keys[i * 2]; meanY += keys[i * 2 + 1]; }
-    meanX = meanX / n;
-    meanY = meanY / n;
-    float meanDevX = 0, meanDevY = 0;
-    for (int i = 0; i < n; i++) {
-      meanDevX += fabsf(keys[i * 2] - meanX);
-      meanDevY += fabsf(keys[i * 2 + 1] - meanY);
-    }
     meanDevX = meanDevX / n;
     meanDevY = meanDevY / n;
     const float sX = 1.0f / meanDevX, sY = 1.0f / meanDevY;
-    sh[0] = meanX; sh[1] = meanY; sh[2] = sX; sh[3] = sY;
+    sh[2] = sX; sh[3] = sY;
     for (int i = 0; i < 9; i++) T[i] = 0.0f;
     T[0] = sX; T[4] = sY; T[2] = -meanX * sX; T[5] = -meanY * sY; T[8] = 1.0f;
   }
   __syncthreads();
-  const float meanX = sh[0], meanY = sh[1], sX = sh[2], sY = sh[3];
+  const float sX = sh[2], sY = sh[3];
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     pn[i * 2] = (keys[i * 2] - meanX) * sX;
     pn[i * 2 + 1] = (keys[i * 2 + 1] - meanY) * sY;
@@ -261,6 +357,140 @@ tv_fit_kernel(int n_hyp, const int* __restrict__ sets, const float4* __restrict_
     float T2inv[9], tmp[9], H21[9], H12[9];
     inv3f(t2, T2inv);
     mat3_mul(T2inv, Hn, tmp);
+    mat3_mul(tmp, t1, H21);
+    inv3f(H21, H12);
+    for (int i = 0; i < 9; i++) { out[i] = H21[i]; out[9 + i] = H12[i]; }
+  }
+}
+
+// ------------------------------------------------------------------------------- cooperative fit
+//
+// tv_fit_kernel above keeps one thread per hypothesis (matrices in local memory, ~3.5 warps per SM
+// for 16384 hypotheses: latency-bound).  tv_fit_sub_kernel gives every hypothesis a SUB-WARP of
+// L = M lanes (8 for the 8x9 fundamental system, 16 for the 16x9 homography system): lane k owns
+// row k of A (and row k of V), the matrices live in shared memory, the three column dot products
+// of a Jacobi pair are formed as per-lane products followed by an ORDERED chain of adds over the
+// rows (shuffles), i.e. literally the restatement's  alpha += a*a  sequence, so every value is
+// bit-identical to the one-thread version.  4 (F) or 2 (H) hypotheses per warp.
+
+template <int L>
+__device__ __forceinline__ float ordered_sum(float v, int m, unsigned mask) {
+  float s = __shfl_sync(mask, v, 0, L);
+  for (int k = 1; k < m; k++) s = s + __shfl_sync(mask, v, k, L);
+  return s;
+}
+
+// A: M x 9 and V: 9 x 9 in shared memory (row-major), sub-warp of L = M lanes, r = lane in sub-warp.
+template <int M>
+__device__ void jacobi_null_vector_sub(float* A, float* V, int r, unsigned mask, float* v_out) {
+  constexpr int N = 9;
+  for (int e = r; e < N * N; e += M) V[e] = (e / N == e % N) ? 1.0f : 0.0f;
+  float tiny;
+  {
+    float row = 0.0f;
+    for (int j = 0; j < N; j++) row += A[r * N + j] * A[r * N + j];
+    tiny = kJacobiTiny * ordered_sum<M>(row, M, mask);  // sum over rows of the row sums
+  }
+  __syncwarp(mask);
+  for (int sweep = 0; sweep < kMaxSweeps; sweep++) {
+    bool rotated = false;
+    for (int p = 0; p < N - 1; p++) {
+      for (int q = p + 1; q < N; q++) {
+        const float ap = A[r * N + p], aq = A[r * N + q];
+        const float alpha = ordered_sum<M>(ap * ap, M, mask);
+        const float beta = ordered_sum<M>(aq * aq, M, mask);
+        const float gamma = ordered_sum<M>(ap * aq, M, mask);
+        if (alpha <= tiny || beta <= tiny) continue;
+        if (fabsf(gamma) <= kJacobiTol * sqrtf(alpha * beta)) continue;
+        rotated = true;
+        const float zeta = (beta - alpha) / (2.0f * gamma);
+        float t = 1.0f / (fabsf(zeta) + sqrtf(1.0f + zeta * zeta));
+        if (zeta < 0.0f) t = -t;
+        const float c = 1.0f / sqrtf(1.0f + t * t);
+        const float s = c * t;
+        A[r * N + p] = c * ap - s * aq;
+        A[r * N + q] = s * ap + c * aq;
+        for (int k = r; k < N; k += M) {
+          const float vp = V[k * N + p], vq = V[k * N + q];
+          V[k * N + p] = c * vp - s * vq;
+          V[k * N + q] = s * vp + c * vq;
+        }
+      }
+    }
+    if (!rotated) break;
+  }
+  __syncwarp(mask);
+  // column with the smallest norm (first index on ties)
+  int best = 0;
+  float bn = 0.0f;
+  for (int j = 0; j < N; j++) {
+    const float a = A[r * N + j];
+    const float nj = sqrtf(ordered_sum<M>(a * a, M, mask));
+    if (j == 0 || nj < bn) { bn = nj; best = j; }
+  }
+  for (int k = 0; k < N; k++) v_out[k] = V[k * N + best];
+}
+
+// MODEL 0: fundamental (M = 8), MODEL 1: homography (M = 16).  models: [2][n_hyp][18].
+template <int MODEL>
+__global__ void __launch_bounds__(256)
+tv_fit_sub_kernel(int n_hyp, const int* __restrict__ sets, const float4* __restrict__ pnm,
+                  const float* __restrict__ T1, const float* __restrict__ T2, float* __restrict__ models) {
+  constexpr int M = MODEL == 0 ? 8 : 16;
+  constexpr int PER_WARP = 32 / M;
+  constexpr int FL = M * 9 + 81;  // floats per hypothesis
+  extern __shared__ float sm_fit[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int sub = lane / M, r = lane - sub * M;
+  const unsigned mask = (M == 8 ? 0xFFu : 0xFFFFu) << (sub * M);
+  const int hyp = (blockIdx.x * (blockDim.x >> 5) + wid) * PER_WARP + sub;
+  if (hyp >= n_hyp) return;  // whole sub-warps leave together
+  float* A = sm_fit + (size_t)(wid * PER_WARP + sub) * FL;
+  float* V = A + M * 9;
+  const int* set = sets + (size_t)hyp * 8;
+  {
+    const float4 m = pnm[set[MODEL == 0 ? r : (r >> 1)]];
+    const float u1 = m.x, v1 = m.y, u2 = m.z, v2 = m.w;
+    float* row = A + r * 9;
+    if (MODEL == 0) {
+      row[0] = u2 * u1; row[1] = u2 * v1; row[2] = u2;
+      row[3] = v2 * u1; row[4] = v2 * v1; row[5] = v2;
+      row[6] = u1; row[7] = v1; row[8] = 1.0f;
+    } else if ((r & 1) == 0) {
+      row[0] = 0.0f; row[1] = 0.0f; row[2] = 0.0f;
+      row[3] = -u1; row[4] = -v1; row[5] = -1.0f;
+      row[6] = v2 * u1; row[7] = v2 * v1; row[8] = v2;
+    } else {
+      row[0] = u1; row[1] = v1; row[2] = 1.0f;
+      row[3] = 0.0f; row[4] = 0.0f; row[5] = 0.0f;
+      row[6] = -u2 * u1; row[7] = -u2 * v1; row[8] = -u2;
+    }
+  }
+  __syncwarp(mask);
+  float nv[9];
+  jacobi_null_vector_sub<M>(A, V, r, mask, nv);
+  if (r != 0) return;
+  float t1[9], t2[9];
+  for (int i = 0; i < 9; i++) { t1[i] = T1[i]; t2[i] = T2[i]; }
+  float* out = models + ((size_t)MODEL * n_hyp + hyp) * 18;
+  if (MODEL == 0) {
+    float U[9], w[3], Vs[9];
+    svd3(nv, U, w, Vs);
+    w[2] = 0.0f;
+    float Fn[9];
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++)
+        Fn[i * 3 + j] = (U[i * 3] * w[0]) * Vs[j * 3] + (U[i * 3 + 1] * w[1]) * Vs[j * 3 + 1] +
+                        (U[i * 3 + 2] * w[2]) * Vs[j * 3 + 2];
+    float T2t[9], tmp[9], F21[9];
+    mat3_T(t2, T2t);
+    mat3_mul(T2t, Fn, tmp);
+    mat3_mul(tmp, t1, F21);
+    for (int i = 0; i < 9; i++) { out[i] = F21[i]; out[9 + i] = 0.0f; }
+  } else {
+    float T2inv[9], tmp[9], H21[9], H12[9];
+    inv3f(t2, T2inv);
+    mat3_mul(T2inv, nv, tmp);
     mat3_mul(tmp, t1, H21);
     inv3f(H21, H12);
     for (int i = 0; i < 9; i++) { out[i] = H21[i]; out[9 + i] = H12[i]; }
@@ -620,8 +850,15 @@ cudaError_t launch_tv_ransac(const TVBuffers& b, float sigma, int n_sm, cudaStre
   nl++;
   tv_gather_kernel<<<(b.N + 255) / 256, 256, 0, stream>>>(b.N, b.m1, b.m2, b.keys1, b.keys2, b.pn1, b.pn2, b.uv, b.pnm);
   nl++;
-  tv_fit_kernel<<<(2 * b.n_hyp + 63) / 64, 64, 0, stream>>>(b.n_hyp, b.sets, b.pnm, b.T1, b.T2, b.models);
-  nl++;
+  {
+    // cooperative fit: 4 fundamental / 2 homography hypotheses per warp, 8 warps per CTA
+    const int wpc = 8;
+    const int gF = (b.n_hyp + wpc * 4 - 1) / (wpc * 4), gH = (b.n_hyp + wpc * 2 - 1) / (wpc * 2);
+    const size_t smF = (size_t)wpc * 4 * (8 * 9 + 81) * sizeof(float), smH = (size_t)wpc * 2 * (16 * 9 + 81) * sizeof(float);
+    tv_fit_sub_kernel<0><<<gF, wpc * 32, smF, stream>>>(b.n_hyp, b.sets, b.pnm, b.T1, b.T2, b.models);
+    tv_fit_sub_kernel<1><<<gH, wpc * 32, smH, stream>>>(b.n_hyp, b.sets, b.pnm, b.T1, b.T2, b.models);
+    nl += 2;
+  }
   const float inv_sigma2 = 1.0f / (sigma * sigma);
   const size_t smem = (size_t)b.N * sizeof(float4);
   const int stage = smem <= 160 * 1024 ? 1 : 0;
