@@ -622,24 +622,33 @@ __device__ bool pcg_phase(const Scope& sc, const BAWin& W, double tol, int max_i
   return ok;
 }
 
-// Small windows (acc_mode 1): CTA 0 of the scope gathers the per-CTA partials of S / b_s / b_p,
-// builds the damped dense reduced camera system in shared memory (n = 6*Ncf <= 96) and warp 0
-// runs block-Jacobi PCG on it with shuffles only.  sm: >= n*n + 4*n + 36*Ncf doubles.
+// Small windows (acc_mode >= 1): CTA 0 of the scope gathers the per-CTA partials of S / b_s / b_p,
+// builds the damped dense reduced camera system in shared memory (n = 6*Ncf <= 96) and runs
+// block-Jacobi PCG on it with the whole CTA: thread (chunk c, row r) multiplies a slice of row r,
+// the slices are combined in chunk order, dot products are reduced in fixed order.
+// sm: >= n*n + (5 + chunks)*n + 36*Ncf doubles (host: pcg_dense_doubles()).
 // Writes x_p and the summed raw gradient b_p to global memory for the other CTAs.
 template <class Scope>
 __device__ bool pcg_dense_smem(const Scope& sc, const BAWin& W, double lambda, double tol, int max_iter,
                                double* sm, int& iters_out) {
   const int n = W.Ncf * 6, nb = sc.nblk();
+  const int tid = threadIdx.x;
+  const int C = max(1, (int)blockDim.x / max(n, 1));  // column chunks
+  const int Wc = (n + C - 1) / C;                      // columns per chunk
   double* Sd = sm;               // n x n, symmetric
   double* bsv = Sd + n * n;      // n
   double* pv = bsv + n;          // n
   double* rv = pv + n;           // n
-  double* Mi = rv + n;           // Ncf x 36
-  __shared__ int s_ok, s_it;
+  double* xv = rv + n;           // n
+  double* apv = xv + n;          // n
+  double* Mi = apv + n;          // Ncf x 36 (first the Cholesky factors, then the inverses)
+  double* prt = Mi + W.Ncf * 36; // C x n partial products
+  __shared__ int s_ok;
+  __shared__ double s_red[8];
   iters_out = 0;
   if (n == 0) return true;
   const int n_s = W.nblk * 36;
-  for (int e = threadIdx.x; e < n_s; e += blockDim.x) {
+  for (int e = tid; e < n_s; e += blockDim.x) {
     double v = 0.0;
     for (int b = 0; b < nb; b++) v += __ldcg(W.Spart + (size_t)b * W.acc_len + e);
     const int blk = e / 36, ab = e - blk * 36, a = ab / 6, c = ab - a * 6;
@@ -659,119 +668,137 @@ __device__ bool pcg_dense_smem(const Scope& sc, const BAWin& W, double lambda, d
       Sd[q * n + r] = v;
     }
   }
-  for (int e = threadIdx.x; e < 2 * n; e += blockDim.x) {
+  for (int e = tid; e < 2 * n; e += blockDim.x) {
     double v = 0.0;
     for (int b = 0; b < nb; b++) v += __ldcg(W.Spart + (size_t)b * W.acc_len + n_s + e);
     if (e < n) bsv[e] = v; else __stcg(W.bp + (e - n), v);
   }
-  if (threadIdx.x == 0) { s_ok = 1; s_it = 0; }
+  if (tid == 0) s_ok = 1;
   __syncthreads();
-  for (int i = threadIdx.x; i < W.Ncf; i += blockDim.x) {
-    double A[36];
-#pragma unroll
-    for (int a = 0; a < 6; a++)
-#pragma unroll
-      for (int c = 0; c < 6; c++) A[a * 6 + c] = Sd[(i * 6 + a) * n + i * 6 + c];
-    if (!spd6_inverse(A, Mi + i * 36)) s_ok = 0;
-  }
-  __syncthreads();
-  const int spd_ok = s_ok;
-  __syncthreads();  // warp 0 rewrites s_ok below: every warp has read it
-  if (spd_ok && threadIdx.x < 32) {
-    const int lane = threadIdx.x;
-    constexpr int R = 3;  // rows per lane: n <= 96
-    double x[R], r[R], z[R], pp[R];
-    double rz = 0.0;
-#pragma unroll
-    for (int k = 0; k < R; k++) {
-      const int row = lane + 32 * k;
-      x[k] = 0.0; r[k] = 0.0; z[k] = 0.0; pp[k] = 0.0;
-      if (row < n) {
-        const int i = row / 6, a = row - i * 6;
-        double zz = 0.0;
-#pragma unroll
-        for (int c = 0; c < 6; c++) zz += Mi[i * 36 + a * 6 + c] * bsv[i * 6 + c];
-        r[k] = bsv[row]; z[k] = zz; pp[k] = zz;
-        pv[row] = zz;
-        rz += r[k] * zz;
-      }
-    }
-    rz = warp_sum(rz);
-    __syncwarp();
+  // block-Jacobi preconditioner: 6x6 Cholesky by one thread per camera, then the six columns of
+  // the inverse by six threads per camera
+  double* Lf = prt;  // Ncf x 36 scratch for the factors (prt is free until the first product)
+  for (int i = tid; i < W.Ncf; i += blockDim.x) {
+    double L[36];
     bool ok = true;
-    int it = 0;
-    if (!(rz > 0.0)) {
-      ok = (rz == 0.0);
-    } else {
-      const double stop = tol * tol * rz;
-      for (; it < max_iter; it++) {
-        double ap[R], pap = 0.0;
 #pragma unroll
-        for (int k = 0; k < R; k++) {
-          const int row = lane + 32 * k;
-          ap[k] = 0.0;
-          if (row < n) {
-            double s0 = 0.0, s1 = 0.0;
-            int c = 0;
-            for (; c + 1 < n; c += 2) {
-              s0 += Sd[c * n + row] * pv[c];
-              s1 += Sd[(c + 1) * n + row] * pv[c + 1];
-            }
-            if (c < n) s0 += Sd[c * n + row] * pv[c];
-            ap[k] = s0 + s1;
-            pap += pp[k] * ap[k];
-          }
+    for (int r = 0; r < 6; r++) {
+#pragma unroll
+      for (int c = 0; c <= r; c++) {
+        double v = Sd[(i * 6 + r) * n + i * 6 + c];
+#pragma unroll
+        for (int k = 0; k < c; k++) v -= L[r * 6 + k] * L[c * 6 + k];
+        if (c < r) L[r * 6 + c] = v * L[c * 6 + c];  // diagonal holds 1 / L_cc
+        else {
+          if (!(v > 0.0)) { ok = false; v = 1.0; }
+          L[r * 6 + r] = 1.0 / sqrt(v);
         }
-        pap = warp_sum(pap);
-        if (!(pap > 0.0)) { ok = false; break; }
-        const double alpha = rz / pap;
-#pragma unroll
-        for (int k = 0; k < R; k++) {
-          const int row = lane + 32 * k;
-          if (row < n) {
-            x[k] += alpha * pp[k];
-            r[k] -= alpha * ap[k];
-            rv[row] = r[k];
-          }
-        }
-        __syncwarp();
-        double rzn = 0.0;
-#pragma unroll
-        for (int k = 0; k < R; k++) {
-          const int row = lane + 32 * k;
-          if (row < n) {
-            const int i = row / 6, a = row - i * 6;
-            double zz = 0.0;
-#pragma unroll
-            for (int c = 0; c < 6; c++) zz += Mi[i * 36 + a * 6 + c] * rv[i * 6 + c];
-            z[k] = zz;
-            rzn += r[k] * zz;
-          }
-        }
-        rzn = warp_sum(rzn);
-        if (!(rzn > stop)) { it++; break; }
-        const double beta = rzn / rz;
-        rz = rzn;
-#pragma unroll
-        for (int k = 0; k < R; k++) {
-          const int row = lane + 32 * k;
-          if (row < n) { pp[k] = z[k] + beta * pp[k]; pv[row] = pp[k]; }
-        }
-        __syncwarp();
       }
     }
+    if (!ok) s_ok = 0;
 #pragma unroll
-    for (int k = 0; k < R; k++) {
-      const int row = lane + 32 * k;
-      if (row < n) __stcg(W.xp + row, ok ? x[k] : 0.0);
-    }
-    if (lane == 0) { s_ok = ok ? 1 : 0; s_it = it; }
+    for (int e = 0; e < 36; e++) Lf[i * 36 + e] = L[e];
   }
   __syncthreads();
-  iters_out = s_it;
-  const bool result = s_ok != 0;
-  __syncthreads();  // the next call re-initialises s_ok / s_it
-  return result;
+  for (int e = tid; e < n; e += blockDim.x) {  // column `col` of inverse(S_ii)
+    const int i = e / 6, col = e - i * 6;
+    const double* L = Lf + i * 36;
+    double y[6];
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+      double v = (r == col) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k = 0; k < r; k++) v -= L[r * 6 + k] * y[k];
+      y[r] = v * L[r * 6 + r];
+    }
+#pragma unroll
+    for (int r = 5; r >= 0; r--) {
+      double v = y[r];
+#pragma unroll
+      for (int k = r + 1; k < 6; k++) v -= L[k * 6 + r] * y[k];
+      y[r] = v * L[r * 6 + r];
+    }
+#pragma unroll
+    for (int r = 0; r < 6; r++) Mi[i * 36 + r * 6 + col] = y[r];
+  }
+  __syncthreads();
+  if (!s_ok) return false;
+  // fixed-order sum over the first n threads (<= 3 warps); result in every thread
+  auto cta_dot = [&](double v) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((tid & 31) == 0 && tid < 96) s_red[tid >> 5] = v;
+    __syncthreads();
+    double t = s_red[0];
+    if (n > 32) t += s_red[1];
+    if (n > 64) t += s_red[2];
+    return t;
+  };
+  auto precond = [&](int row, const double* vec) {
+    const int i = row / 6, a = row - i * 6;
+    double zz = 0.0;
+#pragma unroll
+    for (int c = 0; c < 6; c++) zz += Mi[i * 36 + a * 6 + c] * vec[i * 6 + c];
+    return zz;
+  };
+  double x = 0.0, r = 0.0, z = 0.0, p = 0.0;
+  if (tid < n) {
+    r = bsv[tid];
+    z = precond(tid, bsv);
+    p = z;
+    pv[tid] = p;
+  }
+  double rz = cta_dot(tid < n ? r * z : 0.0);  // its barriers also publish pv
+  bool ok = true;
+  int it = 0;
+  if (!(rz > 0.0)) {
+    ok = (rz == 0.0);
+  } else {
+    const double stop = tol * tol * rz;
+    const int row = tid % n, ch = tid / n;
+    for (; it < max_iter; it++) {
+      if (ch < C) {  // slice [ch*Wc, ...) of row `row`; S is symmetric, so read it column-major
+        double s0 = 0.0;
+        const int c1 = min(n, (ch + 1) * Wc);
+        for (int c = ch * Wc; c < c1; c++) s0 += Sd[c * n + row] * pv[c];
+        prt[ch * n + row] = s0;
+      }
+      __syncthreads();
+      double ap = 0.0;
+      if (tid < n) {
+        for (int c = 0; c < C; c++) ap += prt[c * n + tid];
+        apv[tid] = ap;
+      }
+      const double pap = cta_dot(tid < n ? p * ap : 0.0);
+      if (!(pap > 0.0)) { ok = false; break; }
+      const double alpha = rz / pap;
+      if (tid < n) {
+        x += alpha * p;
+        r -= alpha * ap;
+        rv[tid] = r;
+      }
+      __syncthreads();
+      if (tid < n) z = precond(tid, rv);
+      const double rzn = cta_dot(tid < n ? r * z : 0.0);
+      if (!(rzn > stop)) { it++; break; }
+      const double beta = rzn / rz;
+      rz = rzn;
+      if (tid < n) { p = z + beta * p; pv[tid] = p; }
+      __syncthreads();
+    }
+  }
+  if (tid < n) __stcg(W.xp + tid, ok ? x : 0.0);
+  __syncthreads();
+  iters_out = it;
+  return ok;
+}
+
+int pcg_dense_doubles(int Ncf, int threads) {
+  const int n = Ncf * 6;
+  if (n == 0) return 0;
+  const int C = threads / n > 1 ? threads / n : 1;
+  const int extra = C * n > Ncf * 36 ? C * n : Ncf * 36;  // partial products / Cholesky scratch
+  return n * n + 5 * n + 36 * Ncf + extra;
 }
 
 // ------------------------------------------------------------------------------- cameras
@@ -1642,6 +1669,10 @@ __device__ __forceinline__ void solve_window_dispatch(const Scope& sc, const BAW
 }
 
 // Batched windows: one thread-block cluster per window (cluster dims set at launch).
+// KMODE >= 0: every window of the batch uses accumulation mode KMODE (the usual case: one camera
+// count per batch) — a kernel specialised for that mode gets its own register allocation instead of
+// the maximum over all modes; KMODE < 0: per-window dispatch.
+template <int KMODE>
 __global__ void __launch_bounds__(256, 1)
 ba_window_cluster_kernel(const BAWin* __restrict__ wins, BARun run, int kmax_all, int work_stride,
                          int ints_per_warp) {
@@ -1651,7 +1682,8 @@ ba_window_cluster_kernel(const BAWin* __restrict__ wins, BARun run, int kmax_all
   const int n_clusters = gridDim.x / sc.nblk();
   const int cid = blockIdx.x / sc.nblk();
   for (int w = cid; w < run.n_win; w += n_clusters) {
-    solve_window_dispatch(sc, wins[w], run, v);
+    if (KMODE >= 0) solve_window<(KMODE >= 0 ? KMODE : 0)>(sc, wins[w], run, v.st, v.pst, v.wa, v.pcg, v.red);
+    else solve_window_dispatch(sc, wins[w], run, v);
     sc.sync();
   }
 }
@@ -1927,14 +1959,15 @@ void shard_flags(const void* host_copy, int* cont_trials, int* terminate) {
   *terminate = s->terminate;
 }
 
-cudaError_t launch_ba_cluster(const BAWin* wins_dev, const BARun& run, int kmax, int work_stride,
-                              int ints_per_warp, int n_clusters, int cluster_size, int threads,
-                              cudaStream_t stream) {
+template <int KMODE>
+static cudaError_t launch_ba_cluster_t(const BAWin* wins_dev, const BARun& run, int kmax, int work_stride,
+                                       int ints_per_warp, int n_clusters, int cluster_size, int threads,
+                                       cudaStream_t stream) {
   const size_t smem = ba_smem_bytes(threads, work_stride, ints_per_warp);
-  cudaError_t e = cudaFuncSetAttribute(ba_window_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(ba_window_cluster_kernel<KMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   if (cluster_size > 8) {
-    e = cudaFuncSetAttribute(ba_window_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    e = cudaFuncSetAttribute(ba_window_cluster_kernel<KMODE>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     if (e != cudaSuccess) return e;
   }
   cudaLaunchConfig_t cfg = {};
@@ -1949,7 +1982,20 @@ cudaError_t launch_ba_cluster(const BAWin* wins_dev, const BARun& run, int kmax,
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, ba_window_cluster_kernel, wins_dev, run, kmax, work_stride, ints_per_warp);
+  return cudaLaunchKernelEx(&cfg, ba_window_cluster_kernel<KMODE>, wins_dev, run, kmax, work_stride, ints_per_warp);
+}
+
+// mode: the common accumulation mode of the batch (0..3) or -1 for a mixed batch
+cudaError_t launch_ba_cluster(const BAWin* wins_dev, const BARun& run, int mode, int kmax, int work_stride,
+                              int ints_per_warp, int n_clusters, int cluster_size, int threads,
+                              cudaStream_t stream) {
+  switch (mode) {
+    case 3: return launch_ba_cluster_t<3>(wins_dev, run, kmax, work_stride, ints_per_warp, n_clusters, cluster_size, threads, stream);
+    case 2: return launch_ba_cluster_t<2>(wins_dev, run, kmax, work_stride, ints_per_warp, n_clusters, cluster_size, threads, stream);
+    case 1: return launch_ba_cluster_t<1>(wins_dev, run, kmax, work_stride, ints_per_warp, n_clusters, cluster_size, threads, stream);
+    case 0: return launch_ba_cluster_t<0>(wins_dev, run, kmax, work_stride, ints_per_warp, n_clusters, cluster_size, threads, stream);
+    default: return launch_ba_cluster_t<-1>(wins_dev, run, kmax, work_stride, ints_per_warp, n_clusters, cluster_size, threads, stream);
+  }
 }
 
 int ba_grid_capacity(int threads, int kmax) {

@@ -170,6 +170,7 @@ struct urmvo_ba_plan {
   int total_c = 0, total_p = 0, total_o = 0;
   int kmax = 1;
   int work_stride = 0, ints_per_warp = 0;
+  int batch_mode = -1;  // common accumulation mode of all windows or -1
   int cluster_size = 1, threads = 256, n_clusters = 0;
   bool use_grid = false;
   int grid_blocks = 0;
@@ -424,14 +425,15 @@ static int ba_plan_create_impl(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, const
       else { need = std::max(ba_pack_doubles(), w.acc_len); ints = std::max(ints, 128); }
       stride = std::max(stride, need);
       if (w.acc_mode >= 1) {
-        const int n = w.Ncf * 6;
-        pcg_d = std::max(pcg_d, n * n + 4 * n + 36 * w.Ncf);
+        pcg_d = std::max(pcg_d, pcg_dense_doubles(w.Ncf, p->threads));
       }
     }
     stride = std::max(stride, (pcg_d + nw - 1) / nw);
     stride = (stride + 1) & ~1;  // keep the int area 16-byte aligned
     p->work_stride = stride;
     p->ints_per_warp = ints;
+    p->batch_mode = wh[0].acc_mode;
+    for (auto& w : wh) if (w.acc_mode != p->batch_mode) p->batch_mode = -1;
     if (ba_smem_bytes(p->threads, stride, ints) <= smem_budget) break;
     if (p->threads > 64) { p->threads -= 32; continue; }
     // drop the most expensive small-window mode to the next cheaper one and retry
@@ -770,7 +772,7 @@ extern "C" int urmvo_ba_plan_run(urmvo_ba_plan* p) {
   const BAWin* wins = (const BAWin*)(p->dev + p->off_wins);
   cudaError_t e;
   if (p->use_grid) e = launch_ba_grid(wins, p->run, p->kmax, p->grid_blocks, p->threads, p->ctx->stream);
-  else e = launch_ba_cluster(wins, p->run, p->kmax, p->work_stride, p->ints_per_warp, p->n_clusters, p->cluster_size, p->threads, p->ctx->stream);
+  else e = launch_ba_cluster(wins, p->run, p->batch_mode, p->kmax, p->work_stride, p->ints_per_warp, p->n_clusters, p->cluster_size, p->threads, p->ctx->stream);
   if (e != cudaSuccess) return fail(URMVO_ERR_CUDA, std::string("BA kernel launch: ") + cudaGetErrorString(e));
   p->ctx->launches++;
   return URMVO_OK;

@@ -12,9 +12,10 @@ namespace urmvo {
 size_t ba_smem_bytes(int threads, int work_stride, int ints_per_warp);
 int ba_stage_doubles(int kmax);  // staging fields of the one-point-per-warp modes
 int ba_pack_doubles();           // staging fields of the packed modes
+int pcg_dense_doubles(int Ncf, int threads);  // shared memory of the dense in-smem PCG
 int ba_tile_doubles();           // atomic mode: per-warp transposition tile for coalesced REDs
 // Batched windows: grid = n_clusters * cluster_size CTAs, one cluster per window.
-cudaError_t launch_ba_cluster(const BAWin* wins_dev, const BARun& run, int kmax, int work_stride,
+cudaError_t launch_ba_cluster(const BAWin* wins_dev, const BARun& run, int mode, int kmax, int work_stride,
                               int ints_per_warp, int n_clusters, int cluster_size, int threads,
                               cudaStream_t stream);
 // One (or a few) large problems on a cooperative grid. grid_blocks <= co-resident capacity.
