@@ -416,6 +416,16 @@ def side_measurements(ctx, stream, torch):
                               "pcg_iters": int(bst.pcg_iters[0] + bst.pcg_iters[1]),
                               "linearise_bytes_survey_8d": int(168 * big["uv"].shape[0] + 96 * big["pts"].shape[0] + 272 * 50)}
     bplan.close()
+    # the single 10-keyframe window of configs[0] (latency form: one window on a 16-CTA cluster)
+    one = synth.cfg1()
+    splan = U.BAPlan(ctx, pack_ba_batch([one]))
+    dt = timed(splan.run, 10)
+    sst = splan.download()[3][0]
+    t0 = time.perf_counter(); o = po.local_ba(one); tc = time.perf_counter() - t0
+    extra["ba_single_window_cfg1"] = {"lm_iters_per_s": (sst.iters[0] + sst.iters[1]) / dt, "ms": dt * 1e3,
+                                      "cpu_lm_iters_per_s": (o[3].iters[0] + o[3].iters[1]) / tc, "cpu_sample": "1 window, 1 thread",
+                                      "rel_cost_diff": abs(sst.chi2_final[1] - o[3].chi2_final[1]) / abs(o[3].chi2_final[1])}
+    splan.close()
     return extra
 
 

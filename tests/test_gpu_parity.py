@@ -319,3 +319,56 @@ def test_sharded_ba_two_ranks_over_nccl(oracle):
     line = [l for l in out.stdout.splitlines() if "rel cost diff" in l][0]
     rel = float(line.split("rel cost diff")[1].split(";")[0])
     assert rel < REL_COST and "inlier mismatches 0" in line
+
+
+def test_hypothesis_sharded_ransac_two_ranks(oracle):
+    """cfg3 hypotheses split over two GPUs, winners merged with the earliest-index tie rule."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                          "127.0.0.1", "--master-port", "29534", os.path.join(root, "scripts", "sharded_ransac.py"), "2048", "--check"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "match" in out.stdout and "MISMATCH" not in out.stdout
+
+
+# ------------------------------------------------------------------------------- more LM edge cases
+
+def test_ba_far_start_exercises_rejections_and_termination(oracle, ctx):
+    """A bad initial estimate: rejected trials (lambda growth), possibly early termination; the
+    trial / iteration pattern and the stale-error classification must follow the oracle."""
+    for seed, rot, tr, pt in ((51, 12.0, 1.0, 1.5), (52, 20.0, 2.0, 2.0), (53, 0.0, 0.0, 0.0)):
+        p = synth.small_ba(seed=seed, rot_sigma_deg=rot, trans_sigma=tr, pt_sigma=pt, outlier_frac=0.15)
+        gp, gx, gi, gs = ctx.local_ba(p)
+        op, ox, oi, os_ = oracle.local_ba(p)
+        rows = os_.rows()
+        assert list(gs.iters) == list(os_.iters)[:2]
+        assert gs.trials[0] == sum(r[3] for r in rows[: os_.iters[0]])
+        if abs(os_.chi2_final[1]) > 0:
+            assert abs(gs.chi2_final[1] - os_.chi2_final[1]) <= 1e-6 * abs(os_.chi2_final[1])
+        assert (gi != oi).sum() == 0
+
+
+def test_ba_batch_of_full_size_windows_matches_single_solves(oracle, ctx):
+    """BASELINE size: a batch of cfg1 windows (one window per SM) gives, window by window, what the
+    single-window (16-CTA cluster) solve and the oracle give."""
+    probs = [synth.make_ba(3001 + i, 10, 2000, 7.7, 10, 3, 0.05) for i in range(6)]
+    batch = pack_ba_batch(probs * 30)  # 180 windows > 148 SMs
+    plan = U.BAPlan(ctx, batch)
+    plan.run()
+    poses, pts, inl, st = plan.download()
+    plan.close()
+    for w in (0, 5, 77, 179):
+        p = probs[w % 6]
+        c = slice(batch["cam_off"][w], batch["cam_off"][w + 1]); o = slice(batch["obs_off"][w], batch["obs_off"][w + 1])
+        sp, sx, si, ss = ctx.local_ba(p)
+        assert np.abs(poses[c] - sp).max() < 1e-9 and np.array_equal(inl[o], si)
+    op, ox, oi, os_ = oracle.local_ba(probs[0])
+    assert abs(st[0].chi2_final[1] - os_.chi2_final[1]) <= 1e-6 * abs(os_.chi2_final[1]) and np.array_equal(inl[:oi.size], oi)
+    # identical windows give bit-identical results wherever they run
+    c0 = slice(batch["cam_off"][0], batch["cam_off"][1]); c6 = slice(batch["cam_off"][6], batch["cam_off"][7])
+    assert np.array_equal(poses[c0], poses[c6])
