@@ -109,11 +109,18 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def wait_first(self, timeout=3.0):
+        """nvidia-smi needs a few hundred ms to start: block until the first sample arrived."""
+        t0 = time.perf_counter()
+        while self.proc and not self.rows and time.perf_counter() - t0 < timeout:
+            time.sleep(0.01)
+
+    def stop(self, t_begin=None, t_end=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.03)  # let the last sample of the region arrive
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -121,7 +128,10 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = [r for (t, r) in self.rows if t_begin is None or (t_begin <= t <= t_end + 0.05)]
+        if not rows:  # region shorter than one sampling period: take the samples around it
+            rows = [r for (t, r) in self.rows][-3:]
+        for r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
@@ -268,10 +278,14 @@ def main():
     _, _, _, st0 = plans[0].download()
     stats_rot = [plans[r].download()[3] for r in range(n_rot)]
     sampler = ClockSampler(local_rank)
+    sampler.start()
+    sampler.wait_first()
+    for w in range(3):  # keep the GPU under load while the sampler spins up
+        plans[w % n_rot].run()
+    ctx.sync()
     launches0 = ctx.launches
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     torch.cuda.synchronize(); barrier()
-    sampler.start()
     t_wall0 = time.perf_counter()
     for k in range(args.steps):
         ev[k][0].record(stream)
@@ -279,7 +293,7 @@ def main():
         ev[k][1].record(stream)
     ctx.sync(); torch.cuda.synchronize(); barrier()
     t_wall = time.perf_counter() - t_wall0
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_wall0, t_wall0 + t_wall)
     gpu_launches = ctx.launches - launches0
     step_ms = [a.elapsed_time(b) for a, b in ev]
     t_dev = max_over_ranks(sum(step_ms) / 1e3)
@@ -316,6 +330,7 @@ def main():
     out = {"poses": torch.empty_like(pinned["poses"]).pin_memory().numpy(),
            "pts": torch.empty_like(pinned["pts"]).pin_memory().numpy(),
            "inlier": torch.empty(host["uv"].shape[0], dtype=torch.uint8).pin_memory().numpy()}
+    # (a) one call at a time on one context: the latency form
     for _ in range(2):
         ctx.local_ba_batch(hb, out=out)
     torch.cuda.synchronize(); barrier()
@@ -326,11 +341,41 @@ def main():
         _, _, _, sts = ctx.local_ba_batch(hb, out=out)
         e2e_its += sum(s.iters[0] + s.iters[1] for s in sts)
     torch.cuda.synchronize(); barrier()
+    t_seq = max_over_ranks(time.perf_counter() - t0)
+    seq_value = sum_over_ranks(float(e2e_its)) / t_seq
+    # (b) the throughput form a caller with several windows in flight uses: two host threads, each
+    # with its own context (own stream, own pinned staging), alternate steps, so the flattening /
+    # H2D / D2H of one step overlaps the kernel of the other.  Every step still copies its inputs
+    # from pinned host memory and reads its results back inside the timed region.
+    ctx2 = U.Context(local_rank)
+    out2 = {k: torch.empty(v.shape, dtype=torch.from_numpy(v).dtype).pin_memory().numpy() for k, v in out.items()}
+    ctx2.local_ba_batch(hb, out=out2)
+    n_pipe = 2 * max(2, min(args.steps, 8))
+    its_box = [0, 0]
+
+    def worker(idx, c, o):
+        for _ in range(n_pipe // 2):
+            _, _, _, sts = c.local_ba_batch(hb, out=o)
+            its_box[idx] += sum(s.iters[0] + s.iters[1] for s in sts)
+
+    torch.cuda.synchronize(); barrier()
+    t0 = time.perf_counter()
+    th = [threading.Thread(target=worker, args=(0, ctx, out)), threading.Thread(target=worker, args=(1, ctx2, out2))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    torch.cuda.synchronize(); barrier()
     t_e2e = max_over_ranks(time.perf_counter() - t0)
-    e2e_value = sum_over_ranks(float(e2e_its)) / t_e2e
+    e2e_value = sum_over_ranks(float(sum(its_box))) / t_e2e
+    gpu_launches_e2e = n_pipe
+    ctx2.close()
     d2h = out["poses"].nbytes + out["pts"].nbytes + out["inlier"].nbytes + 72 * len(probs)
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(batch_bytes), "d2h_bytes_per_step": int(d2h),
-           "ms_per_step": 1e3 * t_e2e / n_e2e, "steps": n_e2e}
+           "ms_per_step": 1e3 * t_e2e / n_pipe, "steps": n_pipe,
+           "how": "urmvo_local_ba_batch on host (pinned) buffers, two host threads / contexts alternating steps",
+           "single_call": {"value": seq_value, "ms_per_step": 1e3 * t_seq / n_e2e, "steps": n_e2e,
+                           "how": "one urmvo_local_ba_batch call at a time"}}
 
     # ---------------------------------------------------------------- parity spot check + CPU baseline (rank 0)
     cpu_baseline = None
