@@ -1,0 +1,44 @@
+"""Development: attribute the warp-stall samples of an ncu report (--import-source on) to source lines.
+Usage: ncu_lines.py <report.ncu-rep> <kernel mangled-name substring> [top]
+Needs the same build of liburmvo_b200.so that was profiled (line table comes from nvdisasm -g)."""
+import collections, csv, io, os, re, subprocess, sys, tempfile
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+rep, kname = sys.argv[1], sys.argv[2]
+top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
+tmp = tempfile.mkdtemp()
+subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "ur-mvo_b200/lib/liburmvo_b200.so")], cwd=tmp, capture_output=True)
+cubin = [f for f in os.listdir(tmp) if f.startswith("ba_kernels")][0]
+dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.split("\n")
+start = next(i for i, l in enumerate(dis) if l.startswith(".text.") and kname in l and l.rstrip().endswith(":"))
+seq, cur = [], None
+for l in dis[start + 1:]:
+    if l.startswith("//-----") : break
+    m = re.search(r'//## File "([^"]+)", line (\d+)', l)
+    if m: cur = int(m.group(2)); continue
+    m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", l)
+    if m: seq.append((int(m.group(1), 16), cur, m.group(2)))
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(out)))
+hdr, data = rows[1], rows[2:]
+ia, isamp, iex = hdr.index("Address"), hdr.index("# Samples"), hdr.index("Instructions Executed")
+stallcols = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
+assert len(data) == len(seq), (len(data), len(seq))
+byline, exline, bystall, tot = collections.Counter(), collections.Counter(), collections.defaultdict(collections.Counter), collections.Counter()
+for d, (off, ln, txt) in zip(data, seq):
+    ln = ln or -1
+    byline[ln] += int(d[isamp]); exline[ln] += int(d[iex])
+    for i in stallcols:
+        bystall[ln][hdr[i]] += int(d[i]); tot[hdr[i]] += int(d[i])
+n = sum(byline.values())
+src = open(os.path.join(ROOT, "ur-mvo_b200/csrc/ba_kernels.cu")).read().split("\n")
+print("samples", n, "warp-instructions %.3f G" % (sum(exline.values()) / 1e9))
+print(" ".join(f"{k[6:]}={v / sum(tot.values()) * 100:.1f}%" for k, v in tot.most_common(8)))
+for ln, c in byline.most_common(top):
+    t3 = ", ".join(f"{k[6:]}:{v}" for k, v in bystall[ln].most_common(3))
+    print(f"{ln:5d} {c / n * 100:5.1f}% ex={exline[ln]:9d} [{t3}] {src[ln - 1].strip()[:90] if ln > 0 else ''}")
+if len(sys.argv) > 4:  # dump the SASS of the given source lines with their samples
+    want = {int(x) for x in sys.argv[4].split(",")}
+    for k, (d, (off, ln, txt)) in enumerate(zip(data, seq)):
+        if ln in want and int(d[isamp]) > 50:
+            ctx = " | ".join(seq[j][2][:40] for j in range(max(0, k - 3), k))
+            print(f"{ln:5d} {off:6x} samples={d[isamp]:>6s} ex={d[iex]:>9s} {txt[:70]}    <- {ctx}")
