@@ -42,3 +42,9 @@ if len(sys.argv) > 4:  # dump the SASS of the given source lines with their samp
         if ln in want and int(d[isamp]) > 50:
             ctx = " | ".join(seq[j][2][:40] for j in range(max(0, k - 3), k))
             print(f"{ln:5d} {off:6x} samples={d[isamp]:>6s} ex={d[iex]:>9s} {txt[:70]}    <- {ctx}")
+if os.environ.get("REGIONS"):  # REGIONS="name:lo-hi,name:lo-hi": executed warp instructions / samples per line range
+    tot_ex = sum(exline.values())
+    for r in os.environ["REGIONS"].split(","):
+        name, rng = r.split(":"); lo, hi = (int(x) for x in rng.split("-"))
+        ex = sum(v for l, v in exline.items() if lo <= l <= hi); sm = sum(v for l, v in byline.items() if lo <= l <= hi)
+        print(f"{name:14s} lines {lo}-{hi}: instr {ex / tot_ex * 100:5.1f}%  samples {sm / n * 100:5.1f}%")

@@ -928,22 +928,76 @@ __device__ void backsub_phase(const Scope& sc, const BAWin& W, int cur, double l
 // point, the two observation slots of its camera pair.  No read-modify-write traffic, no atomics;
 // the register blocks are flushed once per phase and summed in warp order, then CTA order.
 
-constexpr int kPackSlots = 32;
+constexpr int kPackSlots = 33;     // 32 observation slots + one all-zero slot (index kPackZero)
+constexpr int kPackZero = 32;      // slot referenced by an absent (point, camera) entry: contributes exactly 0
 constexpr int kPackCam = 16;     // width of the (point-in-group, free camera) -> slot table
 constexpr int kPackFields = 38;  // Jp[12] | B[6] | A[6] | we[2] | w | h[6] | bl[3] | g[2]
 
 struct PackStage {
   double* f;          // kPackFields x 32
   signed char* slot;  // 32 x kPackCam
-  __device__ __forceinline__ double& Jp(int a, int s) { return f[a * 32 + s]; }
-  __device__ __forceinline__ double& B(int a, int s) { return f[(12 + a) * 32 + s]; }
-  __device__ __forceinline__ double& A(int a, int s) { return f[(18 + a) * 32 + s]; }
-  __device__ __forceinline__ double& we(int a, int s) { return f[(24 + a) * 32 + s]; }
-  __device__ __forceinline__ double& w(int s) { return f[26 * 32 + s]; }
-  __device__ __forceinline__ double& h(int a, int s) { return f[(27 + a) * 32 + s]; }
-  __device__ __forceinline__ double& bl(int a, int s) { return f[(33 + a) * 32 + s]; }
-  __device__ __forceinline__ double& g(int a, int s) { return f[(36 + a) * 32 + s]; }
+  __device__ __forceinline__ double& Jp(int a, int s) { return f[a * kPackSlots + s]; }
+  __device__ __forceinline__ double& B(int a, int s) { return f[(12 + a) * kPackSlots + s]; }
+  __device__ __forceinline__ double& A(int a, int s) { return f[(18 + a) * kPackSlots + s]; }
+  __device__ __forceinline__ double& we(int a, int s) { return f[(24 + a) * kPackSlots + s]; }
+  __device__ __forceinline__ double& w(int s) { return f[26 * kPackSlots + s]; }
+  __device__ __forceinline__ double& h(int a, int s) { return f[(27 + a) * kPackSlots + s]; }
+  __device__ __forceinline__ double& bl(int a, int s) { return f[(33 + a) * kPackSlots + s]; }
+  __device__ __forceinline__ double& g(int a, int s) { return f[(36 + a) * kPackSlots + s]; }
+  __device__ __forceinline__ double* recbuf() { return f + kPackFields * kPackSlots; }  // 32 x 32 bytes
 };
+
+// Packed-mode record access.  The record of the NEXT group is copied global -> shared with cp.async
+// (LDGSTS: no destination registers, so the compiler cannot consume it early) into the lane's 32-byte
+// cell of the warp's record buffer and read back at the top of the next iteration.
+struct RecRegs { int4 a, b; };
+__device__ __forceinline__ void rec_prefetch(double* buf, const ObsRec* rec, int g, int lane) {
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(buf) + lane * 32;
+  const size_t src = __cvta_generic_to_global(rec + (size_t)g * 32 + lane);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16), "l"(src + 16) : "memory");
+}
+__device__ __forceinline__ RecRegs rec_take(const double* buf, int lane) {
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  const int4* r = reinterpret_cast<const int4*>(buf) + lane * 2;
+  RecRegs x;
+  x.a = r[0];
+  x.b = r[1];
+  return x;
+}
+
+// Build the per-(group, lane) records from the CSR arrays and the current edge levels.
+template <class Scope>
+__device__ void pack_records(const Scope& sc, const BAWin& W) {
+  const int lane = threadIdx.x & 31;
+  const int wpc = blockDim.x >> 5;
+  const int gw = sc.blk() * wpc + (threadIdx.x >> 5);
+  const int gstride = sc.nblk() * wpc;
+  for (int g = gw; g < W.n_grp; g += gstride) {
+    const int p0 = W.grp_pt[g];
+    const int np = W.grp_pt[g + 1] - p0;
+    const int o0 = W.pt_start[p0];
+    const int nobs = W.pt_start[p0 + np] - o0;
+    ObsRec r;
+    r.u = 0.0; r.v = 0.0; r.pl = p0; r.c = 0; r.s0 = 0; r.s1 = 0; r.pi = 0; r.cf = -1;
+    r.np = (unsigned char)np; r.lev = 1; r.valid = 0; r.pad = 0;
+    if (lane < nobs) {
+      const int o = o0 + lane;
+      const int pl = W.opt[o];
+      r.u = W.uv[(size_t)o * 2];
+      r.v = W.uv[(size_t)o * 2 + 1];
+      r.pl = pl;
+      r.c = W.ocam[o];
+      r.s0 = (unsigned char)(W.pt_start[pl] - o0);
+      r.s1 = (unsigned char)(W.pt_start[pl + 1] - o0);
+      r.pi = (unsigned char)(pl - p0);
+      r.cf = (signed char)W.cam_free[r.c];
+      r.lev = W.level[o];
+      r.valid = 1;
+    }
+    W.rec[(size_t)g * 32 + lane] = r;
+  }
+}
 
 template <bool DIAG, int NB, class Scope>
 __device__ void lin_phase_packed(const Scope& sc, const BAWin& W, int cur, double lambda, bool robust,
@@ -957,13 +1011,7 @@ __device__ void lin_phase_packed(const Scope& sc, const BAWin& W, int cur, doubl
   const double* __restrict__ pts = W.pts[cur];
   const double K[4] = {W.intr[0], W.intr[1], W.intr[2], W.intr[3]};
   // the descriptor lives in global memory: take its fields into registers once
-  const int* __restrict__ grp_pt = W.grp_pt;
-  const int* __restrict__ pt_start = W.pt_start;
-  const int* __restrict__ opt = W.opt;
-  const int* __restrict__ ocam = W.ocam;
-  const int* __restrict__ cam_free = W.cam_free;
-  const uint8_t* __restrict__ level = W.level;
-  const double2* __restrict__ uvp = reinterpret_cast<const double2*>(W.uv);
+  const ObsRec* rec = W.rec;
   double* __restrict__ Dinv_out = W.Dinv;
   double* __restrict__ bl_out = W.bl;
   const int Ncf = W.Ncf, n_grp = W.n_grp, nblk = W.nblk;
@@ -988,41 +1036,38 @@ __device__ void lin_phase_packed(const Scope& sc, const BAWin& W, int cur, doubl
   double accb[12];  // b_s | b_p of camera `lane` (DIAG: diag(Hpp) in the first 6)
 #pragma unroll
   for (int e = 0; e < 12; e++) accb[e] = 0.0;
+  // absent (point, camera) entries of the slot table point at the all-zero slot, so the pair loop
+  // below runs without divergent branches: an absent pair adds exactly +0 to the accumulators
+  for (int a = lane; a < kPackFields; a += 32) st.f[a * kPackSlots + kPackZero] = 0.0;
+  int bsi[NB], bsj[NB];  // table columns of the lane's block(s); lanes without a block read column 0
+  bool has[NB];
+#pragma unroll
+  for (int nb = 0; nb < NB; nb++) {
+    has[nb] = bci[nb] >= 0;
+    bsi[nb] = has[nb] ? bci[nb] : 0;
+    bsj[nb] = has[nb] ? bcj[nb] : 0;
+  }
+  const int bcol = lane & (kPackCam - 1);  // camera column of the b_s / b_p accumulation (lanes < 16)
 
-  // software pipeline: the header and the per-lane observation record of the NEXT group are
-  // fetched while the current group is processed, so the L2 round trips overlap the arithmetic
-  int n_p0 = 0, n_np = 0, n_o0 = 0, n_nobs = 0, n_pl = 0, n_c = 0, n_lev = 1;
-  double2 n_uv = make_double2(0.0, 0.0);
-  auto fetch = [&](int g) {
-    n_p0 = grp_pt[g];
-    n_np = grp_pt[g + 1] - n_p0;
-    n_o0 = pt_start[n_p0];
-    n_nobs = pt_start[n_p0 + n_np] - n_o0;
-    n_pl = n_p0; n_c = 0; n_lev = 1;
-    if (lane < n_nobs) {
-      const int o = n_o0 + lane;
-      n_pl = opt[o];
-      n_lev = level[o];
-      n_c = ocam[o];
-      n_uv = uvp[o];
-    }
-  };
-  if (gw < n_grp) fetch(gw);
+  // software pipeline: the record of the NEXT group is fetched (one level of loads) while the
+  // current group is processed, so the L2 round trip overlaps the arithmetic
+  double* const rbuf = st.recbuf();
+  if (gw < n_grp) rec_prefetch(rbuf, rec, gw, lane);
   for (int g = gw; g < n_grp; g += gstride) {
-    const int p0 = n_p0, np = n_np, o0 = n_o0, nobs = n_nobs;
-    const int pl = n_pl, c = n_c, lev = n_lev;
-    const double2 uv = n_uv;
-    reinterpret_cast<int*>(st.slot)[lane] = -1;       // 32 * 16 bytes = 128 ints of 0xFF
-    reinterpret_cast<int*>(st.slot)[lane + 32] = -1;
-    reinterpret_cast<int*>(st.slot)[lane + 64] = -1;
-    reinterpret_cast<int*>(st.slot)[lane + 96] = -1;
+    const RecRegs rr = rec_take(rbuf, lane);
+    const double2 uv = make_double2(__hiloint2double(rr.a.y, rr.a.x), __hiloint2double(rr.a.w, rr.a.z));
+    const int pl = rr.b.x, c = rr.b.y;
+    const int s0 = rr.b.z & 255, s1 = (rr.b.z >> 8) & 255, pi = (rr.b.z >> 16) & 255;
+    const int cf_ld = rr.b.z >> 24;  // arithmetic shift keeps the sign of the int8
+    const int np = rr.b.w & 255, lev = (rr.b.w >> 8) & 255;
+    const bool valid = (rr.b.w >> 16) & 1;
+    reinterpret_cast<int*>(st.slot)[lane] = 0x20202020;  // 32 * 16 bytes, every entry = kPackZero
+    reinterpret_cast<int*>(st.slot)[lane + 32] = 0x20202020;
+    reinterpret_cast<int*>(st.slot)[lane + 64] = 0x20202020;
+    reinterpret_cast<int*>(st.slot)[lane + 96] = 0x20202020;
     __syncwarp();
-    const bool valid = lane < nobs;
-    const int pi = pl - p0;
-    const int s0 = pt_start[pl] - o0, s1 = pt_start[pl + 1] - o0;
     const double X[3] = {pts[pl * 3], pts[pl * 3 + 1], pts[pl * 3 + 2]};
-    const int cf_ld = cam_free[c];
-    if (g + gstride < n_grp) fetch(g + gstride);
+    if (g + gstride < n_grp) rec_prefetch(rbuf, rec, g + gstride, lane);
     double hc[6] = {0, 0, 0, 0, 0, 0}, blc[3] = {0, 0, 0};
     int cf = -1;
     double B[6];
@@ -1068,9 +1113,13 @@ __device__ void lin_phase_packed(const Scope& sc, const BAWin& W, int cur, doubl
     }
     __syncwarp();
     // per-point sums in observation order (every lane for its own point)
+    // (uniform trip count: lanes past the end of their range add the all-zero slot)
     double h[6] = {0, 0, 0, 0, 0, 0}, bl[3] = {0, 0, 0};
-    if (valid) {
-      for (int s = s0; s < s1; s++) {
+    {
+      const int len = valid ? s1 - s0 : 0;
+      const int maxlen = __reduce_max_sync(0xffffffffu, len);
+      for (int t = 0; t < maxlen; t++) {
+        const int s = t < len ? s0 + t : kPackZero;
 #pragma unroll
         for (int a = 0; a < 6; a++) h[a] += st.h(a, s);
         if (!DIAG) {
@@ -1082,16 +1131,13 @@ __device__ void lin_phase_packed(const Scope& sc, const BAWin& W, int cur, doubl
     if (DIAG) {
       if (valid) maxdiag_acc = fmax(maxdiag_acc, fmax(fabs(h[0]), fmax(fabs(h[3]), fabs(h[5]))));
       __syncwarp();
-      if (lane < Ncf) {
-        for (int q = 0; q < np; q++) {
-          const int s = st.slot[q * kPackCam + lane];
-          if (s < 0) continue;
-          const double w = st.w(s);
+      for (int q = 0; q < np; q++) {
+        const int s = lane < kPackCam ? st.slot[q * kPackCam + bcol] : kPackZero;
+        const double w = st.w(s);
 #pragma unroll
-          for (int a = 0; a < 6; a++) {
-            const double j0 = st.Jp(a, s), j1 = st.Jp(6 + a, s);
-            accb[a] += w * (j0 * j0 + j1 * j1);
-          }
+        for (int a = 0; a < 6; a++) {
+          const double j0 = st.Jp(a, s), j1 = st.Jp(6 + a, s);
+          accb[a] += w * (j0 * j0 + j1 * j1);
         }
       }
       __syncwarp();
@@ -1123,25 +1169,41 @@ __device__ void lin_phase_packed(const Scope& sc, const BAWin& W, int cur, doubl
       }
     }
     __syncwarp();
-    // S-stationary accumulation: for every point of the group, the lane's camera pair(s)
+    // S-stationary accumulation: for every point of the group, the lane's camera pair(s).  The slot
+    // bytes of point q+1 are fetched while point q is processed.
+    int nsi[NB], nsj[NB], nsb;
+    {
+      const signed char* sl = st.slot;
+#pragma unroll
+      for (int nb = 0; nb < NB; nb++) { nsi[nb] = sl[bsi[nb]]; nsj[nb] = sl[bsj[nb]]; }
+      nsb = sl[bcol];
+    }
     for (int q = 0; q < np; q++) {
-      const signed char* sl = st.slot + q * kPackCam;
+      int csi[NB], csj[NB];
+#pragma unroll
+      for (int nb = 0; nb < NB; nb++) { csi[nb] = nsi[nb]; csj[nb] = nsj[nb]; }
+      const int csb = nsb;
+      {
+        const signed char* sl = st.slot + (q + 1 < 32 ? q + 1 : 31) * kPackCam;
+#pragma unroll
+        for (int nb = 0; nb < NB; nb++) { nsi[nb] = sl[bsi[nb]]; nsj[nb] = sl[bsj[nb]]; }
+        nsb = sl[bcol];
+      }
 #pragma unroll
       for (int nb = 0; nb < NB; nb++) {
-        if (bci[nb] < 0) continue;
-        const int si = sl[bci[nb]], sj = sl[bcj[nb]];
-        if (si < 0 || sj < 0) continue;
+        const bool ok = has[nb] && !((csi[nb] | csj[nb]) & kPackZero);
+        const int si = ok ? csi[nb] : kPackZero, sj = ok ? csj[nb] : kPackZero;
         double M[4];
         {
           const double a0 = st.A(0, si), a1 = st.A(1, si), a2 = st.A(2, si);
           const double a3 = st.A(3, si), a4 = st.A(4, si), a5 = st.A(5, si);
           const double b0 = st.B(0, sj), b1 = st.B(1, sj), b2 = st.B(2, sj);
           const double b3 = st.B(3, sj), b4 = st.B(4, sj), b5 = st.B(5, sj);
-          M[0] = -(a0 * b0 + a1 * b1 + a2 * b2);
+          const double wd = si == sj ? st.w(si) : 0.0;
+          M[0] = wd - (a0 * b0 + a1 * b1 + a2 * b2);
           M[1] = -(a0 * b3 + a1 * b4 + a2 * b5);
           M[2] = -(a3 * b0 + a4 * b1 + a5 * b2);
-          M[3] = -(a3 * b3 + a4 * b4 + a5 * b5);
-          if (si == sj) { const double w = st.w(si); M[0] += w; M[3] += w; }
+          M[3] = wd - (a3 * b3 + a4 * b4 + a5 * b5);
         }
         double T[12];
 #pragma unroll
@@ -1158,16 +1220,14 @@ __device__ void lin_phase_packed(const Scope& sc, const BAWin& W, int cur, doubl
             accS[nb][a * 6 + b] = fma(j1, T[6 + b], fma(j0, T[b], accS[nb][a * 6 + b]));
         }
       }
-      if (lane < Ncf) {
-        const int s = sl[lane];
-        if (s >= 0) {
-          const double g0 = st.g(0, s), g1 = st.g(1, s), w0 = st.we(0, s), w1 = st.we(1, s);
+      {
+        const int s = lane < kPackCam ? csb : kPackZero;
+        const double g0 = st.g(0, s), g1 = st.g(1, s), w0 = st.we(0, s), w1 = st.we(1, s);
 #pragma unroll
-          for (int a = 0; a < 6; a++) {
-            const double j0 = st.Jp(a, s), j1 = st.Jp(6 + a, s);
-            accb[a] = fma(-j1, g1, fma(-j0, g0, accb[a]));
-            accb[6 + a] = fma(-j1, w1, fma(-j0, w0, accb[6 + a]));
-          }
+        for (int a = 0; a < 6; a++) {
+          const double j0 = st.Jp(a, s), j1 = st.Jp(6 + a, s);
+          accb[a] = fma(-j1, g1, fma(-j0, g0, accb[a]));
+          accb[6 + a] = fma(-j1, w1, fma(-j0, w0, accb[6 + a]));
         }
       }
     }
@@ -1213,52 +1273,31 @@ __device__ void backsub_phase_packed(const Scope& sc, const BAWin& W, int cur, d
   const double* __restrict__ camRt = W.camRt[cur];
   const double* __restrict__ camRtT = W.camRt[tr];
   const double K[4] = {W.intr[0], W.intr[1], W.intr[2], W.intr[3]};
-  const int* __restrict__ grp_pt = W.grp_pt;
-  const int* __restrict__ pt_start = W.pt_start;
-  const int* __restrict__ opt = W.opt;
-  const int* __restrict__ ocam = W.ocam;
-  const int* __restrict__ cam_free = W.cam_free;
-  const uint8_t* __restrict__ level = W.level;
-  const double2* __restrict__ uvp = reinterpret_cast<const double2*>(W.uv);
+  const ObsRec* rec = W.rec;
   const double* __restrict__ pts_cur = W.pts[cur];
   double* __restrict__ pts_tr = W.pts[tr];
   const double* __restrict__ Dinv_in = W.Dinv;
   const double* __restrict__ bl_in = W.bl;
   const double* __restrict__ xp = W.xp;
   const int n_grp = W.n_grp;
-  int n_p0 = 0, n_np = 0, n_o0 = 0, n_nobs = 0, n_pl = 0, n_c = 0, n_lev = 1;
-  double2 n_uv = make_double2(0.0, 0.0);
-  auto fetch = [&](int g) {
-    n_p0 = grp_pt[g];
-    n_np = grp_pt[g + 1] - n_p0;
-    n_o0 = pt_start[n_p0];
-    n_nobs = pt_start[n_p0 + n_np] - n_o0;
-    n_pl = n_p0; n_c = 0; n_lev = 1;
-    if (lane < n_nobs) {
-      const int o = n_o0 + lane;
-      n_pl = opt[o];
-      n_lev = level[o];
-      n_c = ocam[o];
-      n_uv = uvp[o];
-    }
-  };
-  if (gw < n_grp) fetch(gw);
+  double* const rbuf = st.recbuf();
+  if (lane < 3) st.h(lane, kPackZero) = 0.0;  // all-zero slot for the uniform per-point sums
+  if (gw < n_grp) rec_prefetch(rbuf, rec, gw, lane);
   for (int g = gw; g < n_grp; g += gstride) {
-    const int o0 = n_o0, nobs = n_nobs;
-    const bool valid = lane < nobs;
-    const int pl = n_pl;
-    const int c = n_c;
-    const double2 uv = n_uv;
-    const bool active = valid && !n_lev;
-    const int s0 = pt_start[pl] - o0, s1 = pt_start[pl + 1] - o0;
+    const RecRegs rr = rec_take(rbuf, lane);
+    const double2 uv = make_double2(__hiloint2double(rr.a.y, rr.a.x), __hiloint2double(rr.a.w, rr.a.z));
+    const int pl = rr.b.x, c = rr.b.y;
+    const int s0 = rr.b.z & 255, s1 = (rr.b.z >> 8) & 255;
+    const int cf_ld = rr.b.z >> 24;
+    const bool valid = (rr.b.w >> 16) & 1;
+    const bool active = valid && !((rr.b.w >> 8) & 255);
     const double X[3] = {pts_cur[pl * 3], pts_cur[pl * 3 + 1], pts_cur[pl * 3 + 2]};
-    const int cf_ld = cam_free[c];
     double Di[6], bb[3];
 #pragma unroll
     for (int a = 0; a < 6; a++) Di[a] = Dinv_in[(size_t)pl * 6 + a];
 #pragma unroll
     for (int a = 0; a < 3; a++) bb[a] = bl_in[(size_t)pl * 3 + a];
-    if (g + gstride < n_grp) fetch(g + gstride);
+    if (g + gstride < n_grp) rec_prefetch(rbuf, rec, g + gstride, lane);
     double c3[3] = {0, 0, 0};
     if (active) {
       const int cf = cf_ld;
@@ -1287,12 +1326,17 @@ __device__ void backsub_phase_packed(const Scope& sc, const BAWin& W, int cur, d
     for (int a = 0; a < 3; a++) st.h(a, lane) = c3[a];
     __syncwarp();
     double Xn[3] = {X[0], X[1], X[2]};
-    if (valid) {
-      double cs[3] = {0, 0, 0};
-      for (int s = s0; s < s1; s++) {
+    double cs[3] = {0, 0, 0};
+    {
+      const int len = valid ? s1 - s0 : 0;
+      const int maxlen = __reduce_max_sync(0xffffffffu, len);
+      for (int t = 0; t < maxlen; t++) {
+        const int s = t < len ? s0 + t : kPackZero;
 #pragma unroll
         for (int a = 0; a < 3; a++) cs[a] += st.h(a, s);
       }
+    }
+    if (valid) {
       const double b0 = bb[0], b1 = bb[1], b2 = bb[2];
       const double r0 = b0 - cs[0], r1 = b1 - cs[1], r2 = b2 - cs[2];
       const double x0 = Di[0] * r0 + Di[1] * r1 + Di[2] * r2;
@@ -1599,6 +1643,7 @@ template <int MODE, class Scope>
 __device__ void solve_window(const Scope& sc, const BAWin& W, const BARun& run, WarpStage st,
                              PackStage pst, WorkArea wa, double* pcg_sm, double* red) {
   window_init(sc, W);
+  if (MODE >= 2) { pack_records(sc, W); sc.sync(); }
   int cur = 0, last_eval = 0, parity = 0;
   bool have_eval = false;  // has any computeActiveErrors() run? (g2o's cached _error is zero before)
   urmvo_ba_stats* stats = reinterpret_cast<urmvo_ba_stats*>(W.stats);
@@ -1624,6 +1669,7 @@ __device__ void solve_window(const Scope& sc, const BAWin& W, const BARun& run, 
       if (writer && stats) stats->n_level1 = (int)s1[0];
     }
     sc.sync();
+    if (MODE >= 2 && pass == 0) { pack_records(sc, W); sc.sync(); }  // new edge levels
   }
   window_finish(sc, W, cur);
 }
@@ -1711,7 +1757,7 @@ int ba_stage_doubles(int kmax) { return kStageFields * kmax; }
 int ba_tile_doubles() { return 32 * 37; }
 // grid kernels: at least 23 KB per warp so that a ~60-neighbour block row fits the PCG cache
 static __host__ __device__ int grid_work_stride(int kmax) { const int n = kStageFields * kmax + 32 * 37; return n > 2944 ? n : 2944; }
-int ba_pack_doubles() { return kPackFields * kPackSlots; }
+int ba_pack_doubles() { return kPackFields * kPackSlots + 128; }
 
 // ------------------------------------------------------------------------------- point-sharded BA
 //

@@ -4,6 +4,23 @@
 
 namespace urmvo {
 
+// Packed modes: one 32-byte record per (group, lane), rebuilt on the device by pack_records() at the
+// start of a solve and after the outlier classification.  A lane reads everything that does not
+// change inside an LM pass with two 16-byte loads, one group ahead of its use (the CSR arrays would
+// need three dependent levels of loads).
+struct alignas(16) ObsRec {
+  double u, v;
+  int pl;                  // point index (first point of the group for an idle lane)
+  int c;                   // camera index
+  unsigned char s0, s1;    // the point's observation range, relative to the group's first observation
+  unsigned char pi;        // point index inside the group
+  signed char cf;          // dense free-camera index or -1
+  unsigned char np;        // points in the group (same in all lanes)
+  unsigned char lev;       // g2o edge level (1 for an idle lane)
+  unsigned char valid;     // lane carries an observation
+  unsigned char pad;
+};
+
 // One BA window (one LocalmapOptimization call), all pointers are device pointers.
 // HBM layout: SoA, fp64; observations sorted point-major so that one point's
 // observations are contiguous; cameras as 7-double (q,t) T_cw state + a derived 12-double (R|t).
@@ -36,6 +53,7 @@ struct BAWin {
   double* camRt[2];        // Nc*12  R (row-major 9) | t (3) derived from cam[]
   double* pts[2];          // Np*3
   uint8_t* level;          // No     0 active, 1 excluded (g2o edge level)
+  ObsRec* rec;             // n_grp*32 packed-mode observation records (device-built)
   // ---- linear system
   double* S;               // nblk*36 row-major blocks
   double* bs;              // Ncf*6  Schur right-hand side

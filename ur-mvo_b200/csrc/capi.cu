@@ -494,6 +494,9 @@ static int ba_plan_create_impl(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, const
   size_t o_cam[2], o_camRt[2], o_pts[2];
   for (int k = 0; k < 2; k++) { o_cam[k] = A.take<double>(TC * 7); o_camRt[k] = A.take<double>(TC * 12); o_pts[k] = A.take<double>(TP * 3); }
   const size_t o_level = A.take<uint8_t>(TO);
+  size_t sum_rec = 0;
+  for (auto& w : wh) if (w.acc_mode >= 2) sum_rec += (w.grp_pt.size() - 1) * 32;
+  const size_t o_rec = A.take<ObsRec>(sum_rec);
   const size_t o_scal = A.take<double>(32);  // sharded: head of the contiguous all-reduce buffer
   const size_t o_S = A.take<double>((size_t)sum_blk * 36);
   const size_t o_vec = A.take<double>((size_t)(sum_ncf + B) * 6 * 8);  // bs bp hdiag xp r z p Ap (indexed by c_ncf, which counts Ncf+1 per window)
@@ -543,7 +546,7 @@ static int ba_plan_create_impl(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, const
   }
   unsigned char* H = (unsigned char*)ctx->pinned;  // mirrors [o_pt_start, upload_end)
   auto hp = [&](size_t off) { return H + (off - o_pt_start); };
-  size_t c_pt = 0, c_ncf = 0, c_blk = 0, c_grp = 0;
+  size_t c_pt = 0, c_ncf = 0, c_blk = 0, c_grp = 0, c_rec = 0;
   BAWin* hw = (BAWin*)hp(p->off_wins);
   for (int w = 0; w < B; w++) {
     const WinHost& W = wh[w];
@@ -585,6 +588,8 @@ static int ba_plan_create_impl(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, const
       d.pts[k] = (double*)(D + o_pts[k]) + p0 * 3;
     }
     d.level = D + o_level + ob0;
+    d.rec = (ObsRec*)(D + o_rec) + c_rec;
+    if (W.acc_mode >= 2) c_rec += (W.grp_pt.size() - 1) * 32;
     d.S = (double*)(D + o_S) + c_blk * 36;
     double* vec = (double*)(D + o_vec) + c_ncf * 6 * 8;
     const size_t n6 = (size_t)W.Ncf * 6;
