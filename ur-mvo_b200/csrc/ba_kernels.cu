@@ -1282,6 +1282,10 @@ __device__ void backsub_phase_packed(const Scope& sc, const BAWin& W, int cur, d
   const int n_grp = W.n_grp;
   double* const rbuf = st.recbuf();
   if (lane < 3) st.h(lane, kPackZero) = 0.0;  // all-zero slot for the uniform per-point sums
+  // the pose increments (<= 16 free cameras x 6) into the warp's staging area (the Jp fields are free here)
+  double* const xs = st.f;
+  for (int e = lane; e < W.Ncf * 6; e += 32) xs[e] = __ldcg(xp + e);
+  __syncwarp();
   if (gw < n_grp) rec_prefetch(rbuf, rec, gw, lane);
   for (int g = gw; g < n_grp; g += gstride) {
     const RecRegs rr = rec_take(rbuf, lane);
@@ -1312,7 +1316,7 @@ __device__ void backsub_phase_packed(const Scope& sc, const BAWin& W, int cur, d
         double t0 = 0, t1 = 0;
 #pragma unroll
         for (int a = 0; a < 6; a++) {
-          const double xa = __ldcg(xp + cf * 6 + a);
+          const double xa = xs[cf * 6 + a];
           t0 += Jp[a] * xa;
           t1 += Jp[6 + a] * xa;
         }
