@@ -39,7 +39,8 @@ class TVStats(C.Structure):
 
 
 def lib_path():
-    return os.path.join(_PKG_ROOT, "lib", "liburmvo_b200.so")
+    # URMVO_B200_LIB: development override for A/B runs of two builds of the same library
+    return os.environ.get("URMVO_B200_LIB") or os.path.join(_PKG_ROOT, "lib", "liburmvo_b200.so")
 
 
 def build_library():
