@@ -29,6 +29,7 @@ typedef struct urmvo_ctx urmvo_ctx;
 typedef struct urmvo_ba_plan urmvo_ba_plan;       /* device-resident batch of BA windows */
 typedef struct urmvo_pose_plan urmvo_pose_plan;   /* device-resident batch of pose-only frames */
 typedef struct urmvo_tv_plan urmvo_tv_plan;       /* device-resident two-view problem */
+typedef struct urmvo_fm_plan urmvo_fm_plan;       /* device-resident batch of fundamental-matrix RANSAC problems */
 
 typedef enum {
   URMVO_OK = 0,
@@ -181,6 +182,40 @@ int urmvo_tv_plan_download_hyps(urmvo_tv_plan* plan, int model, float* scores, u
 int urmvo_tv_plan_reconstruct(urmvo_tv_plan* plan, float* T21, float* P3D, uint8_t* triangulated,
                               uint8_t* mask_H, uint8_t* mask_F, urmvo_tv_stats* stats, int* success);
 void urmvo_tv_plan_destroy(urmvo_tv_plan* plan);
+
+/* ---- per-frame outlier rejection of the matcher -----------------------
+ * Replaces the OpenCV call of reference src/point_matching.cc:53
+ *     cv::findFundamentalMat(points0, points1, cv::FM_RANSAC, 3, 0.99, inliers);
+ * (default maxIters 1000) for N >= 15 correspondences: same cv::RNG subset sequence, same 7-point
+ * models, same error and threshold rule, same "strictly more inliers wins, then shrink the
+ * iteration budget" replay, hence the same inlier flags as OpenCV.  Below 15 points OpenCV takes
+ * its direct 7-point / LMedS branches; those stay with the reference's own call,
+ * and this entry point returns URMVO_ERR_UNSUPPORTED. */
+typedef struct {
+  int32_t found;      /* 1: a model with >= 7 inliers exists (cv: non-empty F) */
+  int32_t iters;      /* RANSAC iterations the sequential loop would have run */
+  int32_t n_inliers;
+  int32_t n_models;   /* 7-point models produced by the evaluated iterations */
+  double F[9];        /* row-major, F33 = 1 (p1^T F p0 = 0) */
+} urmvo_fm_stats;
+
+/* B independent frame pairs in one call.  off: B+1 prefix offsets into pts0/pts1 (N_b*2 floats each,
+ * pixel coordinates of the matched keypoints in image 0 / image 1).  inlier: sum(N_b) bytes out. */
+int urmvo_fm_ransac_batch(urmvo_ctx* ctx, int B, const int32_t* off, const float* pts0, const float* pts1,
+                          double thresh, double confidence, int max_iters, uint8_t* inlier,
+                          urmvo_fm_stats* stats);
+/* One frame pair (the call shape of point_matching.cc:53). */
+int urmvo_fm_ransac(urmvo_ctx* ctx, int N, const float* pts0, const float* pts1, double thresh,
+                    double confidence, int max_iters, uint8_t* inlier, urmvo_fm_stats* stats);
+/* Device-resident form: create uploads the correspondences and the host-drawn subsets, run launches
+ * the solve + score kernels (asynchronous, repeatable), finish reads the inlier counts back, replays
+ * OpenCV's sequential selection on the host and launches the mask kernel. */
+int urmvo_fm_plan_create(urmvo_ctx* ctx, urmvo_fm_plan** plan, int B, const int32_t* off, const float* pts0,
+                         const float* pts1, double thresh, double confidence, int max_iters);
+int urmvo_fm_plan_run(urmvo_fm_plan* plan);
+int urmvo_fm_plan_finish(urmvo_fm_plan* plan, uint8_t* inlier, urmvo_fm_stats* stats);
+int urmvo_fm_plan_hypotheses(const urmvo_fm_plan* plan); /* (iteration, problem) pairs evaluated per run */
+void urmvo_fm_plan_destroy(urmvo_fm_plan* plan);
 
 #ifdef __cplusplus
 }

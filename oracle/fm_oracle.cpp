@@ -1,0 +1,366 @@
+// oracle/fm_oracle.cpp — CPU restatement of the per-frame outlier rejection of
+// PointMatching::MatchingPoints (reference src/point_matching.cc:44-58):
+//     cv::findFundamentalMat(points0, points1, cv::FM_RANSAC, 3, 0.99, inliers);
+//
+// TEST INFRASTRUCTURE ONLY (see oracle.h).
+//
+// PARITY PINNED: the algorithm lives in OpenCV (calib3d: fundam.cpp / ptsetreg.cpp), which the
+// reference links but does not vendor.  The Python build of the same library (cv2 4.13) is importable
+// in the build container, so tests/golden/make_golden_fm.py runs the REAL cv2.findFundamentalMat on
+// seeded inputs and commits inputs + inlier masks + F as tests/golden/golden_fm_r01.npz;
+// tests/test_golden_fm.py requires this restatement to reproduce every mask bit-for-bit.
+//
+// Restated pieces (OpenCV 4.x):
+//   cv::RNG (multiply-with-carry, state 0xffffffffffffffff, uniform(a,b) = a + next() % (b-a))
+//   RANSACPointSetRegistrator::run / getSubset (7 distinct indices, <= 10000 attempts, checkSubset)
+//   FMEstimatorCallback::checkSubset -> haveCollinearPoints (last point against all earlier pairs)
+//   run7Point (isotropic normalisation, 2-D null space of the 7x9 system, cubic det = 0, <= 3 models,
+//              de-normalisation, F33 = 1)
+//   cv::solveCubic
+//   FMEstimatorCallback::computeError (max of the two squared point-line distances, float result)
+//   findInliers (err <= (float)(thr*thr)), best = strictly more inliers, RANSACUpdateNumIters
+// Only the N >= 15 branch (FM_RANSAC) is restated: below 15 points OpenCV switches to LMedS, which
+// stays with the reference's own call.
+// The null space comes from a one-sided Jacobi SVD (fp64, cyclic pairs, own stopping rule) instead
+// of LAPACK: any basis of the null space gives the same <= 3 fundamental matrices.
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+
+#include "oracle.h"
+
+namespace {
+
+struct CvRng {
+  uint64_t state = 0xffffffffffffffffull;
+  unsigned next() {
+    state = (uint64_t)(unsigned)state * 4164903690u + (unsigned)(state >> 32);
+    return (unsigned)state;
+  }
+  int uniform(int a, int b) { return a + (int)(next() % (unsigned)(b - a)); }
+};
+
+bool have_collinear(const float* m, const int* idx, int count) {
+  const int i = count - 1;
+  const float* pi = m + 2 * idx[i];
+  for (int j = 0; j < i; j++) {
+    const double dx1 = m[2 * idx[j]] - pi[0], dy1 = m[2 * idx[j] + 1] - pi[1];
+    for (int k = 0; k < j; k++) {
+      const double dx2 = m[2 * idx[k]] - pi[0], dy2 = m[2 * idx[k] + 1] - pi[1];
+      if (std::fabs(dx2 * dy1 - dy2 * dx1) <=
+          FLT_EPSILON * (std::fabs(dx1) + std::fabs(dy1) + std::fabs(dx2) + std::fabs(dy2)))
+        return true;
+    }
+  }
+  return false;
+}
+
+bool get_subset(const float* m1, const float* m2, int count, CvRng& rng, int max_attempts, int* idx) {
+  for (int it = 0; it < max_attempts; it++) {
+    for (int i = 0; i < 7; i++) {
+      int v = rng.uniform(0, count);
+      while (std::find(idx, idx + i, v) != idx + i) v = rng.uniform(0, count);
+      idx[i] = v;
+    }
+    if (!have_collinear(m1, idx, 7) && !have_collinear(m2, idx, 7)) return true;
+  }
+  return false;
+}
+
+// cv::solveCubic: c[0] x^3 + c[1] x^2 + c[2] x + c[3] = 0.  Returns the number of roots (-1: all x).
+int solve_cubic(const double* c, double* r) {
+  double a0 = c[0], a1 = c[1], a2 = c[2], a3 = c[3];
+  int n = 0;
+  double x0 = 0, x1 = 0, x2 = 0;
+  if (a0 == 0) {
+    if (a1 == 0) {
+      if (a2 == 0) {
+        n = a3 == 0 ? -1 : 0;
+      } else {
+        x0 = -a3 / a2;
+        n = 1;
+      }
+    } else {
+      double d = a2 * a2 - 4 * a1 * a3;
+      if (d >= 0) {
+        d = std::sqrt(d);
+        const double q1 = (-a2 + d) * 0.5, q2 = (a2 + d) * -0.5;
+        if (std::fabs(q1) > std::fabs(q2)) {
+          x0 = q1 / a1;
+          x1 = a3 / q1;
+        } else {
+          x0 = q2 / a1;
+          x1 = a3 / q2;
+        }
+        n = d > 0 ? 2 : 1;
+      }
+    }
+  } else {
+    a0 = 1. / a0;
+    a1 *= a0; a2 *= a0; a3 *= a0;
+    const double Q = (a1 * a1 - 3 * a2) * (1. / 9);
+    const double R = (2 * a1 * a1 * a1 - 9 * a1 * a2 + 27 * a3) * (1. / 54);
+    const double Qcubed = Q * Q * Q;
+    double d = Qcubed - R * R;
+    if (d > 0) {
+      const double theta = std::acos(R / std::sqrt(Qcubed));
+      const double sqrtQ = std::sqrt(Q);
+      const double t0 = -2 * sqrtQ, t1 = theta * (1. / 3), t2 = a1 * (1. / 3);
+      x0 = t0 * std::cos(t1) - t2;
+      x1 = t0 * std::cos(t1 + (2. * M_PI / 3)) - t2;
+      x2 = t0 * std::cos(t1 + (4. * M_PI / 3)) - t2;
+      n = 3;
+    } else if (d == 0) {
+      if (R >= 0) {
+        x0 = -2 * std::pow(R, 1. / 3) - a1 / 3;
+        x1 = std::pow(R, 1. / 3) - a1 / 3;
+      } else {
+        x0 = 2 * std::pow(-R, 1. / 3) - a1 / 3;
+        x1 = -std::pow(-R, 1. / 3) - a1 / 3;
+      }
+      x2 = 0;
+      n = x0 == x1 ? 1 : 2;
+      x1 = x0 == x1 ? 0 : x1;
+    } else {
+      double e;
+      d = std::sqrt(-d);
+      e = std::pow(d + std::fabs(R), 1. / 3);
+      if (R > 0) e = -e;
+      x0 = (e + Q / e) - a1 * (1. / 3);
+      n = 1;
+    }
+  }
+  r[0] = x0; r[1] = x1; r[2] = x2;
+  return n;
+}
+
+// One-sided Jacobi on the 7x9 system: V (9x9) accumulates the column rotations; on exit the two
+// columns of A with the smallest norms are (numerically) zero and the same columns of V span the
+// null space.  Spec shared with the CUDA kernel (csrc/fm_kernels.cu): cyclic (p,q) order, rotate
+// when |gamma| > 1e-15 sqrt(alpha beta), columns with squared norm <= 1e-30 ||A||_F^2 are left
+// alone, at most 60 sweeps.  f1 = the null column with the larger index, f2 = the smaller.
+void null_space_7x9(double* A, double* f1, double* f2) {
+  double V[81];
+  for (int i = 0; i < 81; i++) V[i] = (i / 9 == i % 9) ? 1.0 : 0.0;
+  double fro2 = 0.0;
+  for (int r = 0; r < 7; r++) {
+    double row = 0.0;
+    for (int j = 0; j < 9; j++) row += A[r * 9 + j] * A[r * 9 + j];
+    fro2 += row;
+  }
+  const double tiny = 1e-30 * fro2;
+  for (int sweep = 0; sweep < 60; sweep++) {
+    bool rotated = false;
+    for (int p = 0; p < 8; p++)
+      for (int q = p + 1; q < 9; q++) {
+        double alpha = 0, beta = 0, gamma = 0;
+        for (int r = 0; r < 7; r++) {
+          const double ap = A[r * 9 + p], aq = A[r * 9 + q];
+          alpha += ap * ap; beta += aq * aq; gamma += ap * aq;
+        }
+        if (alpha <= tiny || beta <= tiny) continue;
+        if (std::fabs(gamma) <= 1e-15 * std::sqrt(alpha * beta)) continue;
+        rotated = true;
+        const double zeta = (beta - alpha) / (2.0 * gamma);
+        double t = 1.0 / (std::fabs(zeta) + std::sqrt(1.0 + zeta * zeta));
+        if (zeta < 0.0) t = -t;
+        const double c = 1.0 / std::sqrt(1.0 + t * t), s = c * t;
+        for (int r = 0; r < 7; r++) {
+          const double ap = A[r * 9 + p], aq = A[r * 9 + q];
+          A[r * 9 + p] = c * ap - s * aq;
+          A[r * 9 + q] = s * ap + c * aq;
+        }
+        for (int r = 0; r < 9; r++) {
+          const double vp = V[r * 9 + p], vq = V[r * 9 + q];
+          V[r * 9 + p] = c * vp - s * vq;
+          V[r * 9 + q] = s * vp + c * vq;
+        }
+      }
+    if (!rotated) break;
+  }
+  // the two smallest column norms (first index wins ties)
+  double nrm[9];
+  for (int j = 0; j < 9; j++) {
+    double s = 0.0;
+    for (int r = 0; r < 7; r++) s += A[r * 9 + j] * A[r * 9 + j];
+    nrm[j] = s;
+  }
+  int b0 = 0;
+  for (int j = 1; j < 9; j++) if (nrm[j] < nrm[b0]) b0 = j;
+  int b1 = b0 == 0 ? 1 : 0;
+  for (int j = 0; j < 9; j++) if (j != b0 && nrm[j] < nrm[b1]) b1 = j;
+  const int lo = std::min(b0, b1), hi = std::max(b0, b1);
+  for (int r = 0; r < 9; r++) { f1[r] = V[r * 9 + hi]; f2[r] = V[r * 9 + lo]; }
+}
+
+// run7Point on the 7 selected correspondences; F: up to 3 row-major 3x3 matrices.
+int run7point(const float* m1, const float* m2, const int* idx, double* F) {
+  double c1x = 0, c1y = 0, c2x = 0, c2y = 0;
+  for (int i = 0; i < 7; i++) {
+    c1x += m1[2 * idx[i]]; c1y += m1[2 * idx[i] + 1];
+    c2x += m2[2 * idx[i]]; c2y += m2[2 * idx[i] + 1];
+  }
+  const double t = 1. / 7;
+  c1x *= t; c1y *= t; c2x *= t; c2y *= t;
+  double scale1 = 0, scale2 = 0;
+  for (int i = 0; i < 7; i++) {
+    const double dx1 = m1[2 * idx[i]] - c1x, dy1 = m1[2 * idx[i] + 1] - c1y;
+    const double dx2 = m2[2 * idx[i]] - c2x, dy2 = m2[2 * idx[i] + 1] - c2y;
+    scale1 += std::sqrt(dx1 * dx1 + dy1 * dy1);
+    scale2 += std::sqrt(dx2 * dx2 + dy2 * dy2);
+  }
+  scale1 *= t; scale2 *= t;
+  if (scale1 < FLT_EPSILON || scale2 < FLT_EPSILON) return 0;
+  scale1 = std::sqrt(2.) / scale1;
+  scale2 = std::sqrt(2.) / scale2;
+  double A[63];
+  for (int i = 0; i < 7; i++) {
+    const double x0 = (m1[2 * idx[i]] - c1x) * scale1, y0 = (m1[2 * idx[i] + 1] - c1y) * scale1;
+    const double x1 = (m2[2 * idx[i]] - c2x) * scale2, y1 = (m2[2 * idx[i] + 1] - c2y) * scale2;
+    double* a = A + i * 9;
+    a[0] = x1 * x0; a[1] = x1 * y0; a[2] = x1;
+    a[3] = y1 * x0; a[4] = y1 * y0; a[5] = y1;
+    a[6] = x0; a[7] = y0; a[8] = 1;
+  }
+  double f1[9], f2[9];
+  null_space_7x9(A, f1, f2);
+  for (int i = 0; i < 9; i++) f1[i] -= f2[i];
+  double c[4], r[3];
+  double t0 = f2[4] * f2[8] - f2[5] * f2[7], t1 = f2[3] * f2[8] - f2[5] * f2[6], t2 = f2[3] * f2[7] - f2[4] * f2[6];
+  c[3] = f2[0] * t0 - f2[1] * t1 + f2[2] * t2;
+  c[2] = f1[0] * t0 - f1[1] * t1 + f1[2] * t2 - f1[3] * (f2[1] * f2[8] - f2[2] * f2[7]) +
+         f1[4] * (f2[0] * f2[8] - f2[2] * f2[6]) - f1[5] * (f2[0] * f2[7] - f2[1] * f2[6]) +
+         f1[6] * (f2[1] * f2[5] - f2[2] * f2[4]) - f1[7] * (f2[0] * f2[5] - f2[2] * f2[3]) +
+         f1[8] * (f2[0] * f2[4] - f2[1] * f2[3]);
+  t0 = f1[4] * f1[8] - f1[5] * f1[7]; t1 = f1[3] * f1[8] - f1[5] * f1[6]; t2 = f1[3] * f1[7] - f1[4] * f1[6];
+  c[1] = f2[0] * t0 - f2[1] * t1 + f2[2] * t2 - f2[3] * (f1[1] * f1[8] - f1[2] * f1[7]) +
+         f2[4] * (f1[0] * f1[8] - f1[2] * f1[6]) - f2[5] * (f1[0] * f1[7] - f1[1] * f1[6]) +
+         f2[6] * (f1[1] * f1[5] - f1[2] * f1[4]) - f2[7] * (f1[0] * f1[5] - f1[2] * f1[3]) +
+         f2[8] * (f1[0] * f1[4] - f1[1] * f1[3]);
+  c[0] = f1[0] * t0 - f1[1] * t1 + f1[2] * t2;
+  const int n = solve_cubic(c, r);
+  if (n < 1 || n > 3) return n < 0 ? 0 : n;
+  const double T1[9] = {scale1, 0, -scale1 * c1x, 0, scale1, -scale1 * c1y, 0, 0, 1};
+  const double T2[9] = {scale2, 0, -scale2 * c2x, 0, scale2, -scale2 * c2y, 0, 0, 1};
+  for (int k = 0; k < n; k++) {
+    double* fm = F + 9 * k;
+    double lambda = r[k], mu = 1.;
+    const double s = f1[8] * r[k] + f2[8];
+    double Fn[9];
+    if (std::fabs(s) > DBL_EPSILON) {
+      mu = 1. / s;
+      lambda *= mu;
+      Fn[8] = 1.;
+    } else {
+      Fn[8] = 0.;
+    }
+    for (int i = 0; i < 8; i++) Fn[i] = f1[i] * lambda + f2[i] * mu;
+    // F = T2^T * Fn * T1
+    double tmp[9];
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) {
+        double a = 0;
+        for (int l = 0; l < 3; l++) a += T2[l * 3 + i] * Fn[l * 3 + j];
+        tmp[i * 3 + j] = a;
+      }
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) {
+        double a = 0;
+        for (int l = 0; l < 3; l++) a += tmp[i * 3 + l] * T1[l * 3 + j];
+        fm[i * 3 + j] = a;
+      }
+    if (std::fabs(fm[8]) > FLT_EPSILON) {
+      const double inv = 1. / fm[8];
+      for (int i = 0; i < 9; i++) fm[i] *= inv;
+    }
+  }
+  return n;
+}
+
+inline float sampson_max(const double* F, const float* a, const float* b) {
+  const double x1 = a[0], y1 = a[1], x2 = b[0], y2 = b[1];
+  double A = F[0] * x1 + F[1] * y1 + F[2];
+  double B = F[3] * x1 + F[4] * y1 + F[5];
+  double C = F[6] * x1 + F[7] * y1 + F[8];
+  const double s2 = 1. / (A * A + B * B);
+  const double d2 = x2 * A + y2 * B + C;
+  A = F[0] * x2 + F[3] * y2 + F[6];
+  B = F[1] * x2 + F[4] * y2 + F[7];
+  C = F[2] * x2 + F[5] * y2 + F[8];
+  const double s1 = 1. / (A * A + B * B);
+  const double d1 = x1 * A + y1 * B + C;
+  return (float)std::max(d1 * d1 * s1, d2 * d2 * s2);
+}
+
+int update_num_iters(double p, double ep, int model_points, int max_iters) {
+  p = std::min(std::max(p, 0.), 1.);
+  ep = std::min(std::max(ep, 0.), 1.);
+  double num = std::max(1. - p, DBL_MIN);
+  double denom = 1. - std::pow(1. - ep, model_points);
+  if (denom < DBL_MIN) return 0;
+  num = std::log(num);
+  denom = std::log(denom);
+  return denom >= 0 || -num >= max_iters * (-denom) ? max_iters : (int)std::nearbyint(num / denom);
+}
+
+}  // namespace
+
+extern "C" int urmvo_oracle_fm_subsets(int N, const float* p0, const float* p1, int max_iters, int32_t* idx) {
+  CvRng rng;
+  int n = 0;
+  for (; n < max_iters; n++)
+    if (!get_subset(p0, p1, N, rng, 10000, idx + 7 * n)) break;
+  return n;
+}
+
+extern "C" int urmvo_oracle_fm_run7(const float* p0, const float* p1, double* F27) {
+  const int idx[7] = {0, 1, 2, 3, 4, 5, 6};
+  return run7point(p0, p1, idx, F27);
+}
+
+extern "C" void urmvo_oracle_fm_errors(int N, const float* p0, const float* p1, const double* F, float* err) {
+  for (int i = 0; i < N; i++) err[i] = sampson_max(F, p0 + 2 * i, p1 + 2 * i);
+}
+
+extern "C" int urmvo_oracle_fm_ransac(int N, const float* p0, const float* p1, double thresh, double confidence,
+                                      int max_iters, uint8_t* mask, double* F9, int32_t* stats3) {
+  if (N < 15) return -1;  // OpenCV: < 7 nothing, 7 direct, 8..14 LMedS — not this path
+  if (thresh <= 0) thresh = 3;
+  if (confidence < DBL_EPSILON || confidence > 1 - DBL_EPSILON) confidence = 0.99;
+  CvRng rng;
+  int niters = std::max(max_iters, 1), max_good = 0, iter = 0, models = 0;
+  const float t = (float)(thresh * thresh);
+  double best[9] = {0};
+  std::memset(mask, 0, N);
+  uint8_t* cur = new uint8_t[N];
+  for (iter = 0; iter < niters; iter++) {
+    int idx[7];
+    if (!get_subset(p0, p1, N, rng, 10000, idx)) {
+      if (iter == 0) { delete[] cur; return 0; }
+      break;
+    }
+    double F[27];
+    const int nm = run7point(p0, p1, idx, F);
+    if (nm <= 0) continue;
+    for (int k = 0; k < nm; k++) {
+      models++;
+      int good = 0;
+      for (int i = 0; i < N; i++) {
+        const int f = sampson_max(F + 9 * k, p0 + 2 * i, p1 + 2 * i) <= t;
+        cur[i] = (uint8_t)f;
+        good += f;
+      }
+      if (good > std::max(max_good, 6)) {
+        std::memcpy(mask, cur, N);
+        std::memcpy(best, F + 9 * k, sizeof(best));
+        max_good = good;
+        niters = update_num_iters(confidence, (double)(N - good) / N, 7, niters);
+      }
+    }
+  }
+  delete[] cur;
+  if (F9) std::memcpy(F9, best, sizeof(best));
+  if (stats3) { stats3[0] = iter; stats3[1] = max_good; stats3[2] = models; }
+  return max_good > 0 ? 1 : 0;
+}

@@ -112,6 +112,23 @@ void urmvo_oracle_draw_sets(int N, int n_hyp, int reseed, int seed, int32_t* set
  * U m x n row-major (may be NULL). */
 void urmvo_oracle_svd(int m, int n, const float* A, float* sigma, float* U, float* V);
 
+/* ---- per-frame fundamental-matrix RANSAC (reference src/point_matching.cc:44-58 ->
+ * cv::findFundamentalMat(points0, points1, cv::FM_RANSAC, 3, 0.99, inliers)); fm_oracle.cpp.
+ * PARITY PINNED against the real cv2.findFundamentalMat (tests/golden/golden_fm_r01.npz). */
+
+/* N >= 15 matches, p0/p1: N*2 floats.  mask: N bytes out, F9: best model (row-major, F33 = 1),
+ * stats3 = {iterations run, inliers of the best model, models scored}.
+ * Returns 1 if a model was found, 0 if none, -1 if N < 15 (OpenCV's 7-point / LMedS branches). */
+int urmvo_oracle_fm_ransac(int N, const float* p0, const float* p1, double thresh, double confidence,
+                           int max_iters, uint8_t* mask, double* F9, int32_t* stats3);
+/* The 7-index subsets OpenCV's RANSAC draws for iterations 0..max_iters-1 (cv::RNG state -1,
+ * collinearity re-draws included).  idx: max_iters*7.  Returns the number of subsets generated. */
+int urmvo_oracle_fm_subsets(int N, const float* p0, const float* p1, int max_iters, int32_t* idx);
+/* run7Point on 7 correspondences: up to 3 models (27 doubles).  Returns the number of models. */
+int urmvo_oracle_fm_run7(const float* p0, const float* p1, double* F27);
+/* FMEstimatorCallback::computeError: err[i] = (float)max(d1^2 s1, d2^2 s2). */
+void urmvo_oracle_fm_errors(int N, const float* p0, const float* p1, const double* F, float* err);
+
 #ifdef __cplusplus
 }
 #endif

@@ -177,3 +177,37 @@ def se3_inverse(T):
     out = np.zeros(7)
     lib().urmvo_oracle_se3_inverse(_p(T), _p(out))
     return out
+
+
+# ---- per-frame fundamental-matrix RANSAC (cv::findFundamentalMat FM_RANSAC restatement, fm_oracle.cpp)
+
+def fm_ransac(p0, p1, thresh=3.0, confidence=0.99, max_iters=1000):
+    """Returns dict(found, mask[N] u8, F[3,3], iters, n_inliers, models)."""
+    p0 = np.ascontiguousarray(p0, dtype=np.float32); p1 = np.ascontiguousarray(p1, dtype=np.float32)
+    N = len(p0)
+    mask = np.zeros(N, dtype=np.uint8); F = np.zeros(9); st = np.zeros(3, dtype=np.int32)
+    rc = lib().urmvo_oracle_fm_ransac(C.c_int(N), _p(p0), _p(p1), C.c_double(thresh), C.c_double(confidence),
+                                      C.c_int(max_iters), _p(mask), _p(F), _p(st))
+    return dict(found=rc, mask=mask, F=F.reshape(3, 3), iters=int(st[0]), n_inliers=int(st[1]), models=int(st[2]))
+
+
+def fm_subsets(p0, p1, max_iters=1000):
+    p0 = np.ascontiguousarray(p0, dtype=np.float32); p1 = np.ascontiguousarray(p1, dtype=np.float32)
+    idx = np.zeros((max_iters, 7), dtype=np.int32)
+    n = lib().urmvo_oracle_fm_subsets(C.c_int(len(p0)), _p(p0), _p(p1), C.c_int(max_iters), _p(idx))
+    return idx[:n]
+
+
+def fm_run7(p0, p1):
+    p0 = np.ascontiguousarray(p0, dtype=np.float32); p1 = np.ascontiguousarray(p1, dtype=np.float32)
+    F = np.zeros(27)
+    n = lib().urmvo_oracle_fm_run7(_p(p0), _p(p1), _p(F))
+    return F.reshape(3, 3, 3)[:max(n, 0)]
+
+
+def fm_errors(p0, p1, F):
+    p0 = np.ascontiguousarray(p0, dtype=np.float32); p1 = np.ascontiguousarray(p1, dtype=np.float32)
+    F = np.ascontiguousarray(F, dtype=np.float64)
+    err = np.zeros(len(p0), dtype=np.float32)
+    lib().urmvo_oracle_fm_errors(C.c_int(len(p0)), _p(p0), _p(p1), _p(F), _p(err))
+    return err

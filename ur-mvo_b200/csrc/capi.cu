@@ -17,6 +17,7 @@
 
 #include "../../include/urmvo_b200.h"
 #include "ba_types.h"
+#include "capi_internal.h"
 #include "kernels.h"
 
 using namespace urmvo;
@@ -25,17 +26,7 @@ namespace {
 
 thread_local std::string g_err;
 
-int fail(int code, const std::string& msg) {
-  g_err = msg;
-  return code;
-}
-
-#define CU_TRY(expr)                                                                        \
-  do {                                                                                      \
-    cudaError_t _e = (expr);                                                                \
-    if (_e != cudaSuccess)                                                                  \
-      return fail(URMVO_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));      \
-  } while (0)
+inline int fail(int code, const std::string& msg) { return urmvo::set_error(code, msg); }
 
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
@@ -85,32 +76,11 @@ struct Arena {
 
 }  // namespace
 
-struct urmvo_ctx {
-  int device = 0;
-  int n_sm = 0;
-  cudaStream_t stream = nullptr;
-  int64_t launches = 0;
-  // optional NCCL communicator for the point-sharded BA (urmvo_comm_init)
-  void* comm = nullptr;
-  int rank = 0, world = 1;
-  // grow-only device workspace lent to the one-shot BA calls (no cudaMalloc / cudaFree per call)
-  unsigned char* ws_dev = nullptr;
-  size_t ws_bytes = 0;
-  bool ws_in_use = false;
-  // reusable pinned staging buffer for the one-shot entry points
-  void* pinned = nullptr;
-  size_t pinned_size = 0;
-  int ensure_pinned(size_t n) {
-    if (n <= pinned_size) return 0;
-    if (pinned) cudaFreeHost(pinned);
-    pinned = nullptr;
-    pinned_size = 0;
-    size_t want = std::max(n, (size_t)1 << 20);
-    if (cudaMallocHost(&pinned, want) != cudaSuccess) return -1;
-    pinned_size = want;
-    return 0;
-  }
-};
+
+int urmvo::set_error(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
 
 extern "C" int urmvo_version(void) { return 100; }
 extern "C" const char* urmvo_last_error(void) { return g_err.c_str(); }

@@ -1,0 +1,348 @@
+// csrc/fm_kernels.cu — per-frame fundamental-matrix RANSAC on sm_100a.
+//
+// Reference behaviour reproduced: src/point_matching.cc:44-58,
+//     cv::findFundamentalMat(points0, points1, cv::FM_RANSAC, 3, 0.99, inliers)
+// i.e. OpenCV's RANSACPointSetRegistrator with the 7-point solver (calib3d fundam.cpp / ptsetreg.cpp;
+// OpenCV is linked, not vendored, by the reference).  The sequential RANSAC loop is data-parallel in
+// everything except two things, which stay on the host (capi.cu):
+//   * the cv::RNG subset draws (a 64-bit multiply-with-carry chain with data-dependent re-draws),
+//   * the "strictly more inliers than the best so far -> shrink the iteration budget" replay, which
+//     needs only the inlier COUNT of every (iteration, model) and picks the same winner as the
+//     sequential loop.
+// The device evaluates every iteration of the budget at once:
+//   fm_solve_kernel  16 lanes per iteration: run7Point (normalise, 7x9 system, 2-D null space by a
+//                    one-sided Jacobi SVD in fp64, cubic det = 0, <= 3 models)          [fp64 ALU]
+//   fm_score_kernel  one warp per (iteration, model): FMEstimatorCallback::computeError in fp64,
+//                    (float)err <= (float)thr^2, ballot/popc inlier count               [fp64 ALU]
+//   fm_mask_kernel   the winner's inlier flags
+// Arithmetic follows the CPU restatement fm_oracle.cpp operation by operation (same summation
+// order: ordered shuffle chains; this file is compiled with -fmad=false), so the models agree to the
+// last bits and the masks are identical; the oracle itself is pinned bit-for-bit against the real
+// cv2.findFundamentalMat (tests/golden/golden_fm_r01.npz).
+#include <cfloat>
+
+#include "kernels.h"
+
+namespace urmvo {
+namespace {
+
+constexpr int kFmLanes = 16;       // lanes per hypothesis in fm_solve_kernel
+constexpr int kFmSweeps = 60;
+constexpr double kFmTol = 1e-15;   // rotate when |gamma| > tol * sqrt(alpha beta)
+constexpr double kFmTiny = 1e-30;  // columns with squared norm <= tiny * ||A||_F^2 are left alone
+
+// sum over lanes 0..m-1 of the sub-warp, in lane order (the oracle's loop order)
+__device__ __forceinline__ double ordered_sum64(double v, int m, unsigned mask) {
+  double s = __shfl_sync(mask, v, 0, kFmLanes);
+  for (int k = 1; k < m; k++) s = s + __shfl_sync(mask, v, k, kFmLanes);
+  return s;
+}
+
+// cv::solveCubic (c[0] x^3 + c[1] x^2 + c[2] x + c[3] = 0); returns the number of roots, -1: any x
+__device__ int solve_cubic(const double* c, double* r) {
+  double a0 = c[0], a1 = c[1], a2 = c[2], a3 = c[3];
+  int n = 0;
+  double x0 = 0, x1 = 0, x2 = 0;
+  if (a0 == 0) {
+    if (a1 == 0) {
+      if (a2 == 0) {
+        n = a3 == 0 ? -1 : 0;
+      } else {
+        x0 = -a3 / a2;
+        n = 1;
+      }
+    } else {
+      double d = a2 * a2 - 4 * a1 * a3;
+      if (d >= 0) {
+        d = sqrt(d);
+        const double q1 = (-a2 + d) * 0.5, q2 = (a2 + d) * -0.5;
+        if (fabs(q1) > fabs(q2)) {
+          x0 = q1 / a1;
+          x1 = a3 / q1;
+        } else {
+          x0 = q2 / a1;
+          x1 = a3 / q2;
+        }
+        n = d > 0 ? 2 : 1;
+      }
+    }
+  } else {
+    a0 = 1. / a0;
+    a1 *= a0; a2 *= a0; a3 *= a0;
+    const double Q = (a1 * a1 - 3 * a2) * (1. / 9);
+    const double R = (2 * a1 * a1 * a1 - 9 * a1 * a2 + 27 * a3) * (1. / 54);
+    const double Qcubed = Q * Q * Q;
+    double d = Qcubed - R * R;
+    if (d > 0) {
+      const double theta = acos(R / sqrt(Qcubed));
+      const double sqrtQ = sqrt(Q);
+      const double t0 = -2 * sqrtQ, t1 = theta * (1. / 3), t2 = a1 * (1. / 3);
+      x0 = t0 * cos(t1) - t2;
+      x1 = t0 * cos(t1 + (2. * 3.14159265358979323846 / 3)) - t2;
+      x2 = t0 * cos(t1 + (4. * 3.14159265358979323846 / 3)) - t2;
+      n = 3;
+    } else if (d == 0) {
+      if (R >= 0) {
+        x0 = -2 * pow(R, 1. / 3) - a1 / 3;
+        x1 = pow(R, 1. / 3) - a1 / 3;
+      } else {
+        x0 = 2 * pow(-R, 1. / 3) - a1 / 3;
+        x1 = -pow(-R, 1. / 3) - a1 / 3;
+      }
+      x2 = 0;
+      n = x0 == x1 ? 1 : 2;
+      x1 = x0 == x1 ? 0 : x1;
+    } else {
+      d = sqrt(-d);
+      double e = pow(d + fabs(R), 1. / 3);
+      if (R > 0) e = -e;
+      x0 = (e + Q / e) - a1 * (1. / 3);
+      n = 1;
+    }
+  }
+  r[0] = x0; r[1] = x1; r[2] = x2;
+  return n;
+}
+
+// models: [n_hyp][27] doubles, n_models: [n_hyp].  pts: float4 (x0,y0,x1,y1) per match, sets hold
+// GLOBAL match indices (the problem's offset already added).
+__global__ void __launch_bounds__(256)
+fm_solve_kernel(int n_hyp, const int* __restrict__ sets, const float4* __restrict__ pts,
+                double* __restrict__ models, int* __restrict__ n_models) {
+  constexpr int PER_WARP = 32 / kFmLanes;
+  constexpr int DL = 7 * 9 + 81;  // doubles per hypothesis
+  extern __shared__ double sm_fm[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int sub = lane / kFmLanes, r = lane - sub * kFmLanes;
+  const unsigned mask = 0xFFFFu << (sub * kFmLanes);
+  const int hyp = (blockIdx.x * (blockDim.x >> 5) + wid) * PER_WARP + sub;
+  if (hyp >= n_hyp) return;  // whole sub-warps leave together
+  double* A = sm_fm + (size_t)(wid * PER_WARP + sub) * DL;
+  double* V = A + 63;
+  // ---- run7Point: normalisation (centroid, mean distance) in the oracle's summation order
+  float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (r < 7) m = pts[sets[(size_t)hyp * 7 + r]];
+  const double t = 1. / 7;
+  const double c1x = ordered_sum64((double)m.x, 7, mask) * t, c1y = ordered_sum64((double)m.y, 7, mask) * t;
+  const double c2x = ordered_sum64((double)m.z, 7, mask) * t, c2y = ordered_sum64((double)m.w, 7, mask) * t;
+  const double dx1 = m.x - c1x, dy1 = m.y - c1y, dx2 = m.z - c2x, dy2 = m.w - c2y;
+  double scale1 = ordered_sum64(sqrt(dx1 * dx1 + dy1 * dy1), 7, mask) * t;
+  double scale2 = ordered_sum64(sqrt(dx2 * dx2 + dy2 * dy2), 7, mask) * t;
+  if (scale1 < FLT_EPSILON || scale2 < FLT_EPSILON) {
+    if (r == 0) n_models[hyp] = 0;
+    return;
+  }
+  scale1 = sqrt(2.) / scale1;
+  scale2 = sqrt(2.) / scale2;
+  if (r < 7) {
+    const double x0 = dx1 * scale1, y0 = dy1 * scale1, x1 = dx2 * scale2, y1 = dy2 * scale2;
+    double* a = A + r * 9;
+    a[0] = x1 * x0; a[1] = x1 * y0; a[2] = x1;
+    a[3] = y1 * x0; a[4] = y1 * y0; a[5] = y1;
+    a[6] = x0; a[7] = y0; a[8] = 1;
+  }
+  for (int e = r; e < 81; e += kFmLanes) V[e] = (e / 9 == e % 9) ? 1.0 : 0.0;
+  __syncwarp(mask);
+  // ---- 2-D null space: one-sided Jacobi on the 7x9 system (lane r < 7 owns row r of A, lane r < 9
+  // row r of V); spec in the CPU restatement fm_oracle.cpp null_space_7x9
+  double tiny;
+  {
+    double row = 0.0;
+    if (r < 7)
+      for (int j = 0; j < 9; j++) row += A[r * 9 + j] * A[r * 9 + j];
+    tiny = kFmTiny * ordered_sum64(row, 7, mask);
+  }
+  for (int sweep = 0; sweep < kFmSweeps; sweep++) {
+    bool rotated = false;
+    for (int p = 0; p < 8; p++) {
+      for (int q = p + 1; q < 9; q++) {
+        const double ap = r < 7 ? A[r * 9 + p] : 0.0, aq = r < 7 ? A[r * 9 + q] : 0.0;
+        const double alpha = ordered_sum64(ap * ap, 7, mask);
+        const double beta = ordered_sum64(aq * aq, 7, mask);
+        const double gamma = ordered_sum64(ap * aq, 7, mask);
+        if (alpha <= tiny || beta <= tiny) continue;
+        if (fabs(gamma) <= kFmTol * sqrt(alpha * beta)) continue;
+        rotated = true;
+        const double zeta = (beta - alpha) / (2.0 * gamma);
+        double tt = 1.0 / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        if (zeta < 0.0) tt = -tt;
+        const double c = 1.0 / sqrt(1.0 + tt * tt), s = c * tt;
+        if (r < 7) {
+          A[r * 9 + p] = c * ap - s * aq;
+          A[r * 9 + q] = s * ap + c * aq;
+        }
+        if (r < 9) {
+          const double vp = V[r * 9 + p], vq = V[r * 9 + q];
+          V[r * 9 + p] = c * vp - s * vq;
+          V[r * 9 + q] = s * vp + c * vq;
+        }
+      }
+    }
+    if (!rotated) break;
+  }
+  __syncwarp(mask);
+  // the two smallest column norms (first index wins ties); f1 = larger column index, f2 = smaller
+  int b0 = 0, b1 = 1;
+  {
+    double nrm[9];
+    for (int j = 0; j < 9; j++) {
+      const double a = r < 7 ? A[r * 9 + j] : 0.0;
+      nrm[j] = ordered_sum64(a * a, 7, mask);
+    }
+    for (int j = 1; j < 9; j++) if (nrm[j] < nrm[b0]) b0 = j;
+    b1 = b0 == 0 ? 1 : 0;
+    for (int j = 0; j < 9; j++) if (j != b0 && nrm[j] < nrm[b1]) b1 = j;
+  }
+  if (r != 0) return;
+  const int lo = b0 < b1 ? b0 : b1, hi = b0 < b1 ? b1 : b0;
+  double f1[9], f2[9];
+  for (int k = 0; k < 9; k++) { f1[k] = V[k * 9 + hi]; f2[k] = V[k * 9 + lo]; }
+  for (int k = 0; k < 9; k++) f1[k] -= f2[k];
+  double c[4], roots[3];
+  double t0 = f2[4] * f2[8] - f2[5] * f2[7], t1 = f2[3] * f2[8] - f2[5] * f2[6], t2 = f2[3] * f2[7] - f2[4] * f2[6];
+  c[3] = f2[0] * t0 - f2[1] * t1 + f2[2] * t2;
+  c[2] = f1[0] * t0 - f1[1] * t1 + f1[2] * t2 - f1[3] * (f2[1] * f2[8] - f2[2] * f2[7]) +
+         f1[4] * (f2[0] * f2[8] - f2[2] * f2[6]) - f1[5] * (f2[0] * f2[7] - f2[1] * f2[6]) +
+         f1[6] * (f2[1] * f2[5] - f2[2] * f2[4]) - f1[7] * (f2[0] * f2[5] - f2[2] * f2[3]) +
+         f1[8] * (f2[0] * f2[4] - f2[1] * f2[3]);
+  t0 = f1[4] * f1[8] - f1[5] * f1[7]; t1 = f1[3] * f1[8] - f1[5] * f1[6]; t2 = f1[3] * f1[7] - f1[4] * f1[6];
+  c[1] = f2[0] * t0 - f2[1] * t1 + f2[2] * t2 - f2[3] * (f1[1] * f1[8] - f1[2] * f1[7]) +
+         f2[4] * (f1[0] * f1[8] - f1[2] * f1[6]) - f2[5] * (f1[0] * f1[7] - f1[1] * f1[6]) +
+         f2[6] * (f1[1] * f1[5] - f1[2] * f1[4]) - f2[7] * (f1[0] * f1[5] - f1[2] * f1[3]) +
+         f2[8] * (f1[0] * f1[4] - f1[1] * f1[3]);
+  c[0] = f1[0] * t0 - f1[1] * t1 + f1[2] * t2;
+  int n = solve_cubic(c, roots);
+  if (n < 1 || n > 3) {
+    n_models[hyp] = n < 0 ? 0 : n;
+    return;
+  }
+  const double T1[9] = {scale1, 0, -scale1 * c1x, 0, scale1, -scale1 * c1y, 0, 0, 1};
+  const double T2[9] = {scale2, 0, -scale2 * c2x, 0, scale2, -scale2 * c2y, 0, 0, 1};
+  for (int k = 0; k < n; k++) {
+    double* fm = models + (size_t)hyp * 27 + 9 * k;
+    double lambda = roots[k], mu = 1.;
+    const double s = f1[8] * roots[k] + f2[8];
+    double Fn[9];
+    if (fabs(s) > DBL_EPSILON) {
+      mu = 1. / s;
+      lambda *= mu;
+      Fn[8] = 1.;
+    } else {
+      Fn[8] = 0.;
+    }
+    for (int i = 0; i < 8; i++) Fn[i] = f1[i] * lambda + f2[i] * mu;
+    double tmp[9], out[9];
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) {
+        double a = 0;
+        for (int l = 0; l < 3; l++) a += T2[l * 3 + i] * Fn[l * 3 + j];
+        tmp[i * 3 + j] = a;
+      }
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) {
+        double a = 0;
+        for (int l = 0; l < 3; l++) a += tmp[i * 3 + l] * T1[l * 3 + j];
+        out[i * 3 + j] = a;
+      }
+    if (fabs(out[8]) > FLT_EPSILON) {
+      const double inv = 1. / out[8];
+      for (int i = 0; i < 9; i++) out[i] *= inv;
+    }
+    for (int i = 0; i < 9; i++) fm[i] = out[i];
+  }
+  n_models[hyp] = n;
+}
+
+// FMEstimatorCallback::computeError for one correspondence
+__device__ __forceinline__ float fm_error(const double* F, const float4 m) {
+  const double x1 = m.x, y1 = m.y, x2 = m.z, y2 = m.w;
+  double a = F[0] * x1 + F[1] * y1 + F[2];
+  double b = F[3] * x1 + F[4] * y1 + F[5];
+  double c = F[6] * x1 + F[7] * y1 + F[8];
+  const double s2 = 1. / (a * a + b * b);
+  const double d2 = x2 * a + y2 * b + c;
+  a = F[0] * x2 + F[3] * y2 + F[6];
+  b = F[1] * x2 + F[4] * y2 + F[7];
+  c = F[2] * x2 + F[5] * y2 + F[8];
+  const double s1 = 1. / (a * a + b * b);
+  const double d1 = x1 * a + y1 * b + c;
+  return (float)fmax(d1 * d1 * s1, d2 * d2 * s2);
+}
+
+// One warp per (hypothesis, model slot).  counts: [n_hyp][3] (0 for unused slots).
+__global__ void __launch_bounds__(256)
+fm_score_kernel(int n_hyp, const int* __restrict__ hyp_prob, const int* __restrict__ off,
+                const float4* __restrict__ pts, const double* __restrict__ models,
+                const int* __restrict__ n_models, float thr2, int* __restrict__ counts) {
+  const int lane = threadIdx.x & 31;
+  const int wpc = blockDim.x >> 5;
+  for (int g = blockIdx.x * wpc + (threadIdx.x >> 5); g < n_hyp * 3; g += gridDim.x * wpc) {
+    const int hyp = g / 3, k = g - hyp * 3;
+    if (k >= n_models[hyp]) {
+      if (lane == 0) counts[g] = 0;
+      continue;
+    }
+    double F[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) F[i] = models[(size_t)hyp * 27 + 9 * k + i];
+    const int b = hyp_prob[hyp];
+    const int i0 = off[b], i1 = off[b + 1];
+    int good = 0;
+    for (int base = i0; base < i1; base += 32) {
+      const int i = base + lane;
+      bool in = false;
+      if (i < i1) in = fm_error(F, pts[i]) <= thr2;
+      good += __popc(__ballot_sync(0xffffffffu, in));
+    }
+    if (lane == 0) counts[g] = good;
+  }
+}
+
+// Inlier flags of the winning model of every problem (found[b] == 0: all zero).
+__global__ void __launch_bounds__(256)
+fm_mask_kernel(int B, const int* __restrict__ off, const float4* __restrict__ pts,
+               const double* __restrict__ win_F, const int* __restrict__ found, float thr2,
+               uint8_t* __restrict__ mask) {
+  const int b = blockIdx.y;
+  if (b >= B) return;
+  const int i0 = off[b], i1 = off[b + 1];
+  double F[9];
+#pragma unroll
+  for (int i = 0; i < 9; i++) F[i] = win_F[(size_t)b * 9 + i];
+  const bool ok = found[b] != 0;
+  for (int i = i0 + blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += gridDim.x * blockDim.x)
+    mask[i] = (ok && fm_error(F, pts[i]) <= thr2) ? 1 : 0;
+}
+
+}  // namespace
+
+cudaError_t launch_fm_solve(int n_hyp, const int* sets, const float4* pts, double* models, int* n_models,
+                            cudaStream_t s) {
+  if (n_hyp <= 0) return cudaSuccess;
+  const int threads = 256, per_cta = (threads / 32) * (32 / kFmLanes);
+  const size_t smem = (size_t)per_cta * (63 + 81) * sizeof(double);
+  fm_solve_kernel<<<(n_hyp + per_cta - 1) / per_cta, threads, smem, s>>>(n_hyp, sets, pts, models, n_models);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fm_score(int n_hyp, const int* hyp_prob, const int* off, const float4* pts,
+                            const double* models, const int* n_models, float thr2, int* counts, int n_sm,
+                            cudaStream_t s) {
+  if (n_hyp <= 0) return cudaSuccess;
+  const int threads = 256, wpc = threads / 32;
+  long long blocks = ((long long)n_hyp * 3 + wpc - 1) / wpc;
+  const long long cap = (long long)n_sm * 8;  // 8 resident CTAs of 256 threads per SM
+  if (blocks > cap) blocks = cap;
+  fm_score_kernel<<<(unsigned)blocks, threads, 0, s>>>(n_hyp, hyp_prob, off, pts, models, n_models, thr2, counts);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fm_mask(int B, int max_n, const int* off, const float4* pts, const double* win_F,
+                           const int* found, float thr2, uint8_t* mask, cudaStream_t s) {
+  if (B <= 0 || max_n <= 0) return cudaSuccess;
+  dim3 grid((unsigned)((max_n + 255) / 256), (unsigned)B);
+  fm_mask_kernel<<<grid, 256, 0, s>>>(B, off, pts, win_F, found, thr2, mask);
+  return cudaGetLastError();
+}
+
+}  // namespace urmvo

@@ -78,4 +78,13 @@ struct TVBuffers {
 cudaError_t launch_tv_ransac(const TVBuffers& b, float sigma, int n_sm, cudaStream_t stream, int* n_launch);
 cudaError_t launch_tv_motion(const TVBuffers& b, float th2, cudaStream_t stream);
 
+// ---- fm_kernels.cu (per-frame fundamental-matrix RANSAC; pts = (x0,y0,x1,y1) per match)
+cudaError_t launch_fm_solve(int n_hyp, const int* sets, const float4* pts, double* models, int* n_models,
+                            cudaStream_t s);
+cudaError_t launch_fm_score(int n_hyp, const int* hyp_prob, const int* off, const float4* pts,
+                            const double* models, const int* n_models, float thr2, int* counts, int n_sm,
+                            cudaStream_t s);
+cudaError_t launch_fm_mask(int B, int max_n, const int* off, const float4* pts, const double* win_F,
+                           const int* found, float thr2, uint8_t* mask, cudaStream_t s);
+
 }  // namespace urmvo

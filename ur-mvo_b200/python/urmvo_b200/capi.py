@@ -14,11 +14,18 @@ EXPORTED_SYMBOLS = [
     "urmvo_pose_plan_create", "urmvo_pose_plan_run", "urmvo_pose_plan_download", "urmvo_pose_plan_destroy",
     "urmvo_two_view", "urmvo_tv_plan_create", "urmvo_tv_plan_run_ransac", "urmvo_tv_plan_download_hyps",
     "urmvo_tv_plan_reconstruct", "urmvo_tv_plan_destroy",
+    "urmvo_fm_ransac", "urmvo_fm_ransac_batch", "urmvo_fm_plan_create", "urmvo_fm_plan_run", "urmvo_fm_plan_finish",
+    "urmvo_fm_plan_hypotheses", "urmvo_fm_plan_destroy",
 ]
 
 
 class UrmvoError(RuntimeError):
     pass
+
+
+class FMStats(C.Structure):
+    _fields_ = [("found", C.c_int32), ("iters", C.c_int32), ("n_inliers", C.c_int32), ("n_models", C.c_int32),
+                ("F", C.c_double * 9)]
 
 
 class BAOptions(C.Structure):
@@ -63,9 +70,11 @@ def load_library():
         for name in EXPORTED_SYMBOLS:
             f = getattr(L, name)
             if name not in ("urmvo_last_error", "urmvo_stream", "urmvo_launch_count", "urmvo_destroy",
-                            "urmvo_ba_plan_destroy", "urmvo_pose_plan_destroy", "urmvo_tv_plan_destroy"):
+                            "urmvo_ba_plan_destroy", "urmvo_pose_plan_destroy", "urmvo_tv_plan_destroy",
+                            "urmvo_fm_plan_destroy"):
                 f.restype = C.c_int
-        for name in ("urmvo_destroy", "urmvo_ba_plan_destroy", "urmvo_pose_plan_destroy", "urmvo_tv_plan_destroy"):
+        for name in ("urmvo_destroy", "urmvo_ba_plan_destroy", "urmvo_pose_plan_destroy", "urmvo_tv_plan_destroy",
+                     "urmvo_fm_plan_destroy"):
             getattr(L, name).restype = None
         _LIB = L
     return _LIB
@@ -177,6 +186,24 @@ class Context:
                                              _p(inl), _p(n_inl)), "urmvo_pose_only_batch")
         return poses, inl, n_inl
 
+    def fm_ransac(self, p0, p1, thresh=3.0, confidence=0.99, max_iters=1000):
+        """cv::findFundamentalMat(p0, p1, FM_RANSAC, thresh, confidence, mask) for one frame pair."""
+        p0 = _f32(p0); p1 = _f32(p1)
+        mask = np.zeros(len(p0), dtype=np.uint8); st = FMStats()
+        _check(self._L.urmvo_fm_ransac(self._h, C.c_int(len(p0)), _p(p0), _p(p1), C.c_double(thresh),
+                                       C.c_double(confidence), C.c_int(max_iters), _p(mask), C.byref(st)),
+               "urmvo_fm_ransac")
+        return dict(found=int(st.found), mask=mask, F=np.array(st.F).reshape(3, 3), iters=int(st.iters),
+                    n_inliers=int(st.n_inliers), models=int(st.n_models))
+
+    def fm_ransac_batch(self, pairs, thresh=3.0, confidence=0.99, max_iters=1000):
+        off, p0, p1 = pack_fm_batch(pairs)
+        mask = np.zeros(int(off[-1]), dtype=np.uint8); st = (FMStats * len(pairs))()
+        _check(self._L.urmvo_fm_ransac_batch(self._h, C.c_int(len(pairs)), _p(off), _p(p0), _p(p1), C.c_double(thresh),
+                                             C.c_double(confidence), C.c_int(max_iters), _p(mask), st),
+               "urmvo_fm_ransac_batch")
+        return [mask[off[b]:off[b + 1]] for b in range(len(pairs))], list(st)
+
     def two_view(self, tv, sets=None):
         k1 = _f32(tv["keys1"]); k2 = _f32(tv["keys2"]); m = _i32(tv["matches12"]); K = _f32(tv["K"])
         sets = _i32(tv["sets"] if sets is None else sets)
@@ -190,6 +217,50 @@ class Context:
                                       _p(T21), _p(P3D), _p(tri), _p(mH), _p(mF), C.byref(st), C.byref(ok)),
                "urmvo_two_view")
         return dict(ok=bool(ok.value), T21=T21, P3D=P3D, triangulated=tri, mask_H=mH, mask_F=mF, stats=st)
+
+
+def pack_fm_batch(pairs):
+    """[(p0, p1), ...] -> (off int32[B+1], pts0 float32[T,2], pts1 float32[T,2])."""
+    off = np.zeros(len(pairs) + 1, dtype=np.int32)
+    off[1:] = np.cumsum([len(a) for a, _ in pairs])
+    pts0 = np.ascontiguousarray(np.concatenate([np.asarray(a, dtype=np.float32).reshape(-1, 2) for a, _ in pairs]))
+    pts1 = np.ascontiguousarray(np.concatenate([np.asarray(b, dtype=np.float32).reshape(-1, 2) for _, b in pairs]))
+    return off, pts0, pts1
+
+
+class FMPlan:
+    """Device-resident batch of per-frame fundamental-matrix RANSAC problems (urmvo_fm_plan_*)."""
+
+    def __init__(self, ctx, pairs, thresh=3.0, confidence=0.99, max_iters=1000):
+        self._L = ctx._L
+        self.ctx = ctx
+        self.off, p0, p1 = pack_fm_batch(pairs)
+        self.B = len(pairs)
+        self._h = C.c_void_p()
+        _check(self._L.urmvo_fm_plan_create(ctx._h, C.byref(self._h), C.c_int(self.B), _p(self.off), _p(p0), _p(p1),
+                                            C.c_double(thresh), C.c_double(confidence), C.c_int(max_iters)),
+               "urmvo_fm_plan_create")
+        self.hypotheses = int(self._L.urmvo_fm_plan_hypotheses(self._h))
+
+    def run(self):
+        _check(self._L.urmvo_fm_plan_run(self._h), "urmvo_fm_plan_run")
+
+    def finish(self):
+        mask = np.zeros(int(self.off[-1]), dtype=np.uint8)
+        st = (FMStats * self.B)()
+        _check(self._L.urmvo_fm_plan_finish(self._h, _p(mask), st), "urmvo_fm_plan_finish")
+        return [mask[self.off[b]:self.off[b + 1]] for b in range(self.B)], list(st)
+
+    def close(self):
+        if self._h:
+            self._L.urmvo_fm_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def nccl_unique_id():

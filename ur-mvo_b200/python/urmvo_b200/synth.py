@@ -235,3 +235,15 @@ def cfg3(seed=1003, n_hyp=8192):
     N = int((tv["matches12"] >= 0).sum())
     tv["sets"] = draw_sets(N, n_hyp, 0)
     return tv
+
+
+def make_fm(seed=1006, n=1000, inlier_frac=0.7, px_sigma=0.7, rot_deg=5.0, t=(0.3, 0.02, 0.05)):
+    """Matched keypoints of one frame pair for the per-frame fundamental-matrix RANSAC
+    (reference src/point_matching.cc:44-58): two (n, 2) float32 arrays of integer pixel positions."""
+    tv = make_two_view(seed, n_keys=n, inlier_frac=inlier_frac, px_sigma=px_sigma, rot_deg=rot_deg, t=t)
+    return tv["keys1"], tv["keys2"]
+
+
+def make_fm_batch(seed=1006, B=256, n=1000, inlier_frac=0.7):
+    """B independent frame pairs (stereo + temporal matches of consecutive keyframes): list of (p0, p1)."""
+    return [make_fm(seed + 7919 * b, n, inlier_frac) for b in range(B)]
