@@ -471,6 +471,40 @@ def side_measurements(ctx, stream, torch):
                                       "cpu_lm_iters_per_s": (o[3].iters[0] + o[3].iters[1]) / tc, "cpu_sample": "1 window, 1 thread",
                                       "rel_cost_diff": abs(sst.chi2_final[1] - o[3].chi2_final[1]) / abs(o[3].chi2_final[1])}
     splan.close()
+    # per-frame outlier rejection: 256 frame pairs x 1000 matches, up to 1000 RANSAC
+    # iterations each; device-resident kernels (solve + score), the whole host-buffer call, and the
+    # reference's own OpenCV call (cv2, when importable) / the CPU restatement beside it
+    pairs = synth.make_fm_batch(1006, 256, 1000, 0.7)
+    fplan = U.FMPlan(ctx, pairs)
+    dt = timed(fplan.run, 5)  # all RANSAC rounds: kernels + host subset draws + host budget replay
+    masks, fst = fplan.finish()
+    its = sum(s.iters for s in fst)
+    ctx.fm_ransac_batch(pairs[:2])  # workspace warm-up
+    t0 = time.perf_counter(); ctx.fm_ransac_batch(pairs); t_call = time.perf_counter() - t0
+    ctx.fm_ransac(*pairs[0])
+    t0 = time.perf_counter()
+    for a, b in pairs[:16]:
+        ctx.fm_ransac(a, b)
+    t_one = (time.perf_counter() - t0) / 16
+    t0 = time.perf_counter()
+    om = [po.fm_ransac(a, b)["mask"] for a, b in pairs[:16]]
+    tc = (time.perf_counter() - t0) / 16
+    fm = {"frame_pairs_per_s": 256 / dt, "ms": dt * 1e3, "iterations_evaluated_per_s": fplan.hypotheses / dt, "iterations_evaluated": fplan.hypotheses,
+          "frame_pairs": 256, "matches": 1000, "iterations_needed_mean": its / 256.0,
+          "e2e_batch_call_frame_pairs_per_s": 256 / t_call, "e2e_single_call_ms": t_one * 1e3,
+          "cpu_port_ms_per_frame_pair": tc * 1e3, "cpu_sample": "16 frame pairs, 1 thread",
+          "masks_equal_cpu_port": bool(all(np.array_equal(a, b) for a, b in zip(masks[:16], om)))}
+    try:
+        import cv2
+        t0 = time.perf_counter()
+        cm = [cv2.findFundamentalMat(a, b, cv2.FM_RANSAC, 3, 0.99)[1].ravel() for a, b in pairs[:16]]
+        fm["opencv_ms_per_frame_pair"] = (time.perf_counter() - t0) / 16 * 1e3
+        fm["opencv_version"] = cv2.__version__
+        fm["masks_equal_opencv"] = bool(all(np.array_equal(a, b) for a, b in zip(masks[:16], cm)))
+    except Exception as e:  # cv2 is test infrastructure here, never required
+        fm["opencv"] = f"unavailable: {type(e).__name__}"
+    extra["fm_ransac_per_frame"] = fm
+    fplan.close()
     return extra
 
 

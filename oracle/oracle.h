@@ -4,7 +4,9 @@
  * include, link or call this.  Only tests/, __graft_entry__.smoke() and the
  * cpu_baseline / --impl reference legs of bench.py use it, as the checker.
  *
- * PARITY UNPINNED: the reference (be2rlab/UR-MVO) ships no tests, golden vectors
+ * PARITY: the fundamental-matrix RANSAC part (fm_oracle.cpp) is PINNED bit-for-bit against outputs
+ * of the real cv2.findFundamentalMat (tests/golden/golden_fm_r01.npz).  The BA / pose-only /
+ * two-view reconstruction parts are PARITY UNPINNED: the reference (be2rlab/UR-MVO) ships no tests, golden vectors
  * or fixtures for this path and its arithmetic lives in g2o / Eigen / OpenCV,
  * none of which is vendored or installable here.  This oracle is
  * a restatement of src/g2o_optimization.cc and src/epipolar_geometry.cc plus the

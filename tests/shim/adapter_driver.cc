@@ -6,6 +6,7 @@
 #include <vector>
 #include "epipolar_geometry.h"
 #include "g2o_optimization.h"
+#include "point_matching_outliers.h"
 template <class T> static std::vector<T> rd(FILE* f, size_t n) { std::vector<T> v(n); if (n && fread(v.data(), sizeof(T), n, f) != n) { perror("read"); exit(2); } return v; }
 template <class T> static void wr(FILE* f, const std::vector<T>& v) { if (!v.empty()) fwrite(v.data(), sizeof(T), v.size(), f); }
 int main(int argc, char** argv) {
@@ -60,6 +61,15 @@ int main(int argc, char** argv) {
     for (bool t : tri) tv.push_back(t);
     if (!ok) { P.assign((size_t)n1 * 3, 0.f); tv.assign(n1, 0); }
     wr(out, okv); wr(out, T); wr(out, P); wr(out, tv);
+  } else if (mode == "fm") {
+    auto hdr = rd<int>(in, 1); int n = hdr[0];
+    auto a = rd<float>(in, (size_t)n * 2); auto b = rd<float>(in, (size_t)n * 2);
+    std::vector<cv::Point2f> p0(n), p1(n);
+    for (int i = 0; i < n; i++) { p0[i].x = a[i*2]; p0[i].y = a[i*2+1]; p1[i].x = b[i*2]; p1[i].y = b[i*2+1]; }
+    std::vector<unsigned char> inl(n, 7);
+    const bool handled = FindFundamentalInliersGPU(p0, p1, inl);
+    std::vector<int> h = {handled ? 1 : 0};
+    wr(out, h); wr(out, inl);
   }
   fclose(in); fclose(out);
   return 0;

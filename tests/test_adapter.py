@@ -22,7 +22,8 @@ def build_driver():
     urmvo_b200.load_library()
     cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-I", os.path.join(ROOT, "tests", "shim"), "-I", os.path.join(ROOT, "include"),
            os.path.join(ROOT, "tests", "shim", "adapter_driver.cc"), os.path.join(ROOT, "ur-mvo_b200", "adapter", "g2o_optimization.cc"),
-           os.path.join(ROOT, "ur-mvo_b200", "adapter", "epipolar_geometry.cc"), "-L", os.path.join(ROOT, "ur-mvo_b200", "lib"),
+           os.path.join(ROOT, "ur-mvo_b200", "adapter", "epipolar_geometry.cc"),
+           os.path.join(ROOT, "ur-mvo_b200", "adapter", "point_matching_outliers.cc"), "-I", os.path.join(ROOT, "ur-mvo_b200", "adapter"), "-L", os.path.join(ROOT, "ur-mvo_b200", "lib"),
            "-lurmvo_b200", "-Wl,-rpath," + os.path.join(ROOT, "ur-mvo_b200", "lib"), "-o", DRIVER]
     subprocess.check_call(cmd)
 
@@ -31,7 +32,8 @@ def test_adapters_compile_and_link_against_the_c_abi():
     build_driver()
     assert os.path.exists(DRIVER)
     syms = subprocess.run(["nm", "-C", DRIVER], capture_output=True, text=True).stdout
-    for s in ("LocalmapOptimization(", "FrameOptimization(", "EpipolarGeometry::reconstruct(", "EpipolarGeometry::Random::RandomInt("):
+    for s in ("LocalmapOptimization(", "FrameOptimization(", "EpipolarGeometry::reconstruct(", "EpipolarGeometry::Random::RandomInt(",
+              "FindFundamentalInliersGPU("):
         assert s in syms, s
 
 
@@ -88,3 +90,18 @@ def test_reconstruct_through_the_adapter_uses_glibc_rand_sets(oracle):
     assert bool(ok) == o["ok"]
     assert np.array_equal(T.view(np.uint32), o["T21"].view(np.uint32))
     assert np.array_equal(P.view(np.uint32), o["P3D"].view(np.uint32)) and np.array_equal(tri, o["triangulated"])
+
+
+@pytest.mark.gpu
+def test_point_matching_outlier_rejection_through_the_adapter():
+    """FindFundamentalInliersGPU (the call of src/point_matching.cc:53) against the committed output
+    of the real cv2.findFundamentalMat; fewer than 15 matches are handed back to the caller."""
+    G = np.load(os.path.join(ROOT, "tests", "golden", "golden_fm_r01.npz"))
+    for k in (3, 11):
+        p0, p1 = G[f"p0_{k}"], G[f"p1_{k}"]
+        out = _run("fm", struct.pack("i", len(p0)) + p0.tobytes() + p1.tobytes())
+        assert struct.unpack("i", out[:4])[0] == 1
+        assert np.array_equal(np.frombuffer(out[4:], dtype=np.uint8), G[f"mask_{k}"])
+    p0, p1 = synth.make_fm(3500, 14, 0.9)
+    out = _run("fm", struct.pack("i", 14) + p0.tobytes() + p1.tobytes())
+    assert struct.unpack("i", out[:4])[0] == 0 and set(out[4:]) == {7}  # untouched

@@ -47,9 +47,10 @@ def test_gpu_batch_equals_single_calls(ctx, oracle):
 def test_gpu_plan_rerun_is_deterministic(ctx):
     pairs = [synth.make_fm(3200 + b, 500, 0.6) for b in range(4)]
     plan = U.FMPlan(ctx, pairs)
-    assert plan.hypotheses == 4 * 1000
     plan.run()
     m1, s1 = plan.finish()
+    # adaptive rounds: at least the iterations OpenCV's loop needs, at most the whole budget
+    assert sum(s.iters for s in s1) <= plan.hypotheses <= 4 * 1000
     plan.run()
     m2, s2 = plan.finish()
     for a, b in zip(m1, m2):

@@ -1,0 +1,45 @@
+// adapter/point_matching_outliers.cc — see point_matching_outliers.h.  Only marshals the two
+// std::vector<cv::Point2f> (already contiguous x,y floats) into urmvo_fm_ransac; the RANSAC itself
+// runs in csrc/fm_kernels.cu.  No CPU fallback: a missing GPU aborts loudly.
+#include "point_matching_outliers.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <mutex>
+
+#include "urmvo_b200.h"
+
+namespace {
+urmvo_ctx* fm_context() {
+  static urmvo_ctx* ctx = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    if (urmvo_create(&ctx, 0) != URMVO_OK) {
+      std::fprintf(stderr, "[urmvo_b200] %s\n", urmvo_last_error());
+      ctx = nullptr;
+    }
+  });
+  return ctx;
+}
+std::mutex g_fm_mutex;  // MatchingPoints is called from the tracking and the mapping thread
+}  // namespace
+
+bool FindFundamentalInliersGPU(const std::vector<cv::Point2f>& points0, const std::vector<cv::Point2f>& points1,
+                               std::vector<unsigned char>& inliers) {
+  static_assert(sizeof(cv::Point2f) == 2 * sizeof(float), "cv::Point2f must be two packed floats");
+  const int n = (int)points0.size();
+  if (n < 15 || points1.size() != points0.size()) return false;
+  urmvo_ctx* ctx = fm_context();
+  if (!ctx) {
+    std::fprintf(stderr, "[urmvo_b200] FindFundamentalInliersGPU: no usable B200, aborting (there is no CPU path)\n");
+    std::abort();
+  }
+  std::lock_guard<std::mutex> lock(g_fm_mutex);
+  inliers.assign(n, 0);
+  const int rc = urmvo_fm_ransac(ctx, n, &points0[0].x, &points1[0].x, 3.0, 0.99, 1000, inliers.data(), nullptr);
+  if (rc != URMVO_OK) {
+    std::fprintf(stderr, "[urmvo_b200] urmvo_fm_ransac: %s\n", urmvo_last_error());
+    std::abort();
+  }
+  return true;
+}

@@ -46,11 +46,11 @@ bool last_point_collinear(const float* m, const int* idx) {
   return false;
 }
 
-// getSubset for iterations 0..max_iters-1; returns the number of subsets (an exhausted attempt
-// budget ends the RANSAC loop).  out: local indices + base.
-int draw_subsets(const float* p0, const float* p1, int N, int max_iters, int base, int* out) {
-  CvRng rng;
-  for (int it = 0; it < max_iters; it++) {
+// getSubset for the next `want` iterations of one problem (the RNG state persists between rounds);
+// returns the number of subsets drawn (< want: the attempt budget ran out, which ends the RANSAC
+// loop of that problem).  out: indices + base (position of the problem in the concatenated arrays).
+int draw_subsets(CvRng& rng, const float* p0, const float* p1, int N, int want, int base, int* out) {
+  for (int it = 0; it < want; it++) {
     int idx[7];
     bool found = false;
     for (int attempt = 0; attempt < 10000 && !found; attempt++) {
@@ -69,7 +69,7 @@ int draw_subsets(const float* p0, const float* p1, int N, int max_iters, int bas
     if (!found) return it;
     for (int i = 0; i < 7; i++) out[(size_t)it * 7 + i] = base + idx[i];
   }
-  return max_iters;
+  return want;
 }
 
 // RANSACUpdateNumIters
@@ -84,56 +84,85 @@ int update_num_iters(double p, double ep, int model_points, int max_iters) {
   return denom >= 0 || -num >= max_iters * (-denom) ? max_iters : (int)std::nearbyint(num / denom);
 }
 
+constexpr int kFirstRound = 256;  // iterations evaluated before the budget is known
+
+// Per-problem state of RANSACPointSetRegistrator::run between rounds.
+struct FmProblem {
+  CvRng rng;
+  int N = 0, base = 0;
+  int niters = 0, iter = 0, max_good = 0, models = 0, win = -1;  // win = hyp_id*3 + slot
+  bool done = false;
+  int pos = 0, cnt = 0;  // slice of the current round
+};
+
+template <class F>
+void parallel_over(int n, F&& fn) {
+  const int hw = (int)std::thread::hardware_concurrency();
+  const int nt = std::max(1, std::min(n / 4, hw > 0 ? hw : 1));  // a thread is worth >= 4 problems
+  if (nt <= 1) {
+    for (int i = 0; i < n; i++) fn(i);
+    return;
+  }
+  std::vector<std::thread> th;
+  for (int t = 0; t < nt; t++)
+    th.emplace_back([&, t] { for (int i = t; i < n; i += nt) fn(i); });
+  for (auto& t : th) t.join();
+}
+
 }  // namespace
 
 struct urmvo_fm_plan {
   urmvo_ctx* ctx = nullptr;
-  int B = 0, total_n = 0, total_hyp = 0, max_n = 0, max_iters = 0;
+  int B = 0, total_n = 0, max_n = 0, max_iters = 0, evaluated = 0;
   double confidence = 0.99;
   float thr2 = 9.f;
-  std::vector<int> off, hyp_off;  // B+1 each
+  std::vector<int> off;
+  std::vector<float> p0, p1;  // host copies: the subset draws of later rounds read the coordinates
+  std::vector<FmProblem> prob;
+  bool borrowed = false;
   unsigned char* dev = nullptr;
-  size_t o_pts = 0, o_off = 0, o_sets = 0, o_prob = 0, o_models = 0, o_nmod = 0, o_counts = 0, o_win = 0,
-         o_found = 0, o_mask = 0, bytes = 0;
-  // pinned host mirrors of what comes back / goes up per finish
-  int* h_counts = nullptr;   // total_hyp*3
-  int* h_nmod = nullptr;     // total_hyp
-  double* h_models = nullptr;  // total_hyp*27 (winner lookup)
-  double* h_win = nullptr;   // B*9
-  int* h_found = nullptr;    // B
-  uint8_t* h_mask = nullptr; // total_n
+  size_t o_pts = 0, o_off = 0, o_models = 0, o_ids = 0, o_sets = 0, o_nmod = 0, o_counts = 0, o_win = 0,
+         o_winF = 0, o_mask = 0, bytes = 0;
+  // pinned host block
+  unsigned char* hb = nullptr;
+  int *h_ids = nullptr, *h_sets = nullptr, *h_nmod = nullptr, *h_counts = nullptr, *h_win = nullptr;
+  double* h_winF = nullptr;
+  uint8_t* h_mask = nullptr;
+  size_t round_cap = 0;  // hypotheses one round can hold
 };
 
 extern "C" void urmvo_fm_plan_destroy(urmvo_fm_plan* p) {
   if (!p) return;
   cudaSetDevice(p->ctx->device);
   cudaStreamSynchronize(p->ctx->stream);
-  if (p->dev) cudaFree(p->dev);
-  if (p->h_counts) cudaFreeHost(p->h_counts);
+  if (p->borrowed) p->ctx->ws_in_use = false;
+  else if (p->dev) cudaFree(p->dev);
+  if (p->hb) cudaFreeHost(p->hb);
   delete p;
 }
 
-extern "C" int urmvo_fm_plan_hypotheses(const urmvo_fm_plan* p) { return p ? p->total_hyp : 0; }
+extern "C" int urmvo_fm_plan_hypotheses(const urmvo_fm_plan* p) { return p ? p->evaluated : 0; }
 
-extern "C" int urmvo_fm_plan_create(urmvo_ctx* ctx, urmvo_fm_plan** out, int B, const int32_t* off,
-                                    const float* pts0, const float* pts1, double thresh, double confidence,
-                                    int max_iters) {
+static int fm_plan_create_impl(urmvo_ctx* ctx, urmvo_fm_plan** out, int B, const int32_t* off, const float* pts0,
+                               const float* pts1, double thresh, double confidence, int max_iters, bool borrow) {
   if (!ctx || !out || B <= 0 || !off || !pts0 || !pts1)
     return set_error(URMVO_ERR_ARG, "fm_plan_create: null or empty input");
   *out = nullptr;
   if (max_iters <= 0) max_iters = 1;
   if (thresh <= 0) thresh = 3;  // cv::findFundamentalMat defaults
   if (confidence < DBL_EPSILON || confidence > 1 - DBL_EPSILON) confidence = 0.99;
+  if (off[0] != 0) return set_error(URMVO_ERR_ARG, "fm_plan_create: offsets must start at 0");
   int max_n = 0;
   for (int b = 0; b < B; b++) {
     const int n = off[b + 1] - off[b];
-    if (off[0] != 0 || n < 0) return set_error(URMVO_ERR_ARG, "fm_plan_create: offsets must start at 0 and ascend");
+    if (n < 0) return set_error(URMVO_ERR_ARG, "fm_plan_create: offsets must ascend");
     if (n < 15)
       return set_error(URMVO_ERR_UNSUPPORTED,
                        "fm_ransac: fewer than 15 correspondences (OpenCV's 7-point / LMedS branch; keep the "
                        "reference's own cv::findFundamentalMat call for these)");
     max_n = std::max(max_n, n);
   }
+  if ((long long)B * max_iters > (1ll << 29)) return set_error(URMVO_ERR_ARG, "fm_plan_create: B * max_iters too large");
   CU_TRY(cudaSetDevice(ctx->device));
   urmvo_fm_plan* p = new urmvo_fm_plan();
   p->ctx = ctx; p->B = B; p->max_iters = max_iters; p->confidence = confidence;
@@ -141,74 +170,66 @@ extern "C" int urmvo_fm_plan_create(urmvo_ctx* ctx, urmvo_fm_plan** out, int B, 
   p->off.assign(off, off + B + 1);
   p->total_n = off[B];
   p->max_n = max_n;
-  // ---- host: subsets of every problem (threads over problems)
-  std::vector<int> sets((size_t)B * max_iters * 7);
-  std::vector<int> n_sets(B, 0);
-  {
-    const int hw = (int)std::thread::hardware_concurrency();
-    const int nt = std::max(1, std::min(B, hw > 0 ? hw : 1));
-    auto work = [&](int t) {
-      for (int b = t; b < B; b += nt)
-        n_sets[b] = draw_subsets(pts0 + 2 * (size_t)off[b], pts1 + 2 * (size_t)off[b], off[b + 1] - off[b], max_iters,
-                                 off[b], sets.data() + (size_t)b * max_iters * 7);
-    };
-    if (nt == 1) {
-      work(0);
-    } else {
-      std::vector<std::thread> th;
-      for (int t = 0; t < nt; t++) th.emplace_back(work, t);
-      for (auto& t : th) t.join();
-    }
-  }
-  p->hyp_off.assign(B + 1, 0);
-  for (int b = 0; b < B; b++) p->hyp_off[b + 1] = p->hyp_off[b] + n_sets[b];
-  p->total_hyp = p->hyp_off[B];
-  const size_t H = (size_t)std::max(p->total_hyp, 1), T = (size_t)p->total_n;
+  p->p0.assign(pts0, pts0 + 2 * (size_t)p->total_n);
+  p->p1.assign(pts1, pts1 + 2 * (size_t)p->total_n);
+  p->prob.resize(B);
+  for (int b = 0; b < B; b++) { p->prob[b].N = off[b + 1] - off[b]; p->prob[b].base = off[b]; }
+  const size_t T = (size_t)p->total_n, H = (size_t)B * max_iters;
+  p->round_cap = H;  // a round never holds more than every remaining iteration of every problem
   auto take = [&](size_t bytes) { size_t o = p->bytes; p->bytes = (p->bytes + bytes + 255) / 256 * 256; return o; };
   p->o_pts = take(T * sizeof(float4));
   p->o_off = take((size_t)(B + 1) * sizeof(int));
-  p->o_sets = take(H * 7 * sizeof(int));
-  p->o_prob = take(H * sizeof(int));
   p->o_models = take(H * 27 * sizeof(double));
+  p->o_ids = take(H * sizeof(int));
+  p->o_sets = take(H * 7 * sizeof(int));
   p->o_nmod = take(H * sizeof(int));
   p->o_counts = take(H * 3 * sizeof(int));
-  p->o_win = take((size_t)B * 9 * sizeof(double));
-  p->o_found = take((size_t)B * sizeof(int));
+  p->o_win = take((size_t)B * sizeof(int));
+  p->o_winF = take((size_t)B * 9 * sizeof(double));
   p->o_mask = take(T);
-  cudaError_t e = cudaMalloc(&p->dev, p->bytes);
-  if (e != cudaSuccess) { delete p; return set_error(URMVO_ERR_CUDA, std::string("cudaMalloc fm plan: ") + cudaGetErrorString(e)); }
-  // one pinned block: [counts | nmod | models | win | found | mask] + upload staging [pts | sets | prob]
-  const size_t hb_counts = H * 3 * sizeof(int), hb_nmod = H * sizeof(int), hb_models = H * 27 * sizeof(double);
-  const size_t hb_win = (size_t)B * 9 * sizeof(double), hb_found = (size_t)B * sizeof(int), hb_mask = (T + 15) / 16 * 16;
-  const size_t hb_pts = T * sizeof(float4), hb_sets = H * 7 * sizeof(int), hb_prob = H * sizeof(int);
-  unsigned char* hb = nullptr;
-  e = cudaMallocHost(&hb, hb_models + hb_win + hb_counts + hb_nmod + hb_found + hb_mask + hb_pts + hb_sets + hb_prob + 64);  // + alignment padding
-  if (e != cudaSuccess) { cudaFree(p->dev); delete p; return set_error(URMVO_ERR_CUDA, "cudaMallocHost fm plan failed"); }
-  p->h_counts = (int*)hb;  // first member: the block is freed through h_counts
-  unsigned char* q = hb + hb_counts;
-  p->h_nmod = (int*)q; q += hb_nmod;
-  // keep 8-byte alignment for the doubles
-  q = (unsigned char*)(((uintptr_t)q + 7) & ~(uintptr_t)7);
-  p->h_models = (double*)q; q += hb_models;
-  p->h_win = (double*)q; q += hb_win;
-  p->h_found = (int*)q; q += hb_found;
-  p->h_mask = (uint8_t*)q; q += hb_mask;
-  q = (unsigned char*)(((uintptr_t)q + 15) & ~(uintptr_t)15);
-  float4* h_pts = (float4*)q; q += hb_pts;
-  int* h_sets = (int*)q; q += hb_sets;
-  int* h_prob = (int*)q;
-  for (size_t i = 0; i < T; i++) h_pts[i] = make_float4(pts0[2 * i], pts0[2 * i + 1], pts1[2 * i], pts1[2 * i + 1]);
-  for (int b = 0; b < B; b++) {
-    std::memcpy(h_sets + (size_t)p->hyp_off[b] * 7, sets.data() + (size_t)b * max_iters * 7, (size_t)n_sets[b] * 7 * sizeof(int));
-    for (int h = p->hyp_off[b]; h < p->hyp_off[b + 1]; h++) h_prob[h] = b;
+  cudaError_t e = cudaSuccess;
+  if (borrow && !ctx->ws_in_use) {
+    if (ctx->ws_bytes < p->bytes) {
+      if (ctx->ws_dev) cudaFree(ctx->ws_dev);
+      ctx->ws_dev = nullptr; ctx->ws_bytes = 0;
+      e = cudaMalloc(&ctx->ws_dev, p->bytes + p->bytes / 4);
+      if (e == cudaSuccess) ctx->ws_bytes = p->bytes + p->bytes / 4;
+    }
+    if (e == cudaSuccess) { p->dev = ctx->ws_dev; p->borrowed = true; ctx->ws_in_use = true; }
+  } else {
+    e = cudaMalloc(&p->dev, p->bytes);
   }
+  if (e != cudaSuccess) { delete p; return set_error(URMVO_ERR_CUDA, std::string("cudaMalloc fm plan: ") + cudaGetErrorString(e)); }
+  // pinned: [winF | ids | sets | nmod | counts | win | mask | pts staging]
+  const size_t b_winF = (size_t)B * 9 * sizeof(double), b_ids = H * sizeof(int), b_sets = H * 7 * sizeof(int);
+  const size_t b_nmod = H * sizeof(int), b_counts = H * 3 * sizeof(int), b_win = (size_t)B * sizeof(int);
+  const size_t b_mask = (T + 15) / 16 * 16, b_pts = T * sizeof(float4);
+  const size_t hb_bytes = b_winF + b_ids + b_sets + b_nmod + b_counts + b_win + b_mask + b_pts + 64;
+  unsigned char* hb = nullptr;
+  if (borrow) {
+    if (ctx->ensure_pinned(hb_bytes)) { urmvo_fm_plan_destroy(p); return set_error(URMVO_ERR_CUDA, "cudaMallocHost failed"); }
+    hb = (unsigned char*)ctx->pinned;
+  } else {
+    e = cudaMallocHost(&hb, hb_bytes);
+    if (e != cudaSuccess) { urmvo_fm_plan_destroy(p); return set_error(URMVO_ERR_CUDA, "cudaMallocHost fm plan failed"); }
+    p->hb = hb;
+  }
+  unsigned char* q = hb;
+  p->h_winF = (double*)q; q += b_winF;
+  p->h_ids = (int*)q; q += b_ids;
+  p->h_sets = (int*)q; q += b_sets;
+  p->h_nmod = (int*)q; q += b_nmod;
+  p->h_counts = (int*)q; q += b_counts;
+  p->h_win = (int*)q; q += b_win;
+  p->h_mask = (uint8_t*)q; q += b_mask;
+  q = (unsigned char*)(((uintptr_t)q + 15) & ~(uintptr_t)15);
+  float4* h_pts = (float4*)q;
+  for (size_t i = 0; i < T; i++) h_pts[i] = make_float4(pts0[2 * i], pts0[2 * i + 1], pts1[2 * i], pts1[2 * i + 1]);
   cudaStream_t s = ctx->stream;
-  cudaError_t e1 = cudaMemcpyAsync(p->dev + p->o_pts, h_pts, hb_pts, cudaMemcpyHostToDevice, s);
+  cudaError_t e1 = cudaMemcpyAsync(p->dev + p->o_pts, h_pts, b_pts, cudaMemcpyHostToDevice, s);
   cudaError_t e2 = cudaMemcpyAsync(p->dev + p->o_off, p->off.data(), (size_t)(B + 1) * sizeof(int), cudaMemcpyHostToDevice, s);
-  cudaError_t e3 = p->total_hyp ? cudaMemcpyAsync(p->dev + p->o_sets, h_sets, (size_t)p->total_hyp * 7 * sizeof(int), cudaMemcpyHostToDevice, s) : cudaSuccess;
-  cudaError_t e4 = p->total_hyp ? cudaMemcpyAsync(p->dev + p->o_prob, h_prob, (size_t)p->total_hyp * sizeof(int), cudaMemcpyHostToDevice, s) : cudaSuccess;
-  cudaError_t e5 = cudaStreamSynchronize(s);  // p->off is pageable, the staging is reused
-  for (cudaError_t ee : {e1, e2, e3, e4, e5})
+  cudaError_t e3 = cudaStreamSynchronize(s);  // p->off is pageable
+  for (cudaError_t ee : {e1, e2, e3})
     if (ee != cudaSuccess) {
       urmvo_fm_plan_destroy(p);
       return set_error(URMVO_ERR_CUDA, std::string("fm_plan_create upload: ") + cudaGetErrorString(ee));
@@ -217,18 +238,85 @@ extern "C" int urmvo_fm_plan_create(urmvo_ctx* ctx, urmvo_fm_plan** out, int B, 
   return URMVO_OK;
 }
 
+extern "C" int urmvo_fm_plan_create(urmvo_ctx* ctx, urmvo_fm_plan** out, int B, const int32_t* off,
+                                    const float* pts0, const float* pts1, double thresh, double confidence,
+                                    int max_iters) {
+  return fm_plan_create_impl(ctx, out, B, off, pts0, pts1, thresh, confidence, max_iters, false);
+}
+
+// The RANSAC loop of every problem, in rounds: round 1 evaluates the first kFirstRound iterations of
+// each problem, later rounds everything that is left of each problem's (shrinking) budget.  After
+// every round the host replays the sequential "better model -> new budget" logic on the counts.
 extern "C" int urmvo_fm_plan_run(urmvo_fm_plan* p) {
   if (!p) return set_error(URMVO_ERR_ARG, "fm_plan_run: null plan");
   CU_TRY(cudaSetDevice(p->ctx->device));
   cudaStream_t s = p->ctx->stream;
   unsigned char* D = p->dev;
-  if (p->total_hyp == 0) return URMVO_OK;
-  CU_TRY(launch_fm_solve(p->total_hyp, (const int*)(D + p->o_sets), (const float4*)(D + p->o_pts),
-                         (double*)(D + p->o_models), (int*)(D + p->o_nmod), s));
-  CU_TRY(launch_fm_score(p->total_hyp, (const int*)(D + p->o_prob), (const int*)(D + p->o_off),
-                         (const float4*)(D + p->o_pts), (const double*)(D + p->o_models),
-                         (const int*)(D + p->o_nmod), p->thr2, (int*)(D + p->o_counts), p->ctx->n_sm, s));
-  p->ctx->launches += 2;
+  for (auto& pr : p->prob) {
+    pr.rng = CvRng();
+    pr.niters = std::max(p->max_iters, 1);
+    pr.iter = 0; pr.max_good = 0; pr.models = 0; pr.win = -1; pr.done = false;
+  }
+  p->evaluated = 0;
+  for (int round = 0;; round++) {
+    // ---- plan the round
+    int n = 0;
+    std::vector<int> active;
+    for (int b = 0; b < p->B; b++) {
+      FmProblem& pr = p->prob[b];
+      if (pr.done) continue;
+      const int want = round == 0 ? std::min(pr.niters, kFirstRound) : pr.niters - pr.iter;
+      if (want <= 0) { pr.done = true; continue; }
+      pr.pos = n; pr.cnt = want;
+      n += want;
+      active.push_back(b);
+    }
+    if (n == 0) break;
+    // ---- host: draw the subsets of the round (cv::RNG chains, one per problem)
+    parallel_over((int)active.size(), [&](int a) {
+      FmProblem& pr = p->prob[active[a]];
+      const int got = draw_subsets(pr.rng, p->p0.data() + 2 * (size_t)pr.base, p->p1.data() + 2 * (size_t)pr.base, pr.N,
+                                   pr.cnt, pr.base, p->h_sets + (size_t)pr.pos * 7);
+      for (int i = 0; i < pr.cnt; i++) p->h_ids[pr.pos + i] = active[a] * p->max_iters + pr.iter + i;
+      // subsets past an exhausted attempt budget are never evaluated: mark them with the first one
+      for (int i = got; i < pr.cnt; i++)
+        for (int k = 0; k < 7; k++) p->h_sets[(size_t)(pr.pos + i) * 7 + k] = pr.base + k;
+      if (got < pr.cnt) pr.cnt = -got - 1;  // remember where the draws ended
+    });
+    CU_TRY(cudaMemcpyAsync(D + p->o_ids, p->h_ids, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaMemcpyAsync(D + p->o_sets, p->h_sets, (size_t)n * 7 * sizeof(int), cudaMemcpyHostToDevice, s));
+    CU_TRY(launch_fm_solve(n, (const int*)(D + p->o_ids), (const int*)(D + p->o_sets), (const float4*)(D + p->o_pts),
+                           (double*)(D + p->o_models), (int*)(D + p->o_nmod), s));
+    CU_TRY(launch_fm_score(n, (const int*)(D + p->o_ids), p->max_iters, (const int*)(D + p->o_off),
+                           (const float4*)(D + p->o_pts), (const double*)(D + p->o_models),
+                           (const int*)(D + p->o_nmod), p->thr2, (int*)(D + p->o_counts), p->ctx->n_sm, s));
+    p->ctx->launches += 2;
+    p->evaluated += n;
+    CU_TRY(cudaMemcpyAsync(p->h_nmod, D + p->o_nmod, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaMemcpyAsync(p->h_counts, D + p->o_counts, (size_t)n * 3 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    // ---- replay of RANSACPointSetRegistrator::run on the round's counts
+    for (int b : active) {
+      FmProblem& pr = p->prob[b];
+      int avail = pr.cnt;
+      bool exhausted = false;
+      if (avail < 0) { avail = -avail - 1; exhausted = true; }
+      int i = 0;
+      for (; i < avail && pr.iter < pr.niters; i++, pr.iter++) {
+        const int nm = p->h_nmod[pr.pos + i];
+        for (int k = 0; k < nm; k++) {
+          pr.models++;
+          const int good = p->h_counts[(size_t)(pr.pos + i) * 3 + k];
+          if (good > std::max(pr.max_good, 6)) {
+            pr.max_good = good;
+            pr.win = p->h_ids[pr.pos + i] * 3 + k;
+            pr.niters = update_num_iters(p->confidence, (double)(pr.N - good) / pr.N, 7, pr.niters);
+          }
+        }
+      }
+      if (pr.iter >= pr.niters || (exhausted && i >= avail)) pr.done = true;
+    }
+  }
   return URMVO_OK;
 }
 
@@ -237,54 +325,25 @@ extern "C" int urmvo_fm_plan_finish(urmvo_fm_plan* p, uint8_t* inlier, urmvo_fm_
   CU_TRY(cudaSetDevice(p->ctx->device));
   cudaStream_t s = p->ctx->stream;
   unsigned char* D = p->dev;
-  const size_t H = (size_t)p->total_hyp;
-  if (H) {
-    CU_TRY(cudaMemcpyAsync(p->h_counts, D + p->o_counts, H * 3 * sizeof(int), cudaMemcpyDeviceToHost, s));
-    CU_TRY(cudaMemcpyAsync(p->h_nmod, D + p->o_nmod, H * sizeof(int), cudaMemcpyDeviceToHost, s));
-    CU_TRY(cudaMemcpyAsync(p->h_models, D + p->o_models, H * 27 * sizeof(double), cudaMemcpyDeviceToHost, s));
-  }
-  CU_TRY(cudaStreamSynchronize(s));
-  // ---- replay of RANSACPointSetRegistrator::run per problem
-  for (int b = 0; b < p->B; b++) {
-    const int N = p->off[b + 1] - p->off[b];
-    const int h0 = p->hyp_off[b], avail = p->hyp_off[b + 1] - h0;
-    int niters = std::max(p->max_iters, 1), max_good = 0, iter = 0, models = 0, best_h = -1, best_k = 0;
-    for (iter = 0; iter < niters; iter++) {
-      if (iter >= avail) break;  // getSubset exhausted its attempts (iter == 0: no model at all)
-      const int h = h0 + iter;
-      const int nm = p->h_nmod[h];
-      for (int k = 0; k < nm; k++) {
-        models++;
-        const int good = p->h_counts[(size_t)h * 3 + k];
-        if (good > std::max(max_good, 6)) {
-          max_good = good;
-          best_h = h; best_k = k;
-          niters = update_num_iters(p->confidence, (double)(N - good) / N, 7, niters);
-        }
-      }
-    }
-    p->h_found[b] = max_good > 0 ? 1 : 0;
-    for (int i = 0; i < 9; i++) p->h_win[(size_t)b * 9 + i] = best_h >= 0 ? p->h_models[(size_t)best_h * 27 + 9 * best_k + i] : 0.0;
-    if (stats) {
-      stats[b].found = p->h_found[b];
-      stats[b].iters = iter;
-      stats[b].n_inliers = max_good;
-      stats[b].n_models = models;
-      for (int i = 0; i < 9; i++) stats[b].F[i] = p->h_win[(size_t)b * 9 + i];
-    }
-  }
-  CU_TRY(cudaMemcpyAsync(D + p->o_win, p->h_win, (size_t)p->B * 9 * sizeof(double), cudaMemcpyHostToDevice, s));
-  CU_TRY(cudaMemcpyAsync(D + p->o_found, p->h_found, (size_t)p->B * sizeof(int), cudaMemcpyHostToDevice, s));
+  for (int b = 0; b < p->B; b++) p->h_win[b] = p->prob[b].max_good > 0 ? p->prob[b].win : -1;
+  CU_TRY(cudaMemcpyAsync(D + p->o_win, p->h_win, (size_t)p->B * sizeof(int), cudaMemcpyHostToDevice, s));
   CU_TRY(launch_fm_mask(p->B, p->max_n, (const int*)(D + p->o_off), (const float4*)(D + p->o_pts),
-                        (const double*)(D + p->o_win), (const int*)(D + p->o_found), p->thr2, D + p->o_mask, s));
+                        (const double*)(D + p->o_models), (const int*)(D + p->o_win), p->thr2, D + p->o_mask,
+                        (double*)(D + p->o_winF), s));
   p->ctx->launches += 1;
-  if (inlier) {
-    CU_TRY(cudaMemcpyAsync(p->h_mask, D + p->o_mask, (size_t)p->total_n, cudaMemcpyDeviceToHost, s));
-    CU_TRY(cudaStreamSynchronize(s));
-    std::memcpy(inlier, p->h_mask, (size_t)p->total_n);
-  } else {
-    CU_TRY(cudaStreamSynchronize(s));
-  }
+  if (inlier) CU_TRY(cudaMemcpyAsync(p->h_mask, D + p->o_mask, (size_t)p->total_n, cudaMemcpyDeviceToHost, s));
+  if (stats) CU_TRY(cudaMemcpyAsync(p->h_winF, D + p->o_winF, (size_t)p->B * 9 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CU_TRY(cudaStreamSynchronize(s));
+  if (inlier) std::memcpy(inlier, p->h_mask, (size_t)p->total_n);
+  if (stats)
+    for (int b = 0; b < p->B; b++) {
+      const FmProblem& pr = p->prob[b];
+      stats[b].found = pr.max_good > 0 ? 1 : 0;
+      stats[b].iters = pr.iter;
+      stats[b].n_inliers = pr.max_good;
+      stats[b].n_models = pr.models;
+      for (int i = 0; i < 9; i++) stats[b].F[i] = p->h_winF[(size_t)b * 9 + i];
+    }
   return URMVO_OK;
 }
 
@@ -293,7 +352,7 @@ extern "C" int urmvo_fm_ransac_batch(urmvo_ctx* ctx, int B, const int32_t* off, 
                                      urmvo_fm_stats* stats) {
   if (!inlier) return set_error(URMVO_ERR_ARG, "fm_ransac: null inlier output");
   urmvo_fm_plan* p = nullptr;
-  int rc = urmvo_fm_plan_create(ctx, &p, B, off, pts0, pts1, thresh, confidence, max_iters);
+  int rc = fm_plan_create_impl(ctx, &p, B, off, pts0, pts1, thresh, confidence, max_iters, true);
   if (rc != URMVO_OK) return rc;
   rc = urmvo_fm_plan_run(p);
   if (rc == URMVO_OK) rc = urmvo_fm_plan_finish(p, inlier, stats);

@@ -20,6 +20,7 @@
 // last bits and the masks are identical; the oracle itself is pinned bit-for-bit against the real
 // cv2.findFundamentalMat (tests/golden/golden_fm_r01.npz).
 #include <cfloat>
+#include <cmath>
 
 #include "kernels.h"
 
@@ -104,11 +105,12 @@ __device__ int solve_cubic(const double* c, double* r) {
   return n;
 }
 
-// models: [n_hyp][27] doubles, n_models: [n_hyp].  pts: float4 (x0,y0,x1,y1) per match, sets hold
-// GLOBAL match indices (the problem's offset already added).
+// One RANSAC round: n hypotheses.  hyp_ids[i] = problem * max_iters + iteration addresses the
+// persistent model store (models: [B*max_iters][27]); sets / n_models are compact per round.
+// pts: float4 (x0,y0,x1,y1) per match, sets hold GLOBAL match indices (problem offset added).
 __global__ void __launch_bounds__(256)
-fm_solve_kernel(int n_hyp, const int* __restrict__ sets, const float4* __restrict__ pts,
-                double* __restrict__ models, int* __restrict__ n_models) {
+fm_solve_kernel(int n_hyp, const int* __restrict__ hyp_ids, const int* __restrict__ sets,
+                const float4* __restrict__ pts, double* __restrict__ models_all, int* __restrict__ n_models) {
   constexpr int PER_WARP = 32 / kFmLanes;
   constexpr int DL = 7 * 9 + 81;  // doubles per hypothesis
   extern __shared__ double sm_fm[];
@@ -219,7 +221,7 @@ fm_solve_kernel(int n_hyp, const int* __restrict__ sets, const float4* __restric
   const double T1[9] = {scale1, 0, -scale1 * c1x, 0, scale1, -scale1 * c1y, 0, 0, 1};
   const double T2[9] = {scale2, 0, -scale2 * c2x, 0, scale2, -scale2 * c2y, 0, 0, 1};
   for (int k = 0; k < n; k++) {
-    double* fm = models + (size_t)hyp * 27 + 9 * k;
+    double* fm = models_all + (size_t)hyp_ids[hyp] * 27 + 9 * k;
     double lambda = roots[k], mu = 1.;
     const double s = f1[8] * roots[k] + f2[8];
     double Fn[9];
@@ -253,95 +255,131 @@ fm_solve_kernel(int n_hyp, const int* __restrict__ sets, const float4* __restric
   n_models[hyp] = n;
 }
 
-// FMEstimatorCallback::computeError for one correspondence
-__device__ __forceinline__ float fm_error(const double* F, const float4 m) {
+// FMEstimatorCallback::computeError + the threshold test of findInliers for one correspondence:
+//   err = (float)std::max(d1^2 * (1/(a1^2+b1^2)), d2^2 * (1/(a2^2+b2^2)));  inlier = err <= (float)thr^2
+// Fast path without the two fp64 divisions: (float)x <= t  <=>  x <= tm (tm = the double midpoint
+// between t and the next float; passed in by the host), and x = d^2/den is compared as
+// d^2 vs tm*den with a relative guard band of 1e-12; anything inside the band (or den == 0) takes
+// the exact path, which repeats OpenCV's expression operation by operation.  The decision is
+// therefore always the exact one.
+struct FmThresh {
+  float t;      // (float)(thresh*thresh)
+  double lo;    // tm * (1 - 1e-12)
+  double hi;    // tm * (1 + 1e-12)
+};
+
+__device__ __forceinline__ bool fm_inlier(const double* F, const float4 m, const FmThresh th) {
   const double x1 = m.x, y1 = m.y, x2 = m.z, y2 = m.w;
-  double a = F[0] * x1 + F[1] * y1 + F[2];
-  double b = F[3] * x1 + F[4] * y1 + F[5];
-  double c = F[6] * x1 + F[7] * y1 + F[8];
-  const double s2 = 1. / (a * a + b * b);
-  const double d2 = x2 * a + y2 * b + c;
-  a = F[0] * x2 + F[3] * y2 + F[6];
-  b = F[1] * x2 + F[4] * y2 + F[7];
-  c = F[2] * x2 + F[5] * y2 + F[8];
-  const double s1 = 1. / (a * a + b * b);
-  const double d1 = x1 * a + y1 * b + c;
-  return (float)fmax(d1 * d1 * s1, d2 * d2 * s2);
+  const double a2 = F[0] * x1 + F[1] * y1 + F[2];
+  const double b2 = F[3] * x1 + F[4] * y1 + F[5];
+  const double c2 = F[6] * x1 + F[7] * y1 + F[8];
+  const double den2 = a2 * a2 + b2 * b2;
+  const double d2 = x2 * a2 + y2 * b2 + c2;
+  const double a1 = F[0] * x2 + F[3] * y2 + F[6];
+  const double b1 = F[1] * x2 + F[4] * y2 + F[7];
+  const double c1 = F[2] * x2 + F[5] * y2 + F[8];
+  const double den1 = a1 * a1 + b1 * b1;
+  const double d1 = x1 * a1 + y1 * b1 + c1;
+  const double n1 = d1 * d1, n2 = d2 * d2;
+  // clearly outside in either direction -> outlier; clearly inside in both -> inlier
+  const bool out = n1 > th.hi * den1 || n2 > th.hi * den2;
+  const bool in = n1 < th.lo * den1 && n2 < th.lo * den2;
+  if (in) return true;
+  if (out && den1 > 0.0 && den2 > 0.0) return false;
+  // exact path (guard band, zero denominators, NaNs): OpenCV's own expression
+  const double s2 = 1. / den2, s1 = 1. / den1;
+  const double e1 = n1 * s1, e2 = n2 * s2;
+  const float err = (float)((e1 < e2) ? e2 : e1);  // std::max(e1, e2)
+  return err <= th.t;
 }
 
-// One warp per (hypothesis, model slot).  counts: [n_hyp][3] (0 for unused slots).
+// One warp per (round hypothesis, model slot).  counts: [n_hyp][3] compact (0 for unused slots).
 __global__ void __launch_bounds__(256)
-fm_score_kernel(int n_hyp, const int* __restrict__ hyp_prob, const int* __restrict__ off,
-                const float4* __restrict__ pts, const double* __restrict__ models,
-                const int* __restrict__ n_models, float thr2, int* __restrict__ counts) {
+fm_score_kernel(int n_hyp, const int* __restrict__ hyp_ids, int max_iters, const int* __restrict__ off,
+                const float4* __restrict__ pts, const double* __restrict__ models_all,
+                const int* __restrict__ n_models, FmThresh th, int* __restrict__ counts) {
   const int lane = threadIdx.x & 31;
   const int wpc = blockDim.x >> 5;
   for (int g = blockIdx.x * wpc + (threadIdx.x >> 5); g < n_hyp * 3; g += gridDim.x * wpc) {
-    const int hyp = g / 3, k = g - hyp * 3;
-    if (k >= n_models[hyp]) {
+    const int i = g / 3, k = g - i * 3;
+    if (k >= n_models[i]) {
       if (lane == 0) counts[g] = 0;
       continue;
     }
+    const int id = hyp_ids[i];
     double F[9];
 #pragma unroll
-    for (int i = 0; i < 9; i++) F[i] = models[(size_t)hyp * 27 + 9 * k + i];
-    const int b = hyp_prob[hyp];
+    for (int e = 0; e < 9; e++) F[e] = models_all[(size_t)id * 27 + 9 * k + e];
+    const int b = id / max_iters;
     const int i0 = off[b], i1 = off[b + 1];
     int good = 0;
     for (int base = i0; base < i1; base += 32) {
-      const int i = base + lane;
+      const int j = base + lane;
       bool in = false;
-      if (i < i1) in = fm_error(F, pts[i]) <= thr2;
+      if (j < i1) in = fm_inlier(F, pts[j], th);
       good += __popc(__ballot_sync(0xffffffffu, in));
     }
     if (lane == 0) counts[g] = good;
   }
 }
 
-// Inlier flags of the winning model of every problem (found[b] == 0: all zero).
+// Inlier flags of the winning model of every problem; win_id[b] = hyp_id*3 + model slot or -1 (no
+// model: all flags 0).  Also gathers the winning models into win_F [B][9].
 __global__ void __launch_bounds__(256)
 fm_mask_kernel(int B, const int* __restrict__ off, const float4* __restrict__ pts,
-               const double* __restrict__ win_F, const int* __restrict__ found, float thr2,
-               uint8_t* __restrict__ mask) {
+               const double* __restrict__ models_all, const int* __restrict__ win_id, FmThresh th,
+               uint8_t* __restrict__ mask, double* __restrict__ win_F) {
   const int b = blockIdx.y;
   if (b >= B) return;
   const int i0 = off[b], i1 = off[b + 1];
+  const int w = win_id[b];
   double F[9];
 #pragma unroll
-  for (int i = 0; i < 9; i++) F[i] = win_F[(size_t)b * 9 + i];
-  const bool ok = found[b] != 0;
+  for (int i = 0; i < 9; i++) F[i] = w >= 0 ? models_all[(size_t)(w / 3) * 27 + 9 * (w % 3) + i] : 0.0;
+  if (blockIdx.x == 0 && threadIdx.x < 9) win_F[(size_t)b * 9 + threadIdx.x] = F[threadIdx.x];
   for (int i = i0 + blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += gridDim.x * blockDim.x)
-    mask[i] = (ok && fm_error(F, pts[i]) <= thr2) ? 1 : 0;
+    mask[i] = (w >= 0 && fm_inlier(F, pts[i], th)) ? 1 : 0;
 }
 
 }  // namespace
 
-cudaError_t launch_fm_solve(int n_hyp, const int* sets, const float4* pts, double* models, int* n_models,
-                            cudaStream_t s) {
+static FmThresh make_thresh(float t) {
+  // (float)x <= t  <=>  x <= midpoint(t, nextafterf(t, +inf)) up to the tie, which the exact path decides
+  const double tm = 0.5 * ((double)t + (double)nextafterf(t, INFINITY));
+  FmThresh th;
+  th.t = t;
+  th.lo = tm * (1.0 - 1e-12);
+  th.hi = tm * (1.0 + 1e-12);
+  return th;
+}
+
+cudaError_t launch_fm_solve(int n_hyp, const int* hyp_ids, const int* sets, const float4* pts, double* models_all,
+                            int* n_models, cudaStream_t s) {
   if (n_hyp <= 0) return cudaSuccess;
   const int threads = 256, per_cta = (threads / 32) * (32 / kFmLanes);
   const size_t smem = (size_t)per_cta * (63 + 81) * sizeof(double);
-  fm_solve_kernel<<<(n_hyp + per_cta - 1) / per_cta, threads, smem, s>>>(n_hyp, sets, pts, models, n_models);
+  fm_solve_kernel<<<(n_hyp + per_cta - 1) / per_cta, threads, smem, s>>>(n_hyp, hyp_ids, sets, pts, models_all, n_models);
   return cudaGetLastError();
 }
 
-cudaError_t launch_fm_score(int n_hyp, const int* hyp_prob, const int* off, const float4* pts,
-                            const double* models, const int* n_models, float thr2, int* counts, int n_sm,
+cudaError_t launch_fm_score(int n_hyp, const int* hyp_ids, int max_iters, const int* off, const float4* pts,
+                            const double* models_all, const int* n_models, float thr2, int* counts, int n_sm,
                             cudaStream_t s) {
   if (n_hyp <= 0) return cudaSuccess;
   const int threads = 256, wpc = threads / 32;
   long long blocks = ((long long)n_hyp * 3 + wpc - 1) / wpc;
   const long long cap = (long long)n_sm * 8;  // 8 resident CTAs of 256 threads per SM
   if (blocks > cap) blocks = cap;
-  fm_score_kernel<<<(unsigned)blocks, threads, 0, s>>>(n_hyp, hyp_prob, off, pts, models, n_models, thr2, counts);
+  fm_score_kernel<<<(unsigned)blocks, threads, 0, s>>>(n_hyp, hyp_ids, max_iters, off, pts, models_all, n_models,
+                                                       make_thresh(thr2), counts);
   return cudaGetLastError();
 }
 
-cudaError_t launch_fm_mask(int B, int max_n, const int* off, const float4* pts, const double* win_F,
-                           const int* found, float thr2, uint8_t* mask, cudaStream_t s) {
+cudaError_t launch_fm_mask(int B, int max_n, const int* off, const float4* pts, const double* models_all,
+                           const int* win_id, float thr2, uint8_t* mask, double* win_F, cudaStream_t s) {
   if (B <= 0 || max_n <= 0) return cudaSuccess;
   dim3 grid((unsigned)((max_n + 255) / 256), (unsigned)B);
-  fm_mask_kernel<<<grid, 256, 0, s>>>(B, off, pts, win_F, found, thr2, mask);
+  fm_mask_kernel<<<grid, 256, 0, s>>>(B, off, pts, models_all, win_id, make_thresh(thr2), mask, win_F);
   return cudaGetLastError();
 }
 

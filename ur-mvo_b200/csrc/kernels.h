@@ -78,13 +78,15 @@ struct TVBuffers {
 cudaError_t launch_tv_ransac(const TVBuffers& b, float sigma, int n_sm, cudaStream_t stream, int* n_launch);
 cudaError_t launch_tv_motion(const TVBuffers& b, float th2, cudaStream_t stream);
 
-// ---- fm_kernels.cu (per-frame fundamental-matrix RANSAC; pts = (x0,y0,x1,y1) per match)
-cudaError_t launch_fm_solve(int n_hyp, const int* sets, const float4* pts, double* models, int* n_models,
+// ---- fm_kernels.cu (per-frame fundamental-matrix RANSAC; pts = (x0,y0,x1,y1) per match).
+// One RANSAC round evaluates n_hyp hypotheses; hyp_ids[i] = problem * max_iters + iteration addresses
+// the persistent model store models_all [B*max_iters][27]; sets / n_models / counts are per round.
+cudaError_t launch_fm_solve(int n_hyp, const int* hyp_ids, const int* sets, const float4* pts, double* models_all,
+                            int* n_models, cudaStream_t s);
+cudaError_t launch_fm_score(int n_hyp, const int* hyp_ids, int max_iters, const int* off, const float4* pts,
+                            const double* models_all, const int* n_models, float thr2, int* counts, int n_sm,
                             cudaStream_t s);
-cudaError_t launch_fm_score(int n_hyp, const int* hyp_prob, const int* off, const float4* pts,
-                            const double* models, const int* n_models, float thr2, int* counts, int n_sm,
-                            cudaStream_t s);
-cudaError_t launch_fm_mask(int B, int max_n, const int* off, const float4* pts, const double* win_F,
-                           const int* found, float thr2, uint8_t* mask, cudaStream_t s);
+cudaError_t launch_fm_mask(int B, int max_n, const int* off, const float4* pts, const double* models_all,
+                           const int* win_id, float thr2, uint8_t* mask, double* win_F, cudaStream_t s);
 
 }  // namespace urmvo

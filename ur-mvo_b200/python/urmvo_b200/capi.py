@@ -240,10 +240,12 @@ class FMPlan:
         _check(self._L.urmvo_fm_plan_create(ctx._h, C.byref(self._h), C.c_int(self.B), _p(self.off), _p(p0), _p(p1),
                                             C.c_double(thresh), C.c_double(confidence), C.c_int(max_iters)),
                "urmvo_fm_plan_create")
-        self.hypotheses = int(self._L.urmvo_fm_plan_hypotheses(self._h))
+        self.hypotheses = 0  # RANSAC iterations evaluated by the last run()
 
     def run(self):
+        """All RANSAC rounds of every problem (kernels + the host replay of OpenCV's budget logic)."""
         _check(self._L.urmvo_fm_plan_run(self._h), "urmvo_fm_plan_run")
+        self.hypotheses = int(self._L.urmvo_fm_plan_hypotheses(self._h))
 
     def finish(self):
         mask = np.zeros(int(self.off[-1]), dtype=np.uint8)
