@@ -21,8 +21,8 @@
 //   findInliers (err <= (float)(thr*thr)), best = strictly more inliers, RANSACUpdateNumIters
 // Only the N >= 15 branch (FM_RANSAC) is restated: below 15 points OpenCV switches to LMedS, which
 // stays with the reference's own call.
-// The null space comes from a one-sided Jacobi SVD (fp64, cyclic pairs, own stopping rule) instead
-// of LAPACK: any basis of the null space gives the same <= 3 fundamental matrices.
+// The null space comes from a Householder QR of the transposed 7x9 system instead of the SVD OpenCV
+// calls (LAPACK): any basis of the null space gives the same <= 3 fundamental matrices.
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
@@ -135,63 +135,53 @@ int solve_cubic(const double* c, double* r) {
   return n;
 }
 
-// One-sided Jacobi on the 7x9 system: V (9x9) accumulates the column rotations; on exit the two
-// columns of A with the smallest norms are (numerically) zero and the same columns of V span the
-// null space.  Spec shared with the CUDA kernel (csrc/fm_kernels.cu): cyclic (p,q) order, rotate
-// when |gamma| > 1e-15 sqrt(alpha beta), columns with squared norm <= 1e-30 ||A||_F^2 are left
-// alone, at most 60 sweeps.  f1 = the null column with the larger index, f2 = the smaller.
+// Sum of 16 values in the order of a 16-lane xor-butterfly (what the CUDA kernel's shuffles do):
+// pairwise tree ((v0+v1)+(v2+v3))+... ; every lane of the butterfly ends with this same value.
+double tree16(const double* v) {
+  double a[16];
+  for (int i = 0; i < 16; i++) a[i] = v[i];
+  for (int w = 1; w < 16; w <<= 1)
+    for (int i = 0; i < 16; i += 2 * w) a[i] = a[i] + a[i + w];
+  return a[0];
+}
+
+// 2-D null space of the 7x9 system A (rows = equations): Householder QR of M = A^T (9x7),
+// Q = H_0 H_1 ... H_6, and the last two columns of Q span null(A).  f1 = Q e_8, f2 = Q e_7.
+// Spec shared with the CUDA kernel (csrc/fm_kernels.cu), operation by operation: reflector k uses
+// x = M[k.., k], sigma = tree16(x^2), norm = sqrt(sigma), alpha = -sign(x_k) norm, v = x - alpha e_k,
+// beta = 1 / (norm (norm + |x_k|)) (0 when norm == 0), M[:, j] -= (beta * tree16(v . M[:, j])) * v.
+// OpenCV takes the last two right singular vectors of an SVD instead; any basis of the null space
+// gives the same <= 3 fundamental matrices (tests/test_golden_fm.py pins the result against cv2).
 void null_space_7x9(double* A, double* f1, double* f2) {
-  double V[81];
-  for (int i = 0; i < 81; i++) V[i] = (i / 9 == i % 9) ? 1.0 : 0.0;
-  double fro2 = 0.0;
-  for (int r = 0; r < 7; r++) {
-    double row = 0.0;
-    for (int j = 0; j < 9; j++) row += A[r * 9 + j] * A[r * 9 + j];
-    fro2 += row;
+  double M[16][7];  // row r of A^T, rows 9..15 are the idle lanes (zero)
+  for (int r = 0; r < 16; r++)
+    for (int k = 0; k < 7; k++) M[r][k] = r < 9 ? A[k * 9 + r] : 0.0;
+  double V[7][16], beta[7];
+  for (int k = 0; k < 7; k++) {
+    double x[16], sq[16];
+    for (int r = 0; r < 16; r++) { x[r] = r >= k ? M[r][k] : 0.0; sq[r] = x[r] * x[r]; }
+    const double sigma = tree16(sq);
+    const double xkk = M[k][k];
+    const double norm = std::sqrt(sigma);
+    const double alpha = xkk >= 0.0 ? -norm : norm;
+    for (int r = 0; r < 16; r++) V[k][r] = r == k ? x[r] - alpha : x[r];
+    beta[k] = norm > 0.0 ? 1.0 / (norm * (norm + std::fabs(xkk))) : 0.0;
+    for (int j = k + 1; j < 7; j++) {
+      double pr[16];
+      for (int r = 0; r < 16; r++) pr[r] = V[k][r] * M[r][j];
+      const double w = beta[k] * tree16(pr);
+      for (int r = 0; r < 16; r++) M[r][j] = M[r][j] - w * V[k][r];
+    }
   }
-  const double tiny = 1e-30 * fro2;
-  for (int sweep = 0; sweep < 60; sweep++) {
-    bool rotated = false;
-    for (int p = 0; p < 8; p++)
-      for (int q = p + 1; q < 9; q++) {
-        double alpha = 0, beta = 0, gamma = 0;
-        for (int r = 0; r < 7; r++) {
-          const double ap = A[r * 9 + p], aq = A[r * 9 + q];
-          alpha += ap * ap; beta += aq * aq; gamma += ap * aq;
-        }
-        if (alpha <= tiny || beta <= tiny) continue;
-        if (std::fabs(gamma) <= 1e-15 * std::sqrt(alpha * beta)) continue;
-        rotated = true;
-        const double zeta = (beta - alpha) / (2.0 * gamma);
-        double t = 1.0 / (std::fabs(zeta) + std::sqrt(1.0 + zeta * zeta));
-        if (zeta < 0.0) t = -t;
-        const double c = 1.0 / std::sqrt(1.0 + t * t), s = c * t;
-        for (int r = 0; r < 7; r++) {
-          const double ap = A[r * 9 + p], aq = A[r * 9 + q];
-          A[r * 9 + p] = c * ap - s * aq;
-          A[r * 9 + q] = s * ap + c * aq;
-        }
-        for (int r = 0; r < 9; r++) {
-          const double vp = V[r * 9 + p], vq = V[r * 9 + q];
-          V[r * 9 + p] = c * vp - s * vq;
-          V[r * 9 + q] = s * vp + c * vq;
-        }
-      }
-    if (!rotated) break;
+  double y1[16], y2[16];
+  for (int r = 0; r < 16; r++) { y1[r] = r == 8 ? 1.0 : 0.0; y2[r] = r == 7 ? 1.0 : 0.0; }
+  for (int k = 6; k >= 0; k--) {
+    double p1[16], p2[16];
+    for (int r = 0; r < 16; r++) { p1[r] = V[k][r] * y1[r]; p2[r] = V[k][r] * y2[r]; }
+    const double w1 = beta[k] * tree16(p1), w2 = beta[k] * tree16(p2);
+    for (int r = 0; r < 16; r++) { y1[r] = y1[r] - w1 * V[k][r]; y2[r] = y2[r] - w2 * V[k][r]; }
   }
-  // the two smallest column norms (first index wins ties)
-  double nrm[9];
-  for (int j = 0; j < 9; j++) {
-    double s = 0.0;
-    for (int r = 0; r < 7; r++) s += A[r * 9 + j] * A[r * 9 + j];
-    nrm[j] = s;
-  }
-  int b0 = 0;
-  for (int j = 1; j < 9; j++) if (nrm[j] < nrm[b0]) b0 = j;
-  int b1 = b0 == 0 ? 1 : 0;
-  for (int j = 0; j < 9; j++) if (j != b0 && nrm[j] < nrm[b1]) b1 = j;
-  const int lo = std::min(b0, b1), hi = std::max(b0, b1);
-  for (int r = 0; r < 9; r++) { f1[r] = V[r * 9 + hi]; f2[r] = V[r * 9 + lo]; }
+  for (int r = 0; r < 9; r++) { f1[r] = y1[r]; f2[r] = y2[r]; }
 }
 
 // run7Point on the 7 selected correspondences; F: up to 3 row-major 3x3 matrices.

@@ -11,12 +11,12 @@
 //     sequential loop.
 // The device evaluates every iteration of the budget at once:
 //   fm_solve_kernel  16 lanes per iteration: run7Point (normalise, 7x9 system, 2-D null space by a
-//                    one-sided Jacobi SVD in fp64, cubic det = 0, <= 3 models)          [fp64 ALU]
+//                    Householder QR in fp64 registers, cubic det = 0, <= 3 models)      [fp64 latency]
 //   fm_score_kernel  one warp per (iteration, model): FMEstimatorCallback::computeError in fp64,
 //                    (float)err <= (float)thr^2, ballot/popc inlier count               [fp64 ALU]
 //   fm_mask_kernel   the winner's inlier flags
 // Arithmetic follows the CPU restatement fm_oracle.cpp operation by operation (same summation
-// order: ordered shuffle chains; this file is compiled with -fmad=false), so the models agree to the
+// order: ordered shuffle chains / 16-lane butterflies; this file is compiled with -fmad=false), so the models agree to the
 // last bits and the masks are identical; the oracle itself is pinned bit-for-bit against the real
 // cv2.findFundamentalMat (tests/golden/golden_fm_r01.npz).
 #include <cfloat>
@@ -28,15 +28,19 @@ namespace urmvo {
 namespace {
 
 constexpr int kFmLanes = 16;       // lanes per hypothesis in fm_solve_kernel
-constexpr int kFmSweeps = 60;
-constexpr double kFmTol = 1e-15;   // rotate when |gamma| > tol * sqrt(alpha beta)
-constexpr double kFmTiny = 1e-30;  // columns with squared norm <= tiny * ||A||_F^2 are left alone
 
 // sum over lanes 0..m-1 of the sub-warp, in lane order (the oracle's loop order)
 __device__ __forceinline__ double ordered_sum64(double v, int m, unsigned mask) {
   double s = __shfl_sync(mask, v, 0, kFmLanes);
   for (int k = 1; k < m; k++) s = s + __shfl_sync(mask, v, k, kFmLanes);
   return s;
+}
+
+// 16-lane xor butterfly: every lane ends with the pairwise-tree sum ((v0+v1)+(v2+v3))+...
+__device__ __forceinline__ double tree_sum16(double v, unsigned mask) {
+#pragma unroll
+  for (int w = 1; w < 16; w <<= 1) v = v + __shfl_xor_sync(mask, v, w, kFmLanes);
+  return v;
 }
 
 // cv::solveCubic (c[0] x^3 + c[1] x^2 + c[2] x + c[3] = 0); returns the number of roots, -1: any x
@@ -112,7 +116,7 @@ __global__ void __launch_bounds__(256)
 fm_solve_kernel(int n_hyp, const int* __restrict__ hyp_ids, const int* __restrict__ sets,
                 const float4* __restrict__ pts, double* __restrict__ models_all, int* __restrict__ n_models) {
   constexpr int PER_WARP = 32 / kFmLanes;
-  constexpr int DL = 7 * 9 + 81;  // doubles per hypothesis
+  constexpr int DL = 7 * 9;  // doubles per hypothesis: the 7x9 system, later the two null vectors
   extern __shared__ double sm_fm[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int sub = lane / kFmLanes, r = lane - sub * kFmLanes;
@@ -120,7 +124,6 @@ fm_solve_kernel(int n_hyp, const int* __restrict__ hyp_ids, const int* __restric
   const int hyp = (blockIdx.x * (blockDim.x >> 5) + wid) * PER_WARP + sub;
   if (hyp >= n_hyp) return;  // whole sub-warps leave together
   double* A = sm_fm + (size_t)(wid * PER_WARP + sub) * DL;
-  double* V = A + 63;
   // ---- run7Point: normalisation (centroid, mean distance) in the oracle's summation order
   float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
   if (r < 7) m = pts[sets[(size_t)hyp * 7 + r]];
@@ -143,62 +146,45 @@ fm_solve_kernel(int n_hyp, const int* __restrict__ hyp_ids, const int* __restric
     a[3] = y1 * x0; a[4] = y1 * y0; a[5] = y1;
     a[6] = x0; a[7] = y0; a[8] = 1;
   }
-  for (int e = r; e < 81; e += kFmLanes) V[e] = (e / 9 == e % 9) ? 1.0 : 0.0;
   __syncwarp(mask);
-  // ---- 2-D null space: one-sided Jacobi on the 7x9 system (lane r < 7 owns row r of A, lane r < 9
-  // row r of V); spec in the CPU restatement fm_oracle.cpp null_space_7x9
-  double tiny;
-  {
-    double row = 0.0;
-    if (r < 7)
-      for (int j = 0; j < 9; j++) row += A[r * 9 + j] * A[r * 9 + j];
-    tiny = kFmTiny * ordered_sum64(row, 7, mask);
-  }
-  for (int sweep = 0; sweep < kFmSweeps; sweep++) {
-    bool rotated = false;
-    for (int p = 0; p < 8; p++) {
-      for (int q = p + 1; q < 9; q++) {
-        const double ap = r < 7 ? A[r * 9 + p] : 0.0, aq = r < 7 ? A[r * 9 + q] : 0.0;
-        const double alpha = ordered_sum64(ap * ap, 7, mask);
-        const double beta = ordered_sum64(aq * aq, 7, mask);
-        const double gamma = ordered_sum64(ap * aq, 7, mask);
-        if (alpha <= tiny || beta <= tiny) continue;
-        if (fabs(gamma) <= kFmTol * sqrt(alpha * beta)) continue;
-        rotated = true;
-        const double zeta = (beta - alpha) / (2.0 * gamma);
-        double tt = 1.0 / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-        if (zeta < 0.0) tt = -tt;
-        const double c = 1.0 / sqrt(1.0 + tt * tt), s = c * tt;
-        if (r < 7) {
-          A[r * 9 + p] = c * ap - s * aq;
-          A[r * 9 + q] = s * ap + c * aq;
-        }
-        if (r < 9) {
-          const double vp = V[r * 9 + p], vq = V[r * 9 + q];
-          V[r * 9 + p] = c * vp - s * vq;
-          V[r * 9 + q] = s * vp + c * vq;
-        }
-      }
+  // ---- 2-D null space: Householder QR of M = A^T (9x7).  Lane r holds row r of M (lanes >= 9:
+  // zeros); reflector k: sigma = sum x^2 over rows >= k (16-lane xor butterfly), alpha = -sign(x_k)
+  // sqrt(sigma), v = x - alpha e_k, beta = 1/(norm (norm + |x_k|)); the last two columns of
+  // Q = H_0 ... H_6 span the null space (f1 = Q e_8, f2 = Q e_7).  Spec: fm_oracle.cpp null_space_7x9.
+  double mrow[7], vk[7], bk[7];
+#pragma unroll
+  for (int k = 0; k < 7; k++) mrow[k] = r < 9 ? A[k * 9 + r] : 0.0;
+#pragma unroll
+  for (int k = 0; k < 7; k++) {
+    const double x = r >= k ? mrow[k] : 0.0;
+    const double sigma = tree_sum16(x * x, mask);
+    const double xkk = __shfl_sync(mask, mrow[k], k, kFmLanes);
+    const double norm = sqrt(sigma);
+    const double alpha = xkk >= 0.0 ? -norm : norm;
+    const double v = r == k ? x - alpha : x;
+    const double beta = norm > 0.0 ? 1.0 / (norm * (norm + fabs(xkk))) : 0.0;
+    vk[k] = v;
+    bk[k] = beta;
+#pragma unroll
+    for (int j = k + 1; j < 7; j++) {
+      const double w = beta * tree_sum16(v * mrow[j], mask);
+      mrow[j] = mrow[j] - w * v;
     }
-    if (!rotated) break;
+  }
+  double y1 = r == 8 ? 1.0 : 0.0, y2 = r == 7 ? 1.0 : 0.0;
+#pragma unroll
+  for (int k = 6; k >= 0; k--) {
+    const double w1 = bk[k] * tree_sum16(vk[k] * y1, mask);
+    const double w2 = bk[k] * tree_sum16(vk[k] * y2, mask);
+    y1 = y1 - w1 * vk[k];
+    y2 = y2 - w2 * vk[k];
   }
   __syncwarp(mask);
-  // the two smallest column norms (first index wins ties); f1 = larger column index, f2 = smaller
-  int b0 = 0, b1 = 1;
-  {
-    double nrm[9];
-    for (int j = 0; j < 9; j++) {
-      const double a = r < 7 ? A[r * 9 + j] : 0.0;
-      nrm[j] = ordered_sum64(a * a, 7, mask);
-    }
-    for (int j = 1; j < 9; j++) if (nrm[j] < nrm[b0]) b0 = j;
-    b1 = b0 == 0 ? 1 : 0;
-    for (int j = 0; j < 9; j++) if (j != b0 && nrm[j] < nrm[b1]) b1 = j;
-  }
+  if (r < 9) { A[r] = y1; A[9 + r] = y2; }  // the staging area is free now
+  __syncwarp(mask);
   if (r != 0) return;
-  const int lo = b0 < b1 ? b0 : b1, hi = b0 < b1 ? b1 : b0;
   double f1[9], f2[9];
-  for (int k = 0; k < 9; k++) { f1[k] = V[k * 9 + hi]; f2[k] = V[k * 9 + lo]; }
+  for (int k = 0; k < 9; k++) { f1[k] = A[k]; f2[k] = A[9 + k]; }
   for (int k = 0; k < 9; k++) f1[k] -= f2[k];
   double c[4], roots[3];
   double t0 = f2[4] * f2[8] - f2[5] * f2[7], t1 = f2[3] * f2[8] - f2[5] * f2[6], t2 = f2[3] * f2[7] - f2[4] * f2[6];
@@ -357,7 +343,7 @@ cudaError_t launch_fm_solve(int n_hyp, const int* hyp_ids, const int* sets, cons
                             int* n_models, cudaStream_t s) {
   if (n_hyp <= 0) return cudaSuccess;
   const int threads = 256, per_cta = (threads / 32) * (32 / kFmLanes);
-  const size_t smem = (size_t)per_cta * (63 + 81) * sizeof(double);
+  const size_t smem = (size_t)per_cta * 63 * sizeof(double);
   fm_solve_kernel<<<(n_hyp + per_cta - 1) / per_cta, threads, smem, s>>>(n_hyp, hyp_ids, sets, pts, models_all, n_models);
   return cudaGetLastError();
 }
