@@ -1048,6 +1048,7 @@ __device__ void lin_phase_packed(const Scope& sc, const BAWin& W, int cur, doubl
     bsj[nb] = has[nb] ? bcj[nb] : 0;
   }
   const int bcol = lane & (kPackCam - 1);  // camera column of the b_s / b_p accumulation (lanes < 16)
+  const bool diag_lane = NB == 1 && has[0] && bci[0] == bcj[0];
 
   // software pipeline: the record of the NEXT group is fetched (one level of loads) while the
   // current group is processed, so the L2 round trip overlaps the arithmetic
@@ -1171,12 +1172,15 @@ __device__ void lin_phase_packed(const Scope& sc, const BAWin& W, int cur, doubl
     __syncwarp();
     // S-stationary accumulation: for every point of the group, the lane's camera pair(s).  The slot
     // bytes of point q+1 are fetched while point q is processed.
-    int nsi[NB], nsj[NB], nsb;
+    // NB == 1: the lane that owns the DIAGONAL block (ci, ci) also accumulates b_s / b_p of camera
+    // ci — it already holds J_ci of the point in registers for its block, so the gradients cost no
+    // extra shared-memory traffic.  NB == 2 keeps the camera = lane layout for the gradients.
+    int nsi[NB], nsj[NB], nsb = kPackZero;
     {
       const signed char* sl = st.slot;
 #pragma unroll
       for (int nb = 0; nb < NB; nb++) { nsi[nb] = sl[bsi[nb]]; nsj[nb] = sl[bsj[nb]]; }
-      nsb = sl[bcol];
+      if (NB > 1) nsb = sl[bcol];
     }
     for (int q = 0; q < np; q++) {
       int csi[NB], csj[NB];
@@ -1187,7 +1191,7 @@ __device__ void lin_phase_packed(const Scope& sc, const BAWin& W, int cur, doubl
         const signed char* sl = st.slot + (q + 1 < 32 ? q + 1 : 31) * kPackCam;
 #pragma unroll
         for (int nb = 0; nb < NB; nb++) { nsi[nb] = sl[bsi[nb]]; nsj[nb] = sl[bsj[nb]]; }
-        nsb = sl[bcol];
+        if (NB > 1) nsb = sl[bcol];
       }
 #pragma unroll
       for (int nb = 0; nb < NB; nb++) {
@@ -1212,15 +1216,23 @@ __device__ void lin_phase_packed(const Scope& sc, const BAWin& W, int cur, doubl
           T[b] = M[0] * j0 + M[1] * j1;
           T[6 + b] = M[2] * j0 + M[3] * j1;
         }
+        // gradient terms ride on the diagonal lane (NB == 1): slot si when the block is diagonal
+        const int sg = (NB == 1 && diag_lane) ? si : kPackZero;
+        double g0 = 0.0, g1 = 0.0, w0 = 0.0, w1 = 0.0;
+        if (NB == 1) { g0 = st.g(0, sg); g1 = st.g(1, sg); w0 = st.we(0, sg); w1 = st.we(1, sg); }
 #pragma unroll
         for (int a = 0; a < 6; a++) {
           const double j0 = st.Jp(a, si), j1 = st.Jp(6 + a, si);
 #pragma unroll
           for (int b = 0; b < 6; b++)  // two chained FMAs per element (not mul + fma + add)
             accS[nb][a * 6 + b] = fma(j1, T[6 + b], fma(j0, T[b], accS[nb][a * 6 + b]));
+          if (NB == 1) {
+            accb[a] = fma(-j1, g1, fma(-j0, g0, accb[a]));
+            accb[6 + a] = fma(-j1, w1, fma(-j0, w0, accb[6 + a]));
+          }
         }
       }
-      {
+      if (NB > 1) {
         const int s = lane < kPackCam ? csb : kPackZero;
         const double g0 = st.g(0, s), g1 = st.g(1, s), w0 = st.we(0, s), w1 = st.we(1, s);
 #pragma unroll
@@ -1252,11 +1264,12 @@ __device__ void lin_phase_packed(const Scope& sc, const BAWin& W, int cur, doubl
       for (int e = 0; e < 36; e++) acc[(size_t)blk * 36 + e] = accS[nb][e];
     }
   }
-  if (lane < W.Ncf) {
+  if (NB == 1 ? diag_lane : lane < W.Ncf) {
+    const int cb = NB == 1 ? bci[0] : lane;  // camera whose gradients this lane holds
 #pragma unroll
     for (int a = 0; a < 6; a++) {
-      acc[(size_t)W.nblk * 36 + lane * 6 + a] = accb[a];
-      acc[(size_t)W.nblk * 36 + W.Ncf * 6 + lane * 6 + a] = accb[6 + a];
+      acc[(size_t)W.nblk * 36 + cb * 6 + a] = accb[a];
+      acc[(size_t)W.nblk * 36 + W.Ncf * 6 + cb * 6 + a] = accb[6 + a];
     }
   }
   cta_reduce_copies(sc, W, wa, 0, W.acc_len);
