@@ -1299,22 +1299,53 @@ __device__ void backsub_phase_packed(const Scope& sc, const BAWin& W, int cur, d
   double* const xs = st.f;
   for (int e = lane; e < W.Ncf * 6; e += 32) xs[e] = __ldcg(xp + e);
   __syncwarp();
-  if (gw < n_grp) rec_prefetch(rbuf, rec, gw, lane);
-  for (int g = gw; g < n_grp; g += gstride) {
-    const RecRegs rr = rec_take(rbuf, lane);
+  // Pipeline: record one group ahead (32 B per lane), its point index two groups ahead (4 B per lane,
+  // into the slot-table area, which BACKSUB does not use) so that the point position X of the NEXT
+  // group — the operand every lane needs first — can be copied into shared memory (free Jp fields)
+  // while the current group is processed.  No shared memory is added: L1 capacity matters here.
+  int* const plbuf = reinterpret_cast<int*>(st.slot);      // [2][32]
+  double* const xb = st.f + 4 * kPackSlots + lane * 3;      // fields 4.. are free in BACKSUB
+  auto pl_prefetch = [&](int par, int g2) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(plbuf + par * 32 + lane);
+    const size_t src = __cvta_generic_to_global(&rec[(size_t)g2 * 32 + lane].pl);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+  };
+  auto x_prefetch = [&](int npl) {
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(xb + a);
+      const size_t src = __cvta_generic_to_global(pts_cur + npl * 3 + a);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+    }
+  };
+  int par = 0;
+  if (gw < n_grp) {
+    rec_prefetch(rbuf, rec, gw, lane);
+    pl_prefetch(0, gw);
+    if (gw + gstride < n_grp) pl_prefetch(1, gw + gstride);
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    x_prefetch(plbuf[lane]);
+  }
+  for (int g = gw; g < n_grp; g += gstride, par ^= 1) {
+    const RecRegs rr = rec_take(rbuf, lane);  // waits for every outstanding copy
+    const double X[3] = {xb[0], xb[1], xb[2]};
+    const int npl = plbuf[(par ^ 1) * 32 + lane];
     const double2 uv = make_double2(__hiloint2double(rr.a.y, rr.a.x), __hiloint2double(rr.a.w, rr.a.z));
     const int pl = rr.b.x, c = rr.b.y;
     const int s0 = rr.b.z & 255, s1 = (rr.b.z >> 8) & 255;
     const int cf_ld = rr.b.z >> 24;
     const bool valid = (rr.b.w >> 16) & 1;
     const bool active = valid && !((rr.b.w >> 8) & 255);
-    const double X[3] = {pts_cur[pl * 3], pts_cur[pl * 3 + 1], pts_cur[pl * 3 + 2]};
+    if (g + gstride < n_grp) {
+      rec_prefetch(rbuf, rec, g + gstride, lane);
+      x_prefetch(npl);
+      if (g + 2 * gstride < n_grp) pl_prefetch(par, g + 2 * gstride);
+    }
     double Di[6], bb[3];
 #pragma unroll
     for (int a = 0; a < 6; a++) Di[a] = Dinv_in[(size_t)pl * 6 + a];
 #pragma unroll
     for (int a = 0; a < 3; a++) bb[a] = bl_in[(size_t)pl * 3 + a];
-    if (g + gstride < n_grp) rec_prefetch(rbuf, rec, g + gstride, lane);
     double c3[3] = {0, 0, 0};
     if (active) {
       const int cf = cf_ld;
