@@ -17,6 +17,7 @@ if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
 which = sys.argv[1] if len(sys.argv) > 1 else "small"
 check = "--check" in sys.argv
+tol = float([a for a in sys.argv if a.startswith("--tol=")][0][6:]) if any(a.startswith("--tol=") for a in sys.argv) else 0.0
 if which == "small":
     prob = synth.make_ba(77, 40, 3000, 9.0, 14, 2, 0.02)
 elif which == "cfg5":
@@ -34,7 +35,7 @@ cov = torch.from_numpy(U.ba_covisibility(loc).astype(np.int32)).cuda()
 if world > 1:
     dist.all_reduce(cov, op=dist.ReduceOp.MAX)
 cov = cov.cpu().numpy().astype(np.uint8)
-plan = U.ShardedBAPlan(ctx, loc, covis=cov)
+plan = U.ShardedBAPlan(ctx, loc, covis=cov, opts=U.BAOptions(tol, 0, 0, 0, 0) if tol > 0 else None)
 plan.run()  # warm-up
 if world > 1: dist.barrier()
 torch.cuda.synchronize(); t0 = time.perf_counter()

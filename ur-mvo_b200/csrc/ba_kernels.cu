@@ -630,7 +630,7 @@ __device__ bool pcg_phase(const Scope& sc, const BAWin& W, double tol, int max_i
 // Writes x_p and the summed raw gradient b_p to global memory for the other CTAs.
 template <class Scope>
 __device__ bool pcg_dense_smem(const Scope& sc, const BAWin& W, double lambda, double tol, int max_iter,
-                               double* sm, int& iters_out) {
+                               bool use_pcg, double* sm, int& iters_out) {
   const int n = W.Ncf * 6, nb = sc.nblk();
   const int tid = threadIdx.x;
   const int C = max(1, (int)blockDim.x / max(n, 1));  // column chunks
@@ -647,15 +647,19 @@ __device__ bool pcg_dense_smem(const Scope& sc, const BAWin& W, double lambda, d
   __shared__ double s_red[8];
   iters_out = 0;
   if (n == 0) return true;
+  // the descriptor lives in global memory: take the fields used per element into registers once
+  const double* __restrict__ Spart = W.Spart;
+  double* __restrict__ bp_out = W.bp;
+  const int acc_len = W.acc_len, Ncf = W.Ncf;
   const int n_s = W.nblk * 36;
   for (int e = tid; e < n_s; e += blockDim.x) {
     double v = 0.0;
-    for (int b = 0; b < nb; b++) v += __ldcg(W.Spart + (size_t)b * W.acc_len + e);
+    for (int b = 0; b < nb; b++) v += __ldcg(Spart + (size_t)b * acc_len + e);
     const int blk = e / 36, ab = e - blk * 36, a = ab / 6, c = ab - a * 6;
-    // dense upper layout: block index -> (ci, cj)
-    int ci = 0;
-    while (W.row_ptr[ci + 1] <= blk) ci++;
-    const int cj = ci + (blk - W.row_ptr[ci]);
+    // dense upper layout (<= 16 free cameras): row ci starts at ci*Ncf - ci(ci-1)/2
+    int ci = 0, start = 0;
+    while (start + (Ncf - ci) <= blk) { start += Ncf - ci; ci++; }
+    const int cj = ci + (blk - start);
     const int r = ci * 6 + a, q = cj * 6 + c;
     if (ci == cj) {
       if (a <= c) {  // the diagonal block is taken from its upper triangle
@@ -670,11 +674,44 @@ __device__ bool pcg_dense_smem(const Scope& sc, const BAWin& W, double lambda, d
   }
   for (int e = tid; e < 2 * n; e += blockDim.x) {
     double v = 0.0;
-    for (int b = 0; b < nb; b++) v += __ldcg(W.Spart + (size_t)b * W.acc_len + n_s + e);
-    if (e < n) bsv[e] = v; else __stcg(W.bp + (e - n), v);
+    for (int b = 0; b < nb; b++) v += __ldcg(Spart + (size_t)b * acc_len + n_s + e);
+    if (e < n) bsv[e] = v; else __stcg(bp_out + (e - n), v);
   }
   if (tid == 0) s_ok = 1;
   __syncthreads();
+  if (!use_pcg) {
+    // Direct solve (default): symmetric Gaussian elimination S = L D L^T on the lower triangle with
+    // the right-hand side carried along as an extra column, then back substitution — the exact
+    // solve g2o's LinearSolverEigen performs, one CTA barrier per pivot.  A non-positive pivot
+    // fails the solve like a failed Cholesky does in g2o.
+    double* invd = pv;  // 1 / d_k
+    const int tx = tid & 15, ty = tid >> 4, ny = blockDim.x >> 4;
+    bool ok = true;
+    for (int k = 0; k < n; k++) {
+      const double d = Sd[k * n + k];
+      if (!(d > 0.0)) { ok = false; break; }  // uniform: every thread reads the same pivot
+      const double inv = 1.0 / d;
+      if (tid == 0) invd[k] = inv;
+      const double bk = bsv[k];
+      for (int i = k + 1 + ty; i < n; i += ny) {
+        const double lik = Sd[i * n + k] * inv;
+        for (int j = k + 1 + tx; j <= i; j += 16) Sd[i * n + j] -= lik * Sd[j * n + k];
+        if (tx == 0) bsv[i] -= lik * bk;
+      }
+      __syncthreads();
+    }
+    if (ok) {
+      for (int k = n - 1; k >= 0; k--) {
+        const double xk = bsv[k] * invd[k];  // final: every update of row k has been applied
+        for (int i = tid; i < k; i += blockDim.x) bsv[i] -= Sd[k * n + i] * xk;
+        if (tid == 0) xv[k] = xk;
+        __syncthreads();
+      }
+    }
+    for (int i = tid; i < n; i += blockDim.x) __stcg(W.xp + i, ok ? xv[i] : 0.0);
+    __syncthreads();
+    return ok;
+  }
   // block-Jacobi preconditioner: 6x6 Cholesky by one thread per camera, then the six columns of
   // the inverse by six threads per camera
   double* Lf = prt;  // Ncf x 36 scratch for the factors (prt is free until the first product)
@@ -1526,7 +1563,7 @@ __device__ LMResult lm_optimize(const Scope& sc, const BAWin& W, const BARun& ru
       const long long _tp = clock64();
       if (SMEM) {
         if (sc.blk() == 0) {
-          ok2 = pcg_dense_smem(sc, W, lambda, run.pcg_tol, run.pcg_max_iter, pcg_sm, pcg_it);
+          ok2 = pcg_dense_smem(sc, W, lambda, run.pcg_tol, run.pcg_max_iter, run.dense_pcg != 0, pcg_sm, pcg_it);
           if (threadIdx.x == 0) { __stcg(flags, ok2 ? 1.0 : 0.0); __stcg(flags + 1, (double)pcg_it); }
         }
         sc.sync();

@@ -30,7 +30,7 @@ class FMStats(C.Structure):
 
 class BAOptions(C.Structure):
     _fields_ = [("pcg_tol", C.c_double), ("pcg_max_iter", C.c_int32), ("cluster_size", C.c_int32),
-                ("threads", C.c_int32), ("force_atomic", C.c_int32)]
+                ("threads", C.c_int32), ("force_atomic", C.c_int32), ("dense_solver", C.c_int32)]
 
 
 class BAStats(C.Structure):
