@@ -60,8 +60,8 @@ typedef struct {
   int32_t threads;       /* threads per CTA; 0 -> auto */
   int32_t force_atomic;  /* 1: always accumulate S with global fp64 atomics (default: shared-memory copies when they fit) */
   int32_t dense_solver;  /* windows whose reduced camera system is solved in shared memory (<= 16 free cameras):
-                            0 -> direct LDL^T factorisation (what g2o's LinearSolverEigen does, exact),
-                            1 -> block-Jacobi PCG like the large systems */
+                            0 -> block-Jacobi PCG (default, the same solver as the large systems),
+                            1 -> direct LDL^T factorisation (what g2o's LinearSolverEigen does; same speed) */
 } urmvo_ba_options;
 
 typedef struct {

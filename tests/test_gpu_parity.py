@@ -375,11 +375,11 @@ def test_ba_batch_of_full_size_windows_matches_single_solves(oracle, ctx):
 
 
 def test_ba_dense_solver_ldlt_and_pcg_agree(ctx, oracle):
-    """The in-shared-memory reduced camera system: direct LDL^T (default) and block-Jacobi PCG
+    """The in-shared-memory reduced camera system: block-Jacobi PCG (default) and the direct LDL^T
     (dense_solver = 1) both meet the parity bar; the direct solve reports no PCG iterations."""
     prob = synth.cfg1()
-    gs0, _ = _check_ba(oracle, ctx, prob, opts=U.BAOptions(0, 0, 0, 0, 0, 0))
-    gs1, _ = _check_ba(oracle, ctx, prob, opts=U.BAOptions(0, 0, 0, 0, 0, 1))
+    gs0, _ = _check_ba(oracle, ctx, prob, opts=U.BAOptions(0, 0, 0, 0, 0, 1))
+    gs1, _ = _check_ba(oracle, ctx, prob, opts=U.BAOptions(0, 0, 0, 0, 0, 0))
     assert gs0.pcg_iters[0] == 0 and gs0.pcg_iters[1] == 0
     assert gs1.pcg_iters[0] > 0
     assert list(gs0.trials) == list(gs1.trials)

@@ -680,7 +680,7 @@ __device__ bool pcg_dense_smem(const Scope& sc, const BAWin& W, double lambda, d
   if (tid == 0) s_ok = 1;
   __syncthreads();
   if (!use_pcg) {
-    // Direct solve (default): symmetric Gaussian elimination S = L D L^T on the lower triangle with
+    // Direct solve (urmvo_ba_options.dense_solver = 1): symmetric Gaussian elimination S = L D L^T on the lower triangle with
     // the right-hand side carried along as an extra column, then back substitution — the exact
     // solve g2o's LinearSolverEigen performs, one CTA barrier per pivot.  A non-positive pivot
     // fails the solve like a failed Cholesky does in g2o.

@@ -83,7 +83,7 @@ struct BARun {
   int pcg_max_iter;
   int it0, it1;
   int n_win;
-  int dense_pcg;       // 1: block-Jacobi PCG for the in-shared-memory systems too (default: LDL^T)
+  int dense_pcg;       // 1 (default): block-Jacobi PCG for the in-shared-memory systems, 0: direct LDL^T
   const void* timing_stats;  // the window whose stats pointer equals this records phase cycles
 };
 
