@@ -249,6 +249,7 @@ __device__ void lin_phase(const Scope& sc, const BAWin& W, int cur, double lambd
     for (int a = 0; a < 6; a++) h[a] = warp_sum(h[a]);
     if (DIAG) {
       maxdiag_acc = fmax(maxdiag_acc, fmax(fabs(h[0]), fmax(fabs(h[3]), fabs(h[5]))));
+      if (SMEM) __syncwarp();  // the next point's lanes add into the same warp copy (racecheck)
       continue;
     }
 #pragma unroll
