@@ -12,7 +12,7 @@
 // threshold 5e-7, <= 30 sweeps) — see DESIGN.md §6.
 //
 //   tv_normalize_kernel   one CTA per image; the running sums are sequential like the reference's
-//   tv_fit_kernel         one thread per (model, hypothesis): 8-point DLT + Jacobi SVD
+//   tv_fit_sub_kernel     8 (F) / 16 (H) lanes per hypothesis: 8-point DLT + Jacobi SVD, lane = row
 //   tv_score_kernel       one warp per (model, hypothesis): lanes stride over the matches,
 //                         __ballot_sync builds the inlier mask words, the score is accumulated in
 //                         match order (the reference's summation order) by a lane-ordered chain
@@ -301,72 +301,10 @@ __global__ void tv_gather_kernel(int N, const int* __restrict__ m1, const int* _
 
 // ------------------------------------------------------------------------------- model fitting
 
-// Thread t < n_hyp fits F for hypothesis t; thread n_hyp + t fits H.  models: [2][n_hyp][18]
-// (F: 9 used; H: H21 | H12).
-__global__ void __launch_bounds__(64)
-tv_fit_kernel(int n_hyp, const int* __restrict__ sets, const float4* __restrict__ pnm,
-              const float* __restrict__ T1, const float* __restrict__ T2, float* __restrict__ models) {
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= 2 * n_hyp) return;
-  const int model = g / n_hyp, hyp = g - model * n_hyp;
-  const int* set = sets + (size_t)hyp * 8;
-  float t1[9], t2[9];
-  for (int i = 0; i < 9; i++) { t1[i] = T1[i]; t2[i] = T2[i]; }
-  float* out = models + ((size_t)model * n_hyp + hyp) * 18;
-  if (model == 0) {
-    float A[8 * 9];
-    for (int j = 0; j < 8; j++) {
-      const float4 m = pnm[set[j]];
-      const float u1 = m.x, v1 = m.y, u2 = m.z, v2 = m.w;
-      float* r = A + j * 9;
-      r[0] = u2 * u1; r[1] = u2 * v1; r[2] = u2;
-      r[3] = v2 * u1; r[4] = v2 * v1; r[5] = v2;
-      r[6] = u1; r[7] = v1; r[8] = 1.0f;
-    }
-    float Fpre[9];
-    null_vector(8, 9, A, Fpre);
-    float U[9], w[3], V[9];
-    svd3(Fpre, U, w, V);
-    w[2] = 0.0f;
-    float Fn[9];
-    for (int i = 0; i < 3; i++)
-      for (int j = 0; j < 3; j++)
-        Fn[i * 3 + j] = (U[i * 3] * w[0]) * V[j * 3] + (U[i * 3 + 1] * w[1]) * V[j * 3 + 1] +
-                        (U[i * 3 + 2] * w[2]) * V[j * 3 + 2];
-    float T2t[9], tmp[9], F21[9];
-    mat3_T(t2, T2t);
-    mat3_mul(T2t, Fn, tmp);
-    mat3_mul(tmp, t1, F21);
-    for (int i = 0; i < 9; i++) { out[i] = F21[i]; out[9 + i] = 0.0f; }
-  } else {
-    float A[16 * 9];
-    for (int j = 0; j < 8; j++) {
-      const float4 m = pnm[set[j]];
-      const float u1 = m.x, v1 = m.y, u2 = m.z, v2 = m.w;
-      float* r0 = A + (2 * j) * 9;
-      float* r1 = A + (2 * j + 1) * 9;
-      r0[0] = 0.0f; r0[1] = 0.0f; r0[2] = 0.0f;
-      r0[3] = -u1; r0[4] = -v1; r0[5] = -1.0f;
-      r0[6] = v2 * u1; r0[7] = v2 * v1; r0[8] = v2;
-      r1[0] = u1; r1[1] = v1; r1[2] = 1.0f;
-      r1[3] = 0.0f; r1[4] = 0.0f; r1[5] = 0.0f;
-      r1[6] = -u2 * u1; r1[7] = -u2 * v1; r1[8] = -u2;
-    }
-    float Hn[9];
-    null_vector(16, 9, A, Hn);
-    float T2inv[9], tmp[9], H21[9], H12[9];
-    inv3f(t2, T2inv);
-    mat3_mul(T2inv, Hn, tmp);
-    mat3_mul(tmp, t1, H21);
-    inv3f(H21, H12);
-    for (int i = 0; i < 9; i++) { out[i] = H21[i]; out[9 + i] = H12[i]; }
-  }
-}
-
 // ------------------------------------------------------------------------------- cooperative fit
 //
-// tv_fit_kernel above keeps one thread per hypothesis (matrices in local memory, ~3.5 warps per SM
-// for 16384 hypotheses: latency-bound).  tv_fit_sub_kernel gives every hypothesis a SUB-WARP of
+// The first version kept one thread per hypothesis (matrices in local memory, ~3.5 warps per SM for
+// 16384 hypotheses: latency-bound, profiles/README.md).  tv_fit_sub_kernel gives every hypothesis a SUB-WARP of
 // L = M lanes (8 for the 8x9 fundamental system, 16 for the 16x9 homography system): lane k owns
 // row k of A (and row k of V), the matrices live in shared memory, the three column dot products
 // of a Jacobi pair are formed as per-lane products followed by an ORDERED chain of adds over the
