@@ -96,7 +96,12 @@ __device__ __forceinline__ bool solve6(const double* Hp, const double* b, double
 }  // namespace
 
 // level: per-observation scratch (0 active / 1 excluded).  inlier: in/out flags.
-__global__ void __launch_bounds__(256)
+// MINB = CTAs per SM the register allocation is capped for: 1 keeps everything in registers (172) and
+// is fastest when the batch fits one wave (B <= #SMs, and for single-frame latency); 2 caps at 128
+// registers (a few spills) so that a batch of up to 2 x #SMs frames is resident at once instead of
+// running a second, partly empty wave — +34 % on 256 frames.
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB)
 pose_only_kernel(int B, const int* __restrict__ obs_off, const double* __restrict__ pose_in,
                  const double* __restrict__ uv, const double* __restrict__ Xw, double fx, double fy,
                  double cx, double cy, double chi2_thr, double delta, int rounds, int its_per_round,
@@ -266,9 +271,17 @@ cudaError_t launch_pose_only(int B, const int* obs_off, const double* pose_in, c
                              int rounds, int its_per_round, uint8_t* inlier, uint8_t* level,
                              double* pose_out, int* n_inlier, int* lm_iters, cudaStream_t stream) {
   if (B <= 0) return cudaSuccess;
-  pose_only_kernel<<<B, 256, 0, stream>>>(B, obs_off, pose_in, uv, Xw, intr[0], intr[1], intr[2], intr[3],
-                                          chi2_thr, delta, rounds, its_per_round, inlier, level,
-                                          pose_out, n_inlier, lm_iters);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (B > sms)
+    pose_only_kernel<2><<<B, 256, 0, stream>>>(B, obs_off, pose_in, uv, Xw, intr[0], intr[1], intr[2], intr[3],
+                                               chi2_thr, delta, rounds, its_per_round, inlier, level,
+                                               pose_out, n_inlier, lm_iters);
+  else
+    pose_only_kernel<1><<<B, 256, 0, stream>>>(B, obs_off, pose_in, uv, Xw, intr[0], intr[1], intr[2], intr[3],
+                                               chi2_thr, delta, rounds, its_per_round, inlier, level,
+                                               pose_out, n_inlier, lm_iters);
   return cudaGetLastError();
 }
 
