@@ -229,6 +229,10 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank)
         return
+    # one process per GPU shares the host: give every rank its share of the cores for the host side
+    # of the C ABI (window flattening, subset drawing) instead of oversubscribing them N times
+    if world > 1 and "URMVO_B200_HOST_THREADS" not in os.environ:
+        os.environ["URMVO_B200_HOST_THREADS"] = str(max(2, (os.cpu_count() or 2) // world))
 
     import torch
     import torch.distributed as dist

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <atomic>
 #include <string>
@@ -76,6 +77,16 @@ struct Arena {
 
 }  // namespace
 
+
+int urmvo::host_threads() {
+  static const int n = [] {
+    const char* e = std::getenv("URMVO_B200_HOST_THREADS");
+    int v = e ? std::atoi(e) : 0;
+    if (v <= 0) v = (int)std::thread::hardware_concurrency();
+    return v > 0 ? v : 1;
+  }();
+  return n;
+}
 
 int urmvo::set_error(int code, const std::string& msg) {
   g_err = msg;
@@ -315,7 +326,7 @@ static int ba_plan_create_impl(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, const
     if (Nc <= 0 || Np < 0 || No < 0) { delete p; return fail(URMVO_ERR_ARG, "ba_plan_create: bad window offsets"); }
   }
   {  // windows are independent: flatten them on all host threads
-    const int nt = std::max(1, std::min({(int)std::thread::hardware_concurrency(), 16, B / 4}));
+    const int nt = std::max(1, std::min({urmvo::host_threads(), 16, B / 4}));
     std::atomic<int> next(0);
     auto work = [&]() {
       for (int w = next++; w < B; w = next++) {

@@ -12,6 +12,9 @@
 namespace urmvo {
 // records the message returned by urmvo_last_error() (thread-local) and returns `code`
 int set_error(int code, const std::string& msg);
+// Host threads the library may use for flattening / subset drawing: URMVO_B200_HOST_THREADS if set
+// (one process per GPU on a shared host should divide the cores), else hardware_concurrency().
+int host_threads();
 }  // namespace urmvo
 
 #define CU_TRY(expr)                                                                                  \

@@ -97,7 +97,7 @@ struct FmProblem {
 
 template <class F>
 void parallel_over(int n, F&& fn) {
-  const int hw = (int)std::thread::hardware_concurrency();
+  const int hw = urmvo::host_threads();
   const int nt = std::max(1, std::min(n / 4, hw > 0 ? hw : 1));  // a thread is worth >= 4 problems
   if (nt <= 1) {
     for (int i = 0; i < n; i++) fn(i);
