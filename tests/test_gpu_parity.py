@@ -383,3 +383,35 @@ def test_ba_dense_solver_ldlt_and_pcg_agree(ctx, oracle):
     assert gs0.pcg_iters[0] == 0 and gs0.pcg_iters[1] == 0
     assert gs1.pcg_iters[0] > 0
     assert list(gs0.trials) == list(gs1.trials)
+
+
+def _thin(prob, keep):
+    """Keep the observations selected by the boolean mask (arrays stay point-major)."""
+    q = dict(prob)
+    for k in ("uv", "obs_cam", "obs_pt"):
+        q[k] = np.ascontiguousarray(prob[k][keep])
+    return q
+
+
+def test_ba_packed_groups_of_32_single_observation_points(oracle, ctx):
+    """Packed mode edge: groups of 32 points with one observation each (the slot table is full, the
+    slot prefetch of point q+1 clamps at row 31) mixed with ordinary points."""
+    p = synth.make_ba(41, 8, 600, 6.0, 8, 2, 0.02)
+    first = np.r_[True, p["obs_pt"][1:] != p["obs_pt"][:-1]]
+    keep = first | (p["obs_pt"] >= 300)          # points 0..299 keep only their first observation
+    q = _thin(p, keep)
+    counts = np.bincount(q["obs_pt"], minlength=600)
+    assert (counts[:300] == 1).all() and counts[300:].max() > 3
+    _check_ba(oracle, ctx, q)
+
+
+def test_ba_packed_point_with_32_observations(oracle, ctx):
+    """Packed mode edge: kmax = 32 (one point fills a whole group) with 7 free of 40 cameras."""
+    p = synth.make_ba(43, 40, 300, 30.0, 40, 33, 0.02)
+    counts = np.bincount(p["obs_pt"], minlength=300)
+    order = np.argsort(-counts)
+    # cap every point at 32 observations (drop the surplus of the few that have more)
+    rank_in_pt = np.arange(len(p["obs_pt"])) - np.r_[0, np.cumsum(counts)][p["obs_pt"]]
+    q = _thin(p, rank_in_pt < 32)
+    assert np.bincount(q["obs_pt"]).max() == 32 and int((q["fixed"] == 0).sum()) == 7
+    _check_ba(oracle, ctx, q)
