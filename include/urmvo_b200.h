@@ -4,6 +4,7 @@
  *   LocalmapOptimization   /root/reference/include/g2o_optimization.h:13-15  (src/g2o_optimization.cc:20-177)
  *   FrameOptimization      /root/reference/include/g2o_optimization.h:17-19  (src/g2o_optimization.cc:179-321)
  *   EpipolarGeometry::reconstruct  /root/reference/include/epipolar_geometry.h:31-35 (src/epipolar_geometry.cc:18-98)
+ *   cv::findFundamentalMat(FM_RANSAC) call of PointMatching::MatchingPoints  (src/point_matching.cc:50-60)
  * The C++ adapters in ur-mvo_b200/adapter/ keep those signatures and flatten the reference's
  * MapOfPoses / MapOfPoints3d / constraint vectors / cv::KeyPoint into the SoA arrays below.
  *

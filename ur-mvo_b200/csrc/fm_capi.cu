@@ -162,7 +162,7 @@ static int fm_plan_create_impl(urmvo_ctx* ctx, urmvo_fm_plan** out, int B, const
                        "reference's own cv::findFundamentalMat call for these)");
     max_n = std::max(max_n, n);
   }
-  if ((long long)B * max_iters > (1ll << 29)) return set_error(URMVO_ERR_ARG, "fm_plan_create: B * max_iters too large");
+  if ((long long)B * max_iters > (1ll << 24)) return set_error(URMVO_ERR_ARG, "fm_plan_create: B * max_iters exceeds 2^24 hypotheses (3.6 GB of models); split the batch");
   CU_TRY(cudaSetDevice(ctx->device));
   urmvo_fm_plan* p = new urmvo_fm_plan();
   p->ctx = ctx; p->B = B; p->max_iters = max_iters; p->confidence = confidence;
