@@ -5,6 +5,7 @@
  *   FrameOptimization      /root/reference/include/g2o_optimization.h:17-19  (src/g2o_optimization.cc:179-321)
  *   EpipolarGeometry::reconstruct  /root/reference/include/epipolar_geometry.h:31-35 (src/epipolar_geometry.cc:18-98)
  *   cv::findFundamentalMat(FM_RANSAC) call of PointMatching::MatchingPoints  (src/point_matching.cc:50-60)
+ *   Mapping::TriangulateMappoint, batched  (src/mapping.cc:151-205)
  * The C++ adapters in ur-mvo_b200/adapter/ keep those signatures and flatten the reference's
  * MapOfPoses / MapOfPoints3d / constraint vectors / cv::KeyPoint into the SoA arrays below.
  *
@@ -220,6 +221,17 @@ int urmvo_fm_plan_run(urmvo_fm_plan* plan);
 int urmvo_fm_plan_finish(urmvo_fm_plan* plan, uint8_t* inlier, urmvo_fm_stats* stats);
 int urmvo_fm_plan_hypotheses(const urmvo_fm_plan* plan); /* (iteration, problem) pairs evaluated per run */
 void urmvo_fm_plan_destroy(urmvo_fm_plan* plan);
+
+/* ---- batched mappoint triangulation ----------------------------------
+ * Mapping::TriangulateMappoint (reference src/mapping.cc:151-205) for n_pts mappoints in one launch:
+ * multi-view midpoint from the observing keyframes, Eigen::ColPivHouseholderQR rank test (1e-5).
+ * obs_off: n_pts+1 offsets; per observer the index of its keyframe in poses_Rp and the keypoint (u,v);
+ * poses_Rp: n_poses x 12 doubles, the keyframe pose T_wc as R (row-major) | p (Frame::GetPose()).
+ * ok[l] = 1 and pts[3l..] written on success; ok[l] = 0 (< 2 observers or rank < 3) leaves pts[3l..]
+ * untouched, like the reference's early return. */
+int urmvo_triangulate_batch(urmvo_ctx* ctx, int n_pts, const int32_t* obs_off, const int32_t* obs_pose,
+                            const double* obs_uv, int n_poses, const double* poses_Rp, const double* intr,
+                            double* pts, uint8_t* ok);
 
 #ifdef __cplusplus
 }

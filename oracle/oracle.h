@@ -131,6 +131,11 @@ int urmvo_oracle_fm_run7(const float* p0, const float* p1, double* F27);
 /* FMEstimatorCallback::computeError: err[i] = (float)max(d1^2 s1, d2^2 s2). */
 void urmvo_oracle_fm_errors(int N, const float* p0, const float* p1, const double* F, float* err);
 
+/* ---- Mapping::TriangulateMappoint (reference src/mapping.cc:151-205), tri_oracle.cpp.  PARITY UNPINNED.
+ * n_obs observers of one mappoint: Rp = (R row-major | p) of the keyframe pose T_wc (12 doubles each),
+ * uv = keypoint position.  Returns 1 and writes X (3) on success, 0 for < 2 observers or rank < 3. */
+int urmvo_oracle_triangulate(int n_obs, const double* Rp, const double* uv, const double* intr, double* X);
+
 #ifdef __cplusplus
 }
 #endif

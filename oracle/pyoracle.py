@@ -211,3 +211,15 @@ def fm_errors(p0, p1, F):
     err = np.zeros(len(p0), dtype=np.float32)
     lib().urmvo_oracle_fm_errors(C.c_int(len(p0)), _p(p0), _p(p1), _p(F), _p(err))
     return err
+
+
+# ---- Mapping::TriangulateMappoint (tri_oracle.cpp)
+
+def triangulate(Rp, uv, intr):
+    """Rp: (n,12) [R row-major | p] of the observing keyframes' T_wc, uv: (n,2). Returns (ok, X[3])."""
+    Rp = np.ascontiguousarray(Rp, dtype=np.float64); uv = np.ascontiguousarray(uv, dtype=np.float64)
+    intr = np.ascontiguousarray(intr, dtype=np.float64)
+    X = np.zeros(3)
+    lib().urmvo_oracle_triangulate.restype = C.c_int
+    ok = lib().urmvo_oracle_triangulate(C.c_int(len(uv)), _p(Rp), _p(uv), _p(intr), _p(X))
+    return bool(ok), X

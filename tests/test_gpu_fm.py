@@ -89,3 +89,29 @@ def test_gpu_fewer_than_15_points_is_refused(ctx):
     p0, p1 = synth.make_fm(3500, 14, 0.9)
     with pytest.raises(U.UrmvoError, match="fewer than 15"):
         ctx.fm_ransac(p0, p1)
+
+
+def test_gpu_triangulate_batch_matches_oracle(ctx, oracle):
+    """Mapping::TriangulateMappoint batched (SURVEY §8f row 3): same accept / reject flags as the
+    CPU restatement, positions to 1e-9, rejected mappoints keep their previous position."""
+    t = synth.make_triangulation(13, n_pts=800, degenerate_frac=0.1)
+    prev = np.full((800, 3), 7.0)
+    pts, ok = ctx.triangulate_batch(t["obs_off"], t["obs_pose"], t["obs_uv"], t["poses_Rp"], t["intr"], pts=prev)
+    n_rej = 0
+    for l in range(800):
+        s = slice(t["obs_off"][l], t["obs_off"][l + 1])
+        o_ok, X = oracle.triangulate(t["poses_Rp"][t["obs_pose"][s]], t["obs_uv"][s], t["intr"])
+        assert bool(ok[l]) == o_ok, l
+        if o_ok:
+            assert np.abs(pts[l] - X).max() <= 1e-9 * max(1.0, np.abs(X).max())
+        else:
+            n_rej += 1
+            assert np.array_equal(pts[l], prev[l])
+    assert 20 < n_rej < 200
+
+
+def test_gpu_triangulate_batch_rejects_bad_indices(ctx):
+    t = synth.make_triangulation(14, n_pts=10)
+    bad = t["obs_pose"].copy(); bad[0] = 99
+    with pytest.raises(U.UrmvoError, match="pose index"):
+        ctx.triangulate_batch(t["obs_off"], bad, t["obs_uv"], t["poses_Rp"], t["intr"])

@@ -15,7 +15,7 @@ EXPORTED_SYMBOLS = [
     "urmvo_two_view", "urmvo_tv_plan_create", "urmvo_tv_plan_run_ransac", "urmvo_tv_plan_download_hyps",
     "urmvo_tv_plan_reconstruct", "urmvo_tv_plan_destroy",
     "urmvo_fm_ransac", "urmvo_fm_ransac_batch", "urmvo_fm_plan_create", "urmvo_fm_plan_run", "urmvo_fm_plan_finish",
-    "urmvo_fm_plan_hypotheses", "urmvo_fm_plan_destroy",
+    "urmvo_fm_plan_hypotheses", "urmvo_fm_plan_destroy", "urmvo_triangulate_batch",
 ]
 
 
@@ -203,6 +203,17 @@ class Context:
                                              C.c_double(confidence), C.c_int(max_iters), _p(mask), st),
                "urmvo_fm_ransac_batch")
         return [mask[off[b]:off[b + 1]] for b in range(len(pairs))], list(st)
+
+    def triangulate_batch(self, obs_off, obs_pose, obs_uv, poses_Rp, intr, pts=None):
+        """Mapping::TriangulateMappoint for a batch of mappoints. Returns (pts[n,3], ok[n])."""
+        obs_off = _i32(obs_off); obs_pose = _i32(obs_pose); obs_uv = _f64(obs_uv); poses_Rp = _f64(poses_Rp)
+        n = len(obs_off) - 1
+        out = np.zeros((n, 3)) if pts is None else _f64(pts).copy()
+        ok = np.zeros(n, dtype=np.uint8)
+        _check(self._L.urmvo_triangulate_batch(self._h, C.c_int(n), _p(obs_off), _p(obs_pose), _p(obs_uv),
+                                               C.c_int(len(poses_Rp)), _p(poses_Rp), _p(_f64(intr)), _p(out), _p(ok)),
+               "urmvo_triangulate_batch")
+        return out, ok
 
     def two_view(self, tv, sets=None):
         k1 = _f32(tv["keys1"]); k2 = _f32(tv["keys2"]); m = _i32(tv["matches12"]); K = _f32(tv["K"])

@@ -247,3 +247,34 @@ def make_fm(seed=1006, n=1000, inlier_frac=0.7, px_sigma=0.7, rot_deg=5.0, t=(0.
 def make_fm_batch(seed=1006, B=256, n=1000, inlier_frac=0.7):
     """B independent frame pairs (stereo + temporal matches of consecutive keyframes): list of (p0, p1)."""
     return [make_fm(seed + 7919 * b, n, inlier_frac) for b in range(B)]
+
+
+def make_triangulation(seed=1007, n_pts=500, n_poses=12, max_obs=10, px_sigma=0.5, degenerate_frac=0.05):
+    """New mappoints of a keyframe for Mapping::TriangulateMappoint (reference src/mapping.cc:151-205):
+    poses_Rp (n_poses, 12) = keyframe poses T_wc as [R row-major | p], CSR observer lists, keypoints.
+    A few mappoints are degenerate on purpose (one observer, or all observers at the same centre)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    gt = _trajectory(rng, n_poses)
+    Rs = quat_to_R(gt[:, :4])
+    poses_Rp = np.concatenate([Rs.reshape(n_poses, 9), gt[:, 4:]], axis=1)
+    X = np.stack([rng.uniform(-2, 2, n_pts), rng.uniform(-1.5, 1.5, n_pts), rng.uniform(3, 9, n_pts)], axis=-1)
+    X = X @ Rs[0].T + gt[0, 4:]
+    off, idx, uv = [0], [], []
+    kind = rng.uniform(size=n_pts)
+    for l in range(n_pts):
+        k = int(rng.integers(2, max_obs + 1))
+        cams = np.sort(rng.choice(n_poses, size=min(k, n_poses), replace=False))
+        if kind[l] < degenerate_frac / 2:
+            cams = cams[:1]                      # fewer than 2 observers
+        for c in cams:
+            xc = Rs[c].T @ (X[l] - gt[c, 4:])
+            p = np.array([xc[0] / xc[2] * FX + CX, xc[1] / xc[2] * FY + CY]) + px_sigma * rng.standard_normal(2)
+            if degenerate_frac / 2 <= kind[l] < degenerate_frac:
+                c = cams[0]                      # the same keyframe, same pixel: rank-deficient system
+                xc = Rs[c].T @ (X[l] - gt[c, 4:])
+                p = np.array([xc[0] / xc[2] * FX + CX, xc[1] / xc[2] * FY + CY])
+            idx.append(int(c)); uv.append(p)
+        off.append(len(idx))
+    return dict(obs_off=np.array(off, dtype=np.int32), obs_pose=np.array(idx, dtype=np.int32),
+                obs_uv=np.array(uv, dtype=np.float64).reshape(-1, 2), poses_Rp=poses_Rp,
+                intr=np.array([FX, FY, CX, CY]), gt=X)
