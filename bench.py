@@ -509,6 +509,21 @@ def side_measurements(ctx, stream, torch):
         fm["opencv"] = f"unavailable: {type(e).__name__}"
     extra["fm_ransac_per_frame"] = fm
     fplan.close()
+    # batched mappoint triangulation: host-buffer call vs the CPU restatement
+    tri = synth.make_triangulation(1007, n_pts=5000, n_poses=35)
+    ctx.triangulate_batch(tri["obs_off"], tri["obs_pose"], tri["obs_uv"], tri["poses_Rp"], tri["intr"])
+    t0 = time.perf_counter()
+    gp, gok = ctx.triangulate_batch(tri["obs_off"], tri["obs_pose"], tri["obs_uv"], tri["poses_Rp"], tri["intr"])
+    t_gpu = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    n_same = 0
+    for l in range(500):
+        sl = slice(tri["obs_off"][l], tri["obs_off"][l + 1])
+        ook, _ = po.triangulate(tri["poses_Rp"][tri["obs_pose"][sl]], tri["obs_uv"][sl], tri["intr"])
+        n_same += int(ook == bool(gok[l]))
+    t_cpu = (time.perf_counter() - t0) / 500
+    extra["triangulate_batch"] = {"mappoints": 5000, "e2e_call_ms": t_gpu * 1e3, "mappoints_per_s": 5000 / t_gpu,
+                                  "cpu_port_us_per_mappoint_incl_python": t_cpu * 1e6, "flags_equal_cpu_port": n_same == 500}
     return extra
 
 
