@@ -7,7 +7,8 @@ rep, kname = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "ur-mvo_b200/lib/liburmvo_b200.so")], cwd=tmp, capture_output=True)
-cubin = [f for f in os.listdir(tmp) if f.startswith("ba_kernels")][0]
+unit = os.environ.get("UNIT", "ba_kernels")  # translation unit (cubin name prefix / source file) of the kernel
+cubin = [f for f in os.listdir(tmp) if f.startswith(unit)][0]
 dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.split("\n")
 start = next(i for i, l in enumerate(dis) if l.startswith(".text.") and kname in l and l.rstrip().endswith(":"))
 seq, cur = [], None
@@ -30,7 +31,7 @@ for d, (off, ln, txt) in zip(data, seq):
     for i in stallcols:
         bystall[ln][hdr[i]] += int(d[i]); tot[hdr[i]] += int(d[i])
 n = sum(byline.values())
-src = open(os.path.join(ROOT, "ur-mvo_b200/csrc/ba_kernels.cu")).read().split("\n")
+src = open(os.path.join(ROOT, f"ur-mvo_b200/csrc/{unit}.cu")).read().split("\n")
 print("samples", n, "warp-instructions %.3f G" % (sum(exline.values()) / 1e9))
 print(" ".join(f"{k[6:]}={v / sum(tot.values()) * 100:.1f}%" for k, v in tot.most_common(8)))
 for ln, c in byline.most_common(top):

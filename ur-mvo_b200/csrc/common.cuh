@@ -71,11 +71,24 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double* red) {
     for (int k = 0; k < NV; k++) red[k * 32 + wid] = v[k];
   }
   __syncthreads();
+  if (NV <= 4) {
 #pragma unroll
-  for (int k = 0; k < NV; k++) {
-    double s = 0.0;
-    for (int w = 0; w < nw; w++) s += red[k * 32 + w];
-    v[k] = s;
+    for (int k = 0; k < NV; k++) {
+      double s = 0.0;
+      for (int w = 0; w < nw; w++) s += red[k * 32 + w];
+      v[k] = s;
+    }
+  } else {
+    // many values: thread k sums the warp partials of value k once (same warp order), everybody
+    // reads the NV totals back — instead of NV * nw dependent additions in every thread
+    if (threadIdx.x < NV) {
+      double s = 0.0;
+      for (int w = 0; w < nw; w++) s += red[threadIdx.x * 32 + w];
+      red[NV * 32 + threadIdx.x] = s;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NV; k++) v[k] = red[NV * 32 + k];
   }
 }
 

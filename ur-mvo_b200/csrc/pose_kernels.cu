@@ -54,41 +54,48 @@ __device__ __forceinline__ void pose_jac(const double* pc, const double* K, doub
 }
 
 // Solve (H + lambda I) x = b, H symmetric packed upper (21). False if not positive definite.
+// LDL^T with reciprocal pivots: every thread of the CTA runs this redundantly between two passes over
+// the observations, so its serial latency is what matters — 6 divisions on the critical path instead
+// of the 6 square roots + 18 divisions of a textbook Cholesky with substitutions.
 __device__ __forceinline__ bool solve6(const double* Hp, const double* b, double lambda, double* x) {
-  double L[36];
+  double A[36], L[36], dinv[6], dd[6];
   int idx = 0;
-  double A[36];
 #pragma unroll
   for (int i = 0; i < 6; i++)
 #pragma unroll
     for (int j = i; j < 6; j++) { A[i * 6 + j] = Hp[idx]; A[j * 6 + i] = Hp[idx]; idx++; }
 #pragma unroll
-  for (int i = 0; i < 6; i++) {
+  for (int j = 0; j < 6; j++) {
+    double v[6];
+    double d = A[j * 6 + j] + lambda;
 #pragma unroll
-    for (int j = 0; j <= i; j++) {
-      double s = A[i * 6 + j] + (i == j ? lambda : 0.0);
+    for (int k = 0; k < j; k++) { v[k] = L[j * 6 + k] * dd[k]; d -= L[j * 6 + k] * v[k]; }
+    if (!(d > 0.0)) return false;
+    dd[j] = d;
+    dinv[j] = 1.0 / d;
 #pragma unroll
-      for (int k = 0; k < j; k++) s -= L[i * 6 + k] * L[j * 6 + k];
-      if (j < i) L[i * 6 + j] = s / L[j * 6 + j];
-      else {
-        if (!(s > 0.0)) return false;
-        L[i * 6 + i] = sqrt(s);
-      }
+    for (int i = j + 1; i < 6; i++) {
+      double s = A[i * 6 + j];
+#pragma unroll
+      for (int k = 0; k < j; k++) s -= L[i * 6 + k] * v[k];
+      L[i * 6 + j] = s * dinv[j];
     }
   }
 #pragma unroll
-  for (int i = 0; i < 6; i++) {
+  for (int i = 0; i < 6; i++) {  // z = L^-1 b (unit lower triangle)
     double s = b[i];
 #pragma unroll
     for (int k = 0; k < i; k++) s -= L[i * 6 + k] * x[k];
-    x[i] = s / L[i * 6 + i];
+    x[i] = s;
   }
 #pragma unroll
-  for (int i = 5; i >= 0; i--) {
+  for (int i = 0; i < 6; i++) x[i] *= dinv[i];
+#pragma unroll
+  for (int i = 5; i >= 0; i--) {  // x = L^-T y
     double s = x[i];
 #pragma unroll
     for (int k = i + 1; k < 6; k++) s -= L[k * 6 + i] * x[k];
-    x[i] = s / L[i * 6 + i];
+    x[i] = s;
   }
   return true;
 }
