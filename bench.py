@@ -483,7 +483,7 @@ def side_measurements(ctx, stream, torch):
     dt = timed(fplan.run, 5)  # all RANSAC rounds: kernels + host subset draws + host budget replay
     masks, fst = fplan.finish()
     its = sum(s.iters for s in fst)
-    ctx.fm_ransac_batch(pairs[:2])  # workspace warm-up
+    ctx.fm_ransac_batch(pairs)  # workspace warm-up (the grow-only device / pinned buffers reach their size)
     t0 = time.perf_counter(); ctx.fm_ransac_batch(pairs); t_call = time.perf_counter() - t0
     ctx.fm_ransac(*pairs[0])
     t0 = time.perf_counter()
