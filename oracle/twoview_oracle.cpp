@@ -29,28 +29,43 @@ constexpr float kJacobiTol = 5e-7f;
 // columns only chases round-off and would keep every solve at the sweep limit.
 constexpr float kJacobiTiny = 1e-14f;
 
+// Sum over the m rows of a design matrix.  Part of the specification: for m < 8 (the 3x3 and 4x4
+// problems, solved by one thread) the terms are added in row order; for m >= 8 (the 8x9 / 16x9
+// systems of a hypothesis, whose rows live in the lanes of a sub-warp on the GPU) they are added as
+// a pairwise tree over 8 or 16 terms (zero-padded) — the order of an xor-butterfly of shuffles.
+template <class F>
+inline float row_sum(int m, F term) {
+  if (m < 8) {
+    float s = 0.0f;
+    for (int k = 0; k < m; k++) s = (k == 0) ? term(k) : s + term(k);
+    return s;
+  }
+  const int P = m <= 8 ? 8 : 16;
+  float t[16];
+  for (int k = 0; k < P; k++) t[k] = k < m ? term(k) : 0.0f;
+  for (int w = 1; w < P; w <<= 1)
+    for (int i = 0; i < P; i += 2 * w) t[i] = t[i] + t[i + w];
+  return t[0];
+}
+
 // One-sided Jacobi: A (m x n, row-major, leading dim n) becomes U*Sigma, V (n x n) accumulates.
 void jacobi_onesided(int m, int n, float* A, float* V) {
   for (int i = 0; i < n; i++)
     for (int j = 0; j < n; j++) V[i * n + j] = (i == j) ? 1.0f : 0.0f;
-  float fro2 = 0.0f;  // sum over rows of the row sums (this order is part of the specification)
-  for (int k = 0; k < m; k++) {
+  // sum over rows of the row sums (this order is part of the specification)
+  const float fro2 = row_sum(m, [&](int k) {
     float row = 0.0f;
     for (int j = 0; j < n; j++) row += A[k * n + j] * A[k * n + j];
-    fro2 = (k == 0) ? row : fro2 + row;
-  }
+    return row;
+  });
   const float tiny = kJacobiTiny * fro2;
   for (int sweep = 0; sweep < kMaxSweeps; sweep++) {
     bool rotated = false;
     for (int p = 0; p < n - 1; p++) {
       for (int q = p + 1; q < n; q++) {
-        float alpha = 0.0f, beta = 0.0f, gamma = 0.0f;
-        for (int k = 0; k < m; k++) {
-          float ap = A[k * n + p], aq = A[k * n + q];
-          alpha += ap * ap;
-          beta += aq * aq;
-          gamma += ap * aq;
-        }
+        const float alpha = row_sum(m, [&](int k) { return A[k * n + p] * A[k * n + p]; });
+        const float beta = row_sum(m, [&](int k) { return A[k * n + q] * A[k * n + q]; });
+        const float gamma = row_sum(m, [&](int k) { return A[k * n + p] * A[k * n + q]; });
         if (alpha <= tiny || beta <= tiny) continue;
         if (std::fabs(gamma) <= kJacobiTol * std::sqrt(alpha * beta)) continue;
         rotated = true;
@@ -76,9 +91,7 @@ void jacobi_onesided(int m, int n, float* A, float* V) {
 }
 
 inline float col_norm(int m, int n, const float* A, int j) {
-  float s = 0.0f;
-  for (int k = 0; k < m; k++) s += A[k * n + j] * A[k * n + j];
-  return std::sqrt(s);
+  return std::sqrt(row_sum(m, [&](int k) { return A[k * n + j] * A[k * n + j]; }));
 }
 
 // Right singular vector of the smallest singular value (JacobiSVD::matrixV().col(n-1)).

@@ -307,15 +307,19 @@ __global__ void tv_gather_kernel(int N, const int* __restrict__ m1, const int* _
 // 16384 hypotheses: latency-bound, profiles/README.md).  tv_fit_sub_kernel gives every hypothesis a SUB-WARP of
 // L = M lanes (8 for the 8x9 fundamental system, 16 for the 16x9 homography system): lane k owns
 // row k of A (and row k of V), the matrices live in shared memory, the three column dot products
-// of a Jacobi pair are formed as per-lane products followed by an ORDERED chain of adds over the
-// rows (shuffles), i.e. literally the restatement's  alpha += a*a  sequence, so every value is
-// bit-identical to the one-thread version.  4 (F) or 2 (H) hypotheses per warp.
+// of a Jacobi pair are formed as per-lane products followed by an xor butterfly over the rows
+// (log2 M shuffle steps): the specification sums the rows of these systems as a pairwise tree, which
+// is exactly what the butterfly computes, so every value is bit-identical to the CPU restatement.
+// (A lane-ordered chain of M adds, the first version, cost 2-3x the shuffles for the same result
+// class.)  4 (F) or 2 (H) hypotheses per warp.
 
+// Sum over the M rows (= lanes of the sub-warp): xor butterfly, i.e. the pairwise tree
+// ((v0+v1)+(v2+v3))+... of the specification for m >= 8; every lane ends with the same bits.
 template <int L>
-__device__ __forceinline__ float ordered_sum(float v, int m, unsigned mask) {
-  float s = __shfl_sync(mask, v, 0, L);
-  for (int k = 1; k < m; k++) s = s + __shfl_sync(mask, v, k, L);
-  return s;
+__device__ __forceinline__ float row_sum(float v, unsigned mask) {
+#pragma unroll
+  for (int w = 1; w < L; w <<= 1) v = v + __shfl_xor_sync(mask, v, w, L);
+  return v;
 }
 
 // A: M x 9 and V: 9 x 9 in shared memory (row-major), sub-warp of L = M lanes, r = lane in sub-warp.
@@ -327,7 +331,7 @@ __device__ void jacobi_null_vector_sub(float* A, float* V, int r, unsigned mask,
   {
     float row = 0.0f;
     for (int j = 0; j < N; j++) row += A[r * N + j] * A[r * N + j];
-    tiny = kJacobiTiny * ordered_sum<M>(row, M, mask);  // sum over rows of the row sums
+    tiny = kJacobiTiny * row_sum<M>(row, mask);  // sum over rows of the row sums
   }
   __syncwarp(mask);
   for (int sweep = 0; sweep < kMaxSweeps; sweep++) {
@@ -335,9 +339,9 @@ __device__ void jacobi_null_vector_sub(float* A, float* V, int r, unsigned mask,
     for (int p = 0; p < N - 1; p++) {
       for (int q = p + 1; q < N; q++) {
         const float ap = A[r * N + p], aq = A[r * N + q];
-        const float alpha = ordered_sum<M>(ap * ap, M, mask);
-        const float beta = ordered_sum<M>(aq * aq, M, mask);
-        const float gamma = ordered_sum<M>(ap * aq, M, mask);
+        const float alpha = row_sum<M>(ap * ap, mask);
+        const float beta = row_sum<M>(aq * aq, mask);
+        const float gamma = row_sum<M>(ap * aq, mask);
         if (alpha <= tiny || beta <= tiny) continue;
         if (fabsf(gamma) <= kJacobiTol * sqrtf(alpha * beta)) continue;
         rotated = true;
@@ -363,7 +367,7 @@ __device__ void jacobi_null_vector_sub(float* A, float* V, int r, unsigned mask,
   float bn = 0.0f;
   for (int j = 0; j < N; j++) {
     const float a = A[r * N + j];
-    const float nj = sqrtf(ordered_sum<M>(a * a, M, mask));
+    const float nj = sqrtf(row_sum<M>(a * a, mask));
     if (j == 0 || nj < bn) { bn = nj; best = j; }
   }
   for (int k = 0; k < N; k++) v_out[k] = V[k * N + best];
