@@ -94,6 +94,41 @@ inline float col_norm(int m, int n, const float* A, int j) {
   return std::sqrt(row_sum(m, [&](int k) { return A[k * n + j] * A[k * n + j]; }));
 }
 
+// Null vector of the 8x9 system of an 8-point fundamental fit (what V.col(8) of the reference's
+// JacobiSVD is, up to sign): Householder QR of M = A^T (9x8), Q = H_0 ... H_7, null vector = Q e_8.
+// Specification shared with the CUDA kernel (lane r of a 16-lane group holds row r of M, rows 9..15
+// are zero): reflector k uses x = M[k.., k], sigma = row_sum16(x^2), norm = sqrt(sigma),
+// alpha = -sign(x_k) norm, v = x - alpha e_k, beta = 1 / (norm (norm + |x_k|)) (0 if norm == 0),
+// M[:, j] -= (beta * row_sum16(v . M[:, j])) * v; row_sum16 is the pairwise tree of row_sum(16, .).
+// 8 square roots and 8 divisions instead of ~200 Jacobi rotations.
+void null_vector_qr_8x9(const float* A, float* v) {
+  float M[16][8];
+  for (int r = 0; r < 16; r++)
+    for (int k = 0; k < 8; k++) M[r][k] = r < 9 ? A[k * 9 + r] : 0.0f;
+  float V[8][16], beta[8];
+  for (int k = 0; k < 8; k++) {
+    float x[16];
+    for (int r = 0; r < 16; r++) x[r] = r >= k ? M[r][k] : 0.0f;
+    const float sigma = row_sum(16, [&](int r) { return x[r] * x[r]; });
+    const float xkk = M[k][k];
+    const float norm = std::sqrt(sigma);
+    const float alpha = xkk >= 0.0f ? -norm : norm;
+    for (int r = 0; r < 16; r++) V[k][r] = r == k ? x[r] - alpha : x[r];
+    beta[k] = norm > 0.0f ? 1.0f / (norm * (norm + std::fabs(xkk))) : 0.0f;
+    for (int j = k + 1; j < 8; j++) {
+      const float w = beta[k] * row_sum(16, [&](int r) { return V[k][r] * M[r][j]; });
+      for (int r = 0; r < 16; r++) M[r][j] = M[r][j] - w * V[k][r];
+    }
+  }
+  float y[16];
+  for (int r = 0; r < 16; r++) y[r] = r == 8 ? 1.0f : 0.0f;
+  for (int k = 7; k >= 0; k--) {
+    const float w = beta[k] * row_sum(16, [&](int r) { return V[k][r] * y[r]; });
+    for (int r = 0; r < 16; r++) y[r] = y[r] - w * V[k][r];
+  }
+  for (int r = 0; r < 9; r++) v[r] = y[r];
+}
+
 // Right singular vector of the smallest singular value (JacobiSVD::matrixV().col(n-1)).
 void null_vector(int m, int n, float* A, float* v) {
   float V[81];
@@ -219,7 +254,7 @@ void fit_F(const TwoView& tv, const int32_t* set, float* F21) {
     r[6] = u1; r[7] = v1; r[8] = 1.0f;
   }
   float Fpre[9];
-  null_vector(8, 9, A, Fpre);
+  null_vector_qr_8x9(A, Fpre);
   float U[9], w[3], V[9];
   svd3(Fpre, U, w, V);
   w[2] = 0.0f;

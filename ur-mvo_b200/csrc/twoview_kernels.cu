@@ -373,24 +373,60 @@ __device__ void jacobi_null_vector_sub(float* A, float* V, int r, unsigned mask,
   for (int k = 0; k < N; k++) v_out[k] = V[k * N + best];
 }
 
-// MODEL 0: fundamental (M = 8), MODEL 1: homography (M = 16).  models: [2][n_hyp][18].
+// Null vector of the 8x9 fundamental system: Householder QR of A^T in registers, lane r of a 16-lane
+// group = row r of the 9x8 matrix (specification: null_vector_qr_8x9 of the CPU restatement).
+__device__ void qr_null_vector_8x9(float* A, int r, unsigned mask, float* v_out) {
+  float mrow[8], vk[8], bk[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) mrow[k] = r < 9 ? A[k * 9 + r] : 0.0f;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const float x = r >= k ? mrow[k] : 0.0f;
+    const float sigma = row_sum<16>(x * x, mask);
+    const float xkk = __shfl_sync(mask, mrow[k], k, 16);
+    const float norm = sqrtf(sigma);
+    const float alpha = xkk >= 0.0f ? -norm : norm;
+    const float v = r == k ? x - alpha : x;
+    const float beta = norm > 0.0f ? 1.0f / (norm * (norm + fabsf(xkk))) : 0.0f;
+    vk[k] = v;
+    bk[k] = beta;
+#pragma unroll
+    for (int j = k + 1; j < 8; j++) {
+      const float w = beta * row_sum<16>(v * mrow[j], mask);
+      mrow[j] = mrow[j] - w * v;
+    }
+  }
+  float y = r == 8 ? 1.0f : 0.0f;
+#pragma unroll
+  for (int k = 7; k >= 0; k--) {
+    const float w = bk[k] * row_sum<16>(vk[k] * y, mask);
+    y = y - w * vk[k];
+  }
+  __syncwarp(mask);
+  if (r < 9) A[r] = y;  // the staging area is free now
+  __syncwarp(mask);
+  for (int k = 0; k < 9; k++) v_out[k] = A[k];
+}
+
+// MODEL 0: fundamental (8x9 system, Householder null vector), MODEL 1: homography (16x9 system,
+// Jacobi SVD); 16 lanes per hypothesis in both.  models: [2][n_hyp][18].
 template <int MODEL>
 __global__ void __launch_bounds__(256)
 tv_fit_sub_kernel(int n_hyp, const int* __restrict__ sets, const float4* __restrict__ pnm,
                   const float* __restrict__ T1, const float* __restrict__ T2, float* __restrict__ models) {
-  constexpr int M = MODEL == 0 ? 8 : 16;
+  constexpr int M = 16;
   constexpr int PER_WARP = 32 / M;
-  constexpr int FL = M * 9 + 81;  // floats per hypothesis
+  constexpr int FL = MODEL == 0 ? 8 * 9 : M * 9 + 81;  // floats per hypothesis
   extern __shared__ float sm_fit[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int sub = lane / M, r = lane - sub * M;
-  const unsigned mask = (M == 8 ? 0xFFu : 0xFFFFu) << (sub * M);
+  const unsigned mask = 0xFFFFu << (sub * M);
   const int hyp = (blockIdx.x * (blockDim.x >> 5) + wid) * PER_WARP + sub;
   if (hyp >= n_hyp) return;  // whole sub-warps leave together
   float* A = sm_fit + (size_t)(wid * PER_WARP + sub) * FL;
   float* V = A + M * 9;
   const int* set = sets + (size_t)hyp * 8;
-  {
+  if (MODEL == 1 || r < 8) {
     const float4 m = pnm[set[MODEL == 0 ? r : (r >> 1)]];
     const float u1 = m.x, v1 = m.y, u2 = m.z, v2 = m.w;
     float* row = A + r * 9;
@@ -410,7 +446,8 @@ tv_fit_sub_kernel(int n_hyp, const int* __restrict__ sets, const float4* __restr
   }
   __syncwarp(mask);
   float nv[9];
-  jacobi_null_vector_sub<M>(A, V, r, mask, nv);
+  if (MODEL == 0) qr_null_vector_8x9(A, r, mask, nv);
+  else jacobi_null_vector_sub<M>(A, V, r, mask, nv);
   if (r != 0) return;
   float t1[9], t2[9];
   for (int i = 0; i < 9; i++) { t1[i] = T1[i]; t2[i] = T2[i]; }
@@ -795,8 +832,8 @@ cudaError_t launch_tv_ransac(const TVBuffers& b, float sigma, int n_sm, cudaStre
   {
     // cooperative fit: 4 fundamental / 2 homography hypotheses per warp, 8 warps per CTA
     const int wpc = 8;
-    const int gF = (b.n_hyp + wpc * 4 - 1) / (wpc * 4), gH = (b.n_hyp + wpc * 2 - 1) / (wpc * 2);
-    const size_t smF = (size_t)wpc * 4 * (8 * 9 + 81) * sizeof(float), smH = (size_t)wpc * 2 * (16 * 9 + 81) * sizeof(float);
+    const int gF = (b.n_hyp + wpc * 2 - 1) / (wpc * 2), gH = (b.n_hyp + wpc * 2 - 1) / (wpc * 2);
+    const size_t smF = (size_t)wpc * 2 * (8 * 9) * sizeof(float), smH = (size_t)wpc * 2 * (16 * 9 + 81) * sizeof(float);
     tv_fit_sub_kernel<0><<<gF, wpc * 32, smF, stream>>>(b.n_hyp, b.sets, b.pnm, b.T1, b.T2, b.models);
     tv_fit_sub_kernel<1><<<gH, wpc * 32, smH, stream>>>(b.n_hyp, b.sets, b.pnm, b.T1, b.T2, b.models);
     nl += 2;
