@@ -542,11 +542,16 @@ tv_score_kernel(int N, int n_hyp, const float4* __restrict__ uv_g, const float* 
       }
       const uint32_t word = __ballot_sync(0xffffffffu, bIn);
       if (lane == 0) mw[base >> 5] = word;
-      // the reference adds in match order (score += ... twice per match): replay that order
-      const int cnt = min(32, N - base);
-      for (int l = 0; l < cnt; l++) {
-        score += __shfl_sync(0xffffffffu, c1, l);
-        score += __shfl_sync(0xffffffffu, c2, l);
+      // the reference adds in match order (score += ... twice per match): replay that order.
+      // Directions that failed their test contribute +0.0f, which leaves the fp32 sum unchanged, so
+      // only the non-zero terms are visited (most hypotheses have few inliers): same bits, a chain
+      // of popc(nz1) + popc(nz2) dependent adds instead of 64 per 32 matches.
+      const uint32_t nz1 = __ballot_sync(0xffffffffu, c1 != 0.0f);
+      const uint32_t nz2 = __ballot_sync(0xffffffffu, c2 != 0.0f);
+      for (uint32_t any = nz1 | nz2; any; any &= any - 1) {
+        const int l = __ffs(any) - 1;
+        if ((nz1 >> l) & 1u) score += __shfl_sync(0xffffffffu, c1, l);
+        if ((nz2 >> l) & 1u) score += __shfl_sync(0xffffffffu, c2, l);
       }
     }
     if (lane == 0) scores[g] = score;
