@@ -828,20 +828,22 @@ struct urmvo_pose_plan {
   double chi2_thr = 0, delta = 0;
   int rounds = 4, its = 10;
   unsigned char* dev = nullptr;
+  bool borrowed = false;  // dev is the context's grow-only workspace (one-shot urmvo_pose_only_batch)
   size_t o_off = 0, o_pose_in = 0, o_uv = 0, o_X = 0, o_inl_in = 0, o_inl = 0, o_level = 0, o_pose_out = 0,
          o_ninl = 0, o_iters = 0;
 };
 
 extern "C" void urmvo_pose_plan_destroy(urmvo_pose_plan* p) {
   if (!p) return;
-  if (p->dev) { cudaSetDevice(p->ctx->device); cudaFree(p->dev); }
+  if (p->borrowed) p->ctx->ws_in_use = false;
+  else if (p->dev) { cudaSetDevice(p->ctx->device); cudaFree(p->dev); }
   delete p;
 }
 
-extern "C" int urmvo_pose_plan_create(urmvo_ctx* ctx, urmvo_pose_plan** out, int B, const int32_t* obs_off,
+static int pose_plan_create_impl(urmvo_ctx* ctx, urmvo_pose_plan** out, int B, const int32_t* obs_off,
                                       const double* poses, const double* uv, const double* Xw,
                                       const double* intr, double chi2_thr, int rounds, int its_per_round,
-                                      const uint8_t* inlier) {
+                                      const uint8_t* inlier, bool borrow_ws) {
   if (!ctx || !out) return fail(URMVO_ERR_ARG, "pose_plan_create: null context / out");
   *out = nullptr;
   if (B <= 0 || !obs_off || !poses || !uv || !Xw || !intr) return fail(URMVO_ERR_ARG, "pose_plan_create: null or empty input");
@@ -861,7 +863,18 @@ extern "C" int urmvo_pose_plan_create(urmvo_ctx* ctx, urmvo_pose_plan** out, int
   p->o_uv = A.take<double>(TO * 2); p->o_X = A.take<double>(TO * 3);
   p->o_inl_in = A.take<uint8_t>(TO); p->o_inl = A.take<uint8_t>(TO); p->o_level = A.take<uint8_t>(TO);
   p->o_pose_out = A.take<double>((size_t)B * 7); p->o_ninl = A.take<int>(B); p->o_iters = A.take<int>(B);
-  cudaError_t ce = cudaMalloc(&p->dev, A.off);
+  cudaError_t ce = cudaSuccess;
+  if (borrow_ws && !ctx->ws_in_use) {  // per-frame calls: no cudaMalloc / cudaFree each time
+    if (ctx->ws_bytes < A.off) {
+      if (ctx->ws_dev) cudaFree(ctx->ws_dev);
+      ctx->ws_dev = nullptr; ctx->ws_bytes = 0;
+      ce = cudaMalloc(&ctx->ws_dev, A.off + A.off / 4);
+      if (ce == cudaSuccess) ctx->ws_bytes = A.off + A.off / 4;
+    }
+    if (ce == cudaSuccess) { p->dev = ctx->ws_dev; p->borrowed = true; ctx->ws_in_use = true; }
+  } else {
+    ce = cudaMalloc(&p->dev, A.off);
+  }
   if (ce != cudaSuccess) { delete p; return fail(URMVO_ERR_CUDA, std::string("cudaMalloc pose plan: ") + cudaGetErrorString(ce)); }
   cudaStream_t s = ctx->stream;
   std::vector<int> off(B + 1);
@@ -879,6 +892,13 @@ extern "C" int urmvo_pose_plan_create(urmvo_ctx* ctx, urmvo_pose_plan** out, int
     if (x != cudaSuccess) { urmvo_pose_plan_destroy(p); return fail(URMVO_ERR_CUDA, std::string("pose_plan_create upload: ") + cudaGetErrorString(x)); }
   *out = p;
   return URMVO_OK;
+}
+
+extern "C" int urmvo_pose_plan_create(urmvo_ctx* ctx, urmvo_pose_plan** out, int B, const int32_t* obs_off,
+                                      const double* poses, const double* uv, const double* Xw,
+                                      const double* intr, double chi2_thr, int rounds, int its_per_round,
+                                      const uint8_t* inlier) {
+  return pose_plan_create_impl(ctx, out, B, obs_off, poses, uv, Xw, intr, chi2_thr, rounds, its_per_round, inlier, false);
 }
 
 extern "C" int urmvo_pose_plan_run(urmvo_pose_plan* p) {
@@ -913,7 +933,7 @@ extern "C" int urmvo_pose_only_batch(urmvo_ctx* ctx, int B, const int32_t* obs_o
                                      const double* uv, const double* Xw, const double* intr, double chi2_thr,
                                      int rounds, int its_per_round, uint8_t* inlier, int32_t* n_inlier) {
   urmvo_pose_plan* p = nullptr;
-  int rc = urmvo_pose_plan_create(ctx, &p, B, obs_off, poses, uv, Xw, intr, chi2_thr, rounds, its_per_round, inlier);
+  int rc = pose_plan_create_impl(ctx, &p, B, obs_off, poses, uv, Xw, intr, chi2_thr, rounds, its_per_round, inlier, true);
   if (rc != URMVO_OK) return rc;
   rc = urmvo_pose_plan_run(p);
   if (rc == URMVO_OK) rc = urmvo_pose_plan_download(p, poses, inlier ? inlier + obs_off[0] : nullptr, n_inlier, nullptr);
@@ -930,18 +950,20 @@ struct urmvo_tv_plan {
   float Kh[9];
   std::vector<int> m1, m2;
   unsigned char* dev = nullptr;
+  bool borrowed = false;  // dev is the context's grow-only workspace (one-shot urmvo_two_view)
   bool ransac_done = false;
 };
 
 extern "C" void urmvo_tv_plan_destroy(urmvo_tv_plan* p) {
   if (!p) return;
-  if (p->dev) { cudaSetDevice(p->ctx->device); cudaFree(p->dev); }
+  if (p->borrowed) p->ctx->ws_in_use = false;
+  else if (p->dev) { cudaSetDevice(p->ctx->device); cudaFree(p->dev); }
   delete p;
 }
 
-extern "C" int urmvo_tv_plan_create(urmvo_ctx* ctx, urmvo_tv_plan** out, int n1, const float* keys1, int n2,
-                                    const float* keys2, const int32_t* matches12, const float* K, float sigma,
-                                    int n_hyp, const int32_t* sets) {
+static int tv_plan_create_impl(urmvo_ctx* ctx, urmvo_tv_plan** out, int n1, const float* keys1, int n2,
+                               const float* keys2, const int32_t* matches12, const float* K, float sigma,
+                               int n_hyp, const int32_t* sets, bool borrow_ws) {
   if (!ctx || !out) return fail(URMVO_ERR_ARG, "tv_plan_create: null context / out");
   *out = nullptr;
   if (n1 <= 0 || n2 <= 0 || !keys1 || !keys2 || !matches12 || !K || n_hyp <= 0 || !sets || !(sigma > 0))
@@ -974,7 +996,18 @@ extern "C" int urmvo_tv_plan_create(urmvo_ctx* ctx, urmvo_tv_plan** out, int n1,
   const size_t o_bi = A.take<int>(2), o_bs = A.take<float>(2);
   const size_t o_P3D = A.take<float>((size_t)8 * n1 * 3), o_good = A.take<uint8_t>((size_t)8 * n1), o_cos = A.take<float>(N);
   const size_t o_motion = A.take<TVMotionOut>(1);
-  cudaError_t ce = cudaMalloc(&p->dev, A.off);
+  cudaError_t ce = cudaSuccess;
+  if (borrow_ws && !ctx->ws_in_use) {  // no cudaMalloc / cudaFree per call (each costs ~1-2 ms)
+    if (ctx->ws_bytes < A.off) {
+      if (ctx->ws_dev) cudaFree(ctx->ws_dev);
+      ctx->ws_dev = nullptr; ctx->ws_bytes = 0;
+      ce = cudaMalloc(&ctx->ws_dev, A.off + A.off / 4);
+      if (ce == cudaSuccess) ctx->ws_bytes = A.off + A.off / 4;
+    }
+    if (ce == cudaSuccess) { p->dev = ctx->ws_dev; p->borrowed = true; ctx->ws_in_use = true; }
+  } else {
+    ce = cudaMalloc(&p->dev, A.off);
+  }
   if (ce != cudaSuccess) { delete p; return fail(URMVO_ERR_CUDA, std::string("cudaMalloc tv plan: ") + cudaGetErrorString(ce)); }
   unsigned char* D = p->dev;
   b.keys1 = (float*)(D + o_k1); b.keys2 = (float*)(D + o_k2);
@@ -998,6 +1031,12 @@ extern "C" int urmvo_tv_plan_create(urmvo_ctx* ctx, urmvo_tv_plan** out, int n1,
     if (x != cudaSuccess) { urmvo_tv_plan_destroy(p); return fail(URMVO_ERR_CUDA, std::string("tv_plan_create upload: ") + cudaGetErrorString(x)); }
   *out = p;
   return URMVO_OK;
+}
+
+extern "C" int urmvo_tv_plan_create(urmvo_ctx* ctx, urmvo_tv_plan** out, int n1, const float* keys1, int n2,
+                                    const float* keys2, const int32_t* matches12, const float* K, float sigma,
+                                    int n_hyp, const int32_t* sets) {
+  return tv_plan_create_impl(ctx, out, n1, keys1, n2, keys2, matches12, K, sigma, n_hyp, sets, false);
 }
 
 extern "C" int urmvo_tv_plan_run_ransac(urmvo_tv_plan* p) {
@@ -1142,7 +1181,7 @@ extern "C" int urmvo_two_view(urmvo_ctx* ctx, int n1, const float* keys1, int n2
                               const int32_t* sets, float* T21, float* P3D, uint8_t* triangulated,
                               uint8_t* mask_H, uint8_t* mask_F, urmvo_tv_stats* stats, int* success) {
   urmvo_tv_plan* p = nullptr;
-  int rc = urmvo_tv_plan_create(ctx, &p, n1, keys1, n2, keys2, matches12, K, sigma, n_hyp, sets);
+  int rc = tv_plan_create_impl(ctx, &p, n1, keys1, n2, keys2, matches12, K, sigma, n_hyp, sets, true);
   if (rc != URMVO_OK) return rc;
   rc = urmvo_tv_plan_run_ransac(p);
   if (rc == URMVO_OK) rc = urmvo_tv_plan_reconstruct(p, T21, P3D, triangulated, mask_H, mask_F, stats, success);
