@@ -994,7 +994,7 @@ static int tv_plan_create_impl(urmvo_ctx* ctx, urmvo_tv_plan** out, int n1, cons
   const size_t o_models = A.take<float>((size_t)2 * n_hyp * 18), o_scores = A.take<float>((size_t)2 * n_hyp);
   const size_t o_masks = A.take<uint32_t>((size_t)2 * n_hyp * b.words);
   const size_t o_bi = A.take<int>(2), o_bs = A.take<float>(2);
-  const size_t o_P3D = A.take<float>((size_t)8 * n1 * 3), o_good = A.take<uint8_t>((size_t)8 * n1), o_cos = A.take<float>(N);
+  const size_t o_P3D = A.take<float>((size_t)8 * n1 * 3), o_good = A.take<uint8_t>((size_t)8 * n1), o_cos = A.take<float>((size_t)8 * N);
   const size_t o_motion = A.take<TVMotionOut>(1);
   cudaError_t ce = cudaSuccess;
   if (borrow_ws && !ctx->ws_in_use) {  // no cudaMalloc / cudaFree per call (each costs ~1-2 ms)

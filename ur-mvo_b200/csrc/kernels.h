@@ -71,7 +71,7 @@ struct TVBuffers {
   float* best_score;  // [2]
   float* P3D;         // [8][n1*3]
   uint8_t* good;      // [8][n1]
-  float* cosbuf;      // [N]
+  float* cosbuf;      // [8][N]
   TVMotionOut* motion;
 };
 // normalise + gather + fit + score + arg-max: 5 launches. Returns launches made in *n_launch.

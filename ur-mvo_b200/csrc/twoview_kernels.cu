@@ -590,7 +590,8 @@ __global__ void tv_argmax_kernel(int n_hyp, const float* __restrict__ scores, in
 // ------------------------------------------------------------------------------- motion recovery
 
 
-// Single CTA.  P3D: [8][n1*3], good: [8][n1], cosbuf: [N] scratch.
+// One CTA per motion hypothesis (grid = 8; every CTA repeats the cheap model selection /
+// decomposition, CTA 0 publishes it).  P3D: [8][n1*3], good: [8][n1], cosbuf: [8][N] scratch.
 __global__ void __launch_bounds__(256)
 tv_motion_kernel(int N, int n1, int n_hyp, const float4* __restrict__ uv, const int* __restrict__ m1,
                  const float* __restrict__ Kg, float th2, const float* __restrict__ models,
@@ -699,18 +700,23 @@ tv_motion_kernel(int N, int n1, int n_hyp, const float4* __restrict__ uv, const 
     }
     s_nm = nm;
     s_model = used;
-    out->used_H = used;
-    out->n_motion = nm;
-    for (int h = 0; h < 8; h++) {
-      out->n_good[h] = 0;
-      out->cos_kth[h] = 1.0f;
-      for (int i = 0; i < 9; i++) out->R[h][i] = (h < nm) ? sR[h][i] : 0.0f;
-      for (int i = 0; i < 3; i++) out->t[h][i] = (h < nm) ? st[h][i] : 0.0f;
+    if (blockIdx.x == 0) {
+      out->used_H = used;
+      out->n_motion = nm;
+      for (int h = 0; h < 8; h++) {
+        for (int i = 0; i < 9; i++) out->R[h][i] = (h < nm) ? sR[h][i] : 0.0f;
+        for (int i = 0; i < 3; i++) out->t[h][i] = (h < nm) ? st[h][i] : 0.0f;
+      }
+    }
+    if (blockIdx.x < 8) {  // every CTA owns the entry of its hypothesis
+      out->n_good[blockIdx.x] = 0;
+      out->cos_kth[blockIdx.x] = 1.0f;
     }
   }
   __syncthreads();
   const int nm = s_nm, model = s_model;
   if (model < 0) return;
+  cosbuf += (size_t)blockIdx.x * N;
   const uint32_t* mask = masks + ((size_t)model * n_hyp + best_idx[model]) * words;
   {  // N inliers of the selected model
     int c = 0;
@@ -721,11 +727,11 @@ tv_motion_kernel(int N, int n1, int n_hyp, const float4* __restrict__ uv, const 
       if ((int)threadIdx.x < off) s_red[threadIdx.x] += s_red[threadIdx.x + off];
       __syncthreads();
     }
-    if (threadIdx.x == 0) out->n_inl = s_red[0];
+    if (threadIdx.x == 0 && blockIdx.x == 0) out->n_inl = s_red[0];
     __syncthreads();
   }
   const float fx = sK[0], fy = sK[4], cx = sK[2], cy = sK[5];
-  for (int h = 0; h < nm; h++) {
+  for (int h = blockIdx.x; h < nm; h += gridDim.x) {
     // _check_R_T for motion hypothesis h
     float R[9], t[3], P1[12], P2[12], O2[3];
     for (int i = 0; i < 9; i++) R[i] = sR[h][i];
@@ -863,7 +869,7 @@ cudaError_t launch_tv_ransac(const TVBuffers& b, float sigma, int n_sm, cudaStre
 }
 
 cudaError_t launch_tv_motion(const TVBuffers& b, float th2, cudaStream_t stream) {
-  tv_motion_kernel<<<1, 256, 0, stream>>>(b.N, b.n1, b.n_hyp, b.uv, b.m1, b.K, th2, b.models, b.masks,
+  tv_motion_kernel<<<8, 256, 0, stream>>>(b.N, b.n1, b.n_hyp, b.uv, b.m1, b.K, th2, b.models, b.masks,
                                           b.best_idx, b.best_score, b.P3D, b.good, b.cosbuf, b.motion);
   return cudaGetLastError();
 }
