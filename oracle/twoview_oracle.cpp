@@ -7,8 +7,9 @@
 // identical 8-point sets.
 //
 // Eigen::JacobiSVD (Eigen 3.3.7, absent here) cannot be reproduced bit for bit; it is replaced by
-// a fully specified one-sided (Hestenes) Jacobi SVD, cyclic-by-rows pair order, rotation threshold
-// |g| <= 5e-7*sqrt(a*b), at most 30 sweeps.  All uses in the reference are invariant to the sign /
+// a fully specified one-sided (Hestenes) Jacobi SVD, cyclic-by-rows pair order, a pair is left alone
+// when g^2 <= (5e-7)^2 a b, rotation t = 2g / (d +- sqrt(d^2 + 4 g^2)) with d = b - a, at most 30
+// sweeps; the null vector of the 8x9 fundamental system comes from a Householder QR instead.  All uses in the reference are invariant to the sign /
 // ordering conventions of the SVD (SURVEY.md §7 "RANSAC bit-exactness").
 
 #include <algorithm>
@@ -24,6 +25,7 @@ namespace {
 
 constexpr int kMaxSweeps = 30;
 constexpr float kJacobiTol = 5e-7f;
+constexpr float kJacobiTol2 = kJacobiTol * kJacobiTol;  // the test is gamma^2 <= tol^2 alpha beta (no square root)
 // A column whose squared norm is below kJacobiTiny * ||A||_F^2 is numerically zero (the null column
 // of a rank-deficient DLT system reaches ~1e-20 after a few sweeps); rotating it against the other
 // columns only chases round-off and would keep every solve at the sweep limit.
@@ -67,11 +69,11 @@ void jacobi_onesided(int m, int n, float* A, float* V) {
         const float beta = row_sum(m, [&](int k) { return A[k * n + q] * A[k * n + q]; });
         const float gamma = row_sum(m, [&](int k) { return A[k * n + p] * A[k * n + q]; });
         if (alpha <= tiny || beta <= tiny) continue;
-        if (std::fabs(gamma) <= kJacobiTol * std::sqrt(alpha * beta)) continue;
+        if (gamma * gamma <= kJacobiTol2 * (alpha * beta)) continue;
         rotated = true;
-        float zeta = (beta - alpha) / (2.0f * gamma);
-        float t = 1.0f / (std::fabs(zeta) + std::sqrt(1.0f + zeta * zeta));
-        if (zeta < 0.0f) t = -t;
+        const float dlt = beta - alpha;
+        const float rad = std::sqrt(dlt * dlt + 4.0f * (gamma * gamma));
+        const float t = (2.0f * gamma) / (dlt >= 0.0f ? dlt + rad : dlt - rad);
         float c = 1.0f / std::sqrt(1.0f + t * t);
         float s = c * t;
         for (int k = 0; k < m; k++) {

@@ -32,6 +32,7 @@ namespace {
 
 constexpr int kMaxSweeps = 30;
 constexpr float kJacobiTol = 5e-7f;
+constexpr float kJacobiTol2 = kJacobiTol * kJacobiTol;  // the test is gamma^2 <= tol^2 alpha beta (no square root)
 // columns with squared norm <= kJacobiTiny * ||A||_F^2 are numerically zero and are not rotated
 // (otherwise the null column of a rank-deficient system keeps every solve at the sweep limit)
 constexpr float kJacobiTiny = 1e-14f;
@@ -61,11 +62,11 @@ __device__ __noinline__ void jacobi_onesided(int m, int n, float* A, float* V) {
           gamma += ap * aq;
         }
         if (alpha <= tiny || beta <= tiny) continue;
-        if (fabsf(gamma) <= kJacobiTol * sqrtf(alpha * beta)) continue;
+        if (gamma * gamma <= kJacobiTol2 * (alpha * beta)) continue;
         rotated = true;
-        const float zeta = (beta - alpha) / (2.0f * gamma);
-        float t = 1.0f / (fabsf(zeta) + sqrtf(1.0f + zeta * zeta));
-        if (zeta < 0.0f) t = -t;
+        const float dlt = beta - alpha;
+        const float rad = sqrtf(dlt * dlt + 4.0f * (gamma * gamma));
+        const float t = (2.0f * gamma) / (dlt >= 0.0f ? dlt + rad : dlt - rad);
         const float c = 1.0f / sqrtf(1.0f + t * t);
         const float s = c * t;
         for (int k = 0; k < m; k++) {
@@ -116,10 +117,10 @@ __device__ __forceinline__ bool jacobi3_pair(float (&A)[9], float (&V)[9], float
     gamma += ap * aq;
   }
   if (alpha <= tiny || beta <= tiny) return false;
-  if (fabsf(gamma) <= kJacobiTol * sqrtf(alpha * beta)) return false;
-  const float zeta = (beta - alpha) / (2.0f * gamma);
-  float t = 1.0f / (fabsf(zeta) + sqrtf(1.0f + zeta * zeta));
-  if (zeta < 0.0f) t = -t;
+  if (gamma * gamma <= kJacobiTol2 * (alpha * beta)) return false;
+  const float dlt = beta - alpha;
+  const float rad = sqrtf(dlt * dlt + 4.0f * (gamma * gamma));
+  const float t = (2.0f * gamma) / (dlt >= 0.0f ? dlt + rad : dlt - rad);
   const float c = 1.0f / sqrtf(1.0f + t * t);
   const float s = c * t;
 #pragma unroll
@@ -343,11 +344,11 @@ __device__ void jacobi_null_vector_sub(float* A, float* V, int r, unsigned mask,
         const float beta = row_sum<M>(aq * aq, mask);
         const float gamma = row_sum<M>(ap * aq, mask);
         if (alpha <= tiny || beta <= tiny) continue;
-        if (fabsf(gamma) <= kJacobiTol * sqrtf(alpha * beta)) continue;
+        if (gamma * gamma <= kJacobiTol2 * (alpha * beta)) continue;
         rotated = true;
-        const float zeta = (beta - alpha) / (2.0f * gamma);
-        float t = 1.0f / (fabsf(zeta) + sqrtf(1.0f + zeta * zeta));
-        if (zeta < 0.0f) t = -t;
+        const float dlt = beta - alpha;
+        const float rad = sqrtf(dlt * dlt + 4.0f * (gamma * gamma));
+        const float t = (2.0f * gamma) / (dlt >= 0.0f ? dlt + rad : dlt - rad);
         const float c = 1.0f / sqrtf(1.0f + t * t);
         const float s = c * t;
         A[r * N + p] = c * ap - s * aq;
