@@ -64,6 +64,11 @@ typedef struct {
   int32_t dense_solver;  /* windows whose reduced camera system is solved in shared memory (<= 16 free cameras):
                             0 -> block-Jacobi PCG (default, the same solver as the large systems),
                             1 -> direct LDL^T factorisation (what g2o's LinearSolverEigen does; same speed) */
+  int32_t large_mode;    /* one large window (>= 100k observations) and the point-sharded solve:
+                            0 -> tile mode when it fits (points renumbered along the trajectory, S as a block band,
+                                 direct block-banded Cholesky — csrc/ba_large.cu), else the atomic / PCG kernels,
+                            1 -> always the round-1 path (global fp64 atomics + block-Jacobi PCG),
+                            2 -> tile mode or URMVO_ERR_UNSUPPORTED */
 } urmvo_ba_options;
 
 typedef struct {
@@ -127,6 +132,13 @@ int urmvo_sharded_ba_create(urmvo_ctx* ctx, urmvo_ba_plan** plan, int Nc, const 
                             const int32_t* cam, const int32_t* pt, const double* intr, double chi2_thr,
                             int it0, int it1, const uint8_t* covis, const urmvo_ba_options* opts);
 int urmvo_sharded_ba_run(urmvo_ba_plan* plan);
+
+/* Phase times of the last run of a large / sharded plan in tile mode, from CUDA events around the first
+ * trial of every enqueued batch: ms[0] linearise, ms[1] all-reduce of the reduced camera system,
+ * ms[2] direct band solve, ms[3] back-substitution + trial cost + decision.  info[0] = 1 if the plan
+ * runs in tile mode, info[1] = block half-bandwidth of S, info[2] = trials enqueued, info[3] = host
+ * synchronisations, info[4] = doubles per all-reduce of the reduced system.  Returns URMVO_OK. */
+int urmvo_ba_plan_phase_info(urmvo_ba_plan* plan, float* ms4, int32_t* info5);
 
 /* Development aid: SM cycles spent per phase by window 0 of the BA launches since the last reset
  * (0 LIN diag, 1 LIN, 2 reduce, 3 PCG, 4 camera update, 5 BACKSUB, 6 reduce, 7 unused). */

@@ -31,6 +31,8 @@ struct BAWin {
   int acc_mode;     // 0: fp64 atomics into the global block-sparse S + BSR PCG (large systems)
                     // 1: warp-private shared-memory copies + dense in-smem PCG (<= 16 free cameras)
                     // 2/3: packed groups, 1/2 register-resident blocks per lane (+ dense PCG)
+                    // 4: tile mode (csrc/ba_large.cu): point chunks with S-stationary register blocks,
+                    //    band storage of S and a direct block-banded Cholesky solve
   int n_grp;        // packed modes: number of point groups
   int acc_len;      // acc_mode 1: doubles per accumulator copy = nblk*36 + Ncf*12
   double intr[4];   // fx fy cx cy
@@ -69,6 +71,18 @@ struct BAWin {
   double* bl;              // Np*3
   double* part;            // scope reduction scratch: 2 * nblk_scope * 8
   double* Spart;           // acc_mode 1: one accumulator copy per CTA of the scope (nblk_scope * acc_len)
+  // ---- tile mode (acc_mode 4): one large problem as phase kernels, csrc/ba_large.cu.  Points are
+  // renumbered by their first free camera and cut into CHUNKS of consecutive points whose reduced-
+  // system blocks (<= 256, inside a window of <= 32 consecutive free cameras) are owned one per thread.
+  // S is stored as a full band: block (i, j), i <= j <= i + bw, at row_ptr[i] + (j - i).
+  int n_chunk, bw;
+  const int* chunk_grp;    // n_chunk+1  packed groups of each chunk
+  const int* grp_cbase;    // n_grp      first free camera of the chunk window of a group
+  const int* chunk_blk;    // n_chunk+1  blocks owned by the threads of a chunk, into blk_desc
+  const int* blk_desc;     // 2 ints per block: (ci - cbase) | (cj - cbase) << 8, index of the block in S
+  double* Lband;           // Ncf*(bw+1)*36 block columns of the Cholesky factor (diagonals as reciprocals)
+  double* cpart;           // per-CTA partial sums of the phase kernels [grid][4]
+  unsigned int* ticket;    // last-CTA tickets of the phase kernels
   // ---- outputs
   double* pose_out;        // Nc*7 T_wc
   double* pts_out;         // Np*3

@@ -170,6 +170,17 @@ struct urmvo_ba_plan {
   int n6 = 0;
   void* shard_state = nullptr;       // device
   void* shard_state_host = nullptr;  // pinned + mapped mirror written by k_sh_decide
+  // tile mode (csrc/ba_large.cu): one large problem as plain phase kernels, direct band solve
+  bool tile = false;
+  int band_m = 0;                    // bw + 1
+  int ncf = 0;
+  size_t off_hd = 0;                 // [hdiag | scal] is the all-reduce buffer of the lambda initialisation
+  size_t n_reduce_diag = 0;
+  std::vector<int> pt_perm;          // device point index -> caller's point index
+  // phase times of the last run (ms, CUDA events on the context stream): LIN, all-reduce, solve, BACKSUB
+  float phase_ms[4] = {0, 0, 0, 0};
+  int n_trial_launches = 0, n_host_syncs = 0;
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 namespace {
@@ -180,6 +191,10 @@ struct WinHost {
   int acc_mode = 0, acc_len = 0;
   std::vector<int> grp_pt;  // packed modes: point groups with <= 32 observations and <= 32 points
   std::vector<int> pt_start, cam_free, row_ptr, col, lrow_ptr, lcol, lblk;
+  // tile mode (acc_mode 4, csrc/ba_large.cu)
+  int bw = 0, n_chunk = 0;
+  std::vector<int> pt_order;  // new point index -> caller's point index
+  std::vector<int> chunk_grp, grp_cbase, chunk_blk, blk_desc;
 };
 
 // Builds CSR over points, free-camera indices and the upper-BSR structure of S for one window.
@@ -287,6 +302,149 @@ int build_window(int Nc, const uint8_t* fixed, int Np, int No, const int32_t* ob
   return URMVO_OK;
 }
 
+
+// Tile mode (csrc/ba_large.cu) for ONE large problem.  Renumbers the points by their first free
+// camera, keeps every point's observations together (caller's relative order), stores S as a full
+// block band and cuts the points into chunks whose blocks fit one CTA (<= 256 blocks inside a window
+// of <= 32 consecutive free cameras).  `order` receives the observation permutation (sorted position
+// -> caller index).  Returns 1 when the problem does not fit the mode (caller falls back to the
+// atomic / PCG path), 0 on success, < 0 on invalid input.
+int build_large(int Nc, const uint8_t* fixed, int Np, int No, const int32_t* obs_cam, const int32_t* obs_pt,
+                const uint8_t* covis, int n_sm, int max_m, WinHost& w, std::vector<int>& order) {
+  w.Nc = Nc; w.Np = Np; w.No = No;
+  w.cam_free.assign(Nc, -1);
+  w.Ncf = 0;
+  for (int c = 0; c < Nc; c++)
+    if (!fixed[c]) w.cam_free[c] = w.Ncf++;
+  const int n = w.Ncf;
+  if (n == 0 || Np == 0 || No == 0) return 1;
+  std::vector<int> cnt(Np, 0), kmin(Np, n), kmax_c(Np, -1);
+  for (int o = 0; o < No; o++) {
+    const int p = obs_pt[o], c = obs_cam[o];
+    if ((unsigned)p >= (unsigned)Np || (unsigned)c >= (unsigned)Nc)
+      return fail(URMVO_ERR_ARG, "local_ba: observation index out of range");
+    cnt[p]++;
+    const int cf = w.cam_free[c];
+    if (cf >= 0) { kmin[p] = std::min(kmin[p], cf); kmax_c[p] = std::max(kmax_c[p], cf); }
+  }
+  w.kmax = 1;
+  for (int l = 0; l < Np; l++) w.kmax = std::max(w.kmax, cnt[l]);
+  if (w.kmax > 32) return 1;
+  // points by first free camera (counting sort, stable); points seen by fixed cameras only go last
+  w.pt_order.resize(Np);
+  {
+    std::vector<int> start(n + 2, 0);
+    for (int l = 0; l < Np; l++) start[kmin[l] + 1]++;
+    for (int k = 0; k <= n; k++) start[k + 1] += start[k];
+    for (int l = 0; l < Np; l++) w.pt_order[start[kmin[l]]++] = l;
+  }
+  std::vector<int> inv(Np);
+  for (int q = 0; q < Np; q++) inv[w.pt_order[q]] = q;
+  w.pt_start.assign(Np + 1, 0);
+  for (int q = 0; q < Np; q++) w.pt_start[q + 1] = w.pt_start[q] + cnt[w.pt_order[q]];
+  order.resize(No);
+  {
+    std::vector<int> fill(w.pt_start.begin(), w.pt_start.end() - 1);
+    for (int o = 0; o < No; o++) order[fill[inv[obs_pt[o]]]++] = o;  // stable inside a point
+  }
+  // a camera that sees the same point twice is not supported by the one-slot-per-(point, camera) table
+  {
+    std::vector<int> seen(Nc, -1);
+    for (int q = 0; q < Np; q++)
+      for (int s = w.pt_start[q]; s < w.pt_start[q + 1]; s++) {
+        const int c = obs_cam[order[s]];
+        if (seen[c] == q) return 1;
+        seen[c] = q;
+      }
+  }
+  // block half-bandwidth of S
+  int bw = 0;
+  if (covis) {
+    for (int i = 0; i < n; i++)
+      for (int j = i + 1; j < n; j++)
+        if (covis[(size_t)i * n + j]) bw = std::max(bw, j - i);
+  } else {
+    for (int l = 0; l < Np; l++)
+      if (kmax_c[l] >= 0) bw = std::max(bw, kmax_c[l] - kmin[l]);
+  }
+  if (bw + 1 > max_m) return 1;
+  w.bw = bw;
+  w.row_ptr.assign(n + 1, 0);
+  for (int i = 0; i < n; i++) w.row_ptr[i + 1] = w.row_ptr[i] + std::min(bw, n - 1 - i) + 1;
+  w.nblk = w.row_ptr[n];
+  w.col.resize(w.nblk);
+  for (int i = 0; i < n; i++)
+    for (int e = w.row_ptr[i]; e < w.row_ptr[i + 1]; e++) w.col[e] = i + (e - w.row_ptr[i]);
+  w.lrow_ptr.assign(n + 1, 0);
+  for (int j = 0; j < n; j++) w.lrow_ptr[j + 1] = w.lrow_ptr[j] + std::min(bw, j);
+  w.lcol.resize(w.lrow_ptr[n]);
+  w.lblk.resize(w.lrow_ptr[n]);
+  for (int j = 0; j < n; j++)
+    for (int e = 0; e < std::min(bw, j); e++) {
+      const int i = j - std::min(bw, j) + e;
+      w.lcol[w.lrow_ptr[j] + e] = i;
+      w.lblk[w.lrow_ptr[j] + e] = w.row_ptr[i] + (j - i);
+    }
+  // chunks of consecutive (renumbered) points
+  auto window_blocks = [&](int c0, int c1) {
+    long long b = 0;
+    for (int ci = c0; ci <= c1; ci++) b += std::min(c1, ci + bw) - ci + 1;
+    return b;
+  };
+  const int cap = std::max(96, (Np + n_sm - 1) / n_sm);
+  w.chunk_grp.assign(1, 0);
+  w.chunk_blk.assign(1, 0);
+  w.grp_pt.assign(1, 0);
+  w.grp_cbase.clear();
+  w.blk_desc.clear();
+  int q = 0;
+  while (q < Np) {
+    const int lq = w.pt_order[q];
+    int c0 = kmin[lq], c1 = kmax_c[lq];
+    const bool no_cam = c1 < 0;
+    if (!no_cam && (c1 - c0 + 1 > 32 || window_blocks(c0, c1) > 256)) return 1;
+    int q_end = q + 1;
+    while (q_end < Np && q_end - q < cap) {
+      const int l = w.pt_order[q_end];
+      if ((kmax_c[l] < 0) != no_cam) break;
+      if (!no_cam) {
+        const int n1 = std::max(c1, kmax_c[l]);  // kmin is non-decreasing: c0 stays
+        if (n1 - c0 + 1 > 32 || window_blocks(c0, n1) > 256) break;
+        c1 = n1;
+      }
+      q_end++;
+    }
+    // packed groups of the chunk: <= 32 observations and <= 32 points each
+    int obs = 0, pts_in = 0;
+    for (int l = q; l < q_end; l++) {
+      const int k = w.pt_start[l + 1] - w.pt_start[l];
+      if ((obs + k > 32 || pts_in == 32) && pts_in > 0) {
+        w.grp_pt.push_back(l);
+        w.grp_cbase.push_back(no_cam ? 0 : c0);
+        obs = 0; pts_in = 0;
+      }
+      obs += k;
+      pts_in++;
+    }
+    w.grp_pt.push_back(q_end);
+    w.grp_cbase.push_back(no_cam ? 0 : c0);
+    w.chunk_grp.push_back((int)w.grp_cbase.size());
+    if (!no_cam)
+      for (int ci = c0; ci <= c1; ci++)
+        for (int cj = ci; cj <= std::min(c1, ci + bw); cj++) {
+          w.blk_desc.push_back((ci - c0) | ((cj - c0) << 8));
+          w.blk_desc.push_back(w.row_ptr[ci] + (cj - ci));
+        }
+    w.chunk_blk.push_back((int)w.blk_desc.size() / 2);
+    q = q_end;
+  }
+  w.n_chunk = (int)w.chunk_grp.size() - 1;
+  w.acc_mode = 4;
+  w.acc_len = 0;
+  w.dup_cam = false;
+  return 0;
+}
+
 }  // namespace
 
 extern "C" void urmvo_ba_plan_destroy(urmvo_ba_plan* p) {
@@ -296,6 +454,7 @@ extern "C" void urmvo_ba_plan_destroy(urmvo_ba_plan* p) {
   else if (p->dev) cudaFree(p->dev);
   if (p->shard_state) cudaFree(p->shard_state);
   if (p->shard_state_host) cudaFreeHost(p->shard_state_host);
+  for (cudaEvent_t e : p->ev) if (e) cudaEventDestroy(e);
   delete p;
 }
 
@@ -325,7 +484,18 @@ static int ba_plan_create_impl(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, const
     const int Nc = cam_off[w + 1] - cam_off[w], Np = pt_off[w + 1] - pt_off[w], No = obs_off[w + 1] - obs_off[w];
     if (Nc <= 0 || Np < 0 || No < 0) { delete p; return fail(URMVO_ERR_ARG, "ba_plan_create: bad window offsets"); }
   }
-  {  // windows are independent: flatten them on all host threads
+  const int large_mode = opts ? opts->large_mode : 0;
+  bool tile = false;
+  if (B == 1 && large_mode != 1 && (sharded || obs_off[1] - obs_off[0] >= 100000)) {
+    const int rc = build_large(cam_off[1] - cam_off[0], fixed + cam_off[0], pt_off[1] - pt_off[0], obs_off[1] - obs_off[0],
+                               cam + obs_off[0], pt + obs_off[0], covis, ctx->n_sm, lg_band_max_m(), wh[0], orders[0]);
+    if (rc < 0) { delete p; return rc; }
+    tile = rc == 0;
+    if (tile) sorted_w[0] = 0;
+    else wh[0] = WinHost();
+  }
+  if (large_mode == 2 && !tile) { delete p; return fail(URMVO_ERR_UNSUPPORTED, "ba options: large_mode 2 (tile mode) does not fit this problem"); }
+  if (!tile) {  // windows are independent: flatten them on all host threads
     const int nt = std::max(1, std::min({urmvo::host_threads(), 16, B / 4}));
     std::atomic<int> next(0);
     auto work = [&]() {
@@ -376,6 +546,7 @@ static int ba_plan_create_impl(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, const
   // free cameras; global fp64 atomics + BSR PCG otherwise
   const int force = opts ? opts->force_atomic : 0;  // 1: mode 0, 2: mode <= 1
   for (auto& w : wh) {
+    if (tile) break;
     w.acc_len = w.nblk * 36 + w.Ncf * 12;
     w.acc_mode = 0;
     if (!p->use_grid && force != 1 && !w.dup_cam && w.Ncf <= 16) {
@@ -396,7 +567,7 @@ static int ba_plan_create_impl(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, const
     }
   }
   const size_t smem_budget = 200 * 1024;
-  for (;;) {
+  for (; !tile;) {
     const int nw = p->threads / 32;
     int stride = 0, pcg_d = 0, ints = p->kmax;
     for (auto& w : wh) {
@@ -448,7 +619,17 @@ static int ba_plan_create_impl(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, const
   p->cluster_size = cs;
   p->n_clusters = B;
   int nblk_scope = cs;
-  if (p->use_grid) {
+  p->tile = tile;
+  if (tile) {
+    p->use_grid = true;
+    p->grid_blocks = ctx->n_sm;
+    p->band_m = wh[0].bw + 1;
+    p->ncf = wh[0].Ncf;
+    p->pt_perm = wh[0].pt_order;
+    nblk_scope = 4 * ctx->n_sm;
+    if (band_smem_bytes(p->band_m, p->ncf) > 220 * 1024) { delete p; return fail(URMVO_ERR_UNSUPPORTED, "local_ba: too many free cameras for the direct band solve"); }
+    if (lg_prepare(p->band_m, p->ncf) != cudaSuccess) { delete p; return fail(URMVO_ERR_CUDA, "ba_plan_create: cudaFuncSetAttribute failed"); }
+  } else if (p->use_grid) {
     p->grid_blocks = sharded ? shard_grid_capacity(p->threads, p->kmax) : ba_grid_capacity(p->threads, p->kmax);
     if (p->grid_blocks <= 0) { delete p; return fail(URMVO_ERR_CUDA, "ba_plan_create: occupancy query failed"); }
     nblk_scope = p->grid_blocks;
@@ -471,6 +652,10 @@ static int ba_plan_create_impl(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, const
   const size_t o_pt_start = A.take<int>(TP + B), o_cam_free = A.take<int>(TC), o_grp = A.take<int>(sum_grp + 1);
   const size_t o_row_ptr = A.take<int>(sum_ncf + B), o_col = A.take<int>(sum_blk);
   const size_t o_lrow_ptr = A.take<int>(sum_ncf + B), o_lcol = A.take<int>(sum_blk), o_lblk = A.take<int>(sum_blk);
+  // tile mode: chunk / block-ownership tables
+  const WinHost& w0 = wh[0];
+  const size_t o_chunk_grp = A.take<int>(tile ? w0.chunk_grp.size() : 0), o_grp_cbase = A.take<int>(tile ? w0.grp_cbase.size() : 0);
+  const size_t o_chunk_blk = A.take<int>(tile ? w0.chunk_blk.size() : 0), o_blk_desc = A.take<int>(tile ? w0.blk_desc.size() : 0);
   p->off_wins = A.take<BAWin>(B);
   const size_t upload_end = A.off;  // everything above is filled from the host
   size_t o_cam[2], o_camRt[2], o_pts[2];
@@ -479,10 +664,15 @@ static int ba_plan_create_impl(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, const
   size_t sum_rec = 0;
   for (auto& w : wh) if (w.acc_mode >= 2) sum_rec += (w.grp_pt.size() - 1) * 32;
   const size_t o_rec = A.take<ObsRec>(sum_rec);
+  const size_t o_hd = A.take<double>(tile ? (size_t)w0.Ncf * 6 : 0);  // tile mode: [hdiag | scal] is reduced at the lambda initialisation
   const size_t o_scal = A.take<double>(32);  // sharded: head of the contiguous all-reduce buffer
   const size_t o_S = A.take<double>((size_t)sum_blk * 36);
   const size_t o_vec = A.take<double>((size_t)(sum_ncf + B) * 6 * 8);  // bs bp hdiag xp r z p Ap (indexed by c_ncf, which counts Ncf+1 per window)
-  if (sharded) {
+  if (tile) {
+    p->off_hd = o_hd;
+    p->n_reduce_diag = (o_scal - o_hd) / sizeof(double) + 32;
+  }
+  if (sharded || tile) {
     p->off_scal = o_scal;
     p->n6 = wh[0].Ncf * 6;
     p->n_reduce_main = (o_vec - o_scal) / sizeof(double) + (size_t)2 * p->n6;  // scal | S | pad | b_s | b_p
@@ -499,6 +689,9 @@ static int ba_plan_create_impl(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, const
     if (wh[w].acc_mode) spart_total += (size_t)nblk_scope * wh[w].acc_len;
   }
   const size_t o_spart = A.take<double>(spart_total);
+  const size_t o_lband = A.take<double>(tile ? (size_t)w0.Ncf * (w0.bw + 1) * 36 : 0);
+  const size_t o_cpart = A.take<double>(tile ? (size_t)16 * ctx->n_sm : 0);
+  const size_t o_ticket = A.take<unsigned int>(tile ? 8 : 0);
   p->off_pose_out = A.take<double>(TC * 7);
   p->off_pts_out = A.take<double>(TP * 3);
   p->off_inlier = A.take<uint8_t>(TO);
@@ -522,7 +715,7 @@ static int ba_plan_create_impl(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, const
 
   // ---- host staging of the small index arrays + descriptors (pinned), big arrays copied directly
   const size_t idx_bytes = upload_end - o_pt_start;
-  if (ctx->ensure_pinned(idx_bytes + (all_sorted ? 0 : TO * (sizeof(double) * 2 + 2 * sizeof(int))))) {
+  if (ctx->ensure_pinned(idx_bytes + (all_sorted ? 0 : TO * (sizeof(double) * 2 + 2 * sizeof(int))) + (tile ? TP * 3 * sizeof(double) : 0))) {
     urmvo_ba_plan_destroy(p);
     return fail(URMVO_ERR_CUDA, "cudaMallocHost failed");
   }
@@ -585,6 +778,21 @@ static int ba_plan_create_impl(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, const
     d.pts_out = (double*)(D + p->off_pts_out) + p0 * 3;
     d.inlier = D + p->off_inlier + ob0;
     d.stats = (urmvo_ba_stats*)(D + p->off_stats) + w;
+    if (tile) {
+      std::memcpy(hp(o_chunk_grp), W.chunk_grp.data(), W.chunk_grp.size() * sizeof(int));
+      std::memcpy(hp(o_grp_cbase), W.grp_cbase.data(), W.grp_cbase.size() * sizeof(int));
+      std::memcpy(hp(o_chunk_blk), W.chunk_blk.data(), W.chunk_blk.size() * sizeof(int));
+      if (!W.blk_desc.empty()) std::memcpy(hp(o_blk_desc), W.blk_desc.data(), W.blk_desc.size() * sizeof(int));
+      d.n_chunk = W.n_chunk; d.bw = W.bw;
+      d.chunk_grp = (const int*)(D + o_chunk_grp);
+      d.grp_cbase = (const int*)(D + o_grp_cbase);
+      d.chunk_blk = (const int*)(D + o_chunk_blk);
+      d.blk_desc = (const int*)(D + o_blk_desc);
+      d.Lband = (double*)(D + o_lband);
+      d.cpart = (double*)(D + o_cpart);
+      d.ticket = (unsigned int*)(D + o_ticket);
+      d.hdiag = (double*)(D + o_hd);
+    }
     if (w == 0) p->run.timing_stats = d.stats;
     c_pt += W.Np + 1;
     c_ncf += W.Ncf + 1;
@@ -597,7 +805,20 @@ static int ba_plan_create_impl(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, const
   };
   cudaError_t e1 = up(o_pt_start, H, idx_bytes);
   cudaError_t e2 = up(o_pose_in, poses, TC * 7 * sizeof(double));
-  cudaError_t e3 = up(o_pts_in, pts, TP * 3 * sizeof(double));
+  cudaError_t e3;
+  std::vector<int> pt_inv;
+  if (tile) {  // points renumbered by first free camera
+    double* hpts = (double*)(H + idx_bytes + (all_sorted ? 0 : TO * (sizeof(double) * 2 + 2 * sizeof(int))));
+    pt_inv.resize(TP);
+    for (size_t q = 0; q < TP; q++) {
+      const int l = p->pt_perm[q];
+      pt_inv[l] = (int)q;
+      hpts[q * 3] = pts[(size_t)l * 3]; hpts[q * 3 + 1] = pts[(size_t)l * 3 + 1]; hpts[q * 3 + 2] = pts[(size_t)l * 3 + 2];
+    }
+    e3 = up(o_pts_in, hpts, TP * 3 * sizeof(double));
+  } else {
+    e3 = up(o_pts_in, pts, TP * 3 * sizeof(double));
+  }
   cudaError_t e4, e5;
   cudaError_t e8 = cudaSuccess;
   if (all_sorted) {
@@ -612,7 +833,7 @@ static int ba_plan_create_impl(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, const
       huv[o * 2] = uv[(size_t)perm[o] * 2];
       huv[o * 2 + 1] = uv[(size_t)perm[o] * 2 + 1];
       hcam[o] = cam[perm[o]];
-      hpt[o] = pt[perm[o]];
+      hpt[o] = tile ? pt_inv[pt[perm[o]]] : pt[perm[o]];
     }
     e4 = up(o_uv, huv, TO * 2 * sizeof(double));
     e5 = up(o_ocam, hcam, TO * sizeof(int));
@@ -620,8 +841,13 @@ static int ba_plan_create_impl(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, const
   }
   cudaError_t e6 = cudaMemsetAsync(D + p->off_stats, 0, sizeof(urmvo_ba_stats) * B, s);
   if (sharded && e6 == cudaSuccess) e6 = cudaMemsetAsync(D + o_scal, 0, o_vec - o_scal + (size_t)8 * p->n6 * sizeof(double), s);
-  if (sharded && e6 == cudaSuccess) e6 = cudaMalloc(&p->shard_state, shard_state_bytes());
-  if (sharded && e6 == cudaSuccess) e6 = cudaHostAlloc(&p->shard_state_host, shard_state_bytes(), cudaHostAllocMapped);
+  const size_t state_bytes = std::max(shard_state_bytes(), lg_state_bytes());
+  if ((sharded || tile) && e6 == cudaSuccess) e6 = cudaMalloc(&p->shard_state, state_bytes);
+  if ((sharded || tile) && e6 == cudaSuccess) e6 = cudaHostAlloc(&p->shard_state_host, state_bytes, cudaHostAllocMapped);
+  if (tile && e6 == cudaSuccess) e6 = cudaMemsetAsync(D + o_hd, 0, o_vec - o_hd + (size_t)8 * p->n6 * sizeof(double), s);
+  if (tile)
+    for (cudaEvent_t& ev : p->ev)
+      if (e6 == cudaSuccess) e6 = cudaEventCreate(&ev);
   // the pinned staging buffer is reused by later calls: wait for the copies that read it
   cudaError_t e7 = cudaStreamSynchronize(s);
   for (cudaError_t e : {e1, e2, e3, e4, e5, e6, e7, e8})
@@ -695,9 +921,84 @@ extern "C" int urmvo_sharded_ba_create(urmvo_ctx* ctx, urmvo_ba_plan** plan, int
   const int32_t co[2] = {0, Nc}, po[2] = {0, Np}, oo[2] = {0, No};
   urmvo_ba_options o = {};
   if (opts) o = *opts;
-  o.force_atomic = 1;
+  o.force_atomic = 1;  // when the tile mode does not fit: global atomics + BSR PCG (the round-1 path)
   return ba_plan_create_impl(ctx, plan, 1, co, po, oo, poses, fixed, pts, uv, cam, pt, intr, chi2_thr, it0, it1, &o,
                              true, covis);
+}
+
+
+// Tile mode (csrc/ba_large.cu): the LM loop of one large problem (alone or as one rank of the
+// point-sharded solve).  Whole LM iterations are enqueued without synchronising: the LM state lives on
+// the device, kernels of trials that turned out not to be needed return at once; the host looks at
+// the state once per batch of enqueued trials (normally once per optimize() call).  Every rank
+// enqueues the same sequence because every rank sees the same reduced values.
+static int run_large(urmvo_ba_plan* p) {
+  urmvo_ctx* ctx = p->ctx;
+  cudaStream_t s = ctx->stream;
+  const BAWin* wins = (const BAWin*)(p->dev + p->off_wins);
+  double* scal = (double*)(p->dev + p->off_scal);
+  double* hd = (double*)(p->dev + p->off_hd);
+  const int G = p->grid_blocks;
+  const bool multi = ctx->comm && ctx->world > 1;
+  auto allreduce = [&](double* buf, size_t n) -> int {
+    if (!multi) return 0;
+    const int rc = g_nccl.AllReduce(buf, buf, n, NcclApi::kFloat64, NcclApi::kSum, ctx->comm, s);
+    if (rc != 0) return fail(URMVO_ERR_NCCL, std::string("ncclAllReduce: ") + g_nccl.GetErrorString(rc));
+    return 0;
+  };
+#define LG_TRY(expr) do { cudaError_t _e = (expr); ctx->launches++; if (_e != cudaSuccess) return fail(URMVO_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); } while (0)
+  for (float& v : p->phase_ms) v = 0.f;
+  p->n_trial_launches = 0; p->n_host_syncs = 0;
+  struct Mark { int kind; };  // events are only recorded for the first trial of every batch (cheap, representative)
+  LG_TRY(launch_lg_init(wins, p->shard_state, 2 * G, s));
+  LG_TRY(launch_lg_pack(wins, 2 * G, s));
+  for (int pass = 0; pass < 2; pass++) {
+    const int n_iter = pass == 0 ? p->run.it0 : p->run.it1;
+    LG_TRY(launch_lg_begin_pass(p->shard_state, pass == 0 ? 1 : 0, n_iter, s));
+    if (n_iter > 0) {
+      // computeLambdaInit: diag(Hpp), max diag(Hll), chi2 — one all-reduce of [hdiag | scal]
+      CU_TRY(cudaMemsetAsync(hd, 0, p->n_reduce_diag * sizeof(double), s));
+      LG_TRY(launch_lg_lin(wins, p->run, p->shard_state, scal, 1, ctx->rank, G, s));
+      if (allreduce(hd, p->n_reduce_diag)) return URMVO_ERR_NCCL;
+      LG_TRY(launch_lg_lambda(wins, p->shard_state, scal, ctx->world, s));
+      int remaining = n_iter;
+      for (;;) {
+        for (int t = 0; t < remaining; t++) {
+          const bool timed = (t == 0);
+          CU_TRY(cudaMemsetAsync(scal, 0, p->n_reduce_main * sizeof(double), s));
+          if (timed) CU_TRY(cudaEventRecord(p->ev[0], s));
+          LG_TRY(launch_lg_lin(wins, p->run, p->shard_state, scal, 0, ctx->rank, G, s));
+          if (timed) CU_TRY(cudaEventRecord(p->ev[1], s));
+          if (allreduce(scal, p->n_reduce_main)) return URMVO_ERR_NCCL;
+          if (timed) CU_TRY(cudaEventRecord(p->ev[2], s));
+          LG_TRY(launch_lg_solve(wins, p->shard_state, p->band_m, p->ncf, s));
+          if (timed) CU_TRY(cudaEventRecord(p->ev[3], s));
+          LG_TRY(launch_lg_backsub(wins, p->run, p->shard_state, scal, 2 * G, s));
+          if (allreduce(scal + 2, 2)) return URMVO_ERR_NCCL;
+          LG_TRY(launch_lg_decide(p->shard_state, scal, p->shard_state_host, s));
+          if (timed) CU_TRY(cudaEventRecord(p->ev[4], s));
+          p->n_trial_launches++;
+        }
+        CU_TRY(cudaStreamSynchronize(s));
+        p->n_host_syncs++;
+        for (int k = 0; k < 4; k++) {
+          float ms = 0.f;
+          if (cudaEventElapsedTime(&ms, p->ev[k], p->ev[k + 1]) == cudaSuccess) p->phase_ms[k] += ms;
+        }
+        int active = 0, it = 0;
+        lg_flags(p->shard_state_host, &active, &it);
+        if (!active) break;
+        remaining = std::max(1, n_iter - it);
+      }
+    }
+    LG_TRY(launch_lg_classify(wins, p->run, p->shard_state, pass, 2 * G, s));
+    ctx->launches++;
+    if (pass == 0) LG_TRY(launch_lg_pack(wins, 2 * G, s));  // new edge levels
+  }
+  LG_TRY(launch_lg_finish(wins, p->shard_state, 2 * G, s));
+#undef LG_TRY
+  CU_TRY(cudaStreamSynchronize(s));
+  return URMVO_OK;
 }
 
 // Host-driven LM loop of the sharded problem: identical control flow on every rank, the decisions
@@ -706,6 +1007,7 @@ extern "C" int urmvo_sharded_ba_run(urmvo_ba_plan* p) {
   if (!p || !p->sharded) return fail(URMVO_ERR_ARG, "sharded_ba_run: not a sharded plan");
   urmvo_ctx* ctx = p->ctx;
   CU_TRY(cudaSetDevice(ctx->device));
+  if (p->tile) return run_large(p);
   cudaStream_t s = ctx->stream;
   const BAWin* wins = (const BAWin*)(p->dev + p->off_wins);
   double* scal = (double*)(p->dev + p->off_scal);
@@ -756,6 +1058,7 @@ extern "C" int urmvo_ba_plan_run(urmvo_ba_plan* p) {
   if (!p) return fail(URMVO_ERR_ARG, "ba_plan_run: null plan");
   if (p->sharded) return urmvo_sharded_ba_run(p);
   CU_TRY(cudaSetDevice(p->ctx->device));
+  if (p->tile) return run_large(p);
   const BAWin* wins = (const BAWin*)(p->dev + p->off_wins);
   cudaError_t e;
   if (p->use_grid) e = launch_ba_grid(wins, p->run, p->kmax, p->grid_blocks, p->threads, p->ctx->stream);
@@ -771,7 +1074,12 @@ extern "C" int urmvo_ba_plan_download(urmvo_ba_plan* p, double* poses, double* p
   CU_TRY(cudaSetDevice(p->ctx->device));
   cudaStream_t s = p->ctx->stream;
   if (poses) CU_TRY(cudaMemcpyAsync(poses, p->dev + p->off_pose_out, (size_t)p->total_c * 7 * sizeof(double), cudaMemcpyDeviceToHost, s));
-  if (pts) CU_TRY(cudaMemcpyAsync(pts, p->dev + p->off_pts_out, (size_t)p->total_p * 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  std::vector<double> ptmp;
+  if (pts && p->pt_perm.empty()) CU_TRY(cudaMemcpyAsync(pts, p->dev + p->off_pts_out, (size_t)p->total_p * 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (pts && !p->pt_perm.empty()) {
+    ptmp.resize((size_t)p->total_p * 3);
+    CU_TRY(cudaMemcpyAsync(ptmp.data(), p->dev + p->off_pts_out, ptmp.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+  }
   std::vector<uint8_t> tmp;
   if (inlier) {
     if (p->perm.empty()) {
@@ -785,10 +1093,27 @@ extern "C" int urmvo_ba_plan_download(urmvo_ba_plan* p, double* poses, double* p
   CU_TRY(cudaStreamSynchronize(s));
   if (inlier && !p->perm.empty())
     for (int o = 0; o < p->total_o; o++) inlier[p->perm[o]] = tmp[o];
+  if (pts && !p->pt_perm.empty())
+    for (int q = 0; q < p->total_p; q++) {
+      const size_t l = (size_t)p->pt_perm[q];
+      pts[l * 3] = ptmp[(size_t)q * 3]; pts[l * 3 + 1] = ptmp[(size_t)q * 3 + 1]; pts[l * 3 + 2] = ptmp[(size_t)q * 3 + 2];
+    }
+  return URMVO_OK;
+}
+
+extern "C" int urmvo_ba_plan_phase_info(urmvo_ba_plan* p, float* ms4, int32_t* info5) {
+  if (!p || !ms4 || !info5) return fail(URMVO_ERR_ARG, "ba_plan_phase_info: null argument");
+  for (int k = 0; k < 4; k++) ms4[k] = p->phase_ms[k];
+  info5[0] = p->tile ? 1 : 0;
+  info5[1] = p->tile ? p->band_m - 1 : -1;
+  info5[2] = p->n_trial_launches;
+  info5[3] = p->n_host_syncs;
+  info5[4] = (int32_t)p->n_reduce_main;
   return URMVO_OK;
 }
 
 extern "C" int urmvo_debug_ba_timing(uint64_t* cycles8, int reset) {
+  if (!cycles8) return fail(URMVO_ERR_ARG, "debug_ba_timing: null output");
   unsigned long long t[8];
   CU_TRY(ba_timing_read(t, reset != 0));
   for (int i = 0; i < 8; i++) cycles8[i] = t[i];

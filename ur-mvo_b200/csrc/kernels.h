@@ -39,6 +39,23 @@ cudaError_t launch_sh_classify(const BAWin* w, const BARun& run, void* stt, int 
                                cudaStream_t s);
 cudaError_t launch_sh_finish(const BAWin* w, void* stt, int grid, int threads, cudaStream_t s);
 void shard_flags(const void* host_copy, int* cont_trials, int* terminate);
+// large problems in tile mode (ba_large.cu): plain launches on the context stream, no grid barriers
+size_t lg_state_bytes();
+int lg_band_max_m();
+size_t band_smem_bytes(int M, int Ncf);
+cudaError_t lg_prepare(int M, int Ncf);
+cudaError_t launch_lg_init(const BAWin* w, void* stt, int grid, cudaStream_t s);
+cudaError_t launch_lg_begin_pass(void* stt, int robust, int n_iter, cudaStream_t s);
+cudaError_t launch_lg_pack(const BAWin* w, int grid, cudaStream_t s);
+cudaError_t launch_lg_lin(const BAWin* w, const BARun& run, void* stt, double* scal, int diag, int rank, int grid,
+                          cudaStream_t s);
+cudaError_t launch_lg_lambda(const BAWin* w, void* stt, const double* scal, int world, cudaStream_t s);
+cudaError_t launch_lg_solve(const BAWin* w, void* stt, int M, int Ncf, cudaStream_t s);
+cudaError_t launch_lg_backsub(const BAWin* w, const BARun& run, void* stt, double* scal, int grid, cudaStream_t s);
+cudaError_t launch_lg_decide(void* stt, const double* scal, void* host_copy, cudaStream_t s);
+cudaError_t launch_lg_classify(const BAWin* w, const BARun& run, void* stt, int pass, int grid, cudaStream_t s);  // 2 launches
+cudaError_t launch_lg_finish(const BAWin* w, void* stt, int grid, cudaStream_t s);
+void lg_flags(const void* host_copy, int* active, int* it);
 constexpr int kBAPartWidth = 8;  // doubles per CTA and buffer in BAWin::part (+8 flag doubles)
 
 // ---- pose_kernels.cu

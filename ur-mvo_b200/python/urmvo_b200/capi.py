@@ -9,7 +9,7 @@ _LIB = None
 EXPORTED_SYMBOLS = [
     "urmvo_version", "urmvo_last_error", "urmvo_create", "urmvo_destroy", "urmvo_stream", "urmvo_sync",
     "urmvo_launch_count", "urmvo_local_ba", "urmvo_local_ba_batch", "urmvo_ba_plan_create",
-    "urmvo_ba_plan_run", "urmvo_ba_plan_download", "urmvo_ba_plan_destroy", "urmvo_debug_ba_timing", "urmvo_nccl_unique_id", "urmvo_comm_init", "urmvo_ba_covisibility",
+    "urmvo_ba_plan_run", "urmvo_ba_plan_download", "urmvo_ba_plan_destroy", "urmvo_ba_plan_phase_info", "urmvo_debug_ba_timing", "urmvo_nccl_unique_id", "urmvo_comm_init", "urmvo_ba_covisibility",
     "urmvo_sharded_ba_create", "urmvo_sharded_ba_run", "urmvo_pose_only_batch",
     "urmvo_pose_plan_create", "urmvo_pose_plan_run", "urmvo_pose_plan_download", "urmvo_pose_plan_destroy",
     "urmvo_two_view", "urmvo_tv_plan_create", "urmvo_tv_plan_run_ransac", "urmvo_tv_plan_download_hyps",
@@ -30,7 +30,8 @@ class FMStats(C.Structure):
 
 class BAOptions(C.Structure):
     _fields_ = [("pcg_tol", C.c_double), ("pcg_max_iter", C.c_int32), ("cluster_size", C.c_int32),
-                ("threads", C.c_int32), ("force_atomic", C.c_int32), ("dense_solver", C.c_int32)]
+                ("threads", C.c_int32), ("force_atomic", C.c_int32), ("dense_solver", C.c_int32),
+                ("large_mode", C.c_int32)]
 
 
 class BAStats(C.Structure):
@@ -311,6 +312,17 @@ def shard_points(prob, rank, world):
     return loc
 
 
+def _phase_info(L, h):
+    """Phase times (ms) and counters of the last run of a large / sharded plan (tile mode)."""
+    ms = (C.c_float * 4)()
+    info = (C.c_int32 * 5)()
+    _check(L.urmvo_ba_plan_phase_info(h, ms, info), "urmvo_ba_plan_phase_info")
+    return {"tile_mode": bool(info[0]), "half_bandwidth_blocks": int(info[1]), "trials_enqueued": int(info[2]),
+            "host_syncs": int(info[3]), "allreduce_doubles_per_trial": int(info[4]),
+            "phase_ms_first_trial_of_each_batch": {"lin": float(ms[0]), "allreduce": float(ms[1]), "solve": float(ms[2]),
+                                                   "backsub_decide": float(ms[3])}}
+
+
 class ShardedBAPlan:
     """One large BA sharded by point over the ranks of ctx's NCCL communicator (or alone)."""
 
@@ -330,6 +342,9 @@ class ShardedBAPlan:
 
     def run(self):
         _check(self._L.urmvo_sharded_ba_run(self._h), "urmvo_sharded_ba_run")
+
+    def phase_info(self):
+        return _phase_info(self._L, self._h)
 
     def download(self):
         poses = np.zeros(self.shapes[0]); pts = np.zeros(self.shapes[1]); inl = np.zeros(self.shapes[2], dtype=np.uint8)
@@ -382,6 +397,9 @@ class BAPlan:
 
     def run(self):
         _check(self._L.urmvo_ba_plan_run(self._h), "urmvo_ba_plan_run")
+
+    def phase_info(self):
+        return _phase_info(self._L, self._h)
 
     def download(self):
         poses = np.zeros(self.shapes[0]); pts = np.zeros(self.shapes[1]); inl = np.zeros(self.shapes[2], dtype=np.uint8)
