@@ -143,6 +143,9 @@ int urmvo_ba_plan_phase_info(urmvo_ba_plan* plan, float* ms4, int32_t* info5);
 /* Development aid: SM cycles spent per phase by window 0 of the BA launches since the last reset
  * (0 LIN diag, 1 LIN, 2 reduce, 3 PCG, 4 camera update, 5 BACKSUB, 6 reduce, 7 unused). */
 int urmvo_debug_ba_timing(uint64_t* cycles8, int reset);
+/* Same for the direct band solve of the tile mode (thread 0 of its CTA): 0 diagonal factorisation,
+ * 1 panel, 2 trailing update, 3 back substitution, 4 whole kernel, 5 tail, 6 block steps. */
+int urmvo_debug_lg_timing(uint64_t* cycles8, int reset);
 
 /* ------------------------------------------------------------------ pose-only (B7-B8) */
 

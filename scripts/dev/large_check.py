@@ -19,7 +19,7 @@ def report(tag, g, o):
     op, ox, oi, os_ = o
     rel = abs(gs.chi2_final[1] - os_.chi2_final[1]) / abs(os_.chi2_final[1])
     print(f"[{tag}] rel cost diff {rel:.2e}; pose maxdiff {np.abs(gp-op).max():.2e}; pts maxdiff {np.abs(gx-ox).max():.2e}; "
-          f"inlier mismatches {(gi!=oi).sum()}; iters {list(gs.iters)} vs {list(os_.iters)[:2]}; trials {list(gs.trials)} vs {list(os_.trials)[:2]}; "
+          f"inlier mismatches {(gi!=oi).sum()}; iters {list(gs.iters)} vs {list(os_.iters)[:2]}; trials {list(gs.trials)} vs {sum(r[3] for r in os_.rows())}; "
           f"chi {list(gs.chi2_final)} vs {list(os_.chi2_final)[:2]}", flush=True)
 
 
@@ -65,7 +65,12 @@ if which in ("cfg5", "all"):
     for mode in (0, 1):
         loc = U.shard_points(p, 0, 1)
         plan = U.ShardedBAPlan(ctx, loc, covis=U.ba_covisibility(loc), opts=U.BAOptions(0, 0, 0, 0, 0, 0, mode))
+        ctx.lg_timing(True)
         dt = timed(plan, 2)
+        lt = ctx.lg_timing(True)
+        if mode == 0 and lt[6]:
+            print("    band solve cycles/step: panel seg %.0f, trailing seg %.0f (thread 0: update %.0f, fetch+take %.0f; diagonal warp factor %.0f), backsub %.0f; whole kernel %.0f cyc/step, steps %d"
+                  % (lt[1] / lt[6], lt[2] / lt[6], lt[0] / lt[6], lt[7] / lt[6], lt[5] / lt[6], lt[3] / lt[6], lt[4] / lt[6], lt[6]), flush=True)
         g = plan.download()
         res[mode] = g
         st = g[3]

@@ -18,9 +18,14 @@ for l in dis[start + 1:]:
     if m: cur = int(m.group(2)); continue
     m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", l)
     if m: seq.append((int(m.group(1), 16), cur, m.group(2)))
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass", "--kernel-name", "regex:" + os.environ.get("KREGEX", kname)],
+                     capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 hdr, data = rows[1], rows[2:]
+for k, r in enumerate(data):  # keep the first kernel section only
+    if r and r[0] == "Kernel Name":
+        data = data[:k]
+        break
 ia, isamp, iex = hdr.index("Address"), hdr.index("# Samples"), hdr.index("Instructions Executed")
 stallcols = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
 assert len(data) == len(seq), (len(data), len(seq))

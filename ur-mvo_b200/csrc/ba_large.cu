@@ -38,6 +38,11 @@ struct LgState {
   int active;  // the current optimize() call still has trials to run
 };
 
+// development aid (urmvo_debug_lg_timing): SM cycles of thread 0 of the band solve per segment
+// 0 diagonal factorisation (to barrier 1)  1 panel (to barrier 2)  2 trailing update + row load
+// 3 back substitution  4 whole kernel  5 tail (x_p, scale, cameras)  6 steps
+__device__ unsigned long long g_lg_timing[8];
+
 constexpr int kLgThreads = 256;
 constexpr int kLgWarps = kLgThreads / 32;
 constexpr int kLgStage = kPackFields * kPackSlots;  // doubles per warp
@@ -466,44 +471,58 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 template <int N>
 __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-constexpr int kBandRing = 8;      // columns of the factor in flight during back substitution
-constexpr int kBandMaxM = 17;     // bw + 1 <= 17: M*M <= 289 threads with one register-resident block each
-constexpr int kBandThreads = 320;
+constexpr int kBandHalf = 8;      // columns of the factor per half of the back-substitution ring
+constexpr int kBandMaxM = 17;     // bw + 1 <= 17: M*M <= 289 ring threads with one register-resident block each
+constexpr int kBandThreads = 352; // 10 warps of ring threads + one warp that factorises the diagonal blocks
 
-__host__ __device__ inline int band_cells(int M) { return (M * M > kBandRing * M ? M * M : kBandRing * M); }
+__host__ __device__ inline int band_cells(int M) { return (M * M > 2 * kBandHalf * M ? M * M : 2 * kBandHalf * M); }
 size_t band_smem_bytes(int M, int Ncf) {
-  return ((size_t)band_cells(M) * 36 + (size_t)M * 37 + 48 + (size_t)M * 6 + (size_t)Ncf * 6 + 64) * sizeof(double);
+  return ((size_t)band_cells(M) * 36 + (size_t)2 * M * 37 + 48 + 2 * 36 + 40 + (size_t)Ncf * 6 + 64) * sizeof(double);
 }
 
+// S is stored with a uniform row stride in tile mode: block (i, i + d) at (i * M + d) * 36.
+//
+// Per step k (two CTA barriers):
+//   (b) 6 (M - 1) "row threads" turn the published blocks of column k into L_ik = A_ik L_kk^-T, one row
+//       each (the rows of a block are independent), update the right-hand side, store the factor;
+//   (c) ring threads subtract L_ik L_jk^T from their register-resident trailing blocks; the owners
+//       of column k + 1 and of the diagonal block k + 2 publish theirs to shared memory; MEANWHILE the
+//       diagonal warp applies the last update to diagonal block k + 1, factorises it (6x6 Cholesky,
+//       reciprocal diagonal via rsqrt) and forward-substitutes y_{k+1};
+//   (d) the ring row of step k takes the blocks of row k + M (fetched with cp.async a whole
+//       generation ahead into the thread's private cell).
 __global__ void __launch_bounds__(kBandThreads, 1)
 k_lg_solve(const BAWin* __restrict__ wins, LgState* stt, int M) {
   extern __shared__ __align__(16) unsigned char smem[];
   if (!stt->active) return;
   const BAWin& W = wins[0];
-  const int n = W.Ncf, T = M * M, t = threadIdx.x;
+  const int n = W.Ncf, T = M * M, t = threadIdx.x, lane = t & 31;
   const int n6 = n * 6;
-  double* cells = reinterpret_cast<double*>(smem);   // [T][36]; back substitution: ring [kBandRing][M][36]
-  double* P = cells + (size_t)band_cells(M) * 36;    // [M][37] panel blocks of the current step
-  double* Dk = P + M * 37;                           // 36: L_kk (strict lower) with reciprocal diagonal; +6: y_k
-  double* part = Dk + 48;                            // [M][6] back-substitution partial products
-  double* yv = part + M * 6;                         // n6: right-hand side -> y -> x
+  double* cells = reinterpret_cast<double*>(smem);   // [T][36]; back substitution: ring [2][kBandHalf][M][36]
+  double* P = cells + (size_t)band_cells(M) * 36;    // [M][37] L_ik of the current step
+  double* Praw = P + M * 37;                         // [M][37] blocks of the next column, before the solve
+  double* Dk = Praw + M * 37;                        // 36: L_kk (strict lower) with reciprocal diagonal; +6: y_k
+  double* Dnext = Dk + 48;                           // [2][36] diagonal blocks published by their owners
+  double* Dtmp = Dnext + 72;                         // 36 (+4)
+  double* yv = Dtmp + 40;                            // n6: right-hand side -> y -> x
   double* redv = yv + n6;                            // 64: final reduction
   __shared__ int s_fail;
   const double lambda = stt->lambda;
   const double* __restrict__ S = W.S;
-  const int* __restrict__ row_ptr = W.row_ptr;
   double* __restrict__ Lg = W.Lband;
   const bool ring = t < T;
-  const int r = ring ? t / M : 0, c = ring ? t - r * M : 0;
+  const bool diag_warp = t >= kBandThreads - 32;
+  // column-major ring: the threads of one ring column (the panel of a step) are consecutive
+  const int c = ring ? t / M : 0, r = ring ? t - c * M : 0;
   const int off = ring ? (r - c + M) % M : 0;
   double* cell = cells + (size_t)(ring ? t : 0) * 36;
   for (int i = t; i < n6; i += blockDim.x) yv[i] = W.bs[i];
   if (t == 0) s_fail = 0;
-  // fetch of block (i, i - off): the transposed upper block (i - off, i) at row_ptr[i - off] + off
+  // fetch of block (i, i - off): the transposed upper block (i - off, i)
   auto prefetch = [&](int i) {
     const int j = i - off;
     if (ring && j >= 0 && i < n) {
-      const double* src = S + ((size_t)row_ptr[j] + off) * 36;
+      const double* src = S + ((size_t)j * M + off) * 36;
 #pragma unroll
       for (int q = 0; q < 18; q++) cp_async16(cell + q * 2, src + q * 2);
     }
@@ -524,91 +543,115 @@ k_lg_solve(const BAWin* __restrict__ wins, LgState* stt, int M) {
     }
     return live;
   };
-  int i_cur = r;                 // row of the block this thread holds
-  prefetch(i_cur);
-  bool have = take(i_cur);
-  int pending = i_cur + M;       // row of the next block of this thread
-  bool need_fetch = true;        // its fetch is issued one barrier after the cell was read
-  __syncthreads();
-
-  for (int k = 0; k < n; k++) {
-    const int j_cur = i_cur - off;
-    // (a) diagonal block: 6x6 Cholesky in registers, y_k = L_kk^-1 b_k
-    if (have && off == 0 && i_cur == k) {
+  auto publish = [&](double* dst) {
+#pragma unroll
+    for (int e = 0; e < 36; e++) dst[e] = a[e];
+  };
+  // The diagonal warp: Dnext[kk & 1] minus the update of step kk - 1 -> Cholesky -> Dk, y_kk, factor column.
+  auto factor_diag = [&](int kk, bool with_update) {
+    const double* Dn = Dnext + (kk & 1) * 36;
+    const double* P1 = P + 37;
+    for (int e = lane; e < 36; e += 32) {
+      const int x = e / 6, y = e - x * 6;
+      double v = Dn[e];
+      if (with_update) {
+#pragma unroll
+        for (int q = 0; q < 6; q++) v = fma(-P1[x * 6 + q], P1[y * 6 + q], v);
+      }
+      Dtmp[e] = v;
+    }
+    __syncwarp();
+    if (lane == 0) {
+      double d[36];
+#pragma unroll
+      for (int e = 0; e < 36; e++) d[e] = Dtmp[e];
       bool bad = false;
 #pragma unroll
       for (int q = 0; q < 6; q++) {
-        const double d = a[q * 7];
-        if (!(d > 0.0)) bad = true;
-        const double ri = rsqrt(bad ? 1.0 : d);
-        a[q * 7] = ri;
+        const double dd = d[q * 7];
+        if (!(dd > 0.0)) bad = true;
+        const double ri = rsqrt(bad ? 1.0 : dd);
+        d[q * 7] = ri;
 #pragma unroll
-        for (int x = q + 1; x < 6; x++) a[x * 6 + q] *= ri;
+        for (int x = q + 1; x < 6; x++) d[x * 6 + q] *= ri;
 #pragma unroll
         for (int y = q + 1; y < 6; y++)
 #pragma unroll
-          for (int x = y; x < 6; x++) a[x * 6 + y] -= a[x * 6 + q] * a[y * 6 + q];
+          for (int x = y; x < 6; x++) d[x * 6 + y] -= d[x * 6 + q] * d[y * 6 + q];
       }
       if (bad) s_fail = 1;
       double yk[6];
 #pragma unroll
       for (int x = 0; x < 6; x++) {
-        double v = yv[k * 6 + x];
+        double v = yv[kk * 6 + x];
 #pragma unroll
-        for (int y = 0; y < x; y++) v -= a[x * 6 + y] * yk[y];
-        yk[x] = v * a[x * 7];
+        for (int y = 0; y < x; y++) v -= d[x * 6 + y] * yk[y];
+        yk[x] = v * d[x * 7];
       }
 #pragma unroll
-      for (int x = 0; x < 6; x++) { yv[k * 6 + x] = yk[x]; Dk[36 + x] = yk[x]; }
-      double* Lk = Lg + (size_t)k * M * 36;
+      for (int x = 0; x < 6; x++) { yv[kk * 6 + x] = yk[x]; Dk[36 + x] = yk[x]; }
+      double2* Lk = reinterpret_cast<double2*>(Lg + (size_t)kk * M * 36);
 #pragma unroll
       for (int x = 0; x < 6; x++)
 #pragma unroll
-        for (int y = 0; y < 6; y++) {
-          const double v = y <= x ? a[x * 6 + y] : 0.0;
-          Dk[x * 6 + y] = v;
-          Lk[x * 6 + y] = v;
+        for (int y = 0; y < 6; y += 2) {
+          const double v0 = y <= x ? d[x * 6 + y] : 0.0, v1 = y + 1 <= x ? d[x * 6 + y + 1] : 0.0;
+          Dk[x * 6 + y] = v0; Dk[x * 6 + y + 1] = v1;
+          Lk[(x * 6 + y) >> 1] = make_double2(v0, v1);
         }
-      have = false;
     }
-    __syncthreads();
-    if (s_fail) break;  // uniform: written before the barrier
-    if (need_fetch) { prefetch(pending); need_fetch = false; }
-    // (b) panel: L_ik = A_ik L_kk^-T row by row, right-hand side y_i -= L_ik y_k
-    if (have && off > 0 && j_cur == k) {
+    __syncwarp();
+  };
+  const long long t_start = clock64();
+  long long t_seg[3] = {0, 0, 0}, t_upd = 0, t_take = 0;
+  int i_cur = r;                 // row of the block this thread holds
+  prefetch(i_cur);
+  bool have = take(i_cur);
+  int pending = i_cur + M;       // row of the next block of this thread
+  bool need_fetch = true;        // its fetch is issued a barrier after the cell was read
+  if (have && off == 0 && i_cur < 2) publish(Dnext + i_cur * 36);
+  if (have && off > 0 && i_cur - off == 0) publish(Praw + off * 37);
+  __syncthreads();
+  prefetch(pending);             // every cell has been read
+  need_fetch = false;
+  if (diag_warp) factor_diag(0, false);
+  __syncthreads();
+
+  for (int k = 0; k < n; k++) {
+    const int j_cur = i_cur - off;
+    const long long t0 = clock64();
+    if (s_fail) break;  // uniform: written before the last barrier
+    // (b) panel, one row per thread: L_ik[x][:] = A_ik[x][:] L_kk^-T, y_i[x] -= L_ik[x][:] y_k
+    if (t < 6 * (M - 1)) {
+      const int d = 1 + t / 6, x = t - (d - 1) * 6;
+      if (k + d < n) {
+        const double* src = Praw + d * 37 + x * 6;
+        double row[6];
 #pragma unroll
-      for (int q = 0; q < 6; q++) {
-        const double ri = Dk[q * 7];
-        double lq[6];
+        for (int q = 0; q < 6; q++) row[q] = src[q];
 #pragma unroll
-        for (int p2 = 0; p2 < 6; p2++) lq[p2] = p2 < q ? Dk[q * 6 + p2] : 0.0;
-#pragma unroll
-        for (int x = 0; x < 6; x++) {
-          double v = a[x * 6 + q];
+        for (int q = 0; q < 6; q++) {
+          double v = row[q];
 #pragma unroll
           for (int p2 = 0; p2 < 6; p2++)
-            if (p2 < q) v -= a[x * 6 + p2] * lq[p2];
-          a[x * 6 + q] = v * ri;
+            if (p2 < q) v = fma(-row[p2], Dk[q * 6 + p2], v);
+          row[q] = v * Dk[q * 7];
         }
+        double* dst = P + d * 37 + x * 6;
+        double yy = yv[(k + d) * 6 + x];
+#pragma unroll
+        for (int q = 0; q < 6; q++) { dst[q] = row[q]; yy = fma(-row[q], Dk[36 + q], yy); }
+        yv[(k + d) * 6 + x] = yy;
+        double2* Lk = reinterpret_cast<double2*>(Lg + ((size_t)k * M + d) * 36 + x * 6);
+        Lk[0] = make_double2(row[0], row[1]);
+        Lk[1] = make_double2(row[2], row[3]);
+        Lk[2] = make_double2(row[4], row[5]);
       }
-      double* Pd = P + off * 37;
-      double* Lk = Lg + ((size_t)k * M + off) * 36;
-#pragma unroll
-      for (int e = 0; e < 36; e++) { Pd[e] = a[e]; Lk[e] = a[e]; }
-      double yk[6];
-#pragma unroll
-      for (int q = 0; q < 6; q++) yk[q] = Dk[36 + q];
-#pragma unroll
-      for (int x = 0; x < 6; x++) {
-        double v = yv[i_cur * 6 + x];
-#pragma unroll
-        for (int q = 0; q < 6; q++) v -= a[x * 6 + q] * yk[q];
-        yv[i_cur * 6 + x] = v;
-      }
-      have = false;
     }
+    if (have && j_cur == k) have = false;  // column k is eliminated (panel rows / diagonal warp)
     __syncthreads();
-    // (c) trailing update A_ij -= L_ik L_jk^T
+    const long long t1 = clock64();
+    // (c) trailing update A_ij -= L_ik L_jk^T; the diagonal warp factorises block k + 1 meanwhile
     if (have && j_cur > k) {
       const double* Pi = P + (i_cur - k) * 37;
       const double* Pj = P + (j_cur - k) * 37;
@@ -631,16 +674,35 @@ k_lg_solve(const BAWin* __restrict__ wins, LgState* stt, int M) {
           }
         }
       }
+      if (off == 0 && i_cur == k + 2) publish(Dnext + (i_cur & 1) * 36);  // complete up to the update of step k
+      if (off > 0 && j_cur == k + 1) publish(Praw + off * 37);            // the panel of the next step
+    } else if (diag_warp && k + 1 < n) {
+      const long long td = clock64();
+      factor_diag(k + 1, M > 1);
+      if (lane == 0) t_seg[2] += clock64() - td;
     }
-    // (d) row k + M enters the window: its blocks go to ring row k mod M
+    const long long t1b = clock64();
+    // (d) row k + M enters the window: its blocks go to ring row k mod M.  The take comes BEFORE the
+    // fetches of this step are issued: the cp.async scoreboard is per warp, so a wait behind another
+    // lane's fresh fetch would wait for that fetch (one L2 round trip per step).
+    const bool fetch_now = need_fetch;
+    need_fetch = false;
     if (ring && pending == k + M) {
       have = take(pending);
       i_cur = pending;
       pending += M;
       need_fetch = true;
+      if (have && off == 0 && i_cur == k + 2) publish(Dnext + (i_cur & 1) * 36);  // M == 2
+      if (have && off > 0 && i_cur - off == k + 1) publish(Praw + off * 37);      // off == M - 1
     }
+    if (fetch_now) prefetch(pending);
+    const long long t1c = clock64();
+    __syncthreads();
+    t_seg[0] += t1 - t0; t_seg[1] += clock64() - t1;
+    if (t == 0) { t_upd += t1b - t1; t_take += t1c - t1b; }
   }
   __syncthreads();
+  const long long t_fact = clock64();
   if (s_fail) {
     cp_async_wait_all();
     for (int i = t; i < n6; i += blockDim.x) W.xp[i] = 0.0;
@@ -649,53 +711,81 @@ k_lg_solve(const BAWin* __restrict__ wins, LgState* stt, int M) {
   }
   cp_async_wait_all();
   __syncthreads();
-  // ---- back substitution L^T x = y, columns of the factor streamed through a cp.async ring
-  auto fetch_col = [&](int kk) {
-    if (kk >= 0 && t < M * 18) cp_async16(cells + ((size_t)(kk % kBandRing) * M * 36) + t * 2, Lg + (size_t)kk * M * 36 + t * 2);
+  // ---- back substitution L^T x = y.  The factor comes back through a two-half ring in shared memory:
+  // while warp 0 consumes the kBandHalf columns of one half (lane = (d mod 5, q) multiplies, the five
+  // groups are combined in fixed order by shuffles, every lane solves the 6x6 triangle redundantly),
+  // the other warps fetch the next kBandHalf columns into the other half.
+  {
+    const int col_d = M * 36;  // doubles per column
+    auto fetch_batch = [&](int b, int first, int nthr) {  // columns k_hi(b) .. k_lo(b) -> half b & 1
+      const int k_hi = n - 1 - b * kBandHalf;
+      if (k_hi < 0) return;
+      const int k_lo = k_hi - kBandHalf + 1 > 0 ? k_hi - kBandHalf + 1 : 0;
+      const int chunks = (k_hi - k_lo + 1) * M * 18;
+      double* dst = cells + (size_t)(b & 1) * kBandHalf * col_d;
+      for (int ch = first; ch < chunks; ch += nthr) {
+        const int kc = ch / (M * 18), w2 = ch - kc * (M * 18);
+        cp_async16(dst + (size_t)kc * col_d + w2 * 2, Lg + (size_t)(k_hi - kc) * col_d + w2 * 2);
+      }
+    };
+    fetch_batch(0, t, blockDim.x);
     cp_async_commit();
-  };
-  // kBandRing - 1 columns in flight: the fetch issued in iteration k overwrites the slot of column
-  // k + 2, which every thread finished reading before the first barrier of iteration k + 1
-  constexpr int D = kBandRing - 1;
-  for (int kk = n - 1; kk > n - D; kk--) fetch_col(kk);
-  for (int k = n - 1; k >= 0; k--) {
-    fetch_col(k - (D - 1));
-    cp_async_wait_group<D - 1>();
+    cp_async_wait_all();
     __syncthreads();
-    const double* col = cells + (size_t)(k % kBandRing) * M * 36;
-    if (t < (M - 1) * 6) {
-      const int d = 1 + t / 6, q = t - (d - 1) * 6;
-      double v = 0.0;
-      if (k + d < n) {
+    const int g = lane / 6, q = lane - g * 6;
+    double xl[6] = {0, 0, 0, 0, 0, 0};  // x_{k+1}
+    const int n_batch = (n + kBandHalf - 1) / kBandHalf;
+    for (int b = 0; b < n_batch; b++) {
+      if (t >= 32) {
+        fetch_batch(b + 1, t - 32, blockDim.x - 32);
+        cp_async_commit();
+      } else {
+        const int k_hi = n - 1 - b * kBandHalf;
+        const int k_lo = k_hi - kBandHalf + 1 > 0 ? k_hi - kBandHalf + 1 : 0;
+        const double* half = cells + (size_t)(b & 1) * kBandHalf * col_d;
+        for (int k = k_hi; k >= k_lo; k--) {
+          const double* col = half + (size_t)(k_hi - k) * col_d;
+          double v = 0.0;
+          if (g < 5) {
+            double vv[4] = {0, 0, 0, 0};
 #pragma unroll
-        for (int x = 0; x < 6; x++) v += col[d * 36 + x * 6 + q] * yv[(k + d) * 6 + x];
+            for (int u = 0; u < 4; u++) {  // d = 1 + g + 5u <= 16: independent chains, operands loaded up front
+              const int d = 1 + g + 5 * u;
+              if (d < M && k + d < n) {
+                const double* Lb = col + d * 36 + q;
+                const double* xv = yv + (k + d) * 6;
+                double lb[6], xx[6];
+#pragma unroll
+                for (int x = 0; x < 6; x++) { lb[x] = Lb[x * 6]; xx[x] = (u == 0 && g == 0) ? xl[x] : xv[x]; }
+#pragma unroll
+                for (int x = 0; x < 6; x++) vv[u] = fma(lb[x], xx[x], vv[u]);
+              }
+            }
+            v = (vv[0] + vv[1]) + (vv[2] + vv[3]);
+          }
+          double tot = __shfl_sync(0xffffffffu, v, q);
+#pragma unroll
+          for (int g2 = 1; g2 < 5; g2++) tot += __shfl_sync(0xffffffffu, v, g2 * 6 + q);
+          const double rq = yv[k * 6 + q] - tot;
+          double rr[6];
+#pragma unroll
+          for (int x = 0; x < 6; x++) rr[x] = __shfl_sync(0xffffffffu, rq, x);
+#pragma unroll
+          for (int x = 5; x >= 0; x--) {
+            double s2 = rr[x];
+#pragma unroll
+            for (int x2 = 5; x2 > x; x2--) s2 = fma(-col[x2 * 6 + x], xl[x2], s2);
+            xl[x] = s2 * col[x * 7];
+          }
+          if (lane < 6) yv[k * 6 + lane] = xl[lane];
+          __syncwarp();
+        }
       }
-      part[(d - 1) * 6 + q] = v;
+      cp_async_wait_all();
+      __syncthreads();
     }
-    __syncthreads();
-    if (t == 0) {
-      double v[6];
-#pragma unroll
-      for (int q = 0; q < 6; q++) v[q] = yv[k * 6 + q];
-      for (int d = 0; d < M - 1; d++) {
-#pragma unroll
-        for (int q = 0; q < 6; q++) v[q] -= part[d * 6 + q];
-      }
-      double x[6];
-#pragma unroll
-      for (int q = 5; q >= 0; q--) {
-        double s2 = v[q];
-#pragma unroll
-        for (int x2 = 5; x2 > q; x2--) s2 -= col[x2 * 6 + q] * x[x2];
-        x[q] = s2 * col[q * 7];
-      }
-#pragma unroll
-      for (int q = 0; q < 6; q++) yv[k * 6 + q] = x[q];
-    }
-    // the next iteration's first barrier orders this write before its readers
   }
-  cp_async_wait_all();
-  __syncthreads();
+  const long long t_back = clock64();
   // ---- x_p, pose part of computeScale sum x (lambda x + b_p), trial cameras exp(x_c) * T_c
   double sc = 0.0;
   for (int i = t; i < n6; i += blockDim.x) {
@@ -736,6 +826,13 @@ k_lg_solve(const BAWin* __restrict__ wins, LgState* stt, int M) {
     for (int e = 0; e < 9; e++) o[e] = R[e];
     o[9] = qo[4]; o[10] = qo[5]; o[11] = qo[6];
   }
+  if (t == 0) {
+    const long long t_end = clock64();
+    g_lg_timing[0] += t_upd; g_lg_timing[7] += t_take; g_lg_timing[1] += t_seg[0]; g_lg_timing[2] += t_seg[1];
+    g_lg_timing[3] += t_back - t_fact; g_lg_timing[4] += t_end - t_start;
+    g_lg_timing[6] += n;
+  }
+  if (t == kBandThreads - 32) atomicAdd(&g_lg_timing[5], (unsigned long long)t_seg[2]);  // diagonal warp: factorisation time
 }
 
 // ------------------------------------------------------------------------------- phase BACKSUB
@@ -950,6 +1047,14 @@ k_lg_finish(const BAWin* __restrict__ wins, const LgState* stt) {
 // ------------------------------------------------------------------------------- host launchers
 
 size_t lg_state_bytes() { return sizeof(LgState); }
+cudaError_t lg_timing_read(unsigned long long* out, bool reset) {
+  cudaError_t e = cudaMemcpyFromSymbol(out, g_lg_timing, sizeof(unsigned long long) * 8);
+  if (e == cudaSuccess && reset) {
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    e = cudaMemcpyToSymbol(g_lg_timing, z, sizeof(z));
+  }
+  return e;
+}
 int lg_band_max_m() { return kBandMaxM; }
 
 static size_t lg_lin_smem() {

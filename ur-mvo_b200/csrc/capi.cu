@@ -367,24 +367,20 @@ int build_large(int Nc, const uint8_t* fixed, int Np, int No, const int32_t* obs
     for (int l = 0; l < Np; l++)
       if (kmax_c[l] >= 0) bw = std::max(bw, kmax_c[l] - kmin[l]);
   }
+  if (n >= 2) bw = std::max(bw, 1);  // the band solve looks one block column ahead
   if (bw + 1 > max_m) return 1;
   w.bw = bw;
+  // uniform row stride bw + 1 (the last rows carry unused blocks): block (i, i + d) at i * (bw + 1) + d,
+  // so that the band solve addresses S without an index load
   w.row_ptr.assign(n + 1, 0);
-  for (int i = 0; i < n; i++) w.row_ptr[i + 1] = w.row_ptr[i] + std::min(bw, n - 1 - i) + 1;
+  for (int i = 0; i < n; i++) w.row_ptr[i + 1] = w.row_ptr[i] + bw + 1;
   w.nblk = w.row_ptr[n];
   w.col.resize(w.nblk);
   for (int i = 0; i < n; i++)
-    for (int e = w.row_ptr[i]; e < w.row_ptr[i + 1]; e++) w.col[e] = i + (e - w.row_ptr[i]);
-  w.lrow_ptr.assign(n + 1, 0);
-  for (int j = 0; j < n; j++) w.lrow_ptr[j + 1] = w.lrow_ptr[j] + std::min(bw, j);
-  w.lcol.resize(w.lrow_ptr[n]);
-  w.lblk.resize(w.lrow_ptr[n]);
-  for (int j = 0; j < n; j++)
-    for (int e = 0; e < std::min(bw, j); e++) {
-      const int i = j - std::min(bw, j) + e;
-      w.lcol[w.lrow_ptr[j] + e] = i;
-      w.lblk[w.lrow_ptr[j] + e] = w.row_ptr[i] + (j - i);
-    }
+    for (int e = w.row_ptr[i]; e < w.row_ptr[i + 1]; e++) w.col[e] = i + (e - w.row_ptr[i]);  // >= n: padding
+  w.lrow_ptr.assign(n + 1, 0);  // mirror lists are not used in tile mode
+  w.lcol.clear();
+  w.lblk.clear();
   // chunks of consecutive (renumbered) points
   auto window_blocks = [&](int c0, int c1) {
     long long b = 0;
@@ -1109,6 +1105,14 @@ extern "C" int urmvo_ba_plan_phase_info(urmvo_ba_plan* p, float* ms4, int32_t* i
   info5[2] = p->n_trial_launches;
   info5[3] = p->n_host_syncs;
   info5[4] = (int32_t)p->n_reduce_main;
+  return URMVO_OK;
+}
+
+extern "C" int urmvo_debug_lg_timing(uint64_t* cycles8, int reset) {
+  if (!cycles8) return fail(URMVO_ERR_ARG, "debug_lg_timing: null output");
+  unsigned long long t[8];
+  CU_TRY(lg_timing_read(t, reset != 0));
+  for (int i = 0; i < 8; i++) cycles8[i] = t[i];
   return URMVO_OK;
 }
 

@@ -41,6 +41,7 @@ cudaError_t launch_sh_finish(const BAWin* w, void* stt, int grid, int threads, c
 void shard_flags(const void* host_copy, int* cont_trials, int* terminate);
 // large problems in tile mode (ba_large.cu): plain launches on the context stream, no grid barriers
 size_t lg_state_bytes();
+cudaError_t lg_timing_read(unsigned long long* out, bool reset);
 int lg_band_max_m();
 size_t band_smem_bytes(int M, int Ncf);
 cudaError_t lg_prepare(int M, int Ncf);

@@ -9,7 +9,7 @@ _LIB = None
 EXPORTED_SYMBOLS = [
     "urmvo_version", "urmvo_last_error", "urmvo_create", "urmvo_destroy", "urmvo_stream", "urmvo_sync",
     "urmvo_launch_count", "urmvo_local_ba", "urmvo_local_ba_batch", "urmvo_ba_plan_create",
-    "urmvo_ba_plan_run", "urmvo_ba_plan_download", "urmvo_ba_plan_destroy", "urmvo_ba_plan_phase_info", "urmvo_debug_ba_timing", "urmvo_nccl_unique_id", "urmvo_comm_init", "urmvo_ba_covisibility",
+    "urmvo_ba_plan_run", "urmvo_ba_plan_download", "urmvo_ba_plan_destroy", "urmvo_ba_plan_phase_info", "urmvo_debug_ba_timing", "urmvo_debug_lg_timing", "urmvo_nccl_unique_id", "urmvo_comm_init", "urmvo_ba_covisibility",
     "urmvo_sharded_ba_create", "urmvo_sharded_ba_run", "urmvo_pose_only_batch",
     "urmvo_pose_plan_create", "urmvo_pose_plan_run", "urmvo_pose_plan_download", "urmvo_pose_plan_destroy",
     "urmvo_two_view", "urmvo_tv_plan_create", "urmvo_tv_plan_run_ransac", "urmvo_tv_plan_download_hyps",
@@ -136,6 +136,12 @@ class Context:
         assert uid.size == 128
         _check(self._L.urmvo_comm_init(self._h, C.c_int(rank), C.c_int(world), _p(uid)), "urmvo_comm_init")
         self.rank, self.world = rank, world
+
+    def lg_timing(self, reset=True):
+        """SM cycles per segment of the tile-mode band solve since the last reset (development aid)."""
+        t = (C.c_uint64 * 8)()
+        _check(self._L.urmvo_debug_lg_timing(t, C.c_int(1 if reset else 0)), "urmvo_debug_lg_timing")
+        return list(t)
 
     def ba_timing(self, reset=True):
         """SM cycles per BA phase of window 0 since the last reset (development aid)."""
