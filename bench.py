@@ -308,17 +308,26 @@ def main():
     alg = float(np.mean([algorithmic_bytes([probs[i] for i in orders[k % n_rot]], stats_rot[k % n_rot]) for k in range(args.steps)]))
     own = float(np.mean([own_bytes([probs[i] for i in orders[k % n_rot]], stats_rot[k % n_rot]) for k in range(args.steps)]))
     peak, peak_src = hbm_peak()
-    achieved = alg / (kern_ms * 1e-3) / 1e9
+    # The kernel is matrix-free: per damped solve it moves OUR compulsory bytes (own_bytes),
+    # not the explicit-W bytes of SURVEY.md §8d.  `achieved` is therefore the own-formula figure, which is
+    # what ncu measures as DRAM traffic; the §8d figure is kept as a secondary key.  The binding unit is
+    # the fp64 pipe / issue (ncu: profiles/), so the honest statement is "HBM 5 % busy, fp64-bound".
+    achieved = own / (kern_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "ba_window_cluster_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg, "kernel_ms": kern_ms,
-                "own_formula_bytes_per_launch": own, "own_formula_gbs": own / (kern_ms * 1e-3) / 1e9,
-                "note": "achieved uses SURVEY.md §8d explicit-W bytes per damped solve; the kernel is matrix-free "
-                        "(never writes per-observation blocks) and is fp64-ALU/latency-bound, see DESIGN.md §4"}
+                "algorithmic_bytes_per_launch": own, "kernel_ms": kern_ms,
+                "binding_unit": "fp64 issue / latency (not HBM)",
+                "survey_8d_explicit_w_bytes_per_launch": alg, "survey_8d_explicit_w_gbs": alg / (kern_ms * 1e-3) / 1e9,
+                "survey_8d_explicit_w_frac": alg / (kern_ms * 1e-3) / 1e9 / peak,
+                "note": "achieved = compulsory bytes of the matrix-free formulation (2*24 B/obs + 216 B/point + ... per damped "
+                        "solve) over the kernel time; the SURVEY §8d explicit-W bytes are never moved and are listed only for "
+                        "reference; fp64-pipe utilisation from ncu is in profiles/ (fp64_pipe_active_pct)"}
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         try:
-            roofline["traffic"] = json.load(open(prof)).get("ba_window_cluster_kernel_bytes_per_launch")
+            tj = json.load(open(prof))
+            roofline["traffic"] = tj.get("ba_window_cluster_kernel_bytes_per_launch")
+            roofline["fp64_pipe_active_pct"] = tj.get("ba_window_cluster_kernel_fp64_pipe_active_pct")
         except Exception:
             pass
 
@@ -381,6 +390,11 @@ def main():
            "single_call": {"value": seq_value, "ms_per_step": 1e3 * t_seq / n_e2e, "steps": n_e2e,
                            "how": "one urmvo_local_ba_batch call at a time"}}
 
+    # ---------------------------------------------------------------- point-sharded cfg5 at every N
+    sharded = None
+    if not args.no_extra:
+        sharded = sharded_cfg5(ctx, stream, torch, dist, rank, world, peak)
+
     # ---------------------------------------------------------------- parity spot check + CPU baseline (rank 0)
     cpu_baseline = None
     parity = None
@@ -397,6 +411,8 @@ def main():
                                       "CPU restatement of g2o LM — real g2o is not buildable here"}
             if not args.no_extra:
                 extra = side_measurements(ctx, stream, torch)
+        if sharded is not None:
+            extra["ba_sharded_cfg5"] = sharded
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True,
@@ -414,6 +430,71 @@ def main():
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def sharded_cfg5(ctx, stream, torch, dist, rank, world, peak):
+    """BASELINE configs[4]: ONE bundle adjustment with 1000 cameras / 200k points / ~2M observations, points
+    sharded over the `world` GPUs, the reduced camera system all-reduced over NCCL every trial
+    (strong scaling: the problem is fixed).  Collective: every rank calls it.  Returns the dict rank 0
+    reports under extra.ba_sharded_cfg5 (None on the other ranks)."""
+    import urmvo_b200 as U
+    from urmvo_b200 import synth
+    prob = synth.cfg5()
+    if world > 1:
+        uid = torch.from_numpy(U.nccl_unique_id() if rank == 0 else np.zeros(128, dtype=np.uint8)).cuda()
+        dist.broadcast(uid, 0)
+        ctx.comm_init(rank, world, uid.cpu().numpy())
+    loc = U.shard_points(prob, rank, world)
+    cov = torch.from_numpy(U.ba_covisibility(loc).astype(np.int32)).cuda()
+    if world > 1:
+        dist.all_reduce(cov, op=dist.ReduceOp.MAX)
+    cov = cov.cpu().numpy().astype(np.uint8)
+    plan = U.ShardedBAPlan(ctx, loc, covis=cov)
+    plan.run()  # warm-up (NCCL channels, lazy module load)
+    reps = 3
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    ms = []
+    for a, b in ev:
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        a.record(stream)
+        plan.run()
+        b.record(stream)
+        ctx.sync()
+        ms.append(a.elapsed_time(b))
+    t = torch.tensor([float(np.mean(ms))], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item()) * 1e-3
+    info = plan.phase_info()
+    poses, pts, inl, st = plan.download()
+    plan.close()
+    if rank != 0:
+        return None
+    n_b = max(1, info["host_syncs"])
+    ph = {k: v / n_b for k, v in info["phase_ms_first_trial_of_each_batch"].items()}
+    No_loc, Np_loc = loc["uv"].shape[0], loc["pts"].shape[0]
+    b_lin = 168 * No_loc + 96 * Np_loc + 272 * prob["poses"].shape[0]
+    out = {"ms": dt * 1e3, "lm_iters_per_s": (st.iters[0] + st.iters[1]) / dt, "lm_iters": int(st.iters[0] + st.iters[1]),
+           "trials": int(st.trials[0] + st.trials[1]), "pcg_iters": int(st.pcg_iters[0] + st.pcg_iters[1]),
+           "solver": "direct block-banded Cholesky (tile mode)" if info["tile_mode"] else "block-Jacobi PCG (round-1 path)",
+           "half_bandwidth_blocks": info["half_bandwidth_blocks"], "host_syncs_per_solve": info["host_syncs"],
+           "allreduce_bytes_per_trial": 8 * info["allreduce_doubles_per_trial"] if world > 1 else 0,
+           "phase_ms_per_trial": ph, "cameras": int(prob["poses"].shape[0]), "points": int(prob["pts"].shape[0]),
+           "obs": int(prob["uv"].shape[0]), "obs_on_rank0": int(No_loc), "n_gpus": world, "scaling": "strong",
+           "roofline_lin": {"bound": "hbm", "kernel": "k_lg_lin", "achieved": b_lin / (ph["lin"] * 1e-3) / 1e9 if ph["lin"] > 0 else None,
+                            "peak": peak, "unit": "GB/s", "frac": b_lin / (ph["lin"] * 1e-3) / 1e9 / peak if ph["lin"] > 0 else None,
+                            "algorithmic_bytes_per_launch": b_lin, "note": "SURVEY §8d B_lin = 168 No + 96 Np + 272 Nc of the rank's shard"}}
+    import pyoracle as po
+    t0 = time.perf_counter()
+    o = po.local_ba(prob)
+    tc = time.perf_counter() - t0
+    out["cpu_lm_iters_per_s"] = (o[3].iters[0] + o[3].iters[1]) / tc
+    out["cpu_sample"] = "the same problem once, 1 thread (CPU restatement, skyline Cholesky)"
+    out["rel_cost_diff_vs_oracle"] = abs(st.chi2_final[1] - o[3].chi2_final[1]) / abs(o[3].chi2_final[1])
+    out["pose_maxdiff_vs_oracle"] = float(np.abs(poses - o[0]).max())
+    return out
 
 
 def side_measurements(ctx, stream, torch):
@@ -460,10 +541,21 @@ def side_measurements(ctx, stream, torch):
     bplan = U.BAPlan(ctx, pack_ba_batch([big]))
     dt = timed(bplan.run, 2)
     bst = bplan.download()[3][0]
+    binfo = bplan.phase_info()
+    nb = max(1, binfo["host_syncs"])
+    lin_ms = binfo["phase_ms_first_trial_of_each_batch"]["lin"] / nb
+    b_lin4 = int(168 * big["uv"].shape[0] + 96 * big["pts"].shape[0] + 272 * 50)
+    peak4, _ = hbm_peak()
+    t0 = time.perf_counter(); o4 = po.local_ba(big); tc4 = time.perf_counter() - t0
     extra["ba_large_cfg4"] = {"lm_iters_per_s": (bst.iters[0] + bst.iters[1]) / dt, "ms": dt * 1e3,
                               "obs": int(big["uv"].shape[0]), "trials": int(bst.trials[0] + bst.trials[1]),
                               "pcg_iters": int(bst.pcg_iters[0] + bst.pcg_iters[1]),
-                              "linearise_bytes_survey_8d": int(168 * big["uv"].shape[0] + 96 * big["pts"].shape[0] + 272 * 50)}
+                              "tile_mode": binfo["tile_mode"], "phase_ms_per_trial": {k: v / nb for k, v in binfo["phase_ms_first_trial_of_each_batch"].items()},
+                              "linearise_bytes_survey_8d": b_lin4,
+                              "roofline_lin": {"bound": "hbm", "kernel": "k_lg_lin", "achieved": b_lin4 / (lin_ms * 1e-3) / 1e9 if lin_ms > 0 else None,
+                                               "peak": peak4, "unit": "GB/s", "frac": b_lin4 / (lin_ms * 1e-3) / 1e9 / peak4 if lin_ms > 0 else None},
+                              "cpu_lm_iters_per_s": (o4[3].iters[0] + o4[3].iters[1]) / tc4, "cpu_sample": "the same window once, 1 thread",
+                              "rel_cost_diff": abs(bst.chi2_final[1] - o4[3].chi2_final[1]) / abs(o4[3].chi2_final[1])}
     bplan.close()
     # the single 10-keyframe window of configs[0] (latency form: one window on a 16-CTA cluster)
     one = synth.cfg1()

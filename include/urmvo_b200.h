@@ -189,9 +189,24 @@ int urmvo_two_view(urmvo_ctx* ctx, int n1, const float* keys1, int n2, const flo
                    const int32_t* sets, float* T21, float* P3D, uint8_t* triangulated,
                    uint8_t* mask_H, uint8_t* mask_F, urmvo_tv_stats* stats, int* success);
 
+/* Scoring rule of the FUNDAMENTAL hypotheses (the homography rule is always the reference's):
+ *  URMVO_TV_SCORE_REFERENCE  what EpipolarGeometry::_check_F computes (src/epipolar_geometry.cc:372-449): the two
+ *                            squared point-to-epipolar-line distances / sigma^2, each tested against 3.841, each
+ *                            passing one adding 5.991 - chi2 — the default, and the only mode with a reference to match;
+ *  URMVO_TV_SCORE_SAMPSON    Sampson error (x2^T F x1)^2 / (|F x1|_12^2 + |F^T x2|_12^2) / sigma^2, ONE test against
+ *                            3.841 per match, score += 5.991 - chi2 (the mode BASELINE.json's north_star names;
+ *                            bit-exact against the oracle's restatement of the same rule). */
+enum { URMVO_TV_SCORE_REFERENCE = 0, URMVO_TV_SCORE_SAMPSON = 1 };
+int urmvo_two_view_scored(urmvo_ctx* ctx, int n1, const float* keys1, int n2, const float* keys2,
+                          const int32_t* matches12, const float* K, float sigma, int n_hyp,
+                          const int32_t* sets, int score_mode, float* T21, float* P3D, uint8_t* triangulated,
+                          uint8_t* mask_H, uint8_t* mask_F, urmvo_tv_stats* stats, int* success);
+
 int urmvo_tv_plan_create(urmvo_ctx* ctx, urmvo_tv_plan** plan, int n1, const float* keys1, int n2,
                          const float* keys2, const int32_t* matches12, const float* K, float sigma,
                          int n_hyp, const int32_t* sets);
+/* Selects the scoring rule used by the next run_ransac (default URMVO_TV_SCORE_REFERENCE). */
+int urmvo_tv_plan_set_score_mode(urmvo_tv_plan* plan, int score_mode);
 /* Fit + score + arg-max of all hypotheses of both models (asynchronous). */
 int urmvo_tv_plan_run_ransac(urmvo_tv_plan* plan);
 /* Per-hypothesis results for parity tests: model 0 = F, 1 = H.

@@ -104,6 +104,17 @@ int urmvo_oracle_two_view(int n1, const float* keys1, int n2, const float* keys2
 int urmvo_oracle_score_all(int n1, const float* keys1, int n2, const float* keys2,
                            const int32_t* matches12, float sigma, int n_hyp, const int32_t* sets,
                            int model, float* scores, uint32_t* masks, float* models);
+/* Same two entry points with the scoring rule of the fundamental model selectable: score_mode 0 = the
+ * reference's symmetric point-line chi2 (src/epipolar_geometry.cc:372-449), 1 = Sampson error (the extra
+ * mode BASELINE.json's north_star names; not computed by the reference). */
+int urmvo_oracle_two_view_mode(int n1, const float* keys1, int n2, const float* keys2,
+                               const int32_t* matches12, const float* K, float sigma, int n_hyp,
+                               const int32_t* sets, int score_mode, float* T21, float* P3D,
+                               uint8_t* triangulated, uint8_t* mask_H, uint8_t* mask_F,
+                               urmvo_oracle_tv_stats* stats);
+int urmvo_oracle_score_all_mode(int n1, const float* keys1, int n2, const float* keys2,
+                                const int32_t* matches12, float sigma, int n_hyp, const int32_t* sets,
+                                int model, int score_mode, float* scores, uint32_t* masks, float* models);
 
 /* Draw n_hyp x 8 index sets exactly as reconstruct() does (:53-71) with glibc rand().
  * reseed != 0 calls srand(seed) first (Random::seed_rand). */

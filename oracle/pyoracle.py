@@ -49,6 +49,8 @@ def lib():
         _LIB.urmvo_oracle_pose_only.restype = C.c_int
         _LIB.urmvo_oracle_two_view.restype = C.c_int
         _LIB.urmvo_oracle_score_all.restype = C.c_int
+        _LIB.urmvo_oracle_two_view_mode.restype = C.c_int
+        _LIB.urmvo_oracle_score_all_mode.restype = C.c_int
     return _LIB
 
 
@@ -99,7 +101,7 @@ def pose_only_batch(batch, chi2_thr=10.0, rounds=4, its=10, n_threads=1):
     return poses, inl, n_inl
 
 
-def two_view(tv, sets=None):
+def two_view(tv, sets=None, score_mode=0):
     k1 = np.ascontiguousarray(tv["keys1"], dtype=np.float32)
     k2 = np.ascontiguousarray(tv["keys2"], dtype=np.float32)
     m = np.ascontiguousarray(tv["matches12"], dtype=np.int32)
@@ -112,13 +114,13 @@ def two_view(tv, sets=None):
     mH = np.zeros(N, dtype=np.uint8)
     mF = np.zeros(N, dtype=np.uint8)
     st = TVStats()
-    ok = lib().urmvo_oracle_two_view(C.c_int(k1.shape[0]), _p(k1), C.c_int(k2.shape[0]), _p(k2), _p(m), _p(K),
-                                     C.c_float(tv.get("sigma", 1.0)), C.c_int(sets.shape[0]), _p(sets), _p(T21),
-                                     _p(P3D), _p(tri), _p(mH), _p(mF), C.byref(st))
+    ok = lib().urmvo_oracle_two_view_mode(C.c_int(k1.shape[0]), _p(k1), C.c_int(k2.shape[0]), _p(k2), _p(m), _p(K),
+                                          C.c_float(tv.get("sigma", 1.0)), C.c_int(sets.shape[0]), _p(sets),
+                                          C.c_int(score_mode), _p(T21), _p(P3D), _p(tri), _p(mH), _p(mF), C.byref(st))
     return dict(ok=bool(ok), T21=T21, P3D=P3D, triangulated=tri, mask_H=mH, mask_F=mF, stats=st)
 
 
-def score_all(tv, model, sets=None):
+def score_all(tv, model, sets=None, score_mode=0):
     """model 0 = F, 1 = H. Returns scores[n_hyp], masks[n_hyp, words], models[n_hyp, 9]."""
     k1 = np.ascontiguousarray(tv["keys1"], dtype=np.float32)
     k2 = np.ascontiguousarray(tv["keys2"], dtype=np.float32)
@@ -129,9 +131,9 @@ def score_all(tv, model, sets=None):
     scores = np.zeros(sets.shape[0], dtype=np.float32)
     masks = np.zeros((sets.shape[0], words), dtype=np.uint32)
     models = np.zeros((sets.shape[0], 9), dtype=np.float32)
-    lib().urmvo_oracle_score_all(C.c_int(k1.shape[0]), _p(k1), C.c_int(k2.shape[0]), _p(k2), _p(m),
-                                 C.c_float(tv.get("sigma", 1.0)), C.c_int(sets.shape[0]), _p(sets), C.c_int(model),
-                                 _p(scores), _p(masks), _p(models))
+    lib().urmvo_oracle_score_all_mode(C.c_int(k1.shape[0]), _p(k1), C.c_int(k2.shape[0]), _p(k2), _p(m),
+                                      C.c_float(tv.get("sigma", 1.0)), C.c_int(sets.shape[0]), _p(sets), C.c_int(model),
+                                      C.c_int(score_mode), _p(scores), _p(masks), _p(models))
     return scores, masks, models
 
 

@@ -215,6 +215,7 @@ struct TwoView {
   float sigma, sigma2;
   int n_hyp;
   const int32_t* sets;
+  int score_mode = 0;  // 0: the reference's symmetric point-line chi2 (:372-449); 1: Sampson error (extra mode)
   // per-image normalisation (:735-780)
   std::vector<float> pn1, pn2;
   float T1[9], T2[9];
@@ -296,8 +297,39 @@ void fit_H(const TwoView& tv, const int32_t* set, float* H21, float* H12) {
   inv3f(H21, H12);
 }
 
+// Sampson-error variant of _check_F (BASELINE.json north_star (4); NOT what the reference computes):
+//   d = (x2^T F x1)^2 / ((F x1)_1^2 + (F x1)_2^2 + (F^T x2)_1^2 + (F^T x2)_2^2), chi2 = d / sigma^2,
+// one test per match against the 1-dof threshold 3.841, score += 5.991 - chi2 for an inlier.  Same
+// operation order as the CUDA kernel (fp32, no contraction).
+float check_F_sampson(const TwoView& tv, const float* F, uint8_t* mask) {
+  const float f11 = F[0], f12 = F[1], f13 = F[2], f21 = F[3], f22 = F[4], f23 = F[5],
+              f31 = F[6], f32 = F[7], f33 = F[8];
+  float score = 0;
+  const float th = 3.841;
+  const float thScore = 5.991;
+  const float invSigmaSquare = 1.0 / (tv.sigma * tv.sigma);
+  for (int i = 0; i < tv.N; i++) {
+    const float u1 = tv.keys1[tv.m1[i] * 2], v1 = tv.keys1[tv.m1[i] * 2 + 1];
+    const float u2 = tv.keys2[tv.m2[i] * 2], v2 = tv.keys2[tv.m2[i] * 2 + 1];
+    const float a2 = f11 * u1 + f12 * v1 + f13;
+    const float b2 = f21 * u1 + f22 * v1 + f23;
+    const float c2 = f31 * u1 + f32 * v1 + f33;
+    const float num2 = a2 * u2 + b2 * v2 + c2;
+    const float a1 = f11 * u2 + f21 * v2 + f31;
+    const float b1 = f12 * u2 + f22 * v2 + f32;
+    const float den = (a2 * a2 + b2 * b2) + (a1 * a1 + b1 * b1);
+    const float sampson = num2 * num2 / den;
+    const float chiSquare = sampson * invSigmaSquare;
+    bool bIn = true;
+    if (chiSquare > th) bIn = false; else score += thScore - chiSquare;
+    mask[i] = bIn ? 1 : 0;
+  }
+  return score;
+}
+
 // _check_F (:372-449). mask: N bytes.
 float check_F(const TwoView& tv, const float* F, uint8_t* mask) {
+  if (tv.score_mode == 1) return check_F_sampson(tv, F, mask);
   const float f11 = F[0], f12 = F[1], f13 = F[2], f21 = F[3], f22 = F[4], f23 = F[5],
               f31 = F[6], f32 = F[7], f33 = F[8];
   float score = 0;
@@ -634,12 +666,27 @@ void tv_setup(TwoView& tv, int n1, const float* keys1, int n2, const float* keys
 
 }  // namespace
 
+extern "C" int urmvo_oracle_two_view_mode(int n1, const float* keys1, int n2, const float* keys2,
+                                          const int32_t* matches12, const float* K, float sigma,
+                                          int n_hyp, const int32_t* sets, int score_mode, float* T21, float* P3D,
+                                          uint8_t* triangulated, uint8_t* mask_H, uint8_t* mask_F,
+                                          urmvo_oracle_tv_stats* stats);
 extern "C" int urmvo_oracle_two_view(int n1, const float* keys1, int n2, const float* keys2,
                                      const int32_t* matches12, const float* K, float sigma,
                                      int n_hyp, const int32_t* sets, float* T21, float* P3D,
                                      uint8_t* triangulated, uint8_t* mask_H, uint8_t* mask_F,
                                      urmvo_oracle_tv_stats* stats) {
+  return urmvo_oracle_two_view_mode(n1, keys1, n2, keys2, matches12, K, sigma, n_hyp, sets, 0, T21, P3D,
+                                    triangulated, mask_H, mask_F, stats);
+}
+
+extern "C" int urmvo_oracle_two_view_mode(int n1, const float* keys1, int n2, const float* keys2,
+                                          const int32_t* matches12, const float* K, float sigma,
+                                          int n_hyp, const int32_t* sets, int score_mode, float* T21, float* P3D,
+                                          uint8_t* triangulated, uint8_t* mask_H, uint8_t* mask_F,
+                                          urmvo_oracle_tv_stats* stats) {
   TwoView tv;
+  tv.score_mode = score_mode;
   tv_setup(tv, n1, keys1, n2, keys2, matches12, K, sigma, n_hyp, sets);
   urmvo_oracle_tv_stats local;
   urmvo_oracle_tv_stats* st = stats ? stats : &local;
@@ -671,11 +718,23 @@ extern "C" int urmvo_oracle_two_view(int n1, const float* keys1, int n2, const f
   return reconstruct_F(tv, inlF, F, T21, P3D, triangulated, minParallax, 50, st) ? 1 : 0;
 }
 
+extern "C" int urmvo_oracle_score_all_mode(int n1, const float* keys1, int n2, const float* keys2,
+                                           const int32_t* matches12, float sigma, int n_hyp,
+                                           const int32_t* sets, int model, int score_mode, float* scores,
+                                           uint32_t* masks, float* models);
 extern "C" int urmvo_oracle_score_all(int n1, const float* keys1, int n2, const float* keys2,
                                       const int32_t* matches12, float sigma, int n_hyp,
                                       const int32_t* sets, int model, float* scores,
                                       uint32_t* masks, float* models) {
+  return urmvo_oracle_score_all_mode(n1, keys1, n2, keys2, matches12, sigma, n_hyp, sets, model, 0, scores, masks, models);
+}
+
+extern "C" int urmvo_oracle_score_all_mode(int n1, const float* keys1, int n2, const float* keys2,
+                                           const int32_t* matches12, float sigma, int n_hyp,
+                                           const int32_t* sets, int model, int score_mode, float* scores,
+                                           uint32_t* masks, float* models) {
   TwoView tv;
+  tv.score_mode = score_mode;
   tv_setup(tv, n1, keys1, n2, keys2, matches12, nullptr, sigma, n_hyp, sets);
   const int words = (tv.N + 31) / 32;
   std::vector<uint8_t> cur(tv.N);

@@ -18,6 +18,7 @@ if world > 1:
 which = sys.argv[1] if len(sys.argv) > 1 else "small"
 check = "--check" in sys.argv
 tol = float([a for a in sys.argv if a.startswith("--tol=")][0][6:]) if any(a.startswith("--tol=") for a in sys.argv) else 0.0
+mode = int([a for a in sys.argv if a.startswith("--mode=")][0][7:]) if any(a.startswith("--mode=") for a in sys.argv) else 0
 if which == "small":
     prob = synth.make_ba(77, 40, 3000, 9.0, 14, 2, 0.02)
 elif which == "cfg5":
@@ -35,7 +36,7 @@ cov = torch.from_numpy(U.ba_covisibility(loc).astype(np.int32)).cuda()
 if world > 1:
     dist.all_reduce(cov, op=dist.ReduceOp.MAX)
 cov = cov.cpu().numpy().astype(np.uint8)
-plan = U.ShardedBAPlan(ctx, loc, covis=cov, opts=U.BAOptions(tol, 0, 0, 0, 0) if tol > 0 else None)
+plan = U.ShardedBAPlan(ctx, loc, covis=cov, opts=U.BAOptions(tol, 0, 0, 0, 0, 0, mode))
 plan.run()  # warm-up
 if world > 1: dist.barrier()
 torch.cuda.synchronize(); t0 = time.perf_counter()
@@ -47,7 +48,9 @@ poses, pts, inl, st = plan.download()
 its = st.iters[0] + st.iters[1]
 if rank == 0:
     print(f"[sharded BA x{world}] Nc={prob['poses'].shape[0]} Np={prob['pts'].shape[0]} No={prob['uv'].shape[0]} local No={loc['uv'].shape[0]} "
-          f"S blocks={int(cov.sum())}: {dt*1e3:.2f} ms, {its} LM it ({st.trials[0]+st.trials[1]} trials, {st.pcg_iters[0]+st.pcg_iters[1]} PCG it) -> {its/dt:.1f} it/s; chi {list(st.chi2_final)}", flush=True)
+          f"S blocks={int(cov.sum())} tile={plan.phase_info()['tile_mode']}: {dt*1e3:.2f} ms, {its} LM it ({st.trials[0]+st.trials[1]} trials, {st.pcg_iters[0]+st.pcg_iters[1]} PCG it) -> {its/dt:.1f} it/s; chi {list(st.chi2_final)}", flush=True)
+if rank == 0:
+    print("   ", plan.phase_info(), flush=True)
 if check:
     import pyoracle as po
     if rank == 0:

@@ -157,11 +157,49 @@ def test_ba_golden_fixture(ctx):
     assert abs(gs.chi2_final[1] - tr[-1, 1]) <= REL_COST * abs(tr[-1, 1])
 
 
-def test_ba_large_window_cfg4_grid_kernel(oracle, ctx):
-    """400k observations on the cooperative whole-grid kernel; the oracle takes a few seconds."""
+@pytest.mark.parametrize("large_mode", [0, 1])
+def test_ba_large_window_cfg4_grid_kernel(oracle, ctx, large_mode):
+    """400k observations: tile mode (phase kernels, S as a block band, direct banded Cholesky;
+    large_mode 0) and the round-1 cooperative whole-grid kernel (global atomics + PCG; large_mode 1).
+    The oracle takes a few seconds."""
     p = synth.cfg4()
     assert p["uv"].shape[0] > 300000
-    _check_ba(oracle, ctx, p)
+    _check_ba(oracle, ctx, p, opts=U.BAOptions(0, 0, 0, 0, 0, 0, large_mode))
+
+
+def test_ba_large_tile_mode_is_selected_and_bit_reproducible(ctx):
+    """cfg4 runs in tile mode by default; two runs of the same plan agree to the last bit in the LM
+    decisions (iterations, trials) and to 1e-12 in the cost (the chunk flush uses fp64 atomics)."""
+    plan = U.BAPlan(ctx, pack_ba_batch([synth.cfg4()]))
+    plan.run()
+    a = plan.download()
+    info = plan.phase_info()
+    plan.run()
+    b = plan.download()
+    plan.close()
+    assert info["tile_mode"] and 1 <= info["half_bandwidth_blocks"] <= 16
+    assert info["host_syncs"] <= 4  # whole LM iterations are enqueued without synchronising
+    assert list(a[3][0].trials) == list(b[3][0].trials) and np.array_equal(a[2], b[2])
+    assert abs(a[3][0].chi2_final[1] - b[3][0].chi2_final[1]) <= 1e-12 * abs(b[3][0].chi2_final[1])
+
+
+def test_ba_bal_scale_cfg5_single_rank_matches_oracle(oracle, ctx):
+    """BASELINE configs[4] at full size (1000 cameras, 200k points, ~2M observations) on one rank of
+    the point-sharded path: cost, poses, flags and the LM trace against the CPU oracle."""
+    p = synth.cfg5()
+    assert p["poses"].shape[0] == 1000 and p["uv"].shape[0] > 1500000
+    loc = U.shard_points(p, 0, 1)
+    plan = U.ShardedBAPlan(ctx, loc, covis=U.ba_covisibility(loc))
+    plan.run()
+    gp, gx, gi, gs = plan.download()
+    assert plan.phase_info()["tile_mode"]
+    plan.close()
+    op, ox, oi, os_ = oracle.local_ba(p)
+    assert abs(gs.chi2_final[1] - os_.chi2_final[1]) <= REL_COST * abs(os_.chi2_final[1])
+    assert np.abs(gp - op).max() <= POSE_TOL and np.abs(gx - ox).max() <= 1e-4
+    assert np.array_equal(gi, oi)
+    assert list(gs.iters) == list(os_.iters)[:2]
+    assert gs.trials[0] + gs.trials[1] == sum(r[3] for r in os_.rows())
 
 
 def test_ba_rejects_bad_input(ctx):
@@ -206,10 +244,10 @@ def test_pose_only_all_outliers_and_golden(oracle, ctx):
 
 # ------------------------------------------------------------------------------- two view
 
-def _check_hyps(oracle, plan, tv):
+def _check_hyps(oracle, plan, tv, score_mode=0):
     for model in (0, 1):
         gs, gm, gM = plan.download_hyps(model)
-        os_, om, oM = oracle.score_all(tv, model)
+        os_, om, oM = oracle.score_all(tv, model, score_mode=score_mode)
         assert np.array_equal(gs.view(np.uint32), os_.view(np.uint32)), f"scores differ (model {model})"
         assert np.array_equal(gm, om), f"masks differ (model {model})"
         assert np.array_equal(gM.view(np.uint32), oM.view(np.uint32)), f"models differ (model {model})"
@@ -234,6 +272,29 @@ def test_two_view_cfg3_bit_exact(oracle, ctx):
     _check_hyps(oracle, plan, tv)
     _check_reconstruct(plan.reconstruct(), oracle.two_view(tv))
     plan.close()
+
+
+def test_two_view_sampson_mode_bit_exact(oracle, ctx):
+    """BASELINE.json north_star (4): fundamental hypotheses scored with the Sampson error (extra mode;
+    the reference's rule stays the default).  Scores, masks, winner and the reconstruction are bit-exact
+    against the oracle's restatement of the same rule; switching back restores the reference rule."""
+    tv = synth.cfg3(n_hyp=1024)
+    plan = U.TVPlan(ctx, tv)
+    plan.set_score_mode(1)
+    plan.run_ransac()
+    _check_hyps(oracle, plan, tv, score_mode=1)
+    _check_reconstruct(plan.reconstruct(), oracle.two_view(tv, score_mode=1))
+    s1 = plan.download_hyps(0)[0]
+    plan.set_score_mode(0)
+    plan.run_ransac()
+    _check_hyps(oracle, plan, tv, score_mode=0)
+    assert not np.array_equal(s1, plan.download_hyps(0)[0])
+    plan.close()
+    small = synth.make_two_view(11, n_keys=300)
+    small["sets"] = synth.draw_sets(300, 200, 0)
+    _check_reconstruct(ctx.two_view(small, score_mode=1), oracle.two_view(small, score_mode=1))
+    with pytest.raises(U.UrmvoError, match="unknown mode"):
+        ctx.two_view(small, score_mode=7)
 
 
 def test_two_view_full_8192_argmax_properties(oracle, ctx):
@@ -291,11 +352,13 @@ def test_two_view_rejects_bad_input(ctx):
 
 # ------------------------------------------------------------------------------- point-sharded BA
 
-def test_sharded_ba_single_rank_matches_oracle(oracle, ctx):
+@pytest.mark.parametrize("large_mode", [0, 1])
+def test_sharded_ba_single_rank_matches_oracle(oracle, ctx, large_mode):
     """The NCCL-sharded phase-kernel path with a world of one rank (all-reduces are identities)."""
     p = synth.make_ba(77, 40, 1500, 8.0, 14, 2, 0.02)
-    plan = U.ShardedBAPlan(ctx, U.shard_points(p, 0, 1), covis=U.ba_covisibility(p))
+    plan = U.ShardedBAPlan(ctx, U.shard_points(p, 0, 1), covis=U.ba_covisibility(p), opts=U.BAOptions(0, 0, 0, 0, 0, 0, large_mode))
     plan.run()
+    assert plan.phase_info()["tile_mode"] == (large_mode == 0)
     gp, gx, gi, gs = plan.download()
     op, ox, oi, os_ = oracle.local_ba(p)
     assert abs(gs.chi2_final[1] - os_.chi2_final[1]) <= REL_COST * abs(os_.chi2_final[1])
@@ -304,7 +367,8 @@ def test_sharded_ba_single_rank_matches_oracle(oracle, ctx):
     plan.close()
 
 
-def test_sharded_ba_two_ranks_over_nccl(oracle):
+@pytest.mark.parametrize("large_mode", [0, 1])
+def test_sharded_ba_two_ranks_over_nccl(oracle, large_mode):
     """Two GPUs, one process each (torchrun): skipped on a single-GPU box."""
     import subprocess
     import sys
@@ -313,12 +377,14 @@ def test_sharded_ba_two_ranks_over_nccl(oracle):
         pytest.skip("needs 2 GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-                          "127.0.0.1", "--master-port", "29533", os.path.join(root, "scripts", "sharded_ba.py"), "small", "--check"],
+                          "127.0.0.1", "--master-port", "29533", os.path.join(root, "scripts", "sharded_ba.py"), "small", "--check",
+                          f"--mode={large_mode}"],
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     line = [l for l in out.stdout.splitlines() if "rel cost diff" in l][0]
     rel = float(line.split("rel cost diff")[1].split(";")[0])
     assert rel < REL_COST and "inlier mismatches 0" in line
+    assert ("tile=True" in out.stdout) == (large_mode == 0)
 
 
 def test_hypothesis_sharded_ransac_two_ranks(oracle):

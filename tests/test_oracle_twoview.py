@@ -135,3 +135,38 @@ def test_duplicate_sets_give_identical_results_and_unmatched_keys_are_skipped(or
     assert s[7] == s[2] and np.array_equal(m[7], m[2]) and np.array_equal(M[7], M[2])
     assert m.shape[1] == (N + 31) // 32
     assert (m[:, -1] >> (N % 32)).max() == 0  # no bits beyond N
+
+
+def test_sampson_mode_matches_float64_sampson_distance(oracle):
+    po = oracle
+    """The extra scoring mode (Sampson error, BASELINE.json north_star (4)): the oracle's fp32 inlier
+    decisions agree with a float64 evaluation of the same formula except within 1e-3 of the threshold,
+    and the mode only changes the fundamental model's scores."""
+    tv = synth.make_two_view(1003, n_keys=500)
+    tv["sets"] = synth.draw_sets(500, 40, 0)
+    s0, m0, M0 = po.score_all(tv, 0)
+    s1, m1, M1 = po.score_all(tv, 0, score_mode=1)
+    assert np.array_equal(M0, M1) and not np.array_equal(s0, s1)
+    h0 = po.score_all(tv, 1)
+    h1 = po.score_all(tv, 1, score_mode=1)
+    assert np.array_equal(h0[0], h1[0]) and np.array_equal(h0[1], h1[1])
+    m = np.asarray(tv["matches12"])
+    i1 = np.nonzero(m >= 0)[0]
+    x1 = np.c_[np.asarray(tv["keys1"], dtype=np.float64)[i1], np.ones(len(i1))]
+    x2 = np.c_[np.asarray(tv["keys2"], dtype=np.float64)[m[i1]], np.ones(len(i1))]
+    n_checked = 0
+    for h in range(40):
+        F = M1[h].astype(np.float64).reshape(3, 3)
+        Fx1 = x1 @ F.T
+        Ftx2 = x2 @ F
+        num = (x2 * Fx1).sum(1)
+        chi = num ** 2 / (Fx1[:, 0] ** 2 + Fx1[:, 1] ** 2 + Ftx2[:, 0] ** 2 + Ftx2[:, 1] ** 2)
+        ref = chi <= 3.841
+        bits = ((m1[h][np.arange(len(i1)) >> 5] >> (np.arange(len(i1)) & 31)) & 1).astype(bool)
+        clear = np.abs(chi - 3.841) > 1e-3 * np.maximum(1.0, chi)
+        assert np.array_equal(bits[clear], ref[clear])
+        assert abs(float(s1[h]) - float((5.991 - chi[ref]).sum())) <= 1e-3 * max(1.0, float(s1[h]))
+        n_checked += int(clear.sum())
+    assert n_checked > 15000
+    full = po.two_view(tv, score_mode=1)
+    assert full["stats"].best_F >= 0

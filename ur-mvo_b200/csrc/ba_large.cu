@@ -217,11 +217,16 @@ k_lg_lin(const BAWin* __restrict__ wins, BARun run, const LgState* __restrict__ 
   for (int ch = blockIdx.x; ch < W.n_chunk; ch += gridDim.x) {
     const int g_begin = W.chunk_grp[ch], g_end = W.chunk_grp[ch + 1];
     const int b0 = W.chunk_blk[ch], nb = W.chunk_blk[ch + 1] - b0;
-    const bool has = tid < nb;
+    // a chunk with <= 128 blocks is swept by several REPLICAS of the block owners (warp-aligned), each
+    // replica visiting every n_rep-th staged group; all replicas flush
+    const int nb_pad = (nb + 31) & ~31;
+    const int n_rep = nb_pad > 0 ? (kLgThreads / nb_pad > 0 ? kLgThreads / nb_pad : 1) : 1;
+    const int my_rep = nb_pad > 0 ? tid / nb_pad : 0, bidx = nb_pad > 0 ? tid - my_rep * nb_pad : tid;
+    const bool has = my_rep < n_rep && bidx < nb;
     int cil = 0, cjl = 0, gblk = 0;
     if (has) {
-      const int d0 = W.blk_desc[(size_t)(b0 + tid) * 2];
-      gblk = W.blk_desc[(size_t)(b0 + tid) * 2 + 1];
+      const int d0 = W.blk_desc[(size_t)(b0 + bidx) * 2];
+      gblk = W.blk_desc[(size_t)(b0 + bidx) * 2 + 1];
       cil = d0 & 255; cjl = (d0 >> 8) & 255;
     }
     const bool diag_lane = has && cil == cjl;
@@ -335,7 +340,7 @@ k_lg_lin(const BAWin* __restrict__ wins, BARun run, const LgState* __restrict__ 
       // ---- sweep: every thread visits the staged points for the camera pair of ITS block
       for (int ws = 0; ws < kLgWarps; ws++) {
         const int np = s_np[ws];
-        if (np == 0) continue;
+        if (np == 0 || ws % n_rep != my_rep % n_rep) continue;
         PackStage sv;
         sv.f = stage0 + (size_t)ws * kLgStage;
         const unsigned char* sl = slot0 + (size_t)ws * kLgSlotBytes;

@@ -1280,6 +1280,7 @@ struct urmvo_tv_plan {
   std::vector<int> m1, m2;
   unsigned char* dev = nullptr;
   bool borrowed = false;  // dev is the context's grow-only workspace (one-shot urmvo_two_view)
+  int score_mode = 0;     // 0: the reference's symmetric point-line chi2, 1: Sampson error (fundamental model)
   bool ransac_done = false;
 };
 
@@ -1372,7 +1373,7 @@ extern "C" int urmvo_tv_plan_run_ransac(urmvo_tv_plan* p) {
   if (!p) return fail(URMVO_ERR_ARG, "tv_plan_run_ransac: null plan");
   CU_TRY(cudaSetDevice(p->ctx->device));
   int nl = 0;
-  cudaError_t e = launch_tv_ransac(p->b, p->sigma, p->ctx->n_sm, p->ctx->stream, &nl);
+  cudaError_t e = launch_tv_ransac(p->b, p->sigma, p->score_mode, p->ctx->n_sm, p->ctx->stream, &nl);
   if (e != cudaSuccess) return fail(URMVO_ERR_CUDA, std::string("two-view RANSAC launch: ") + cudaGetErrorString(e));
   p->ctx->launches += nl;
   p->ransac_done = true;
@@ -1505,13 +1506,33 @@ extern "C" int urmvo_tv_plan_reconstruct(urmvo_tv_plan* p, float* T21, float* P3
   return URMVO_OK;
 }
 
+extern "C" int urmvo_tv_plan_set_score_mode(urmvo_tv_plan* p, int score_mode) {
+  if (!p) return fail(URMVO_ERR_ARG, "tv_plan_set_score_mode: null plan");
+  if (score_mode != URMVO_TV_SCORE_REFERENCE && score_mode != URMVO_TV_SCORE_SAMPSON)
+    return fail(URMVO_ERR_ARG, "tv_plan_set_score_mode: unknown mode");
+  p->score_mode = score_mode;
+  p->ransac_done = false;
+  return URMVO_OK;
+}
+
 extern "C" int urmvo_two_view(urmvo_ctx* ctx, int n1, const float* keys1, int n2, const float* keys2,
                               const int32_t* matches12, const float* K, float sigma, int n_hyp,
                               const int32_t* sets, float* T21, float* P3D, uint8_t* triangulated,
                               uint8_t* mask_H, uint8_t* mask_F, urmvo_tv_stats* stats, int* success) {
+  return urmvo_two_view_scored(ctx, n1, keys1, n2, keys2, matches12, K, sigma, n_hyp, sets, URMVO_TV_SCORE_REFERENCE,
+                               T21, P3D, triangulated, mask_H, mask_F, stats, success);
+}
+
+extern "C" int urmvo_two_view_scored(urmvo_ctx* ctx, int n1, const float* keys1, int n2, const float* keys2,
+                                     const int32_t* matches12, const float* K, float sigma, int n_hyp,
+                                     const int32_t* sets, int score_mode, float* T21, float* P3D,
+                                     uint8_t* triangulated, uint8_t* mask_H, uint8_t* mask_F,
+                                     urmvo_tv_stats* stats, int* success) {
   urmvo_tv_plan* p = nullptr;
   int rc = tv_plan_create_impl(ctx, &p, n1, keys1, n2, keys2, matches12, K, sigma, n_hyp, sets, true);
   if (rc != URMVO_OK) return rc;
+  rc = urmvo_tv_plan_set_score_mode(p, score_mode);
+  if (rc != URMVO_OK) { urmvo_tv_plan_destroy(p); return rc; }
   rc = urmvo_tv_plan_run_ransac(p);
   if (rc == URMVO_OK) rc = urmvo_tv_plan_reconstruct(p, T21, P3D, triangulated, mask_H, mask_F, stats, success);
   urmvo_tv_plan_destroy(p);

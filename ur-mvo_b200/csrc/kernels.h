@@ -93,7 +93,7 @@ struct TVBuffers {
   TVMotionOut* motion;
 };
 // normalise + gather + fit + score + arg-max: 5 launches. Returns launches made in *n_launch.
-cudaError_t launch_tv_ransac(const TVBuffers& b, float sigma, int n_sm, cudaStream_t stream, int* n_launch);
+cudaError_t launch_tv_ransac(const TVBuffers& b, float sigma, int score_mode, int n_sm, cudaStream_t stream, int* n_launch);
 cudaError_t launch_tv_motion(const TVBuffers& b, float th2, cudaStream_t stream);
 
 // ---- fm_kernels.cu (per-frame fundamental-matrix RANSAC; pts = (x0,y0,x1,y1) per match).

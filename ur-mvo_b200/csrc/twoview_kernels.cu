@@ -483,7 +483,7 @@ tv_fit_sub_kernel(int n_hyp, const int* __restrict__ sets, const float4* __restr
 // scores: [2][n_hyp], masks: [2][n_hyp][words].
 __global__ void __launch_bounds__(256)
 tv_score_kernel(int N, int n_hyp, const float4* __restrict__ uv_g, const float* __restrict__ models,
-                float inv_sigma2, int stage_uv, float* __restrict__ scores,
+                float inv_sigma2, int stage_uv, int score_mode, float* __restrict__ scores,
                 uint32_t* __restrict__ masks) {
   extern __shared__ float4 uv_s[];
   if (stage_uv) {
@@ -511,7 +511,20 @@ tv_score_kernel(int N, int n_hyp, const float4* __restrict__ uv_g, const float* 
         const float4 p = uvp[i];
         const float u1 = p.x, v1 = p.y, u2 = p.z, v2 = p.w;
         bIn = true;
-        if (model == 0) {
+        if (model == 0 && score_mode == 1) {
+          // Sampson error (BASELINE.json north_star (4); extra mode, not the reference's metric):
+          // one 1-dof test per match, same operation order as oracle check_F_sampson
+          const float a2 = m[0] * u1 + m[1] * v1 + m[2];
+          const float b2 = m[3] * u1 + m[4] * v1 + m[5];
+          const float cc2 = m[6] * u1 + m[7] * v1 + m[8];
+          const float num2 = a2 * u2 + b2 * v2 + cc2;
+          const float a1 = m[0] * u2 + m[3] * v2 + m[6];
+          const float b1 = m[1] * u2 + m[4] * v2 + m[7];
+          const float den = (a2 * a2 + b2 * b2) + (a1 * a1 + b1 * b1);
+          const float sampson = num2 * num2 / den;
+          const float chiSquare = sampson * inv_sigma2;
+          if (chiSquare > thF) bIn = false; else c1 = thScore - chiSquare;
+        } else if (model == 0) {
           const float a2 = m[0] * u1 + m[1] * v1 + m[2];
           const float b2 = m[3] * u1 + m[4] * v1 + m[5];
           const float cc2 = m[6] * u1 + m[7] * v1 + m[8];
@@ -835,7 +848,7 @@ tv_motion_kernel(int N, int n1, int n_hyp, const float4* __restrict__ uv, const 
   }
 }
 
-cudaError_t launch_tv_ransac(const TVBuffers& b, float sigma, int n_sm, cudaStream_t stream, int* n_launch) {
+cudaError_t launch_tv_ransac(const TVBuffers& b, float sigma, int score_mode, int n_sm, cudaStream_t stream, int* n_launch) {
   int nl = 0;
   tv_normalize_kernel<<<2, 256, 0, stream>>>(b.n1, b.keys1, b.pn1, b.T1, b.n2, b.keys2, b.pn2, b.T2);
   nl++;
@@ -861,7 +874,7 @@ cudaError_t launch_tv_ransac(const TVBuffers& b, float sigma, int n_sm, cudaStre
   int grid = (2 * b.n_hyp + wpc - 1) / wpc;
   const int cap = n_sm * 8;
   if (grid > cap) grid = cap;
-  tv_score_kernel<<<grid, wpc * 32, stage ? smem : 0, stream>>>(b.N, b.n_hyp, b.uv, b.models, inv_sigma2, stage, b.scores, b.masks);
+  tv_score_kernel<<<grid, wpc * 32, stage ? smem : 0, stream>>>(b.N, b.n_hyp, b.uv, b.models, inv_sigma2, stage, score_mode, b.scores, b.masks);
   nl++;
   tv_argmax_kernel<<<2, 256, 0, stream>>>(b.n_hyp, b.scores, b.best_idx, b.best_score);
   nl++;

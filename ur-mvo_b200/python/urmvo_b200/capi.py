@@ -12,7 +12,7 @@ EXPORTED_SYMBOLS = [
     "urmvo_ba_plan_run", "urmvo_ba_plan_download", "urmvo_ba_plan_destroy", "urmvo_ba_plan_phase_info", "urmvo_debug_ba_timing", "urmvo_debug_lg_timing", "urmvo_nccl_unique_id", "urmvo_comm_init", "urmvo_ba_covisibility",
     "urmvo_sharded_ba_create", "urmvo_sharded_ba_run", "urmvo_pose_only_batch",
     "urmvo_pose_plan_create", "urmvo_pose_plan_run", "urmvo_pose_plan_download", "urmvo_pose_plan_destroy",
-    "urmvo_two_view", "urmvo_tv_plan_create", "urmvo_tv_plan_run_ransac", "urmvo_tv_plan_download_hyps",
+    "urmvo_two_view", "urmvo_two_view_scored", "urmvo_tv_plan_set_score_mode", "urmvo_tv_plan_create", "urmvo_tv_plan_run_ransac", "urmvo_tv_plan_download_hyps",
     "urmvo_tv_plan_reconstruct", "urmvo_tv_plan_destroy",
     "urmvo_fm_ransac", "urmvo_fm_ransac_batch", "urmvo_fm_plan_create", "urmvo_fm_plan_run", "urmvo_fm_plan_finish",
     "urmvo_fm_plan_hypotheses", "urmvo_fm_plan_destroy", "urmvo_triangulate_batch",
@@ -222,7 +222,7 @@ class Context:
                "urmvo_triangulate_batch")
         return out, ok
 
-    def two_view(self, tv, sets=None):
+    def two_view(self, tv, sets=None, score_mode=0):
         k1 = _f32(tv["keys1"]); k2 = _f32(tv["keys2"]); m = _i32(tv["matches12"]); K = _f32(tv["K"])
         sets = _i32(tv["sets"] if sets is None else sets)
         N = int((m >= 0).sum())
@@ -230,10 +230,10 @@ class Context:
         tri = np.zeros(k1.shape[0], dtype=np.uint8)
         mH = np.zeros(N, dtype=np.uint8); mF = np.zeros(N, dtype=np.uint8)
         st = TVStats(); ok = C.c_int(0)
-        _check(self._L.urmvo_two_view(self._h, C.c_int(k1.shape[0]), _p(k1), C.c_int(k2.shape[0]), _p(k2), _p(m),
-                                      _p(K), C.c_float(tv.get("sigma", 1.0)), C.c_int(sets.shape[0]), _p(sets),
-                                      _p(T21), _p(P3D), _p(tri), _p(mH), _p(mF), C.byref(st), C.byref(ok)),
-               "urmvo_two_view")
+        _check(self._L.urmvo_two_view_scored(self._h, C.c_int(k1.shape[0]), _p(k1), C.c_int(k2.shape[0]), _p(k2), _p(m),
+                                             _p(K), C.c_float(tv.get("sigma", 1.0)), C.c_int(sets.shape[0]), _p(sets),
+                                             C.c_int(score_mode), _p(T21), _p(P3D), _p(tri), _p(mH), _p(mF), C.byref(st),
+                                             C.byref(ok)), "urmvo_two_view_scored")
         return dict(ok=bool(ok.value), T21=T21, P3D=P3D, triangulated=tri, mask_H=mH, mask_F=mF, stats=st)
 
 
@@ -472,6 +472,10 @@ class TVPlan:
         _check(self._L.urmvo_tv_plan_create(ctx._h, C.byref(self._h), C.c_int(k1.shape[0]), _p(k1), C.c_int(k2.shape[0]),
                                             _p(k2), _p(m), _p(K), C.c_float(tv.get("sigma", 1.0)), C.c_int(self.n_hyp),
                                             _p(sets)), "urmvo_tv_plan_create")
+
+    def set_score_mode(self, score_mode):
+        """0: the reference's symmetric point-line chi2, 1: Sampson error (fundamental hypotheses)."""
+        _check(self._L.urmvo_tv_plan_set_score_mode(self._h, C.c_int(score_mode)), "urmvo_tv_plan_set_score_mode")
 
     def run_ransac(self):
         _check(self._L.urmvo_tv_plan_run_ransac(self._h), "urmvo_tv_plan_run_ransac")
