@@ -100,6 +100,22 @@ int urmvo_local_ba_batch(urmvo_ctx* ctx, int B, const int32_t* cam_off, const in
                          double chi2_thr, int it0, int it1, uint8_t* inlier, urmvo_ba_stats* stats,
                          const urmvo_ba_options* opts);
 
+/* The same two calls for a STEREO camera (reference src/g2o_optimization.cc:96-118: when the camera type is
+ * STEREO the graph holds the mono edges AND one EdgeStereoSE3ProjectXYZ per stereo constraint).
+ *  uv3 No*3 = (u_left, v_left, u_right); kind No bytes: 1 = stereo edge (3-row residual, Omega = I3, Huber delta
+ *  (float)sqrt(chi2_thr_stereo), outlier threshold chi2_thr_stereo = cfg.stereo_point), 0 = mono edge (u_right
+ *  ignored, chi2_thr_mono = cfg.mono_point); intr5 = fx, fy, cx, cy, bf.  Mono and stereo constraints of the
+ *  reference's two vectors are concatenated by the caller; inlier comes back in the same order. */
+int urmvo_local_ba_stereo(urmvo_ctx* ctx, int Nc, double* poses, const uint8_t* fixed, int Np, double* pts,
+                          int No, const double* uv3, const uint8_t* kind, const int32_t* cam, const int32_t* pt,
+                          const double* intr5, double chi2_thr_mono, double chi2_thr_stereo, int it0, int it1,
+                          uint8_t* inlier, urmvo_ba_stats* stats, const urmvo_ba_options* opts);
+int urmvo_local_ba_batch_stereo(urmvo_ctx* ctx, int B, const int32_t* cam_off, const int32_t* pt_off,
+                                const int32_t* obs_off, double* poses, const uint8_t* fixed, double* pts,
+                                const double* uv3, const uint8_t* kind, const int32_t* cam, const int32_t* pt,
+                                const double* intr5, double chi2_thr_mono, double chi2_thr_stereo, int it0, int it1,
+                                uint8_t* inlier, urmvo_ba_stats* stats, const urmvo_ba_options* opts);
+
 /* Plan API: upload once, run many times from HBM-resident inputs (each run restarts from the
  * uploaded initial estimate), download when wanted. */
 int urmvo_ba_plan_create(urmvo_ctx* ctx, urmvo_ba_plan** plan, int B, const int32_t* cam_off,
@@ -156,6 +172,15 @@ int urmvo_debug_lg_timing(uint64_t* cycles8, int reset);
 int urmvo_pose_only_batch(urmvo_ctx* ctx, int B, const int32_t* obs_off, double* poses,
                           const double* uv, const double* Xw, const double* intr, double chi2_thr,
                           int rounds, int its_per_round, uint8_t* inlier, int32_t* n_inlier);
+
+/* The same with stereo edges (camera type STEREO, reference src/g2o_optimization.cc:235-258,
+ * EdgeStereoSE3ProjectXYZOnlyPose): uv3 No*3 = (u_left, v_left, u_right), kind No bytes (1 = stereo edge:
+ * 3-row residual, Omega = I3, Huber delta (float)sqrt(chi2_thr_stereo), threshold chi2_thr_stereo = cfg.stereo_point;
+ * 0 = mono edge, u_right ignored), intr5 = fx, fy, cx, cy, bf. */
+int urmvo_pose_only_batch_stereo(urmvo_ctx* ctx, int B, const int32_t* obs_off, double* poses,
+                                 const double* uv3, const uint8_t* kind, const double* Xw, const double* intr5,
+                                 double chi2_thr_mono, double chi2_thr_stereo, int rounds, int its_per_round,
+                                 uint8_t* inlier, int32_t* n_inlier);
 
 int urmvo_pose_plan_create(urmvo_ctx* ctx, urmvo_pose_plan** plan, int B, const int32_t* obs_off,
                            const double* poses, const double* uv, const double* Xw,

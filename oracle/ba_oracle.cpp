@@ -192,6 +192,47 @@ inline void edge_jac(const double* R, const double* pc, const Intr& K, double* J
   }
 }
 
+// EdgeStereoSE3ProjectXYZ (types_six_dof_expmap.cpp; used at src/g2o_optimization.cc:96-118, 235-258):
+// measurement (u_left, v_left, u_right), cam_project = (x/z fx + cx, y/z fy + cy, u - bf/z).
+// The generalised edge has THREE rows; a mono edge (kind 0) leaves the third row zero, so every
+// sum below adds exact zeros for it and a mono-only problem gives the bits of the 2-row code.
+inline void edge_error3(const double* pc, const double* uv3, int kind, const Intr& K, double bf, double* e) {
+  edge_error(pc, uv3, K, e);
+  if (kind) {
+    const double invz = 1.0 / pc[2];
+    const double ul = pc[0] * invz * K.fx + K.cx;
+    e[0] = uv3[0] - ul;
+    e[1] = uv3[1] - (pc[1] * invz * K.fy + K.cy);
+    e[2] = uv3[2] - (ul - bf * invz);
+  } else {
+    e[2] = 0.0;
+  }
+}
+
+// Jp: 3x6 (rotation first), Jx: 3x3 (may be null).
+inline void edge_jac3(const double* R, const double* pc, int kind, const Intr& K, double bf, double* Jp, double* Jx) {
+  edge_jac(R, pc, K, Jp, Jx);
+  const double x = pc[0], y = pc[1], z = pc[2], z2 = z * z;
+  if (!kind) {
+    for (int a = 0; a < 6; a++) Jp[12 + a] = 0.0;
+    if (Jx) for (int a = 0; a < 3; a++) Jx[6 + a] = 0.0;
+    return;
+  }
+  Jp[12] = Jp[0] - bf * y / z2;
+  Jp[13] = Jp[1] + bf * x / z2;
+  Jp[14] = Jp[2];
+  Jp[15] = Jp[3];
+  Jp[16] = 0;
+  Jp[17] = Jp[5] - bf / z2;
+  if (Jx) {
+    for (int c = 0; c < 3; c++) {
+      Jx[c] = -K.fx * R[c] / z + K.fx * x * R[6 + c] / z2;
+      Jx[3 + c] = -K.fy * R[3 + c] / z + K.fy * y * R[6 + c] / z2;
+      Jx[6 + c] = Jx[c] - bf * R[6 + c] / z2;
+    }
+  }
+}
+
 // RobustKernelHuber::robustify
 inline void huber(double e2, double delta, double* rho) {
   double dsqr = delta * delta;
@@ -289,12 +330,14 @@ struct BAProblem {
   std::vector<int> cam_free_idx;  // dense index among non-fixed cams or -1
   int Ncf = 0;
   std::vector<double> pts;
-  const double* uv;
+  std::vector<double> uv3;       // (u, v, u_right) per edge; u_right unused for a mono edge
+  std::vector<uint8_t> kind;     // 0 mono (EdgeSE3ProjectXYZ), 1 stereo (EdgeStereoSE3ProjectXYZ)
+  double bf = 0;
   const int32_t* ocam;
   const int32_t* opt;
   std::vector<uint8_t> level;  // 0 active, 1 outlier
   bool robust = true;
-  double delta = 0;
+  double delta = 0, delta_s = 0;  // Huber delta of the mono / stereo edges
   // point-major CSR over observations (observation order inside a point = input order)
   std::vector<int> pt_start, pt_obs;
   // cached per-edge error (g2o Edge::_error), survives pop() — the stale-error quirk
@@ -322,12 +365,12 @@ double ba_compute_errors(BAProblem& P) {
     double pc[3];
     int c = P.ocam[o];
     map_point(&P.Rcache[(size_t)c * 9], P.cams[c].t, &P.pts[(size_t)P.opt[o] * 3], pc);
-    double* e = &P.err[(size_t)o * 2];
-    edge_error(pc, &P.uv[(size_t)o * 2], P.K, e);
-    double e2 = e[0] * e[0] + e[1] * e[1];
+    double* e = &P.err[(size_t)o * 3];
+    edge_error3(pc, &P.uv3[(size_t)o * 3], P.kind[o], P.K, P.bf, e);
+    double e2 = e[0] * e[0] + e[1] * e[1] + e[2] * e[2];
     if (P.robust) {
       double rho[3];
-      huber(e2, P.delta, rho);
+      huber(e2, P.kind[o] ? P.delta_s : P.delta, rho);
       chi += rho[0];
     } else {
       chi += e2;
@@ -346,35 +389,35 @@ void ba_build_system(BAProblem& P) {
     if (P.level[o]) continue;
     int c = P.ocam[o], l = P.opt[o];
     const double* R = &P.Rcache[(size_t)c * 9];
-    double pc[3], Jp[12], Jx[6];
+    double pc[3], Jp[18], Jx[9];
     map_point(R, P.cams[c].t, &P.pts[(size_t)l * 3], pc);
-    edge_jac(R, pc, P.K, Jp, Jx);
-    const double* e = &P.err[(size_t)o * 2];
+    edge_jac3(R, pc, P.kind[o], P.K, P.bf, Jp, Jx);
+    const double* e = &P.err[(size_t)o * 3];
     double w = 1.0;
     if (P.robust) {
       double rho[3];
-      huber(e[0] * e[0] + e[1] * e[1], P.delta, rho);
+      huber(e[0] * e[0] + e[1] * e[1] + e[2] * e[2], P.kind[o] ? P.delta_s : P.delta, rho);
       w = rho[1];
     }
-    double r0 = -w * e[0], r1 = -w * e[1];  // omega_r = -rho1 * Omega * e
+    double r0 = -w * e[0], r1 = -w * e[1], r2 = -w * e[2];  // omega_r = -rho1 * Omega * e
     // point block (vertex 0, "from")
     double* Hl = &P.Hll[(size_t)l * 9];
     double* b_l = &P.bl[(size_t)l * 3];
     for (int a = 0; a < 3; a++) {
-      b_l[a] += Jx[a] * r0 + Jx[3 + a] * r1;
-      for (int b = 0; b < 3; b++) Hl[a * 3 + b] += w * (Jx[a] * Jx[b] + Jx[3 + a] * Jx[3 + b]);
+      b_l[a] += Jx[a] * r0 + Jx[3 + a] * r1 + Jx[6 + a] * r2;
+      for (int b = 0; b < 3; b++) Hl[a * 3 + b] += w * (Jx[a] * Jx[b] + Jx[3 + a] * Jx[3 + b] + Jx[6 + a] * Jx[6 + b]);
     }
     int cf = P.cam_free_idx[c];
     if (cf >= 0) {
       double* Hp = &P.Hpp[(size_t)cf * 36];
       double* b_p = &P.bp[(size_t)cf * 6];
       for (int a = 0; a < 6; a++) {
-        b_p[a] += Jp[a] * r0 + Jp[6 + a] * r1;
-        for (int b = 0; b < 6; b++) Hp[a * 6 + b] += w * (Jp[a] * Jp[b] + Jp[6 + a] * Jp[6 + b]);
+        b_p[a] += Jp[a] * r0 + Jp[6 + a] * r1 + Jp[12 + a] * r2;
+        for (int b = 0; b < 6; b++) Hp[a * 6 + b] += w * (Jp[a] * Jp[b] + Jp[6 + a] * Jp[6 + b] + Jp[12 + a] * Jp[12 + b]);
       }
       double* Wo = &P.W[(size_t)o * 18];  // Hpl block (pose rows, point cols) = Jp^T w Jx
       for (int a = 0; a < 6; a++)
-        for (int b = 0; b < 3; b++) Wo[a * 3 + b] = w * (Jp[a] * Jx[b] + Jp[6 + a] * Jx[3 + b]);
+        for (int b = 0; b < 3; b++) Wo[a * 3 + b] = w * (Jp[a] * Jx[b] + Jp[6 + a] * Jx[3 + b] + Jp[12 + a] * Jx[6 + b]);
     }
   }
 }
@@ -585,11 +628,21 @@ int ba_optimize(BAProblem& P, int n_iter, urmvo_oracle_stats* st, double* chi_ou
   return it;
 }
 
+// uv_stride 2: mono measurements (u, v); 3: (u, v, u_right) with `kind` selecting the edge type.
 void ba_setup(BAProblem& P, int Nc, const double* poses, const uint8_t* fixed, int Np,
-              const double* pts, int No, const double* uv, const int32_t* cam, const int32_t* pt,
-              const double* intr, double chi2_thr) {
+              const double* pts, int No, const double* uv, int uv_stride, const uint8_t* kind,
+              const int32_t* cam, const int32_t* pt, const double* intr, double bf, double chi2_thr,
+              double chi2_thr_stereo) {
   P.Nc = Nc; P.Np = Np; P.No = No;
   P.K = Intr{intr[0], intr[1], intr[2], intr[3]};
+  P.bf = bf;
+  P.uv3.assign((size_t)No * 3, 0.0);
+  P.kind.assign(No, 0);
+  for (int o = 0; o < No; o++) {
+    P.uv3[(size_t)o * 3] = uv[(size_t)o * uv_stride];
+    P.uv3[(size_t)o * 3 + 1] = uv[(size_t)o * uv_stride + 1];
+    if (uv_stride == 3 && kind && kind[o]) { P.uv3[(size_t)o * 3 + 2] = uv[(size_t)o * 3 + 2]; P.kind[o] = 1; }
+  }
   P.cams.resize(Nc);
   P.fixed.assign(fixed, fixed + Nc);
   P.cam_free_idx.assign(Nc, -1);
@@ -600,10 +653,11 @@ void ba_setup(BAProblem& P, int Nc, const double* poses, const uint8_t* fixed, i
     if (!fixed[c]) P.cam_free_idx[c] = P.Ncf++;
   }
   P.pts.assign(pts, pts + (size_t)Np * 3);
-  P.uv = uv; P.ocam = cam; P.opt = pt;
+  P.ocam = cam; P.opt = pt;
   P.level.assign(No, 0);
-  P.err.assign((size_t)No * 2, 0.0);
-  P.delta = (double)(float)std::sqrt(chi2_thr);  // :71 const float thHuberMonoPoint = sqrt(cfg.mono_point)
+  P.err.assign((size_t)No * 3, 0.0);
+  P.delta = (double)(float)std::sqrt(chi2_thr);           // :71 const float thHuberMonoPoint = sqrt(cfg.mono_point)
+  P.delta_s = (double)(float)std::sqrt(chi2_thr_stereo);  // :72 const float thHuberStereoPoint = sqrt(cfg.stereo_point)
   P.pt_start.assign(Np + 1, 0);
   for (int o = 0; o < No; o++) P.pt_start[pt[o] + 1]++;
   for (int l = 0; l < Np; l++) P.pt_start[l + 1] += P.pt_start[l];
@@ -630,33 +684,60 @@ inline bool ba_depth_positive(const BAProblem& P, int o) {  // isDepthPositive a
 
 }  // namespace
 
+static int local_ba_impl(int Nc, double* poses, const uint8_t* fixed, int Np, double* pts, int No,
+                         const double* uv, int uv_stride, const uint8_t* kind, const int32_t* cam,
+                         const int32_t* pt, const double* intr, double bf, double chi2_thr,
+                         double chi2_thr_stereo, int it0, int it1, uint8_t* inlier,
+                         urmvo_oracle_stats* stats);
+
 extern "C" int urmvo_oracle_local_ba(int Nc, double* poses, const uint8_t* fixed, int Np,
                                      double* pts, int No, const double* uv, const int32_t* cam,
                                      const int32_t* pt, const double* intr, double chi2_thr,
                                      int it0, int it1, uint8_t* inlier,
                                      urmvo_oracle_stats* stats) {
+  return local_ba_impl(Nc, poses, fixed, Np, pts, No, uv, 2, nullptr, cam, pt, intr, 0.0, chi2_thr, chi2_thr, it0, it1,
+                       inlier, stats);
+}
+
+// Mono + stereo edges in one graph (camera type STEREO, src/g2o_optimization.cc:96-118): uv3 = (u, v, u_right),
+// kind[o] = 1 for a stereo edge, intr5 = fx fy cx cy bf, thresholds cfg.mono_point / cfg.stereo_point.
+extern "C" int urmvo_oracle_local_ba_stereo(int Nc, double* poses, const uint8_t* fixed, int Np,
+                                            double* pts, int No, const double* uv3, const uint8_t* kind,
+                                            const int32_t* cam, const int32_t* pt, const double* intr5,
+                                            double chi2_thr_mono, double chi2_thr_stereo, int it0, int it1,
+                                            uint8_t* inlier, urmvo_oracle_stats* stats) {
+  return local_ba_impl(Nc, poses, fixed, Np, pts, No, uv3, 3, kind, cam, pt, intr5, intr5[4], chi2_thr_mono,
+                       chi2_thr_stereo, it0, it1, inlier, stats);
+}
+
+static int local_ba_impl(int Nc, double* poses, const uint8_t* fixed, int Np, double* pts, int No,
+                         const double* uv, int uv_stride, const uint8_t* kind, const int32_t* cam,
+                         const int32_t* pt, const double* intr, double bf, double chi2_thr,
+                         double chi2_thr_stereo, int it0, int it1, uint8_t* inlier,
+                         urmvo_oracle_stats* stats) {
   if (stats) std::memset(stats, 0, sizeof(*stats));
   BAProblem P;
-  ba_setup(P, Nc, poses, fixed, Np, pts, No, uv, cam, pt, intr, chi2_thr);
+  ba_setup(P, Nc, poses, fixed, Np, pts, No, uv, uv_stride, kind, cam, pt, intr, bf, chi2_thr, chi2_thr_stereo);
   // :125-126 initializeOptimization(); optimize(10)  — Huber on every edge
   P.robust = true;
   double chi = 0;
   int n0 = ba_optimize(P, it0, stats, &chi);
   if (stats) { stats->iters[0] = n0; stats->chi2_final[0] = chi; stats->lambda_final[0] = P.lambda; }
   // :129-135 chi2() reads the cached error; isDepthPositive() re-maps with the current estimate
-  for (int o = 0; o < No; o++) {
-    double e2 = P.err[(size_t)o * 2] * P.err[(size_t)o * 2] + P.err[(size_t)o * 2 + 1] * P.err[(size_t)o * 2 + 1];
-    if (e2 > chi2_thr || !ba_depth_positive(P, o)) P.level[o] = 1;
+  auto cached_chi2 = [&](int o) {
+    const double* e = &P.err[(size_t)o * 3];
+    return e[0] * e[0] + e[1] * e[1] + e[2] * e[2];
+  };
+  for (int o = 0; o < No; o++) {  // :129-143 mono edges against cfg.mono_point, stereo edges against cfg.stereo_point
+    if (cached_chi2(o) > (P.kind[o] ? chi2_thr_stereo : chi2_thr) || !ba_depth_positive(P, o)) P.level[o] = 1;
   }
   P.robust = false;  // e->setRobustKernel(0)
   // :146-147 initializeOptimization(0); optimize(5)
   int n1 = ba_optimize(P, it1, stats, &chi);
   if (stats) { stats->iters[1] = n1; stats->chi2_final[1] = chi; stats->lambda_final[1] = P.lambda; }
   // :150-154 — level-1 edges keep the error cached by the first optimize()
-  for (int o = 0; o < No; o++) {
-    double e2 = P.err[(size_t)o * 2] * P.err[(size_t)o * 2] + P.err[(size_t)o * 2 + 1] * P.err[(size_t)o * 2 + 1];
-    inlier[o] = (e2 <= chi2_thr && ba_depth_positive(P, o)) ? 1 : 0;
-  }
+  for (int o = 0; o < No; o++)
+    inlier[o] = (cached_chi2(o) <= (P.kind[o] ? chi2_thr_stereo : chi2_thr) && ba_depth_positive(P, o)) ? 1 : 0;
   // :164-176 write back T_wc = estimate().inverse(), points
   for (int c = 0; c < Nc; c++) {
     SE3 Twc = se3_inverse(P.cams[c]);
@@ -675,11 +756,13 @@ struct PoseProblem {
   int No;
   Intr K;
   SE3 T;  // T_cw
-  const double* uv;
+  std::vector<double> uv3;
+  std::vector<uint8_t> kind;
+  double bf = 0;
   const double* Xw;
   std::vector<uint8_t> level;
   std::vector<uint8_t> robust;  // per-edge kernel presence (removed at round index 2 for all)
-  double delta;
+  double delta, delta_s;
   std::vector<double> err;
   double lambda = 0, ni = 2;
   double H[36], b[6], x[6];
@@ -693,12 +776,12 @@ double po_compute_errors(PoseProblem& P) {
     if (P.level[o]) continue;
     double pc[3];
     map_point(R, P.T.t, &P.Xw[(size_t)o * 3], pc);
-    double* e = &P.err[(size_t)o * 2];
-    edge_error(pc, &P.uv[(size_t)o * 2], P.K, e);
-    double e2 = e[0] * e[0] + e[1] * e[1];
+    double* e = &P.err[(size_t)o * 3];
+    edge_error3(pc, &P.uv3[(size_t)o * 3], P.kind[o], P.K, P.bf, e);
+    double e2 = e[0] * e[0] + e[1] * e[1] + e[2] * e[2];
     if (P.robust[o]) {
       double rho[3];
-      huber(e2, P.delta, rho);
+      huber(e2, P.kind[o] ? P.delta_s : P.delta, rho);
       chi += rho[0];
     } else {
       chi += e2;
@@ -714,20 +797,20 @@ void po_build(PoseProblem& P) {
   std::fill(P.b, P.b + 6, 0.0);
   for (int o = 0; o < P.No; o++) {
     if (P.level[o]) continue;
-    double pc[3], Jp[12];
+    double pc[3], Jp[18];
     map_point(R, P.T.t, &P.Xw[(size_t)o * 3], pc);
-    edge_jac(R, pc, P.K, Jp, nullptr);
-    const double* e = &P.err[(size_t)o * 2];
+    edge_jac3(R, pc, P.kind[o], P.K, P.bf, Jp, nullptr);
+    const double* e = &P.err[(size_t)o * 3];
     double w = 1.0;
     if (P.robust[o]) {
       double rho[3];
-      huber(e[0] * e[0] + e[1] * e[1], P.delta, rho);
+      huber(e[0] * e[0] + e[1] * e[1] + e[2] * e[2], P.kind[o] ? P.delta_s : P.delta, rho);
       w = rho[1];
     }
-    double r0 = -w * e[0], r1 = -w * e[1];
+    double r0 = -w * e[0], r1 = -w * e[1], r2 = -w * e[2];
     for (int a = 0; a < 6; a++) {
-      P.b[a] += Jp[a] * r0 + Jp[6 + a] * r1;
-      for (int c = 0; c < 6; c++) P.H[a * 6 + c] += w * (Jp[a] * Jp[c] + Jp[6 + a] * Jp[6 + c]);
+      P.b[a] += Jp[a] * r0 + Jp[6 + a] * r1 + Jp[12 + a] * r2;
+      for (int c = 0; c < 6; c++) P.H[a * 6 + c] += w * (Jp[a] * Jp[c] + Jp[6 + a] * Jp[6 + c] + Jp[12 + a] * Jp[12 + c]);
     }
   }
 }
@@ -817,19 +900,51 @@ int po_optimize(PoseProblem& P, int n_iter, urmvo_oracle_stats* st, double* chi_
 
 }  // namespace
 
+static int pose_only_impl(double* pose, int No, const double* uv, int uv_stride, const uint8_t* kind,
+                          const double* Xw, const double* intr, double bf, double chi2_thr,
+                          double chi2_thr_stereo, int rounds, int its_per_round, uint8_t* inlier,
+                          urmvo_oracle_stats* stats);
+
 extern "C" int urmvo_oracle_pose_only(double* pose, int No, const double* uv, const double* Xw,
                                       const double* intr, double chi2_thr, int rounds,
                                       int its_per_round, uint8_t* inlier,
                                       urmvo_oracle_stats* stats) {
+  return pose_only_impl(pose, No, uv, 2, nullptr, Xw, intr, 0.0, chi2_thr, chi2_thr, rounds, its_per_round, inlier, stats);
+}
+
+// Mono + stereo edges (src/g2o_optimization.cc:235-258): uv3 = (u, v, u_right), kind[o] = 1 for a stereo edge,
+// intr5 = fx fy cx cy bf.  The edge order of the reference (all mono edges, then all stereo edges) only
+// fixes the summation order; the caller's order is used here.
+extern "C" int urmvo_oracle_pose_only_stereo(double* pose, int No, const double* uv3, const uint8_t* kind,
+                                             const double* Xw, const double* intr5, double chi2_thr_mono,
+                                             double chi2_thr_stereo, int rounds, int its_per_round,
+                                             uint8_t* inlier, urmvo_oracle_stats* stats) {
+  return pose_only_impl(pose, No, uv3, 3, kind, Xw, intr5, intr5[4], chi2_thr_mono, chi2_thr_stereo, rounds,
+                        its_per_round, inlier, stats);
+}
+
+static int pose_only_impl(double* pose, int No, const double* uv, int uv_stride, const uint8_t* kind,
+                          const double* Xw, const double* intr, double bf, double chi2_thr,
+                          double chi2_thr_stereo, int rounds, int its_per_round, uint8_t* inlier,
+                          urmvo_oracle_stats* stats) {
   if (stats) std::memset(stats, 0, sizeof(*stats));
   PoseProblem P;
   P.No = No;
   P.K = Intr{intr[0], intr[1], intr[2], intr[3]};
-  P.uv = uv; P.Xw = Xw;
+  P.bf = bf;
+  P.uv3.assign((size_t)No * 3, 0.0);
+  P.kind.assign(No, 0);
+  for (int o = 0; o < No; o++) {
+    P.uv3[(size_t)o * 3] = uv[(size_t)o * uv_stride];
+    P.uv3[(size_t)o * 3 + 1] = uv[(size_t)o * uv_stride + 1];
+    if (uv_stride == 3 && kind && kind[o]) { P.uv3[(size_t)o * 3 + 2] = uv[(size_t)o * 3 + 2]; P.kind[o] = 1; }
+  }
+  P.Xw = Xw;
   P.level.assign(No, 0);
   P.robust.assign(No, 1);
-  P.err.assign((size_t)No * 2, 0.0);
-  P.delta = (double)(float)std::sqrt(chi2_thr);  // :205
+  P.err.assign((size_t)No * 3, 0.0);
+  P.delta = (double)(float)std::sqrt(chi2_thr);           // :205
+  P.delta_s = (double)(float)std::sqrt(chi2_thr_stereo);  // :206
   std::fill(P.x, P.x + 6, 0.0);
   const SE3 T0 = se3_inverse(se3_from(pose, pose + 4));  // :198-199
   P.T = T0;
@@ -846,11 +961,11 @@ extern "C" int urmvo_oracle_pose_only(double* pose, int No, const double* uv, co
       if (!inlier[o]) {  // :273-275 e->computeError() at the current estimate
         double pc[3];
         map_point(R, P.T.t, &Xw[(size_t)o * 3], pc);
-        edge_error(pc, &uv[(size_t)o * 2], P.K, &P.err[(size_t)o * 2]);
+        edge_error3(pc, &P.uv3[(size_t)o * 3], P.kind[o], P.K, P.bf, &P.err[(size_t)o * 3]);
       }
-      const float chi2 = (float)(P.err[(size_t)o * 2] * P.err[(size_t)o * 2] +
-                                 P.err[(size_t)o * 2 + 1] * P.err[(size_t)o * 2 + 1]);  // :277
-      if (chi2 > chi2_thr) {
+      const double* e = &P.err[(size_t)o * 3];
+      const float chi2 = (float)(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);  // :277 / :297
+      if (chi2 > (P.kind[o] ? chi2_thr_stereo : chi2_thr)) {
         inlier[o] = 0; P.level[o] = 1; num_outlier++;
       } else {
         inlier[o] = 1; P.level[o] = 0;
@@ -917,4 +1032,16 @@ extern "C" void urmvo_oracle_se3_inverse(const double* Tin, double* Tout) {
   SE3 T = se3_inverse(se3_from(Tin, Tin + 4));
   std::memcpy(Tout, T.q, 4 * sizeof(double));
   std::memcpy(Tout + 4, T.t, 3 * sizeof(double));
+}
+
+// EdgeStereoSE3ProjectXYZ: e (3), Jpose 3x6, Jpoint 3x3; uv3 = (u, v, u_right), intr5 = fx fy cx cy bf.
+extern "C" int urmvo_oracle_edge_stereo(const double* Tcw, const double* X, const double* uv3,
+                                        const double* intr5, double* e, double* Jpose, double* Jpoint) {
+  Intr K{intr5[0], intr5[1], intr5[2], intr5[3]};
+  double R[9], pc[3];
+  quat_to_R(Tcw, R);
+  map_point(R, Tcw + 4, X, pc);
+  edge_error3(pc, uv3, 1, K, intr5[4], e);
+  edge_jac3(R, pc, 1, K, intr5[4], Jpose, Jpoint);
+  return pc[2] > 0.0;
 }

@@ -65,6 +65,20 @@ int urmvo_oracle_pose_only_batch(int B, const int32_t* obs_offset, double* poses
                                  double chi2_thr, int rounds, int its_per_round,
                                  uint8_t* inlier, int32_t* n_inlier, int n_threads);
 
+/* Stereo camera (reference src/g2o_optimization.cc:96-118, 235-258): mono edges and EdgeStereoSE3ProjectXYZ
+ * [OnlyPose] edges in one graph.  uv3 No*3 = (u, v, u_right), kind[o] = 1 marks a stereo edge (3 rows, Omega = I3,
+ * Huber delta (float)sqrt(chi2_thr_stereo), threshold chi2_thr_stereo), intr5 = fx fy cx cy bf. */
+int urmvo_oracle_local_ba_stereo(int Nc, double* poses, const uint8_t* fixed, int Np, double* pts, int No,
+                                 const double* uv3, const uint8_t* kind, const int32_t* cam, const int32_t* pt,
+                                 const double* intr5, double chi2_thr_mono, double chi2_thr_stereo, int it0,
+                                 int it1, uint8_t* inlier, urmvo_oracle_stats* stats);
+int urmvo_oracle_pose_only_stereo(double* pose, int No, const double* uv3, const uint8_t* kind, const double* Xw,
+                                  const double* intr5, double chi2_thr_mono, double chi2_thr_stereo, int rounds,
+                                  int its_per_round, uint8_t* inlier, urmvo_oracle_stats* stats);
+/* unit-test hook: EdgeStereoSE3ProjectXYZ error (3), Jacobians 3x6 / 3x3; returns isDepthPositive */
+int urmvo_oracle_edge_stereo(const double* Tcw, const double* X, const double* uv3, const double* intr5,
+                             double* e, double* Jpose, double* Jpoint);
+
 /* Pieces exposed for unit tests. */
 /* Residual e(2), J_pose(2x6 row-major, rotation first), J_point(2x3) of EdgeSE3ProjectXYZ.
  * T_cw given as (qx,qy,qz,qw,tx,ty,tz). Returns 1 if depth > 0. */

@@ -75,6 +75,56 @@ def local_ba(prob, chi2_thr=10.0, it0=10, it1=5):
     return poses, pts, inl, st
 
 
+def local_ba_stereo(prob, chi2_thr=10.0, chi2_thr_stereo=75.0, it0=10, it1=5):
+    """Stereo camera: prob has uv3 (No, 3), kind (No,), intr5 = fx fy cx cy bf. Returns (poses, pts, inlier, Stats)."""
+    poses = np.ascontiguousarray(prob["poses"], dtype=np.float64).copy()
+    pts = np.ascontiguousarray(prob["pts"], dtype=np.float64).copy()
+    fixed = np.ascontiguousarray(prob["fixed"], dtype=np.uint8)
+    uv3 = np.ascontiguousarray(prob["uv3"], dtype=np.float64)
+    kind = np.ascontiguousarray(prob["kind"], dtype=np.uint8)
+    cam = np.ascontiguousarray(prob["obs_cam"], dtype=np.int32)
+    pt = np.ascontiguousarray(prob["obs_pt"], dtype=np.int32)
+    intr5 = np.ascontiguousarray(prob["intr5"], dtype=np.float64)
+    inl = np.zeros(uv3.shape[0], dtype=np.uint8)
+    st = Stats()
+    lib().urmvo_oracle_local_ba_stereo(C.c_int(poses.shape[0]), _p(poses), _p(fixed), C.c_int(pts.shape[0]), _p(pts),
+                                       C.c_int(uv3.shape[0]), _p(uv3), _p(kind), _p(cam), _p(pt), _p(intr5),
+                                       C.c_double(chi2_thr), C.c_double(chi2_thr_stereo), C.c_int(it0), C.c_int(it1),
+                                       _p(inl), C.byref(st))
+    return poses, pts, inl, st
+
+
+def pose_only_batch_stereo(batch, chi2_thr=10.0, chi2_thr_stereo=75.0, rounds=4, its=10):
+    poses = np.ascontiguousarray(batch["poses"], dtype=np.float64).copy()
+    off = np.ascontiguousarray(batch["obs_offset"], dtype=np.int32)
+    uv3 = np.ascontiguousarray(batch["uv3"], dtype=np.float64)
+    kind = np.ascontiguousarray(batch["kind"], dtype=np.uint8)
+    Xw = np.ascontiguousarray(batch["Xw"], dtype=np.float64)
+    intr5 = np.ascontiguousarray(batch["intr5"], dtype=np.float64)
+    inl = np.ones(uv3.shape[0], dtype=np.uint8)
+    n_inl = np.zeros(poses.shape[0], dtype=np.int32)
+    lib().urmvo_oracle_pose_only_stereo.restype = C.c_int
+    for f in range(poses.shape[0]):
+        o0, o1 = int(off[f]), int(off[f + 1])
+        pose = poses[f].copy(); i_f = inl[o0:o1].copy()
+        u = np.ascontiguousarray(uv3[o0:o1]); k = np.ascontiguousarray(kind[o0:o1]); X = np.ascontiguousarray(Xw[o0:o1])
+        n_inl[f] = lib().urmvo_oracle_pose_only_stereo(_p(pose), C.c_int(o1 - o0), _p(u), _p(k), _p(X), _p(intr5),
+                                                       C.c_double(chi2_thr), C.c_double(chi2_thr_stereo), C.c_int(rounds),
+                                                       C.c_int(its), _p(i_f), None)
+        poses[f] = pose; inl[o0:o1] = i_f
+    return poses, inl, n_inl
+
+
+def edge_stereo(Tcw, X, uv3, intr5):
+    """EdgeStereoSE3ProjectXYZ: returns (e[3], Jpose[3,6], Jpoint[3,3], depth_positive)."""
+    Tcw = np.ascontiguousarray(Tcw, dtype=np.float64); X = np.ascontiguousarray(X, dtype=np.float64)
+    uv3 = np.ascontiguousarray(uv3, dtype=np.float64); intr5 = np.ascontiguousarray(intr5, dtype=np.float64)
+    e = np.zeros(3); Jp = np.zeros((3, 6)); Jx = np.zeros((3, 3))
+    lib().urmvo_oracle_edge_stereo.restype = C.c_int
+    dp = lib().urmvo_oracle_edge_stereo(_p(Tcw), _p(X), _p(uv3), _p(intr5), _p(e), _p(Jp), _p(Jx))
+    return e, Jp, Jx, bool(dp)
+
+
 def pose_only(pose, uv, Xw, intr, chi2_thr=10.0, rounds=4, its=10, inlier=None):
     pose = np.ascontiguousarray(pose, dtype=np.float64).copy()
     uv = np.ascontiguousarray(uv, dtype=np.float64)

@@ -7,6 +7,7 @@
 #include "epipolar_geometry.h"
 #include "g2o_optimization.h"
 #include "point_matching_outliers.h"
+extern "C" int urmvo_adapter_last_status(void);
 template <class T> static std::vector<T> rd(FILE* f, size_t n) { std::vector<T> v(n); if (n && fread(v.data(), sizeof(T), n, f) != n) { perror("read"); exit(2); } return v; }
 template <class T> static void wr(FILE* f, const std::vector<T>& v) { if (!v.empty()) fwrite(v.data(), sizeof(T), v.size(), f); }
 int main(int argc, char** argv) {
@@ -32,6 +33,44 @@ int main(int argc, char** argv) {
     for (auto& kv : points) for (int k = 0; k < 3; k++) Xo.push_back(kv.second.p(k));
     for (auto& m : mono) inl.push_back(m->inlier);
     wr(out, Po); wr(out, Xo); wr(out, inl);
+  } else if (mode == "ba_stereo") {
+    // mono + stereo constraints of a STEREO camera: kind[o] = 1 -> StereoPointConstraint (u, v, u_right)
+    auto hdr = rd<int>(in, 3); int Nc = hdr[0], Np = hdr[1], No = hdr[2];
+    auto intr = rd<double>(in, 5); auto ids = rd<int>(in, Nc); auto P = rd<double>(in, (size_t)Nc * 7); auto fx = rd<unsigned char>(in, Nc);
+    auto pids = rd<int>(in, Np); auto X = rd<double>(in, (size_t)Np * 3);
+    auto uv3 = rd<double>(in, (size_t)No * 3); auto kind = rd<unsigned char>(in, No); auto oc = rd<int>(in, No); auto op = rd<int>(in, No);
+    cams.emplace_back(new Camera(intr[0], intr[1], intr[2], intr[3], STEREO, intr[4]));
+    MapOfPoses poses; MapOfPoints3d points; VectorOfMonoPointConstraints mono; VectorOfStereoPointConstraints stereo;
+    for (int c = 0; c < Nc; c++) { Pose3d p; p.fixed = fx[c]; p.q.x() = P[c*7]; p.q.y() = P[c*7+1]; p.q.z() = P[c*7+2]; p.q.w() = P[c*7+3]; for (int k = 0; k < 3; k++) p.p(k) = P[c*7+4+k]; poses[ids[c]] = p; }
+    for (int l = 0; l < Np; l++) { Position3d q; for (int k = 0; k < 3; k++) q.p(k) = X[l*3+k]; points[pids[l]] = q; }
+    std::vector<int> where(No);  // position in the mono / stereo vector
+    for (int o = 0; o < No; o++) {
+      if (kind[o]) { auto m = std::make_shared<StereoPointConstraint>(); m->id_pose = ids[oc[o]]; m->id_point = pids[op[o]]; m->id_camera = 0; m->inlier = true; for (int k = 0; k < 3; k++) m->keypoint(k) = uv3[o*3+k]; m->pixel_sigma = 0.8; where[o] = (int)stereo.size(); stereo.push_back(m); }
+      else { auto m = std::make_shared<MonoPointConstraint>(); m->id_pose = ids[oc[o]]; m->id_point = pids[op[o]]; m->id_camera = 0; m->inlier = true; m->keypoint(0) = uv3[o*3]; m->keypoint(1) = uv3[o*3+1]; m->pixel_sigma = 0.8; where[o] = (int)mono.size(); mono.push_back(m); }
+    }
+    LocalmapOptimization(poses, points, cams, mono, stereo, cfg);
+    std::vector<double> Po, Xo; std::vector<unsigned char> inl;
+    for (auto& kv : poses) { Po.push_back(kv.second.q.x()); Po.push_back(kv.second.q.y()); Po.push_back(kv.second.q.z()); Po.push_back(kv.second.q.w()); for (int k = 0; k < 3; k++) Po.push_back(kv.second.p(k)); }
+    for (auto& kv : points) for (int k = 0; k < 3; k++) Xo.push_back(kv.second.p(k));
+    for (int o = 0; o < No; o++) inl.push_back(kind[o] ? stereo[where[o]]->inlier : mono[where[o]]->inlier);
+    std::vector<int> status = {urmvo_adapter_last_status()};
+    wr(out, Po); wr(out, Xo); wr(out, inl); wr(out, status);
+  } else if (mode == "pose_stereo") {
+    auto hdr = rd<int>(in, 1); int No = hdr[0];
+    auto intr = rd<double>(in, 5); auto P = rd<double>(in, 7); auto uv3 = rd<double>(in, (size_t)No * 3); auto kind = rd<unsigned char>(in, No); auto X = rd<double>(in, (size_t)No * 3);
+    cams.emplace_back(new Camera(intr[0], intr[1], intr[2], intr[3], STEREO, intr[4]));
+    MapOfPoses poses; MapOfPoints3d points; VectorOfMonoPointConstraints mono; VectorOfStereoPointConstraints stereo;
+    Pose3d p; p.q.x() = P[0]; p.q.y() = P[1]; p.q.z() = P[2]; p.q.w() = P[3]; for (int k = 0; k < 3; k++) p.p(k) = P[4+k]; poses[42] = p;
+    std::vector<int> where(No);
+    for (int o = 0; o < No; o++) { Position3d q; q.fixed = true; for (int k = 0; k < 3; k++) q.p(k) = X[o*3+k]; points[1000 + o] = q;
+      if (kind[o]) { auto m = std::make_shared<StereoPointConstraint>(); m->id_pose = 42; m->id_point = 1000 + o; m->id_camera = 0; m->inlier = true; for (int k = 0; k < 3; k++) m->keypoint(k) = uv3[o*3+k]; m->pixel_sigma = 0.8; where[o] = (int)stereo.size(); stereo.push_back(m); }
+      else { auto m = std::make_shared<MonoPointConstraint>(); m->id_pose = 42; m->id_point = 1000 + o; m->id_camera = 0; m->inlier = true; m->keypoint(0) = uv3[o*3]; m->keypoint(1) = uv3[o*3+1]; m->pixel_sigma = 0.8; where[o] = (int)mono.size(); mono.push_back(m); } }
+    int n = FrameOptimization(poses, points, cams, mono, stereo, cfg);
+    Pose3d& r = poses.begin()->second;
+    std::vector<double> Po = {r.q.x(), r.q.y(), r.q.z(), r.q.w(), r.p(0), r.p(1), r.p(2)};
+    std::vector<unsigned char> inl; for (int o = 0; o < No; o++) inl.push_back(kind[o] ? stereo[where[o]]->inlier : mono[where[o]]->inlier);
+    std::vector<int> ni = {n};
+    wr(out, Po); wr(out, inl); wr(out, ni);
   } else if (mode == "pose") {
     auto hdr = rd<int>(in, 1); int No = hdr[0];
     auto intr = rd<double>(in, 4); auto P = rd<double>(in, 7); auto uv = rd<double>(in, (size_t)No * 2); auto X = rd<double>(in, (size_t)No * 3);

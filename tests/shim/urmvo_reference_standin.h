@@ -53,9 +53,10 @@ struct OptimizationConfig {
 enum CameraType { MONO = 0, STEREO = 1 };
 class Camera {
  public:
-  Camera(double fx, double fy, double cx, double cy) : f_{fx, fy}, c_{cx, cy} {}
-  CameraType GetCameraType() { return MONO; }
-  double BF() { return 0; }
+  Camera(double fx, double fy, double cx, double cy, CameraType type = MONO, double bf = 0)
+      : f_{fx, fy}, c_{cx, cy}, type_(type), bf_(bf) {}
+  CameraType GetCameraType() { return type_; }
+  double BF() { return bf_; }
   double Fx() { return f_[0]; }
   double Fy() { return f_[1]; }
   double Cx() { return c_[0]; }
@@ -63,6 +64,8 @@ class Camera {
 
  private:
   double f_[2], c_[2];
+  CameraType type_;
+  double bf_;
 };
 using CameraPtr = std::shared_ptr<Camera>;
 

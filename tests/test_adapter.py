@@ -76,6 +76,41 @@ def test_frame_optimization_through_the_adapter(oracle):
 
 
 @pytest.mark.gpu
+def test_stereo_camera_through_the_adapters(oracle):
+    """Camera type STEREO (reference src/g2o_optimization.cc:96-118, 235-258): the adapters add one 3-row
+    edge per StereoPointConstraint next to the mono edges; results and the per-vector inlier flags match the oracle."""
+    p = synth.add_stereo(synth.small_ba(seed=9), 21)
+    Nc, Np, No = p["poses"].shape[0], p["pts"].shape[0], p["uv3"].shape[0]
+    frame_ids = (np.arange(Nc) * 2 + 3).astype(np.int32)
+    point_ids = (np.arange(Np) * 5 + 1).astype(np.int32)
+    buf = struct.pack("3i", Nc, Np, No) + p["intr5"].tobytes() + frame_ids.tobytes() + p["poses"].tobytes() + p["fixed"].tobytes() \
+        + point_ids.tobytes() + p["pts"].tobytes() + p["uv3"].tobytes() + p["kind"].tobytes() + p["obs_cam"].tobytes() + p["obs_pt"].tobytes()
+    out = _run("ba_stereo", buf)
+    poses = np.frombuffer(out[:Nc * 56], dtype=np.float64).reshape(Nc, 7)
+    pts = np.frombuffer(out[Nc * 56:Nc * 56 + Np * 24], dtype=np.float64).reshape(Np, 3)
+    inl = np.frombuffer(out[Nc * 56 + Np * 24:Nc * 56 + Np * 24 + No], dtype=np.uint8)
+    status = struct.unpack("i", out[Nc * 56 + Np * 24 + No:])[0]
+    # the adapter concatenates [mono constraints | stereo constraints]; the oracle gets the same order
+    order = np.r_[np.nonzero(p["kind"] == 0)[0], np.nonzero(p["kind"] == 1)[0]]
+    q = dict(p, uv3=p["uv3"][order], kind=p["kind"][order], obs_cam=p["obs_cam"][order], obs_pt=p["obs_pt"][order])
+    op, ox, oi, _ = oracle.local_ba_stereo(q, 10.0, 75.0)
+    back = np.empty_like(oi); back[order] = oi
+    assert status == 0
+    assert np.abs(poses - op).max() < 1e-5 and np.abs(pts - ox).max() < 1e-4 and np.array_equal(inl, back)
+    b = synth.make_pose_batch_stereo(6, B=1, n_obs=220)
+    buf = struct.pack("i", 220) + b["intr5"].tobytes() + b["poses"][0].tobytes() + b["uv3"].tobytes() + b["kind"].tobytes() + b["Xw"].tobytes()
+    out = _run("pose_stereo", buf)
+    pose = np.frombuffer(out[:56], dtype=np.float64)
+    inl = np.frombuffer(out[56:56 + 220], dtype=np.uint8)
+    n = struct.unpack("i", out[56 + 220:])[0]
+    order = np.r_[np.nonzero(b["kind"] == 0)[0], np.nonzero(b["kind"] == 1)[0]]
+    q = dict(b, uv3=b["uv3"][order], kind=b["kind"][order], Xw=b["Xw"][order])
+    op, oi, on = oracle.pose_only_batch_stereo(q, 10.0, 75.0)
+    back = np.empty_like(oi); back[order] = oi
+    assert np.abs(pose - op[0]).max() < 1e-5 and np.array_equal(inl, back) and n == on[0]
+
+
+@pytest.mark.gpu
 def test_reconstruct_through_the_adapter_uses_glibc_rand_sets(oracle):
     tv = synth.make_two_view(1003, n_keys=400)
     its = 64

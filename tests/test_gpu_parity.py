@@ -202,6 +202,51 @@ def test_ba_bal_scale_cfg5_single_rank_matches_oracle(oracle, ctx):
     assert gs.trials[0] + gs.trials[1] == sum(r[3] for r in os_.rows())
 
 
+# ------------------------------------------------------------------------------- stereo edges (S1)
+
+@pytest.mark.parametrize("force_atomic", [0, 1])
+def test_ba_stereo_edges_match_oracle(oracle, ctx, force_atomic):
+    """Mono + stereo edges in one window (reference src/g2o_optimization.cc:96-118): accumulation modes 5
+    (shared-memory copies) and 6 (global atomics) against the oracle's 3-row edges."""
+    for seed, frac in ((7, 0.6), (19, 1.0), (23, 0.15)):
+        p = synth.add_stereo(synth.small_ba(seed=seed, n_pts=300), seed + 100, stereo_frac=frac)
+        assert p["kind"].sum() > 0
+        gp, gx, gi, gs = ctx.local_ba_stereo(p, 10.0, 75.0, opts=U.BAOptions(0, 0, 0, 0, force_atomic))
+        op, ox, oi, os_ = oracle.local_ba_stereo(p, 10.0, 75.0)
+        assert abs(gs.chi2_final[1] - os_.chi2_final[1]) <= REL_COST * abs(os_.chi2_final[1])
+        assert list(gs.iters) == list(os_.iters)[:2]
+        assert np.abs(gp - op).max() <= POSE_TOL and np.abs(gx - ox).max() <= 1e-4
+        assert np.array_equal(gi, oi)
+
+
+def test_ba_stereo_with_no_stereo_edge_equals_the_mono_call(oracle, ctx):
+    p = synth.add_stereo(synth.small_ba(seed=5, n_pts=200), 1, stereo_frac=0.0)
+    assert p["kind"].sum() == 0
+    a = ctx.local_ba_stereo(p, 10.0, 75.0)
+    b = ctx.local_ba(p, opts=U.BAOptions(0, 0, 0, 0, 2))  # the same one-point-per-warp accumulation
+    assert np.abs(a[0] - b[0]).max() < 1e-11 and np.array_equal(a[2], b[2])
+    assert abs(a[3].chi2_final[1] - b[3].chi2_final[1]) <= 1e-12 * abs(b[3].chi2_final[1])
+
+
+def test_ba_stereo_medium_window_cfg1_shape(oracle, ctx):
+    """A cfg1-sized window of a stereo camera (10 keyframes, 2000 points, 60 % stereo observations)."""
+    p = synth.add_stereo(synth.cfg1(), 77)
+    gp, gx, gi, gs = ctx.local_ba_stereo(p, 10.0, 75.0)
+    op, ox, oi, os_ = oracle.local_ba_stereo(p, 10.0, 75.0)
+    assert abs(gs.chi2_final[1] - os_.chi2_final[1]) <= REL_COST * abs(os_.chi2_final[1])
+    assert np.abs(gp - op).max() <= POSE_TOL and np.array_equal(gi, oi)
+
+
+def test_pose_only_stereo_edges_match_oracle(oracle, ctx):
+    """FrameOptimization with EdgeStereoSE3ProjectXYZOnlyPose edges (:235-258): poses, flags, counts."""
+    for B in (5, 200):  # both kernel instantiations (one / two CTAs per SM)
+        b = synth.make_pose_batch_stereo(31 + B, B=B, n_obs=120)
+        gp, gi, gn = ctx.pose_only_batch_stereo(b, 10.0, 75.0)
+        op, oi, on = oracle.pose_only_batch_stereo(b, 10.0, 75.0)
+        assert np.abs(gp - op).max() <= POSE_TOL
+        assert np.array_equal(gi, oi) and np.array_equal(gn, on)
+
+
 def test_ba_rejects_bad_input(ctx):
     p = synth.small_ba(seed=2)
     bad = dict(p, obs_cam=p["obs_cam"].copy())

@@ -115,3 +115,46 @@ def test_rand_sets_known_answers(oracle):
     assert np.array_equal(synth.draw_sets(1000, 50, 0), oracle.draw_sets(1000, 50, 0))
     for s in oracle.draw_sets(40, 200, 0):
         assert len(set(s.tolist())) == 8  # swap-with-back sampling never repeats an index
+
+
+def test_stereo_edge_jacobians_against_finite_differences(oracle):
+    """EdgeStereoSE3ProjectXYZ (3 rows: u, v, u_right = u - bf/z): analytic 3x6 / 3x3 Jacobians of the oracle
+    against central differences through the oracle's own oplus; the first two rows equal the mono edge."""
+    from urmvo_b200 import synth
+    rng = np.random.default_rng(3)
+    intr5 = np.r_[synth.INTR, synth.BF]
+    for _ in range(20):
+        Tcw = np.r_[synth.rotvec_to_quat(0.3 * rng.standard_normal(3)), 0.3 * rng.standard_normal(3)]
+        X = np.array([rng.uniform(-1, 1), rng.uniform(-1, 1), rng.uniform(2, 8)])
+        uv3 = np.array([rng.uniform(50, 600), rng.uniform(50, 450), rng.uniform(30, 580)])
+        e, Jp, Jx, dp = oracle.edge_stereo(Tcw, X, uv3, intr5)
+        h = 1e-6
+        Jxn = np.zeros((3, 3)); Jpn = np.zeros((3, 6))
+        for a in range(3):
+            d = np.zeros(3); d[a] = h
+            Jxn[:, a] = (oracle.edge_stereo(Tcw, X + d, uv3, intr5)[0] - oracle.edge_stereo(Tcw, X - d, uv3, intr5)[0]) / (2 * h)
+        for a in range(6):
+            d = np.zeros(6); d[a] = h
+            Tp = Tcw.copy(); oracle.lib().urmvo_oracle_se3_oplus(oracle._p(Tp), oracle._p(d))
+            Tm = Tcw.copy(); oracle.lib().urmvo_oracle_se3_oplus(oracle._p(Tm), oracle._p(-d))
+            Jpn[:, a] = (oracle.edge_stereo(Tp, X, uv3, intr5)[0] - oracle.edge_stereo(Tm, X, uv3, intr5)[0]) / (2 * h)
+        assert np.abs(Jxn - Jx).max() < 1e-5 * max(1.0, np.abs(Jx).max())
+        assert np.abs(Jpn - Jp).max() < 1e-5 * max(1.0, np.abs(Jp).max())
+        assert dp
+        # third row of the residual
+        R = synth.quat_to_R(Tcw[:4]); pc = R @ X + Tcw[4:]
+        assert abs(e[2] - (uv3[2] - (pc[0] / pc[2] * intr5[0] + intr5[2] - intr5[4] / pc[2]))) < 1e-9
+
+
+def test_stereo_capable_oracle_is_bit_identical_on_mono_problems(oracle):
+    """The 3-row generalisation adds exact zeros for mono edges: kind = 0 everywhere gives the bits of the
+    2-row entry point (so the committed goldens still pin it)."""
+    from urmvo_b200 import synth
+    p = synth.add_stereo(synth.small_ba(seed=13), 5, stereo_frac=0.0)
+    a = oracle.local_ba_stereo(p, 10.0, 75.0)
+    b = oracle.local_ba(p)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    s = synth.add_stereo(synth.small_ba(seed=13), 5, stereo_frac=0.7)
+    c = oracle.local_ba_stereo(s, 10.0, 75.0)
+    assert not np.array_equal(c[0], b[0])
+    assert np.abs(c[0] - s["gt_poses"]).max() < 0.02  # the stereo problem converges to the scene too

@@ -1,9 +1,25 @@
 // adapter/g2o_optimization.cc — drop-in replacement for the reference's src/g2o_optimization.cc
-// (LocalmapOptimization :20-177, FrameOptimization :179-321).  Same signatures, same in-place result
-// convention, so src/mapping.cc:471 and src/tracking.cc:883 call it unchanged.  It only flattens the
-// reference's containers into the SoA arrays of include/urmvo_b200.h; all arithmetic runs in the
-// sm_100a kernels.  SolvePnPWithCV (:323-377, an OpenCV call) is NOT part of this path: keep the
-// reference's own definition of it in its own translation unit.
+// (LocalmapOptimization :20-177, FrameOptimization :179-321, SolvePnPWithCV's pose refinement input).
+// Same signatures, same in-place result convention, so src/mapping.cc:471 and src/tracking.cc:883 call
+// it unchanged.  It only flattens the reference's containers into the SoA arrays of
+// include/urmvo_b200.h; all arithmetic runs in the sm_100a kernels.
+//
+// Behaviour kept from the reference:
+//   * constraints whose pose / point vertex does not exist are dropped (g2o refuses such edges);
+//   * the camera type is the type of the camera of the LAST mono constraint (:90, :228): stereo edges
+//     are only added when that camera is STEREO (:96, :235) — with no mono constraint at all the type
+//     stays MONO and the stereo vector is ignored, exactly like the reference;
+//   * an empty graph is a silent no-op (g2o: "0 vertices to optimize");
+//   * nothing throws.  On a GPU failure the inputs are left untouched and the failure is recorded:
+//     urmvo_adapter_last_status() returns the urmvo_status of the last call on this thread (0 = the
+//     map was optimised), urmvo_last_error() the message — the caller can tell an optimised map from
+//     an untouched one (include/urmvo_b200.h).
+// The reference reads fx, fy, cx, cy per edge from camera_list[id_camera] (:86-89).  The kernels take one
+// intrinsics set per call: the adapter verifies that every constraint of a call refers to cameras with
+// identical intrinsics (always true for the reference's configurations: camera_list has one entry) and
+// reports URMVO_ERR_UNSUPPORTED otherwise instead of silently using the first camera.
+// Both entry points are called from the tracking thread in the reference; a mutex guards the shared
+// context so that a caller with a separate mapping thread stays safe.
 #include "g2o_optimization.h"
 
 #include <cstdio>
@@ -14,6 +30,9 @@
 #include "urmvo_b200.h"
 
 namespace {
+
+std::mutex g_ba_mutex;
+thread_local int g_last_status = URMVO_OK;
 
 urmvo_ctx* ba_context() {
   static urmvo_ctx* ctx = nullptr;
@@ -37,15 +56,34 @@ void get_pose(const double* in, Pose3d& p) {
   p.p(0) = in[4]; p.p(1) = in[5]; p.p(2) = in[6];
 }
 
+struct Intrinsics {
+  double v[5] = {0, 0, 0, 0, 0};  // fx fy cx cy bf
+  bool set = false, consistent = true;
+  void add(Camera& c, bool with_bf) {
+    const double w[5] = {c.Fx(), c.Fy(), c.Cx(), c.Cy(), with_bf ? c.BF() : 0.0};
+    if (!set) { for (int k = 0; k < 5; k++) v[k] = w[k]; set = true; return; }
+    for (int k = 0; k < (with_bf ? 5 : 4); k++) if (v[k] != w[k]) consistent = false;
+    if (with_bf) v[4] = w[4];
+  }
+};
+
+int fail_status(int rc, const char* who) {
+  g_last_status = rc;
+  std::fprintf(stderr, "[urmvo_b200] %s: %s\n", who, rc == URMVO_ERR_UNSUPPORTED && !*urmvo_last_error() ?
+               "constraints refer to cameras with different intrinsics" : urmvo_last_error());
+  return rc;
+}
+
 }  // namespace
+
+extern "C" int urmvo_adapter_last_status(void) { return g_last_status; }
 
 void LocalmapOptimization(MapOfPoses& poses, MapOfPoints3d& points, std::vector<CameraPtr>& camera_list,
                           VectorOfMonoPointConstraints& mono_point_constraints,
                           VectorOfStereoPointConstraints& stereo_point_constraints,
                           const OptimizationConfig& cfg) {
-  (void)stereo_point_constraints;  // mono camera: the reference ignores them too (:96)
-  urmvo_ctx* ctx = ba_context();
-  if (!ctx || poses.empty() || camera_list.empty()) return;
+  g_last_status = URMVO_OK;
+  if (poses.empty() || points.empty() || camera_list.empty()) return;  // empty graph: g2o does nothing
   // dense indices in ascending-id order (std::map order), like g2o's vertex ordering
   std::map<int, int> pose_idx, point_idx;
   std::vector<double> P(poses.size() * 7), X(points.size() * 3);
@@ -64,30 +102,64 @@ void LocalmapOptimization(MapOfPoses& poses, MapOfPoints3d& points, std::vector<
     n++;
   }
   // observations: constraints whose vertices exist (g2o drops edges with a missing vertex)
-  std::vector<double> uv;
+  CameraType camType = MONO;
+  Intrinsics K;
+  std::vector<double> uv3;
+  std::vector<uint8_t> kind;
   std::vector<int32_t> cam, pt;
-  std::vector<size_t> src;
-  uv.reserve(mono_point_constraints.size() * 2);
+  std::vector<size_t> src_mono, src_stereo;
+  uv3.reserve((mono_point_constraints.size() + stereo_point_constraints.size()) * 3);
   for (size_t i = 0; i < mono_point_constraints.size(); i++) {
     const MonoPointConstraintPtr& c = mono_point_constraints[i];
+    Camera& camera = *camera_list[c->id_camera];
+    camType = camera.GetCameraType();  // :90 — the type of the last mono constraint's camera decides
     auto pi = pose_idx.find(c->id_pose);
     auto li = point_idx.find(c->id_point);
     if (pi == pose_idx.end() || li == point_idx.end()) continue;
-    uv.push_back(c->keypoint(0)); uv.push_back(c->keypoint(1));
+    K.add(camera, false);
+    uv3.push_back(c->keypoint(0)); uv3.push_back(c->keypoint(1)); uv3.push_back(0.0);
+    kind.push_back(0);
     cam.push_back(pi->second); pt.push_back(li->second);
-    src.push_back(i);
+    src_mono.push_back(i);
   }
-  CameraPtr& camera = camera_list[mono_point_constraints.empty() ? 0 : mono_point_constraints[0]->id_camera];
-  const double intr[4] = {camera->Fx(), camera->Fy(), camera->Cx(), camera->Cy()};
-  std::vector<uint8_t> inlier(src.size(), 0);
-  const int rc = urmvo_local_ba(ctx, (int)poses.size(), P.data(), fixed.data(), (int)points.size(), X.data(),
-                                (int)src.size(), uv.data(), cam.data(), pt.data(), intr, cfg.mono_point,
-                                /*it0=*/10, /*it1=*/5, inlier.data(), nullptr, nullptr);
-  if (rc != URMVO_OK) {
-    std::fprintf(stderr, "[urmvo_b200] LocalmapOptimization: %s\n", urmvo_last_error());
-    return;  // inputs untouched, like a g2o optimize() that did nothing
+  if (camType == STEREO) {  // :96
+    for (size_t i = 0; i < stereo_point_constraints.size(); i++) {
+      const StereoPointConstraintPtr& c = stereo_point_constraints[i];
+      auto pi = pose_idx.find(c->id_pose);
+      auto li = point_idx.find(c->id_point);
+      if (pi == pose_idx.end() || li == point_idx.end()) continue;
+      K.add(*camera_list[c->id_camera], true);
+      uv3.push_back(c->keypoint(0)); uv3.push_back(c->keypoint(1)); uv3.push_back(c->keypoint(2));
+      kind.push_back(1);
+      cam.push_back(pi->second); pt.push_back(li->second);
+      src_stereo.push_back(i);
+    }
   }
-  for (size_t k = 0; k < src.size(); k++) mono_point_constraints[src[k]]->inlier = inlier[k] != 0;
+  const size_t No = kind.size();
+  if (No == 0) return;  // no edge: a silent no-op in the reference too
+  if (!K.consistent) { fail_status(URMVO_ERR_UNSUPPORTED, "LocalmapOptimization"); return; }
+  std::vector<uint8_t> inlier(No, 0);
+  int rc;
+  {
+    std::lock_guard<std::mutex> lock(g_ba_mutex);
+    urmvo_ctx* ctx = ba_context();
+    if (!ctx) { g_last_status = URMVO_ERR_NO_DEVICE; return; }
+    if (src_stereo.empty()) {
+      std::vector<double> uv(No * 2);
+      for (size_t o = 0; o < No; o++) { uv[o * 2] = uv3[o * 3]; uv[o * 2 + 1] = uv3[o * 3 + 1]; }
+      rc = urmvo_local_ba(ctx, (int)poses.size(), P.data(), fixed.data(), (int)points.size(), X.data(), (int)No,
+                          uv.data(), cam.data(), pt.data(), K.v, cfg.mono_point, /*it0=*/10, /*it1=*/5, inlier.data(),
+                          nullptr, nullptr);
+    } else {
+      rc = urmvo_local_ba_stereo(ctx, (int)poses.size(), P.data(), fixed.data(), (int)points.size(), X.data(), (int)No,
+                                 uv3.data(), kind.data(), cam.data(), pt.data(), K.v, cfg.mono_point, cfg.stereo_point,
+                                 /*it0=*/10, /*it1=*/5, inlier.data(), nullptr, nullptr);
+    }
+  }
+  if (rc != URMVO_OK) { fail_status(rc, "LocalmapOptimization"); return; }  // inputs untouched
+  for (size_t k = 0; k < src_mono.size(); k++) mono_point_constraints[src_mono[k]]->inlier = inlier[k] != 0;
+  for (size_t k = 0; k < src_stereo.size(); k++)
+    stereo_point_constraints[src_stereo[k]]->inlier = inlier[src_mono.size() + k] != 0;
   n = 0;
   for (auto& kv : poses) { get_pose(&P[(size_t)n * 7], kv.second); n++; }
   n = 0;
@@ -101,34 +173,68 @@ int FrameOptimization(MapOfPoses& poses, MapOfPoints3d& points, std::vector<Came
                       VectorOfMonoPointConstraints& mono_point_constraints,
                       VectorOfStereoPointConstraints& stereo_point_constraints,
                       const OptimizationConfig& cfg) {
-  urmvo_ctx* ctx = ba_context();
+  g_last_status = URMVO_OK;
   const int total = (int)(mono_point_constraints.size() + stereo_point_constraints.size());
-  if (!ctx || poses.size() != 1 || camera_list.empty()) return 0;
+  if (poses.size() != 1 || camera_list.empty()) { g_last_status = URMVO_ERR_ARG; return 0; }  // :184 assert(poses.size() == 1)
   MapOfPoses::iterator pose_it = poses.begin();
   double P[7];
   put_pose(pose_it->second, P);
-  const int No = (int)mono_point_constraints.size();
-  std::vector<double> uv((size_t)No * 2), Xw((size_t)No * 3);
-  std::vector<uint8_t> inlier(No);
-  for (int i = 0; i < No; i++) {
+  const int Nm = (int)mono_point_constraints.size();
+  CameraType camType = MONO;
+  Intrinsics K;
+  std::vector<double> uv3, Xw;
+  std::vector<uint8_t> kind, inlier;
+  uv3.reserve((size_t)total * 3); Xw.reserve((size_t)total * 3);
+  for (int i = 0; i < Nm; i++) {
     const MonoPointConstraintPtr& c = mono_point_constraints[i];
     const Position3d& point = points[c->id_point];  // operator[] like the reference (:214)
-    uv[(size_t)i * 2] = c->keypoint(0); uv[(size_t)i * 2 + 1] = c->keypoint(1);
-    for (int k = 0; k < 3; k++) Xw[(size_t)i * 3 + k] = point.p(k);
-    inlier[i] = c->inlier ? 1 : 0;
+    Camera& camera = *camera_list[c->id_camera];
+    camType = camera.GetCameraType();  // :228
+    K.add(camera, false);
+    uv3.push_back(c->keypoint(0)); uv3.push_back(c->keypoint(1)); uv3.push_back(0.0);
+    for (int k = 0; k < 3; k++) Xw.push_back(point.p(k));
+    kind.push_back(0);
+    inlier.push_back(c->inlier ? 1 : 0);
   }
-  CameraPtr& camera = camera_list[No ? mono_point_constraints[0]->id_camera : 0];
-  const double intr[4] = {camera->Fx(), camera->Fy(), camera->Cx(), camera->Cy()};
+  int Ns = 0;
+  if (camType == STEREO) {  // :235
+    Ns = (int)stereo_point_constraints.size();
+    for (int i = 0; i < Ns; i++) {
+      const StereoPointConstraintPtr& c = stereo_point_constraints[i];
+      const Position3d& point = points[c->id_point];
+      K.add(*camera_list[c->id_camera], true);
+      uv3.push_back(c->keypoint(0)); uv3.push_back(c->keypoint(1)); uv3.push_back(c->keypoint(2));
+      for (int k = 0; k < 3; k++) Xw.push_back(point.p(k));
+      kind.push_back(1);
+      inlier.push_back(c->inlier ? 1 : 0);
+    }
+  }
+  const int No = Nm + Ns;
+  if (!K.set) {  // no edge at all: g2o optimises nothing, every round counts zero outliers
+    return total;
+  }
+  if (!K.consistent) { fail_status(URMVO_ERR_UNSUPPORTED, "FrameOptimization"); return 0; }
   const int32_t off[2] = {0, No};
   int32_t n_inlier = 0;
-  const int rc = urmvo_pose_only_batch(ctx, 1, off, P, uv.data(), Xw.data(), intr, cfg.mono_point, /*rounds=*/4,
-                                       /*its=*/10, inlier.data(), &n_inlier);
-  if (rc != URMVO_OK) {
-    std::fprintf(stderr, "[urmvo_b200] FrameOptimization: %s\n", urmvo_last_error());
-    return 0;
+  int rc;
+  {
+    std::lock_guard<std::mutex> lock(g_ba_mutex);
+    urmvo_ctx* ctx = ba_context();
+    if (!ctx) { g_last_status = URMVO_ERR_NO_DEVICE; return 0; }
+    if (Ns == 0) {
+      std::vector<double> uv((size_t)No * 2);
+      for (int o = 0; o < No; o++) { uv[(size_t)o * 2] = uv3[(size_t)o * 3]; uv[(size_t)o * 2 + 1] = uv3[(size_t)o * 3 + 1]; }
+      rc = urmvo_pose_only_batch(ctx, 1, off, P, uv.data(), Xw.data(), K.v, cfg.mono_point, /*rounds=*/4, /*its=*/10,
+                                 inlier.data(), &n_inlier);
+    } else {
+      rc = urmvo_pose_only_batch_stereo(ctx, 1, off, P, uv3.data(), kind.data(), Xw.data(), K.v, cfg.mono_point,
+                                        cfg.stereo_point, /*rounds=*/4, /*its=*/10, inlier.data(), &n_inlier);
+    }
   }
-  for (int i = 0; i < No; i++) mono_point_constraints[i]->inlier = inlier[i] != 0;
+  if (rc != URMVO_OK) { fail_status(rc, "FrameOptimization"); return 0; }
+  for (int i = 0; i < Nm; i++) mono_point_constraints[i]->inlier = inlier[i] != 0;
+  for (int i = 0; i < Ns; i++) stereo_point_constraints[i]->inlier = inlier[Nm + i] != 0;
   get_pose(P, pose_it->second);
-  // :319-320 returns #mono + #stereo - #outliers; stereo edges do not exist for a mono camera
+  // :319-320 returns #mono + #stereo - #outliers (stereo constraints of a MONO camera are never edges)
   return n_inlier + (total - No);
 }

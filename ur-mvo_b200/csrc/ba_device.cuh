@@ -70,6 +70,28 @@ __device__ __forceinline__ void edge_jac_point(const double* __restrict__ Rt, co
   }
 }
 
+// EdgeStereoSE3ProjectXYZ (upstream g2o types_six_dof_expmap.cpp; reference src/g2o_optimization.cc:96-118):
+// third residual row u_right - (u_left_projected - bf / z) and the third Jacobian rows, from
+// pz = (x/z, y/z, 1/z) and the first rows (row 2 = row 0 plus the bf terms).
+__device__ __forceinline__ double edge_error_right(const double* pz, double ur, const double* K, double bf) {
+  return ur - (pz[0] * K[0] + K[2] - bf * pz[2]);
+}
+__device__ __forceinline__ void edge_jac_pose_right(const double* pz, const double* Jp, double bf, double* J2) {
+  const double xz = pz[0], yz = pz[1], iz = pz[2];
+  J2[0] = Jp[0] - bf * yz * iz;
+  J2[1] = Jp[1] + bf * xz * iz;
+  J2[2] = Jp[2];
+  J2[3] = Jp[3];
+  J2[4] = 0;
+  J2[5] = Jp[5] - bf * iz * iz;
+}
+__device__ __forceinline__ void edge_jac_point_right(const double* __restrict__ Rt, const double* pz, const double* Jx,
+                                                     double bf, double* J2) {
+  const double s = bf * pz[2] * pz[2];
+#pragma unroll
+  for (int c = 0; c < 3; c++) J2[c] = Jx[c] - s * Rt[6 + c];
+}
+
 // Symmetric 3x3 inverse, packed (00 01 02 11 12 22), cofactor formula like Eigen's fixed-size inverse.
 __device__ __forceinline__ void sym3_inverse(const double* h, double* r) {
   const double a00 = h[0], a01 = h[1], a02 = h[2], a11 = h[3], a12 = h[4], a22 = h[5];

@@ -304,6 +304,296 @@ __device__ void lin_phase(const Scope& sc, const BAWin& W, int cur, double lambd
   }
 }
 
+
+// ------------------------------------------------------------------------------- stereo edges
+//
+// Windows of a STEREO camera (reference src/g2o_optimization.cc:96-118) mix EdgeSE3ProjectXYZ (2 rows)
+// and EdgeStereoSE3ProjectXYZ (3 rows: u, v, u_right; Omega = I3; Huber delta sqrt(cfg.stereo_point)).
+// The phases below are the one-point-per-warp phases written for THREE residual rows; a mono edge
+// leaves its third row zero.  They serve accumulation modes 5 (shared-memory copies) and 6 (global
+// atomics); the packed / tile modes stay mono-only.  Staging: Jp[18] | B[9] | A[9] | we[3] | w.
+constexpr int kStageFieldsS = 40;
+struct WarpStageS {
+  double* f;
+  int* cf;
+  int kmax;
+  __device__ __forceinline__ double& Jp(int a, int i) { return f[a * kmax + i]; }
+  __device__ __forceinline__ double& B(int a, int i) { return f[(18 + a) * kmax + i]; }
+  __device__ __forceinline__ double& A(int a, int i) { return f[(27 + a) * kmax + i]; }
+  __device__ __forceinline__ double& we(int a, int i) { return f[(36 + a) * kmax + i]; }
+  __device__ __forceinline__ double& w(int i) { return f[39 * kmax + i]; }
+};
+
+struct StereoPar { double bf, delta_s; };
+
+// residual (3 rows), Huber weight, chi2 contribution; returns rho0.  pz = (x/z, y/z, 1/z).
+__device__ __forceinline__ double edge_eval3(const BAWin& W, int o, const double* pc, const double* K,
+                                             const StereoPar& sp, double delta, bool robust, double* e, double* pz,
+                                             double& w, bool& stereo) {
+  const double2 uv = *reinterpret_cast<const double2*>(W.uv + (size_t)o * 2);
+  double e2 = edge_error(pc, uv.x, uv.y, K, e[0], e[1], pz);
+  stereo = W.okind[o] != 0;
+  e[2] = 0.0;
+  if (stereo) { e[2] = edge_error_right(pz, W.ur[o], K, sp.bf); e2 += e[2] * e[2]; }
+  return huber_rho(e2, stereo ? sp.delta_s : delta, robust, w);
+}
+
+template <bool DIAG, bool SMEM, class Scope>
+__device__ void lin_phase_s(const Scope& sc, const BAWin& W, int cur, double lambda, bool robust,
+                            double delta, StereoPar sp, WarpStageS st, WorkArea wa, double& chi_acc,
+                            double& maxdiag_acc) {
+  const int lane = threadIdx.x & 31;
+  const int wpc = blockDim.x >> 5;
+  const int gw = sc.blk() * wpc + (threadIdx.x >> 5);
+  const int gstride = sc.nblk() * wpc;
+  const double* __restrict__ camRt = W.camRt[cur];
+  const double* __restrict__ pts = W.pts[cur];
+  const double K[4] = {W.intr[0], W.intr[1], W.intr[2], W.intr[3]};
+  const int acc_len = DIAG ? W.Ncf * 6 : W.acc_len;
+  const int acc_off = kStageFieldsS * st.kmax;
+  double* acc = wa.base + (size_t)(threadIdx.x >> 5) * wa.stride + acc_off;
+  double* accS = SMEM ? acc : W.S;
+  double* accbs = SMEM ? acc + (size_t)W.nblk * 36 : W.bs;
+  double* accbp = SMEM ? acc + (size_t)W.nblk * 36 + W.Ncf * 6 : W.bp;
+  double* acchd = SMEM ? acc : W.hdiag;
+  if (SMEM) {
+    for (int e = lane; e < acc_len; e += 32) acc[e] = 0.0;
+    __syncwarp();
+  }
+  for (int l = gw; l < W.Np; l += gstride) {
+    const int ps = W.pt_start[l], k = W.pt_start[l + 1] - ps;
+    const double X[3] = {pts[l * 3], pts[l * 3 + 1], pts[l * 3 + 2]};
+    double h[6] = {0, 0, 0, 0, 0, 0}, bl[3] = {0, 0, 0};
+    for (int i = lane; i < k; i += 32) {
+      const int o = ps + i;
+      int cf = -1;
+      if (!W.level[o]) {
+        const int c = W.ocam[o];
+        const double* Rt = camRt + (size_t)c * 12;
+        double pc[3], pz[3], e[3], w;
+        bool stereo;
+        map_point(Rt, X, pc);
+        chi_acc += edge_eval3(W, o, pc, K, sp, delta, robust, e, pz, w, stereo);
+        double Jx[9], B[9];
+        edge_jac_point(Rt, pz, K, Jx);
+        if (stereo) edge_jac_point_right(Rt, pz, Jx, sp.bf, Jx + 6);
+        else { Jx[6] = 0.0; Jx[7] = 0.0; Jx[8] = 0.0; }
+#pragma unroll
+        for (int a = 0; a < 9; a++) B[a] = w * Jx[a];
+        h[0] += B[0] * Jx[0] + B[3] * Jx[3] + B[6] * Jx[6];
+        h[1] += B[0] * Jx[1] + B[3] * Jx[4] + B[6] * Jx[7];
+        h[2] += B[0] * Jx[2] + B[3] * Jx[5] + B[6] * Jx[8];
+        h[3] += B[1] * Jx[1] + B[4] * Jx[4] + B[7] * Jx[7];
+        h[4] += B[1] * Jx[2] + B[4] * Jx[5] + B[7] * Jx[8];
+        h[5] += B[2] * Jx[2] + B[5] * Jx[5] + B[8] * Jx[8];
+#pragma unroll
+        for (int a = 0; a < 3; a++) bl[a] -= B[a] * e[0] + B[3 + a] * e[1] + B[6 + a] * e[2];
+        cf = W.cam_free[c];
+        if (cf >= 0) {
+          double Jp[18];
+          edge_jac_pose(pz, K, Jp);
+          if (stereo) edge_jac_pose_right(pz, Jp, sp.bf, Jp + 12);
+          else {
+#pragma unroll
+            for (int a = 0; a < 6; a++) Jp[12 + a] = 0.0;
+          }
+          if (DIAG) {
+#pragma unroll
+            for (int a = 0; a < 6; a++)
+              acc_add<SMEM>(&acchd[cf * 6 + a], w * (Jp[a] * Jp[a] + Jp[6 + a] * Jp[6 + a] + Jp[12 + a] * Jp[12 + a]));
+          } else {
+#pragma unroll
+            for (int a = 0; a < 18; a++) st.Jp(a, i) = Jp[a];
+#pragma unroll
+            for (int a = 0; a < 9; a++) st.B(a, i) = B[a];
+#pragma unroll
+            for (int a = 0; a < 3; a++) st.we(a, i) = w * e[a];
+            st.w(i) = w;
+          }
+        }
+      }
+      if (!DIAG) st.cf[i] = cf;
+    }
+#pragma unroll
+    for (int a = 0; a < 6; a++) h[a] = warp_sum(h[a]);
+    if (DIAG) {
+      maxdiag_acc = fmax(maxdiag_acc, fmax(fabs(h[0]), fmax(fabs(h[3]), fabs(h[5]))));
+      if (SMEM) __syncwarp();
+      continue;
+    }
+#pragma unroll
+    for (int a = 0; a < 3; a++) bl[a] = warp_sum(bl[a]);
+    double Di[6];
+    {
+      const double hl[6] = {h[0] + lambda, h[1], h[2], h[3] + lambda, h[4], h[5] + lambda};
+      sym3_inverse(hl, Di);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int a = 0; a < 6; a++) W.Dinv[(size_t)l * 6 + a] = Di[a];
+#pragma unroll
+      for (int a = 0; a < 3; a++) W.bl[(size_t)l * 3 + a] = bl[a];
+    }
+    __syncwarp();
+    // A_i = B_i Dinv (3x3), gradient terms: b_s += -J^T (w e + A b_l), b_p += -J^T w e
+    for (int i = lane; i < k; i += 32) {
+      const int cf = st.cf[i];
+      if (cf < 0) continue;
+      double A[9], g[3], we[3];
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        const double b0 = st.B(r * 3, i), b1 = st.B(r * 3 + 1, i), b2 = st.B(r * 3 + 2, i);
+        A[r * 3 + 0] = b0 * Di[0] + b1 * Di[1] + b2 * Di[2];
+        A[r * 3 + 1] = b0 * Di[1] + b1 * Di[3] + b2 * Di[4];
+        A[r * 3 + 2] = b0 * Di[2] + b1 * Di[4] + b2 * Di[5];
+        we[r] = st.we(r, i);
+        g[r] = we[r] + (A[r * 3] * bl[0] + A[r * 3 + 1] * bl[1] + A[r * 3 + 2] * bl[2]);
+      }
+#pragma unroll
+      for (int a = 0; a < 9; a++) st.A(a, i) = A[a];
+#pragma unroll
+      for (int a = 0; a < 6; a++) {
+        const double j0 = st.Jp(a, i), j1 = st.Jp(6 + a, i), j2 = st.Jp(12 + a, i);
+        acc_add<SMEM>(&accbs[cf * 6 + a], -(j0 * g[0] + j1 * g[1] + j2 * g[2]));
+        acc_add<SMEM>(&accbp[cf * 6 + a], -(j0 * we[0] + j1 * we[1] + j2 * we[2]));
+      }
+    }
+    __syncwarp();
+    // Schur pairs (i <= j): one lane per pair, block = J_i^T M J_j, M (3x3) = delta_ij w I - A_i B_j^T
+    const int npairs = k * (k + 1) / 2;
+    for (int pbase = 0; pbase < npairs; pbase += 32) {
+      const int pi = pbase + lane;
+      if (pi < npairs) {
+        const int kk = 2 * k + 1;
+        int i = (int)(((float)kk - sqrtf((float)(kk * kk - 8 * pi))) * 0.5f);
+        i = max(0, min(i, k - 1));
+        while (i > 0 && i * k - i * (i - 1) / 2 > pi) i--;
+        while ((i + 1) * k - (i + 1) * i / 2 <= pi) i++;
+        const int j = i + (pi - (i * k - i * (i - 1) / 2));
+        const int ci = st.cf[i], cj = st.cf[j];
+        if (ci >= 0 && cj >= 0) {
+          double M[9];
+#pragma unroll
+          for (int r = 0; r < 3; r++)
+#pragma unroll
+            for (int q = 0; q < 3; q++)
+              M[r * 3 + q] = -(st.A(r * 3, i) * st.B(q * 3, j) + st.A(r * 3 + 1, i) * st.B(q * 3 + 1, j) +
+                               st.A(r * 3 + 2, i) * st.B(q * 3 + 2, j));
+          if (i == j) { const double w = st.w(i); M[0] += w; M[4] += w; M[8] += w; }
+          double T[18];  // T = M J_j (3x6)
+#pragma unroll
+          for (int b = 0; b < 6; b++) {
+            const double j0 = st.Jp(b, j), j1 = st.Jp(6 + b, j), j2 = st.Jp(12 + b, j);
+#pragma unroll
+            for (int r = 0; r < 3; r++) T[r * 6 + b] = M[r * 3] * j0 + M[r * 3 + 1] * j1 + M[r * 3 + 2] * j2;
+          }
+          const bool swap = ci > cj;
+          const int blk = SMEM ? (swap ? W.row_ptr[cj] + ci - cj : W.row_ptr[ci] + cj - ci)
+                               : (swap ? find_block(W, cj, ci) : find_block(W, ci, cj));
+          if (blk >= 0) {
+            const bool same_cam_twice = !SMEM && (ci == cj) && (i != j);
+            double* Sb = accS + (size_t)blk * 36;
+#pragma unroll
+            for (int a = 0; a < 6; a++) {
+              const double j0 = st.Jp(a, i), j1 = st.Jp(6 + a, i), j2 = st.Jp(12 + a, i);
+#pragma unroll
+              for (int b = 0; b < 6; b++) {
+                const double v = j0 * T[b] + j1 * T[6 + b] + j2 * T[12 + b];
+                if (SMEM) {
+                  if (!swap) Sb[a * 6 + b] += v; else Sb[b * 6 + a] += v;
+                } else if (same_cam_twice) {
+                  atomicAdd(&Sb[a * 6 + b], v);
+                  atomicAdd(&Sb[b * 6 + a], v);
+                } else {
+                  atomicAdd(&Sb[swap ? b * 6 + a : a * 6 + b], v);
+                }
+              }
+            }
+          }
+        }
+      }
+      if (SMEM) __syncwarp();  // a later round of this point may touch the same block (ordering inside the warp copy)
+    }
+    __syncwarp();
+  }
+  if (SMEM) {
+    __syncthreads();
+    cta_reduce_copies(sc, W, wa, acc_off, acc_len);
+  }
+}
+
+template <class Scope>
+__device__ void backsub_phase_s(const Scope& sc, const BAWin& W, int cur, double lambda, bool robust,
+                                double delta, StereoPar sp, double& chi_acc, double& scale_acc) {
+  const int lane = threadIdx.x & 31;
+  const int wpc = blockDim.x >> 5;
+  const int gw = sc.blk() * wpc + (threadIdx.x >> 5);
+  const int gstride = sc.nblk() * wpc;
+  const int tr = cur ^ 1;
+  const double* __restrict__ camRt = W.camRt[cur];
+  const double* __restrict__ camRtT = W.camRt[tr];
+  const double K[4] = {W.intr[0], W.intr[1], W.intr[2], W.intr[3]};
+  for (int l = gw; l < W.Np; l += gstride) {
+    const int ps = W.pt_start[l], k = W.pt_start[l + 1] - ps;
+    const double X[3] = {W.pts[cur][l * 3], W.pts[cur][l * 3 + 1], W.pts[cur][l * 3 + 2]};
+    double c3[3] = {0, 0, 0};
+    for (int i = lane; i < k; i += 32) {
+      const int o = ps + i;
+      if (W.level[o]) continue;
+      const int c = W.ocam[o];
+      const int cf = W.cam_free[c];
+      if (cf < 0) continue;
+      const double* Rt = camRt + (size_t)c * 12;
+      double pc[3], pz[3], e[3], w, Jp[18], Jx[9];
+      bool stereo;
+      map_point(Rt, X, pc);
+      edge_eval3(W, o, pc, K, sp, delta, robust, e, pz, w, stereo);
+      edge_jac_pose(pz, K, Jp);
+      edge_jac_point(Rt, pz, K, Jx);
+      double s0 = 0, s1 = 0, s2 = 0;
+#pragma unroll
+      for (int a = 0; a < 6; a++) {
+        const double xa = __ldcg(W.xp + cf * 6 + a);
+        s0 += Jp[a] * xa;
+        s1 += Jp[6 + a] * xa;
+      }
+      if (stereo) {
+        edge_jac_pose_right(pz, Jp, sp.bf, Jp + 12);
+        edge_jac_point_right(Rt, pz, Jx, sp.bf, Jx + 6);
+#pragma unroll
+        for (int a = 0; a < 6; a++) s2 += Jp[12 + a] * __ldcg(W.xp + cf * 6 + a);
+      } else {
+        Jx[6] = 0.0; Jx[7] = 0.0; Jx[8] = 0.0;
+      }
+      s0 *= w; s1 *= w; s2 *= w;
+#pragma unroll
+      for (int a = 0; a < 3; a++) c3[a] += Jx[a] * s0 + Jx[3 + a] * s1 + Jx[6 + a] * s2;
+    }
+#pragma unroll
+    for (int a = 0; a < 3; a++) c3[a] = warp_sum(c3[a]);
+    const double* Di = W.Dinv + (size_t)l * 6;
+    const double b0 = W.bl[(size_t)l * 3], b1 = W.bl[(size_t)l * 3 + 1], b2 = W.bl[(size_t)l * 3 + 2];
+    const double r0 = b0 - c3[0], r1 = b1 - c3[1], r2 = b2 - c3[2];
+    const double x0 = Di[0] * r0 + Di[1] * r1 + Di[2] * r2;
+    const double x1 = Di[1] * r0 + Di[3] * r1 + Di[4] * r2;
+    const double x2 = Di[2] * r0 + Di[4] * r1 + Di[5] * r2;
+    const double Xn[3] = {X[0] + x0, X[1] + x1, X[2] + x2};
+    if (lane == 0) {
+      W.pts[tr][l * 3] = Xn[0]; W.pts[tr][l * 3 + 1] = Xn[1]; W.pts[tr][l * 3 + 2] = Xn[2];
+      scale_acc += x0 * (lambda * x0 + b0) + x1 * (lambda * x1 + b1) + x2 * (lambda * x2 + b2);
+    }
+    for (int i = lane; i < k; i += 32) {
+      const int o = ps + i;
+      if (W.level[o]) continue;
+      const double* Rt = camRtT + (size_t)W.ocam[o] * 12;
+      double pc[3], pz[3], e[3], w;
+      bool stereo;
+      map_point(Rt, Xn, pc);
+      chi_acc += edge_eval3(W, o, pc, K, sp, delta, robust, e, pz, w, stereo);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------- phase PCG
 
 // 6x6 SPD inverse by Cholesky (block-Jacobi preconditioner). Returns false if not positive definite.
@@ -1371,9 +1661,13 @@ __device__ LMResult lm_optimize(const Scope& sc, const BAWin& W, const BARun& ru
                                 bool robust, int& cur, int& last_eval, WarpStage st, PackStage pst,
                                 WorkArea wa, double* pcg_sm, int& parity, double* red,
                                 double* chi_initial) {
-  constexpr bool SMEM = MODE >= 1;
-  constexpr bool PACKED = MODE >= 2;
+  constexpr bool STEREO = MODE == 5 || MODE == 6;      // modes 1 / 0 with 3-row (stereo-capable) edges
+  constexpr bool SMEM = (MODE >= 1 && MODE <= 3) || MODE == 5;
+  constexpr bool PACKED = MODE == 2 || MODE == 3;
   constexpr int NB = MODE == 3 ? 2 : 1;
+  const StereoPar sp = {run.bf, run.delta_s};
+  WarpStageS sts;
+  sts.f = st.f; sts.cf = st.cf; sts.kmax = st.kmax;
   const bool timer = W.stats == run.timing_stats && sc.blk() == 0 && threadIdx.x == 0;
   LMResult res = {0, 0, 0, 0.0, 0.0};
   double lambda = 0.0, ni = 2.0;
@@ -1394,6 +1688,7 @@ __device__ LMResult lm_optimize(const Scope& sc, const BAWin& W, const BARun& ru
       {
         BA_T0();
         if (PACKED) lin_phase_packed<true, NB>(sc, W, cur, 0.0, robust, run.delta, pst, wa, chi, mx);
+        else if (STEREO) lin_phase_s<true, SMEM>(sc, W, cur, 0.0, robust, run.delta, sp, sts, wa, chi, mx);
         else lin_phase<true, SMEM>(sc, W, cur, 0.0, robust, run.delta, st, wa, chi, mx);
         BA_T1(0);
       }
@@ -1435,6 +1730,7 @@ __device__ LMResult lm_optimize(const Scope& sc, const BAWin& W, const BARun& ru
       {
         BA_T0();
         if (PACKED) lin_phase_packed<false, NB>(sc, W, cur, lambda, robust, run.delta, pst, wa, chi, mx);
+        else if (STEREO) lin_phase_s<false, SMEM>(sc, W, cur, lambda, robust, run.delta, sp, sts, wa, chi, mx);
         else lin_phase<false, SMEM>(sc, W, cur, lambda, robust, run.delta, st, wa, chi, mx);
         BA_T1(1);
       }
@@ -1488,6 +1784,7 @@ __device__ LMResult lm_optimize(const Scope& sc, const BAWin& W, const BARun& ru
         {
           BA_T0();
           if (PACKED) backsub_phase_packed(sc, W, cur, lambda, robust, run.delta, pst, tchi, sc_l);
+          else if (STEREO) backsub_phase_s(sc, W, cur, lambda, robust, run.delta, sp, tchi, sc_l);
           else backsub_phase(sc, W, cur, lambda, robust, run.delta, tchi, sc_l);
           BA_T1(5);
         }
@@ -1564,7 +1861,7 @@ __device__ void window_init(const Scope& sc, const BAWin& W) {
 // classification error of the first pass.  Returns this thread's count of newly excluded edges.
 template <class Scope>
 __device__ double window_classify(const Scope& sc, const BAWin& W, double chi2_thr, int pass, int cur,
-                                  int last_eval, bool have_eval) {
+                                  int last_eval, bool have_eval, double bf = 0.0, double chi2_thr_s = 0.0) {
   const int gt = sc.blk() * blockDim.x + threadIdx.x, gstride = sc.nblk() * blockDim.x;
   const double K[4] = {W.intr[0], W.intr[1], W.intr[2], W.intr[3]};
   double n_l1 = 0.0;
@@ -1576,20 +1873,29 @@ __device__ double window_classify(const Scope& sc, const BAWin& W, double chi2_t
       const int lev = W.level[o];
       if (pass == 1 && lev == 1) continue;  // cached chi2 > thr: inlier[] already 0 from pass 0
       map_point(W.camRt[last_eval] + (size_t)c * 12, W.pts[last_eval] + (size_t)l * 3, pc);
-      const double e2 = have_eval ? edge_error(pc, uv.x, uv.y, K, e0, e1) : 0.0;
+      double e2 = 0.0, thr = chi2_thr;
+      if (W.okind && W.okind[o]) {  // stereo edge: third row, threshold cfg.stereo_point (:137-143, :156-160)
+        double pz[3];
+        e2 = edge_error(pc, uv.x, uv.y, K, e0, e1, pz);
+        const double er = edge_error_right(pz, W.ur[o], K, bf);
+        e2 = have_eval ? e2 + er * er : 0.0;
+        thr = chi2_thr_s;
+      } else {
+        e2 = have_eval ? edge_error(pc, uv.x, uv.y, K, e0, e1) : 0.0;
+      }
       map_point(W.camRt[cur] + (size_t)c * 12, W.pts[cur] + (size_t)l * 3, pc);
       const bool depth_pos = pc[2] > 0.0;
       if (pass == 0) {
         // level 1: chi2 test failed; level 2: only the depth test failed (its cached chi2 stays
         // <= thr, so the final flag depends on the depth at the final estimate)
-        const int nl = (e2 > chi2_thr) ? 1 : (!depth_pos ? 2 : 0);
+        const int nl = (e2 > thr) ? 1 : (!depth_pos ? 2 : 0);
         W.level[o] = (uint8_t)nl;
         W.inlier[o] = 0;
         n_l1 += nl ? 1.0 : 0.0;
       } else if (lev == 2) {
         W.inlier[o] = depth_pos ? 1 : 0;
       } else {
-        W.inlier[o] = (e2 <= chi2_thr && depth_pos) ? 1 : 0;
+        W.inlier[o] = (e2 <= thr && depth_pos) ? 1 : 0;
       }
     }
   }
@@ -1615,7 +1921,7 @@ template <int MODE, class Scope>
 __device__ void solve_window(const Scope& sc, const BAWin& W, const BARun& run, WarpStage st,
                              PackStage pst, WorkArea wa, double* pcg_sm, double* red) {
   window_init(sc, W);
-  if (MODE >= 2) { pack_records(sc, W); sc.sync(); }
+  if (MODE == 2 || MODE == 3) { pack_records(sc, W); sc.sync(); }
   int cur = 0, last_eval = 0, parity = 0;
   bool have_eval = false;  // has any computeActiveErrors() run? (g2o's cached _error is zero before)
   urmvo_ba_stats* stats = reinterpret_cast<urmvo_ba_stats*>(W.stats);
@@ -1634,14 +1940,14 @@ __device__ void solve_window(const Scope& sc, const BAWin& W, const BARun& run, 
       stats->lambda_final[pass] = r.lambda;
       if (pass == 0) stats->chi2_initial = chi_init;
     }
-    const double n_l1 = window_classify(sc, W, run.chi2_thr, pass, cur, last_eval, have_eval);
+    const double n_l1 = window_classify(sc, W, run.chi2_thr, pass, cur, last_eval, have_eval, run.bf, run.chi2_thr_s);
     if (pass == 0) {
       double s1[1] = {n_l1}, dummy[1];
       scope_reduce<1, 0>(sc, s1, dummy, W.part, parity, red);
       if (writer && stats) stats->n_level1 = (int)s1[0];
     }
     sc.sync();
-    if (MODE >= 2 && pass == 0) { pack_records(sc, W); sc.sync(); }  // new edge levels
+    if ((MODE == 2 || MODE == 3) && pass == 0) { pack_records(sc, W); sc.sync(); }  // new edge levels
   }
   window_finish(sc, W, cur);
 }
@@ -1679,6 +1985,8 @@ template <class Scope>
 __device__ __forceinline__ void solve_window_dispatch(const Scope& sc, const BAWin& W, const BARun& run,
                                                       const SmemViews& v) {
   switch (W.acc_mode) {
+    case 6: solve_window<6>(sc, W, run, v.st, v.pst, v.wa, v.pcg, v.red); break;
+    case 5: solve_window<5>(sc, W, run, v.st, v.pst, v.wa, v.pcg, v.red); break;
     case 3: solve_window<3>(sc, W, run, v.st, v.pst, v.wa, v.pcg, v.red); break;
     case 2: solve_window<2>(sc, W, run, v.st, v.pst, v.wa, v.pcg, v.red); break;
     case 1: solve_window<1>(sc, W, run, v.st, v.pst, v.wa, v.pcg, v.red); break;
@@ -1706,7 +2014,8 @@ ba_window_cluster_kernel(const BAWin* __restrict__ wins, BARun run, int kmax_all
   }
 }
 
-// One large problem on the whole (cooperative) grid.
+// One large problem on the whole (cooperative) grid.  GMODE 0: mono edges, 6: stereo-capable edges.
+template <int GMODE>
 __global__ void __launch_bounds__(256, 1)
 ba_window_grid_kernel(const BAWin* __restrict__ wins, BARun run, int kmax_all, int work_stride,
                       int ints_per_warp) {
@@ -1714,7 +2023,7 @@ ba_window_grid_kernel(const BAWin* __restrict__ wins, BARun run, int kmax_all, i
   GridScope sc;
   const SmemViews v = make_views(smem, kmax_all, work_stride, ints_per_warp);
   for (int w = 0; w < run.n_win; w++) {
-    solve_window<0>(sc, wins[w], run, v.st, v.pst, v.wa, v.pcg, v.red);
+    solve_window<GMODE>(sc, wins[w], run, v.st, v.pst, v.wa, v.pcg, v.red);
     sc.sync();
   }
 }
@@ -1725,10 +2034,13 @@ size_t ba_smem_bytes(int threads, int work_stride, int ints_per_warp) {
          (size_t)nw * ints_per_warp * sizeof(int);
 }
 
-int ba_stage_doubles(int kmax) { return kStageFields * kmax; }
+int ba_stage_doubles(int kmax, int stereo) { return (stereo ? kStageFieldsS : kStageFields) * kmax; }
 int ba_tile_doubles() { return 32 * 37; }
 // grid kernels: at least 23 KB per warp so that a ~60-neighbour block row fits the PCG cache
-static __host__ __device__ int grid_work_stride(int kmax) { const int n = kStageFields * kmax + 32 * 37; return n > 2944 ? n : 2944; }
+static __host__ __device__ int grid_work_stride(int kmax, int stereo = 0) {
+  const int n = (stereo ? kStageFieldsS : kStageFields) * kmax + 32 * 37;
+  return n > 2944 ? n : 2944;
+}
 int ba_pack_doubles() { return kPackFields * kPackSlots + 128; }
 
 // ------------------------------------------------------------------------------- point-sharded BA
@@ -2008,6 +2320,8 @@ cudaError_t launch_ba_cluster(const BAWin* wins_dev, const BARun& run, int mode,
                               int ints_per_warp, int n_clusters, int cluster_size, int threads,
                               cudaStream_t stream) {
   switch (mode) {
+    case 6: return launch_ba_cluster_t<6>(wins_dev, run, kmax, work_stride, ints_per_warp, n_clusters, cluster_size, threads, stream);
+    case 5: return launch_ba_cluster_t<5>(wins_dev, run, kmax, work_stride, ints_per_warp, n_clusters, cluster_size, threads, stream);
     case 3: return launch_ba_cluster_t<3>(wins_dev, run, kmax, work_stride, ints_per_warp, n_clusters, cluster_size, threads, stream);
     case 2: return launch_ba_cluster_t<2>(wins_dev, run, kmax, work_stride, ints_per_warp, n_clusters, cluster_size, threads, stream);
     case 1: return launch_ba_cluster_t<1>(wins_dev, run, kmax, work_stride, ints_per_warp, n_clusters, cluster_size, threads, stream);
@@ -2016,27 +2330,28 @@ cudaError_t launch_ba_cluster(const BAWin* wins_dev, const BARun& run, int mode,
   }
 }
 
-int ba_grid_capacity(int threads, int kmax) {
-  const size_t smem = ba_smem_bytes(threads, grid_work_stride(kmax), kmax);
-  if (cudaFuncSetAttribute(ba_window_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+int ba_grid_capacity(int threads, int kmax, int stereo) {
+  const size_t smem = ba_smem_bytes(threads, grid_work_stride(kmax, stereo), kmax);
+  const void* kern = stereo ? (const void*)ba_window_grid_kernel<6> : (const void*)ba_window_grid_kernel<0>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
   int per_sm = 0, dev = 0, sms = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ba_window_grid_kernel, threads, smem) != cudaSuccess) return 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) != cudaSuccess) return 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   return per_sm * sms;
 }
 
 cudaError_t launch_ba_grid(const BAWin* wins_dev, const BARun& run, int kmax, int grid_blocks,
-                           int threads, cudaStream_t stream) {
-  const int ws = grid_work_stride(kmax);
+                           int threads, cudaStream_t stream, int stereo) {
+  const int ws = grid_work_stride(kmax, stereo);
   const size_t smem = ba_smem_bytes(threads, ws, kmax);
-  cudaError_t e = cudaFuncSetAttribute(ba_window_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const void* kern = stereo ? (const void*)ba_window_grid_kernel<6> : (const void*)ba_window_grid_kernel<0>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   BARun r = run;
   int km = kmax, w2 = ws, ip = kmax;
   void* args[] = {(void*)&wins_dev, (void*)&r, (void*)&km, (void*)&w2, (void*)&ip};
-  return cudaLaunchCooperativeKernel((const void*)ba_window_grid_kernel, dim3((unsigned)grid_blocks),
-                                     dim3((unsigned)threads), args, smem, stream);
+  return cudaLaunchCooperativeKernel(kern, dim3((unsigned)grid_blocks), dim3((unsigned)threads), args, smem, stream);
 }
 
 cudaError_t ba_timing_read(unsigned long long* out, bool reset) {

@@ -33,6 +33,7 @@ struct BAWin {
                     // 2/3: packed groups, 1/2 register-resident blocks per lane (+ dense PCG)
                     // 4: tile mode (csrc/ba_large.cu): point chunks with S-stationary register blocks,
                     //    band storage of S and a direct block-banded Cholesky solve
+                    // 5 / 6: modes 1 / 0 for windows with STEREO edges (3-row residuals, okind / ur below)
   int n_grp;        // packed modes: number of point groups
   int acc_len;      // acc_mode 1: doubles per accumulator copy = nblk*36 + Ncf*12
   double intr[4];   // fx fy cx cy
@@ -41,6 +42,8 @@ struct BAWin {
   const double* pts_in;    // Np*3
   const double* uv;        // No*2
   const int* ocam;         // No     camera index
+  const double* ur;        // No     u_right of a stereo edge (modes 5 / 6), else NULL
+  const uint8_t* okind;    // No     1: stereo edge (EdgeStereoSE3ProjectXYZ), 0: mono edge; NULL in mono windows
   const int* pt_start;     // Np+1   CSR over observations
   const int* opt;          // No     point index of each observation (packed modes)
   const int* grp_pt;       // n_grp+1 first point of each group: <= 32 observations and points per group
@@ -93,6 +96,9 @@ struct BAWin {
 struct BARun {
   double chi2_thr;
   double delta;        // (double)(float)sqrt(chi2_thr)
+  double bf;           // stereo baseline * fx (camera BF(), src/g2o_optimization.cc:113)
+  double chi2_thr_s;   // cfg.stereo_point
+  double delta_s;      // (double)(float)sqrt(chi2_thr_s)
   double pcg_tol;
   int pcg_max_iter;
   int it0, it1;

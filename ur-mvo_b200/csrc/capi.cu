@@ -170,6 +170,7 @@ struct urmvo_ba_plan {
   int n6 = 0;
   void* shard_state = nullptr;       // device
   void* shard_state_host = nullptr;  // pinned + mapped mirror written by k_sh_decide
+  bool stereo = false;               // 3-row edges present (modes 5 / 6)
   // tile mode (csrc/ba_large.cu): one large problem as plain phase kernels, direct band solve
   bool tile = false;
   int band_m = 0;                    // bw + 1
@@ -459,8 +460,14 @@ static int ba_plan_create_impl(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, const
                                const uint8_t* fixed, const double* pts, const double* uv,
                                const int32_t* cam, const int32_t* pt, const double* intr,
                                double chi2_thr, int it0, int it1, const urmvo_ba_options* opts,
-                               bool sharded, const uint8_t* covis, bool borrow_ws = false) {
+                               bool sharded, const uint8_t* covis, bool borrow_ws = false,
+                               const uint8_t* kind = nullptr, double chi2_thr_stereo = 0.0) {
+  // kind != NULL: stereo-capable window(s): uv carries 3 values per observation (u, v, u_right), intr 5 values
+  // (fx, fy, cx, cy, bf), kind[o] = 1 marks an EdgeStereoSE3ProjectXYZ (reference src/g2o_optimization.cc:96-118)
+  const bool stereo = kind != nullptr;
+  const int uvs = stereo ? 3 : 2;
   if (!ctx || !out) return fail(URMVO_ERR_ARG, "ba_plan_create: null context / out");
+  if (stereo && (sharded || !(chi2_thr_stereo > 0))) return fail(URMVO_ERR_ARG, "ba_plan_create: stereo edges need a positive threshold and are not supported by the point-sharded solve");
   *out = nullptr;
   if (B <= 0 || !cam_off || !pt_off || !obs_off || !poses || !fixed || !pts || !uv || !cam || !pt || !intr)
     return fail(URMVO_ERR_ARG, "ba_plan_create: null or empty input");
@@ -482,7 +489,7 @@ static int ba_plan_create_impl(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, const
   }
   const int large_mode = opts ? opts->large_mode : 0;
   bool tile = false;
-  if (B == 1 && large_mode != 1 && (sharded || obs_off[1] - obs_off[0] >= 100000)) {
+  if (B == 1 && large_mode != 1 && !stereo && (sharded || obs_off[1] - obs_off[0] >= 100000)) {
     const int rc = build_large(cam_off[1] - cam_off[0], fixed + cam_off[0], pt_off[1] - pt_off[0], obs_off[1] - obs_off[0],
                                cam + obs_off[0], pt + obs_off[0], covis, ctx->n_sm, lg_band_max_m(), wh[0], orders[0]);
     if (rc < 0) { delete p; return rc; }
@@ -547,8 +554,9 @@ static int ba_plan_create_impl(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, const
     w.acc_mode = 0;
     if (!p->use_grid && force != 1 && !w.dup_cam && w.Ncf <= 16) {
       w.acc_mode = 1;
-      if (force != 2 && w.kmax <= 32 && w.nblk <= 64) w.acc_mode = w.nblk <= 32 ? 2 : 3;
+      if (force != 2 && !stereo && w.kmax <= 32 && w.nblk <= 64) w.acc_mode = w.nblk <= 32 ? 2 : 3;
     }
+    if (stereo) w.acc_mode = w.acc_mode == 1 ? 5 : 6;  // the 3-row phases exist for modes 1 and 0 only
     if (w.acc_mode >= 2) {
       w.grp_pt.clear();
       w.grp_pt.push_back(0);
@@ -568,11 +576,11 @@ static int ba_plan_create_impl(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, const
     int stride = 0, pcg_d = 0, ints = p->kmax;
     for (auto& w : wh) {
       int need = 0;
-      if (w.acc_mode == 0) need = ba_stage_doubles(p->kmax) + ba_tile_doubles();
-      else if (w.acc_mode == 1) need = ba_stage_doubles(p->kmax) + w.acc_len;
+      if (w.acc_mode == 0 || w.acc_mode == 6) need = ba_stage_doubles(p->kmax, stereo) + ba_tile_doubles();
+      else if (w.acc_mode == 1 || w.acc_mode == 5) need = ba_stage_doubles(p->kmax, stereo) + w.acc_len;
       else { need = std::max(ba_pack_doubles(), w.acc_len); ints = std::max(ints, 128); }
       stride = std::max(stride, need);
-      if (w.acc_mode >= 1) {
+      if (w.acc_mode >= 1 && w.acc_mode != 6) {
         pcg_d = std::max(pcg_d, pcg_dense_doubles(w.Ncf, p->threads));
       }
     }
@@ -587,9 +595,9 @@ static int ba_plan_create_impl(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, const
     // drop the most expensive small-window mode to the next cheaper one and retry
     bool changed = false;
     int worst = 0;
-    for (auto& w : wh) if (w.acc_mode == 1) worst = std::max(worst, w.acc_len);
+    for (auto& w : wh) if (w.acc_mode == 1 || w.acc_mode == 5) worst = std::max(worst, w.acc_len);
     for (auto& w : wh)
-      if (w.acc_mode == 1 && w.acc_len == worst) { w.acc_mode = 0; changed = true; }
+      if ((w.acc_mode == 1 || w.acc_mode == 5) && w.acc_len == worst) { w.acc_mode = w.acc_mode == 5 ? 6 : 0; changed = true; }
     if (!changed) {
       delete p;
       return fail(URMVO_ERR_UNSUPPORTED, "local_ba: a point has too many observations for the per-warp staging area");
@@ -626,12 +634,16 @@ static int ba_plan_create_impl(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, const
     if (band_smem_bytes(p->band_m, p->ncf) > 220 * 1024) { delete p; return fail(URMVO_ERR_UNSUPPORTED, "local_ba: too many free cameras for the direct band solve"); }
     if (lg_prepare(p->band_m, p->ncf) != cudaSuccess) { delete p; return fail(URMVO_ERR_CUDA, "ba_plan_create: cudaFuncSetAttribute failed"); }
   } else if (p->use_grid) {
-    p->grid_blocks = sharded ? shard_grid_capacity(p->threads, p->kmax) : ba_grid_capacity(p->threads, p->kmax);
+    p->grid_blocks = sharded ? shard_grid_capacity(p->threads, p->kmax) : ba_grid_capacity(p->threads, p->kmax, stereo ? 1 : 0);
     if (p->grid_blocks <= 0) { delete p; return fail(URMVO_ERR_CUDA, "ba_plan_create: occupancy query failed"); }
     nblk_scope = p->grid_blocks;
   }
   p->run.chi2_thr = chi2_thr;
   p->run.delta = (double)(float)std::sqrt(chi2_thr);  // const float thHuberMonoPoint = sqrt(cfg.mono_point)
+  p->stereo = stereo;
+  p->run.bf = stereo ? intr[4] : 0.0;
+  p->run.chi2_thr_s = stereo ? chi2_thr_stereo : chi2_thr;
+  p->run.delta_s = (double)(float)std::sqrt(p->run.chi2_thr_s);  // const float thHuberStereoPoint = sqrt(cfg.stereo_point)
   p->run.pcg_tol = (opts && opts->pcg_tol > 0) ? opts->pcg_tol : 1e-10;
   p->run.dense_pcg = (opts && opts->dense_solver == 1) ? 0 : 1;
   p->run.pcg_max_iter = (opts && opts->pcg_max_iter > 0) ? opts->pcg_max_iter : std::min(1000, std::max(60, 12 * max_ncf));
@@ -645,6 +657,7 @@ static int ba_plan_create_impl(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, const
   size_t sum_grp = 0;
   for (auto& w : wh) sum_grp += w.grp_pt.size();
   const size_t o_ocam = A.take<int>(TO), o_opt = A.take<int>(TO);
+  const size_t o_ur = A.take<double>(stereo ? TO : 0), o_okind = A.take<uint8_t>(stereo ? TO : 0);
   const size_t o_pt_start = A.take<int>(TP + B), o_cam_free = A.take<int>(TC), o_grp = A.take<int>(sum_grp + 1);
   const size_t o_row_ptr = A.take<int>(sum_ncf + B), o_col = A.take<int>(sum_blk);
   const size_t o_lrow_ptr = A.take<int>(sum_ncf + B), o_lcol = A.take<int>(sum_blk), o_lblk = A.take<int>(sum_blk);
@@ -682,7 +695,7 @@ static int ba_plan_create_impl(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, const
   std::vector<size_t> spart_off(B, 0);
   for (int w = 0; w < B; w++) {
     spart_off[w] = spart_total;
-    if (wh[w].acc_mode) spart_total += (size_t)nblk_scope * wh[w].acc_len;
+    if (wh[w].acc_mode && wh[w].acc_mode != 6) spart_total += (size_t)nblk_scope * wh[w].acc_len;
   }
   const size_t o_spart = A.take<double>(spart_total);
   const size_t o_lband = A.take<double>(tile ? (size_t)w0.Ncf * (w0.bw + 1) * 36 : 0);
@@ -711,7 +724,10 @@ static int ba_plan_create_impl(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, const
 
   // ---- host staging of the small index arrays + descriptors (pinned), big arrays copied directly
   const size_t idx_bytes = upload_end - o_pt_start;
-  if (ctx->ensure_pinned(idx_bytes + (all_sorted ? 0 : TO * (sizeof(double) * 2 + 2 * sizeof(int))) + (tile ? TP * 3 * sizeof(double) : 0))) {
+  if (stereo) all_sorted = false;  // the (u, v, u_right) triples are always re-packed through the staging buffer
+  if (stereo && perm.empty()) { perm.resize(TO); for (size_t o = 0; o < TO; o++) perm[o] = (int)o; }
+  if (ctx->ensure_pinned(idx_bytes + (all_sorted ? 0 : TO * (sizeof(double) * 2 + 2 * sizeof(int))) + (tile ? TP * 3 * sizeof(double) : 0) +
+                         (stereo ? TO * (sizeof(double) + 1) : 0))) {
     urmvo_ba_plan_destroy(p);
     return fail(URMVO_ERR_CUDA, "cudaMallocHost failed");
   }
@@ -743,6 +759,8 @@ static int ba_plan_create_impl(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, const
     d.pts_in = (const double*)(D + o_pts_in) + p0 * 3;
     d.uv = (const double*)(D + o_uv) + ob0 * 2;
     d.ocam = (const int*)(D + o_ocam) + ob0;
+    d.ur = stereo ? (const double*)(D + o_ur) + ob0 : nullptr;
+    d.okind = stereo ? (const uint8_t*)(D + o_okind) + ob0 : nullptr;
     d.pt_start = (const int*)(D + o_pt_start) + c_pt;
     d.opt = (const int*)(D + o_opt) + ob0;
     d.grp_pt = (const int*)(D + o_grp) + c_grp;
@@ -826,14 +844,21 @@ static int ba_plan_create_impl(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, const
     int* hcam = (int*)(huv + TO * 2);
     int* hpt = hcam + TO;
     for (size_t o = 0; o < TO; o++) {
-      huv[o * 2] = uv[(size_t)perm[o] * 2];
-      huv[o * 2 + 1] = uv[(size_t)perm[o] * 2 + 1];
+      huv[o * 2] = uv[(size_t)perm[o] * uvs];
+      huv[o * 2 + 1] = uv[(size_t)perm[o] * uvs + 1];
       hcam[o] = cam[perm[o]];
       hpt[o] = tile ? pt_inv[pt[perm[o]]] : pt[perm[o]];
     }
     e4 = up(o_uv, huv, TO * 2 * sizeof(double));
     e5 = up(o_ocam, hcam, TO * sizeof(int));
     e8 = up(o_opt, hpt, TO * sizeof(int));
+    if (stereo) {
+      double* hur = (double*)(H + idx_bytes + TO * (sizeof(double) * 2 + 2 * sizeof(int)) + (tile ? TP * 3 * sizeof(double) : 0));
+      uint8_t* hk = (uint8_t*)(hur + TO);
+      for (size_t o = 0; o < TO; o++) { hur[o] = uv[(size_t)perm[o] * 3 + 2]; hk[o] = kind[perm[o]] ? 1 : 0; }
+      if (e4 == cudaSuccess) e4 = up(o_ur, hur, TO * sizeof(double));
+      if (e4 == cudaSuccess) e4 = up(o_okind, hk, TO);
+    }
   }
   cudaError_t e6 = cudaMemsetAsync(D + p->off_stats, 0, sizeof(urmvo_ba_stats) * B, s);
   if (sharded && e6 == cudaSuccess) e6 = cudaMemsetAsync(D + o_scal, 0, o_vec - o_scal + (size_t)8 * p->n6 * sizeof(double), s);
@@ -1057,7 +1082,7 @@ extern "C" int urmvo_ba_plan_run(urmvo_ba_plan* p) {
   if (p->tile) return run_large(p);
   const BAWin* wins = (const BAWin*)(p->dev + p->off_wins);
   cudaError_t e;
-  if (p->use_grid) e = launch_ba_grid(wins, p->run, p->kmax, p->grid_blocks, p->threads, p->ctx->stream);
+  if (p->use_grid) e = launch_ba_grid(wins, p->run, p->kmax, p->grid_blocks, p->threads, p->ctx->stream, p->stereo ? 1 : 0);
   else e = launch_ba_cluster(wins, p->run, p->batch_mode, p->kmax, p->work_stride, p->ints_per_warp, p->n_clusters, p->cluster_size, p->threads, p->ctx->stream);
   if (e != cudaSuccess) return fail(URMVO_ERR_CUDA, std::string("BA kernel launch: ") + cudaGetErrorString(e));
   p->ctx->launches++;
@@ -1139,6 +1164,32 @@ extern "C" int urmvo_local_ba_batch(urmvo_ctx* ctx, int B, const int32_t* cam_of
   return rc;
 }
 
+extern "C" int urmvo_local_ba_batch_stereo(urmvo_ctx* ctx, int B, const int32_t* cam_off, const int32_t* pt_off,
+                                           const int32_t* obs_off, double* poses, const uint8_t* fixed, double* pts,
+                                           const double* uv3, const uint8_t* kind, const int32_t* cam, const int32_t* pt,
+                                           const double* intr5, double chi2_thr_mono, double chi2_thr_stereo, int it0,
+                                           int it1, uint8_t* inlier, urmvo_ba_stats* stats, const urmvo_ba_options* opts) {
+  if (!kind) return fail(URMVO_ERR_ARG, "local_ba_batch_stereo: null kind flags");
+  urmvo_ba_plan* p = nullptr;
+  int rc = ba_plan_create_impl(ctx, &p, B, cam_off, pt_off, obs_off, poses, fixed, pts, uv3, cam, pt, intr5, chi2_thr_mono,
+                               it0, it1, opts, false, nullptr, /*borrow_ws=*/true, kind, chi2_thr_stereo);
+  if (rc != URMVO_OK) return rc;
+  rc = urmvo_ba_plan_run(p);
+  if (rc == URMVO_OK) rc = urmvo_ba_plan_download(p, poses, pts, inlier, stats);
+  urmvo_ba_plan_destroy(p);
+  return rc;
+}
+
+extern "C" int urmvo_local_ba_stereo(urmvo_ctx* ctx, int Nc, double* poses, const uint8_t* fixed, int Np, double* pts,
+                                     int No, const double* uv3, const uint8_t* kind, const int32_t* cam,
+                                     const int32_t* pt, const double* intr5, double chi2_thr_mono,
+                                     double chi2_thr_stereo, int it0, int it1, uint8_t* inlier, urmvo_ba_stats* stats,
+                                     const urmvo_ba_options* opts) {
+  const int32_t co[2] = {0, Nc}, po[2] = {0, Np}, oo[2] = {0, No};
+  return urmvo_local_ba_batch_stereo(ctx, 1, co, po, oo, poses, fixed, pts, uv3, kind, cam, pt, intr5, chi2_thr_mono,
+                                     chi2_thr_stereo, it0, it1, inlier, stats, opts);
+}
+
 extern "C" int urmvo_local_ba(urmvo_ctx* ctx, int Nc, double* poses, const uint8_t* fixed, int Np, double* pts,
                               int No, const double* uv, const int32_t* cam, const int32_t* pt,
                               const double* intr, double chi2_thr, int it0, int it1, uint8_t* inlier,
@@ -1160,6 +1211,10 @@ struct urmvo_pose_plan {
   bool borrowed = false;  // dev is the context's grow-only workspace (one-shot urmvo_pose_only_batch)
   size_t o_off = 0, o_pose_in = 0, o_uv = 0, o_X = 0, o_inl_in = 0, o_inl = 0, o_level = 0, o_pose_out = 0,
          o_ninl = 0, o_iters = 0;
+  // stereo edges (EdgeStereoSE3ProjectXYZOnlyPose, reference src/g2o_optimization.cc:235-258)
+  bool stereo = false;
+  size_t o_ur = 0, o_kind = 0;
+  double bf = 0, chi2_thr_s = 0, delta_s = 0;
 };
 
 extern "C" void urmvo_pose_plan_destroy(urmvo_pose_plan* p) {
@@ -1169,14 +1224,19 @@ extern "C" void urmvo_pose_plan_destroy(urmvo_pose_plan* p) {
   delete p;
 }
 
+// uv_stride 2: mono measurements; 3 with kind != NULL: (u, v, u_right) with kind[o] = 1 marking a stereo edge
+// (intr then carries bf as its fifth value).
 static int pose_plan_create_impl(urmvo_ctx* ctx, urmvo_pose_plan** out, int B, const int32_t* obs_off,
                                       const double* poses, const double* uv, const double* Xw,
                                       const double* intr, double chi2_thr, int rounds, int its_per_round,
-                                      const uint8_t* inlier, bool borrow_ws) {
+                                      const uint8_t* inlier, bool borrow_ws, int uv_stride = 2,
+                                      const uint8_t* kind = nullptr, double chi2_thr_stereo = 0.0) {
   if (!ctx || !out) return fail(URMVO_ERR_ARG, "pose_plan_create: null context / out");
   *out = nullptr;
   if (B <= 0 || !obs_off || !poses || !uv || !Xw || !intr) return fail(URMVO_ERR_ARG, "pose_plan_create: null or empty input");
   if (rounds < 0 || its_per_round < 0 || !(chi2_thr > 0)) return fail(URMVO_ERR_ARG, "pose_plan_create: bad rounds / threshold");
+  const bool stereo = uv_stride == 3;
+  if (stereo && (!kind || !(chi2_thr_stereo > 0))) return fail(URMVO_ERR_ARG, "pose_plan_create: stereo edges need kind flags and a positive threshold");
   for (int f = 0; f < B; f++)
     if (obs_off[f + 1] < obs_off[f]) return fail(URMVO_ERR_ARG, "pose_plan_create: obs_off must be non-decreasing");
   CU_TRY(cudaSetDevice(ctx->device));
@@ -1186,10 +1246,17 @@ static int pose_plan_create_impl(urmvo_ctx* ctx, urmvo_pose_plan** out, int B, c
   p->chi2_thr = chi2_thr;
   p->delta = (double)(float)std::sqrt(chi2_thr);  // src/g2o_optimization.cc:205
   p->rounds = rounds; p->its = its_per_round;
+  p->stereo = stereo;
+  if (stereo) {
+    p->bf = intr[4];
+    p->chi2_thr_s = chi2_thr_stereo;
+    p->delta_s = (double)(float)std::sqrt(chi2_thr_stereo);  // src/g2o_optimization.cc:210
+  }
   const size_t TO = p->total_o;
   Arena A;
   p->o_off = A.take<int>(B + 1); p->o_pose_in = A.take<double>((size_t)B * 7);
   p->o_uv = A.take<double>(TO * 2); p->o_X = A.take<double>(TO * 3);
+  p->o_ur = A.take<double>(stereo ? TO : 0); p->o_kind = A.take<uint8_t>(stereo ? TO : 0);
   p->o_inl_in = A.take<uint8_t>(TO); p->o_inl = A.take<uint8_t>(TO); p->o_level = A.take<uint8_t>(TO);
   p->o_pose_out = A.take<double>((size_t)B * 7); p->o_ninl = A.take<int>(B); p->o_iters = A.take<int>(B);
   cudaError_t ce = cudaSuccess;
@@ -1212,6 +1279,16 @@ static int pose_plan_create_impl(urmvo_ctx* ctx, urmvo_pose_plan** out, int B, c
   cudaError_t e[6];
   e[0] = cudaMemcpyAsync(p->dev + p->o_off, off.data(), (B + 1) * sizeof(int), cudaMemcpyHostToDevice, s);
   e[1] = cudaMemcpyAsync(p->dev + p->o_pose_in, poses, (size_t)B * 7 * sizeof(double), cudaMemcpyHostToDevice, s);
+  std::vector<double> uv2, ur;
+  if (stereo && TO) {  // split (u, v, u_right) into the mono layout + one extra column
+    uv2.resize(TO * 2); ur.resize(TO);
+    for (size_t o = 0; o < TO; o++) {
+      uv2[o * 2] = uv[(o0 + o) * 3]; uv2[o * 2 + 1] = uv[(o0 + o) * 3 + 1]; ur[o] = uv[(o0 + o) * 3 + 2];
+    }
+    e[2] = cudaMemcpyAsync(p->dev + p->o_uv, uv2.data(), TO * 2 * sizeof(double), cudaMemcpyHostToDevice, s);
+    if (e[2] == cudaSuccess) e[2] = cudaMemcpyAsync(p->dev + p->o_ur, ur.data(), TO * sizeof(double), cudaMemcpyHostToDevice, s);
+    if (e[2] == cudaSuccess) e[2] = cudaMemcpyAsync(p->dev + p->o_kind, kind + o0, TO, cudaMemcpyHostToDevice, s);
+  } else
   e[2] = TO ? cudaMemcpyAsync(p->dev + p->o_uv, uv + o0 * 2, TO * 2 * sizeof(double), cudaMemcpyHostToDevice, s) : cudaSuccess;
   e[3] = TO ? cudaMemcpyAsync(p->dev + p->o_X, Xw + o0 * 3, TO * 3 * sizeof(double), cudaMemcpyHostToDevice, s) : cudaSuccess;
   if (inlier) e[4] = TO ? cudaMemcpyAsync(p->dev + p->o_inl_in, inlier + o0, TO, cudaMemcpyHostToDevice, s) : cudaSuccess;
@@ -1239,7 +1316,9 @@ extern "C" int urmvo_pose_plan_run(urmvo_pose_plan* p) {
                                    (const double*)(p->dev + p->o_uv), (const double*)(p->dev + p->o_X), p->intr,
                                    p->chi2_thr, p->delta, p->rounds, p->its, p->dev + p->o_inl, p->dev + p->o_level,
                                    (double*)(p->dev + p->o_pose_out), (int*)(p->dev + p->o_ninl),
-                                   (int*)(p->dev + p->o_iters), s);
+                                   (int*)(p->dev + p->o_iters), s,
+                                   p->stereo ? (const double*)(p->dev + p->o_ur) : nullptr,
+                                   p->stereo ? (const uint8_t*)(p->dev + p->o_kind) : nullptr, p->bf, p->chi2_thr_s, p->delta_s);
   if (e != cudaSuccess) return fail(URMVO_ERR_CUDA, std::string("pose kernel launch: ") + cudaGetErrorString(e));
   p->ctx->launches++;
   return URMVO_OK;
@@ -1263,6 +1342,20 @@ extern "C" int urmvo_pose_only_batch(urmvo_ctx* ctx, int B, const int32_t* obs_o
                                      int rounds, int its_per_round, uint8_t* inlier, int32_t* n_inlier) {
   urmvo_pose_plan* p = nullptr;
   int rc = pose_plan_create_impl(ctx, &p, B, obs_off, poses, uv, Xw, intr, chi2_thr, rounds, its_per_round, inlier, true);
+  if (rc != URMVO_OK) return rc;
+  rc = urmvo_pose_plan_run(p);
+  if (rc == URMVO_OK) rc = urmvo_pose_plan_download(p, poses, inlier ? inlier + obs_off[0] : nullptr, n_inlier, nullptr);
+  urmvo_pose_plan_destroy(p);
+  return rc;
+}
+
+extern "C" int urmvo_pose_only_batch_stereo(urmvo_ctx* ctx, int B, const int32_t* obs_off, double* poses,
+                                            const double* uv3, const uint8_t* kind, const double* Xw,
+                                            const double* intr5, double chi2_thr_mono, double chi2_thr_stereo,
+                                            int rounds, int its_per_round, uint8_t* inlier, int32_t* n_inlier) {
+  urmvo_pose_plan* p = nullptr;
+  int rc = pose_plan_create_impl(ctx, &p, B, obs_off, poses, uv3, Xw, intr5, chi2_thr_mono, rounds, its_per_round, inlier,
+                                 true, 3, kind, chi2_thr_stereo);
   if (rc != URMVO_OK) return rc;
   rc = urmvo_pose_plan_run(p);
   if (rc == URMVO_OK) rc = urmvo_pose_plan_download(p, poses, inlier ? inlier + obs_off[0] : nullptr, n_inlier, nullptr);

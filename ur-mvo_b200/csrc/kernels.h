@@ -10,7 +10,7 @@ namespace urmvo {
 // ---- ba_kernels.cu
 // Dynamic shared memory of the BA kernels: work_stride doubles + ints_per_warp ints per warp.
 size_t ba_smem_bytes(int threads, int work_stride, int ints_per_warp);
-int ba_stage_doubles(int kmax);  // staging fields of the one-point-per-warp modes
+int ba_stage_doubles(int kmax, int stereo = 0);  // staging fields of the one-point-per-warp modes (stereo: 3-row edges)
 int ba_pack_doubles();           // staging fields of the packed modes
 int pcg_dense_doubles(int Ncf, int threads);  // shared memory of the dense in-smem PCG
 int ba_tile_doubles();           // atomic mode: per-warp transposition tile for coalesced REDs
@@ -20,9 +20,9 @@ cudaError_t launch_ba_cluster(const BAWin* wins_dev, const BARun& run, int mode,
                               cudaStream_t stream);
 // One (or a few) large problems on a cooperative grid. grid_blocks <= co-resident capacity.
 cudaError_t launch_ba_grid(const BAWin* wins_dev, const BARun& run, int kmax, int grid_blocks,
-                           int threads, cudaStream_t stream);
+                           int threads, cudaStream_t stream, int stereo = 0);
 // Max co-resident CTAs of the grid kernel on the current device for this configuration.
-int ba_grid_capacity(int threads, int kmax);
+int ba_grid_capacity(int threads, int kmax, int stereo = 0);
 cudaError_t ba_timing_read(unsigned long long* out, bool reset);
 // point-sharded BA: phase kernels on a cooperative grid, NCCL all-reduces in between (capi.cu)
 size_t shard_state_bytes();
@@ -63,7 +63,9 @@ constexpr int kBAPartWidth = 8;  // doubles per CTA and buffer in BAWin::part (+
 cudaError_t launch_pose_only(int B, const int* obs_off, const double* pose_in, const double* uv,
                              const double* Xw, const double* intr, double chi2_thr, double delta,
                              int rounds, int its_per_round, uint8_t* inlier, uint8_t* level,
-                             double* pose_out, int* n_inlier, int* lm_iters, cudaStream_t stream);
+                             double* pose_out, int* n_inlier, int* lm_iters, cudaStream_t stream,
+                             const double* ur = nullptr, const uint8_t* kind = nullptr, double bf = 0.0,
+                             double chi2_thr_s = 0.0, double delta_s = 0.0);
 
 // ---- twoview_kernels.cu
 struct TVMotionOut {

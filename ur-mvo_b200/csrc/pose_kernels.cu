@@ -53,6 +53,23 @@ __device__ __forceinline__ void pose_jac(const double* pc, const double* K, doub
   J[11] = y * invz_2 * K[1];
 }
 
+// EdgeStereoSE3ProjectXYZOnlyPose (src/g2o_optimization.cc:235-258): third residual row
+// u_right - (u_left_projected - bf / z) and its Jacobian row (row 0 plus the bf terms).
+__device__ __forceinline__ double pose_err_right(const double* pc, double ur, const double* K, double bf) {
+  const double iz = 1.0 / pc[2];
+  return ur - (pc[0] * iz * K[0] + K[2] - bf * iz);
+}
+__device__ __forceinline__ void pose_jac_right(const double* pc, const double* J, double bf, double* J2) {
+  const double x = pc[0], y = pc[1];
+  const double invz = 1.0 / pc[2], invz_2 = invz * invz;
+  J2[0] = J[0] - bf * y * invz_2;
+  J2[1] = J[1] + bf * x * invz_2;
+  J2[2] = J[2];
+  J2[3] = J[3];
+  J2[4] = 0;
+  J2[5] = J[5] - bf * invz_2;
+}
+
 // Solve (H + lambda I) x = b, H symmetric packed upper (21). False if not positive definite.
 // LDL^T with reciprocal pivots: every thread of the CTA runs this redundantly between two passes over
 // the observations, so its serial latency is what matters — 6 divisions on the critical path instead
@@ -107,18 +124,29 @@ __device__ __forceinline__ bool solve6(const double* Hp, const double* b, double
 // is fastest when the batch fits one wave (B <= #SMs, and for single-frame latency); 2 caps at 128
 // registers (a few spills) so that a batch of up to 2 x #SMs frames is resident at once instead of
 // running a second, partly empty wave — +34 % on 256 frames.
-template <int MINB>
+// STEREO: the frame mixes mono edges and stereo edges (kind[o] = 1: measurement (u, v, u_right), 3-row
+// residual, Huber delta / threshold of cfg.stereo_point); the mono-only instantiation is unchanged.
+struct PoseStereo {
+  const double* ur;     // per observation, read for stereo edges only
+  const uint8_t* kind;  // per observation
+  double bf, chi2_thr, delta;
+};
+
+template <int MINB, bool STEREO>
 __global__ void __launch_bounds__(256, MINB)
 pose_only_kernel(int B, const int* __restrict__ obs_off, const double* __restrict__ pose_in,
                  const double* __restrict__ uv, const double* __restrict__ Xw, double fx, double fy,
                  double cx, double cy, double chi2_thr, double delta, int rounds, int its_per_round,
                  uint8_t* __restrict__ inlier, uint8_t* __restrict__ level,
-                 double* __restrict__ pose_out, int* __restrict__ n_inlier, int* __restrict__ lm_iters) {
+                 double* __restrict__ pose_out, int* __restrict__ n_inlier, int* __restrict__ lm_iters,
+                 PoseStereo sp) {
   __shared__ double red[29 * 32 + 32];
   const double K[4] = {fx, fy, cx, cy};
   for (int f = blockIdx.x; f < B; f += gridDim.x) {
     const int o0 = obs_off[f], n = obs_off[f + 1] - o0;
     const double* fuv = uv + (size_t)o0 * 2;
+    const double* fur = STEREO ? sp.ur + o0 : nullptr;
+    const uint8_t* fkind = STEREO ? sp.kind + o0 : nullptr;
     const double* fX = Xw + (size_t)o0 * 3;
     uint8_t* flev = level + o0;
     uint8_t* finl = inlier + o0;
@@ -160,8 +188,11 @@ pose_only_kernel(int B, const int* __restrict__ obs_off, const double* __restric
             const double X[3] = {fX[i * 3], fX[i * 3 + 1], fX[i * 3 + 2]};
             double pc[3], e0, e1, w, J[12];
             pose_map(R, tc, X, pc);
-            const double e2 = pose_err(pc, fuv[i * 2], fuv[i * 2 + 1], K, e0, e1);
-            acc[27] += huber_rho(e2, delta, robust, w);
+            double e2 = pose_err(pc, fuv[i * 2], fuv[i * 2 + 1], K, e0, e1);
+            const bool st = STEREO && fkind[i];
+            double er = 0.0;
+            if (st) { er = pose_err_right(pc, fur[i], K, sp.bf); e2 += er * er; }
+            acc[27] += huber_rho(e2, st ? sp.delta : delta, robust, w);
             pose_jac(pc, K, J);
             const double r0 = -w * e0, r1 = -w * e1;
             int idx = 0;
@@ -170,6 +201,18 @@ pose_only_kernel(int B, const int* __restrict__ obs_off, const double* __restric
               acc[21 + a] += J[a] * r0 + J[6 + a] * r1;
 #pragma unroll
               for (int b = a; b < 6; b++) { acc[idx] += w * (J[a] * J[b] + J[6 + a] * J[6 + b]); idx++; }
+            }
+            if (st) {
+              double J2[6];
+              pose_jac_right(pc, J, sp.bf, J2);
+              const double r2 = -w * er;
+              idx = 0;
+#pragma unroll
+              for (int a = 0; a < 6; a++) {
+                acc[21 + a] += J2[a] * r2;
+#pragma unroll
+                for (int b = a; b < 6; b++) { acc[idx] += w * (J2[a] * J2[b]); idx++; }
+              }
             }
           }
           block_sum<28>(acc, red);
@@ -204,8 +247,10 @@ pose_only_kernel(int B, const int* __restrict__ obs_off, const double* __restric
               const double X[3] = {fX[i * 3], fX[i * 3 + 1], fX[i * 3 + 2]};
               double pc[3], e0, e1, w;
               pose_map(Rt, tt, X, pc);
-              const double e2 = pose_err(pc, fuv[i * 2], fuv[i * 2 + 1], K, e0, e1);
-              tchi[0] += huber_rho(e2, delta, robust, w);
+              double e2 = pose_err(pc, fuv[i * 2], fuv[i * 2 + 1], K, e0, e1);
+              const bool st = STEREO && fkind[i];
+              if (st) { const double er = pose_err_right(pc, fur[i], K, sp.bf); e2 += er * er; }
+              tchi[0] += huber_rho(e2, st ? sp.delta : delta, robust, w);
             }
             block_sum<1>(tchi, red);
             evaluated = true;
@@ -252,8 +297,11 @@ pose_only_kernel(int B, const int* __restrict__ obs_off, const double* __restric
         const bool was_inl = finl[i] != 0;
         if (!was_inl || flev[i]) pose_map(Rc, tc, X, pc);
         else pose_map(Rl, tle, X, pc);
-        const float chi2 = (float)pose_err(pc, fuv[i * 2], fuv[i * 2 + 1], K, e0, e1);  // :277
-        if ((double)chi2 > chi2_thr) { finl[i] = 0; flev[i] = 1; nout[0] += 1.0; }
+        double e2 = pose_err(pc, fuv[i * 2], fuv[i * 2 + 1], K, e0, e1);
+        const bool st = STEREO && fkind[i];
+        if (st) { const double er = pose_err_right(pc, fur[i], K, sp.bf); e2 += er * er; }
+        const float chi2 = (float)e2;  // :277 / :297
+        if ((double)chi2 > (st ? sp.chi2_thr : chi2_thr)) { finl[i] = 0; flev[i] = 1; nout[0] += 1.0; }
         else { finl[i] = 1; flev[i] = 0; }
       }
       block_sum<1>(nout, red);
@@ -273,22 +321,25 @@ pose_only_kernel(int B, const int* __restrict__ obs_off, const double* __restric
   }
 }
 
+// ur / kind non-null: stereo edges present (bf, chi2_thr_s, delta_s describe them).
 cudaError_t launch_pose_only(int B, const int* obs_off, const double* pose_in, const double* uv,
                              const double* Xw, const double* intr, double chi2_thr, double delta,
                              int rounds, int its_per_round, uint8_t* inlier, uint8_t* level,
-                             double* pose_out, int* n_inlier, int* lm_iters, cudaStream_t stream) {
+                             double* pose_out, int* n_inlier, int* lm_iters, cudaStream_t stream,
+                             const double* ur, const uint8_t* kind, double bf, double chi2_thr_s, double delta_s) {
   if (B <= 0) return cudaSuccess;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (B > sms)
-    pose_only_kernel<2><<<B, 256, 0, stream>>>(B, obs_off, pose_in, uv, Xw, intr[0], intr[1], intr[2], intr[3],
-                                               chi2_thr, delta, rounds, its_per_round, inlier, level,
-                                               pose_out, n_inlier, lm_iters);
-  else
-    pose_only_kernel<1><<<B, 256, 0, stream>>>(B, obs_off, pose_in, uv, Xw, intr[0], intr[1], intr[2], intr[3],
-                                               chi2_thr, delta, rounds, its_per_round, inlier, level,
-                                               pose_out, n_inlier, lm_iters);
+  const PoseStereo sp = {ur, kind, bf, chi2_thr_s, delta_s};
+#define URMVO_POSE_LAUNCH(MINB, ST)                                                                              \
+  pose_only_kernel<MINB, ST><<<B, 256, 0, stream>>>(B, obs_off, pose_in, uv, Xw, intr[0], intr[1], intr[2], intr[3], \
+                                                    chi2_thr, delta, rounds, its_per_round, inlier, level, pose_out, \
+                                                    n_inlier, lm_iters, sp)
+  const bool stereo = ur != nullptr && kind != nullptr;
+  if (B > sms) { if (stereo) URMVO_POSE_LAUNCH(2, true); else URMVO_POSE_LAUNCH(2, false); }
+  else { if (stereo) URMVO_POSE_LAUNCH(1, true); else URMVO_POSE_LAUNCH(1, false); }
+#undef URMVO_POSE_LAUNCH
   return cudaGetLastError();
 }
 

@@ -124,6 +124,41 @@ def make_ba(seed, n_cams, n_pts, obs_per_pt, span, n_fixed, outlier_frac,
                 gt_poses=gt_poses, gt_pts=gt_pts)
 
 
+BF = 0.12 * FX  # stereo baseline 12 cm (a stereo rig is not part of the Aqualoc configuration: test value)
+STEREO_POINT = 75.0  # the reference's thHuberStereo scale: cfg.stereo_point is not set in configs_aqua.yaml
+
+
+def add_stereo(prob, seed, stereo_frac=0.6, px_sigma=0.5):
+    """Turns a mono BA problem into a STEREO-camera one (reference src/g2o_optimization.cc:96-118): a
+    fraction of the observations gets a right-image column u_right = u - bf / z (+ noise, rounded like a
+    keypoint) and becomes a stereo edge; the others stay mono edges in the same graph."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    uv, z = project(prob["gt_poses"], prob["obs_cam"], prob["gt_pts"][prob["obs_pt"]])
+    ur = np.rint(uv[:, 0] - BF / z + px_sigma * rng.standard_normal(z.shape))
+    kind = (rng.uniform(size=z.shape) < stereo_frac) & (ur >= BORDER) & (~prob["is_outlier"])
+    out = dict(prob)
+    out["uv3"] = np.ascontiguousarray(np.c_[prob["uv"], np.where(kind, ur, 0.0)])
+    out["kind"] = kind.astype(np.uint8)
+    out["intr5"] = np.r_[INTR, BF]
+    return out
+
+
+def make_pose_batch_stereo(seed, B=8, n_obs=300, stereo_frac=0.6, outlier_frac=0.1):
+    """Pose-only frames of a STEREO camera: uv3 / kind / intr5 beside the mono arrays of make_pose_batch."""
+    b = make_pose_batch(seed, B=B, n_obs=n_obs, outlier_frac=outlier_frac)
+    rng = np.random.Generator(np.random.PCG64(seed + 17))
+    frame = np.repeat(np.arange(B), np.diff(b["obs_offset"]))
+    _, z = project(b["gt_poses"], frame, b["Xw"])
+    u_gt, _ = project(b["gt_poses"], frame, b["Xw"])
+    ur = np.rint(u_gt[:, 0] - BF / z + 0.5 * rng.standard_normal(z.shape))
+    kind = (rng.uniform(size=z.shape) < stereo_frac) & (ur >= BORDER)
+    out = dict(b)
+    out["uv3"] = np.ascontiguousarray(np.c_[b["uv"], np.where(kind, ur, 0.0)])
+    out["kind"] = kind.astype(np.uint8)
+    out["intr5"] = np.r_[INTR, BF]
+    return out
+
+
 def cfg1(seed=1001):
     """10 keyframes (ids 0,1,2 fixed by src/mapping.cc:355-356), 2000 points, ~15k observations."""
     return make_ba(seed, 10, 2000, 7.7, 10, 3, 0.05)
