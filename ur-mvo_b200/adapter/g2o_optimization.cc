@@ -58,12 +58,16 @@ void get_pose(const double* in, Pose3d& p) {
 
 struct Intrinsics {
   double v[5] = {0, 0, 0, 0, 0};  // fx fy cx cy bf
-  bool set = false, consistent = true;
+  bool set = false, bf_set = false, consistent = true;
   void add(Camera& c, bool with_bf) {
-    const double w[5] = {c.Fx(), c.Fy(), c.Cx(), c.Cy(), with_bf ? c.BF() : 0.0};
-    if (!set) { for (int k = 0; k < 5; k++) v[k] = w[k]; set = true; return; }
-    for (int k = 0; k < (with_bf ? 5 : 4); k++) if (v[k] != w[k]) consistent = false;
-    if (with_bf) v[4] = w[4];
+    const double w[4] = {c.Fx(), c.Fy(), c.Cx(), c.Cy()};
+    if (!set) { for (int k = 0; k < 4; k++) v[k] = w[k]; set = true; }
+    for (int k = 0; k < 4; k++) if (v[k] != w[k]) consistent = false;
+    if (with_bf) {
+      const double bf = c.BF();
+      if (bf_set && v[4] != bf) consistent = false;
+      v[4] = bf; bf_set = true;
+    }
   }
 };
 
