@@ -49,3 +49,33 @@ def test_two_view_oracle_matches_golden_bit_for_bit(oracle):
         assert np.array_equal(s.view(np.uint32), G["tv_scores_" + tag].view(np.uint32))
         assert np.array_equal(m, G["tv_masks_" + tag])
         assert np.array_equal(M.view(np.uint32), G["tv_models_" + tag].view(np.uint32))
+
+
+def test_oracle_against_reference_goldens(oracle):
+    """Real g2o / Eigen outputs of the UNMODIFIED reference (oracle/build_ref.sh + oracle/make_ref_goldens.py).
+    The reference cannot be built in this image (no Eigen3 / OpenCV C++ / g2o / yaml-cpp), so the file does
+    not exist yet and the BA / pose-only / two-view oracles stay "parity unpinned" (DESIGN.md §2); the day
+    tests/golden/golden_ref.npz is committed this test pins them at the tolerance BASELINE.json states."""
+    import pytest
+    import sys
+    path = os.path.join(GOLDEN, "golden_ref.npz")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/golden_ref.npz not generated: the reference's toolchain is not available here")
+    sys.path.insert(0, os.path.join(os.path.dirname(GOLDEN), "..", "oracle"))
+    from make_ref_goldens import problems
+    R = np.load(path)
+    for name, (kind, p) in problems().items():
+        if kind == "ba":
+            poses, pts, inl, _ = oracle.local_ba(p)
+            assert np.abs(poses - R[name + "_poses"]).max() <= 1e-5, name
+            assert np.abs(pts - R[name + "_pts"]).max() <= 1e-4, name
+            assert (inl != R[name + "_inlier"]).sum() == 0, name
+        elif kind == "pose":
+            pose, inl, n, _ = oracle.pose_only(p["poses"][0], p["uv"], p["Xw"], p["intr"])
+            assert np.abs(pose - R[name + "_pose"]).max() <= 1e-5 and np.array_equal(inl, R[name + "_inlier"]) and n == int(R[name + "_n"][0]), name
+        else:
+            q = dict(p, sets=synth.draw_sets(int((p["matches12"] >= 0).sum()), 200, 0))
+            o = oracle.two_view(q)
+            assert int(o["ok"]) == int(R[name + "_ok"][0]), name
+            if o["ok"]:
+                assert np.abs(o["T21"] - R[name + "_T21"]).max() <= 1e-4 and np.array_equal(o["triangulated"], R[name + "_tri"]), name
