@@ -1,6 +1,8 @@
 // adapter/point_matching_outliers.cc — see point_matching_outliers.h.  Only marshals the two
 // std::vector<cv::Point2f> (already contiguous x,y floats) into urmvo_fm_ransac; the RANSAC itself
-// runs in csrc/fm_kernels.cu.  No CPU fallback: a missing GPU aborts loudly.
+// runs in csrc/fm_kernels.cu.  No CPU fallback and no abort: a GPU failure is reported to the caller
+// (FindFundamentalInliersStatus), who decides whether to keep the reference's own OpenCV call for that
+// frame or to stop.
 #include "point_matching_outliers.h"
 
 #include <cstdio>
@@ -21,25 +23,32 @@ urmvo_ctx* fm_context() {
   });
   return ctx;
 }
-std::mutex g_fm_mutex;  // MatchingPoints is called from the tracking and the mapping thread
+std::mutex g_fm_mutex;  // one context, one call at a time (the reference calls MatchingPoints from the tracking thread)
+thread_local int g_fm_status = URMVO_OK;
 }  // namespace
+
+int FindFundamentalInliersStatus() { return g_fm_status; }
 
 bool FindFundamentalInliersGPU(const std::vector<cv::Point2f>& points0, const std::vector<cv::Point2f>& points1,
                                std::vector<unsigned char>& inliers) {
   static_assert(sizeof(cv::Point2f) == 2 * sizeof(float), "cv::Point2f must be two packed floats");
   const int n = (int)points0.size();
-  if (n < 15 || points1.size() != points0.size()) return false;
+  g_fm_status = URMVO_ERR_UNSUPPORTED;
+  if (n < 15 || points1.size() != points0.size()) return false;  // OpenCV's direct 7-point / LMedS branches
   urmvo_ctx* ctx = fm_context();
   if (!ctx) {
-    std::fprintf(stderr, "[urmvo_b200] FindFundamentalInliersGPU: no usable B200, aborting (there is no CPU path)\n");
-    std::abort();
+    g_fm_status = URMVO_ERR_NO_DEVICE;
+    std::fprintf(stderr, "[urmvo_b200] FindFundamentalInliersGPU: no usable B200 (there is no CPU path in this library)\n");
+    return false;
   }
   std::lock_guard<std::mutex> lock(g_fm_mutex);
-  inliers.assign(n, 0);
-  const int rc = urmvo_fm_ransac(ctx, n, &points0[0].x, &points1[0].x, 3.0, 0.99, 1000, inliers.data(), nullptr);
-  if (rc != URMVO_OK) {
+  std::vector<unsigned char> out(n, 0);
+  const int rc = urmvo_fm_ransac(ctx, n, &points0[0].x, &points1[0].x, 3.0, 0.99, 1000, out.data(), nullptr);
+  g_fm_status = rc;
+  if (rc != URMVO_OK) {  // e.g. a failed cudaMalloc: `inliers` stays untouched, the caller sees false + the status
     std::fprintf(stderr, "[urmvo_b200] urmvo_fm_ransac: %s\n", urmvo_last_error());
-    std::abort();
+    return false;
   }
+  inliers.swap(out);
   return true;
 }

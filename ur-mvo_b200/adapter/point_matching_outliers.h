@@ -8,7 +8,12 @@
 // Fills `inliers` (one byte per correspondence, 1 = keep) exactly as
 //     cv::findFundamentalMat(points0, points1, cv::FM_RANSAC, 3, 0.99, inliers);
 // does, on the GPU.  Returns true when the GPU path handled the call.  Returns false — leaving
-// `inliers` untouched — for fewer than 15 correspondences (OpenCV's direct 7-point / LMedS branches):
-// the caller then makes the original OpenCV call, see INTEGRATION.md.
+// `inliers` untouched — in two cases the caller can tell apart with FindFundamentalInliersStatus():
+//   URMVO_ERR_UNSUPPORTED  fewer than 15 correspondences (OpenCV's direct 7-point / LMedS branches): make the
+//                          original OpenCV call, see INTEGRATION.md;
+//   any other status       the GPU call failed (no B200, a CUDA error such as a failed allocation): the message is
+//                          in urmvo_last_error(); nothing aborts — keep the OpenCV call for this frame or stop.
 bool FindFundamentalInliersGPU(const std::vector<cv::Point2f>& points0, const std::vector<cv::Point2f>& points1,
                                std::vector<unsigned char>& inliers);
+// urmvo_status of the last FindFundamentalInliersGPU call on this thread (0 after a handled call).
+int FindFundamentalInliersStatus();

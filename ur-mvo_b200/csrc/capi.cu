@@ -171,6 +171,7 @@ struct urmvo_ba_plan {
   void* shard_state = nullptr;       // device
   void* shard_state_host = nullptr;  // pinned + mapped mirror written by k_sh_decide
   bool stereo = false;               // 3-row edges present (modes 5 / 6)
+  bool cluster_auto = true;          // cluster_size was chosen here: it may be halved if the GPU cannot co-schedule it
   // tile mode (csrc/ba_large.cu): one large problem as plain phase kernels, direct band solve
   bool tile = false;
   int band_m = 0;                    // bw + 1
@@ -455,6 +456,15 @@ extern "C" void urmvo_ba_plan_destroy(urmvo_ba_plan* p) {
   delete p;
 }
 
+static int ba_plan_create_impl_(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, const int32_t* cam_off,
+                               const int32_t* pt_off, const int32_t* obs_off, const double* poses,
+                               const uint8_t* fixed, const double* pts, const double* uv,
+                               const int32_t* cam, const int32_t* pt, const double* intr,
+                               double chi2_thr, int it0, int it1, const urmvo_ba_options* opts,
+                               bool sharded, const uint8_t* covis, bool borrow_ws,
+                               const uint8_t* kind, double chi2_thr_stereo);
+
+// no exception crosses the C ABI: allocation failures of the host-side flattening become a status
 static int ba_plan_create_impl(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, const int32_t* cam_off,
                                const int32_t* pt_off, const int32_t* obs_off, const double* poses,
                                const uint8_t* fixed, const double* pts, const double* uv,
@@ -462,6 +472,23 @@ static int ba_plan_create_impl(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, const
                                double chi2_thr, int it0, int it1, const urmvo_ba_options* opts,
                                bool sharded, const uint8_t* covis, bool borrow_ws = false,
                                const uint8_t* kind = nullptr, double chi2_thr_stereo = 0.0) {
+  try {
+    return ba_plan_create_impl_(ctx, out, B, cam_off, pt_off, obs_off, poses, fixed, pts, uv, cam, pt, intr, chi2_thr, it0,
+                                it1, opts, sharded, covis, borrow_ws, kind, chi2_thr_stereo);
+  } catch (const std::exception& e) {
+    if (ctx) ctx->ws_in_use = false;
+    if (out) *out = nullptr;
+    return fail(URMVO_ERR_ARG, std::string("ba_plan_create: ") + e.what());
+  }
+}
+
+static int ba_plan_create_impl_(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, const int32_t* cam_off,
+                               const int32_t* pt_off, const int32_t* obs_off, const double* poses,
+                               const uint8_t* fixed, const double* pts, const double* uv,
+                               const int32_t* cam, const int32_t* pt, const double* intr,
+                               double chi2_thr, int it0, int it1, const urmvo_ba_options* opts,
+                               bool sharded, const uint8_t* covis, bool borrow_ws,
+                               const uint8_t* kind, double chi2_thr_stereo) {
   // kind != NULL: stereo-capable window(s): uv carries 3 values per observation (u, v, u_right), intr 5 values
   // (fx, fy, cx, cy, bf), kind[o] = 1 marks an EdgeStereoSE3ProjectXYZ (reference src/g2o_optimization.cc:96-118)
   const bool stereo = kind != nullptr;
@@ -622,6 +649,7 @@ static int ba_plan_create_impl(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, const
   }
   p->cluster_size = cs;
   p->n_clusters = B;
+  p->cluster_auto = !(opts && opts->cluster_size > 0);
   int nblk_scope = cs;
   p->tile = tile;
   if (tile) {
@@ -918,7 +946,8 @@ extern "C" int urmvo_comm_init(urmvo_ctx* ctx, int rank, int world, const uint8_
 
 extern "C" int urmvo_ba_covisibility(int Nc, const uint8_t* fixed, int Np, int No, const int32_t* cam,
                                      const int32_t* pt, uint8_t* upper) {
-  if (Nc <= 0 || !fixed || !cam || !pt || !upper) return fail(URMVO_ERR_ARG, "ba_covisibility: null input");
+  if (Nc <= 0 || Np < 0 || No < 0 || !fixed || !cam || !pt || !upper) return fail(URMVO_ERR_ARG, "ba_covisibility: null input or negative size");
+  try {
   std::vector<int> cf(Nc, -1);
   int n = 0;
   for (int c = 0; c < Nc; c++) if (!fixed[c]) cf[c] = n++;
@@ -933,12 +962,18 @@ extern "C" int urmvo_ba_covisibility(int Nc, const uint8_t* fixed, int Np, int N
       for (size_t b = 0; b < v.size(); b++)
         if (v[a] <= v[b]) upper[(size_t)v[a] * n + v[b]] = 1;
   return n;
+  } catch (const std::exception& e) {
+    return fail(URMVO_ERR_ARG, std::string("ba_covisibility: ") + e.what());
+  }
 }
 
 extern "C" int urmvo_sharded_ba_create(urmvo_ctx* ctx, urmvo_ba_plan** plan, int Nc, const double* poses,
                                        const uint8_t* fixed, int Np, const double* pts, int No, const double* uv,
                                        const int32_t* cam, const int32_t* pt, const double* intr, double chi2_thr,
                                        int it0, int it1, const uint8_t* covis, const urmvo_ba_options* opts) {
+  if (ctx && ctx->world > 1 && !covis)
+    return fail(URMVO_ERR_ARG, "sharded_ba_create: with more than one rank the OR-ed co-visibility (urmvo_ba_covisibility) is "
+                               "required so that every rank builds the same structure of S");
   const int32_t co[2] = {0, Nc}, po[2] = {0, Np}, oo[2] = {0, No};
   urmvo_ba_options o = {};
   if (opts) o = *opts;
@@ -1083,7 +1118,18 @@ extern "C" int urmvo_ba_plan_run(urmvo_ba_plan* p) {
   const BAWin* wins = (const BAWin*)(p->dev + p->off_wins);
   cudaError_t e;
   if (p->use_grid) e = launch_ba_grid(wins, p->run, p->kmax, p->grid_blocks, p->threads, p->ctx->stream, p->stereo ? 1 : 0);
-  else e = launch_ba_cluster(wins, p->run, p->batch_mode, p->kmax, p->work_stride, p->ints_per_warp, p->n_clusters, p->cluster_size, p->threads, p->ctx->stream);
+  else {
+    e = launch_ba_cluster(wins, p->run, p->batch_mode, p->kmax, p->work_stride, p->ints_per_warp, p->n_clusters, p->cluster_size, p->threads, p->ctx->stream);
+    // a 16-CTA (non-portable) cluster with ~200 KB of shared memory per CTA may not be schedulable (MIG, partly
+    // disabled GPCs, another resident context): fall back to smaller clusters instead of failing the keyframe
+    while (e != cudaSuccess && p->cluster_auto && p->cluster_size > 1 &&
+           (e == cudaErrorInvalidConfiguration || e == cudaErrorLaunchOutOfResources || e == cudaErrorInvalidValue ||
+            e == cudaErrorCooperativeLaunchTooLarge)) {
+      (void)cudaGetLastError();
+      p->cluster_size /= 2;
+      e = launch_ba_cluster(wins, p->run, p->batch_mode, p->kmax, p->work_stride, p->ints_per_warp, p->n_clusters, p->cluster_size, p->threads, p->ctx->stream);
+    }
+  }
   if (e != cudaSuccess) return fail(URMVO_ERR_CUDA, std::string("BA kernel launch: ") + cudaGetErrorString(e));
   p->ctx->launches++;
   return URMVO_OK;
