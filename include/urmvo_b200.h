@@ -69,6 +69,11 @@ typedef struct {
                                  direct block-banded Cholesky — csrc/ba_large.cu), else the atomic / PCG kernels,
                             1 -> always the round-1 path (global fp64 atomics + block-Jacobi PCG),
                             2 -> tile mode or URMVO_ERR_UNSUPPORTED */
+  int32_t band_solver;   /* tile mode, direct solve of the block-banded reduced camera system:
+                            0 -> block cyclic reduction for long trajectories (>= 160 free cameras: log-depth
+                                 elimination on many SMs, csrc/ba_bcr.cu), else the sequential block-banded Cholesky,
+                            1 -> always the sequential band Cholesky (one SM, one block column after the other),
+                            2 -> cyclic reduction whenever the shape allows it (>= 2 super-blocks) */
 } urmvo_ba_options;
 
 typedef struct {

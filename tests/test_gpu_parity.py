@@ -202,6 +202,29 @@ def test_ba_bal_scale_cfg5_single_rank_matches_oracle(oracle, ctx):
     assert gs.trials[0] + gs.trials[1] == sum(r[3] for r in os_.rows())
 
 
+@pytest.mark.parametrize("n_cams,n_pts,span", [(40, 1500, 14), (47, 1800, 6), (130, 6000, 16), (333, 12000, 9)])
+def test_ba_cyclic_reduction_solver_matches_oracle_and_band_solver(oracle, ctx, n_cams, n_pts, span):
+    """Block cyclic reduction of the banded reduced camera system (csrc/ba_bcr.cu, forced with
+    band_solver = 2) against the oracle's skyline Cholesky and against the sequential band solve:
+    2 ... 6 levels, a partial last super-block, odd and even numbers of super-blocks."""
+    p = synth.make_ba(500 + n_cams, n_cams, n_pts, 0.6 * span, span, 2, 0.02)
+    res = []
+    for solver in (2, 1):
+        plan = U.ShardedBAPlan(ctx, U.shard_points(p, 0, 1), covis=U.ba_covisibility(p), opts=U.BAOptions(0, 0, 0, 0, 0, 0, 0, solver))
+        plan.run()
+        info = plan.phase_info()
+        assert info["tile_mode"] and ("cyclic" in info["band_solver"]) == (solver == 2), info
+        res.append(plan.download())
+        plan.close()
+    op, ox, oi, os_ = oracle.local_ba(p)
+    for gp, gx, gi, gs in res:
+        assert abs(gs.chi2_final[1] - os_.chi2_final[1]) <= REL_COST * abs(os_.chi2_final[1])
+        assert np.abs(gp - op).max() <= POSE_TOL and np.array_equal(gi, oi)
+        assert list(gs.iters) == list(os_.iters)[:2]
+        assert gs.trials[0] + gs.trials[1] == sum(r[3] for r in os_.rows())
+    assert np.abs(res[0][0] - res[1][0]).max() <= 1e-9
+
+
 # ------------------------------------------------------------------------------- stereo edges (S1)
 
 @pytest.mark.parametrize("force_atomic", [0, 1])

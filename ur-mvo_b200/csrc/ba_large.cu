@@ -25,18 +25,12 @@
 // LM state has already finished return immediately (LgState::active).
 
 #include "ba_device.cuh"
+#include "ba_large_tail.cuh"
 #include "kernels.h"
 #include "../../include/urmvo_b200.h"
 
 namespace urmvo {
 
-struct LgState {
-  double lambda, ni, currentChi, rho, chi_initial, scale_pose;
-  int cur, last_eval, have_eval;
-  int robust, it, n_iter, qmax, ok2;
-  int iters, trials, pcg_iters, n_level1;
-  int active;  // the current optimize() call still has trials to run
-};
 
 // development aid (urmvo_debug_lg_timing): SM cycles of thread 0 of the band solve per segment
 // 0 diagonal factorisation (to barrier 1)  1 panel (to barrier 2)  2 trailing update + row load
@@ -791,46 +785,7 @@ k_lg_solve(const BAWin* __restrict__ wins, LgState* stt, int M) {
     }
   }
   const long long t_back = clock64();
-  // ---- x_p, pose part of computeScale sum x (lambda x + b_p), trial cameras exp(x_c) * T_c
-  double sc = 0.0;
-  for (int i = t; i < n6; i += blockDim.x) {
-    const double x = yv[i];
-    W.xp[i] = x;
-    sc += x * (lambda * x + W.bp[i]);
-  }
-  sc = warp_sum(sc);
-  if ((t & 31) == 0) redv[t >> 5] = sc;
-  __syncthreads();
-  if (t == 0) {
-    double s2 = 0.0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); w++) s2 += redv[w];
-    stt->scale_pose = s2;
-    stt->ok2 = 1;
-  }
-  const int cur = stt->cur, tr = cur ^ 1;
-  for (int cc = t; cc < W.Nc; cc += blockDim.x) {
-    const double* q = W.cam[cur] + (size_t)cc * 7;
-    double* qo = W.cam[tr] + (size_t)cc * 7;
-    const int cf = W.cam_free[cc];
-    if (cf >= 0) {
-      double u[6];
-#pragma unroll
-      for (int e = 0; e < 6; e++) u[e] = yv[cf * 6 + e];
-      double qn[4], tn[3];
-      se3_oplus(u, q, q + 4, qn, tn);
-      qo[0] = qn[0]; qo[1] = qn[1]; qo[2] = qn[2]; qo[3] = qn[3];
-      qo[4] = tn[0]; qo[5] = tn[1]; qo[6] = tn[2];
-    } else {
-#pragma unroll
-      for (int e = 0; e < 7; e++) qo[e] = q[e];
-    }
-    double R[9];
-    quat_to_R(qo, R);
-    double* o = W.camRt[tr] + (size_t)cc * 12;
-#pragma unroll
-    for (int e = 0; e < 9; e++) o[e] = R[e];
-    o[9] = qo[4]; o[10] = qo[5]; o[11] = qo[6];
-  }
+  lg_solve_tail(W, stt, yv, redv, lambda);
   if (t == 0) {
     const long long t_end = clock64();
     g_lg_timing[0] += t_upd; g_lg_timing[7] += t_take; g_lg_timing[1] += t_seg[0]; g_lg_timing[2] += t_seg[1];

@@ -107,6 +107,15 @@ struct BARun {
   const void* timing_stats;  // the window whose stats pointer equals this records phase cycles
 };
 
+// Device-side Levenberg-Marquardt state of one large problem in tile mode (csrc/ba_large.cu, ba_bcr.cu).
+struct LgState {
+  double lambda, ni, currentChi, rho, chi_initial, scale_pose;
+  int cur, last_eval, have_eval;
+  int robust, it, n_iter, qmax, ok2;
+  int iters, trials, pcg_iters, n_level1;
+  int active;  // the current optimize() call still has trials to run
+};
+
 // One pose-only frame.
 struct PoseFrame {
   int No;

@@ -176,6 +176,10 @@ struct urmvo_ba_plan {
   bool tile = false;
   int band_m = 0;                    // bw + 1
   int ncf = 0;
+  bool use_bcr = false;              // long trajectories: block cyclic reduction (csrc/ba_bcr.cu) instead of the sequential band solve
+  BcrShape bcr{};
+  size_t off_bcr = 0;
+  int n_solve_launches = 1;
   size_t off_hd = 0;                 // [hdiag | scal] is the all-reduce buffer of the lambda initialisation
   size_t n_reduce_diag = 0;
   std::vector<int> pt_perm;          // device point index -> caller's point index
@@ -659,6 +663,9 @@ static int ba_plan_create_impl_(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, cons
     p->ncf = wh[0].Ncf;
     p->pt_perm = wh[0].pt_order;
     nblk_scope = 4 * ctx->n_sm;
+    const int band_solver = opts ? opts->band_solver : 0;
+    p->use_bcr = band_solver != 1 && bcr_shape(p->ncf, wh[0].bw, band_solver == 2, &p->bcr);
+    if (p->use_bcr && bcr_prepare(p->bcr) != cudaSuccess) { delete p; return fail(URMVO_ERR_CUDA, "ba_plan_create: cudaFuncSetAttribute failed (cyclic reduction)"); }
     if (band_smem_bytes(p->band_m, p->ncf) > 220 * 1024) { delete p; return fail(URMVO_ERR_UNSUPPORTED, "local_ba: too many free cameras for the direct band solve"); }
     if (lg_prepare(p->band_m, p->ncf) != cudaSuccess) { delete p; return fail(URMVO_ERR_CUDA, "ba_plan_create: cudaFuncSetAttribute failed"); }
   } else if (p->use_grid) {
@@ -728,6 +735,7 @@ static int ba_plan_create_impl_(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, cons
   const size_t o_spart = A.take<double>(spart_total);
   const size_t o_lband = A.take<double>(tile ? (size_t)w0.Ncf * (w0.bw + 1) * 36 : 0);
   const size_t o_cpart = A.take<double>(tile ? (size_t)16 * ctx->n_sm : 0);
+  p->off_bcr = A.take<double>(tile && p->use_bcr ? p->bcr.total : 0);
   const size_t o_ticket = A.take<unsigned int>(tile ? 8 : 0);
   p->off_pose_out = A.take<double>(TC * 7);
   p->off_pts_out = A.take<double>(TP * 3);
@@ -1027,7 +1035,14 @@ static int run_large(urmvo_ba_plan* p) {
           if (timed) CU_TRY(cudaEventRecord(p->ev[1], s));
           if (allreduce(scal, p->n_reduce_main)) return URMVO_ERR_NCCL;
           if (timed) CU_TRY(cudaEventRecord(p->ev[2], s));
-          LG_TRY(launch_lg_solve(wins, p->shard_state, p->band_m, p->ncf, s));
+          if (p->use_bcr) {
+            int nl = 0;
+            LG_TRY(launch_bcr_solve(wins, p->shard_state, p->bcr, (double*)(p->dev + p->off_bcr), s, &nl));
+            ctx->launches += nl - 1;
+            p->n_solve_launches = nl;
+          } else {
+            LG_TRY(launch_lg_solve(wins, p->shard_state, p->band_m, p->ncf, s));
+          }
           if (timed) CU_TRY(cudaEventRecord(p->ev[3], s));
           LG_TRY(launch_lg_backsub(wins, p->run, p->shard_state, scal, 2 * G, s));
           if (allreduce(scal + 2, 2)) return URMVO_ERR_NCCL;
@@ -1171,7 +1186,7 @@ extern "C" int urmvo_ba_plan_download(urmvo_ba_plan* p, double* poses, double* p
 extern "C" int urmvo_ba_plan_phase_info(urmvo_ba_plan* p, float* ms4, int32_t* info5) {
   if (!p || !ms4 || !info5) return fail(URMVO_ERR_ARG, "ba_plan_phase_info: null argument");
   for (int k = 0; k < 4; k++) ms4[k] = p->phase_ms[k];
-  info5[0] = p->tile ? 1 : 0;
+  info5[0] = p->tile ? (p->use_bcr ? 2 + 16 * p->bcr.L + 4096 * p->bcr.K : 1) : 0;  // 1: band solve, 2 + 16 levels + 4096 super-blocks: cyclic reduction
   info5[1] = p->tile ? p->band_m - 1 : -1;
   info5[2] = p->n_trial_launches;
   info5[3] = p->n_host_syncs;

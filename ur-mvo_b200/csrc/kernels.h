@@ -57,6 +57,17 @@ cudaError_t launch_lg_decide(void* stt, const double* scal, void* host_copy, cud
 cudaError_t launch_lg_classify(const BAWin* w, const BARun& run, void* stt, int pass, int grid, cudaStream_t s);  // 2 launches
 cudaError_t launch_lg_finish(const BAWin* w, void* stt, int grid, cudaStream_t s);
 void lg_flags(const void* host_copy, int* active, int* it);
+// long block-banded systems: block cyclic reduction instead of the sequential band solve (ba_bcr.cu)
+constexpr int kBcrMaxMb = 108;      // scalars per super-block (18 cameras)
+constexpr int kBcrMaxLevels = 12;
+struct BcrShape {
+  int n, m, mb, K, L, M;            // free cameras, cameras / scalars per super-block, super-blocks, levels, band row stride
+  size_t coff[kBcrMaxLevels + 1];   // first coupling block of each level
+  size_t off_D, off_C, off_rhs, off_x, off_invd, off_fail, total;  // doubles, into the workspace
+};
+bool bcr_shape(int n, int bw, int force, BcrShape* out);
+cudaError_t bcr_prepare(const BcrShape& sh);
+cudaError_t launch_bcr_solve(const BAWin* w, void* stt, const BcrShape& sh, double* work, cudaStream_t s, int* n_launch);
 constexpr int kBAPartWidth = 8;  // doubles per CTA and buffer in BAWin::part (+8 flag doubles)
 
 // ---- pose_kernels.cu

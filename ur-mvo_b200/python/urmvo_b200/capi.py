@@ -32,7 +32,7 @@ class FMStats(C.Structure):
 class BAOptions(C.Structure):
     _fields_ = [("pcg_tol", C.c_double), ("pcg_max_iter", C.c_int32), ("cluster_size", C.c_int32),
                 ("threads", C.c_int32), ("force_atomic", C.c_int32), ("dense_solver", C.c_int32),
-                ("large_mode", C.c_int32)]
+                ("large_mode", C.c_int32), ("band_solver", C.c_int32)]
 
 
 class BAStats(C.Structure):
@@ -351,7 +351,12 @@ def _phase_info(L, h):
     ms = (C.c_float * 4)()
     info = (C.c_int32 * 5)()
     _check(L.urmvo_ba_plan_phase_info(h, ms, info), "urmvo_ba_plan_phase_info")
-    return {"tile_mode": bool(info[0]), "half_bandwidth_blocks": int(info[1]), "trials_enqueued": int(info[2]),
+    solver = "none"
+    if info[0] == 1:
+        solver = "sequential block-banded Cholesky"
+    elif info[0] & 2:
+        solver = f"block cyclic reduction ({info[0] >> 12} super-blocks, {(info[0] >> 4) & 255} levels)"
+    return {"tile_mode": bool(info[0]), "band_solver": solver, "half_bandwidth_blocks": int(info[1]), "trials_enqueued": int(info[2]),
             "host_syncs": int(info[3]), "allreduce_doubles_per_trial": int(info[4]),
             "phase_ms_first_trial_of_each_batch": {"lin": float(ms[0]), "allreduce": float(ms[1]), "solve": float(ms[2]),
                                                    "backsub_decide": float(ms[3])}}
