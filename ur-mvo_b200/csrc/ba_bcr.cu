@@ -33,6 +33,8 @@ namespace urmvo {
 namespace {
 
 constexpr int kBcrThreads = 256;
+constexpr int kBcrCholThreads = 736;  // lower 3 x 3 tiles of a 108 x 108 block (666) + 36 right-hand-side tiles
+constexpr int kBcrBackThreads = 512;
 constexpr int kBcrTile = 48;        // output tile of k_bcr_update (3 x 3 values per thread)
 constexpr int kBcrRowsPerWarp = 4;  // vectors a warp of k_bcr_trsm carries through one substitution
 
@@ -84,79 +86,176 @@ k_bcr_assemble(const BAWin* __restrict__ wins, const LgState* __restrict__ stt, 
   }
 }
 
-// ---- Cholesky of one mb x mb block in shared memory + y = L^-1 b (+ x = L^-T y for the last block) ----
-// Input: lower triangle of D (row-major).  Output F[r][c] = L[max(r,c)][min(r,c)] (row j of F holds row j
-// of L up to the diagonal and column j of L after it: both substitutions read rows of F), the
-// reciprocal diagonal in invd, y over b.  Right-looking, one barrier per column: the column is read
-// unscaled, A[i][c] -= A[i][j] A[c][j] / A[j][j].
-__device__ __forceinline__ void bcr_chol_block(double* A, int lda, int mb, double* invd_s, int* fail_flag) {
-  const int t = threadIdx.x, nt = blockDim.x;
-  for (int j = 0; j < mb; j++) {
-    const double d = A[j * lda + j];
-    const bool bad = !(d > 0.0);
-    const double ri = rsqrt(bad ? 1.0 : d);
-    const double r2 = ri * ri;
-    if (t == 0) { invd_s[j] = ri; if (bad) *fail_flag = 1; }
-    // trailing lower triangle (i >= c > j): one row per warp, lanes over the columns
-    const int warp = t >> 5, lane = t & 31, n_warp = nt >> 5;
-    for (int i = j + 1 + warp; i < mb; i += n_warp) {
-      const double f = A[i * lda + j] * r2;
-      for (int c = j + 1 + lane; c <= i; c += 32) A[i * lda + c] = fma(-f, A[c * lda + j], A[i * lda + c]);
-    }
-    __syncthreads();
-  }
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const size_t src = __cvta_generic_to_global(gsrc);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const size_t src = __cvta_generic_to_global(gsrc);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n cp.async.wait_all;" ::: "memory");
+}
+// mb x mb block (contiguous, 16-byte aligned on both sides) -> shared memory, every request in flight at once
+__device__ __forceinline__ void bcr_fetch_block(double* dst, const double* __restrict__ src, int mb) {
+  for (int c = threadIdx.x; c < mb * mb / 2; c += blockDim.x) cp_async16(dst + 2 * c, src + 2 * c);
 }
 
-__global__ void __launch_bounds__(kBcrThreads)
+// Backward substitution L^T x = t by ONE warp: lane l holds t[l], t[l + 32], ...; row j of F (row j of L in
+// front of the diagonal) comes from shared memory.  Right-looking: x_j = t_j / L_jj, t_i -= L_ji x_j (i < j).
+template <int NSLOT>
+__device__ __forceinline__ void bcr_backsolve_warp(const double* __restrict__ F_s, int ldf, const double* __restrict__ invd_s,
+                                                   int mb, const double* __restrict__ t_in, double* __restrict__ x_out) {
+  const int lane = threadIdx.x & 31;
+  double v[NSLOT];
+#pragma unroll
+  for (int sl = 0; sl < NSLOT; sl++) v[sl] = sl * 32 + lane < mb ? t_in[sl * 32 + lane] : 0.0;
+#pragma unroll
+  for (int jb = NSLOT - 1; jb >= 0; jb--) {
+    const int jn = mb - jb * 32 < 32 ? mb - jb * 32 : 32;
+    for (int jj = jn - 1; jj >= 0; jj--) {
+      const int j = jb * 32 + jj;
+      const double xj = __shfl_sync(0xffffffffu, v[jb], jj) * invd_s[j];
+      if (lane == jj) v[jb] = xj;
+      const double* Fj = F_s + (size_t)j * ldf;
+#pragma unroll
+      for (int sl = 0; sl <= jb; sl++) {
+        const int i = sl * 32 + lane;
+        if (i < j) v[sl] = fma(-Fj[i], xj, v[sl]);
+      }
+    }
+  }
+#pragma unroll
+  for (int sl = 0; sl < NSLOT; sl++)
+    if (sl * 32 + lane < mb) x_out[sl * 32 + lane] = v[sl];
+}
+__device__ __forceinline__ void bcr_backsolve(const double* F_s, int ldf, const double* invd_s, int mb, const double* t_in,
+                                              double* x_out) {
+  if (mb <= 64) bcr_backsolve_warp<2>(F_s, ldf, invd_s, mb, t_in, x_out);
+  else if (mb <= 96) bcr_backsolve_warp<3>(F_s, ldf, invd_s, mb, t_in, x_out);
+  else bcr_backsolve_warp<4>(F_s, ldf, invd_s, mb, t_in, x_out);
+}
+
+// ---- Cholesky of one mb x mb block, y = L^-1 b (+ x = L^-T y for the last block) ----
+// Input: lower triangle of D (row-major).  Output F[r][c] = L[max(r,c)][min(r,c)] (row j of F holds row j
+// of L up to the diagonal and column j of L behind it: both substitutions read rows of F), the
+// reciprocal diagonal in invd, y over b.
+// Register-resident: thread (ti, tc), ti >= tc, owns the 3 x 3 tile of rows 3 ti.., columns 3 tc.. for the whole
+// factorisation; T = mb / 3 more threads own the right-hand side as one more (1 x 3)-tiled row.  Step p:
+// (1) the owner of (p, p) factorises it, (2) the owners of column p solve against it and publish their tiles,
+// (3) everybody to the right subtracts L_ip L_cp^T.  Two barriers per step, mb / 3 steps.
+__global__ void __launch_bounds__(kBcrCholThreads)
 k_bcr_chol(const LgState* __restrict__ stt, BcrShape sh, double* __restrict__ work, int level, int last) {
   extern __shared__ __align__(16) double smem_d[];
   if (!stt->active) return;
-  const int mb = sh.mb, lda = mb + 1;
+  const int mb = sh.mb, T = mb / 3, n_tiles = T * (T + 1) / 2;
   const int s = 1 << level;
   const int k = last ? 0 : (2 * blockIdx.x + 1) * s;
-  double* A = smem_d;                 // [mb][lda]
-  double* invd_s = A + mb * lda;      // mb
-  double* yv = invd_s + mb;           // mb
+  double* panel = smem_d;             // [T + 1][9]: L_ip of the step, entry T: y_p
+  double* Lpp = panel + (T + 1) * 9;  // r0 l10 r1 l20 l21 r2 (reciprocal diagonal)
+  double* invd_s = Lpp + 8;           // mb
+  double* yv = invd_s + mb;           // mb (last block only)
+  double* F_s = yv + mb;              // [mb][mb] (last block only)
   int* fail = reinterpret_cast<int*>(work + sh.off_fail);
   double* D = work + sh.off_D + (size_t)k * mb * mb;
   double* b = work + sh.off_rhs + (size_t)k * mb;
-  for (int e = threadIdx.x; e < mb * mb; e += blockDim.x) {
-    const int r = e / mb, c = e - r * mb;
-    A[r * lda + c] = D[e];
+  const int tid = threadIdx.x;
+  const bool is_mat = tid < n_tiles, is_rhs = tid >= n_tiles && tid < n_tiles + T;
+  int ti = 0, tc = 0;
+  if (is_mat) {
+    ti = (int)((sqrtf(8.0f * (float)tid + 1.0f) - 1.0f) * 0.5f);
+    while ((ti + 1) * (ti + 2) / 2 <= tid) ti++;
+    while (ti * (ti + 1) / 2 > tid) ti--;
+    tc = tid - ti * (ti + 1) / 2;
+  } else if (is_rhs) {
+    ti = T;
+    tc = tid - n_tiles;
   }
-  for (int e = threadIdx.x; e < mb; e += blockDim.x) yv[e] = b[e];
-  __syncthreads();
-  bcr_chol_block(A, lda, mb, invd_s, fail);
-  // F: scaled factor, mirrored
-  for (int e = threadIdx.x; e < mb * mb; e += blockDim.x) {
-    const int r = e / mb, c = e - r * mb;
-    const int hi = r > c ? r : c, lo = r > c ? c : r;
-    D[e] = hi == lo ? 1.0 / invd_s[lo] : A[hi * lda + lo] * invd_s[lo];
+  double a[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  if (is_mat) {
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+      for (int c = 0; c < 3; c++) a[r][c] = D[(size_t)(ti * 3 + r) * mb + tc * 3 + c];
+  } else if (is_rhs) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) a[0][c] = b[tc * 3 + c];
   }
-  for (int e = threadIdx.x; e < mb; e += blockDim.x) work[sh.off_invd + (size_t)k * mb + e] = invd_s[e];
-  // y = L^-1 b by warp 0 (unscaled columns: L[i][j] = A[i][j] invd[j])
-  if (threadIdx.x < 32) {
-    const int lane = threadIdx.x;
-    for (int j = 0; j < mb; j++) {
-      const double yj = yv[j] * invd_s[j];
-      __syncwarp();
-      if (lane == 0) yv[j] = yj;
-      const double f = yj * invd_s[j];
-      for (int i = j + 1 + lane; i < mb; i += 32) yv[i] = fma(-A[i * lda + j], f, yv[i]);
-      __syncwarp();
+  for (int p = 0; p < T; p++) {
+    if (is_mat && ti == p && tc == p) {
+      const double d0 = a[0][0];
+      const bool bad0 = !(d0 > 0.0);
+      const double r0 = rsqrt(bad0 ? 1.0 : d0);
+      const double l10 = a[1][0] * r0, l20 = a[2][0] * r0;
+      const double d1 = a[1][1] - l10 * l10;
+      const bool bad1 = !(d1 > 0.0);
+      const double r1 = rsqrt(bad1 ? 1.0 : d1);
+      const double l21 = (a[2][1] - l20 * l10) * r1;
+      const double d2 = a[2][2] - l20 * l20 - l21 * l21;
+      const bool bad2 = !(d2 > 0.0);
+      const double r2 = rsqrt(bad2 ? 1.0 : d2);
+      if (bad0 || bad1 || bad2) *fail = 1;
+      Lpp[0] = r0; Lpp[1] = l10; Lpp[2] = r1; Lpp[3] = l20; Lpp[4] = l21; Lpp[5] = r2;
+      invd_s[p * 3] = r0; invd_s[p * 3 + 1] = r1; invd_s[p * 3 + 2] = r2;
+      a[0][0] = d0 * r0; a[1][0] = l10; a[1][1] = d1 * r1; a[2][0] = l20; a[2][1] = l21; a[2][2] = d2 * r2;
+      a[0][1] = l10; a[0][2] = l20; a[1][2] = l21;  // mirrored: the tile is written out whole
     }
-    if (last) {  // x = L^-T y
-      for (int j = mb - 1; j >= 0; j--) {
-        const double xj = yv[j] * invd_s[j];
-        __syncwarp();
-        if (lane == 0) yv[j] = xj;
-        for (int i = lane; i < j; i += 32) yv[i] = fma(-A[j * lda + i] * invd_s[i], xj, yv[i]);
-        __syncwarp();
+    __syncthreads();
+    if ((is_mat || is_rhs) && tc == p && ti > p) {
+      const double r0 = Lpp[0], l10 = Lpp[1], r1 = Lpp[2], l20 = Lpp[3], l21 = Lpp[4], r2 = Lpp[5];
+      double* dst = panel + ti * 9;
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        if (r > 0 && is_rhs) break;
+        const double x0 = a[r][0] * r0;
+        const double x1 = (a[r][1] - x0 * l10) * r1;
+        const double x2 = (a[r][2] - x0 * l20 - x1 * l21) * r2;
+        a[r][0] = x0; a[r][1] = x1; a[r][2] = x2;
+        dst[r * 3] = x0; dst[r * 3 + 1] = x1; dst[r * 3 + 2] = x2;
       }
     }
-    double* out = last ? work + sh.off_x + (size_t)k * mb : b;
-    for (int e = lane; e < mb; e += 32) out[e] = yv[e];
+    __syncthreads();
+    if ((is_mat || is_rhs) && tc > p) {
+      const double* Li = panel + ti * 9;
+      const double* Lc = panel + tc * 9;
+      double lc[9];
+#pragma unroll
+      for (int e = 0; e < 9; e++) lc[e] = Lc[e];
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        if (r > 0 && is_rhs) break;
+        const double i0 = Li[r * 3], i1 = Li[r * 3 + 1], i2 = Li[r * 3 + 2];
+#pragma unroll
+        for (int c = 0; c < 3; c++) a[r][c] -= i0 * lc[c * 3] + i1 * lc[c * 3 + 1] + i2 * lc[c * 3 + 2];
+      }
+    }
   }
+  // F (mirrored factor), y
+  if (is_mat) {
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        D[(size_t)(ti * 3 + r) * mb + tc * 3 + c] = a[r][c];
+        if (ti != tc) D[(size_t)(tc * 3 + c) * mb + ti * 3 + r] = a[r][c];
+        if (last) {
+          F_s[(ti * 3 + r) * mb + tc * 3 + c] = a[r][c];
+          if (ti != tc) F_s[(tc * 3 + c) * mb + ti * 3 + r] = a[r][c];
+        }
+      }
+  } else if (is_rhs) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      if (last) yv[tc * 3 + c] = a[0][c];
+      else b[tc * 3 + c] = a[0][c];
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < mb; e += blockDim.x) work[sh.off_invd + (size_t)k * mb + e] = invd_s[e];
+  if (last && tid < 32) bcr_backsolve(F_s, mb, invd_s, mb, yv, work + sh.off_x + (size_t)k * mb);  // x = L^-T y
 }
 
 // ---- Z = C L^-T for the rows of the (up to) two coupling blocks of every eliminated super-block ----
@@ -174,6 +273,8 @@ __device__ __forceinline__ void bcr_trsm_rows(const double* __restrict__ F_s, in
       const int i = sl * 32 + lane;
       v[q][sl] = (q < n_rows && i < mb) ? Zrows[(size_t)q * mb + i] : 0.0;
     }
+  cp_async_wait_all();  // F (fetched by the whole CTA while the rows were loaded)
+  __syncthreads();
 #pragma unroll
   for (int jb = 0; jb < NSLOT; jb++) {
     const int jn = mb - jb * 32 < 32 ? mb - jb * 32 : 32;
@@ -207,7 +308,8 @@ __device__ __forceinline__ void bcr_trsm_rows(const double* __restrict__ F_s, in
     }
 }
 
-// grid: (CTAs per eliminated super-block, eliminated super-blocks of the level)
+// grid: (CTAs per eliminated super-block, eliminated super-blocks of the level); every warp takes exactly one
+// group of kBcrRowsPerWarp rows (mb is a multiple of 6, the groups are cut per coupling block)
 __global__ void __launch_bounds__(kBcrThreads)
 k_bcr_trsm(const LgState* __restrict__ stt, BcrShape sh, double* __restrict__ work, int level) {
   extern __shared__ __align__(16) double smem_d[];
@@ -218,39 +320,49 @@ k_bcr_trsm(const LgState* __restrict__ stt, BcrShape sh, double* __restrict__ wo
   const bool has_right = u + 1 < n_act;
   double* F_s = smem_d;
   double* invd_s = F_s + (size_t)mb * ldf;
-  const double* F = work + sh.off_D + (size_t)k * mb * mb;
-  for (int e = threadIdx.x; e < mb * mb; e += blockDim.x) F_s[e] = F[e];
+  bcr_fetch_block(F_s, work + sh.off_D + (size_t)k * mb * mb, mb);
   for (int e = threadIdx.x; e < mb; e += blockDim.x) invd_s[e] = work[sh.off_invd + (size_t)k * mb + e];
-  __syncthreads();
   const int warp = threadIdx.x >> 5, n_warp = blockDim.x >> 5;
-  const int total = (has_right ? 2 : 1) * mb;  // rows of Z_a, then rows of Z_c
-  const int per_cta = n_warp * kBcrRowsPerWarp;
-  for (int r0 = (blockIdx.x * n_warp + warp) * kBcrRowsPerWarp; r0 < total; r0 += gridDim.x * per_cta) {
-    // a group of rows never straddles the two blocks when mb is a multiple of kBcrRowsPerWarp; handle the general case
-    int first = r0, cnt = total - r0 < kBcrRowsPerWarp ? total - r0 : kBcrRowsPerWarp;
-    while (cnt > 0) {
-      const int blk = first >= mb ? 1 : 0;
-      const int in_blk = first - blk * mb;
-      const int take = (blk == 0 && first + cnt > mb) ? mb - first : cnt;
-      double* Z = work + bcr_pair(sh, level, blk == 0 ? u - 1 : u) + (size_t)in_blk * mb;
-      if (mb <= 64) bcr_trsm_rows<2>(F_s, ldf, invd_s, mb, Z, take);
-      else if (mb <= 96) bcr_trsm_rows<3>(F_s, ldf, invd_s, mb, Z, take);
-      else bcr_trsm_rows<4>(F_s, ldf, invd_s, mb, Z, take);
-      first += take;
-      cnt -= take;
-    }
-  }
+  const int groups_blk = (mb + kBcrRowsPerWarp - 1) / kBcrRowsPerWarp;
+  const int g = blockIdx.x * n_warp + warp;  // group of rows: [0, groups_blk) in Z_a, then Z_c
+  const int blk = g >= groups_blk ? 1 : 0;
+  const int r0 = (g - blk * groups_blk) * kBcrRowsPerWarp;
+  const bool work_here = g < (has_right ? 2 : 1) * groups_blk;
+  const int take = work_here ? (mb - r0 < kBcrRowsPerWarp ? mb - r0 : kBcrRowsPerWarp) : 0;
+  double* Z = work + bcr_pair(sh, level, blk == 0 || !work_here ? u - 1 : u) + (size_t)(work_here ? r0 : 0) * mb;
+  if (mb <= 64) bcr_trsm_rows<2>(F_s, ldf, invd_s, mb, Z, take);
+  else if (mb <= 96) bcr_trsm_rows<3>(F_s, ldf, invd_s, mb, Z, take);
+  else bcr_trsm_rows<4>(F_s, ldf, invd_s, mb, Z, take);
 }
 
 // ---- products of the level: C (-)= A B^T, 48 x 48 tiles, the contracted index staged whole in shared memory ----
 // Work items: (a) every surviving super-block a: D_a -= Z Z^T for the eliminated neighbours on both sides (lower
 // tiles only), b_a -= Z y; (b) every eliminated super-block with two neighbours: the new coupling -Z_a Z_c^T,
 // stored [surviving at level + 1][eliminated at level + 1].
-__device__ __forceinline__ void bcr_load_tile(double* dst, const double* __restrict__ src, int row0, int mb) {
-  // dst[k][kBcrTile + 1] <- src[row0 + i][k], zero rows beyond mb
+// Tiles are staged row-major with an odd row stride (mb + 1): thread (ty, tx) reads rows 3 ty.. of A (two
+// distinct addresses per warp: broadcast) and rows 3 tx.. of B (16 rows, 3 (mb + 1) doubles apart: conflict-free).
+__device__ __forceinline__ void bcr_fetch_tile(double* dst, const double* __restrict__ src, int row0, int mb) {
+  const int ld = mb + 1;
   for (int e = threadIdx.x; e < kBcrTile * mb; e += blockDim.x) {
     const int i = e / mb, k = e - i * mb;
-    dst[k * (kBcrTile + 1) + i] = row0 + i < mb ? src[(size_t)(row0 + i) * mb + k] : 0.0;
+    if (row0 + i < mb) cp_async8(dst + i * ld + k, src + (size_t)(row0 + i) * mb + k);
+    else dst[i * ld + k] = 0.0;
+  }
+}
+__device__ __forceinline__ void bcr_tile_product(const double* __restrict__ As, const double* __restrict__ Bs, int mb,
+                                                 int ty, int tx, double (&acc)[3][3]) {
+  const int ld = mb + 1;
+  const double* a0 = As + (ty * 3) * ld;
+  const double* b0 = Bs + (tx * 3) * ld;
+#pragma unroll 4
+  for (int k = 0; k < mb; k++) {
+    double av[3], bv[3];
+#pragma unroll
+    for (int q = 0; q < 3; q++) { av[q] = a0[q * ld + k]; bv[q] = b0[q * ld + k]; }
+#pragma unroll
+    for (int p = 0; p < 3; p++)
+#pragma unroll
+      for (int q = 0; q < 3; q++) acc[p][q] = fma(av[p], bv[q], acc[p][q]);
   }
 }
 
@@ -258,13 +370,13 @@ __global__ void __launch_bounds__(kBcrThreads)
 k_bcr_update(const LgState* __restrict__ stt, BcrShape sh, double* __restrict__ work, int level) {
   extern __shared__ __align__(16) double smem_d[];
   if (!stt->active) return;
-  const int mb = sh.mb;
+  const int mb = sh.mb, ld = mb + 1;
   const int s = 1 << level, n_act = (sh.K + s - 1) / s;
   const int T = (mb + kBcrTile - 1) / kBcrTile, Tl = T * (T + 1) / 2;
   const int n_surv = (n_act + 1) / 2, n_el = n_act / 2;
-  double* As = smem_d;
-  double* Bs = As + (size_t)mb * (kBcrTile + 1);
-  double* ys = Bs + (size_t)mb * (kBcrTile + 1);
+  double* As = smem_d;                        // [2 sides][48][ld]
+  double* Bs = As + (size_t)2 * kBcrTile * ld;  // [2 sides][48][ld]
+  double* ys = Bs + (size_t)2 * kBcrTile * ld;  // [2][mb]
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   int b = blockIdx.x;
   if (b < n_surv * Tl) {
@@ -274,32 +386,29 @@ k_bcr_update(const LgState* __restrict__ stt, BcrShape sh, double* __restrict__ 
     while ((ti + 1) * (ti + 2) / 2 <= tl) ti++;
     const int tj = tl - ti * (ti + 1) / 2;
     const int v = 2 * f, a = v * s;
-    double acc[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-    double racc = 0.0;
+    // side 0: eliminated neighbour on the right (pair v), side 1: on the left (pair v - 1); rows = a in both
+    const bool have[2] = {v + 1 < n_act, v >= 2};
     for (int side = 0; side < 2; side++) {
-      // side 0: eliminated neighbour on the right (pair v, rows = a), side 1: on the left (pair v - 1, rows = a)
-      if (side == 0 ? v + 1 >= n_act : v < 2) continue;
+      if (!have[side]) continue;
       const int pair = side == 0 ? v : v - 1;
       const int kel = side == 0 ? a + s : a - s;
       const double* Z = work + bcr_pair(sh, level, pair);
-      __syncthreads();
-      bcr_load_tile(As, Z, ti * kBcrTile, mb);
-      if (tj != ti) bcr_load_tile(Bs, Z, tj * kBcrTile, mb);
+      bcr_fetch_tile(As + (size_t)side * kBcrTile * ld, Z, ti * kBcrTile, mb);
+      if (tj != ti) bcr_fetch_tile(Bs + (size_t)side * kBcrTile * ld, Z, tj * kBcrTile, mb);
       if (tj == 0)
-        for (int e = threadIdx.x; e < mb; e += blockDim.x) ys[e] = work[sh.off_rhs + (size_t)kel * mb + e];
-      __syncthreads();
-      const double* Bt = tj != ti ? Bs : As;
-      for (int k = 0; k < mb; k++) {
-        double av[3], bv[3];
-#pragma unroll
-        for (int q = 0; q < 3; q++) { av[q] = As[k * (kBcrTile + 1) + ty * 3 + q]; bv[q] = Bt[k * (kBcrTile + 1) + tx * 3 + q]; }
-#pragma unroll
-        for (int p = 0; p < 3; p++)
-#pragma unroll
-          for (int q = 0; q < 3; q++) acc[p][q] = fma(av[p], bv[q], acc[p][q]);
-      }
+        for (int e = threadIdx.x; e < mb; e += blockDim.x) ys[side * mb + e] = work[sh.off_rhs + (size_t)kel * mb + e];
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    double acc[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    double racc = 0.0;
+    for (int side = 0; side < 2; side++) {
+      if (!have[side]) continue;
+      const double* At = As + (size_t)side * kBcrTile * ld;
+      const double* Bt = tj != ti ? Bs + (size_t)side * kBcrTile * ld : At;
+      bcr_tile_product(At, Bt, mb, ty, tx, acc);
       if (tj == 0 && threadIdx.x < kBcrTile)
-        for (int k = 0; k < mb; k++) racc = fma(As[k * (kBcrTile + 1) + threadIdx.x], ys[k], racc);
+        for (int k = 0; k < mb; k++) racc = fma(At[threadIdx.x * ld + k], ys[side * mb + k], racc);
     }
     double* D = work + sh.off_D + (size_t)a * mb * mb;
 #pragma unroll
@@ -325,21 +434,12 @@ k_bcr_update(const LgState* __restrict__ stt, BcrShape sh, double* __restrict__ 
   const double* Zc = work + bcr_pair(sh, level, u);      // rows: right neighbour
   const int jn = (u - 1) / 2;                            // pair index at level + 1
   const bool left_survives = (jn & 1) == 0;
-  const double* Ar = left_survives ? Za : Zc;            // rows of the new block
-  const double* Bc = left_survives ? Zc : Za;            // columns of the new block
-  bcr_load_tile(As, Ar, ti * kBcrTile, mb);
-  bcr_load_tile(Bs, Bc, tj * kBcrTile, mb);
+  bcr_fetch_tile(As, left_survives ? Za : Zc, ti * kBcrTile, mb);  // rows of the new block
+  bcr_fetch_tile(Bs, left_survives ? Zc : Za, tj * kBcrTile, mb);  // columns of the new block
+  cp_async_wait_all();
   __syncthreads();
   double acc[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-  for (int k = 0; k < mb; k++) {
-    double av[3], bv[3];
-#pragma unroll
-    for (int q = 0; q < 3; q++) { av[q] = As[k * (kBcrTile + 1) + ty * 3 + q]; bv[q] = Bs[k * (kBcrTile + 1) + tx * 3 + q]; }
-#pragma unroll
-    for (int p = 0; p < 3; p++)
-#pragma unroll
-      for (int q = 0; q < 3; q++) acc[p][q] = fma(av[p], bv[q], acc[p][q]);
-  }
+  bcr_tile_product(As, Bs, mb, ty, tx, acc);
   double* C = work + bcr_pair(sh, level + 1, jn);
 #pragma unroll
   for (int p = 0; p < 3; p++)
@@ -351,7 +451,7 @@ k_bcr_update(const LgState* __restrict__ stt, BcrShape sh, double* __restrict__ 
 }
 
 // ---- downwards: x_k = L^-T (y_k - Z_a^T x_a - Z_c^T x_c) for the super-blocks eliminated at `level` ----
-__global__ void __launch_bounds__(kBcrThreads)
+__global__ void __launch_bounds__(kBcrBackThreads)
 k_bcr_back(const LgState* __restrict__ stt, BcrShape sh, double* __restrict__ work, int level) {
   extern __shared__ __align__(16) double smem_d[];
   if (!stt->active) return;
@@ -363,73 +463,65 @@ k_bcr_back(const LgState* __restrict__ stt, BcrShape sh, double* __restrict__ wo
   double* tv = F_s + (size_t)mb * mb;         // mb
   double* xa = tv + mb;                       // mb
   double* xc = xa + mb;                       // mb
-  double* part = xc + mb;                     // [4][mb]
-  double* invd_s = part + 4 * mb;             // mb
-  const double* F = work + sh.off_D + (size_t)k * mb * mb;
-  for (int e = threadIdx.x; e < mb * mb; e += blockDim.x) F_s[e] = F[e];
+  double* part = xc + mb;                     // [8][mb]
+  double* invd_s = part + 8 * mb;             // mb
+  bcr_fetch_block(F_s, work + sh.off_D + (size_t)k * mb * mb, mb);
   for (int e = threadIdx.x; e < mb; e += blockDim.x) {
     xa[e] = work[sh.off_x + (size_t)(k - s) * mb + e];
     xc[e] = has_right ? work[sh.off_x + (size_t)(k + s) * mb + e] : 0.0;
     invd_s[e] = work[sh.off_invd + (size_t)k * mb + e];
   }
   __syncthreads();
-  // Z^T x: thread (g, j), g = quarter of the rows
+  // Z^T x: thread (g, j) sums every 8th row, 8 loads in flight
   {
     const double* Za = work + bcr_pair(sh, level, u - 1);
-    const double* Zc = work + bcr_pair(sh, level, u);
-    const int g = threadIdx.x / 64, j0 = threadIdx.x - g * 64;
-    for (int j = j0; j < mb; j += 64) {
-      double acc = 0.0;
+    const double* Zc = work + bcr_pair(sh, level, has_right ? u : u - 1);
+    const int g = threadIdx.x >> 7, j = threadIdx.x & 127;  // 4 groups of 128 columns at 512 threads
+    if (j < mb) {
+      double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll 4
       for (int r = g; r < mb; r += 4) {
-        acc = fma(Za[(size_t)r * mb + j], xa[r], acc);
-        if (has_right) acc = fma(Zc[(size_t)r * mb + j], xc[r], acc);
+        acc0 = fma(Za[(size_t)r * mb + j], xa[r], acc0);
+        acc1 = fma(Zc[(size_t)r * mb + j], xc[r], acc1);  // xc = 0 without a right neighbour
       }
-      part[g * mb + j] = acc;
+      part[g * mb + j] = acc0 + acc1;
     }
   }
+  cp_async_wait_all();
   __syncthreads();
   for (int j = threadIdx.x; j < mb; j += blockDim.x)
     tv[j] = work[sh.off_rhs + (size_t)k * mb + j] - ((part[j] + part[mb + j]) + (part[2 * mb + j] + part[3 * mb + j]));
   __syncthreads();
-  if (threadIdx.x < 32) {
-    const int lane = threadIdx.x;
-    for (int j = mb - 1; j >= 0; j--) {
-      const double xj = tv[j] * invd_s[j];
-      __syncwarp();
-      if (lane == 0) tv[j] = xj;
-      const double* Fj = F_s + (size_t)j * mb;
-      for (int i = lane; i < j; i += 32) tv[i] = fma(-Fj[i], xj, tv[i]);
-      __syncwarp();
-    }
-    for (int e = lane; e < mb; e += 32) work[sh.off_x + (size_t)k * mb + e] = tv[e];
-  }
+  if (threadIdx.x < 32) bcr_backsolve(F_s, mb, invd_s, mb, tv, work + sh.off_x + (size_t)k * mb);
 }
 
-// ---- x -> x_p, computeScale (pose part), trial cameras; a failed factorisation fails the solve ----
+// ---- x -> x_p, computeScale (pose part) by CTA 0; trial cameras by the other CTAs ----
+// A failed factorisation fails the solve (g2o: Cholesky failure => the trial is rejected, ok2 = false).
 __global__ void __launch_bounds__(kBcrThreads)
 k_bcr_tail(const BAWin* __restrict__ wins, LgState* stt, BcrShape sh, const double* __restrict__ work) {
-  extern __shared__ __align__(16) double smem_d[];
+  __shared__ double redv[32];
   if (!stt->active) return;
   const BAWin& W = wins[0];
   const int n6 = sh.n * 6;
-  double* yv = smem_d;
-  double* redv = yv + n6;
   const int fail = *reinterpret_cast<const int*>(work + sh.off_fail);
-  if (fail) {  // g2o: Cholesky failure => the trial is rejected (ok2 = false)
-    for (int i = threadIdx.x; i < n6; i += blockDim.x) W.xp[i] = 0.0;
-    if (threadIdx.x == 0) { stt->ok2 = 0; stt->scale_pose = 0.0; }
-    return;
+  const double* x = work + sh.off_x;  // super-blocks are contiguous in x
+  if (blockIdx.x == 0) {
+    if (fail) {
+      for (int i = threadIdx.x; i < n6; i += blockDim.x) W.xp[i] = 0.0;
+      if (threadIdx.x == 0) { stt->ok2 = 0; stt->scale_pose = 0.0; }
+      return;
+    }
+    lg_tail_scale(W, stt, x, redv, stt->lambda);
+  } else if (!fail) {
+    lg_tail_cameras(W, stt, x, (blockIdx.x - 1) * blockDim.x + threadIdx.x, (gridDim.x - 1) * blockDim.x);
   }
-  for (int i = threadIdx.x; i < n6; i += blockDim.x) yv[i] = work[sh.off_x + i];  // super-blocks are contiguous in x
-  __syncthreads();
-  lg_solve_tail(W, stt, yv, redv, stt->lambda);
 }
 
-size_t chol_smem(int mb) { return ((size_t)mb * (mb + 1) + 2 * mb) * sizeof(double); }
+size_t chol_smem(int mb, bool last) { return ((size_t)(mb / 3 + 1) * 9 + 8 + 2 * mb + (last ? (size_t)mb * mb : 0)) * sizeof(double); }
 size_t trsm_smem(int mb) { return ((size_t)mb * mb + mb) * sizeof(double); }
-size_t update_smem(int mb) { return ((size_t)2 * mb * (kBcrTile + 1) + mb) * sizeof(double); }
-size_t back_smem(int mb) { return ((size_t)mb * mb + 8 * mb) * sizeof(double); }
-size_t tail_smem(int n) { return ((size_t)n * 6 + 64) * sizeof(double); }
+size_t update_smem(int mb) { return ((size_t)4 * kBcrTile * (mb + 1) + 2 * mb) * sizeof(double); }
+size_t back_smem(int mb) { return ((size_t)mb * mb + 12 * mb) * sizeof(double); }
+int chol_threads(int mb) { const int T = mb / 3; return ((T * (T + 1) / 2 + T + 31) / 32) * 32; }
 
 }  // namespace
 
@@ -472,15 +564,14 @@ bool bcr_shape(int n, int bw, int force, BcrShape* out) {
 }
 
 cudaError_t bcr_prepare(const BcrShape& sh) {
-  cudaError_t e = cudaFuncSetAttribute(k_bcr_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_smem(sh.mb));
+  cudaError_t e = cudaFuncSetAttribute(k_bcr_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_smem(sh.mb, true));
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_bcr_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsm_smem(sh.mb));
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_bcr_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_smem(sh.mb));
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_bcr_back, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)back_smem(sh.mb));
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(k_bcr_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem(sh.n));
+  return e;
 }
 
 // The whole solve as plain launches on the stream; *n_launch receives the number of kernels enqueued.
@@ -494,23 +585,23 @@ cudaError_t launch_bcr_solve(const BAWin* w, void* stt_v, const BcrShape& sh, do
     const int s = 1 << l, n_act = (sh.K + s - 1) / s;
     const int n_el = n_act / 2, n_surv = (n_act + 1) / 2;
     if (n_el == 0) continue;
-    k_bcr_chol<<<n_el, kBcrThreads, chol_smem(mb), st>>>(stt, sh, work, l, 0);
-    const int rows_cta = (kBcrThreads / 32) * kBcrRowsPerWarp;
-    const int ctas = (2 * mb + rows_cta - 1) / rows_cta;
+    k_bcr_chol<<<n_el, chol_threads(mb), chol_smem(mb, false), st>>>(stt, sh, work, l, 0);
+    const int groups = 2 * ((mb + kBcrRowsPerWarp - 1) / kBcrRowsPerWarp), warps_cta = kBcrThreads / 32;
+    const int ctas = (groups + warps_cta - 1) / warps_cta;
     k_bcr_trsm<<<dim3(ctas, n_el), kBcrThreads, trsm_smem(mb), st>>>(stt, sh, work, l);
     k_bcr_update<<<n_surv * (T * (T + 1) / 2) + n_el * T * T, kBcrThreads, update_smem(mb), st>>>(stt, sh, work, l);
     nl += 3;
   }
-  k_bcr_chol<<<1, kBcrThreads, chol_smem(mb), st>>>(stt, sh, work, 0, 1);
+  k_bcr_chol<<<1, chol_threads(mb), chol_smem(mb, true), st>>>(stt, sh, work, 0, 1);
   nl++;
   for (int l = sh.L - 1; l >= 0; l--) {
     const int s = 1 << l, n_act = (sh.K + s - 1) / s;
     const int n_el = n_act / 2;
     if (n_el == 0) continue;
-    k_bcr_back<<<n_el, kBcrThreads, back_smem(mb), st>>>(stt, sh, work, l);
+    k_bcr_back<<<n_el, kBcrBackThreads, back_smem(mb), st>>>(stt, sh, work, l);
     nl++;
   }
-  k_bcr_tail<<<1, kBcrThreads, tail_smem(sh.n), st>>>(w, stt, sh, work);
+  k_bcr_tail<<<1 + (sh.n + 2 + kBcrThreads - 1) / kBcrThreads * 4, kBcrThreads, 0, st>>>(w, stt, sh, work);
   nl++;
   if (n_launch) *n_launch = nl;
   return cudaGetLastError();

@@ -7,9 +7,9 @@
 
 namespace urmvo {
 
-// yv: the solution in shared memory (Ncf*6), redv: >= blockDim.x/32 doubles of shared scratch.
-__device__ __forceinline__ void lg_solve_tail(const BAWin& W, LgState* stt, const double* yv, double* redv,
-                                              double lambda) {
+// Pose part of computeScale and x_p.  yv: the solution (Ncf*6, shared or global memory), redv: >= blockDim.x/32
+// doubles of shared scratch.  One CTA.
+__device__ __forceinline__ void lg_tail_scale(const BAWin& W, LgState* stt, const double* yv, double* redv, double lambda) {
   const int t = threadIdx.x, n6 = W.Ncf * 6;
   double sc = 0.0;
   for (int i = t; i < n6; i += blockDim.x) {
@@ -26,8 +26,12 @@ __device__ __forceinline__ void lg_solve_tail(const BAWin& W, LgState* stt, cons
     stt->scale_pose = s2;
     stt->ok2 = 1;
   }
+}
+
+// Trial cameras exp(x_c) * T_c for the cameras first, first + stride, ...
+__device__ __forceinline__ void lg_tail_cameras(const BAWin& W, const LgState* stt, const double* yv, int first, int stride) {
   const int cur = stt->cur, tr = cur ^ 1;
-  for (int cc = t; cc < W.Nc; cc += blockDim.x) {
+  for (int cc = first; cc < W.Nc; cc += stride) {
     const double* q = W.cam[cur] + (size_t)cc * 7;
     double* qo = W.cam[tr] + (size_t)cc * 7;
     const int cf = W.cam_free[cc];
@@ -50,6 +54,12 @@ __device__ __forceinline__ void lg_solve_tail(const BAWin& W, LgState* stt, cons
     for (int e = 0; e < 9; e++) o[e] = R[e];
     o[9] = qo[4]; o[10] = qo[5]; o[11] = qo[6];
   }
+}
+
+__device__ __forceinline__ void lg_solve_tail(const BAWin& W, LgState* stt, const double* yv, double* redv,
+                                              double lambda) {
+  lg_tail_scale(W, stt, yv, redv, lambda);
+  lg_tail_cameras(W, stt, yv, threadIdx.x, blockDim.x);
 }
 
 }  // namespace urmvo
