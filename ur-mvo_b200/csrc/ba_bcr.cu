@@ -52,10 +52,12 @@ k_bcr_assemble(const BAWin* __restrict__ wins, const LgState* __restrict__ stt, 
   const int n = sh.n, m = sh.m, mb = sh.mb, M = sh.M, bw = M - 1;
   const double lambda = stt->lambda;
   const double* __restrict__ S = W.S;
-  const int k = blockIdx.x >> 1, which = blockIdx.x & 1;
+  const int k = blockIdx.x >> 3, which = (blockIdx.x >> 2) & 1, quarter = blockIdx.x & 3;
+  const int e_begin = quarter * ((mb * mb + 3) / 4), e_end = min(mb * mb, e_begin + (mb * mb + 3) / 4);
   if (which == 0) {
     double* D = work + sh.off_D + (size_t)k * mb * mb;
-    for (int e = threadIdx.x; e < mb * mb; e += blockDim.x) {
+#pragma unroll 4
+    for (int e = e_begin + threadIdx.x; e < e_end; e += blockDim.x) {
       const int r = e / mb, c = e - r * mb;
       double v = 0.0;
       if (r >= c) {
@@ -70,12 +72,14 @@ k_bcr_assemble(const BAWin* __restrict__ wins, const LgState* __restrict__ stt, 
       D[e] = v;
     }
     double* b = work + sh.off_rhs + (size_t)k * mb;
-    for (int e = threadIdx.x; e < mb; e += blockDim.x) b[e] = k * mb + e < n * 6 ? W.bs[k * mb + e] : 0.0;
+    if (quarter == 0)
+      for (int e = threadIdx.x; e < mb; e += blockDim.x) b[e] = k * mb + e < n * 6 ? W.bs[k * mb + e] : 0.0;
     if (blockIdx.x == 0 && threadIdx.x == 0) *reinterpret_cast<int*>(work + sh.off_fail) = 0;
   } else if (k + 1 < sh.K) {
     double* C = work + bcr_pair(sh, 0, k);
     const bool transposed = (k & 1) != 0;  // odd left super-block: it is the eliminated one
-    for (int e = threadIdx.x; e < mb * mb; e += blockDim.x) {
+#pragma unroll 4
+    for (int e = e_begin + threadIdx.x; e < e_end; e += blockDim.x) {
       const int r0 = e / mb, c0 = e - r0 * mb;
       const int r = transposed ? c0 : r0, c = transposed ? r0 : c0;  // (r, c) of E = S[k-th rows, (k+1)-th columns]
       const int ia = k * m + r / 6, ic = (k + 1) * m + c / 6;
@@ -184,26 +188,29 @@ k_bcr_chol(const LgState* __restrict__ stt, BcrShape sh, double* __restrict__ wo
 #pragma unroll
     for (int c = 0; c < 3; c++) a[0][c] = b[tc * 3 + c];
   }
+  // 3 x 3 Cholesky of the diagonal tile.  The three reciprocal square roots are taken of the leading minors
+  // d0, m1 = a11 d0 - a10^2, m2 = det(tile), which do not depend on each other: one rsqrt latency
+  // instead of three (1 / L11 = sqrt(d0) / sqrt(m1), 1 / L22 = sqrt(m1) / sqrt(m2)).
+  auto factor_diag = [&](int p) {
+    const double d0 = a[0][0], a10 = a[1][0], a11 = a[1][1], a20 = a[2][0], a21 = a[2][1], a22 = a[2][2];
+    const double m1 = fma(a11, d0, -a10 * a10);
+    const double c0 = fma(a11, a22, -a21 * a21), c1 = fma(a10, a22, -a21 * a20), c2 = fma(a10, a21, -a11 * a20);
+    const double m2 = fma(d0, c0, fma(-a10, c1, a20 * c2));
+    const bool bad = !(d0 > 0.0) || !(m1 > 0.0) || !(m2 > 0.0);
+    const double q0 = rsqrt(bad ? 1.0 : d0), q1 = rsqrt(bad ? 1.0 : m1), q2 = rsqrt(bad ? 1.0 : m2);
+    const double s0 = d0 * q0, s1 = m1 * q1;  // sqrt(d0), sqrt(m1)
+    const double r0 = q0, r1 = q1 * s0, r2 = q2 * s1;
+    const double l10 = a10 * r0, l20 = a20 * r0;
+    const double l21 = (a21 - l20 * l10) * r1;
+    if (bad) *fail = 1;
+    Lpp[0] = r0; Lpp[1] = l10; Lpp[2] = r1; Lpp[3] = l20; Lpp[4] = l21; Lpp[5] = r2;
+    invd_s[p * 3] = r0; invd_s[p * 3 + 1] = r1; invd_s[p * 3 + 2] = r2;
+    a[0][0] = s0; a[1][0] = l10; a[1][1] = s1 * q0; a[2][0] = l20; a[2][1] = l21; a[2][2] = m2 * q2 * q1;
+    a[0][1] = l10; a[0][2] = l20; a[1][2] = l21;  // mirrored: the tile is written out whole
+  };
+  if (is_mat && ti == 0 && tc == 0) factor_diag(0);
+  __syncthreads();
   for (int p = 0; p < T; p++) {
-    if (is_mat && ti == p && tc == p) {
-      const double d0 = a[0][0];
-      const bool bad0 = !(d0 > 0.0);
-      const double r0 = rsqrt(bad0 ? 1.0 : d0);
-      const double l10 = a[1][0] * r0, l20 = a[2][0] * r0;
-      const double d1 = a[1][1] - l10 * l10;
-      const bool bad1 = !(d1 > 0.0);
-      const double r1 = rsqrt(bad1 ? 1.0 : d1);
-      const double l21 = (a[2][1] - l20 * l10) * r1;
-      const double d2 = a[2][2] - l20 * l20 - l21 * l21;
-      const bool bad2 = !(d2 > 0.0);
-      const double r2 = rsqrt(bad2 ? 1.0 : d2);
-      if (bad0 || bad1 || bad2) *fail = 1;
-      Lpp[0] = r0; Lpp[1] = l10; Lpp[2] = r1; Lpp[3] = l20; Lpp[4] = l21; Lpp[5] = r2;
-      invd_s[p * 3] = r0; invd_s[p * 3 + 1] = r1; invd_s[p * 3 + 2] = r2;
-      a[0][0] = d0 * r0; a[1][0] = l10; a[1][1] = d1 * r1; a[2][0] = l20; a[2][1] = l21; a[2][2] = d2 * r2;
-      a[0][1] = l10; a[0][2] = l20; a[1][2] = l21;  // mirrored: the tile is written out whole
-    }
-    __syncthreads();
     if ((is_mat || is_rhs) && tc == p && ti > p) {
       const double r0 = Lpp[0], l10 = Lpp[1], r1 = Lpp[2], l20 = Lpp[3], l21 = Lpp[4], r2 = Lpp[5];
       double* dst = panel + ti * 9;
@@ -231,7 +238,10 @@ k_bcr_chol(const LgState* __restrict__ stt, BcrShape sh, double* __restrict__ wo
 #pragma unroll
         for (int c = 0; c < 3; c++) a[r][c] -= i0 * lc[c * 3] + i1 * lc[c * 3 + 1] + i2 * lc[c * 3 + 2];
       }
+      // the next diagonal tile is complete: its owner factorises it while the others finish their updates
+      if (is_mat && ti == p + 1 && tc == p + 1) factor_diag(p + 1);
     }
+    __syncthreads();
   }
   // F (mirrored factor), y
   if (is_mat) {
@@ -343,10 +353,14 @@ k_bcr_trsm(const LgState* __restrict__ stt, BcrShape sh, double* __restrict__ wo
 // distinct addresses per warp: broadcast) and rows 3 tx.. of B (16 rows, 3 (mb + 1) doubles apart: conflict-free).
 __device__ __forceinline__ void bcr_fetch_tile(double* dst, const double* __restrict__ src, int row0, int mb) {
   const int ld = mb + 1;
-  for (int e = threadIdx.x; e < kBcrTile * mb; e += blockDim.x) {
-    const int i = e / mb, k = e - i * mb;
-    if (row0 + i < mb) cp_async8(dst + i * ld + k, src + (size_t)(row0 + i) * mb + k);
-    else dst[i * ld + k] = 0.0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warp = blockDim.x >> 5;
+  for (int i = warp; i < kBcrTile; i += n_warp) {
+    const bool in = row0 + i < mb;
+    const double* row = src + (size_t)(row0 + i) * mb;
+    for (int k = lane; k < mb; k += 32) {
+      if (in) cp_async8(dst + i * ld + k, row + k);
+      else dst[i * ld + k] = 0.0;
+    }
   }
 }
 __device__ __forceinline__ void bcr_tile_product(const double* __restrict__ As, const double* __restrict__ Bs, int mb,
@@ -579,7 +593,7 @@ cudaError_t launch_bcr_solve(const BAWin* w, void* stt_v, const BcrShape& sh, do
   LgState* stt = (LgState*)stt_v;
   int nl = 0;
   const int mb = sh.mb, T = (mb + kBcrTile - 1) / kBcrTile;
-  k_bcr_assemble<<<2 * sh.K, kBcrThreads, 0, st>>>(w, stt, sh, work);
+  k_bcr_assemble<<<8 * sh.K, kBcrThreads, 0, st>>>(w, stt, sh, work);
   nl++;
   for (int l = 0; l < sh.L; l++) {
     const int s = 1 << l, n_act = (sh.K + s - 1) / s;
