@@ -282,6 +282,35 @@ int urmvo_fm_plan_finish(urmvo_fm_plan* plan, uint8_t* inlier, urmvo_fm_stats* s
 int urmvo_fm_plan_hypotheses(const urmvo_fm_plan* plan); /* (iteration, problem) pairs evaluated per run */
 void urmvo_fm_plan_destroy(urmvo_fm_plan* plan);
 
+/* ------------------------------------------------------------------ SolvePnPWithCV (B9)
+ * Replaces the OpenCV call of SolvePnPWithCV, reference src/g2o_optimization.cc:353-355:
+ *     cv::solvePnPRansac(object_points, image_points, camera_matrix, dist_coeffs (zero), rvec, tvec,
+ *                        false, 100, 20.0, 0.99, cv_inliers);
+ * run for every tracked frame before FrameOptimization (src/tracking.cc:799).  Same procedure as OpenCV's: 5-point
+ * subsets drawn with cv::RNG(-1), EPnP per subset, float reprojection error <= reproj_thr^2, strictly-more-inliers
+ * wins, RANSACUpdateNumIters(confidence), refinement of the winner over its inliers.  All hypotheses of the budget
+ * are evaluated in parallel and OpenCV's sequential bookkeeping is replayed on the host, so the result does not
+ * depend on the parallel evaluation.
+ *  obj N*3 floats (the reference gathers cv::Point3f, :344-346), img N*2 floats, intr = fx,fy,cx,cy.
+ *  max_iters / reproj_thr / confidence = 100 / 20.0 / 0.99 in the reference (<= 0 selects these).
+ *  inlier: N bytes out (1 = in cv_inliers).  stats->R, t: T_cw (the reference converts (rvec, tvec) to
+ *  T_wc = [R^T, -R^T t], :357-366).  Problems with fewer than 6 points return URMVO_ERR_UNSUPPORTED (the reference
+ *  itself returns 0 below 8 points, :349-350, without calling OpenCV). */
+typedef struct {
+  int32_t found;      /* 1: some minimal sample had more than 4 inliers */
+  int32_t iters;      /* iterations OpenCV's loop runs before its adaptive budget ends */
+  int32_t n_inliers;  /* inliers of the best model = cv_inliers.rows */
+  int32_t n_models;   /* minimal samples among those iterations that produced a model */
+  double R[9];        /* T_cw rotation, row-major, after the refinement over the inliers */
+  double t[3];
+} urmvo_pnp_stats;
+int urmvo_pnp_ransac(urmvo_ctx* ctx, int N, const float* obj, const float* img, const double* intr, int max_iters,
+                     double reproj_thr, double confidence, uint8_t* inlier, urmvo_pnp_stats* stats);
+/* B frames at once: frame b owns points [off[b], off[b+1]) of obj / img / inlier; stats: B entries. */
+int urmvo_pnp_ransac_batch(urmvo_ctx* ctx, int B, const int32_t* off, const float* obj, const float* img,
+                           const double* intr, int max_iters, double reproj_thr, double confidence, uint8_t* inlier,
+                           urmvo_pnp_stats* stats);
+
 /* ---- batched mappoint triangulation ----------------------------------
  * Mapping::TriangulateMappoint (reference src/mapping.cc:151-205) for n_pts mappoints in one launch:
  * multi-view midpoint from the observing keyframes, Eigen::ColPivHouseholderQR rank test (1e-5).

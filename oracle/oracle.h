@@ -156,6 +156,20 @@ int urmvo_oracle_fm_run7(const float* p0, const float* p1, double* F27);
 /* FMEstimatorCallback::computeError: err[i] = (float)max(d1^2 s1, d2^2 s2). */
 void urmvo_oracle_fm_errors(int N, const float* p0, const float* p1, const double* F, float* err);
 
+/* ---- SolvePnPWithCV (reference src/g2o_optimization.cc:323-377): cv::solvePnPRansac(..., false, 100, 20.0, 0.99),
+ * pnp_oracle.cpp.  PARITY PARTLY PINNED (statistically against cv2.solvePnPRansac, see the file header).
+ * obj N*3 floats, img N*2 floats, K4 = fx fy cx cy.  R9 / t3: T_cw after the final refinement over the inliers,
+ * mask: N bytes (inliers of the best RANSAC model), stats4 = {iterations run, inliers, models scored, 0},
+ * counts (may be NULL): inlier count of every iteration run (-1: no model).  Returns 1 found, 0 none, -1 N < 6. */
+int urmvo_oracle_pnp_ransac(int N, const float* obj, const float* img, const double* K4, int max_iters,
+                            double reproj_thr, double confidence, double* R9, double* t3, uint8_t* mask,
+                            int32_t* stats4, int32_t* counts);
+/* The 5-index subsets of iterations 0..max_iters-1 (cv::RNG state -1, no checkSubset).  idx: max_iters*5. */
+int urmvo_oracle_pnp_subsets(int N, int max_iters, int32_t* idx);
+/* EPnP on the 5 correspondences idx5 (the RANSAC kernel): T_cw.  Returns 1 on success. */
+int urmvo_oracle_pnp_epnp5(const float* obj, const float* img, const double* K4, const int32_t* idx5, double* R9,
+                           double* t3);
+
 /* ---- Mapping::TriangulateMappoint (reference src/mapping.cc:151-205), tri_oracle.cpp.  PARITY UNPINNED.
  * n_obs observers of one mappoint: Rp = (R row-major | p) of the keyframe pose T_wc (12 doubles each),
  * uv = keypoint position.  Returns 1 and writes X (3) on success, 0 for < 2 observers or rank < 3. */

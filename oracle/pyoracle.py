@@ -275,3 +275,33 @@ def triangulate(Rp, uv, intr):
     lib().urmvo_oracle_triangulate.restype = C.c_int
     ok = lib().urmvo_oracle_triangulate(C.c_int(len(uv)), _p(Rp), _p(uv), _p(intr), _p(X))
     return bool(ok), X
+
+
+# ---- SolvePnPWithCV (cv::solvePnPRansac restatement, pnp_oracle.cpp)
+
+def pnp_ransac(obj, img, K4, max_iters=100, reproj=20.0, confidence=0.99):
+    """Returns dict(found, R[3,3], t[3] (T_cw after the refinement over the inliers), mask[N] u8, iters, n_inliers,
+    models, counts[iters])."""
+    obj = np.ascontiguousarray(obj, dtype=np.float32); img = np.ascontiguousarray(img, dtype=np.float32)
+    K4 = np.ascontiguousarray(K4, dtype=np.float64)
+    N = len(obj)
+    R = np.zeros(9); t = np.zeros(3); mask = np.zeros(N, dtype=np.uint8); st = np.zeros(4, dtype=np.int32)
+    counts = np.zeros(max(max_iters, 1), dtype=np.int32)
+    rc = lib().urmvo_oracle_pnp_ransac(C.c_int(N), _p(obj), _p(img), _p(K4), C.c_int(max_iters), C.c_double(reproj),
+                                       C.c_double(confidence), _p(R), _p(t), _p(mask), _p(st), _p(counts))
+    return dict(found=rc, R=R.reshape(3, 3), t=t, mask=mask, iters=int(st[0]), n_inliers=int(st[1]), models=int(st[2]),
+                counts=counts[:int(st[0])])
+
+
+def pnp_subsets(N, max_iters=100):
+    idx = np.zeros((max_iters, 5), dtype=np.int32)
+    lib().urmvo_oracle_pnp_subsets(C.c_int(N), C.c_int(max_iters), _p(idx))
+    return idx
+
+
+def pnp_epnp5(obj, img, K4, idx5):
+    obj = np.ascontiguousarray(obj, dtype=np.float32); img = np.ascontiguousarray(img, dtype=np.float32)
+    K4 = np.ascontiguousarray(K4, dtype=np.float64); idx5 = np.ascontiguousarray(idx5, dtype=np.int32)
+    R = np.zeros(9); t = np.zeros(3)
+    ok = lib().urmvo_oracle_pnp_epnp5(_p(obj), _p(img), _p(K4), _p(idx5), _p(R), _p(t))
+    return ok, R.reshape(3, 3), t

@@ -120,4 +120,14 @@ cudaError_t launch_fm_score(int n_hyp, const int* hyp_ids, int max_iters, const 
 cudaError_t launch_fm_mask(int B, int max_n, const int* off, const float4* pts, const double* models_all,
                            const int* win_id, float thr2, uint8_t* mask, double* win_F, cudaStream_t s);
 
+// ---- pnp_kernels.cu (SolvePnPWithCV: EPnP RANSAC hypotheses, inlier counting, refinement over the inliers).
+// H = B * max_iters hypotheses; sets [H][5] indices local to the problem; models [H][12] = R | t (T_cw);
+// masks [H][words_max]; counts[h] = inliers or -1 (no model).
+cudaError_t launch_pnp_hypotheses(int H, int max_iters, int words_max, const int* off, const int* sets, const float* obj,
+                                  const float* img, const double* K4, double* models, int* valid, float thr2,
+                                  unsigned* masks, int* counts, cudaStream_t s);
+cudaError_t launch_pnp_refine(int B, int max_iters, int words_max, const int* off, const float* obj, const float* img,
+                              const double* K4, const double* models, const unsigned* masks, const int* best,
+                              double* out_Rt, uint8_t* inlier, cudaStream_t s);
+
 }  // namespace urmvo

@@ -17,6 +17,7 @@ EXPORTED_SYMBOLS = [
     "urmvo_tv_plan_reconstruct", "urmvo_tv_plan_destroy",
     "urmvo_fm_ransac", "urmvo_fm_ransac_batch", "urmvo_fm_plan_create", "urmvo_fm_plan_run", "urmvo_fm_plan_finish",
     "urmvo_fm_plan_hypotheses", "urmvo_fm_plan_destroy", "urmvo_triangulate_batch",
+    "urmvo_pnp_ransac", "urmvo_pnp_ransac_batch",
 ]
 
 
@@ -27,6 +28,11 @@ class UrmvoError(RuntimeError):
 class FMStats(C.Structure):
     _fields_ = [("found", C.c_int32), ("iters", C.c_int32), ("n_inliers", C.c_int32), ("n_models", C.c_int32),
                 ("F", C.c_double * 9)]
+
+
+class PnPStats(C.Structure):
+    _fields_ = [("found", C.c_int32), ("iters", C.c_int32), ("n_inliers", C.c_int32), ("n_models", C.c_int32),
+                ("R", C.c_double * 9), ("t", C.c_double * 3)]
 
 
 class BAOptions(C.Structure):
@@ -153,6 +159,25 @@ class Context:
     @property
     def launches(self):
         return int(self._L.urmvo_launch_count(self._h))
+
+    # ---- SolvePnPWithCV (cv::solvePnPRansac)
+    def pnp_ransac_batch(self, problems, intr, max_iters=100, reproj=20.0, confidence=0.99):
+        """problems: list of (obj[N,3] f32, img[N,2] f32).  Returns a list of dict(found, R, t, mask, iters, n_inliers, models)."""
+        off = np.zeros(len(problems) + 1, dtype=np.int32)
+        off[1:] = np.cumsum([len(o) for o, _ in problems])
+        obj = _f32(np.concatenate([np.asarray(o, dtype=np.float32).reshape(-1, 3) for o, _ in problems]))
+        img = _f32(np.concatenate([np.asarray(i, dtype=np.float32).reshape(-1, 2) for _, i in problems]))
+        K4 = _f64(intr)
+        inl = np.zeros(int(off[-1]), dtype=np.uint8)
+        st = (PnPStats * len(problems))()
+        _check(self._L.urmvo_pnp_ransac_batch(self._h, C.c_int(len(problems)), _p(off), _p(obj), _p(img), _p(K4),
+                                              C.c_int(max_iters), C.c_double(reproj), C.c_double(confidence), _p(inl), st),
+               "urmvo_pnp_ransac_batch")
+        return [dict(found=int(s.found), R=np.array(s.R).reshape(3, 3), t=np.array(s.t), mask=inl[off[b]:off[b + 1]].copy(),
+                     iters=int(s.iters), n_inliers=int(s.n_inliers), models=int(s.n_models)) for b, s in enumerate(st)]
+
+    def pnp_ransac(self, obj, img, intr, max_iters=100, reproj=20.0, confidence=0.99):
+        return self.pnp_ransac_batch([(obj, img)], intr, max_iters, reproj, confidence)[0]
 
     # ---- one-shot, host buffers in / out (the reference-facing calls)
     def local_ba(self, prob, chi2_thr=10.0, it0=10, it1=5, opts=None):

@@ -313,3 +313,24 @@ def make_triangulation(seed=1007, n_pts=500, n_poses=12, max_obs=10, px_sigma=0.
     return dict(obs_off=np.array(off, dtype=np.int32), obs_pose=np.array(idx, dtype=np.int32),
                 obs_uv=np.array(uv, dtype=np.float64).reshape(-1, 2), poses_Rp=poses_Rp,
                 intr=np.array([FX, FY, CX, CY]), gt=X)
+
+
+def make_pnp(seed=1008, n=300, outlier_frac=0.2, px_sigma=0.7, rot_deg=10.0, trans=0.5):
+    """2D-3D matches of one tracked frame for SolvePnPWithCV (reference src/g2o_optimization.cc:323-377):
+    obj (n, 3) float32 mappoint positions, img (n, 2) float32 keypoints, intr = fx fy cx cy, and the true T_cw
+    (R, t).  Outliers are keypoints at random pixel positions."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    u = rng.uniform(BORDER + 2, W_IMG - BORDER - 2, size=n)
+    v = rng.uniform(BORDER + 2, H_IMG - BORDER - 2, size=n)
+    d = rng.uniform(2.0, 8.0, size=n)
+    pc = np.stack([(u - CX) / FX * d, (v - CY) / FY * d, d], axis=-1)
+    rv = np.deg2rad(rot_deg) * rng.standard_normal(3) / np.sqrt(3.0)
+    R = quat_to_R(rotvec_to_quat(rv[None, :]))[0]  # T_cw rotation
+    t = trans * rng.standard_normal(3)
+    X = (pc - t) @ R  # X_w = R^T (X_c - t)
+    uv = np.stack([u, v], axis=-1) + px_sigma * rng.standard_normal((n, 2))
+    is_out = rng.uniform(size=n) < outlier_frac
+    uv[is_out] = np.stack([rng.uniform(BORDER, W_IMG - BORDER, size=int(is_out.sum())),
+                           rng.uniform(BORDER, H_IMG - BORDER, size=int(is_out.sum()))], axis=-1)
+    return dict(obj=X.astype(np.float32), img=uv.astype(np.float32), intr=np.array([FX, FY, CX, CY]), R=R, t=t,
+                is_outlier=is_out)
