@@ -614,6 +614,39 @@ def side_measurements(ctx, stream, torch):
         fm["opencv"] = f"unavailable: {type(e).__name__}"
     extra["fm_ransac_per_frame"] = fm
     fplan.close()
+    # SolvePnPWithCV: cv::solvePnPRansac(100 iterations, 20 px, 0.99) per tracked frame;
+    # host-buffer calls (H2D / D2H inside), cv2 and the CPU restatement beside them
+    frames = [synth.make_pnp(1008 + 31 * b, 1000, 0.2) for b in range(64)]
+    pr = [(f["obj"], f["img"]) for f in frames]
+    ctx.pnp_ransac_batch(pr, frames[0]["intr"]); ctx.pnp_ransac(*pr[0], frames[0]["intr"])
+    t0 = time.perf_counter(); gb = ctx.pnp_ransac_batch(pr, frames[0]["intr"]); t_b = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    for o_, i_ in pr[:16]:
+        ctx.pnp_ransac(o_, i_, frames[0]["intr"])
+    t_1 = (time.perf_counter() - t0) / 16
+    t0 = time.perf_counter()
+    ob = [po.pnp_ransac(o_, i_, frames[0]["intr"]) for o_, i_ in pr[:16]]
+    t_o = (time.perf_counter() - t0) / 16
+    pnp = {"frames": 64, "points": 1000, "e2e_batch_call_frames_per_s": 64 / t_b, "e2e_single_call_ms": t_1 * 1e3,
+           "cpu_port_ms_per_frame": t_o * 1e3, "cpu_sample": "16 frames, 1 thread",
+           "masks_equal_cpu_port": bool(all(np.array_equal(a["mask"], b["mask"]) for a, b in zip(gb[:16], ob))),
+           "pose_maxdiff_cpu_port": float(max(max(np.abs(a["R"] - b["R"]).max(), np.abs(a["t"] - b["t"]).max()) for a, b in zip(gb[:16], ob)))}
+    try:
+        import cv2
+        Kc = np.array([[frames[0]["intr"][0], 0, frames[0]["intr"][2]], [0, frames[0]["intr"][1], frames[0]["intr"][3]], [0, 0, 1.0]])
+        t0 = time.perf_counter()
+        cv = [cv2.solvePnPRansac(o_, i_, Kc, np.zeros(5), iterationsCount=100, reprojectionError=20.0, confidence=0.99) for o_, i_ in pr[:16]]
+        pnp["opencv_ms_per_frame"] = (time.perf_counter() - t0) / 16 * 1e3
+        pnp["opencv_version"] = cv2.__version__
+        same = 0
+        for g_, (ok, rv, tv, inl) in zip(gb[:16], cv):
+            m = np.zeros(1000, dtype=np.uint8)
+            m[inl.ravel()] = 1
+            same += int(np.array_equal(m, g_["mask"]))
+        pnp["inlier_sets_equal_opencv"] = f"{same}/16"
+    except Exception as e:  # cv2 is test infrastructure here, never required
+        pnp["opencv"] = f"unavailable: {type(e).__name__}"
+    extra["pnp_ransac_per_frame"] = pnp
     # batched mappoint triangulation: host-buffer call vs the CPU restatement
     tri = synth.make_triangulation(1007, n_pts=5000, n_poses=35)
     ctx.triangulate_batch(tri["obs_off"], tri["obs_pose"], tri["obs_uv"], tri["poses_Rp"], tri["intr"])

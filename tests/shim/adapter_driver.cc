@@ -100,6 +100,25 @@ int main(int argc, char** argv) {
     for (bool t : tri) tv.push_back(t);
     if (!ok) { P.assign((size_t)n1 * 3, 0.f); tv.assign(n1, 0); }
     wr(out, okv); wr(out, T); wr(out, P); wr(out, tv);
+  } else if (mode == "pnp") {
+    // n slots of the frame: valid[i] = 0 -> nullptr mappoint, 2 -> invalid mappoint, 1 -> usable
+    auto hdr = rd<int>(in, 1); int n = hdr[0];
+    auto intr = rd<double>(in, 4); auto X = rd<double>(in, (size_t)n * 3); auto uv = rd<double>(in, (size_t)n * 2); auto valid = rd<unsigned char>(in, n);
+    CameraPtr cam(new Camera(intr[0], intr[1], intr[2], intr[3]));
+    std::vector<Eigen::Vector2d> kps(n);
+    std::vector<MappointPtr> mps(n);
+    for (int i = 0; i < n; i++) {
+      kps[i](0) = uv[i*2]; kps[i](1) = uv[i*2+1];
+      Eigen::Vector3d p; for (int k = 0; k < 3; k++) p(k) = X[i*3+k];
+      if (valid[i]) mps[i] = std::make_shared<Mappoint>(5000 + 3 * i, p, valid[i] == 1);
+    }
+    FramePtr frame(new Frame(cam, kps));
+    Eigen::Matrix4d Twc; for (int i = 0; i < 4; i++) Twc(i, i) = 1.0;
+    std::vector<int> inl;
+    const int cnt = SolvePnPWithCV(frame, mps, Twc, inl);
+    inl.resize(n, -1);
+    std::vector<int> c = {cnt, urmvo_adapter_last_status()}; std::vector<double> T(Twc.d, Twc.d + 16);
+    wr(out, c); wr(out, T); wr(out, inl);
   } else if (mode == "fm") {
     auto hdr = rd<int>(in, 1); int n = hdr[0];
     auto a = rd<float>(in, (size_t)n * 2); auto b = rd<float>(in, (size_t)n * 2);

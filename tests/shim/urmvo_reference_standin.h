@@ -69,11 +69,43 @@ class Camera {
 };
 using CameraPtr = std::shared_ptr<Camera>;
 
-// ---- g2o_optimization.h: the two entry points the adapter defines
+// ---- what g2o_optimization.h pulls in from frame.h / mappoint.h (only what SolvePnPWithCV reads:
+// include/frame.h:57,83, include/mappoint.h:27,33,36)
+class Mappoint {
+ public:
+  Mappoint(int id, const Eigen::Vector3d& p, bool valid = true) : id_(id), p_(p), valid_(valid) {}
+  int GetId() { return id_; }
+  bool IsValid() { return valid_; }
+  Eigen::Vector3d& GetPosition() { return p_; }
+
+ private:
+  int id_;
+  Eigen::Vector3d p_;
+  bool valid_;
+};
+using MappointPtr = std::shared_ptr<Mappoint>;
+class Frame {
+ public:
+  Frame(CameraPtr camera, std::vector<Eigen::Vector2d> keypoints) : camera_(camera), kps_(std::move(keypoints)) {}
+  CameraPtr GetCamera() { return camera_; }
+  bool GetKeypointPosition(size_t idx, Eigen::Vector2d& keypoint_pos) {
+    if (idx >= kps_.size()) return false;
+    keypoint_pos = kps_[idx];
+    return true;
+  }
+
+ private:
+  CameraPtr camera_;
+  std::vector<Eigen::Vector2d> kps_;
+};
+using FramePtr = std::shared_ptr<Frame>;
+
+// ---- g2o_optimization.h: the entry points the adapter defines
 void LocalmapOptimization(MapOfPoses&, MapOfPoints3d&, std::vector<CameraPtr>&, VectorOfMonoPointConstraints&,
                           VectorOfStereoPointConstraints&, const OptimizationConfig&);
 int FrameOptimization(MapOfPoses&, MapOfPoints3d&, std::vector<CameraPtr>&, VectorOfMonoPointConstraints&,
                       VectorOfStereoPointConstraints&, const OptimizationConfig&);
+int SolvePnPWithCV(FramePtr frame, std::vector<MappointPtr>& mappoints, Eigen::Matrix4d& pose, std::vector<int>& inliers);
 
 // ---- epipolar_geometry.h: public interface + the members the constructor initialises
 class EpipolarGeometry {

@@ -32,7 +32,7 @@ def test_adapters_compile_and_link_against_the_c_abi():
     build_driver()
     assert os.path.exists(DRIVER)
     syms = subprocess.run(["nm", "-C", DRIVER], capture_output=True, text=True).stdout
-    for s in ("LocalmapOptimization(", "FrameOptimization(", "EpipolarGeometry::reconstruct(", "EpipolarGeometry::Random::RandomInt(",
+    for s in ("LocalmapOptimization(", "FrameOptimization(", "SolvePnPWithCV(", "EpipolarGeometry::reconstruct(", "EpipolarGeometry::Random::RandomInt(",
               "FindFundamentalInliersGPU("):
         assert s in syms, s
 
@@ -140,3 +140,35 @@ def test_point_matching_outlier_rejection_through_the_adapter():
     p0, p1 = synth.make_fm(3500, 14, 0.9)
     out = _run("fm", struct.pack("i", 14) + p0.tobytes() + p1.tobytes())
     assert struct.unpack("i", out[:4])[0] == 0 and set(out[4:]) == {7}  # untouched
+
+
+@pytest.mark.gpu
+def test_solve_pnp_with_cv_through_the_adapter(oracle):
+    """SolvePnPWithCV (reference src/g2o_optimization.cc:323-377): null / invalid mappoints are skipped, the pose
+    comes back as T_wc, inliers carry mappoint ids at the FRAME's slot indices."""
+    p = synth.make_pnp(4400, 400, 0.25)
+    n = 400
+    valid = np.ones(n, dtype=np.uint8)
+    valid[::17] = 0   # no mappoint in this slot
+    valid[5::23] = 2  # mappoint exists but is invalid
+    buf = struct.pack("i", n) + p["intr"].tobytes() + p["obj"].astype(np.float64).tobytes() + p["img"].astype(np.float64).tobytes() + valid.tobytes()
+    out = _run("pnp", buf)
+    cnt, status = struct.unpack("2i", out[:8])
+    Twc = np.frombuffer(out[8:8 + 128], dtype=np.float64).reshape(4, 4)
+    inl = np.frombuffer(out[8 + 128:], dtype=np.int32)
+    use = valid == 1
+    o = oracle.pnp_ransac(p["obj"][use], p["img"][use], p["intr"])
+    assert status == 0 and cnt == o["n_inliers"]
+    want = np.full(n, -1, dtype=np.int32)
+    want[np.flatnonzero(use)[o["mask"] == 1]] = 5000 + 3 * np.flatnonzero(use)[o["mask"] == 1]
+    assert np.array_equal(inl, want)
+    Rwc, twc = o["R"].T, -o["R"].T @ o["t"]
+    assert np.abs(Twc[:3, :3] - Rwc).max() < 1e-9 and np.abs(Twc[:3, 3] - twc).max() < 1e-9 and np.array_equal(Twc[3], [0, 0, 0, 1])
+
+
+@pytest.mark.gpu
+def test_solve_pnp_with_cv_needs_eight_points():
+    p = synth.make_pnp(4401, 7, 0.0)
+    buf = struct.pack("i", 7) + p["intr"].tobytes() + p["obj"].astype(np.float64).tobytes() + p["img"].astype(np.float64).tobytes() + np.ones(7, dtype=np.uint8).tobytes()
+    out = _run("pnp", buf)
+    assert struct.unpack("2i", out[:8]) == (0, 0)  # reference :349-350: fewer than 8 correspondences -> 0

@@ -1,5 +1,5 @@
 // adapter/g2o_optimization.cc — drop-in replacement for the reference's src/g2o_optimization.cc
-// (LocalmapOptimization :20-177, FrameOptimization :179-321, SolvePnPWithCV's pose refinement input).
+// (LocalmapOptimization :20-177, FrameOptimization :179-321, SolvePnPWithCV :323-377).
 // Same signatures, same in-place result convention, so src/mapping.cc:471 and src/tracking.cc:883 call
 // it unchanged.  It only flattens the reference's containers into the SoA arrays of
 // include/urmvo_b200.h; all arithmetic runs in the sm_100a kernels.
@@ -241,4 +241,58 @@ int FrameOptimization(MapOfPoses& poses, MapOfPoints3d& points, std::vector<Came
   get_pose(P, pose_it->second);
   // :319-320 returns #mono + #stereo - #outliers (stereo constraints of a MONO camera are never edges)
   return n_inlier + (total - No);
+}
+
+
+// SolvePnPWithCV (reference src/g2o_optimization.cc:323-377): same gather (valid mappoints with a keypoint, float
+// positions), same "< 8 correspondences -> 0" guard, the OpenCV call replaced by urmvo_pnp_ransac, the same
+// conversion of T_cw to pose = T_wc and of the inlier list to mappoint ids.  A GPU failure returns 0 (the
+// reference's `catch (...) return 0`) and is recorded in urmvo_adapter_last_status().
+int SolvePnPWithCV(FramePtr frame, std::vector<MappointPtr>& mappoints, Eigen::Matrix4d& pose, std::vector<int>& inliers) {
+  g_last_status = URMVO_OK;
+  std::vector<float> object_points, image_points;
+  std::vector<int> point_indexes;
+  CameraPtr camera = frame->GetCamera();
+  for (size_t i = 0; i < mappoints.size(); i++) {
+    MappointPtr mpt = mappoints[i];
+    if (mpt == nullptr || !mpt->IsValid()) continue;
+    Eigen::Vector2d keypoint;
+    if (!frame->GetKeypointPosition(i, keypoint)) continue;
+    const Eigen::Vector3d& point_position = mpt->GetPosition();
+    for (int k = 0; k < 3; k++) object_points.push_back((float)point_position(k));
+    image_points.push_back((float)keypoint(0));
+    image_points.push_back((float)keypoint(1));
+    point_indexes.push_back((int)i);
+  }
+  const int n = (int)point_indexes.size();
+  if (n < 8) return 0;
+  urmvo_ctx* ctx = ba_context();
+  if (!ctx) { fail_status(URMVO_ERR_NO_DEVICE, "SolvePnPWithCV"); return 0; }
+  const double intr[4] = {camera->Fx(), camera->Fy(), camera->Cx(), camera->Cy()};
+  std::vector<uint8_t> flags(n);
+  urmvo_pnp_stats st;
+  int rc;
+  {
+    std::lock_guard<std::mutex> lock(g_ba_mutex);
+    rc = urmvo_pnp_ransac(ctx, n, object_points.data(), image_points.data(), intr, 100, 20.0, 0.99, flags.data(), &st);
+  }
+  if (rc != URMVO_OK) { fail_status(rc, "SolvePnPWithCV"); return 0; }
+  // pose = [R_wc | -R_wc t_cw] (:357-366); the other entries of `pose` are the caller's (identity in tracking.cc:797)
+  for (int r = 0; r < 3; r++) {
+    double tw = 0;
+    for (int c = 0; c < 3; c++) {
+      pose(r, c) = st.R[c * 3 + r];
+      tw -= st.R[c * 3 + r] * st.t[c];
+    }
+    pose(r, 3) = tw;
+  }
+  inliers = std::vector<int>(mappoints.size(), -1);
+  int n_in = 0;
+  for (int i = 0; i < n; i++)
+    if (flags[i]) {
+      const int point_idx = point_indexes[i];
+      inliers[point_idx] = mappoints[point_idx]->GetId();
+      n_in++;
+    }
+  return st.found ? n_in : 0;
 }
