@@ -534,8 +534,15 @@ def side_measurements(ctx, stream, torch):
     dt = timed(plan.run_ransac, 5)
     sub = dict(tv); sub["sets"] = tv["sets"][:256]
     t0 = time.perf_counter(); po.score_all(sub, 0); po.score_all(sub, 1); tc = time.perf_counter() - t0
+    # cfg2 / cfg3 are not HBM-bound; achieved FLOP/s against the non-tensor peaks (148 SMs x 128 FFMA or
+    # 64 DFMA per clock x 2 x 1.965 GHz).  Algorithmic flop: (54 + 2 divisions at 8) per match and F hypothesis,
+    # 60 per match and H hypothesis; the fits are a few per cent on top and not counted.
+    FP32_PEAK, FP64_PEAK = 148 * 128 * 2 * 1.965e9 / 1e12, 148 * 64 * 2 * 1.965e9 / 1e12
+    gflop3 = 8192 * 1000 * (54 + 16 + 60) / 1e9
     extra["ransac_cfg3"] = {"hyps_per_s": 2 * 8192 / dt, "ms": dt * 1e3, "hyps": 2 * 8192, "matches": 1000,
-                            "cpu_hyps_per_s": 512 / tc, "cpu_sample": "256 F + 256 H hypotheses, 1 thread"}
+                            "cpu_hyps_per_s": 512 / tc, "cpu_sample": "256 F + 256 H hypotheses, 1 thread",
+                            "roofline": {"bound": "fp32 (non-tensor)", "achieved": gflop3 / dt / 1e3, "peak": FP32_PEAK, "unit": "TFLOP/s",
+                                         "frac": gflop3 / dt / 1e3 / FP32_PEAK, "algorithmic_gflop": gflop3}}
     plan.close()
     # cfg2: 256 frames x 1000 matches, 4 x 10 iterations
     pb = synth.cfg2()
@@ -545,8 +552,12 @@ def side_measurements(ctx, stream, torch):
     small = {k: (v[:16 * 1000] if k in ("uv", "Xw") else v) for k, v in pb.items()}
     small["poses"] = pb["poses"][:16]; small["obs_offset"] = pb["obs_offset"][:17]
     t0 = time.perf_counter(); po.pose_only_batch(small); tc = time.perf_counter() - t0
+    gflop2 = its * 1000 * 165 / 1e9  # per LM iteration and match: residual + 2x6 Jacobian + 28 sums (~125) + trial cost (~40)
     extra["pose_only_cfg2"] = {"lm_iters_per_s": its / dt, "ms": dt * 1e3, "frames": 256,
-                               "cpu_lm_iters_per_s": (its * 16.0 / 256.0) / tc, "cpu_sample": "16 frames, 1 thread"}
+                               "cpu_lm_iters_per_s": (its * 16.0 / 256.0) / tc, "cpu_sample": "16 frames, 1 thread",
+                               "roofline": {"bound": "fp64 (non-tensor)", "achieved": gflop2 / dt / 1e3, "peak": FP64_PEAK, "unit": "TFLOP/s",
+                                            "frac": gflop2 / dt / 1e3 / FP64_PEAK, "algorithmic_gflop": gflop2,
+                                            "note": "one CTA per frame, L1/L2-resident after the first pass: bound by the serial LM chain per frame, not by throughput"}}
     pplan.close()
     # cfg4: one large window (50 keyframes, 50k points, ~400k observations) on the cooperative grid kernel
     from urmvo_b200.capi import pack_ba_batch

@@ -105,6 +105,55 @@ void jacobi_eig(int n, double* A, double* V) {
   }
 }
 
+// The 12 x 12 problem uses the PARALLEL (round-robin) ordering: a sweep is 11 rounds of 6 disjoint pairs
+// (pair 0 of round r is (r, 11); pair k = 1..5 is ((r + k) mod 11, (r - k) mod 11), smaller index first).  The six
+// rotations of a round are computed from the matrix as it stands at the start of the round, then applied:
+// first to the columns (and to V), then to the rows.  A pair with a_pq == 0 gets the identity.  Same stopping
+// rule as above.  (The CUDA path computes the six rotations of a round on six lanes at once.)
+void jacobi_eig12_rr(double* A, double* V) {
+  const int n = 12;
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < n; j++) V[i * n + j] = i == j ? 1.0 : 0.0;
+  double fro = 0;
+  for (int i = 0; i < n * n; i++) fro += A[i] * A[i];
+  for (int sweep = 0; sweep < 60; sweep++) {
+    double off = 0;
+    for (int p = 0; p < n; p++)
+      for (int q = p + 1; q < n; q++) off += A[p * n + q] * A[p * n + q];
+    if (off <= 1e-32 * fro) break;
+    for (int r = 0; r < 11; r++) {
+      int P[6], Q[6];
+      double C[6], S[6];
+      for (int k = 0; k < 6; k++) {
+        const int a = k == 0 ? r : (r + k) % 11, b = k == 0 ? 11 : (r - k + 11) % 11;
+        P[k] = std::min(a, b);
+        Q[k] = std::max(a, b);
+        const double apq = A[P[k] * n + Q[k]];
+        if (apq == 0.0) { C[k] = 1.0; S[k] = 0.0; continue; }
+        const double theta = (A[Q[k] * n + Q[k]] - A[P[k] * n + P[k]]) / (2.0 * apq);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+        C[k] = 1.0 / std::sqrt(t * t + 1.0);
+        S[k] = t * C[k];
+      }
+      for (int k = 0; k < 6; k++)
+        for (int i = 0; i < n; i++) {
+          const double akp = A[i * n + P[k]], akq = A[i * n + Q[k]];
+          A[i * n + P[k]] = C[k] * akp - S[k] * akq;
+          A[i * n + Q[k]] = S[k] * akp + C[k] * akq;
+          const double vkp = V[i * n + P[k]], vkq = V[i * n + Q[k]];
+          V[i * n + P[k]] = C[k] * vkp - S[k] * vkq;
+          V[i * n + Q[k]] = S[k] * vkp + C[k] * vkq;
+        }
+      for (int k = 0; k < 6; k++)
+        for (int i = 0; i < n; i++) {
+          const double apk = A[P[k] * n + i], aqk = A[Q[k] * n + i];
+          A[P[k] * n + i] = C[k] * apk - S[k] * aqk;
+          A[Q[k] * n + i] = S[k] * apk + C[k] * aqk;
+        }
+    }
+  }
+}
+
 // indices of the diagonal of A sorted by value (stable insertion sort), ascending or descending
 void sort_diag(int n, const double* A, int* order, bool descending) {
   for (int i = 0; i < n; i++) order[i] = i;
@@ -218,7 +267,7 @@ struct Epnp {
         for (int r = 0; r < 10; r++) s += M[r][a] * M[r][b];
         MtM[a * 12 + b] = s;
       }
-    jacobi_eig(12, MtM, VV);
+    jacobi_eig12_rr(MtM, VV);
     int ord12[12];
     sort_diag(12, MtM, ord12, false);
     for (int i = 0; i < 4; i++)

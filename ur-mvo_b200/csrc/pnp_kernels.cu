@@ -8,10 +8,11 @@
 // then solvePnP(ITERATIVE) refines over the inliers of the best model.
 //
 // Here all (<= 100) hypotheses of a frame — and of every frame of a batch — are evaluated at once:
-//   pnp_epnp_kernel    one THREAD per hypothesis: EPnP on 5 correspondences.  The hypothesis is a chain of tiny
+//   pnp_epnp_kernel    one WARP per hypothesis: EPnP on 5 correspondences.  The hypothesis is a chain of tiny
 //                      dense factorisations (3x3 and 12x12 symmetric eigen-problems by cyclic Jacobi, 6x{3,4,5}
 //                      Householder least squares, 5 Gauss-Newton steps x 3 initialisations, a 3x3 absolute
-//                      orientation): there is nothing to tile, the unit of parallelism is the hypothesis;
+//                      orientation).  The 12x12 eigen-problem is 9/10 of the work: the lanes of the warp share
+//                      it in shared memory (lane k = entry k of the rotated rows / columns), lane 0 runs the rest;
 //   pnp_score_kernel   one WARP per hypothesis: lanes stride over the points, ballot -> inlier-mask words and
 //                      the count (HBM traffic: 20 B per point per hypothesis from L2);
 //   (host)             OpenCV's "strictly more inliers wins" / RANSACUpdateNumIters replay over the counts;
@@ -69,6 +70,67 @@ __device__ void jacobi_eig(double* A, double* V) {
   }
 }
 
+// The 12 x 12 matrix of a hypothesis is diagonalised by the 32 lanes of its warp in shared memory with the PARALLEL
+// (round-robin) Jacobi ordering: a sweep is 11 rounds of 6 disjoint pairs (pair 0 of round r is (r, 11); pair
+// k = 1..5 is ((r + k) mod 11, (r - k) mod 11)).  Lanes 0..5 compute the six rotations of a round at once — the two
+// square roots and three divisions of a rotation are a ~1000-cycle dependency chain, paid 11 times per sweep instead
+// of 66 —, then all lanes apply them: first to the columns of A and V, then to the rows of A.  The order of the
+// element operations is that of the CPU restatement (oracle/pnp_oracle.cpp jacobi_eig12_rr).
+__device__ void jacobi_eig12_warp(double* A, double* V, double* cs /* [12] */, int lane) {
+  constexpr int n = 12;
+  for (int e = lane; e < n * n; e += 32) V[e] = (e / n == e % n) ? 1.0 : 0.0;
+  __syncwarp();
+  double fro = 0;
+  for (int i = 0; i < n * n; i++) fro += A[i] * A[i];
+  for (int sweep = 0; sweep < 60; sweep++) {
+    double off = 0;
+    for (int p = 0; p < n; p++)
+      for (int q = p + 1; q < n; q++) off += A[p * n + q] * A[p * n + q];
+    if (off <= 1e-32 * fro) break;
+    for (int r = 0; r < 11; r++) {
+      if (lane < 6) {
+        const int k = lane;
+        const int a = k == 0 ? r : (r + k) % 11, b = k == 0 ? 11 : (r - k + 11) % 11;
+        const int p = a < b ? a : b, q = a < b ? b : a;
+        const double apq = A[p * n + q];
+        double c = 1.0, s = 0.0;
+        if (apq != 0.0) {
+          const double theta = (A[q * n + q] - A[p * n + p]) / (2.0 * apq);
+          const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+          c = 1.0 / sqrt(t * t + 1.0);
+          s = t * c;
+        }
+        cs[2 * k] = c;
+        cs[2 * k + 1] = s;
+      }
+      __syncwarp();
+      for (int item = lane; item < 144; item += 32) {  // columns of A (items 0..71) and of V (72..143)
+        const bool isV = item >= 72;
+        const int it2 = isV ? item - 72 : item;
+        const int k = it2 / 12, i = it2 - k * 12;
+        const int a = k == 0 ? r : (r + k) % 11, b = k == 0 ? 11 : (r - k + 11) % 11;
+        const int p = a < b ? a : b, q = a < b ? b : a;
+        const double c = cs[2 * k], s = cs[2 * k + 1];
+        double* Mx = isV ? V : A;
+        const double xp = Mx[i * n + p], xq = Mx[i * n + q];
+        Mx[i * n + p] = c * xp - s * xq;
+        Mx[i * n + q] = s * xp + c * xq;
+      }
+      __syncwarp();
+      for (int item = lane; item < 72; item += 32) {  // rows of A
+        const int k = item / 12, i = item - k * 12;
+        const int a = k == 0 ? r : (r + k) % 11, b = k == 0 ? 11 : (r - k + 11) % 11;
+        const int p = a < b ? a : b, q = a < b ? b : a;
+        const double c = cs[2 * k], s = cs[2 * k + 1];
+        const double apk = A[p * n + i], aqk = A[q * n + i];
+        A[p * n + i] = c * apk - s * aqk;
+        A[q * n + i] = s * apk + c * aqk;
+      }
+      __syncwarp();
+    }
+  }
+}
+
 template <int n>
 __device__ void sort_diag(const double* A, int* order, bool descending) {
   for (int i = 0; i < n; i++) order[i] = i;
@@ -84,15 +146,21 @@ __device__ void sort_diag(const double* A, int* order, bool descending) {
   }
 }
 
-// least squares by Householder QR (epnp::qr_solve); A: nr x nc row-major, destroyed
-__device__ bool qr_solve(int nr, int nc, double* A, double* b, double* X) {
-  double A1[5], A2[5];
+// least squares by Householder QR (epnp::qr_solve); A: 6 x NC row-major, destroyed.  Fully unrolled: the small
+// systems live in registers (same operations in the same order as the run-time-sized CPU routine).
+template <int NC>
+__device__ __forceinline__ bool qr_solve(double* A, double* b, double* X) {
+  constexpr int nr = 6, nc = NC;
+  double A1[NC], A2[NC];
+#pragma unroll
   for (int k = 0; k < nc; k++) {
     double eta = 0;
+#pragma unroll
     for (int i = k; i < nr; i++) eta = fmax(eta, fabs(A[i * nc + k]));
     if (eta == 0) return false;
     const double inv_eta = 1.0 / eta;
     double sum2 = 0;
+#pragma unroll
     for (int i = k; i < nr; i++) {
       A[i * nc + k] *= inv_eta;
       sum2 += A[i * nc + k] * A[i * nc + k];
@@ -102,22 +170,30 @@ __device__ bool qr_solve(int nr, int nc, double* A, double* b, double* X) {
     A[k * nc + k] += sigma;
     A1[k] = sigma * A[k * nc + k];
     A2[k] = -eta * sigma;
+#pragma unroll
     for (int j = k + 1; j < nc; j++) {
       double sum = 0;
+#pragma unroll
       for (int i = k; i < nr; i++) sum += A[i * nc + k] * A[i * nc + j];
       const double tau = sum / A1[k];
+#pragma unroll
       for (int i = k; i < nr; i++) A[i * nc + j] -= tau * A[i * nc + k];
     }
   }
+#pragma unroll
   for (int j = 0; j < nc; j++) {
     double tau = 0;
+#pragma unroll
     for (int i = j; i < nr; i++) tau += A[i * nc + j] * b[i];
     tau /= A1[j];
+#pragma unroll
     for (int i = j; i < nr; i++) b[i] -= tau * A[i * nc + j];
   }
   X[nc - 1] = b[nc - 1] / A2[nc - 1];
+#pragma unroll
   for (int i = nc - 2; i >= 0; i--) {
     double sum = 0;
+#pragma unroll
     for (int j = i + 1; j < nc; j++) sum += A[i * nc + j] * X[j];
     X[i] = (b[i] - sum) / A2[i];
   }
@@ -131,7 +207,8 @@ struct EpnpState {
   double L[6][10], rho[6];
 };
 
-__device__ bool epnp_prepare(EpnpState& e) {
+// Part 1 (one lane): control points, barycentric coordinates, the 10 x 12 system M (row-major, to shared memory)
+__device__ bool epnp_prepare_M(EpnpState& e, double* M) {
   const int n = 5;
   for (int j = 0; j < 3; j++) {
     double s = 0;
@@ -171,21 +248,18 @@ __device__ bool epnp_prepare(EpnpState& e) {
                        ci[3 * j + 2] * (e.pws[i][2] - e.cws[0][2]);
     e.al[i][0] = 1.0 - e.al[i][1] - e.al[i][2] - e.al[i][3];
   }
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < 4; j++) {
+      M[(2 * i) * 12 + 3 * j] = e.al[i][j] * e.fu; M[(2 * i) * 12 + 3 * j + 1] = 0.0; M[(2 * i) * 12 + 3 * j + 2] = e.al[i][j] * (e.uc - e.us[i][0]);
+      M[(2 * i + 1) * 12 + 3 * j] = 0.0; M[(2 * i + 1) * 12 + 3 * j + 1] = e.al[i][j] * e.fv; M[(2 * i + 1) * 12 + 3 * j + 2] = e.al[i][j] * (e.vc - e.us[i][1]);
+    }
+  return true;
+}
+
+// Part 2 (one lane, after the warp has diagonalised M^T M into (MtM, VV)): the four smallest eigenvectors,
+// L_6x10 and rho
+__device__ void epnp_prepare_L(EpnpState& e, const double* MtM, const double* VV) {
   {
-    double M[10][12];
-    for (int i = 0; i < n; i++)
-      for (int j = 0; j < 4; j++) {
-        M[2 * i][3 * j] = e.al[i][j] * e.fu; M[2 * i][3 * j + 1] = 0.0; M[2 * i][3 * j + 2] = e.al[i][j] * (e.uc - e.us[i][0]);
-        M[2 * i + 1][3 * j] = 0.0; M[2 * i + 1][3 * j + 1] = e.al[i][j] * e.fv; M[2 * i + 1][3 * j + 2] = e.al[i][j] * (e.vc - e.us[i][1]);
-      }
-    double MtM[144], VV[144];
-    for (int a = 0; a < 12; a++)
-      for (int b = 0; b < 12; b++) {
-        double s = 0;
-        for (int r = 0; r < 10; r++) s += M[r][a] * M[r][b];
-        MtM[a * 12 + b] = s;
-      }
-    jacobi_eig<12>(MtM, VV);
     int ord12[12];
     sort_diag<12>(MtM, ord12, false);
     for (int i = 0; i < 4; i++)
@@ -219,18 +293,27 @@ __device__ bool epnp_prepare(EpnpState& e) {
     for (int k = 0; k < 3; k++) s += (e.cws[pa[i]][k] - e.cws[pb[i]][k]) * (e.cws[pa[i]][k] - e.cws[pb[i]][k]);
     e.rho[i] = s;
   }
-  return true;
+}
+
+template <int NC>
+__device__ __forceinline__ bool epnp_betas_solve(const EpnpState& e, const int (&cols)[NC], double* x) {
+  double A[6 * NC], b[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+#pragma unroll
+    for (int j = 0; j < NC; j++) A[i * NC + j] = e.L[i][cols[j]];
+    b[i] = e.rho[i];
+  }
+  return qr_solve<NC>(A, b, x);
 }
 
 __device__ bool epnp_betas(const EpnpState& e, int which, double* be) {
-  const int cols[3][5] = {{0, 1, 3, 6, -1}, {0, 1, 2, -1, -1}, {0, 1, 2, 3, 4}};
-  const int nc = which == 0 ? 4 : which == 1 ? 3 : 5;
-  double A[30], b[6], x[5];
-  for (int i = 0; i < 6; i++) {
-    for (int j = 0; j < nc; j++) A[i * nc + j] = e.L[i][cols[which][j]];
-    b[i] = e.rho[i];
-  }
-  if (!qr_solve(6, nc, A, b, x)) return false;
+  double x[5];
+  bool ok;
+  if (which == 0) { const int c[4] = {0, 1, 3, 6}; ok = epnp_betas_solve<4>(e, c, x); }
+  else if (which == 1) { const int c[3] = {0, 1, 2}; ok = epnp_betas_solve<3>(e, c, x); }
+  else { const int c[5] = {0, 1, 2, 3, 4}; ok = epnp_betas_solve<5>(e, c, x); }
+  if (!ok) return false;
   be[0] = be[1] = be[2] = be[3] = 0.0;
   if (which == 0) {
     if (x[0] < 0) { be[0] = sqrt(-x[0]); be[1] = -x[1] / be[0]; be[2] = -x[2] / be[0]; be[3] = -x[3] / be[0]; }
@@ -247,6 +330,7 @@ __device__ bool epnp_betas(const EpnpState& e, int which, double* be) {
 __device__ bool epnp_gauss_newton(const EpnpState& e, double* be) {
   for (int it = 0; it < 5; it++) {
     double A[24], b[6], x[4];
+#pragma unroll
     for (int i = 0; i < 6; i++) {
       const double* r = e.L[i];
       A[i * 4 + 0] = 2 * r[0] * be[0] + r[1] * be[1] + r[3] * be[2] + r[6] * be[3];
@@ -257,7 +341,7 @@ __device__ bool epnp_gauss_newton(const EpnpState& e, double* be) {
                          r[4] * be[1] * be[2] + r[5] * be[2] * be[2] + r[6] * be[0] * be[3] + r[7] * be[1] * be[3] +
                          r[8] * be[2] * be[3] + r[9] * be[3] * be[3]);
     }
-    if (!qr_solve(6, 4, A, b, x)) return false;
+    if (!qr_solve<4>(A, b, x)) return false;
     for (int i = 0; i < 4; i++) be[i] += x[i];
   }
   return true;
@@ -335,45 +419,73 @@ __device__ double epnp_R_and_t(const EpnpState& e, const double* be, double* R, 
   return sum / n;
 }
 
-// hypothesis h = (problem b, iteration it): sets [H][5] point indices local to the problem, models [H][12] = R | t
-__global__ void __launch_bounds__(32)
+// hypothesis h = (problem b, iteration it): sets [H][5] point indices local to the problem, models [H][12] = R | t.
+// One WARP per hypothesis: lane 0 runs the scalar chain, the 12 x 12 eigen-problem (9/10 of the work) is shared.
+constexpr int kEpnpWarps = 4;
+__global__ void __launch_bounds__(kEpnpWarps * 32)
 pnp_epnp_kernel(int H, int max_iters, const int* __restrict__ off, const int* __restrict__ sets,
                 const float* __restrict__ obj, const float* __restrict__ img, const double* __restrict__ K4,
                 double* __restrict__ models, int* __restrict__ valid) {
-  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ double s_M[kEpnpWarps][120], s_A[kEpnpWarps][144], s_V[kEpnpWarps][144];
+  __shared__ EpnpState s_e[kEpnpWarps];
+  __shared__ double s_cs[kEpnpWarps][12];
+  __shared__ int s_ok[kEpnpWarps];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.x * kEpnpWarps + warp;
   if (h >= H) return;
-  const int b = h / max_iters;
-  const int o0 = off[b];
-  EpnpState e;
-  e.fu = K4[0]; e.fv = K4[1]; e.uc = K4[2]; e.vc = K4[3];
-  const double ifx = 1.0 / K4[0], ify = 1.0 / K4[1];
-  for (int i = 0; i < 5; i++) {
-    const int p = o0 + sets[h * 5 + i];
-    for (int k = 0; k < 3; k++) e.pws[i][k] = obj[3 * p + k];
-    const float xn = (float)(((double)img[2 * p] - K4[2]) * ifx), yn = (float)(((double)img[2 * p + 1] - K4[3]) * ify);
-    e.us[i][0] = (double)xn * K4[0] + K4[2];
-    e.us[i][1] = (double)yn * K4[1] + K4[3];
+  EpnpState& e = s_e[warp];
+  if (lane == 0) {
+    const int b = h / max_iters;
+    const int o0 = off[b];
+    e.fu = K4[0]; e.fv = K4[1]; e.uc = K4[2]; e.vc = K4[3];
+    const double ifx = 1.0 / K4[0], ify = 1.0 / K4[1];
+    for (int i = 0; i < 5; i++) {
+      const int p = o0 + sets[h * 5 + i];
+      for (int k = 0; k < 3; k++) e.pws[i][k] = obj[3 * p + k];
+      const float xn = (float)(((double)img[2 * p] - K4[2]) * ifx), yn = (float)(((double)img[2 * p + 1] - K4[3]) * ify);
+      e.us[i][0] = (double)xn * K4[0] + K4[2];
+      e.us[i][1] = (double)yn * K4[1] + K4[3];
+    }
+    s_ok[warp] = epnp_prepare_M(e, s_M[warp]) ? 1 : 0;
   }
-  bool any = false;
-  double best = 1e300, Rb[9], tb[3];
-  if (epnp_prepare(e)) {
-    for (int which = 0; which < 3; which++) {
-      double be[4], Rc[9], tc[3];
-      if (!epnp_betas(e, which, be) || !epnp_gauss_newton(e, be)) continue;
-      const double err = epnp_R_and_t(e, be, Rc, tc);
-      if (!(err == err)) continue;
-      if (!any || err < best) {
-        best = err;
-        for (int a = 0; a < 9; a++) Rb[a] = Rc[a];
-        for (int a = 0; a < 3; a++) tb[a] = tc[a];
-        any = true;
-      }
+  __syncwarp();
+  const bool ok = s_ok[warp] != 0;
+  if (ok) {
+    for (int en = lane; en < 144; en += 32) {  // M^T M, every entry summed over the rows in order
+      const int a = en / 12, b = en - a * 12;
+      double sm = 0;
+      for (int r = 0; r < 10; r++) sm += s_M[warp][r * 12 + a] * s_M[warp][r * 12 + b];
+      s_A[warp][en] = sm;
+    }
+    __syncwarp();
+    jacobi_eig12_warp(s_A[warp], s_V[warp], s_cs[warp], lane);
+    __syncwarp();
+    if (lane == 0) epnp_prepare_L(e, s_A[warp], s_V[warp]);
+    __syncwarp();
+  }
+  // the three beta initialisations run on lanes 0..2 side by side (Gauss-Newton and the absolute orientation are
+  // the same code on different data); lane 0 then keeps the candidate OpenCV's sequential comparison keeps
+  double err = 1e300, Rc[9], tc[3];
+  bool have = false;
+  if (ok && lane < 3) {
+    double be[4];
+    if (epnp_betas(e, lane, be) && epnp_gauss_newton(e, be)) {
+      err = epnp_R_and_t(e, be, Rc, tc);
+      have = err == err;
     }
   }
-  valid[h] = any ? 1 : 0;
-  if (any) {
-    for (int a = 0; a < 9; a++) models[h * 12 + a] = Rb[a];
-    for (int a = 0; a < 3; a++) models[h * 12 + 9 + a] = tb[a];
+  bool any = false;
+  double best = 1e300;
+  int pick = 0;
+  for (int which = 0; which < 3; which++) {
+    const bool hv = __shfl_sync(0xffffffffu, have ? 1 : 0, which) != 0;
+    const double ev = __shfl_sync(0xffffffffu, err, which);
+    if (hv && (!any || ev < best)) { best = ev; pick = which; any = true; }
+  }
+  if (lane == 0) valid[h] = any ? 1 : 0;
+  if (any && lane == pick) {
+    for (int a = 0; a < 9; a++) models[h * 12 + a] = Rc[a];
+    for (int a = 0; a < 3; a++) models[h * 12 + 9 + a] = tc[a];
   }
 }
 
@@ -566,7 +678,7 @@ pnp_refine_kernel(int max_iters, int words_max, const int* __restrict__ off, con
 cudaError_t launch_pnp_hypotheses(int H, int max_iters, int words_max, const int* off, const int* sets, const float* obj,
                                   const float* img, const double* K4, double* models, int* valid, float thr2,
                                   unsigned* masks, int* counts, cudaStream_t s) {
-  pnp_epnp_kernel<<<(H + 31) / 32, 32, 0, s>>>(H, max_iters, off, sets, obj, img, K4, models, valid);
+  pnp_epnp_kernel<<<(H + kEpnpWarps - 1) / kEpnpWarps, kEpnpWarps * 32, 0, s>>>(H, max_iters, off, sets, obj, img, K4, models, valid);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   pnp_score_kernel<<<(H + 7) / 8, 256, 0, s>>>(H, max_iters, words_max, off, obj, img, K4, models, valid, thr2, masks, counts);
