@@ -62,8 +62,10 @@ typedef struct {
   int32_t threads;       /* threads per CTA; 0 -> auto */
   int32_t force_atomic;  /* 1: always accumulate S with global fp64 atomics (default: shared-memory copies when they fit) */
   int32_t dense_solver;  /* windows whose reduced camera system is solved in shared memory (<= 16 free cameras):
-                            0 -> block-Jacobi PCG (default, the same solver as the large systems),
-                            1 -> direct LDL^T factorisation (what g2o's LinearSolverEigen does; same speed) */
+                            0 -> direct tiled Cholesky (default: what g2o's LinearSolverEigen does, 3x faster than the
+                                 other two; falls back to 1 when the tiles do not fit the CTA),
+                            1 -> direct LDL^T with one barrier per pivot,
+                            2 -> block-Jacobi PCG (tolerance pcg_tol; the solver BASELINE.json's north_star names) */
   int32_t large_mode;    /* one large window (>= 100k observations) and the point-sharded solve:
                             0 -> tile mode when it fits (points renumbered along the trajectory, S as a block band,
                                  direct block-banded Cholesky — csrc/ba_large.cu), else the atomic / PCG kernels,

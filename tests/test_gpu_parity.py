@@ -509,14 +509,20 @@ def test_ba_batch_of_full_size_windows_matches_single_solves(oracle, ctx):
 
 
 def test_ba_dense_solver_ldlt_and_pcg_agree(ctx, oracle):
-    """The in-shared-memory reduced camera system: block-Jacobi PCG (default) and the direct LDL^T
-    (dense_solver = 1) both meet the parity bar; the direct solve reports no PCG iterations."""
+    """The in-shared-memory reduced camera system: tiled Cholesky (default), the one-barrier-per-pivot LDL^T
+    (dense_solver = 1) and block-Jacobi PCG (dense_solver = 2) all meet the parity bar; the direct solves report
+    no PCG iterations."""
     prob = synth.cfg1()
-    gs0, _ = _check_ba(oracle, ctx, prob, opts=U.BAOptions(0, 0, 0, 0, 0, 1))
-    gs1, _ = _check_ba(oracle, ctx, prob, opts=U.BAOptions(0, 0, 0, 0, 0, 0))
-    assert gs0.pcg_iters[0] == 0 and gs0.pcg_iters[1] == 0
-    assert gs1.pcg_iters[0] > 0
-    assert list(gs0.trials) == list(gs1.trials)
+    gs0, _ = _check_ba(oracle, ctx, prob, opts=U.BAOptions(0, 0, 0, 0, 0, 0))
+    gs1, _ = _check_ba(oracle, ctx, prob, opts=U.BAOptions(0, 0, 0, 0, 0, 1))
+    gs2, _ = _check_ba(oracle, ctx, prob, opts=U.BAOptions(0, 0, 0, 0, 0, 2))
+    assert gs0.pcg_iters[0] == 0 and gs0.pcg_iters[1] == 0 and gs1.pcg_iters[0] == 0
+    assert gs2.pcg_iters[0] > 0
+    assert list(gs0.trials) == list(gs1.trials) == list(gs2.trials)
+    # 16 free cameras (n = 96: 528 + 32 tiles do not fit 256 threads -> falls back to the LDL^T) and 2 free cameras
+    for n_cams, n_fixed in ((18, 2), (4, 2)):
+        p = synth.make_ba(900 + n_cams, n_cams, 60 * n_cams, 4.0, n_cams, n_fixed, 0.03)
+        _check_ba(oracle, ctx, p)
 
 
 def _thin(prob, keep):

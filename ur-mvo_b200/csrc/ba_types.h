@@ -103,7 +103,7 @@ struct BARun {
   int pcg_max_iter;
   int it0, it1;
   int n_win;
-  int dense_pcg;       // 1 (default): block-Jacobi PCG for the in-shared-memory systems, 0: direct LDL^T
+  int dense_solver;    // in-shared-memory systems: 0 tiled Cholesky (default), 1 one-barrier-per-pivot LDL^T, 2 block-Jacobi PCG
   const void* timing_stats;  // the window whose stats pointer equals this records phase cycles
 };
 

@@ -680,7 +680,7 @@ static int ba_plan_create_impl_(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, cons
   p->run.chi2_thr_s = stereo ? chi2_thr_stereo : chi2_thr;
   p->run.delta_s = (double)(float)std::sqrt(p->run.chi2_thr_s);  // const float thHuberStereoPoint = sqrt(cfg.stereo_point)
   p->run.pcg_tol = (opts && opts->pcg_tol > 0) ? opts->pcg_tol : 1e-10;
-  p->run.dense_pcg = (opts && opts->dense_solver == 1) ? 0 : 1;
+  p->run.dense_solver = opts ? std::min(std::max(opts->dense_solver, 0), 2) : 0;
   p->run.pcg_max_iter = (opts && opts->pcg_max_iter > 0) ? opts->pcg_max_iter : std::min(1000, std::max(60, 12 * max_ncf));
   p->run.it0 = it0; p->run.it1 = it1; p->run.n_win = B;
   p->run.timing_stats = nullptr;
