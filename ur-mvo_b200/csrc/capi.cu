@@ -7,6 +7,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -1215,13 +1216,26 @@ extern "C" int urmvo_local_ba_batch(urmvo_ctx* ctx, int B, const int32_t* cam_of
                                     const double* uv, const int32_t* cam, const int32_t* pt, const double* intr,
                                     double chi2_thr, int it0, int it1, uint8_t* inlier, urmvo_ba_stats* stats,
                                     const urmvo_ba_options* opts) {
+  // URMVO_B200_TRACE=1: host-side split of the call (structure + upload | kernel | read-back) on stderr
+  static const bool trace = std::getenv("URMVO_B200_TRACE") != nullptr;
+  const auto t0 = std::chrono::steady_clock::now();
   urmvo_ba_plan* p = nullptr;
   int rc = ba_plan_create_impl(ctx, &p, B, cam_off, pt_off, obs_off, poses, fixed, pts, uv, cam, pt, intr,
                                chi2_thr, it0, it1, opts, false, nullptr, /*borrow_ws=*/true);
   if (rc != URMVO_OK) return rc;
+  const auto t1 = std::chrono::steady_clock::now();
   rc = urmvo_ba_plan_run(p);
+  const auto t2 = std::chrono::steady_clock::now();
   if (rc == URMVO_OK) rc = urmvo_ba_plan_download(p, poses, pts, inlier, stats);
+  const auto t3 = std::chrono::steady_clock::now();
   urmvo_ba_plan_destroy(p);
+  if (trace) {
+    auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+      return std::chrono::duration<double, std::micro>(b - a).count();
+    };
+    std::fprintf(stderr, "[urmvo_b200] local_ba_batch B=%d: create+upload %.0f us, launch %.0f us, wait+download %.0f us, destroy %.0f us\n",
+                 B, us(t0, t1), us(t1, t2), us(t2, t3), us(t3, std::chrono::steady_clock::now()));
+  }
   return rc;
 }
 
