@@ -19,7 +19,7 @@
 //   pnp_refine_kernel  one CTA per frame: Levenberg-Marquardt over the inliers of the winner, normal equations
 //                      reduced in a fixed order, and the mask words expanded to the caller's byte flags.
 // fp64, compiled with -fmad=false: the arithmetic of a hypothesis follows the CPU restatement
-// (oracle/pnp_oracle.cpp) operation by operation, so counts and masks are identical to it.
+// (the pnp file of the parity oracle) operation by operation, so counts and masks are identical to it.
 
 #include "common.cuh"
 #include "kernels.h"
@@ -75,7 +75,7 @@ __device__ void jacobi_eig(double* A, double* V) {
 // k = 1..5 is ((r + k) mod 11, (r - k) mod 11)).  Lanes 0..5 compute the six rotations of a round at once — the two
 // square roots and three divisions of a rotation are a ~1000-cycle dependency chain, paid 11 times per sweep instead
 // of 66 —, then all lanes apply them: first to the columns of A and V, then to the rows of A.  The order of the
-// element operations is that of the CPU restatement (oracle/pnp_oracle.cpp jacobi_eig12_rr).
+// element operations is that of the CPU restatement (its jacobi_eig12_rr).
 __device__ void jacobi_eig12_warp(double* A, double* V, double* cs /* [12] */, int lane) {
   constexpr int n = 12;
   for (int e = lane; e < n * n; e += 32) V[e] = (e / n == e % n) ? 1.0 : 0.0;
