@@ -591,6 +591,25 @@ def side_measurements(ctx, stream, torch):
                                       "cpu_lm_iters_per_s": (o[3].iters[0] + o[3].iters[1]) / tc, "cpu_sample": "1 window, 1 thread",
                                       "rel_cost_diff": abs(sst.chi2_final[1] - o[3].chi2_final[1]) / abs(o[3].chi2_final[1])}
     splan.close()
+    # the same window through the device-resident map against the one-shot host-buffer call
+    ctx.local_ba(one)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        ctx.local_ba(one)
+    t_shot = (time.perf_counter() - t0) / 5
+    dmap = U.DeviceMap(ctx, one["intr"])
+    nc1, np1 = one["poses"].shape[0], one["pts"].shape[0]
+    kid = np.arange(nc1, dtype=np.int32) * 3 + 10; pid = np.arange(np1, dtype=np.int32) * 7 + 1000
+    order = np.argsort(one["obs_pt"], kind="stable")
+    dmap.set_keyframes(kid, one["poses"]); dmap.set_points(pid, one["pts"])
+    dmap.add_observations(kid[one["obs_cam"][order]], pid[one["obs_pt"][order]], one["uv"][order])
+    t_map = 0.0
+    for _ in range(6):
+        dmap.set_keyframes(kid, one["poses"]); dmap.set_points(pid, one["pts"]); ctx.sync()  # reset outside the timed region
+        t0 = time.perf_counter(); mres = dmap.local_ba(kid, one["fixed"], pid, max_obs=len(one["uv"])); t_map = time.perf_counter() - t0
+    extra["ba_single_window_cfg1"].update({"e2e_one_shot_call_ms": t_shot * 1e3, "e2e_map_call_ms": t_map * 1e3,
+                                           "map_chi2_equals_one_shot": bool(abs(mres[3].chi2_final[1] - sst.chi2_final[1]) <= 1e-12 * abs(sst.chi2_final[1]))})
+    dmap.close()
     # per-frame outlier rejection: 256 frame pairs x 1000 matches, up to 1000 RANSAC
     # iterations each; device-resident kernels (solve + score), the whole host-buffer call, and the
     # reference's own OpenCV call (cv2, when importable) / the CPU restatement beside it

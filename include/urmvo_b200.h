@@ -284,6 +284,37 @@ int urmvo_fm_plan_finish(urmvo_fm_plan* plan, uint8_t* inlier, urmvo_fm_stats* s
 int urmvo_fm_plan_hypotheses(const urmvo_fm_plan* plan); /* (iteration, problem) pairs evaluated per run */
 void urmvo_fm_plan_destroy(urmvo_fm_plan* plan);
 
+/* ------------------------------------------------------------------ device-resident map
+ * Mapping::LocalMapOptimization (reference src/mapping.cc:335-535) rebuilds the bundle-adjustment problem from
+ * shared_ptr graphs on every keyframe and copies every pose, point and keypoint into fresh containers
+ * (:353-469) before it calls LocalmapOptimization (:471).  With a urmvo_map the keyframe poses, mappoint positions
+ * and observations stay in HBM across keyframes, addressed by the caller's ids (frame ids, mappoint ids); a keyframe
+ * uploads only what is new, a window is selected by id lists, and the optimised values are written back into the map
+ * on the device.  The library keeps the index structure (id -> slot, per-point observer lists) on the host.
+ *  poses: T_wc as (qx,qy,qz,qw,px,py,pz) like Pose3d; intr = fx,fy,cx,cy (mono edges).
+ *  set_*: adds new ids or overwrites existing ones.  remove_observations: unknown pairs are ignored.
+ *  urmvo_map_local_ba: the window is every stored observation (kf, pt) with kf in kf_ids and pt in pt_ids, point by
+ *  point in pt_ids order and in insertion order inside a point; a point with fewer than two observations in the window
+ *  is left out (:463-465).  kf_fixed[i] = 1 keeps keyframe i fixed (:355-356).  Cameras are indexed in kf_ids order, so
+ *  a caller that lists ids in ascending order gets the vertex order of the reference's std::map.  On return the map
+ *  holds the optimised free poses and points (read them with urmvo_map_get_*), and the observations used are listed
+ *  with their inlier flags (n_obs entries of obs_kf / obs_pt / inlier; max_obs = capacity of those arrays) so that
+ *  the caller can erase the outliers (:474-500) with urmvo_map_remove_observations.  Same arithmetic, same results
+ *  as urmvo_local_ba on the same window (tests/test_gpu_map.py). */
+typedef struct urmvo_map urmvo_map;
+int urmvo_map_create(urmvo_ctx* ctx, urmvo_map** map, const double* intr);
+void urmvo_map_destroy(urmvo_map* map);
+int urmvo_map_set_keyframes(urmvo_map* map, int n, const int32_t* ids, const double* poses);
+int urmvo_map_set_points(urmvo_map* map, int n, const int32_t* ids, const double* xyz);
+int urmvo_map_add_observations(urmvo_map* map, int n, const int32_t* kf_ids, const int32_t* pt_ids, const double* uv);
+int urmvo_map_remove_observations(urmvo_map* map, int n, const int32_t* kf_ids, const int32_t* pt_ids);
+int urmvo_map_get_keyframes(urmvo_map* map, int n, const int32_t* ids, double* poses);
+int urmvo_map_get_points(urmvo_map* map, int n, const int32_t* ids, double* xyz);
+int urmvo_map_local_ba(urmvo_map* map, int n_kf, const int32_t* kf_ids, const uint8_t* kf_fixed, int n_pt,
+                       const int32_t* pt_ids, double chi2_thr, int it0, int it1, const urmvo_ba_options* opts,
+                       int32_t max_obs, int32_t* n_obs, int32_t* obs_kf, int32_t* obs_pt, uint8_t* inlier,
+                       urmvo_ba_stats* stats);
+
 /* ------------------------------------------------------------------ SolvePnPWithCV (B9)
  * Replaces the OpenCV call of SolvePnPWithCV, reference src/g2o_optimization.cc:353-355:
  *     cv::solvePnPRansac(object_points, image_points, camera_matrix, dist_coeffs (zero), rvec, tvec,

@@ -25,3 +25,14 @@ ctx.pose_only_batch(pb)
 for rep in range(3):
     t0 = time.perf_counter(); ctx.pose_only_batch(pb); t1 = time.perf_counter()
     print(f"urmvo_pose_only_batch (1 frame x 1000 matches): {1e3*(t1-t0):.3f} ms")
+# the same cfg1 window through the device-resident map (values already in HBM; reset outside the timed region)
+m = U.DeviceMap(ctx, w["intr"])
+Nc, Np = w["poses"].shape[0], w["pts"].shape[0]
+kf_ids = np.arange(Nc, dtype=np.int32) * 3 + 10; pt_ids = np.arange(Np, dtype=np.int32) * 7 + 1000
+m.set_keyframes(kf_ids, w["poses"]); m.set_points(pt_ids, w["pts"])
+order = np.argsort(w["obs_pt"], kind="stable")
+m.add_observations(kf_ids[w["obs_cam"][order]], pt_ids[w["obs_pt"][order]], w["uv"][order])
+for rep in range(5):
+    m.set_keyframes(kf_ids, w["poses"]); m.set_points(pt_ids, w["pts"]); ctx.sync()
+    t0 = time.perf_counter(); okf, opt, inl, st = m.local_ba(kf_ids, w["fixed"], pt_ids, max_obs=len(w["uv"])); t1 = time.perf_counter()
+    print(f"urmvo_map_local_ba (same window, values resident in HBM): {1e3*(t1-t0):.3f} ms, iters {list(st.iters)}")

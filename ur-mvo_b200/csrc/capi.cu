@@ -15,6 +15,7 @@
 #include <atomic>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/urmvo_b200.h"
@@ -146,6 +147,17 @@ extern "C" int64_t urmvo_launch_count(urmvo_ctx* c) { return c ? c->launches : 0
 
 // =====================================================================================  BA
 
+// A window taken from the device-resident map (urmvo_map_local_ba): the values of the plan's pose / point / uv
+// inputs are gathered on the device from the map's slot-addressed arrays; only the slot lists are uploaded.
+struct MapGather {
+  const double* d_kf;   // device: cap_kf * 7 (T_wc)
+  const double* d_pt;   // device: cap_pt * 3
+  const double* d_uv;   // device: cap_obs * 2
+  const int* kf_slot;   // host: Nc
+  const int* pt_slot;   // host: Np
+  const int* obs_slot;  // host: No
+};
+
 struct urmvo_ba_plan {
   urmvo_ctx* ctx = nullptr;
   int B = 0;
@@ -180,6 +192,8 @@ struct urmvo_ba_plan {
   bool use_bcr = false;              // long trajectories: block cyclic reduction (csrc/ba_bcr.cu) instead of the sequential band solve
   BcrShape bcr{};
   size_t off_bcr = 0;
+  size_t off_gather = 0;             // map windows: device copies of the slot lists [kf | pt | obs]
+  size_t off_cam_free = 0;           // dense free-camera index per camera (-1: fixed)
   int n_solve_launches = 1;
   size_t off_hd = 0;                 // [hdiag | scal] is the all-reduce buffer of the lambda initialisation
   size_t n_reduce_diag = 0;
@@ -467,7 +481,7 @@ static int ba_plan_create_impl_(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, cons
                                const int32_t* cam, const int32_t* pt, const double* intr,
                                double chi2_thr, int it0, int it1, const urmvo_ba_options* opts,
                                bool sharded, const uint8_t* covis, bool borrow_ws,
-                               const uint8_t* kind, double chi2_thr_stereo);
+                               const uint8_t* kind, double chi2_thr_stereo, const MapGather* mg);
 
 // no exception crosses the C ABI: allocation failures of the host-side flattening become a status
 static int ba_plan_create_impl(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, const int32_t* cam_off,
@@ -476,10 +490,10 @@ static int ba_plan_create_impl(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, const
                                const int32_t* cam, const int32_t* pt, const double* intr,
                                double chi2_thr, int it0, int it1, const urmvo_ba_options* opts,
                                bool sharded, const uint8_t* covis, bool borrow_ws = false,
-                               const uint8_t* kind = nullptr, double chi2_thr_stereo = 0.0) {
+                               const uint8_t* kind = nullptr, double chi2_thr_stereo = 0.0, const MapGather* mg = nullptr) {
   try {
     return ba_plan_create_impl_(ctx, out, B, cam_off, pt_off, obs_off, poses, fixed, pts, uv, cam, pt, intr, chi2_thr, it0,
-                                it1, opts, sharded, covis, borrow_ws, kind, chi2_thr_stereo);
+                                it1, opts, sharded, covis, borrow_ws, kind, chi2_thr_stereo, mg);
   } catch (const std::exception& e) {
     if (ctx) ctx->ws_in_use = false;
     if (out) *out = nullptr;
@@ -493,7 +507,7 @@ static int ba_plan_create_impl_(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, cons
                                const int32_t* cam, const int32_t* pt, const double* intr,
                                double chi2_thr, int it0, int it1, const urmvo_ba_options* opts,
                                bool sharded, const uint8_t* covis, bool borrow_ws,
-                               const uint8_t* kind, double chi2_thr_stereo) {
+                               const uint8_t* kind, double chi2_thr_stereo, const MapGather* mg) {
   // kind != NULL: stereo-capable window(s): uv carries 3 values per observation (u, v, u_right), intr 5 values
   // (fx, fy, cx, cy, bf), kind[o] = 1 marks an EdgeStereoSE3ProjectXYZ (reference src/g2o_optimization.cc:96-118)
   const bool stereo = kind != nullptr;
@@ -501,8 +515,10 @@ static int ba_plan_create_impl_(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, cons
   if (!ctx || !out) return fail(URMVO_ERR_ARG, "ba_plan_create: null context / out");
   if (stereo && (sharded || !(chi2_thr_stereo > 0))) return fail(URMVO_ERR_ARG, "ba_plan_create: stereo edges need a positive threshold and are not supported by the point-sharded solve");
   *out = nullptr;
-  if (B <= 0 || !cam_off || !pt_off || !obs_off || !poses || !fixed || !pts || !uv || !cam || !pt || !intr)
+  if (B <= 0 || !cam_off || !pt_off || !obs_off || !fixed || !cam || !pt || !intr || (!mg && (!poses || !pts || !uv)))
     return fail(URMVO_ERR_ARG, "ba_plan_create: null or empty input");
+  if (mg && (B != 1 || stereo || sharded || obs_off[1] - obs_off[0] >= 100000))
+    return fail(URMVO_ERR_UNSUPPORTED, "map window: one mono window of fewer than 100000 observations");
   if (it0 < 0 || it1 < 0 || !(chi2_thr > 0)) return fail(URMVO_ERR_ARG, "ba_plan_create: bad iteration counts / threshold");
   CU_TRY(cudaSetDevice(ctx->device));
   std::vector<WinHost> wh(B);
@@ -695,12 +711,14 @@ static int ba_plan_create_impl_(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, cons
   const size_t o_ocam = A.take<int>(TO), o_opt = A.take<int>(TO);
   const size_t o_ur = A.take<double>(stereo ? TO : 0), o_okind = A.take<uint8_t>(stereo ? TO : 0);
   const size_t o_pt_start = A.take<int>(TP + B), o_cam_free = A.take<int>(TC), o_grp = A.take<int>(sum_grp + 1);
+  p->off_cam_free = o_cam_free;
   const size_t o_row_ptr = A.take<int>(sum_ncf + B), o_col = A.take<int>(sum_blk);
   const size_t o_lrow_ptr = A.take<int>(sum_ncf + B), o_lcol = A.take<int>(sum_blk), o_lblk = A.take<int>(sum_blk);
   // tile mode: chunk / block-ownership tables
   const WinHost& w0 = wh[0];
   const size_t o_chunk_grp = A.take<int>(tile ? w0.chunk_grp.size() : 0), o_grp_cbase = A.take<int>(tile ? w0.grp_cbase.size() : 0);
   const size_t o_chunk_blk = A.take<int>(tile ? w0.chunk_blk.size() : 0), o_blk_desc = A.take<int>(tile ? w0.blk_desc.size() : 0);
+  p->off_gather = A.take<int>(mg ? (size_t)p->total_c + p->total_p + p->total_o : 0);  // map windows: slot lists, part of the staged upload
   p->off_wins = A.take<BAWin>(B);
   const size_t upload_end = A.off;  // everything above is filled from the host
   size_t o_cam[2], o_camRt[2], o_pts[2];
@@ -854,8 +872,14 @@ static int ba_plan_create_impl_(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, cons
   auto up = [&](size_t off, const void* src, size_t bytes) {
     return bytes ? cudaMemcpyAsync(D + off, src, bytes, cudaMemcpyHostToDevice, s) : cudaSuccess;
   };
+  if (mg) {
+    int* hg = (int*)hp(p->off_gather);
+    std::memcpy(hg, mg->kf_slot, TC * sizeof(int));
+    std::memcpy(hg + TC, mg->pt_slot, TP * sizeof(int));
+    std::memcpy(hg + TC + TP, mg->obs_slot, TO * sizeof(int));
+  }
   cudaError_t e1 = up(o_pt_start, H, idx_bytes);
-  cudaError_t e2 = up(o_pose_in, poses, TC * 7 * sizeof(double));
+  cudaError_t e2 = mg ? cudaSuccess : up(o_pose_in, poses, TC * 7 * sizeof(double));
   cudaError_t e3;
   std::vector<int> pt_inv;
   if (tile) {  // points renumbered by first free camera
@@ -868,11 +892,19 @@ static int ba_plan_create_impl_(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, cons
     }
     e3 = up(o_pts_in, hpts, TP * 3 * sizeof(double));
   } else {
-    e3 = up(o_pts_in, pts, TP * 3 * sizeof(double));
+    e3 = mg ? cudaSuccess : up(o_pts_in, pts, TP * 3 * sizeof(double));
   }
   cudaError_t e4, e5;
   cudaError_t e8 = cudaSuccess;
-  if (all_sorted) {
+  if (mg) {  // values come from the device-resident map: upload the three slot lists and gather
+    if (!all_sorted) { urmvo_ba_plan_destroy(p); return fail(URMVO_ERR_ARG, "map window: observations must be point-major"); }
+    int* dg = (int*)(D + p->off_gather);  // uploaded with the index structure (e1)
+    e4 = launch_map_gather((double*)(D + o_pose_in), (double*)(D + o_pts_in), (double*)(D + o_uv), mg->d_kf, mg->d_pt, mg->d_uv,
+                             dg, dg + TC, dg + TC + TP, (int)TC, (int)TP, (int)TO, s);
+    ctx->launches++;
+    e5 = up(o_ocam, cam, TO * sizeof(int));
+    e8 = up(o_opt, pt, TO * sizeof(int));
+  } else if (all_sorted) {
     e4 = up(o_uv, uv, TO * 2 * sizeof(double));
     e5 = up(o_ocam, cam, TO * sizeof(int));
     e8 = up(o_opt, pt, TO * sizeof(int));
@@ -1705,4 +1737,332 @@ extern "C" int urmvo_two_view_scored(urmvo_ctx* ctx, int n1, const float* keys1,
   if (rc == URMVO_OK) rc = urmvo_tv_plan_reconstruct(p, T21, P3D, triangulated, mask_H, mask_F, stats, success);
   urmvo_tv_plan_destroy(p);
   return rc;
+}
+
+// =====================================================================================  device-resident map
+//
+// SURVEY.md §8f row 3.  The reference rebuilds the local-BA problem from shared_ptr graphs every keyframe
+// (src/mapping.cc:335-535) and copies every pose, point and keypoint into fresh containers.  Here keyframe
+// poses, mappoint positions and observations stay in HBM across keyframes, addressed by the caller's ids; a
+// window is selected by id lists, its values are gathered on the device, and the optimised poses / points go back
+// into the map on the device.  The host keeps only the INDEX structure (id -> slot, per-point observation lists).
+
+struct urmvo_map {
+  urmvo_ctx* ctx = nullptr;
+  double intr[4] = {0, 0, 0, 0};
+  // id -> slot: frame / mappoint ids are small consecutive integers in the reference (a flat table, no hashing on
+  // the per-keyframe path); ids outside [0, kFlatIds) go through a hash map
+  static constexpr int kFlatIds = 1 << 22;
+  struct IdTable {
+    std::vector<int> flat;
+    std::unordered_map<int, int> big;
+    int find(int id) const {
+      if ((unsigned)id < (unsigned)kFlatIds) return (size_t)id < flat.size() ? flat[id] : -1;
+      auto it = big.find(id);
+      return it == big.end() ? -1 : it->second;
+    }
+    void set(int id, int slot) {
+      if ((unsigned)id < (unsigned)kFlatIds) {
+        if ((size_t)id >= flat.size()) flat.resize(std::max<size_t>((size_t)id + 1, 2 * flat.size()), -1);
+        flat[id] = slot;
+      } else {
+        big[id] = slot;
+      }
+    }
+  };
+  IdTable kf_slot, pt_slot;
+  std::vector<int> kf_ids, pt_ids;                 // slot -> id
+  std::vector<std::vector<int>> pt_obs;            // point slot -> observation slots (insertion order)
+  std::vector<int> obs_kf, obs_pt;                 // observation slot -> keyframe / point slot
+  std::vector<uint8_t> obs_alive;
+  double* d_kf = nullptr; double* d_pt = nullptr; double* d_uv = nullptr;
+  size_t cap_kf = 0, cap_pt = 0, cap_obs = 0;
+  std::vector<int> kf_local;                       // scratch: keyframe slot -> index in the current window or -1
+  std::vector<int> w_kslots, w_pslots, w_oslots, w_cam, w_pt;  // scratch of the window assembly (no reallocation per keyframe)
+};
+
+namespace {
+
+// grow a slot-addressed device array (width W doubles) to hold `need` slots, keeping its contents
+int map_reserve(urmvo_map* m, double** arr, size_t* cap, size_t used, size_t need, int W) {
+  if (need <= *cap) return URMVO_OK;
+  size_t nc = std::max<size_t>(need, std::max<size_t>(2 * *cap, 1024));
+  double* nd = nullptr;
+  if (cudaMalloc(&nd, nc * W * sizeof(double)) != cudaSuccess) return fail(URMVO_ERR_CUDA, "map: cudaMalloc failed");
+  cudaStream_t s = m->ctx->stream;
+  if (*arr && used) {
+    if (cudaMemcpyAsync(nd, *arr, used * W * sizeof(double), cudaMemcpyDeviceToDevice, s) != cudaSuccess ||
+        cudaStreamSynchronize(s) != cudaSuccess) {
+      cudaFree(nd);
+      return fail(URMVO_ERR_CUDA, "map: device copy failed");
+    }
+  }
+  if (*arr) cudaFree(*arr);
+  *arr = nd;
+  *cap = nc;
+  return URMVO_OK;
+}
+
+// values[n * W] into the slots `slots` of a device array: one staged upload + one scatter kernel
+int map_set_rows(urmvo_map* m, double* darr, const std::vector<int>& slots, const double* vals, int W) {
+  const size_t n = slots.size();
+  if (!n) return URMVO_OK;
+  urmvo_ctx* ctx = m->ctx;
+  const size_t vb = n * W * sizeof(double), ib = n * sizeof(int);
+  if (ctx->ensure_pinned(vb + ib)) return fail(URMVO_ERR_CUDA, "map: cudaMallocHost failed");
+  if (ctx->ws_in_use) return fail(URMVO_ERR_ARG, "map: the context workspace is in use by another call");
+  if (ctx->ws_bytes < vb + ib + 256) {
+    if (ctx->ws_dev) cudaFree(ctx->ws_dev);
+    ctx->ws_dev = nullptr; ctx->ws_bytes = 0;
+    const size_t want = std::max(vb + ib + 256, (size_t)1 << 22);
+    if (cudaMalloc(&ctx->ws_dev, want) != cudaSuccess) return fail(URMVO_ERR_CUDA, "map: cudaMalloc failed");
+    ctx->ws_bytes = want;
+  }
+  unsigned char* P = (unsigned char*)ctx->pinned;
+  std::memcpy(P, vals, vb);
+  std::memcpy(P + vb, slots.data(), ib);
+  cudaStream_t s = ctx->stream;
+  CU_TRY(cudaMemcpyAsync(ctx->ws_dev, P, vb + ib, cudaMemcpyHostToDevice, s));
+  CU_TRY(launch_map_set(darr, (const double*)ctx->ws_dev, (const int*)(ctx->ws_dev + vb), (int)n, W, s));
+  ctx->launches++;
+  CU_TRY(cudaStreamSynchronize(s));  // the pinned buffer and the workspace are free again
+  return URMVO_OK;
+}
+
+int map_get_rows(urmvo_map* m, const double* darr, const std::vector<int>& slots, double* vals, int W) {
+  const size_t n = slots.size();
+  if (!n) return URMVO_OK;
+  urmvo_ctx* ctx = m->ctx;
+  const size_t vb = n * W * sizeof(double), ib = n * sizeof(int);
+  if (ctx->ensure_pinned(vb + ib)) return fail(URMVO_ERR_CUDA, "map: cudaMallocHost failed");
+  if (ctx->ws_in_use) return fail(URMVO_ERR_ARG, "map: the context workspace is in use by another call");
+  if (ctx->ws_bytes < vb + ib + 256) {
+    if (ctx->ws_dev) cudaFree(ctx->ws_dev);
+    ctx->ws_dev = nullptr; ctx->ws_bytes = 0;
+    const size_t want = std::max(vb + ib + 256, (size_t)1 << 22);
+    if (cudaMalloc(&ctx->ws_dev, want) != cudaSuccess) return fail(URMVO_ERR_CUDA, "map: cudaMalloc failed");
+    ctx->ws_bytes = want;
+  }
+  unsigned char* P = (unsigned char*)ctx->pinned;
+  std::memcpy(P + vb, slots.data(), ib);
+  cudaStream_t s = ctx->stream;
+  CU_TRY(cudaMemcpyAsync(ctx->ws_dev + vb, P + vb, ib, cudaMemcpyHostToDevice, s));
+  CU_TRY(launch_map_get((double*)ctx->ws_dev, darr, (const int*)(ctx->ws_dev + vb), (int)n, W, s));
+  ctx->launches++;
+  CU_TRY(cudaMemcpyAsync(P, ctx->ws_dev, vb, cudaMemcpyDeviceToHost, s));
+  CU_TRY(cudaStreamSynchronize(s));
+  std::memcpy(vals, P, vb);
+  return URMVO_OK;
+}
+
+}  // namespace
+
+extern "C" int urmvo_map_create(urmvo_ctx* ctx, urmvo_map** out, const double* intr) {
+  try {
+    if (!ctx || !out || !intr) return fail(URMVO_ERR_ARG, "map_create: null argument");
+    urmvo_map* m = new urmvo_map();
+    m->ctx = ctx;
+    for (int k = 0; k < 4; k++) m->intr[k] = intr[k];
+    *out = m;
+    return URMVO_OK;
+  } catch (const std::exception& e) {
+    return fail(URMVO_ERR_ARG, std::string("map_create: ") + e.what());
+  }
+}
+
+extern "C" void urmvo_map_destroy(urmvo_map* m) {
+  if (!m) return;
+  cudaSetDevice(m->ctx->device);
+  if (m->d_kf) cudaFree(m->d_kf);
+  if (m->d_pt) cudaFree(m->d_pt);
+  if (m->d_uv) cudaFree(m->d_uv);
+  delete m;
+}
+
+extern "C" int urmvo_map_set_keyframes(urmvo_map* m, int n, const int32_t* ids, const double* poses) {
+  try {
+    if (!m || n < 0 || (n && (!ids || !poses))) return fail(URMVO_ERR_ARG, "map_set_keyframes: bad argument");
+    CU_TRY(cudaSetDevice(m->ctx->device));
+    std::vector<int> slots(n);
+    for (int i = 0; i < n; i++) {
+      int sl = m->kf_slot.find(ids[i]);
+      if (sl < 0) {
+        sl = (int)m->kf_ids.size();
+        m->kf_slot.set(ids[i], sl);
+        m->kf_ids.push_back(ids[i]);
+      }
+      slots[i] = sl;
+    }
+    if (int rc = map_reserve(m, &m->d_kf, &m->cap_kf, std::min(m->kf_ids.size(), m->cap_kf), m->kf_ids.size(), 7)) return rc;
+    return map_set_rows(m, m->d_kf, slots, poses, 7);
+  } catch (const std::exception& e) {
+    return fail(URMVO_ERR_ARG, std::string("map_set_keyframes: ") + e.what());
+  }
+}
+
+extern "C" int urmvo_map_set_points(urmvo_map* m, int n, const int32_t* ids, const double* xyz) {
+  try {
+    if (!m || n < 0 || (n && (!ids || !xyz))) return fail(URMVO_ERR_ARG, "map_set_points: bad argument");
+    CU_TRY(cudaSetDevice(m->ctx->device));
+    std::vector<int> slots(n);
+    for (int i = 0; i < n; i++) {
+      int sl = m->pt_slot.find(ids[i]);
+      if (sl < 0) {
+        sl = (int)m->pt_ids.size();
+        m->pt_slot.set(ids[i], sl);
+        m->pt_ids.push_back(ids[i]);
+        m->pt_obs.emplace_back();
+      }
+      slots[i] = sl;
+    }
+    if (int rc = map_reserve(m, &m->d_pt, &m->cap_pt, std::min(m->pt_ids.size(), m->cap_pt), m->pt_ids.size(), 3)) return rc;
+    return map_set_rows(m, m->d_pt, slots, xyz, 3);
+  } catch (const std::exception& e) {
+    return fail(URMVO_ERR_ARG, std::string("map_set_points: ") + e.what());
+  }
+}
+
+extern "C" int urmvo_map_add_observations(urmvo_map* m, int n, const int32_t* kf_ids, const int32_t* pt_ids, const double* uv) {
+  try {
+    if (!m || n < 0 || (n && (!kf_ids || !pt_ids || !uv))) return fail(URMVO_ERR_ARG, "map_add_observations: bad argument");
+    CU_TRY(cudaSetDevice(m->ctx->device));
+    for (int i = 0; i < n; i++)
+      if (m->kf_slot.find(kf_ids[i]) < 0 || m->pt_slot.find(pt_ids[i]) < 0)
+        return fail(URMVO_ERR_ARG, "map_add_observations: unknown keyframe or mappoint id");
+    const size_t first = m->obs_kf.size();
+    if (int rc = map_reserve(m, &m->d_uv, &m->cap_obs, std::min(first, m->cap_obs), first + n, 2)) return rc;
+    std::vector<int> slots(n);
+    for (int i = 0; i < n; i++) {
+      const int ks = m->kf_slot.find(kf_ids[i]), ps = m->pt_slot.find(pt_ids[i]);
+      slots[i] = (int)(first + i);
+      m->obs_kf.push_back(ks);
+      m->obs_pt.push_back(ps);
+      m->obs_alive.push_back(1);
+      m->pt_obs[ps].push_back(slots[i]);
+    }
+    return map_set_rows(m, m->d_uv, slots, uv, 2);
+  } catch (const std::exception& e) {
+    return fail(URMVO_ERR_ARG, std::string("map_add_observations: ") + e.what());
+  }
+}
+
+extern "C" int urmvo_map_remove_observations(urmvo_map* m, int n, const int32_t* kf_ids, const int32_t* pt_ids) {
+  try {
+    if (!m || n < 0 || (n && (!kf_ids || !pt_ids))) return fail(URMVO_ERR_ARG, "map_remove_observations: bad argument");
+    for (int i = 0; i < n; i++) {
+      const int ks = m->kf_slot.find(kf_ids[i]), ps = m->pt_slot.find(pt_ids[i]);
+      if (ks < 0 || ps < 0) continue;  // like erasing an absent observer: no-op
+      std::vector<int>& lst = m->pt_obs[ps];
+      for (size_t k = 0; k < lst.size(); k++)
+        if (m->obs_kf[lst[k]] == ks && m->obs_alive[lst[k]]) {
+          m->obs_alive[lst[k]] = 0;
+          lst.erase(lst.begin() + k);
+          break;
+        }
+    }
+    return URMVO_OK;
+  } catch (const std::exception& e) {
+    return fail(URMVO_ERR_ARG, std::string("map_remove_observations: ") + e.what());
+  }
+}
+
+extern "C" int urmvo_map_get_keyframes(urmvo_map* m, int n, const int32_t* ids, double* poses) {
+  try {
+    if (!m || n < 0 || (n && (!ids || !poses))) return fail(URMVO_ERR_ARG, "map_get_keyframes: bad argument");
+    CU_TRY(cudaSetDevice(m->ctx->device));
+    std::vector<int> slots(n);
+    for (int i = 0; i < n; i++) {
+      slots[i] = m->kf_slot.find(ids[i]);
+      if (slots[i] < 0) return fail(URMVO_ERR_ARG, "map_get_keyframes: unknown id");
+    }
+    return map_get_rows(m, m->d_kf, slots, poses, 7);
+  } catch (const std::exception& e) {
+    return fail(URMVO_ERR_ARG, std::string("map_get_keyframes: ") + e.what());
+  }
+}
+
+extern "C" int urmvo_map_get_points(urmvo_map* m, int n, const int32_t* ids, double* xyz) {
+  try {
+    if (!m || n < 0 || (n && (!ids || !xyz))) return fail(URMVO_ERR_ARG, "map_get_points: bad argument");
+    CU_TRY(cudaSetDevice(m->ctx->device));
+    std::vector<int> slots(n);
+    for (int i = 0; i < n; i++) {
+      slots[i] = m->pt_slot.find(ids[i]);
+      if (slots[i] < 0) return fail(URMVO_ERR_ARG, "map_get_points: unknown id");
+    }
+    return map_get_rows(m, m->d_pt, slots, xyz, 3);
+  } catch (const std::exception& e) {
+    return fail(URMVO_ERR_ARG, std::string("map_get_points: ") + e.what());
+  }
+}
+
+extern "C" int urmvo_map_local_ba(urmvo_map* m, int n_kf, const int32_t* kf_ids, const uint8_t* kf_fixed, int n_pt,
+                                  const int32_t* pt_ids, double chi2_thr, int it0, int it1, const urmvo_ba_options* opts,
+                                  int32_t max_obs, int32_t* n_obs, int32_t* obs_kf, int32_t* obs_pt, uint8_t* inlier,
+                                  urmvo_ba_stats* stats) {
+  try {
+    if (!m || n_kf <= 0 || n_pt < 0 || !kf_ids || !kf_fixed || (n_pt && !pt_ids) || !n_obs)
+      return fail(URMVO_ERR_ARG, "map_local_ba: bad argument");
+    urmvo_ctx* ctx = m->ctx;
+    CU_TRY(cudaSetDevice(ctx->device));
+    *n_obs = 0;
+    // ---- the window: index structure only, from the host mirror
+    std::vector<int>&kslots = m->w_kslots, &pslots = m->w_pslots, &oslots = m->w_oslots, &cam = m->w_cam, &pt = m->w_pt;
+    kslots.assign(n_kf, 0); pslots.clear(); oslots.clear(); cam.clear(); pt.clear();
+    m->kf_local.assign(m->kf_ids.size(), -1);
+    for (int i = 0; i < n_kf; i++) {
+      const int sl = m->kf_slot.find(kf_ids[i]);
+      if (sl < 0) return fail(URMVO_ERR_ARG, "map_local_ba: unknown keyframe id");
+      if (m->kf_local[sl] >= 0) return fail(URMVO_ERR_ARG, "map_local_ba: keyframe listed twice");
+      m->kf_local[sl] = i;
+      kslots[i] = sl;
+    }
+    for (int l = 0; l < n_pt; l++) {
+      const int ps = m->pt_slot.find(pt_ids[l]);
+      if (ps < 0) return fail(URMVO_ERR_ARG, "map_local_ba: unknown mappoint id");
+      const std::vector<int>& lst = m->pt_obs[ps];
+      const size_t first = oslots.size();
+      for (int os : lst) {
+        const int c = m->kf_local[m->obs_kf[os]];
+        if (c < 0) continue;
+        oslots.push_back(os);
+        cam.push_back(c);
+        pt.push_back((int)pslots.size());
+      }
+      // mono mappoints enter the optimisation with more than one constraint (reference src/mapping.cc:463-465)
+      if (oslots.size() - first < 2) { oslots.resize(first); cam.resize(first); pt.resize(first); continue; }
+      pslots.push_back(ps);
+    }
+    const int No = (int)oslots.size(), Np = (int)pslots.size();
+    if (No == 0) return URMVO_OK;  // empty graph: nothing to optimise (g2o: silent no-op)
+    if (No > max_obs || !obs_kf || !obs_pt || !inlier)
+      return fail(URMVO_ERR_ARG, "map_local_ba: observation outputs too small (max_obs) or null");
+    const int32_t co[2] = {0, n_kf}, po[2] = {0, Np}, oo[2] = {0, No};
+    MapGather mg{m->d_kf, m->d_pt, m->d_uv, kslots.data(), pslots.data(), oslots.data()};
+    urmvo_ba_plan* p = nullptr;
+    int rc = ba_plan_create_impl(ctx, &p, 1, co, po, oo, nullptr, kf_fixed, nullptr, nullptr, cam.data(), pt.data(), m->intr,
+                                 chi2_thr, it0, it1, opts, false, nullptr, /*borrow_ws=*/true, nullptr, 0.0, &mg);
+    if (rc != URMVO_OK) return rc;
+    rc = urmvo_ba_plan_run(p);
+    if (rc == URMVO_OK) {
+      const int* dg = (const int*)(p->dev + p->off_gather);
+      const cudaError_t e = launch_map_scatter(m->d_kf, m->d_pt, (const double*)(p->dev + p->off_pose_out),
+                                               (const double*)(p->dev + p->off_pts_out), (const int*)(p->dev + p->off_cam_free),
+                                               dg, dg + n_kf, n_kf, Np, ctx->stream);
+      ctx->launches++;
+      if (e != cudaSuccess) rc = fail(URMVO_ERR_CUDA, std::string("map_local_ba scatter: ") + cudaGetErrorString(e));
+    }
+    if (rc == URMVO_OK) rc = urmvo_ba_plan_download(p, nullptr, nullptr, inlier, stats);
+    urmvo_ba_plan_destroy(p);
+    if (rc != URMVO_OK) return rc;
+    for (int o = 0; o < No; o++) {
+      obs_kf[o] = m->kf_ids[m->obs_kf[oslots[o]]];
+      obs_pt[o] = m->pt_ids[m->obs_pt[oslots[o]]];
+    }
+    *n_obs = No;
+    return URMVO_OK;
+  } catch (const std::exception& e) {
+    if (m && m->ctx) m->ctx->ws_in_use = false;
+    return fail(URMVO_ERR_ARG, std::string("map_local_ba: ") + e.what());
+  }
 }

@@ -120,6 +120,15 @@ cudaError_t launch_fm_score(int n_hyp, const int* hyp_ids, int max_iters, const 
 cudaError_t launch_fm_mask(int B, int max_n, const int* off, const float4* pts, const double* models_all,
                            const int* win_id, float thr2, uint8_t* mask, double* win_F, cudaStream_t s);
 
+// ---- map_kernels.cu (device-resident map: slot-addressed keyframe / mappoint / observation arrays)
+cudaError_t launch_map_gather(double* pose_in, double* pts_in, double* uv, const double* d_kf, const double* d_pt,
+                              const double* d_uv, const int* kf_slot, const int* pt_slot, const int* obs_slot, int Nc,
+                              int Np, int No, cudaStream_t s);
+cudaError_t launch_map_scatter(double* d_kf, double* d_pt, const double* pose_out, const double* pts_out, const int* cam_free,
+                               const int* kf_slot, const int* pt_slot, int Nc, int Np, cudaStream_t s);
+cudaError_t launch_map_set(double* dst, const double* vals, const int* slot, int n, int W, cudaStream_t s);
+cudaError_t launch_map_get(double* vals, const double* src, const int* slot, int n, int W, cudaStream_t s);
+
 // ---- pnp_kernels.cu (SolvePnPWithCV: EPnP RANSAC hypotheses, inlier counting, refinement over the inliers).
 // H = B * max_iters hypotheses; sets [H][5] indices local to the problem; models [H][12] = R | t (T_cw);
 // masks [H][words_max]; counts[h] = inliers or -1 (no model).

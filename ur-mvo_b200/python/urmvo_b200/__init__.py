@@ -7,8 +7,8 @@ run anywhere), but creating a Context without a usable B200 raises.
 """
 from .capi import (Context, BAPlan, PosePlan, TVPlan, ShardedBAPlan, BAStats, TVStats, BAOptions, UrmvoError,
                    lib_path, load_library, build_library, EXPORTED_SYMBOLS, nccl_unique_id, ba_covisibility,
-                   shard_points, pack_ba_batch, FMPlan, FMStats, pack_fm_batch)
+                   shard_points, pack_ba_batch, FMPlan, FMStats, pack_fm_batch, DeviceMap, PnPStats)
 
 __all__ = ["Context", "BAPlan", "PosePlan", "TVPlan", "ShardedBAPlan", "nccl_unique_id", "ba_covisibility",
            "shard_points", "pack_ba_batch", "FMPlan", "FMStats", "pack_fm_batch", "BAStats", "TVStats", "BAOptions", "UrmvoError",
-           "lib_path", "load_library", "build_library", "EXPORTED_SYMBOLS"]
+           "lib_path", "load_library", "build_library", "EXPORTED_SYMBOLS", "DeviceMap", "PnPStats"]

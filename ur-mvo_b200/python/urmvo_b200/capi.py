@@ -18,6 +18,8 @@ EXPORTED_SYMBOLS = [
     "urmvo_fm_ransac", "urmvo_fm_ransac_batch", "urmvo_fm_plan_create", "urmvo_fm_plan_run", "urmvo_fm_plan_finish",
     "urmvo_fm_plan_hypotheses", "urmvo_fm_plan_destroy", "urmvo_triangulate_batch",
     "urmvo_pnp_ransac", "urmvo_pnp_ransac_batch",
+    "urmvo_map_create", "urmvo_map_destroy", "urmvo_map_set_keyframes", "urmvo_map_set_points", "urmvo_map_add_observations",
+    "urmvo_map_remove_observations", "urmvo_map_get_keyframes", "urmvo_map_get_points", "urmvo_map_local_ba",
 ]
 
 
@@ -79,10 +81,10 @@ def load_library():
             f = getattr(L, name)
             if name not in ("urmvo_last_error", "urmvo_stream", "urmvo_launch_count", "urmvo_destroy",
                             "urmvo_ba_plan_destroy", "urmvo_pose_plan_destroy", "urmvo_tv_plan_destroy",
-                            "urmvo_fm_plan_destroy"):
+                            "urmvo_fm_plan_destroy", "urmvo_map_destroy"):
                 f.restype = C.c_int
         for name in ("urmvo_destroy", "urmvo_ba_plan_destroy", "urmvo_pose_plan_destroy", "urmvo_tv_plan_destroy",
-                     "urmvo_fm_plan_destroy"):
+                     "urmvo_fm_plan_destroy", "urmvo_map_destroy"):
             getattr(L, name).restype = None
         _LIB = L
     return _LIB
@@ -558,6 +560,69 @@ class TVPlan:
     def close(self):
         if self._h:
             self._L.urmvo_tv_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DeviceMap:
+    """Device-resident map (urmvo_map_*): keyframe poses, mappoint positions and observations stay in HBM across
+    keyframes; windows are selected by id lists."""
+
+    def __init__(self, ctx, intr):
+        self._L = ctx._L
+        self.ctx = ctx
+        self._h = C.c_void_p()
+        _check(self._L.urmvo_map_create(ctx._h, C.byref(self._h), _p(_f64(intr))), "urmvo_map_create")
+
+    def set_keyframes(self, ids, poses):
+        ids = _i32(ids); poses = _f64(poses)
+        _check(self._L.urmvo_map_set_keyframes(self._h, C.c_int(len(ids)), _p(ids), _p(poses)), "urmvo_map_set_keyframes")
+
+    def set_points(self, ids, xyz):
+        ids = _i32(ids); xyz = _f64(xyz)
+        _check(self._L.urmvo_map_set_points(self._h, C.c_int(len(ids)), _p(ids), _p(xyz)), "urmvo_map_set_points")
+
+    def add_observations(self, kf_ids, pt_ids, uv):
+        kf_ids = _i32(kf_ids); pt_ids = _i32(pt_ids); uv = _f64(uv)
+        _check(self._L.urmvo_map_add_observations(self._h, C.c_int(len(kf_ids)), _p(kf_ids), _p(pt_ids), _p(uv)),
+               "urmvo_map_add_observations")
+
+    def remove_observations(self, kf_ids, pt_ids):
+        kf_ids = _i32(kf_ids); pt_ids = _i32(pt_ids)
+        _check(self._L.urmvo_map_remove_observations(self._h, C.c_int(len(kf_ids)), _p(kf_ids), _p(pt_ids)),
+               "urmvo_map_remove_observations")
+
+    def get_keyframes(self, ids):
+        ids = _i32(ids); out = np.zeros((len(ids), 7))
+        _check(self._L.urmvo_map_get_keyframes(self._h, C.c_int(len(ids)), _p(ids), _p(out)), "urmvo_map_get_keyframes")
+        return out
+
+    def get_points(self, ids):
+        ids = _i32(ids); out = np.zeros((len(ids), 3))
+        _check(self._L.urmvo_map_get_points(self._h, C.c_int(len(ids)), _p(ids), _p(out)), "urmvo_map_get_points")
+        return out
+
+    def local_ba(self, kf_ids, kf_fixed, pt_ids, max_obs, chi2_thr=10.0, it0=10, it1=5, opts=None):
+        """Returns (obs_kf, obs_pt, inlier, stats) of the observations used; the map holds the optimised values."""
+        kf_ids = _i32(kf_ids); kf_fixed = _u8(kf_fixed); pt_ids = _i32(pt_ids)
+        n = C.c_int32(0)
+        okf = np.zeros(max_obs, dtype=np.int32); opt = np.zeros(max_obs, dtype=np.int32); inl = np.zeros(max_obs, dtype=np.uint8)
+        st = BAStats()
+        _check(self._L.urmvo_map_local_ba(self._h, C.c_int(len(kf_ids)), _p(kf_ids), _p(kf_fixed), C.c_int(len(pt_ids)), _p(pt_ids),
+                                          C.c_double(chi2_thr), C.c_int(it0), C.c_int(it1),
+                                          C.byref(opts) if opts is not None else None, C.c_int32(max_obs), C.byref(n),
+                                          _p(okf), _p(opt), _p(inl), C.byref(st)), "urmvo_map_local_ba")
+        k = n.value
+        return okf[:k], opt[:k], inl[:k], st
+
+    def close(self):
+        if self._h:
+            self._L.urmvo_map_destroy(self._h)
             self._h = C.c_void_p()
 
     def __del__(self):
