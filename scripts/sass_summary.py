@@ -9,7 +9,7 @@ hist, cur = collections.OrderedDict(), None
 for line in out.split("\n"):
     m = re.match(r"\s+Function : (\S+)", line)
     if m:
-        cur = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip().split("(")[0]
+        cur = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip().replace("(anonymous namespace)::", "").split("(")[0]
         hist[cur] = collections.Counter()
         continue
     m = re.match(r"\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+)", line)
