@@ -123,6 +123,24 @@ int urmvo_local_ba_batch_stereo(urmvo_ctx* ctx, int B, const int32_t* cam_off, c
                                 const double* intr5, double chi2_thr_mono, double chi2_thr_stereo, int it0, int it1,
                                 uint8_t* inlier, urmvo_ba_stats* stats, const urmvo_ba_options* opts);
 
+/* The same two calls with SEVERAL camera models in one graph.  The reference reads fx, fy, cx, cy (and BF) per
+ * constraint from camera_list[mpc->id_camera] (src/g2o_optimization.cc:86-89, :106-113); the calls above take one
+ * intrinsics set, which is what every configuration of the reference has (one camera).  Here intr5_tab holds
+ * n_models (1..128) rows of (fx, fy, cx, cy, bf) and kind_model[o] = (1 if stereo edge, else 0) | (id_camera << 1);
+ * everything else as in the stereo calls (a mono rig passes bf = 0 and no stereo bit).  These windows run on the
+ * one-point-per-warp accumulation modes (the packed / tile modes are single-camera). */
+int urmvo_local_ba_multicam(urmvo_ctx* ctx, int Nc, double* poses, const uint8_t* fixed, int Np, double* pts,
+                            int No, const double* uv3, const uint8_t* kind_model, const int32_t* cam,
+                            const int32_t* pt, int n_models, const double* intr5_tab, double chi2_thr_mono,
+                            double chi2_thr_stereo, int it0, int it1, uint8_t* inlier, urmvo_ba_stats* stats,
+                            const urmvo_ba_options* opts);
+int urmvo_local_ba_batch_multicam(urmvo_ctx* ctx, int B, const int32_t* cam_off, const int32_t* pt_off,
+                                  const int32_t* obs_off, double* poses, const uint8_t* fixed, double* pts,
+                                  const double* uv3, const uint8_t* kind_model, const int32_t* cam,
+                                  const int32_t* pt, int n_models, const double* intr5_tab, double chi2_thr_mono,
+                                  double chi2_thr_stereo, int it0, int it1, uint8_t* inlier, urmvo_ba_stats* stats,
+                                  const urmvo_ba_options* opts);
+
 /* Plan API: upload once, run many times from HBM-resident inputs (each run restarts from the
  * uploaded initial estimate), download when wanted. */
 int urmvo_ba_plan_create(urmvo_ctx* ctx, urmvo_ba_plan** plan, int B, const int32_t* cam_off,
@@ -188,6 +206,13 @@ int urmvo_pose_only_batch_stereo(urmvo_ctx* ctx, int B, const int32_t* obs_off, 
                                  const double* uv3, const uint8_t* kind, const double* Xw, const double* intr5,
                                  double chi2_thr_mono, double chi2_thr_stereo, int rounds, int its_per_round,
                                  uint8_t* inlier, int32_t* n_inlier);
+
+/* Per-constraint camera models (camera_list[mpc->id_camera], src/g2o_optimization.cc:221-224, :243-250): intr5_tab
+ * and kind_model as in urmvo_local_ba_multicam. */
+int urmvo_pose_only_batch_multicam(urmvo_ctx* ctx, int B, const int32_t* obs_off, double* poses,
+                                   const double* uv3, const uint8_t* kind_model, const double* Xw, int n_models,
+                                   const double* intr5_tab, double chi2_thr_mono, double chi2_thr_stereo,
+                                   int rounds, int its_per_round, uint8_t* inlier, int32_t* n_inlier);
 
 int urmvo_pose_plan_create(urmvo_ctx* ctx, urmvo_pose_plan** plan, int B, const int32_t* obs_off,
                            const double* poses, const double* uv, const double* Xw,

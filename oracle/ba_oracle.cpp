@@ -325,6 +325,13 @@ enum SolveResult { kOK = 0, kTerminate = 1 };
 struct BAProblem {
   int Nc, Np, No;
   Intr K;
+  // several camera models in one graph (camera_list[mpc->id_camera], src/g2o_optimization.cc:86-89): per-edge index
+  // into (Ks, bfs); empty = every edge uses (K, bf)
+  std::vector<Intr> Ks;
+  std::vector<double> bfs;
+  std::vector<uint8_t> model;
+  const Intr& Kof(int o) const { return model.empty() ? K : Ks[model[o]]; }
+  double bfof(int o) const { return model.empty() ? bf : bfs[model[o]]; }
   std::vector<SE3> cams;         // T_cw
   std::vector<uint8_t> fixed;
   std::vector<int> cam_free_idx;  // dense index among non-fixed cams or -1
@@ -366,7 +373,7 @@ double ba_compute_errors(BAProblem& P) {
     int c = P.ocam[o];
     map_point(&P.Rcache[(size_t)c * 9], P.cams[c].t, &P.pts[(size_t)P.opt[o] * 3], pc);
     double* e = &P.err[(size_t)o * 3];
-    edge_error3(pc, &P.uv3[(size_t)o * 3], P.kind[o], P.K, P.bf, e);
+    edge_error3(pc, &P.uv3[(size_t)o * 3], P.kind[o], P.Kof(o), P.bfof(o), e);
     double e2 = e[0] * e[0] + e[1] * e[1] + e[2] * e[2];
     if (P.robust) {
       double rho[3];
@@ -391,7 +398,7 @@ void ba_build_system(BAProblem& P) {
     const double* R = &P.Rcache[(size_t)c * 9];
     double pc[3], Jp[18], Jx[9];
     map_point(R, P.cams[c].t, &P.pts[(size_t)l * 3], pc);
-    edge_jac3(R, pc, P.kind[o], P.K, P.bf, Jp, Jx);
+    edge_jac3(R, pc, P.kind[o], P.Kof(o), P.bfof(o), Jp, Jx);
     const double* e = &P.err[(size_t)o * 3];
     double w = 1.0;
     if (P.robust) {
@@ -632,16 +639,25 @@ int ba_optimize(BAProblem& P, int n_iter, urmvo_oracle_stats* st, double* chi_ou
 void ba_setup(BAProblem& P, int Nc, const double* poses, const uint8_t* fixed, int Np,
               const double* pts, int No, const double* uv, int uv_stride, const uint8_t* kind,
               const int32_t* cam, const int32_t* pt, const double* intr, double bf, double chi2_thr,
-              double chi2_thr_stereo) {
+              double chi2_thr_stereo, int n_models = 0) {
   P.Nc = Nc; P.Np = Np; P.No = No;
   P.K = Intr{intr[0], intr[1], intr[2], intr[3]};
   P.bf = bf;
   P.uv3.assign((size_t)No * 3, 0.0);
   P.kind.assign(No, 0);
+  if (n_models > 0) {  // intr = n_models rows of (fx fy cx cy bf); kind[o] = stereo bit | model << 1
+    for (int m = 0; m < n_models; m++) {
+      P.Ks.push_back(Intr{intr[m * 5], intr[m * 5 + 1], intr[m * 5 + 2], intr[m * 5 + 3]});
+      P.bfs.push_back(intr[m * 5 + 4]);
+    }
+    P.model.assign(No, 0);
+  }
   for (int o = 0; o < No; o++) {
     P.uv3[(size_t)o * 3] = uv[(size_t)o * uv_stride];
     P.uv3[(size_t)o * 3 + 1] = uv[(size_t)o * uv_stride + 1];
-    if (uv_stride == 3 && kind && kind[o]) { P.uv3[(size_t)o * 3 + 2] = uv[(size_t)o * 3 + 2]; P.kind[o] = 1; }
+    const bool st = uv_stride == 3 && kind && (n_models > 0 ? (kind[o] & 1) : kind[o]);
+    if (st) { P.uv3[(size_t)o * 3 + 2] = uv[(size_t)o * 3 + 2]; P.kind[o] = 1; }
+    if (n_models > 0) P.model[o] = kind ? (uint8_t)(kind[o] >> 1) : 0;
   }
   P.cams.resize(Nc);
   P.fixed.assign(fixed, fixed + Nc);
@@ -688,7 +704,7 @@ static int local_ba_impl(int Nc, double* poses, const uint8_t* fixed, int Np, do
                          const double* uv, int uv_stride, const uint8_t* kind, const int32_t* cam,
                          const int32_t* pt, const double* intr, double bf, double chi2_thr,
                          double chi2_thr_stereo, int it0, int it1, uint8_t* inlier,
-                         urmvo_oracle_stats* stats);
+                         urmvo_oracle_stats* stats, int n_models = 0);
 
 extern "C" int urmvo_oracle_local_ba(int Nc, double* poses, const uint8_t* fixed, int Np,
                                      double* pts, int No, const double* uv, const int32_t* cam,
@@ -710,14 +726,30 @@ extern "C" int urmvo_oracle_local_ba_stereo(int Nc, double* poses, const uint8_t
                        chi2_thr_stereo, it0, it1, inlier, stats);
 }
 
+// Several camera models in one graph: the reference reads fx, fy, cx, cy (and BF) per constraint from
+// camera_list[mpc->id_camera] (src/g2o_optimization.cc:86-89, :106-113).  intr5_tab = n_models rows of
+// (fx fy cx cy bf); kind_model[o] = (1 if stereo edge) | (camera model index << 1).
+extern "C" int urmvo_oracle_local_ba_multicam(int Nc, double* poses, const uint8_t* fixed, int Np, double* pts,
+                                              int No, const double* uv3, const uint8_t* kind_model,
+                                              const int32_t* cam, const int32_t* pt, int n_models,
+                                              const double* intr5_tab, double chi2_thr_mono,
+                                              double chi2_thr_stereo, int it0, int it1, uint8_t* inlier,
+                                              urmvo_oracle_stats* stats) {
+  if (n_models <= 0 || n_models > 128) return -1;
+  for (int o = 0; o < No; o++)
+    if ((kind_model[o] >> 1) >= n_models) return -1;
+  return local_ba_impl(Nc, poses, fixed, Np, pts, No, uv3, 3, kind_model, cam, pt, intr5_tab, intr5_tab[4],
+                       chi2_thr_mono, chi2_thr_stereo, it0, it1, inlier, stats, n_models);
+}
+
 static int local_ba_impl(int Nc, double* poses, const uint8_t* fixed, int Np, double* pts, int No,
                          const double* uv, int uv_stride, const uint8_t* kind, const int32_t* cam,
                          const int32_t* pt, const double* intr, double bf, double chi2_thr,
                          double chi2_thr_stereo, int it0, int it1, uint8_t* inlier,
-                         urmvo_oracle_stats* stats) {
+                         urmvo_oracle_stats* stats, int n_models) {
   if (stats) std::memset(stats, 0, sizeof(*stats));
   BAProblem P;
-  ba_setup(P, Nc, poses, fixed, Np, pts, No, uv, uv_stride, kind, cam, pt, intr, bf, chi2_thr, chi2_thr_stereo);
+  ba_setup(P, Nc, poses, fixed, Np, pts, No, uv, uv_stride, kind, cam, pt, intr, bf, chi2_thr, chi2_thr_stereo, n_models);
   // :125-126 initializeOptimization(); optimize(10)  — Huber on every edge
   P.robust = true;
   double chi = 0;
@@ -755,6 +787,11 @@ namespace {
 struct PoseProblem {
   int No;
   Intr K;
+  std::vector<Intr> Ks;  // per-edge camera models, see BAProblem
+  std::vector<double> bfs;
+  std::vector<uint8_t> model;
+  const Intr& Kof(int o) const { return model.empty() ? K : Ks[model[o]]; }
+  double bfof(int o) const { return model.empty() ? bf : bfs[model[o]]; }
   SE3 T;  // T_cw
   std::vector<double> uv3;
   std::vector<uint8_t> kind;
@@ -777,7 +814,7 @@ double po_compute_errors(PoseProblem& P) {
     double pc[3];
     map_point(R, P.T.t, &P.Xw[(size_t)o * 3], pc);
     double* e = &P.err[(size_t)o * 3];
-    edge_error3(pc, &P.uv3[(size_t)o * 3], P.kind[o], P.K, P.bf, e);
+    edge_error3(pc, &P.uv3[(size_t)o * 3], P.kind[o], P.Kof(o), P.bfof(o), e);
     double e2 = e[0] * e[0] + e[1] * e[1] + e[2] * e[2];
     if (P.robust[o]) {
       double rho[3];
@@ -799,7 +836,7 @@ void po_build(PoseProblem& P) {
     if (P.level[o]) continue;
     double pc[3], Jp[18];
     map_point(R, P.T.t, &P.Xw[(size_t)o * 3], pc);
-    edge_jac3(R, pc, P.kind[o], P.K, P.bf, Jp, nullptr);
+    edge_jac3(R, pc, P.kind[o], P.Kof(o), P.bfof(o), Jp, nullptr);
     const double* e = &P.err[(size_t)o * 3];
     double w = 1.0;
     if (P.robust[o]) {
@@ -903,7 +940,7 @@ int po_optimize(PoseProblem& P, int n_iter, urmvo_oracle_stats* st, double* chi_
 static int pose_only_impl(double* pose, int No, const double* uv, int uv_stride, const uint8_t* kind,
                           const double* Xw, const double* intr, double bf, double chi2_thr,
                           double chi2_thr_stereo, int rounds, int its_per_round, uint8_t* inlier,
-                          urmvo_oracle_stats* stats);
+                          urmvo_oracle_stats* stats, int n_models = 0);
 
 extern "C" int urmvo_oracle_pose_only(double* pose, int No, const double* uv, const double* Xw,
                                       const double* intr, double chi2_thr, int rounds,
@@ -923,10 +960,23 @@ extern "C" int urmvo_oracle_pose_only_stereo(double* pose, int No, const double*
                         its_per_round, inlier, stats);
 }
 
+// Per-constraint camera models (camera_list[mpc->id_camera], src/g2o_optimization.cc:221-224, :243-250); same
+// encoding as urmvo_oracle_local_ba_multicam.
+extern "C" int urmvo_oracle_pose_only_multicam(double* pose, int No, const double* uv3, const uint8_t* kind_model,
+                                               const double* Xw, int n_models, const double* intr5_tab,
+                                               double chi2_thr_mono, double chi2_thr_stereo, int rounds,
+                                               int its_per_round, uint8_t* inlier, urmvo_oracle_stats* stats) {
+  if (n_models <= 0 || n_models > 128) return -1;
+  for (int o = 0; o < No; o++)
+    if ((kind_model[o] >> 1) >= n_models) return -1;
+  return pose_only_impl(pose, No, uv3, 3, kind_model, Xw, intr5_tab, intr5_tab[4], chi2_thr_mono, chi2_thr_stereo,
+                        rounds, its_per_round, inlier, stats, n_models);
+}
+
 static int pose_only_impl(double* pose, int No, const double* uv, int uv_stride, const uint8_t* kind,
                           const double* Xw, const double* intr, double bf, double chi2_thr,
                           double chi2_thr_stereo, int rounds, int its_per_round, uint8_t* inlier,
-                          urmvo_oracle_stats* stats) {
+                          urmvo_oracle_stats* stats, int n_models) {
   if (stats) std::memset(stats, 0, sizeof(*stats));
   PoseProblem P;
   P.No = No;
@@ -934,10 +984,19 @@ static int pose_only_impl(double* pose, int No, const double* uv, int uv_stride,
   P.bf = bf;
   P.uv3.assign((size_t)No * 3, 0.0);
   P.kind.assign(No, 0);
+  if (n_models > 0) {
+    for (int m = 0; m < n_models; m++) {
+      P.Ks.push_back(Intr{intr[m * 5], intr[m * 5 + 1], intr[m * 5 + 2], intr[m * 5 + 3]});
+      P.bfs.push_back(intr[m * 5 + 4]);
+    }
+    P.model.assign(No, 0);
+  }
   for (int o = 0; o < No; o++) {
     P.uv3[(size_t)o * 3] = uv[(size_t)o * uv_stride];
     P.uv3[(size_t)o * 3 + 1] = uv[(size_t)o * uv_stride + 1];
-    if (uv_stride == 3 && kind && kind[o]) { P.uv3[(size_t)o * 3 + 2] = uv[(size_t)o * 3 + 2]; P.kind[o] = 1; }
+    const bool st = uv_stride == 3 && kind && (n_models > 0 ? (kind[o] & 1) : kind[o]);
+    if (st) { P.uv3[(size_t)o * 3 + 2] = uv[(size_t)o * 3 + 2]; P.kind[o] = 1; }
+    if (n_models > 0) P.model[o] = kind ? (uint8_t)(kind[o] >> 1) : 0;
   }
   P.Xw = Xw;
   P.level.assign(No, 0);
@@ -961,7 +1020,7 @@ static int pose_only_impl(double* pose, int No, const double* uv, int uv_stride,
       if (!inlier[o]) {  // :273-275 e->computeError() at the current estimate
         double pc[3];
         map_point(R, P.T.t, &Xw[(size_t)o * 3], pc);
-        edge_error3(pc, &P.uv3[(size_t)o * 3], P.kind[o], P.K, P.bf, &P.err[(size_t)o * 3]);
+        edge_error3(pc, &P.uv3[(size_t)o * 3], P.kind[o], P.Kof(o), P.bfof(o), &P.err[(size_t)o * 3]);
       }
       const double* e = &P.err[(size_t)o * 3];
       const float chi2 = (float)(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);  // :277 / :297

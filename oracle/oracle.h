@@ -75,6 +75,19 @@ int urmvo_oracle_local_ba_stereo(int Nc, double* poses, const uint8_t* fixed, in
 int urmvo_oracle_pose_only_stereo(double* pose, int No, const double* uv3, const uint8_t* kind, const double* Xw,
                                   const double* intr5, double chi2_thr_mono, double chi2_thr_stereo, int rounds,
                                   int its_per_round, uint8_t* inlier, urmvo_oracle_stats* stats);
+/* Several camera models in one graph: the reference reads the intrinsics per constraint from
+ * camera_list[mpc->id_camera] (src/g2o_optimization.cc:86-89, :106-113, :221-224, :243-250).  intr5_tab = n_models
+ * rows of (fx fy cx cy bf), kind_model[o] = (1 if stereo edge) | (camera model index << 1), n_models <= 128.
+ * Return -1 on a bad model index. */
+int urmvo_oracle_local_ba_multicam(int Nc, double* poses, const uint8_t* fixed, int Np, double* pts, int No,
+                                   const double* uv3, const uint8_t* kind_model, const int32_t* cam,
+                                   const int32_t* pt, int n_models, const double* intr5_tab, double chi2_thr_mono,
+                                   double chi2_thr_stereo, int it0, int it1, uint8_t* inlier,
+                                   urmvo_oracle_stats* stats);
+int urmvo_oracle_pose_only_multicam(double* pose, int No, const double* uv3, const uint8_t* kind_model,
+                                    const double* Xw, int n_models, const double* intr5_tab, double chi2_thr_mono,
+                                    double chi2_thr_stereo, int rounds, int its_per_round, uint8_t* inlier,
+                                    urmvo_oracle_stats* stats);
 /* unit-test hook: EdgeStereoSE3ProjectXYZ error (3), Jacobians 3x6 / 3x3; returns isDepthPositive */
 int urmvo_oracle_edge_stereo(const double* Tcw, const double* X, const double* uv3, const double* intr5,
                              double* e, double* Jpose, double* Jpoint);

@@ -115,6 +115,52 @@ def pose_only_batch_stereo(batch, chi2_thr=10.0, chi2_thr_stereo=75.0, rounds=4,
     return poses, inl, n_inl
 
 
+def local_ba_multicam(prob, chi2_thr=10.0, chi2_thr_stereo=75.0, it0=10, it1=5):
+    """Per-constraint camera models: prob has uv3 (No, 3), kind_model (No,) = stereo bit | model << 1 and
+    intr5_tab (n_models, 5).  Returns (poses, pts, inlier, Stats)."""
+    poses = np.ascontiguousarray(prob["poses"], dtype=np.float64).copy()
+    pts = np.ascontiguousarray(prob["pts"], dtype=np.float64).copy()
+    fixed = np.ascontiguousarray(prob["fixed"], dtype=np.uint8)
+    uv3 = np.ascontiguousarray(prob["uv3"], dtype=np.float64)
+    km = np.ascontiguousarray(prob["kind_model"], dtype=np.uint8)
+    cam = np.ascontiguousarray(prob["obs_cam"], dtype=np.int32)
+    pt = np.ascontiguousarray(prob["obs_pt"], dtype=np.int32)
+    tab = np.ascontiguousarray(prob["intr5_tab"], dtype=np.float64).reshape(-1, 5)
+    inl = np.zeros(uv3.shape[0], dtype=np.uint8)
+    st = Stats()
+    lib().urmvo_oracle_local_ba_multicam.restype = C.c_int
+    rc = lib().urmvo_oracle_local_ba_multicam(C.c_int(poses.shape[0]), _p(poses), _p(fixed), C.c_int(pts.shape[0]),
+                                              _p(pts), C.c_int(uv3.shape[0]), _p(uv3), _p(km), _p(cam), _p(pt),
+                                              C.c_int(tab.shape[0]), _p(tab), C.c_double(chi2_thr),
+                                              C.c_double(chi2_thr_stereo), C.c_int(it0), C.c_int(it1), _p(inl),
+                                              C.byref(st))
+    if rc < 0:
+        raise ValueError("bad camera model index")
+    return poses, pts, inl, st
+
+
+def pose_only_batch_multicam(batch, chi2_thr=10.0, chi2_thr_stereo=75.0, rounds=4, its=10):
+    poses = np.ascontiguousarray(batch["poses"], dtype=np.float64).copy()
+    off = np.ascontiguousarray(batch["obs_offset"], dtype=np.int32)
+    uv3 = np.ascontiguousarray(batch["uv3"], dtype=np.float64)
+    km = np.ascontiguousarray(batch["kind_model"], dtype=np.uint8)
+    Xw = np.ascontiguousarray(batch["Xw"], dtype=np.float64)
+    tab = np.ascontiguousarray(batch["intr5_tab"], dtype=np.float64).reshape(-1, 5)
+    inl = np.ones(uv3.shape[0], dtype=np.uint8)
+    n_inl = np.zeros(poses.shape[0], dtype=np.int32)
+    lib().urmvo_oracle_pose_only_multicam.restype = C.c_int
+    for f in range(poses.shape[0]):
+        o0, o1 = int(off[f]), int(off[f + 1])
+        pose = poses[f].copy(); i_f = inl[o0:o1].copy()
+        u = np.ascontiguousarray(uv3[o0:o1]); k = np.ascontiguousarray(km[o0:o1]); X = np.ascontiguousarray(Xw[o0:o1])
+        n_inl[f] = lib().urmvo_oracle_pose_only_multicam(_p(pose), C.c_int(o1 - o0), _p(u), _p(k), _p(X),
+                                                         C.c_int(tab.shape[0]), _p(tab), C.c_double(chi2_thr),
+                                                         C.c_double(chi2_thr_stereo), C.c_int(rounds), C.c_int(its),
+                                                         _p(i_f), None)
+        poses[f] = pose; inl[o0:o1] = i_f
+    return poses, inl, n_inl
+
+
 def edge_stereo(Tcw, X, uv3, intr5):
     """EdgeStereoSE3ProjectXYZ: returns (e[3], Jpose[3,6], Jpoint[3,3], depth_positive)."""
     Tcw = np.ascontiguousarray(Tcw, dtype=np.float64); X = np.ascontiguousarray(X, dtype=np.float64)

@@ -71,6 +71,44 @@ int main(int argc, char** argv) {
     std::vector<unsigned char> inl; for (int o = 0; o < No; o++) inl.push_back(kind[o] ? stereo[where[o]]->inlier : mono[where[o]]->inlier);
     std::vector<int> ni = {n};
     wr(out, Po); wr(out, inl); wr(out, ni);
+  } else if (mode == "ba_multicam") {
+    // several cameras in camera_list: kind_model[o] = stereo bit | id_camera << 1 (src/g2o_optimization.cc:86-89)
+    auto hdr = rd<int>(in, 4); int Nc = hdr[0], Np = hdr[1], No = hdr[2], Nm = hdr[3];
+    auto tab = rd<double>(in, (size_t)Nm * 5); auto ids = rd<int>(in, Nc); auto P = rd<double>(in, (size_t)Nc * 7); auto fx = rd<unsigned char>(in, Nc);
+    auto pids = rd<int>(in, Np); auto X = rd<double>(in, (size_t)Np * 3);
+    auto uv3 = rd<double>(in, (size_t)No * 3); auto km = rd<unsigned char>(in, No); auto oc = rd<int>(in, No); auto op = rd<int>(in, No);
+    for (int m = 0; m < Nm; m++) cams.emplace_back(new Camera(tab[m*5], tab[m*5+1], tab[m*5+2], tab[m*5+3], STEREO, tab[m*5+4]));
+    MapOfPoses poses; MapOfPoints3d points; VectorOfMonoPointConstraints mono; VectorOfStereoPointConstraints stereo;
+    for (int c = 0; c < Nc; c++) { Pose3d p; p.fixed = fx[c]; p.q.x() = P[c*7]; p.q.y() = P[c*7+1]; p.q.z() = P[c*7+2]; p.q.w() = P[c*7+3]; for (int k = 0; k < 3; k++) p.p(k) = P[c*7+4+k]; poses[ids[c]] = p; }
+    for (int l = 0; l < Np; l++) { Position3d q; for (int k = 0; k < 3; k++) q.p(k) = X[l*3+k]; points[pids[l]] = q; }
+    std::vector<int> where(No);
+    for (int o = 0; o < No; o++) {
+      if (km[o] & 1) { auto m = std::make_shared<StereoPointConstraint>(); m->id_pose = ids[oc[o]]; m->id_point = pids[op[o]]; m->id_camera = km[o] >> 1; m->inlier = true; for (int k = 0; k < 3; k++) m->keypoint(k) = uv3[o*3+k]; m->pixel_sigma = 0.8; where[o] = (int)stereo.size(); stereo.push_back(m); }
+      else { auto m = std::make_shared<MonoPointConstraint>(); m->id_pose = ids[oc[o]]; m->id_point = pids[op[o]]; m->id_camera = km[o] >> 1; m->inlier = true; m->keypoint(0) = uv3[o*3]; m->keypoint(1) = uv3[o*3+1]; m->pixel_sigma = 0.8; where[o] = (int)mono.size(); mono.push_back(m); }
+    }
+    LocalmapOptimization(poses, points, cams, mono, stereo, cfg);
+    std::vector<double> Po, Xo; std::vector<unsigned char> inl;
+    for (auto& kv : poses) { Po.push_back(kv.second.q.x()); Po.push_back(kv.second.q.y()); Po.push_back(kv.second.q.z()); Po.push_back(kv.second.q.w()); for (int k = 0; k < 3; k++) Po.push_back(kv.second.p(k)); }
+    for (auto& kv : points) for (int k = 0; k < 3; k++) Xo.push_back(kv.second.p(k));
+    for (int o = 0; o < No; o++) inl.push_back((km[o] & 1) ? stereo[where[o]]->inlier : mono[where[o]]->inlier);
+    std::vector<int> status = {urmvo_adapter_last_status()};
+    wr(out, Po); wr(out, Xo); wr(out, inl); wr(out, status);
+  } else if (mode == "pose_multicam") {
+    auto hdr = rd<int>(in, 2); int No = hdr[0], Nm = hdr[1];
+    auto tab = rd<double>(in, (size_t)Nm * 5); auto P = rd<double>(in, 7); auto uv3 = rd<double>(in, (size_t)No * 3); auto km = rd<unsigned char>(in, No); auto X = rd<double>(in, (size_t)No * 3);
+    for (int m = 0; m < Nm; m++) cams.emplace_back(new Camera(tab[m*5], tab[m*5+1], tab[m*5+2], tab[m*5+3], STEREO, tab[m*5+4]));
+    MapOfPoses poses; MapOfPoints3d points; VectorOfMonoPointConstraints mono; VectorOfStereoPointConstraints stereo;
+    Pose3d p; p.q.x() = P[0]; p.q.y() = P[1]; p.q.z() = P[2]; p.q.w() = P[3]; for (int k = 0; k < 3; k++) p.p(k) = P[4+k]; poses[42] = p;
+    std::vector<int> where(No);
+    for (int o = 0; o < No; o++) { Position3d q; q.fixed = true; for (int k = 0; k < 3; k++) q.p(k) = X[o*3+k]; points[1000 + o] = q;
+      if (km[o] & 1) { auto m = std::make_shared<StereoPointConstraint>(); m->id_pose = 42; m->id_point = 1000 + o; m->id_camera = km[o] >> 1; m->inlier = true; for (int k = 0; k < 3; k++) m->keypoint(k) = uv3[o*3+k]; m->pixel_sigma = 0.8; where[o] = (int)stereo.size(); stereo.push_back(m); }
+      else { auto m = std::make_shared<MonoPointConstraint>(); m->id_pose = 42; m->id_point = 1000 + o; m->id_camera = km[o] >> 1; m->inlier = true; m->keypoint(0) = uv3[o*3]; m->keypoint(1) = uv3[o*3+1]; m->pixel_sigma = 0.8; where[o] = (int)mono.size(); mono.push_back(m); } }
+    int n = FrameOptimization(poses, points, cams, mono, stereo, cfg);
+    Pose3d& r = poses.begin()->second;
+    std::vector<double> Po = {r.q.x(), r.q.y(), r.q.z(), r.q.w(), r.p(0), r.p(1), r.p(2)};
+    std::vector<unsigned char> inl; for (int o = 0; o < No; o++) inl.push_back((km[o] & 1) ? stereo[where[o]]->inlier : mono[where[o]]->inlier);
+    std::vector<int> ni = {n, urmvo_adapter_last_status()};
+    wr(out, Po); wr(out, inl); wr(out, ni);
   } else if (mode == "pose") {
     auto hdr = rd<int>(in, 1); int No = hdr[0];
     auto intr = rd<double>(in, 4); auto P = rd<double>(in, 7); auto uv = rd<double>(in, (size_t)No * 2); auto X = rd<double>(in, (size_t)No * 3);

@@ -111,6 +111,51 @@ def test_stereo_camera_through_the_adapters(oracle):
 
 
 @pytest.mark.gpu
+def test_several_cameras_in_camera_list_through_the_adapters(oracle):
+    """camera_list with several different cameras: the reference reads the intrinsics of every edge from
+    camera_list[mpc->id_camera] (src/g2o_optimization.cc:86-89, :106-113, :221-224, :243-250); the adapters send the
+    camera-model table and per-edge indices through the multicam entry points."""
+    p = synth.add_camera_models(synth.add_stereo(synth.small_ba(seed=15, n_pts=200), 4), 8, n_models=3)
+    Nc, Np, No = p["poses"].shape[0], p["pts"].shape[0], p["uv3"].shape[0]
+    frame_ids = (np.arange(Nc) * 2 + 3).astype(np.int32)
+    point_ids = (np.arange(Np) * 5 + 1).astype(np.int32)
+    km = p["kind_model"]
+    buf = struct.pack("4i", Nc, Np, No, 3) + p["intr5_tab"].tobytes() + frame_ids.tobytes() + p["poses"].tobytes() + p["fixed"].tobytes() \
+        + point_ids.tobytes() + p["pts"].tobytes() + p["uv3"].tobytes() + km.tobytes() + p["obs_cam"].tobytes() + p["obs_pt"].tobytes()
+    out = _run("ba_multicam", buf)
+    poses = np.frombuffer(out[:Nc * 56], dtype=np.float64).reshape(Nc, 7)
+    pts = np.frombuffer(out[Nc * 56:Nc * 56 + Np * 24], dtype=np.float64).reshape(Np, 3)
+    inl = np.frombuffer(out[Nc * 56 + Np * 24:Nc * 56 + Np * 24 + No], dtype=np.uint8)
+    status = struct.unpack("i", out[Nc * 56 + Np * 24 + No:])[0]
+    order = np.r_[np.nonzero((km & 1) == 0)[0], np.nonzero((km & 1) == 1)[0]]
+    # the adapter numbers the camera models in order of first use; the oracle takes the same table order
+    first = []
+    for m in (km[order] >> 1):
+        if m not in first:
+            first.append(int(m))
+    remap = np.zeros(3, dtype=np.uint8); remap[first] = np.arange(len(first))
+    q = dict(p, uv3=p["uv3"][order], kind_model=((km[order] & 1) | (remap[km[order] >> 1] << 1)).astype(np.uint8),
+             intr5_tab=p["intr5_tab"][first], obs_cam=p["obs_cam"][order], obs_pt=p["obs_pt"][order])
+    op, ox, oi, _ = oracle.local_ba_multicam(q, 10.0, 75.0)
+    back = np.empty_like(oi); back[order] = oi
+    assert status == 0
+    assert np.abs(poses - op).max() < 1e-5 and np.abs(pts - ox).max() < 1e-4 and np.array_equal(inl, back)
+    b = synth.add_camera_models(synth.make_pose_batch_stereo(16, B=1, n_obs=220), 3, n_models=4)
+    km = b["kind_model"]
+    buf = struct.pack("2i", 220, 4) + b["intr5_tab"].tobytes() + b["poses"][0].tobytes() + b["uv3"].tobytes() + km.tobytes() + b["Xw"].tobytes()
+    out = _run("pose_multicam", buf)
+    pose = np.frombuffer(out[:56], dtype=np.float64)
+    inl = np.frombuffer(out[56:56 + 220], dtype=np.uint8)
+    n, status = struct.unpack("2i", out[56 + 220:])
+    order = np.r_[np.nonzero((km & 1) == 0)[0], np.nonzero((km & 1) == 1)[0]]
+    q = dict(b, uv3=b["uv3"][order], kind_model=km[order], Xw=b["Xw"][order])
+    op, oi, on = oracle.pose_only_batch_multicam(q, 10.0, 75.0)
+    back = np.empty_like(oi); back[order] = oi
+    assert status == 0
+    assert np.abs(pose - op[0]).max() < 1e-5 and np.array_equal(inl, back) and n == on[0]
+
+
+@pytest.mark.gpu
 def test_reconstruct_through_the_adapter_uses_glibc_rand_sets(oracle):
     tv = synth.make_two_view(1003, n_keys=400)
     its = 64

@@ -225,6 +225,22 @@ def test_ba_cyclic_reduction_solver_matches_oracle_and_band_solver(oracle, ctx, 
     assert np.abs(res[0][0] - res[1][0]).max() <= 1e-9
 
 
+def test_ba_cyclic_reduction_has_no_camera_count_limit(oracle, ctx):
+    """3 200 cameras: the sequential band solve keeps the whole right-hand side in shared memory (a limit of about
+    2 900 free cameras at half-bandwidth 15), the cyclic reduction does not; parity with the oracle at that size."""
+    p = synth.make_ba(4242, 3200, 40000, 5.4, 9, 2, 0.02)
+    plan = U.ShardedBAPlan(ctx, U.shard_points(p, 0, 1), covis=U.ba_covisibility(p))
+    plan.run()
+    info = plan.phase_info()
+    assert info["tile_mode"] and "cyclic" in info["band_solver"], info
+    gp, gx, gi, gs = plan.download()
+    plan.close()
+    op, ox, oi, os_ = oracle.local_ba(p)
+    assert abs(gs.chi2_final[1] - os_.chi2_final[1]) <= REL_COST * abs(os_.chi2_final[1])
+    assert np.abs(gp - op).max() <= POSE_TOL and np.array_equal(gi, oi)
+    assert list(gs.iters) == list(os_.iters)[:2]
+
+
 # ------------------------------------------------------------------------------- stereo edges (S1)
 
 @pytest.mark.parametrize("force_atomic", [0, 1])
@@ -266,6 +282,47 @@ def test_pose_only_stereo_edges_match_oracle(oracle, ctx):
         b = synth.make_pose_batch_stereo(31 + B, B=B, n_obs=120)
         gp, gi, gn = ctx.pose_only_batch_stereo(b, 10.0, 75.0)
         op, oi, on = oracle.pose_only_batch_stereo(b, 10.0, 75.0)
+        assert np.abs(gp - op).max() <= POSE_TOL
+        assert np.array_equal(gi, oi) and np.array_equal(gn, on)
+
+
+@pytest.mark.parametrize("force_atomic", [0, 1])
+def test_ba_several_camera_models_match_oracle(oracle, ctx, force_atomic):
+    """Per-constraint intrinsics, camera_list[mpc->id_camera] (reference src/g2o_optimization.cc:86-89, :106-113):
+    three / five camera models mixed inside one window, mono and stereo edges, both accumulation modes."""
+    for seed, frac, nm in ((7, 0.6, 3), (23, 0.0, 5), (31, 1.0, 2)):
+        p = synth.add_camera_models(synth.add_stereo(synth.small_ba(seed=seed, n_pts=300), seed + 100, stereo_frac=frac),
+                                    seed + 200, n_models=nm)
+        gp, gx, gi, gs = ctx.local_ba_multicam(p, 10.0, 75.0, opts=U.BAOptions(0, 0, 0, 0, force_atomic))
+        op, ox, oi, os_ = oracle.local_ba_multicam(p, 10.0, 75.0)
+        assert abs(gs.chi2_final[1] - os_.chi2_final[1]) <= REL_COST * abs(os_.chi2_final[1])
+        assert list(gs.iters) == list(os_.iters)[:2]
+        assert np.abs(gp - op).max() <= POSE_TOL and np.abs(gx - ox).max() <= 1e-4
+        assert np.array_equal(gi, oi)
+
+
+def test_ba_one_camera_model_equals_the_stereo_call_and_cfg1_shape(oracle, ctx):
+    p = synth.add_stereo(synth.small_ba(seed=5, n_pts=200), 1)
+    q = dict(p, kind_model=p["kind"].copy(), intr5_tab=p["intr5"].reshape(1, 5))
+    a = ctx.local_ba_stereo(p, 10.0, 75.0)
+    b = ctx.local_ba_multicam(q, 10.0, 75.0)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    big = synth.add_camera_models(synth.add_stereo(synth.cfg1(), 77), 78, n_models=4)  # 10 keyframes, 2000 points
+    gp, gx, gi, gs = ctx.local_ba_multicam(big, 10.0, 75.0)
+    op, ox, oi, os_ = oracle.local_ba_multicam(big, 10.0, 75.0)
+    assert abs(gs.chi2_final[1] - os_.chi2_final[1]) <= REL_COST * abs(os_.chi2_final[1])
+    assert np.abs(gp - op).max() <= POSE_TOL and np.array_equal(gi, oi)
+    bad = dict(big, kind_model=(big["kind_model"] | 0x80).astype(np.uint8))
+    with pytest.raises(U.UrmvoError):
+        ctx.local_ba_multicam(bad, 10.0, 75.0)
+
+
+def test_pose_only_several_camera_models_match_oracle(oracle, ctx):
+    """FrameOptimization with per-constraint camera models (:221-224, :243-250): poses, flags, counts."""
+    for B in (5, 200):
+        b = synth.add_camera_models(synth.make_pose_batch_stereo(31 + B, B=B, n_obs=120), B, n_models=4)
+        gp, gi, gn = ctx.pose_only_batch_multicam(b, 10.0, 75.0)
+        op, oi, on = oracle.pose_only_batch_multicam(b, 10.0, 75.0)
         assert np.abs(gp - op).max() <= POSE_TOL
         assert np.array_equal(gi, oi) and np.array_equal(gn, on)
 

@@ -108,3 +108,69 @@ def test_pose_only_threads_match_serial(oracle):
     a = oracle.pose_only_batch(b, n_threads=1)
     c = oracle.pose_only_batch(b, n_threads=4)
     assert all(np.array_equal(x, y) for x, y in zip(a, c))
+
+
+# ------------------------------------------------------------------------ per-constraint camera models
+
+def test_multicam_with_one_model_is_the_stereo_call(oracle):
+    """camera_list[mpc->id_camera] with a single camera (every reference configuration): the per-edge model
+    lookup must reproduce the single-intrinsics restatement bit for bit."""
+    p = synth.add_stereo(synth.small_ba(seed=13, n_pts=200), 5)
+    q = dict(p, kind_model=p["kind"].copy(), intr5_tab=p["intr5"].reshape(1, 5))
+    a = oracle.local_ba_stereo(p, 10.0, 75.0)
+    b = oracle.local_ba_multicam(q, 10.0, 75.0)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    assert a[3].chi2_final[1] == b[3].chi2_final[1]
+
+
+def test_multicam_residual_uses_the_model_of_the_edge(oracle):
+    """One edge per model: the cost of a zero-iteration solve equals the sum of the robustified errors computed by
+    the single-edge hook with that model's intrinsics (src/g2o_optimization.cc:86-89, :106-113)."""
+    p = synth.add_camera_models(synth.add_stereo(synth.small_ba(seed=3, n_pts=80), 9), 4, n_models=4)
+    assert len(set((p["kind_model"] >> 1).tolist())) == 4
+    _, _, _, st = oracle.local_ba_multicam(p, 10.0, 75.0, it0=1, it1=0)
+    chi0 = st.rows()[0][0] if st.rows() else None
+    # the initial robust cost, recomputed edge by edge
+    tot = 0.0
+    for o in range(len(p["obs_cam"])):
+        c, l = p["obs_cam"][o], p["obs_pt"][o]
+        q, t = p["poses"][c, :4], p["poses"][c, 4:]
+        R = synth.quat_to_R(q[None])[0]
+        Tcw = np.r_[-q[:3], q[3], -(R.T @ t)]
+        km = int(p["kind_model"][o])
+        row = p["intr5_tab"][km >> 1]
+        if km & 1:
+            e = oracle.edge_stereo(Tcw, p["pts"][l], p["uv3"][o], row)[0]
+            d = float(np.float32(np.sqrt(75.0)))
+        else:
+            e = np.r_[oracle.edge(Tcw, p["pts"][l], p["uv3"][o, :2], row[:4])[0], 0.0]
+            d = float(np.float32(np.sqrt(10.0)))
+        e2 = float(e @ e)
+        tot += e2 if e2 <= d * d else 2 * np.sqrt(e2) * d - d * d
+    assert chi0 is not None and abs(chi0 - tot) <= 1e-9 * tot
+
+
+def test_multicam_noise_free_scene_returns_ground_truth(oracle):
+    p = synth.add_stereo(_noise_free(seed=8), 2, stereo_frac=0.5, px_sigma=0.0)
+    # exact right-image columns of the ground truth
+    uv, z = synth.project(p["gt_poses"], p["obs_cam"], p["gt_pts"][p["obs_pt"]])
+    p["uv3"] = np.ascontiguousarray(np.c_[uv, np.where(p["kind"] != 0, uv[:, 0] - synth.BF / z, 0.0)])
+    p = synth.add_camera_models(p, 6, n_models=3)
+    poses, pts, inl, st = oracle.local_ba_multicam(p, 10.0, 75.0, it0=15, it1=15)
+    assert inl.all() and st.chi2_final[1] < 1e-14
+    assert np.abs(pts - p["gt_pts"]).max() < 1e-6
+    assert np.abs(poses[:, 4:] - p["gt_poses"][:, 4:]).max() < 1e-7
+
+
+def test_multicam_pose_only_matches_single_model_and_rejects_bad_index(oracle):
+    b = synth.make_pose_batch_stereo(4, B=3, n_obs=150)
+    one = dict(b, kind_model=b["kind"].copy(), intr5_tab=b["intr5"].reshape(1, 5))
+    a = oracle.pose_only_batch_stereo(b, 10.0, 75.0)
+    c = oracle.pose_only_batch_multicam(one, 10.0, 75.0)
+    assert np.array_equal(a[0], c[0]) and np.array_equal(a[1], c[1]) and np.array_equal(a[2], c[2])
+    many = synth.add_camera_models(b, 12, n_models=5)
+    gp, gi, gn = oracle.pose_only_batch_multicam(many, 10.0, 75.0)
+    # the same scene seen through other pinhole models: the recovered poses stay near the ground truth
+    assert np.abs(gp[:, 4:] - b["gt_poses"][:, 4:]).max() < 0.05 and (gn > 0.7 * 150).all()
+    bad = dict(many, kind_model=(many["kind_model"] | 0xF0).astype(np.uint8))
+    assert (oracle.pose_only_batch_multicam(bad, 10.0, 75.0)[2] < 0).all()

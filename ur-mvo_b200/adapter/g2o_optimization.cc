@@ -14,14 +14,16 @@
 //     urmvo_adapter_last_status() returns the urmvo_status of the last call on this thread (0 = the
 //     map was optimised), urmvo_last_error() the message — the caller can tell an optimised map from
 //     an untouched one (include/urmvo_b200.h).
-// The reference reads fx, fy, cx, cy per edge from camera_list[id_camera] (:86-89).  The kernels take one
-// intrinsics set per call: the adapter verifies that every constraint of a call refers to cameras with
-// identical intrinsics (always true for the reference's configurations: camera_list has one entry) and
-// reports URMVO_ERR_UNSUPPORTED otherwise instead of silently using the first camera.
+// The reference reads fx, fy, cx, cy (and BF) per edge from camera_list[id_camera] (:86-89, :106-113).  The adapter
+// collects the cameras the constraints of a call refer to: when they all have the same intrinsics (always true
+// for the reference's configurations: camera_list has one entry) the single-camera entry points run, otherwise
+// the camera-model table and a per-edge model index go through urmvo_local_ba_multicam /
+// urmvo_pose_only_batch_multicam (more than 128 distinct cameras in one call: URMVO_ERR_UNSUPPORTED).
 // Both entry points are called from the tracking thread in the reference; a mutex guards the shared
 // context so that a caller with a separate mapping thread stays safe.
 #include "g2o_optimization.h"
 
+#include <algorithm>
 #include <cstdio>
 #include <map>
 #include <mutex>
@@ -56,25 +58,30 @@ void get_pose(const double* in, Pose3d& p) {
   p.p(0) = in[4]; p.p(1) = in[5]; p.p(2) = in[6];
 }
 
-struct Intrinsics {
-  double v[5] = {0, 0, 0, 0, 0};  // fx fy cx cy bf
-  bool set = false, bf_set = false, consistent = true;
-  void add(Camera& c, bool with_bf) {
-    const double w[4] = {c.Fx(), c.Fy(), c.Cx(), c.Cy()};
-    if (!set) { for (int k = 0; k < 4; k++) v[k] = w[k]; set = true; }
-    for (int k = 0; k < 4; k++) if (v[k] != w[k]) consistent = false;
-    if (with_bf) {
-      const double bf = c.BF();
-      if (bf_set && v[4] != bf) consistent = false;
-      v[4] = bf; bf_set = true;
-    }
+// the cameras one call refers to: one (fx fy cx cy bf) row per id_camera, in order of first use
+struct CameraModels {
+  std::vector<int> ids;
+  std::vector<double> rows;
+  int index(int id_camera, Camera& c) {
+    for (size_t m = 0; m < ids.size(); m++) if (ids[m] == id_camera) return (int)m;
+    ids.push_back(id_camera);
+    const double w[5] = {c.Fx(), c.Fy(), c.Cx(), c.Cy(), c.BF()};
+    rows.insert(rows.end(), w, w + 5);
+    return (int)ids.size() - 1;
+  }
+  bool empty() const { return ids.empty(); }
+  // all constraints see the same pinhole model (BF only matters when a stereo edge exists)
+  bool single(bool with_bf) const {
+    for (size_t m = 1; m < ids.size(); m++)
+      for (int k = 0; k < (with_bf ? 5 : 4); k++) if (rows[m * 5 + k] != rows[k]) return false;
+    return true;
   }
 };
 
 int fail_status(int rc, const char* who) {
   g_last_status = rc;
   std::fprintf(stderr, "[urmvo_b200] %s: %s\n", who, rc == URMVO_ERR_UNSUPPORTED && !*urmvo_last_error() ?
-               "constraints refer to cameras with different intrinsics" : urmvo_last_error());
+               "constraints refer to more than 128 distinct cameras" : urmvo_last_error());
   return rc;
 }
 
@@ -107,9 +114,9 @@ void LocalmapOptimization(MapOfPoses& poses, MapOfPoints3d& points, std::vector<
   }
   // observations: constraints whose vertices exist (g2o drops edges with a missing vertex)
   CameraType camType = MONO;
-  Intrinsics K;
+  CameraModels K;
   std::vector<double> uv3;
-  std::vector<uint8_t> kind;
+  std::vector<uint8_t> kind, model;
   std::vector<int32_t> cam, pt;
   std::vector<size_t> src_mono, src_stereo;
   uv3.reserve((mono_point_constraints.size() + stereo_point_constraints.size()) * 3);
@@ -120,7 +127,7 @@ void LocalmapOptimization(MapOfPoses& poses, MapOfPoints3d& points, std::vector<
     auto pi = pose_idx.find(c->id_pose);
     auto li = point_idx.find(c->id_point);
     if (pi == pose_idx.end() || li == point_idx.end()) continue;
-    K.add(camera, false);
+    model.push_back((uint8_t)std::min(K.index(c->id_camera, camera), 255));
     uv3.push_back(c->keypoint(0)); uv3.push_back(c->keypoint(1)); uv3.push_back(0.0);
     kind.push_back(0);
     cam.push_back(pi->second); pt.push_back(li->second);
@@ -132,7 +139,7 @@ void LocalmapOptimization(MapOfPoses& poses, MapOfPoints3d& points, std::vector<
       auto pi = pose_idx.find(c->id_pose);
       auto li = point_idx.find(c->id_point);
       if (pi == pose_idx.end() || li == point_idx.end()) continue;
-      K.add(*camera_list[c->id_camera], true);
+      model.push_back((uint8_t)std::min(K.index(c->id_camera, *camera_list[c->id_camera]), 255));
       uv3.push_back(c->keypoint(0)); uv3.push_back(c->keypoint(1)); uv3.push_back(c->keypoint(2));
       kind.push_back(1);
       cam.push_back(pi->second); pt.push_back(li->second);
@@ -141,23 +148,29 @@ void LocalmapOptimization(MapOfPoses& poses, MapOfPoints3d& points, std::vector<
   }
   const size_t No = kind.size();
   if (No == 0) return;  // no edge: a silent no-op in the reference too
-  if (!K.consistent) { fail_status(URMVO_ERR_UNSUPPORTED, "LocalmapOptimization"); return; }
+  if (K.ids.size() > 128) { fail_status(URMVO_ERR_UNSUPPORTED, "LocalmapOptimization"); return; }
   std::vector<uint8_t> inlier(No, 0);
   int rc;
   {
     std::lock_guard<std::mutex> lock(g_ba_mutex);
     urmvo_ctx* ctx = ba_context();
     if (!ctx) { g_last_status = URMVO_ERR_NO_DEVICE; return; }
-    if (src_stereo.empty()) {
+    if (!K.single(!src_stereo.empty())) {  // several camera models: per-edge intrinsics (:86-89, :106-113)
+      for (size_t o = 0; o < No; o++) kind[o] = (uint8_t)(kind[o] | (model[o] << 1));
+      rc = urmvo_local_ba_multicam(ctx, (int)poses.size(), P.data(), fixed.data(), (int)points.size(), X.data(), (int)No,
+                                   uv3.data(), kind.data(), cam.data(), pt.data(), (int)K.ids.size(), K.rows.data(),
+                                   cfg.mono_point, src_stereo.empty() ? cfg.mono_point : cfg.stereo_point,
+                                   /*it0=*/10, /*it1=*/5, inlier.data(), nullptr, nullptr);
+    } else if (src_stereo.empty()) {
       std::vector<double> uv(No * 2);
       for (size_t o = 0; o < No; o++) { uv[o * 2] = uv3[o * 3]; uv[o * 2 + 1] = uv3[o * 3 + 1]; }
       rc = urmvo_local_ba(ctx, (int)poses.size(), P.data(), fixed.data(), (int)points.size(), X.data(), (int)No,
-                          uv.data(), cam.data(), pt.data(), K.v, cfg.mono_point, /*it0=*/10, /*it1=*/5, inlier.data(),
-                          nullptr, nullptr);
+                          uv.data(), cam.data(), pt.data(), K.rows.data(), cfg.mono_point, /*it0=*/10, /*it1=*/5,
+                          inlier.data(), nullptr, nullptr);
     } else {
       rc = urmvo_local_ba_stereo(ctx, (int)poses.size(), P.data(), fixed.data(), (int)points.size(), X.data(), (int)No,
-                                 uv3.data(), kind.data(), cam.data(), pt.data(), K.v, cfg.mono_point, cfg.stereo_point,
-                                 /*it0=*/10, /*it1=*/5, inlier.data(), nullptr, nullptr);
+                                 uv3.data(), kind.data(), cam.data(), pt.data(), K.rows.data(), cfg.mono_point,
+                                 cfg.stereo_point, /*it0=*/10, /*it1=*/5, inlier.data(), nullptr, nullptr);
     }
   }
   if (rc != URMVO_OK) { fail_status(rc, "LocalmapOptimization"); return; }  // inputs untouched
@@ -185,16 +198,16 @@ int FrameOptimization(MapOfPoses& poses, MapOfPoints3d& points, std::vector<Came
   put_pose(pose_it->second, P);
   const int Nm = (int)mono_point_constraints.size();
   CameraType camType = MONO;
-  Intrinsics K;
+  CameraModels K;
   std::vector<double> uv3, Xw;
-  std::vector<uint8_t> kind, inlier;
+  std::vector<uint8_t> kind, model, inlier;
   uv3.reserve((size_t)total * 3); Xw.reserve((size_t)total * 3);
   for (int i = 0; i < Nm; i++) {
     const MonoPointConstraintPtr& c = mono_point_constraints[i];
     const Position3d& point = points[c->id_point];  // operator[] like the reference (:214)
     Camera& camera = *camera_list[c->id_camera];
     camType = camera.GetCameraType();  // :228
-    K.add(camera, false);
+    model.push_back((uint8_t)std::min(K.index(c->id_camera, camera), 255));
     uv3.push_back(c->keypoint(0)); uv3.push_back(c->keypoint(1)); uv3.push_back(0.0);
     for (int k = 0; k < 3; k++) Xw.push_back(point.p(k));
     kind.push_back(0);
@@ -206,7 +219,7 @@ int FrameOptimization(MapOfPoses& poses, MapOfPoints3d& points, std::vector<Came
     for (int i = 0; i < Ns; i++) {
       const StereoPointConstraintPtr& c = stereo_point_constraints[i];
       const Position3d& point = points[c->id_point];
-      K.add(*camera_list[c->id_camera], true);
+      model.push_back((uint8_t)std::min(K.index(c->id_camera, *camera_list[c->id_camera]), 255));
       uv3.push_back(c->keypoint(0)); uv3.push_back(c->keypoint(1)); uv3.push_back(c->keypoint(2));
       for (int k = 0; k < 3; k++) Xw.push_back(point.p(k));
       kind.push_back(1);
@@ -214,10 +227,10 @@ int FrameOptimization(MapOfPoses& poses, MapOfPoints3d& points, std::vector<Came
     }
   }
   const int No = Nm + Ns;
-  if (!K.set) {  // no edge at all: g2o optimises nothing, every round counts zero outliers
+  if (K.empty()) {  // no edge at all: g2o optimises nothing, every round counts zero outliers
     return total;
   }
-  if (!K.consistent) { fail_status(URMVO_ERR_UNSUPPORTED, "FrameOptimization"); return 0; }
+  if (K.ids.size() > 128) { fail_status(URMVO_ERR_UNSUPPORTED, "FrameOptimization"); return 0; }
   const int32_t off[2] = {0, No};
   int32_t n_inlier = 0;
   int rc;
@@ -225,13 +238,18 @@ int FrameOptimization(MapOfPoses& poses, MapOfPoints3d& points, std::vector<Came
     std::lock_guard<std::mutex> lock(g_ba_mutex);
     urmvo_ctx* ctx = ba_context();
     if (!ctx) { g_last_status = URMVO_ERR_NO_DEVICE; return 0; }
-    if (Ns == 0) {
+    if (!K.single(Ns > 0)) {  // several camera models: per-edge intrinsics (:221-224, :243-250)
+      for (int o = 0; o < No; o++) kind[o] = (uint8_t)(kind[o] | (model[o] << 1));
+      rc = urmvo_pose_only_batch_multicam(ctx, 1, off, P, uv3.data(), kind.data(), Xw.data(), (int)K.ids.size(),
+                                          K.rows.data(), cfg.mono_point, Ns > 0 ? cfg.stereo_point : cfg.mono_point,
+                                          /*rounds=*/4, /*its=*/10, inlier.data(), &n_inlier);
+    } else if (Ns == 0) {
       std::vector<double> uv((size_t)No * 2);
       for (int o = 0; o < No; o++) { uv[(size_t)o * 2] = uv3[(size_t)o * 3]; uv[(size_t)o * 2 + 1] = uv3[(size_t)o * 3 + 1]; }
-      rc = urmvo_pose_only_batch(ctx, 1, off, P, uv.data(), Xw.data(), K.v, cfg.mono_point, /*rounds=*/4, /*its=*/10,
-                                 inlier.data(), &n_inlier);
+      rc = urmvo_pose_only_batch(ctx, 1, off, P, uv.data(), Xw.data(), K.rows.data(), cfg.mono_point, /*rounds=*/4,
+                                 /*its=*/10, inlier.data(), &n_inlier);
     } else {
-      rc = urmvo_pose_only_batch_stereo(ctx, 1, off, P, uv3.data(), kind.data(), Xw.data(), K.v, cfg.mono_point,
+      rc = urmvo_pose_only_batch_stereo(ctx, 1, off, P, uv3.data(), kind.data(), Xw.data(), K.rows.data(), cfg.mono_point,
                                         cfg.stereo_point, /*rounds=*/4, /*its=*/10, inlier.data(), &n_inlier);
     }
   }

@@ -324,17 +324,26 @@ struct WarpStageS {
   __device__ __forceinline__ double& w(int i) { return f[39 * kmax + i]; }
 };
 
-struct StereoPar { double bf, delta_s; };
+struct StereoPar { double delta_s; };
 
-// residual (3 rows), Huber weight, chi2 contribution; returns rho0.  pz = (x/z, y/z, 1/z).
-__device__ __forceinline__ double edge_eval3(const BAWin& W, int o, const double* pc, const double* K,
+// Camera model of an edge: the reference reads fx, fy, cx, cy and BF per constraint from
+// camera_list[mpc->id_camera] (src/g2o_optimization.cc:86-89, :106-113).  okind[o] = stereo bit | model << 1,
+// BAWin::intr_tab holds one (fx fy cx cy bf) row per model (one row for the usual single-camera call).
+__device__ __forceinline__ const double* edge_model(const BAWin& W, int o, bool& stereo) {
+  const unsigned kb = W.okind[o];
+  stereo = (kb & 1u) != 0;
+  return W.intr_tab + 5 * (kb >> 1);
+}
+
+// residual (3 rows), Huber weight, chi2 contribution; returns rho0.  pz = (x/z, y/z, 1/z); K = the edge's model row.
+__device__ __forceinline__ double edge_eval3(const BAWin& W, int o, const double* pc, const double*& K,
                                              const StereoPar& sp, double delta, bool robust, double* e, double* pz,
                                              double& w, bool& stereo) {
+  K = edge_model(W, o, stereo);
   const double2 uv = *reinterpret_cast<const double2*>(W.uv + (size_t)o * 2);
   double e2 = edge_error(pc, uv.x, uv.y, K, e[0], e[1], pz);
-  stereo = W.okind[o] != 0;
   e[2] = 0.0;
-  if (stereo) { e[2] = edge_error_right(pz, W.ur[o], K, sp.bf); e2 += e[2] * e[2]; }
+  if (stereo) { e[2] = edge_error_right(pz, W.ur[o], K, K[4]); e2 += e[2] * e[2]; }
   return huber_rho(e2, stereo ? sp.delta_s : delta, robust, w);
 }
 
@@ -348,7 +357,6 @@ __device__ void lin_phase_s(const Scope& sc, const BAWin& W, int cur, double lam
   const int gstride = sc.nblk() * wpc;
   const double* __restrict__ camRt = W.camRt[cur];
   const double* __restrict__ pts = W.pts[cur];
-  const double K[4] = {W.intr[0], W.intr[1], W.intr[2], W.intr[3]};
   const int acc_len = DIAG ? W.Ncf * 6 : W.acc_len;
   const int acc_off = kStageFieldsS * st.kmax;
   double* acc = wa.base + (size_t)(threadIdx.x >> 5) * wa.stride + acc_off;
@@ -372,11 +380,12 @@ __device__ void lin_phase_s(const Scope& sc, const BAWin& W, int cur, double lam
         const double* Rt = camRt + (size_t)c * 12;
         double pc[3], pz[3], e[3], w;
         bool stereo;
+        const double* K;
         map_point(Rt, X, pc);
         chi_acc += edge_eval3(W, o, pc, K, sp, delta, robust, e, pz, w, stereo);
         double Jx[9], B[9];
         edge_jac_point(Rt, pz, K, Jx);
-        if (stereo) edge_jac_point_right(Rt, pz, Jx, sp.bf, Jx + 6);
+        if (stereo) edge_jac_point_right(Rt, pz, Jx, K[4], Jx + 6);
         else { Jx[6] = 0.0; Jx[7] = 0.0; Jx[8] = 0.0; }
 #pragma unroll
         for (int a = 0; a < 9; a++) B[a] = w * Jx[a];
@@ -392,7 +401,7 @@ __device__ void lin_phase_s(const Scope& sc, const BAWin& W, int cur, double lam
         if (cf >= 0) {
           double Jp[18];
           edge_jac_pose(pz, K, Jp);
-          if (stereo) edge_jac_pose_right(pz, Jp, sp.bf, Jp + 12);
+          if (stereo) edge_jac_pose_right(pz, Jp, K[4], Jp + 12);
           else {
 #pragma unroll
             for (int a = 0; a < 6; a++) Jp[12 + a] = 0.0;
@@ -532,7 +541,6 @@ __device__ void backsub_phase_s(const Scope& sc, const BAWin& W, int cur, double
   const int tr = cur ^ 1;
   const double* __restrict__ camRt = W.camRt[cur];
   const double* __restrict__ camRtT = W.camRt[tr];
-  const double K[4] = {W.intr[0], W.intr[1], W.intr[2], W.intr[3]};
   for (int l = gw; l < W.Np; l += gstride) {
     const int ps = W.pt_start[l], k = W.pt_start[l + 1] - ps;
     const double X[3] = {W.pts[cur][l * 3], W.pts[cur][l * 3 + 1], W.pts[cur][l * 3 + 2]};
@@ -546,6 +554,7 @@ __device__ void backsub_phase_s(const Scope& sc, const BAWin& W, int cur, double
       const double* Rt = camRt + (size_t)c * 12;
       double pc[3], pz[3], e[3], w, Jp[18], Jx[9];
       bool stereo;
+      const double* K;
       map_point(Rt, X, pc);
       edge_eval3(W, o, pc, K, sp, delta, robust, e, pz, w, stereo);
       edge_jac_pose(pz, K, Jp);
@@ -558,8 +567,8 @@ __device__ void backsub_phase_s(const Scope& sc, const BAWin& W, int cur, double
         s1 += Jp[6 + a] * xa;
       }
       if (stereo) {
-        edge_jac_pose_right(pz, Jp, sp.bf, Jp + 12);
-        edge_jac_point_right(Rt, pz, Jx, sp.bf, Jx + 6);
+        edge_jac_pose_right(pz, Jp, K[4], Jp + 12);
+        edge_jac_point_right(Rt, pz, Jx, K[4], Jx + 6);
 #pragma unroll
         for (int a = 0; a < 6; a++) s2 += Jp[12 + a] * __ldcg(W.xp + cf * 6 + a);
       } else {
@@ -588,6 +597,7 @@ __device__ void backsub_phase_s(const Scope& sc, const BAWin& W, int cur, double
       const double* Rt = camRtT + (size_t)W.ocam[o] * 12;
       double pc[3], pz[3], e[3], w;
       bool stereo;
+      const double* K;
       map_point(Rt, Xn, pc);
       chi_acc += edge_eval3(W, o, pc, K, sp, delta, robust, e, pz, w, stereo);
     }
@@ -1801,7 +1811,7 @@ __device__ LMResult lm_optimize(const Scope& sc, const BAWin& W, const BARun& ru
   constexpr bool SMEM = (MODE >= 1 && MODE <= 3) || MODE == 5;
   constexpr bool PACKED = MODE == 2 || MODE == 3;
   constexpr int NB = MODE == 3 ? 2 : 1;
-  const StereoPar sp = {run.bf, run.delta_s};
+  const StereoPar sp = {run.delta_s};
   WarpStageS sts;
   sts.f = st.f; sts.cf = st.cf; sts.kmax = st.kmax;
   const bool timer = W.stats == run.timing_stats && sc.blk() == 0 && threadIdx.x == 0;
@@ -1997,7 +2007,7 @@ __device__ void window_init(const Scope& sc, const BAWin& W) {
 // classification error of the first pass.  Returns this thread's count of newly excluded edges.
 template <class Scope>
 __device__ double window_classify(const Scope& sc, const BAWin& W, double chi2_thr, int pass, int cur,
-                                  int last_eval, bool have_eval, double bf = 0.0, double chi2_thr_s = 0.0) {
+                                  int last_eval, bool have_eval, double chi2_thr_s = 0.0) {
   const int gt = sc.blk() * blockDim.x + threadIdx.x, gstride = sc.nblk() * blockDim.x;
   const double K[4] = {W.intr[0], W.intr[1], W.intr[2], W.intr[3]};
   double n_l1 = 0.0;
@@ -2010,14 +2020,16 @@ __device__ double window_classify(const Scope& sc, const BAWin& W, double chi2_t
       if (pass == 1 && lev == 1) continue;  // cached chi2 > thr: inlier[] already 0 from pass 0
       map_point(W.camRt[last_eval] + (size_t)c * 12, W.pts[last_eval] + (size_t)l * 3, pc);
       double e2 = 0.0, thr = chi2_thr;
-      if (W.okind && W.okind[o]) {  // stereo edge: third row, threshold cfg.stereo_point (:137-143, :156-160)
+      bool stereo = false;
+      const double* Ke = W.okind ? edge_model(W, o, stereo) : K;  // stereo-capable windows: the edge's camera model
+      if (stereo) {  // stereo edge: third row, threshold cfg.stereo_point (:137-143, :156-160)
         double pz[3];
-        e2 = edge_error(pc, uv.x, uv.y, K, e0, e1, pz);
-        const double er = edge_error_right(pz, W.ur[o], K, bf);
+        e2 = edge_error(pc, uv.x, uv.y, Ke, e0, e1, pz);
+        const double er = edge_error_right(pz, W.ur[o], Ke, Ke[4]);
         e2 = have_eval ? e2 + er * er : 0.0;
         thr = chi2_thr_s;
       } else {
-        e2 = have_eval ? edge_error(pc, uv.x, uv.y, K, e0, e1) : 0.0;
+        e2 = have_eval ? edge_error(pc, uv.x, uv.y, Ke, e0, e1) : 0.0;
       }
       map_point(W.camRt[cur] + (size_t)c * 12, W.pts[cur] + (size_t)l * 3, pc);
       const bool depth_pos = pc[2] > 0.0;
@@ -2076,7 +2088,7 @@ __device__ void solve_window(const Scope& sc, const BAWin& W, const BARun& run, 
       stats->lambda_final[pass] = r.lambda;
       if (pass == 0) stats->chi2_initial = chi_init;
     }
-    const double n_l1 = window_classify(sc, W, run.chi2_thr, pass, cur, last_eval, have_eval, run.bf, run.chi2_thr_s);
+    const double n_l1 = window_classify(sc, W, run.chi2_thr, pass, cur, last_eval, have_eval, run.chi2_thr_s);
     if (pass == 0) {
       double s1[1] = {n_l1}, dummy[1];
       scope_reduce<1, 0>(sc, s1, dummy, W.part, parity, red);

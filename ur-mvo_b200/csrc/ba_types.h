@@ -43,7 +43,9 @@ struct BAWin {
   const double* uv;        // No*2
   const int* ocam;         // No     camera index
   const double* ur;        // No     u_right of a stereo edge (modes 5 / 6), else NULL
-  const uint8_t* okind;    // No     1: stereo edge (EdgeStereoSE3ProjectXYZ), 0: mono edge; NULL in mono windows
+  const uint8_t* okind;    // No     bit 0: stereo edge (EdgeStereoSE3ProjectXYZ) / mono edge, bits 1-7: camera model
+                           //        of the edge (row of intr_tab); NULL in mono single-camera windows
+  const double* intr_tab;  // n_models rows of (fx fy cx cy bf): camera_list[mpc->id_camera]; modes 5 / 6 only
   const int* pt_start;     // Np+1   CSR over observations
   const int* opt;          // No     point index of each observation (packed modes)
   const int* grp_pt;       // n_grp+1 first point of each group: <= 32 observations and points per group
@@ -96,7 +98,6 @@ struct BAWin {
 struct BARun {
   double chi2_thr;
   double delta;        // (double)(float)sqrt(chi2_thr)
-  double bf;           // stereo baseline * fx (camera BF(), src/g2o_optimization.cc:113)
   double chi2_thr_s;   // cfg.stereo_point
   double delta_s;      // (double)(float)sqrt(chi2_thr_s)
   double pcg_tol;

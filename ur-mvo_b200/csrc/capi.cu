@@ -481,7 +481,7 @@ static int ba_plan_create_impl_(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, cons
                                const int32_t* cam, const int32_t* pt, const double* intr,
                                double chi2_thr, int it0, int it1, const urmvo_ba_options* opts,
                                bool sharded, const uint8_t* covis, bool borrow_ws,
-                               const uint8_t* kind, double chi2_thr_stereo, const MapGather* mg);
+                               const uint8_t* kind, double chi2_thr_stereo, const MapGather* mg, int n_models);
 
 // no exception crosses the C ABI: allocation failures of the host-side flattening become a status
 static int ba_plan_create_impl(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, const int32_t* cam_off,
@@ -490,10 +490,11 @@ static int ba_plan_create_impl(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, const
                                const int32_t* cam, const int32_t* pt, const double* intr,
                                double chi2_thr, int it0, int it1, const urmvo_ba_options* opts,
                                bool sharded, const uint8_t* covis, bool borrow_ws = false,
-                               const uint8_t* kind = nullptr, double chi2_thr_stereo = 0.0, const MapGather* mg = nullptr) {
+                               const uint8_t* kind = nullptr, double chi2_thr_stereo = 0.0, const MapGather* mg = nullptr,
+                               int n_models = 0) {
   try {
     return ba_plan_create_impl_(ctx, out, B, cam_off, pt_off, obs_off, poses, fixed, pts, uv, cam, pt, intr, chi2_thr, it0,
-                                it1, opts, sharded, covis, borrow_ws, kind, chi2_thr_stereo, mg);
+                                it1, opts, sharded, covis, borrow_ws, kind, chi2_thr_stereo, mg, n_models);
   } catch (const std::exception& e) {
     if (ctx) ctx->ws_in_use = false;
     if (out) *out = nullptr;
@@ -507,10 +508,13 @@ static int ba_plan_create_impl_(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, cons
                                const int32_t* cam, const int32_t* pt, const double* intr,
                                double chi2_thr, int it0, int it1, const urmvo_ba_options* opts,
                                bool sharded, const uint8_t* covis, bool borrow_ws,
-                               const uint8_t* kind, double chi2_thr_stereo, const MapGather* mg) {
+                               const uint8_t* kind, double chi2_thr_stereo, const MapGather* mg, int n_models) {
   // kind != NULL: stereo-capable window(s): uv carries 3 values per observation (u, v, u_right), intr 5 values
-  // (fx, fy, cx, cy, bf), kind[o] = 1 marks an EdgeStereoSE3ProjectXYZ (reference src/g2o_optimization.cc:96-118)
+  // (fx, fy, cx, cy, bf), kind[o] = 1 marks an EdgeStereoSE3ProjectXYZ (reference src/g2o_optimization.cc:96-118).
+  // n_models > 0: intr is a table of n_models such rows and kind[o] = stereo bit | camera model << 1 — the reference
+  // reads camera_list[mpc->id_camera] per constraint (:86-89, :106-113)
   const bool stereo = kind != nullptr;
+  if (n_models < 0 || n_models > 128 || (n_models > 0 && !stereo)) return fail(URMVO_ERR_ARG, "ba_plan_create: 1..128 camera models, with per-observation kind bytes");
   const int uvs = stereo ? 3 : 2;
   if (!ctx || !out) return fail(URMVO_ERR_ARG, "ba_plan_create: null context / out");
   if (stereo && (sharded || !(chi2_thr_stereo > 0))) return fail(URMVO_ERR_ARG, "ba_plan_create: stereo edges need a positive threshold and are not supported by the point-sharded solve");
@@ -683,8 +687,9 @@ static int ba_plan_create_impl_(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, cons
     const int band_solver = opts ? opts->band_solver : 0;
     p->use_bcr = band_solver != 1 && bcr_shape(p->ncf, wh[0].bw, band_solver == 2, &p->bcr);
     if (p->use_bcr && bcr_prepare(p->bcr) != cudaSuccess) { delete p; return fail(URMVO_ERR_CUDA, "ba_plan_create: cudaFuncSetAttribute failed (cyclic reduction)"); }
-    if (band_smem_bytes(p->band_m, p->ncf) > 220 * 1024) { delete p; return fail(URMVO_ERR_UNSUPPORTED, "local_ba: too many free cameras for the direct band solve"); }
-    if (lg_prepare(p->band_m, p->ncf) != cudaSuccess) { delete p; return fail(URMVO_ERR_CUDA, "ba_plan_create: cudaFuncSetAttribute failed"); }
+    // the sequential band solve keeps the whole right-hand side in shared memory; the cyclic reduction does not
+    if (!p->use_bcr && band_smem_bytes(p->band_m, p->ncf) > 220 * 1024) { delete p; return fail(URMVO_ERR_UNSUPPORTED, "local_ba: too many free cameras for the direct band solve"); }
+    if (lg_prepare(p->band_m, p->use_bcr ? 0 : p->ncf) != cudaSuccess) { delete p; return fail(URMVO_ERR_CUDA, "ba_plan_create: cudaFuncSetAttribute failed"); }
   } else if (p->use_grid) {
     p->grid_blocks = sharded ? shard_grid_capacity(p->threads, p->kmax) : ba_grid_capacity(p->threads, p->kmax, stereo ? 1 : 0);
     if (p->grid_blocks <= 0) { delete p; return fail(URMVO_ERR_CUDA, "ba_plan_create: occupancy query failed"); }
@@ -693,7 +698,6 @@ static int ba_plan_create_impl_(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, cons
   p->run.chi2_thr = chi2_thr;
   p->run.delta = (double)(float)std::sqrt(chi2_thr);  // const float thHuberMonoPoint = sqrt(cfg.mono_point)
   p->stereo = stereo;
-  p->run.bf = stereo ? intr[4] : 0.0;
   p->run.chi2_thr_s = stereo ? chi2_thr_stereo : chi2_thr;
   p->run.delta_s = (double)(float)std::sqrt(p->run.chi2_thr_s);  // const float thHuberStereoPoint = sqrt(cfg.stereo_point)
   p->run.pcg_tol = (opts && opts->pcg_tol > 0) ? opts->pcg_tol : 1e-10;
@@ -710,6 +714,8 @@ static int ba_plan_create_impl_(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, cons
   for (auto& w : wh) sum_grp += w.grp_pt.size();
   const size_t o_ocam = A.take<int>(TO), o_opt = A.take<int>(TO);
   const size_t o_ur = A.take<double>(stereo ? TO : 0), o_okind = A.take<uint8_t>(stereo ? TO : 0);
+  const int n_tab = std::max(n_models, 1);
+  const size_t o_tab = A.take<double>(stereo ? (size_t)5 * n_tab : 0);
   const size_t o_pt_start = A.take<int>(TP + B), o_cam_free = A.take<int>(TC), o_grp = A.take<int>(sum_grp + 1);
   p->off_cam_free = o_cam_free;
   const size_t o_row_ptr = A.take<int>(sum_ncf + B), o_col = A.take<int>(sum_blk);
@@ -816,6 +822,7 @@ static int ba_plan_create_impl_(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, cons
     d.ocam = (const int*)(D + o_ocam) + ob0;
     d.ur = stereo ? (const double*)(D + o_ur) + ob0 : nullptr;
     d.okind = stereo ? (const uint8_t*)(D + o_okind) + ob0 : nullptr;
+    d.intr_tab = stereo ? (const double*)(D + o_tab) : nullptr;
     d.pt_start = (const int*)(D + o_pt_start) + c_pt;
     d.opt = (const int*)(D + o_opt) + ob0;
     d.grp_pt = (const int*)(D + o_grp) + c_grp;
@@ -924,9 +931,16 @@ static int ba_plan_create_impl_(urmvo_ctx* ctx, urmvo_ba_plan** out, int B, cons
     if (stereo) {
       double* hur = (double*)(H + idx_bytes + TO * (sizeof(double) * 2 + 2 * sizeof(int)) + (tile ? TP * 3 * sizeof(double) : 0));
       uint8_t* hk = (uint8_t*)(hur + TO);
-      for (size_t o = 0; o < TO; o++) { hur[o] = uv[(size_t)perm[o] * 3 + 2]; hk[o] = kind[perm[o]] ? 1 : 0; }
+      bool bad_model = false;
+      for (size_t o = 0; o < TO; o++) {
+        hur[o] = uv[(size_t)perm[o] * 3 + 2];
+        hk[o] = n_models > 0 ? kind[perm[o]] : (kind[perm[o]] ? 1 : 0);
+        bad_model = bad_model || (hk[o] >> 1) >= n_tab;
+      }
+      if (bad_model) { urmvo_ba_plan_destroy(p); return fail(URMVO_ERR_ARG, "ba_plan_create: camera model index out of range"); }
       if (e4 == cudaSuccess) e4 = up(o_ur, hur, TO * sizeof(double));
       if (e4 == cudaSuccess) e4 = up(o_okind, hk, TO);
+      if (e4 == cudaSuccess) e4 = up(o_tab, intr, (size_t)5 * n_tab * sizeof(double));
     }
   }
   cudaError_t e6 = cudaMemsetAsync(D + p->off_stats, 0, sizeof(urmvo_ba_stats) * B, s);
@@ -1287,6 +1301,33 @@ extern "C" int urmvo_local_ba_batch_stereo(urmvo_ctx* ctx, int B, const int32_t*
   return rc;
 }
 
+extern "C" int urmvo_local_ba_batch_multicam(urmvo_ctx* ctx, int B, const int32_t* cam_off, const int32_t* pt_off,
+                                             const int32_t* obs_off, double* poses, const uint8_t* fixed, double* pts,
+                                             const double* uv3, const uint8_t* kind_model, const int32_t* cam,
+                                             const int32_t* pt, int n_models, const double* intr5_tab,
+                                             double chi2_thr_mono, double chi2_thr_stereo, int it0, int it1,
+                                             uint8_t* inlier, urmvo_ba_stats* stats, const urmvo_ba_options* opts) {
+  if (!kind_model || n_models <= 0) return fail(URMVO_ERR_ARG, "local_ba_batch_multicam: null kind / model bytes or no camera model");
+  urmvo_ba_plan* p = nullptr;
+  int rc = ba_plan_create_impl(ctx, &p, B, cam_off, pt_off, obs_off, poses, fixed, pts, uv3, cam, pt, intr5_tab, chi2_thr_mono,
+                               it0, it1, opts, false, nullptr, /*borrow_ws=*/true, kind_model, chi2_thr_stereo, nullptr, n_models);
+  if (rc != URMVO_OK) return rc;
+  rc = urmvo_ba_plan_run(p);
+  if (rc == URMVO_OK) rc = urmvo_ba_plan_download(p, poses, pts, inlier, stats);
+  urmvo_ba_plan_destroy(p);
+  return rc;
+}
+
+extern "C" int urmvo_local_ba_multicam(urmvo_ctx* ctx, int Nc, double* poses, const uint8_t* fixed, int Np, double* pts,
+                                       int No, const double* uv3, const uint8_t* kind_model, const int32_t* cam,
+                                       const int32_t* pt, int n_models, const double* intr5_tab, double chi2_thr_mono,
+                                       double chi2_thr_stereo, int it0, int it1, uint8_t* inlier,
+                                       urmvo_ba_stats* stats, const urmvo_ba_options* opts) {
+  const int32_t co[2] = {0, Nc}, po[2] = {0, Np}, oo[2] = {0, No};
+  return urmvo_local_ba_batch_multicam(ctx, 1, co, po, oo, poses, fixed, pts, uv3, kind_model, cam, pt, n_models,
+                                       intr5_tab, chi2_thr_mono, chi2_thr_stereo, it0, it1, inlier, stats, opts);
+}
+
 extern "C" int urmvo_local_ba_stereo(urmvo_ctx* ctx, int Nc, double* poses, const uint8_t* fixed, int Np, double* pts,
                                      int No, const double* uv3, const uint8_t* kind, const int32_t* cam,
                                      const int32_t* pt, const double* intr5, double chi2_thr_mono,
@@ -1320,7 +1361,7 @@ struct urmvo_pose_plan {
          o_ninl = 0, o_iters = 0;
   // stereo edges (EdgeStereoSE3ProjectXYZOnlyPose, reference src/g2o_optimization.cc:235-258)
   bool stereo = false;
-  size_t o_ur = 0, o_kind = 0;
+  size_t o_ur = 0, o_kind = 0, o_tab = 0;
   double bf = 0, chi2_thr_s = 0, delta_s = 0;
 };
 
@@ -1337,8 +1378,11 @@ static int pose_plan_create_impl(urmvo_ctx* ctx, urmvo_pose_plan** out, int B, c
                                       const double* poses, const double* uv, const double* Xw,
                                       const double* intr, double chi2_thr, int rounds, int its_per_round,
                                       const uint8_t* inlier, bool borrow_ws, int uv_stride = 2,
-                                      const uint8_t* kind = nullptr, double chi2_thr_stereo = 0.0) {
+                                      const uint8_t* kind = nullptr, double chi2_thr_stereo = 0.0, int n_models = 0) {
+  // n_models > 0: intr is a table of n_models rows (fx fy cx cy bf) and kind[o] = stereo bit | camera model << 1
+  // (the reference reads camera_list[mpc->id_camera] per constraint, src/g2o_optimization.cc:221-224, :243-250)
   if (!ctx || !out) return fail(URMVO_ERR_ARG, "pose_plan_create: null context / out");
+  if (n_models < 0 || n_models > 128) return fail(URMVO_ERR_ARG, "pose_plan_create: 1..128 camera models");
   *out = nullptr;
   if (B <= 0 || !obs_off || !poses || !uv || !Xw || !intr) return fail(URMVO_ERR_ARG, "pose_plan_create: null or empty input");
   if (rounds < 0 || its_per_round < 0 || !(chi2_thr > 0)) return fail(URMVO_ERR_ARG, "pose_plan_create: bad rounds / threshold");
@@ -1364,6 +1408,7 @@ static int pose_plan_create_impl(urmvo_ctx* ctx, urmvo_pose_plan** out, int B, c
   p->o_off = A.take<int>(B + 1); p->o_pose_in = A.take<double>((size_t)B * 7);
   p->o_uv = A.take<double>(TO * 2); p->o_X = A.take<double>(TO * 3);
   p->o_ur = A.take<double>(stereo ? TO : 0); p->o_kind = A.take<uint8_t>(stereo ? TO : 0);
+  p->o_tab = A.take<double>(stereo ? (size_t)5 * std::max(n_models, 1) : 0);
   p->o_inl_in = A.take<uint8_t>(TO); p->o_inl = A.take<uint8_t>(TO); p->o_level = A.take<uint8_t>(TO);
   p->o_pose_out = A.take<double>((size_t)B * 7); p->o_ninl = A.take<int>(B); p->o_iters = A.take<int>(B);
   cudaError_t ce = cudaSuccess;
@@ -1387,14 +1432,18 @@ static int pose_plan_create_impl(urmvo_ctx* ctx, urmvo_pose_plan** out, int B, c
   e[0] = cudaMemcpyAsync(p->dev + p->o_off, off.data(), (B + 1) * sizeof(int), cudaMemcpyHostToDevice, s);
   e[1] = cudaMemcpyAsync(p->dev + p->o_pose_in, poses, (size_t)B * 7 * sizeof(double), cudaMemcpyHostToDevice, s);
   std::vector<double> uv2, ur;
+  std::vector<uint8_t> kb;
   if (stereo && TO) {  // split (u, v, u_right) into the mono layout + one extra column
-    uv2.resize(TO * 2); ur.resize(TO);
+    uv2.resize(TO * 2); ur.resize(TO); kb.resize(TO);
     for (size_t o = 0; o < TO; o++) {
       uv2[o * 2] = uv[(o0 + o) * 3]; uv2[o * 2 + 1] = uv[(o0 + o) * 3 + 1]; ur[o] = uv[(o0 + o) * 3 + 2];
+      kb[o] = n_models > 0 ? kind[o0 + o] : (kind[o0 + o] ? 1 : 0);
+      if ((kb[o] >> 1) >= std::max(n_models, 1)) { urmvo_pose_plan_destroy(p); return fail(URMVO_ERR_ARG, "pose_plan_create: camera model index out of range"); }
     }
     e[2] = cudaMemcpyAsync(p->dev + p->o_uv, uv2.data(), TO * 2 * sizeof(double), cudaMemcpyHostToDevice, s);
     if (e[2] == cudaSuccess) e[2] = cudaMemcpyAsync(p->dev + p->o_ur, ur.data(), TO * sizeof(double), cudaMemcpyHostToDevice, s);
-    if (e[2] == cudaSuccess) e[2] = cudaMemcpyAsync(p->dev + p->o_kind, kind + o0, TO, cudaMemcpyHostToDevice, s);
+    if (e[2] == cudaSuccess) e[2] = cudaMemcpyAsync(p->dev + p->o_kind, kb.data(), TO, cudaMemcpyHostToDevice, s);
+    if (e[2] == cudaSuccess) e[2] = cudaMemcpyAsync(p->dev + p->o_tab, intr, (size_t)5 * std::max(n_models, 1) * sizeof(double), cudaMemcpyHostToDevice, s);
   } else
   e[2] = TO ? cudaMemcpyAsync(p->dev + p->o_uv, uv + o0 * 2, TO * 2 * sizeof(double), cudaMemcpyHostToDevice, s) : cudaSuccess;
   e[3] = TO ? cudaMemcpyAsync(p->dev + p->o_X, Xw + o0 * 3, TO * 3 * sizeof(double), cudaMemcpyHostToDevice, s) : cudaSuccess;
@@ -1425,7 +1474,8 @@ extern "C" int urmvo_pose_plan_run(urmvo_pose_plan* p) {
                                    (double*)(p->dev + p->o_pose_out), (int*)(p->dev + p->o_ninl),
                                    (int*)(p->dev + p->o_iters), s,
                                    p->stereo ? (const double*)(p->dev + p->o_ur) : nullptr,
-                                   p->stereo ? (const uint8_t*)(p->dev + p->o_kind) : nullptr, p->bf, p->chi2_thr_s, p->delta_s);
+                                   p->stereo ? (const uint8_t*)(p->dev + p->o_kind) : nullptr,
+                                   p->stereo ? (const double*)(p->dev + p->o_tab) : nullptr, p->chi2_thr_s, p->delta_s);
   if (e != cudaSuccess) return fail(URMVO_ERR_CUDA, std::string("pose kernel launch: ") + cudaGetErrorString(e));
   p->ctx->launches++;
   return URMVO_OK;
@@ -1463,6 +1513,22 @@ extern "C" int urmvo_pose_only_batch_stereo(urmvo_ctx* ctx, int B, const int32_t
   urmvo_pose_plan* p = nullptr;
   int rc = pose_plan_create_impl(ctx, &p, B, obs_off, poses, uv3, Xw, intr5, chi2_thr_mono, rounds, its_per_round, inlier,
                                  true, 3, kind, chi2_thr_stereo);
+  if (rc != URMVO_OK) return rc;
+  rc = urmvo_pose_plan_run(p);
+  if (rc == URMVO_OK) rc = urmvo_pose_plan_download(p, poses, inlier ? inlier + obs_off[0] : nullptr, n_inlier, nullptr);
+  urmvo_pose_plan_destroy(p);
+  return rc;
+}
+
+extern "C" int urmvo_pose_only_batch_multicam(urmvo_ctx* ctx, int B, const int32_t* obs_off, double* poses,
+                                              const double* uv3, const uint8_t* kind_model, const double* Xw,
+                                              int n_models, const double* intr5_tab, double chi2_thr_mono,
+                                              double chi2_thr_stereo, int rounds, int its_per_round, uint8_t* inlier,
+                                              int32_t* n_inlier) {
+  if (n_models <= 0) return fail(URMVO_ERR_ARG, "pose_only_batch_multicam: 1..128 camera models");
+  urmvo_pose_plan* p = nullptr;
+  int rc = pose_plan_create_impl(ctx, &p, B, obs_off, poses, uv3, Xw, intr5_tab, chi2_thr_mono, rounds, its_per_round, inlier,
+                                 true, 3, kind_model, chi2_thr_stereo, n_models);
   if (rc != URMVO_OK) return rc;
   rc = urmvo_pose_plan_run(p);
   if (rc == URMVO_OK) rc = urmvo_pose_plan_download(p, poses, inlier ? inlier + obs_off[0] : nullptr, n_inlier, nullptr);

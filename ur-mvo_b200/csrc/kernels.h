@@ -75,7 +75,7 @@ cudaError_t launch_pose_only(int B, const int* obs_off, const double* pose_in, c
                              const double* Xw, const double* intr, double chi2_thr, double delta,
                              int rounds, int its_per_round, uint8_t* inlier, uint8_t* level,
                              double* pose_out, int* n_inlier, int* lm_iters, cudaStream_t stream,
-                             const double* ur = nullptr, const uint8_t* kind = nullptr, double bf = 0.0,
+                             const double* ur = nullptr, const uint8_t* kind = nullptr, const double* tab = nullptr,
                              double chi2_thr_s = 0.0, double delta_s = 0.0);
 
 // ---- twoview_kernels.cu

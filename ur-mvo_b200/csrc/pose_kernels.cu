@@ -125,11 +125,13 @@ __device__ __forceinline__ bool solve6(const double* Hp, const double* b, double
 // registers (a few spills) so that a batch of up to 2 x #SMs frames is resident at once instead of
 // running a second, partly empty wave — +34 % on 256 frames.
 // STEREO: the frame mixes mono edges and stereo edges (kind[o] = 1: measurement (u, v, u_right), 3-row
-// residual, Huber delta / threshold of cfg.stereo_point); the mono-only instantiation is unchanged.
+// residual, Huber delta / threshold of cfg.stereo_point) and reads the intrinsics of every edge from its camera
+// model row (camera_list[mpc->id_camera]); the mono-only single-camera instantiation is unchanged.
 struct PoseStereo {
   const double* ur;     // per observation, read for stereo edges only
-  const uint8_t* kind;  // per observation
-  double bf, chi2_thr, delta;
+  const uint8_t* kind;  // per observation: stereo bit | camera model << 1
+  const double* tab;    // camera models, rows of (fx fy cx cy bf)
+  double chi2_thr, delta;
 };
 
 template <int MINB, bool STEREO>
@@ -188,12 +190,14 @@ pose_only_kernel(int B, const int* __restrict__ obs_off, const double* __restric
             const double X[3] = {fX[i * 3], fX[i * 3 + 1], fX[i * 3 + 2]};
             double pc[3], e0, e1, w, J[12];
             pose_map(R, tc, X, pc);
-            double e2 = pose_err(pc, fuv[i * 2], fuv[i * 2 + 1], K, e0, e1);
-            const bool st = STEREO && fkind[i];
+            const unsigned kb = STEREO ? fkind[i] : 0u;  // stereo bit | camera model << 1
+            const bool st = STEREO && (kb & 1u);
+            const double* Ke = STEREO ? sp.tab + 5 * (kb >> 1) : K;  // camera_list[mpc->id_camera] (:221-224)
+            double e2 = pose_err(pc, fuv[i * 2], fuv[i * 2 + 1], Ke, e0, e1);
             double er = 0.0;
-            if (st) { er = pose_err_right(pc, fur[i], K, sp.bf); e2 += er * er; }
+            if (st) { er = pose_err_right(pc, fur[i], Ke, Ke[4]); e2 += er * er; }
             acc[27] += huber_rho(e2, st ? sp.delta : delta, robust, w);
-            pose_jac(pc, K, J);
+            pose_jac(pc, Ke, J);
             const double r0 = -w * e0, r1 = -w * e1;
             int idx = 0;
 #pragma unroll
@@ -204,7 +208,7 @@ pose_only_kernel(int B, const int* __restrict__ obs_off, const double* __restric
             }
             if (st) {
               double J2[6];
-              pose_jac_right(pc, J, sp.bf, J2);
+              pose_jac_right(pc, J, Ke[4], J2);
               const double r2 = -w * er;
               idx = 0;
 #pragma unroll
@@ -247,9 +251,11 @@ pose_only_kernel(int B, const int* __restrict__ obs_off, const double* __restric
               const double X[3] = {fX[i * 3], fX[i * 3 + 1], fX[i * 3 + 2]};
               double pc[3], e0, e1, w;
               pose_map(Rt, tt, X, pc);
-              double e2 = pose_err(pc, fuv[i * 2], fuv[i * 2 + 1], K, e0, e1);
-              const bool st = STEREO && fkind[i];
-              if (st) { const double er = pose_err_right(pc, fur[i], K, sp.bf); e2 += er * er; }
+              const unsigned kb = STEREO ? fkind[i] : 0u;
+              const bool st = STEREO && (kb & 1u);
+              const double* Ke = STEREO ? sp.tab + 5 * (kb >> 1) : K;
+              double e2 = pose_err(pc, fuv[i * 2], fuv[i * 2 + 1], Ke, e0, e1);
+              if (st) { const double er = pose_err_right(pc, fur[i], Ke, Ke[4]); e2 += er * er; }
               tchi[0] += huber_rho(e2, st ? sp.delta : delta, robust, w);
             }
             block_sum<1>(tchi, red);
@@ -297,9 +303,11 @@ pose_only_kernel(int B, const int* __restrict__ obs_off, const double* __restric
         const bool was_inl = finl[i] != 0;
         if (!was_inl || flev[i]) pose_map(Rc, tc, X, pc);
         else pose_map(Rl, tle, X, pc);
-        double e2 = pose_err(pc, fuv[i * 2], fuv[i * 2 + 1], K, e0, e1);
-        const bool st = STEREO && fkind[i];
-        if (st) { const double er = pose_err_right(pc, fur[i], K, sp.bf); e2 += er * er; }
+        const unsigned kb = STEREO ? fkind[i] : 0u;
+        const bool st = STEREO && (kb & 1u);
+        const double* Ke = STEREO ? sp.tab + 5 * (kb >> 1) : K;
+        double e2 = pose_err(pc, fuv[i * 2], fuv[i * 2 + 1], Ke, e0, e1);
+        if (st) { const double er = pose_err_right(pc, fur[i], Ke, Ke[4]); e2 += er * er; }
         const float chi2 = (float)e2;  // :277 / :297
         if ((double)chi2 > (st ? sp.chi2_thr : chi2_thr)) { finl[i] = 0; flev[i] = 1; nout[0] += 1.0; }
         else { finl[i] = 1; flev[i] = 0; }
@@ -321,22 +329,22 @@ pose_only_kernel(int B, const int* __restrict__ obs_off, const double* __restric
   }
 }
 
-// ur / kind non-null: stereo edges present (bf, chi2_thr_s, delta_s describe them).
+// ur / kind / tab non-null: stereo-capable frames (tab = camera model rows, chi2_thr_s, delta_s for the stereo edges).
 cudaError_t launch_pose_only(int B, const int* obs_off, const double* pose_in, const double* uv,
                              const double* Xw, const double* intr, double chi2_thr, double delta,
                              int rounds, int its_per_round, uint8_t* inlier, uint8_t* level,
                              double* pose_out, int* n_inlier, int* lm_iters, cudaStream_t stream,
-                             const double* ur, const uint8_t* kind, double bf, double chi2_thr_s, double delta_s) {
+                             const double* ur, const uint8_t* kind, const double* tab, double chi2_thr_s, double delta_s) {
   if (B <= 0) return cudaSuccess;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const PoseStereo sp = {ur, kind, bf, chi2_thr_s, delta_s};
+  const PoseStereo sp = {ur, kind, tab, chi2_thr_s, delta_s};
 #define URMVO_POSE_LAUNCH(MINB, ST)                                                                              \
   pose_only_kernel<MINB, ST><<<B, 256, 0, stream>>>(B, obs_off, pose_in, uv, Xw, intr[0], intr[1], intr[2], intr[3], \
                                                     chi2_thr, delta, rounds, its_per_round, inlier, level, pose_out, \
                                                     n_inlier, lm_iters, sp)
-  const bool stereo = ur != nullptr && kind != nullptr;
+  const bool stereo = ur != nullptr && kind != nullptr && tab != nullptr;
   if (B > sms) { if (stereo) URMVO_POSE_LAUNCH(2, true); else URMVO_POSE_LAUNCH(2, false); }
   else { if (stereo) URMVO_POSE_LAUNCH(1, true); else URMVO_POSE_LAUNCH(1, false); }
 #undef URMVO_POSE_LAUNCH

@@ -9,7 +9,8 @@ _LIB = None
 EXPORTED_SYMBOLS = [
     "urmvo_version", "urmvo_last_error", "urmvo_create", "urmvo_destroy", "urmvo_stream", "urmvo_sync",
     "urmvo_launch_count", "urmvo_local_ba", "urmvo_local_ba_batch", "urmvo_local_ba_stereo", "urmvo_local_ba_batch_stereo",
-    "urmvo_pose_only_batch_stereo", "urmvo_ba_plan_create",
+    "urmvo_pose_only_batch_stereo", "urmvo_local_ba_multicam", "urmvo_local_ba_batch_multicam", "urmvo_pose_only_batch_multicam",
+    "urmvo_ba_plan_create",
     "urmvo_ba_plan_run", "urmvo_ba_plan_download", "urmvo_ba_plan_destroy", "urmvo_ba_plan_phase_info", "urmvo_debug_ba_timing", "urmvo_debug_lg_timing", "urmvo_nccl_unique_id", "urmvo_comm_init", "urmvo_ba_covisibility",
     "urmvo_sharded_ba_create", "urmvo_sharded_ba_run", "urmvo_pose_only_batch",
     "urmvo_pose_plan_create", "urmvo_pose_plan_run", "urmvo_pose_plan_download", "urmvo_pose_plan_destroy",
@@ -219,6 +220,36 @@ class Context:
                                                     _p(Xw), _p(intr5), C.c_double(chi2_thr), C.c_double(chi2_thr_stereo),
                                                     C.c_int(rounds), C.c_int(its), _p(inl), _p(n_inl)),
                "urmvo_pose_only_batch_stereo")
+        return poses, inl, n_inl
+
+    def local_ba_multicam(self, prob, chi2_thr=10.0, chi2_thr_stereo=75.0, it0=10, it1=5, opts=None):
+        """Several camera models in one window (camera_list[mpc->id_camera]): prob has uv3 (No, 3),
+        kind_model (No,) = stereo bit | model << 1, intr5_tab (n_models, 5)."""
+        poses = _f64(prob["poses"]).copy(); pts = _f64(prob["pts"]).copy()
+        fixed = _u8(prob["fixed"]); uv3 = _f64(prob["uv3"]); km = _u8(prob["kind_model"])
+        cam = _i32(prob["obs_cam"]); pt = _i32(prob["obs_pt"]); tab = _f64(prob["intr5_tab"]).reshape(-1, 5)
+        inl = np.zeros(uv3.shape[0], dtype=np.uint8)
+        st = BAStats()
+        _check(self._L.urmvo_local_ba_multicam(self._h, C.c_int(poses.shape[0]), _p(poses), _p(fixed), C.c_int(pts.shape[0]),
+                                               _p(pts), C.c_int(uv3.shape[0]), _p(uv3), _p(km), _p(cam), _p(pt),
+                                               C.c_int(tab.shape[0]), _p(tab), C.c_double(chi2_thr),
+                                               C.c_double(chi2_thr_stereo), C.c_int(it0), C.c_int(it1), _p(inl),
+                                               C.byref(st), C.byref(opts) if opts is not None else None),
+               "urmvo_local_ba_multicam")
+        return poses, pts, inl, st
+
+    def pose_only_batch_multicam(self, batch, chi2_thr=10.0, chi2_thr_stereo=75.0, rounds=4, its=10, inlier=None):
+        """batch: uv3 (No, 3), kind_model (No,), Xw, obs_offset, poses, intr5_tab (n_models, 5)."""
+        poses = _f64(batch["poses"]).copy()
+        off = _i32(batch["obs_offset"]); uv3 = _f64(batch["uv3"]); km = _u8(batch["kind_model"]); Xw = _f64(batch["Xw"])
+        tab = _f64(batch["intr5_tab"]).reshape(-1, 5)
+        inl = np.ones(uv3.shape[0], dtype=np.uint8) if inlier is None else _u8(inlier).copy()
+        n_inl = np.zeros(poses.shape[0], dtype=np.int32)
+        _check(self._L.urmvo_pose_only_batch_multicam(self._h, C.c_int(poses.shape[0]), _p(off), _p(poses), _p(uv3), _p(km),
+                                                      _p(Xw), C.c_int(tab.shape[0]), _p(tab), C.c_double(chi2_thr),
+                                                      C.c_double(chi2_thr_stereo), C.c_int(rounds), C.c_int(its),
+                                                      _p(inl), _p(n_inl)),
+               "urmvo_pose_only_batch_multicam")
         return poses, inl, n_inl
 
     def local_ba_batch(self, batch, chi2_thr=10.0, it0=10, it1=5, opts=None, out=None):

@@ -159,6 +159,36 @@ def make_pose_batch_stereo(seed, B=8, n_obs=300, stereo_frac=0.6, outlier_frac=0
     return out
 
 
+def add_camera_models(prob, seed, n_models=3):
+    """Gives every observation of a stereo-capable problem (uv3 / kind / intr5) one of n_models camera models, the
+    way the reference reads camera_list[mpc->id_camera] per constraint (src/g2o_optimization.cc:86-89): model 0 is
+    the base camera, the others have focal lengths within 15 %, shifted principal points and their own baseline;
+    the measurements are re-expressed in their model (sub-pixel, not re-rounded).  Adds intr5_tab (n_models, 5) and
+    kind_model = stereo bit | model << 1."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    base = np.asarray(prob["intr5"], dtype=np.float64)
+    tab = np.tile(base, (n_models, 1))
+    for m in range(1, n_models):
+        s = 1.0 + 0.15 * rng.uniform(-1, 1)
+        tab[m] = [base[0] * s, base[1] * s * (1.0 + 0.01 * rng.uniform(-1, 1)), base[2] + rng.uniform(-12, 12),
+                  base[3] + rng.uniform(-12, 12), base[4] * rng.uniform(0.7, 1.4)]
+    uv3 = np.asarray(prob["uv3"], dtype=np.float64)
+    kind = np.asarray(prob["kind"], dtype=np.uint8)
+    model = rng.integers(0, n_models, size=uv3.shape[0])
+    K = tab[model]
+    xn = (uv3[:, 0] - base[2]) / base[0]
+    yn = (uv3[:, 1] - base[3]) / base[1]
+    disp = (uv3[:, 0] - uv3[:, 2]) / base[4]  # 1 / z as the base camera measured it
+    u = K[:, 0] * xn + K[:, 2]
+    v = K[:, 1] * yn + K[:, 3]
+    ur = np.where(kind != 0, u - K[:, 4] * disp, 0.0)
+    out = dict(prob)
+    out["uv3"] = np.ascontiguousarray(np.c_[u, v, ur])
+    out["intr5_tab"] = tab
+    out["kind_model"] = (kind | (model << 1)).astype(np.uint8)
+    return out
+
+
 def cfg1(seed=1001):
     """10 keyframes (ids 0,1,2 fixed by src/mapping.cc:355-356), 2000 points, ~15k observations."""
     return make_ba(seed, 10, 2000, 7.7, 10, 3, 0.05)
