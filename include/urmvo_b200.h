@@ -278,14 +278,17 @@ void urmvo_tv_plan_destroy(urmvo_tv_plan* plan);
 /* ---- per-frame outlier rejection of the matcher -----------------------
  * Replaces the OpenCV call of reference src/point_matching.cc:53
  *     cv::findFundamentalMat(points0, points1, cv::FM_RANSAC, 3, 0.99, inliers);
- * (default maxIters 1000) for N >= 15 correspondences: same cv::RNG subset sequence, same 7-point
- * models, same error and threshold rule, same "strictly more inliers wins, then shrink the
- * iteration budget" replay, hence the same inlier flags as OpenCV.  Below 15 points OpenCV takes
- * its direct 7-point / LMedS branches; those stay with the reference's own call,
- * and this entry point returns URMVO_ERR_UNSUPPORTED. */
+ * (default maxIters 1000): same cv::RNG subset sequence, same 7-point models, same error and threshold rule,
+ * same "strictly more inliers wins, then shrink the iteration budget" replay, hence the same inlier flags as
+ * OpenCV.  Below 15 points OpenCV leaves the RANSAC branch and so does this call: N == 7 solves the seven
+ * points directly and flags every match; 8 <= N <= 14 is LMedS (median of the float errors, sigma = 2.5 * 1.4826
+ * * (1 + 5 / (N - 7)) * sqrt(median)).  N == 7 and N == 14 reproduce the real OpenCV bit for bit; for 8 <= N <= 13
+ * the median is the rounding noise of an exactly-fitted sample point (~1e-27), so the result is a valid LMedS
+ * answer but no two implementations (two OpenCV builds included) agree on it.  N < 7: URMVO_ERR_UNSUPPORTED
+ * (OpenCV returns an empty matrix and leaves the mask untouched). */
 typedef struct {
   int32_t found;      /* 1: a model with >= 7 inliers exists (cv: non-empty F) */
-  int32_t iters;      /* RANSAC iterations the sequential loop would have run */
+  int32_t iters;      /* RANSAC / LMedS iterations the sequential loop would have run */
   int32_t n_inliers;
   int32_t n_models;   /* 7-point models produced by the evaluated iterations */
   double F[9];        /* row-major, F33 = 1 (p1^T F p0 = 0) */

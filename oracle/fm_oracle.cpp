@@ -19,8 +19,13 @@
 //   cv::solveCubic
 //   FMEstimatorCallback::computeError (max of the two squared point-line distances, float result)
 //   findInliers (err <= (float)(thr*thr)), best = strictly more inliers, RANSACUpdateNumIters
-// Only the N >= 15 branch (FM_RANSAC) is restated: below 15 points OpenCV switches to LMedS, which
-// stays with the reference's own call.
+// Below 15 points cv::findFundamentalMat leaves the RANSAC branch (fundam.cpp): N == 7 runs the 7-point solver once
+// and sets every mask byte to 1; 8 <= N <= 14 runs LMeDSPointSetRegistrator::run (outlier ratio 0.45 -> 300
+// iterations, median = the count/2-th smallest float error, sigma = 2.5 * 1.4826 * (1 + 5 / (N - 7)) * sqrt(median)).
+// urmvo_oracle_find_fundamental restates the whole dispatch.  For 8 <= N <= 13 the count/2-th smallest error is
+// one of the seven exactly-fitted sample points (~1e-27): the winner is decided by rounding noise of the solver —
+// the restatement is the same algorithm, but no two builds of it (OpenCV's own included) agree bit for bit there;
+// N == 7 and N == 14 are pinned against the real cv2 (tests/golden/make_golden_fm_small.py).
 // The null space comes from a Householder QR of the transposed 7x9 system instead of the SVD OpenCV
 // calls (LAPACK): any basis of the null space gives the same <= 3 fundamental matrices.
 #include <algorithm>
@@ -354,3 +359,69 @@ extern "C" int urmvo_oracle_fm_ransac(int N, const float* p0, const float* p1, d
   if (stats3) { stats3[0] = iter; stats3[1] = max_good; stats3[2] = models; }
   return max_good > 0 ? 1 : 0;
 }
+
+// LMeDSPointSetRegistrator::run (ptsetreg.cpp) with FMEstimatorCallback, 8 <= N <= 14 in findFundamentalMat.
+static int fm_lmeds(int N, const float* p0, const float* p1, double confidence, int max_iters, uint8_t* mask,
+                    double* F9, int32_t* stats3) {
+  CvRng rng;
+  int niters = std::max(update_num_iters(confidence, 0.45, 7, max_iters), 3), iter = 0, models = 0;
+  double min_median = DBL_MAX, best[9] = {0};
+  std::memset(mask, 0, N);
+  float err[16];
+  for (iter = 0; iter < niters; iter++) {
+    int idx[7];
+    if (!get_subset(p0, p1, N, rng, 10000, idx)) {
+      if (iter == 0) return 0;
+      break;
+    }
+    double F[27];
+    const int nm = run7point(p0, p1, idx, F);
+    if (nm <= 0) continue;
+    for (int k = 0; k < nm; k++) {
+      models++;
+      for (int i = 0; i < N; i++) err[i] = sampson_max(F + 9 * k, p0 + 2 * i, p1 + 2 * i);
+      int32_t bits[16];  // std::nth_element(errf.ptr<int>(), ... + count / 2, ...): ordered as integers
+      std::memcpy(bits, err, sizeof(float) * N);
+      std::sort(bits, bits + N);
+      float med;
+      std::memcpy(&med, &bits[N / 2], sizeof(float));
+      const double median = med;
+      if (median < min_median) { min_median = median; std::memcpy(best, F + 9 * k, sizeof(best)); }
+    }
+  }
+  int count = 0;
+  if (min_median < DBL_MAX) {
+    double sigma = 2.5 * 1.4826 * (1 + 5. / (N - 7)) * std::sqrt(min_median);
+    sigma = std::max(sigma, 0.001);
+    const float t = (float)(sigma * sigma);
+    for (int i = 0; i < N; i++) {
+      mask[i] = sampson_max(best, p0 + 2 * i, p1 + 2 * i) <= t ? 1 : 0;
+      count += mask[i];
+    }
+  }
+  if (F9) std::memcpy(F9, best, sizeof(best));
+  if (stats3) { stats3[0] = iter; stats3[1] = count; stats3[2] = models; }
+  return (min_median < DBL_MAX && count >= 7) ? 1 : 0;
+}
+
+// cv::findFundamentalMat(points0, points1, FM_RANSAC, thresh, confidence, mask) for any N (fundam.cpp):
+// returns 1 if OpenCV returns a matrix, 0 if it returns an empty one (the mask is filled as OpenCV leaves it),
+// -1 for N < 7 (OpenCV returns before it creates the mask).
+extern "C" int urmvo_oracle_find_fundamental(int N, const float* p0, const float* p1, double thresh,
+                                             double confidence, int max_iters, uint8_t* mask, double* F9,
+                                             int32_t* stats3) {
+  if (N < 7) return -1;
+  if (N >= 15) return urmvo_oracle_fm_ransac(N, p0, p1, thresh, confidence, max_iters, mask, F9, stats3);
+  if (confidence < DBL_EPSILON || confidence > 1 - DBL_EPSILON) confidence = 0.99;
+  if (N == 7) {  // direct 7-point solution, every point flagged (mask.setTo(1))
+    const int idx[7] = {0, 1, 2, 3, 4, 5, 6};
+    double F[27];
+    const int nm = run7point(p0, p1, idx, F);
+    std::memset(mask, 1, 7);
+    if (F9) { std::memset(F9, 0, 9 * sizeof(double)); if (nm > 0) std::memcpy(F9, F, 9 * sizeof(double)); }
+    if (stats3) { stats3[0] = 1; stats3[1] = 7; stats3[2] = std::max(nm, 0); }
+    return nm > 0 ? 1 : 0;
+  }
+  return fm_lmeds(N, p0, p1, confidence, std::max(max_iters, 1), mask, F9, stats3);
+}
+

@@ -161,6 +161,13 @@ void urmvo_oracle_svd(int m, int n, const float* A, float* sigma, float* U, floa
  * Returns 1 if a model was found, 0 if none, -1 if N < 15 (OpenCV's 7-point / LMedS branches). */
 int urmvo_oracle_fm_ransac(int N, const float* p0, const float* p1, double thresh, double confidence,
                            int max_iters, uint8_t* mask, double* F9, int32_t* stats3);
+/* The whole cv::findFundamentalMat(..., FM_RANSAC, thresh, confidence, mask) dispatch for any N: N >= 15 as above,
+ * N == 7 the direct 7-point solution with every mask byte 1, 8 <= N <= 14 LMeDSPointSetRegistrator::run (pinned
+ * against the real cv2 for N == 7 and N == 14; for 8..13 the median error is a rounding-noise value of an
+ * exactly-fitted sample point and no two builds agree — see fm_oracle.cpp).  Returns 1 / 0 like OpenCV returns
+ * a matrix / an empty one, -1 for N < 7. */
+int urmvo_oracle_find_fundamental(int N, const float* p0, const float* p1, double thresh, double confidence,
+                                  int max_iters, uint8_t* mask, double* F9, int32_t* stats3);
 /* The 7-index subsets OpenCV's RANSAC draws for iterations 0..max_iters-1 (cv::RNG state -1,
  * collinearity re-draws included).  idx: max_iters*7.  Returns the number of subsets generated. */
 int urmvo_oracle_fm_subsets(int N, const float* p0, const float* p1, int max_iters, int32_t* idx);

@@ -289,6 +289,17 @@ def fm_ransac(p0, p1, thresh=3.0, confidence=0.99, max_iters=1000):
     return dict(found=rc, mask=mask, F=F.reshape(3, 3), iters=int(st[0]), n_inliers=int(st[1]), models=int(st[2]))
 
 
+def find_fundamental(p0, p1, thresh=3.0, confidence=0.99, max_iters=1000):
+    """cv::findFundamentalMat(FM_RANSAC) for any N >= 7 (direct 7-point / LMedS / RANSAC). Same dict as fm_ransac."""
+    p0 = np.ascontiguousarray(p0, dtype=np.float32); p1 = np.ascontiguousarray(p1, dtype=np.float32)
+    N = len(p0)
+    mask = np.zeros(N, dtype=np.uint8); F = np.zeros(9); st = np.zeros(3, dtype=np.int32)
+    lib().urmvo_oracle_find_fundamental.restype = C.c_int
+    rc = lib().urmvo_oracle_find_fundamental(C.c_int(N), _p(p0), _p(p1), C.c_double(thresh), C.c_double(confidence),
+                                             C.c_int(max_iters), _p(mask), _p(F), _p(st))
+    return dict(found=rc, mask=mask, F=F.reshape(3, 3), iters=int(st[0]), n_inliers=int(st[1]), models=int(st[2]))
+
+
 def fm_subsets(p0, p1, max_iters=1000):
     p0 = np.ascontiguousarray(p0, dtype=np.float32); p1 = np.ascontiguousarray(p1, dtype=np.float32)
     idx = np.zeros((max_iters, 7), dtype=np.int32)

@@ -175,15 +175,22 @@ def test_reconstruct_through_the_adapter_uses_glibc_rand_sets(oracle):
 @pytest.mark.gpu
 def test_point_matching_outlier_rejection_through_the_adapter():
     """FindFundamentalInliersGPU (the call of src/point_matching.cc:53) against the committed output
-    of the real cv2.findFundamentalMat; fewer than 15 matches are handed back to the caller."""
+    of the real cv2.findFundamentalMat (RANSAC, and the LMedS / 7-point branches below 15 matches); fewer than 7
+    matches are handed back to the caller."""
     G = np.load(os.path.join(ROOT, "tests", "golden", "golden_fm_r01.npz"))
     for k in (3, 11):
         p0, p1 = G[f"p0_{k}"], G[f"p1_{k}"]
         out = _run("fm", struct.pack("i", len(p0)) + p0.tobytes() + p1.tobytes())
         assert struct.unpack("i", out[:4])[0] == 1
         assert np.array_equal(np.frombuffer(out[4:], dtype=np.uint8), G[f"mask_{k}"])
-    p0, p1 = synth.make_fm(3500, 14, 0.9)
-    out = _run("fm", struct.pack("i", 14) + p0.tobytes() + p1.tobytes())
+    GS = np.load(os.path.join(ROOT, "tests", "golden", "golden_fm_small_r02.npz"))
+    for k in (1, 9):  # N == 7 (every match flagged) and N == 14 (LMedS)
+        p0, p1 = GS[f"p0_{k}"], GS[f"p1_{k}"]
+        out = _run("fm", struct.pack("i", len(p0)) + p0.tobytes() + p1.tobytes())
+        assert struct.unpack("i", out[:4])[0] == 1
+        assert np.array_equal(np.frombuffer(out[4:], dtype=np.uint8), GS[f"mask_{k}"])
+    p0, p1 = synth.make_fm(3500, 6, 0.9)
+    out = _run("fm", struct.pack("i", 6) + p0.tobytes() + p1.tobytes())
     assert struct.unpack("i", out[:4])[0] == 0 and set(out[4:]) == {7}  # untouched
 
 

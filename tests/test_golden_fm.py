@@ -87,3 +87,48 @@ def test_error_is_max_of_squared_point_line_distances(oracle):
 def test_below_15_points_is_not_this_path(oracle):
     p0, p1 = synth.make_fm(2023, 14, 0.9)
     assert oracle.fm_ransac(p0, p1)["found"] == -1
+
+
+# ------------------------------------------------------------------ fewer than 15 matches (7-point / LMedS branches)
+
+GS = np.load(os.path.join(GOLDEN, "golden_fm_small_r02.npz"))
+
+
+@pytest.mark.parametrize("k", range(int(GS["n_cases"])))
+def test_oracle_reproduces_opencv_below_15_matches(oracle, k):
+    """N == 7: cv::findFundamentalMat solves the 7 points directly and flags every match; N == 14: LMedS, where
+    the median is the smallest error outside the 7-point sample.  Both reproduce the real cv2 bit for bit."""
+    p0, p1 = GS[f"p0_{k}"], GS[f"p1_{k}"]
+    o = oracle.find_fundamental(p0, p1, 3.0, 0.99, 1000)
+    assert o["found"] == int(GS[f"found_{k}"])
+    assert np.array_equal(o["mask"], GS[f"mask_{k}"])
+    Fs = [f for f in GS[f"F_{k}"].reshape(3, 3, 3) if f[2, 2] != 0]
+    if len(p0) == 7:  # the same set of <= 3 solutions (cv2 orders them by its own null-space basis)
+        mine = oracle.fm_run7(p0, p1)
+        assert len(mine) == len(Fs) and o["models"] == len(Fs)
+        for f in Fs:
+            assert min(np.abs(m - f).max() for m in mine) < 1e-7 * max(1.0, np.abs(f).max())
+        assert min(np.abs(o["F"] - f).max() for f in Fs) < 1e-7 * max(1.0, np.abs(o["F"]).max())
+    else:
+        assert np.abs(o["F"] - Fs[0]).max() < 1e-7 * max(1.0, np.abs(Fs[0]).max())
+
+
+def test_lmeds_between_8_and_13_matches_is_the_same_algorithm_but_not_reproducible(oracle):
+    """8 <= N <= 13: the count/2-th smallest error belongs to an exactly-fitted sample point (~1e-27), so the winner
+    is rounding noise (the generator recorded 1-28 % agreement with cv2).  What is checkable: the result is a valid
+    LMedS answer — the seven points of some sample are inliers of the returned model and sigma follows the rule."""
+    agree = GS["agree_8_13"]
+    assert (agree[:, 0] < agree[:, 1]).all()  # cv2 itself is not reproduced there — documented, not hidden
+    for n in range(8, 14):
+        p0, p1 = synth.make_fm(7000 + n, n, 0.8, 0.5, 4.0)
+        o = oracle.find_fundamental(p0, p1)
+        assert o["iters"] == 300 and o["mask"].sum() >= 7 and o["found"] == 1
+        err = oracle.fm_errors(p0, p1, o["F"])
+        assert np.sort(err)[6] < 1e-12  # seven exactly-fitted points
+
+
+def test_find_fundamental_dispatch(oracle):
+    p0, p1 = synth.make_fm(7100, 40, 0.7)
+    a, b = oracle.find_fundamental(p0, p1), oracle.fm_ransac(p0, p1)
+    assert np.array_equal(a["mask"], b["mask"]) and a["iters"] == b["iters"]
+    assert oracle.find_fundamental(p0[:6], p1[:6])["found"] == -1

@@ -34,7 +34,7 @@ bool FindFundamentalInliersGPU(const std::vector<cv::Point2f>& points0, const st
   static_assert(sizeof(cv::Point2f) == 2 * sizeof(float), "cv::Point2f must be two packed floats");
   const int n = (int)points0.size();
   g_fm_status = URMVO_ERR_UNSUPPORTED;
-  if (n < 15 || points1.size() != points0.size()) return false;  // OpenCV's direct 7-point / LMedS branches
+  if (n < 7 || points1.size() != points0.size()) return false;  // OpenCV: empty matrix, mask never created
   urmvo_ctx* ctx = fm_context();
   if (!ctx) {
     g_fm_status = URMVO_ERR_NO_DEVICE;

@@ -9,8 +9,8 @@
 //     cv::findFundamentalMat(points0, points1, cv::FM_RANSAC, 3, 0.99, inliers);
 // does, on the GPU.  Returns true when the GPU path handled the call.  Returns false — leaving
 // `inliers` untouched — in two cases the caller can tell apart with FindFundamentalInliersStatus():
-//   URMVO_ERR_UNSUPPORTED  fewer than 15 correspondences (OpenCV's direct 7-point / LMedS branches): make the
-//                          original OpenCV call, see INTEGRATION.md;
+//   URMVO_ERR_UNSUPPORTED  fewer than 7 correspondences (OpenCV returns an empty matrix and does not create the mask;
+//                          the reference then reads inliers[i] of an empty vector): keep the original call;
 //   any other status       the GPU call failed (no B200, a CUDA error such as a failed allocation): the message is
 //                          in urmvo_last_error(); nothing aborts — keep the OpenCV call for this frame or stop.
 bool FindFundamentalInliersGPU(const std::vector<cv::Point2f>& points0, const std::vector<cv::Point2f>& points1,

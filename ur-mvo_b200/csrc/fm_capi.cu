@@ -8,6 +8,14 @@
 //   * replaying "goodCount > max(maxGoodCount, 6) -> new best, niters = RANSACUpdateNumIters(...)"
 //     over the per-(iteration, model) inlier counts the device returns.
 // The models, the errors and the inlier flags are computed by fm_kernels.cu.  No CPU fallback.
+//
+// Fewer than 15 matches (cv::findFundamentalMat leaves the RANSAC branch, fundam.cpp): N == 7 solves the seven
+// points once and flags every match; 8 <= N <= 14 is LMeDSPointSetRegistrator::run — a fixed budget
+// (RANSACUpdateNumIters(confidence, 0.45, 7, max_iters), at least 3), the score of a model is its median error
+// (computed on the device), the first strictly smaller median wins, and the inliers are the matches within
+// sigma = 2.5 * 1.4826 * (1 + 5 / (N - 7)) * sqrt(median).  N == 7 and N == 14 reproduce the real OpenCV bit
+// for bit; for 8 <= N <= 13 the median is the rounding noise of an exactly-fitted sample point and no two
+// implementations agree — the call still returns a valid LMedS answer.
 #include <cfloat>
 #include <cmath>
 #include <cstring>
@@ -90,6 +98,8 @@ constexpr int kFirstRound = 256;  // iterations evaluated before the budget is k
 struct FmProblem {
   CvRng rng;
   int N = 0, base = 0;
+  int mode = 0;               // 0: RANSAC (N >= 15), 1: LMedS (8..14), 2: direct 7-point (N == 7)
+  double min_median = DBL_MAX;
   int niters = 0, iter = 0, max_good = 0, models = 0, win = -1;  // win = hyp_id*3 + slot
   bool done = false;
   int pos = 0, cnt = 0;  // slice of the current round
@@ -125,7 +135,8 @@ struct urmvo_fm_plan {
          o_winF = 0, o_mask = 0, bytes = 0;
   // pinned host block
   unsigned char* hb = nullptr;
-  int *h_ids = nullptr, *h_sets = nullptr, *h_nmod = nullptr, *h_counts = nullptr, *h_win = nullptr;
+  int *h_ids = nullptr, *h_sets = nullptr, *h_nmod = nullptr, *h_counts = nullptr, *h_win = nullptr;  // h_win: [win | thr bits]
+  bool any_small = false;  // a problem with fewer than 15 matches
   double* h_winF = nullptr;
   uint8_t* h_mask = nullptr;
   size_t round_cap = 0;  // hypotheses one round can hold
@@ -156,10 +167,10 @@ static int fm_plan_create_impl(urmvo_ctx* ctx, urmvo_fm_plan** out, int B, const
   for (int b = 0; b < B; b++) {
     const int n = off[b + 1] - off[b];
     if (n < 0) return set_error(URMVO_ERR_ARG, "fm_plan_create: offsets must ascend");
-    if (n < 15)
+    if (n < 7)
       return set_error(URMVO_ERR_UNSUPPORTED,
-                       "fm_ransac: fewer than 15 correspondences (OpenCV's 7-point / LMedS branch; keep the "
-                       "reference's own cv::findFundamentalMat call for these)");
+                       "fm_ransac: fewer than 7 correspondences (cv::findFundamentalMat returns an empty matrix and "
+                       "leaves the mask untouched)");
     max_n = std::max(max_n, n);
   }
   if ((long long)B * max_iters > (1ll << 24)) return set_error(URMVO_ERR_ARG, "fm_plan_create: B * max_iters exceeds 2^24 hypotheses (3.6 GB of models); split the batch");
@@ -173,7 +184,11 @@ static int fm_plan_create_impl(urmvo_ctx* ctx, urmvo_fm_plan** out, int B, const
   p->p0.assign(pts0, pts0 + 2 * (size_t)p->total_n);
   p->p1.assign(pts1, pts1 + 2 * (size_t)p->total_n);
   p->prob.resize(B);
-  for (int b = 0; b < B; b++) { p->prob[b].N = off[b + 1] - off[b]; p->prob[b].base = off[b]; }
+  for (int b = 0; b < B; b++) {
+    p->prob[b].N = off[b + 1] - off[b]; p->prob[b].base = off[b];
+    p->prob[b].mode = p->prob[b].N >= 15 ? 0 : (p->prob[b].N == 7 ? 2 : 1);
+    p->any_small = p->any_small || p->prob[b].mode != 0;
+  }
   const size_t T = (size_t)p->total_n, H = (size_t)B * max_iters;
   p->round_cap = H;  // a round never holds more than every remaining iteration of every problem
   auto take = [&](size_t bytes) { size_t o = p->bytes; p->bytes = (p->bytes + bytes + 255) / 256 * 256; return o; };
@@ -184,7 +199,7 @@ static int fm_plan_create_impl(urmvo_ctx* ctx, urmvo_fm_plan** out, int B, const
   p->o_sets = take(H * 7 * sizeof(int));
   p->o_nmod = take(H * sizeof(int));
   p->o_counts = take(H * 3 * sizeof(int));
-  p->o_win = take((size_t)B * sizeof(int));
+  p->o_win = take((size_t)2 * B * sizeof(int));  // [winning model | the problem's own threshold]
   p->o_winF = take((size_t)B * 9 * sizeof(double));
   p->o_mask = take(T);
   cudaError_t e = cudaSuccess;
@@ -202,7 +217,7 @@ static int fm_plan_create_impl(urmvo_ctx* ctx, urmvo_fm_plan** out, int B, const
   if (e != cudaSuccess) { delete p; return set_error(URMVO_ERR_CUDA, std::string("cudaMalloc fm plan: ") + cudaGetErrorString(e)); }
   // pinned: [winF | ids | sets | nmod | counts | win | mask | pts staging]
   const size_t b_winF = (size_t)B * 9 * sizeof(double), b_ids = H * sizeof(int), b_sets = H * 7 * sizeof(int);
-  const size_t b_nmod = H * sizeof(int), b_counts = H * 3 * sizeof(int), b_win = (size_t)B * sizeof(int);
+  const size_t b_nmod = H * sizeof(int), b_counts = H * 3 * sizeof(int), b_win = (size_t)2 * B * sizeof(int);
   const size_t b_mask = (T + 15) / 16 * 16, b_pts = T * sizeof(float4);
   const size_t hb_bytes = b_winF + b_ids + b_sets + b_nmod + b_counts + b_win + b_mask + b_pts + 64;
   unsigned char* hb = nullptr;
@@ -256,6 +271,10 @@ extern "C" int urmvo_fm_plan_run(urmvo_fm_plan* p) {
     pr.rng = CvRng();
     pr.niters = std::max(p->max_iters, 1);
     pr.iter = 0; pr.max_good = 0; pr.models = 0; pr.win = -1; pr.done = false;
+    pr.min_median = DBL_MAX;
+    if (pr.mode == 1)  // OpenCV: at least 3; never more than the hypothesis store of the plan holds per problem
+      pr.niters = std::min(std::max(update_num_iters(p->confidence, 0.45, 7, std::max(p->max_iters, 1)), 3), std::max(p->max_iters, 1));
+    if (pr.mode == 2) pr.niters = 1;
   }
   p->evaluated = 0;
   for (int round = 0;; round++) {
@@ -265,7 +284,7 @@ extern "C" int urmvo_fm_plan_run(urmvo_fm_plan* p) {
     for (int b = 0; b < p->B; b++) {
       FmProblem& pr = p->prob[b];
       if (pr.done) continue;
-      const int want = round == 0 ? std::min(pr.niters, kFirstRound) : pr.niters - pr.iter;
+      const int want = round == 0 ? (pr.mode ? pr.niters : std::min(pr.niters, kFirstRound)) : pr.niters - pr.iter;
       if (want <= 0) { pr.done = true; continue; }
       pr.pos = n; pr.cnt = want;
       n += want;
@@ -275,8 +294,13 @@ extern "C" int urmvo_fm_plan_run(urmvo_fm_plan* p) {
     // ---- host: draw the subsets of the round (cv::RNG chains, one per problem)
     parallel_over((int)active.size(), [&](int a) {
       FmProblem& pr = p->prob[active[a]];
-      const int got = draw_subsets(pr.rng, p->p0.data() + 2 * (size_t)pr.base, p->p1.data() + 2 * (size_t)pr.base, pr.N,
-                                   pr.cnt, pr.base, p->h_sets + (size_t)pr.pos * 7);
+      int got = 1;
+      if (pr.mode == 2) {  // the seven matches themselves, no draw
+        for (int k = 0; k < 7; k++) p->h_sets[(size_t)pr.pos * 7 + k] = pr.base + k;
+      } else {
+        got = draw_subsets(pr.rng, p->p0.data() + 2 * (size_t)pr.base, p->p1.data() + 2 * (size_t)pr.base, pr.N,
+                           pr.cnt, pr.base, p->h_sets + (size_t)pr.pos * 7);
+      }
       for (int i = 0; i < pr.cnt; i++) p->h_ids[pr.pos + i] = active[a] * p->max_iters + pr.iter + i;
       // subsets past an exhausted attempt budget are never evaluated: mark them with the first one
       for (int i = got; i < pr.cnt; i++)
@@ -302,6 +326,26 @@ extern "C" int urmvo_fm_plan_run(urmvo_fm_plan* p) {
       bool exhausted = false;
       if (avail < 0) { avail = -avail - 1; exhausted = true; }
       int i = 0;
+      if (pr.mode == 2) {  // direct solution: the first of the <= 3 models, every match flagged
+        const int nm = p->h_nmod[pr.pos];
+        pr.models = nm; pr.iter = 1; pr.max_good = nm > 0 ? 7 : 0;
+        pr.win = nm > 0 ? p->h_ids[pr.pos] * 3 : -1;
+        pr.done = true;
+        continue;
+      }
+      if (pr.mode == 1) {  // LMeDSPointSetRegistrator::run: the first strictly smaller median wins
+        for (; i < avail && pr.iter < pr.niters; i++, pr.iter++) {
+          const int nm = p->h_nmod[pr.pos + i];
+          for (int k = 0; k < nm; k++) {
+            pr.models++;
+            float med;
+            std::memcpy(&med, &p->h_counts[(size_t)(pr.pos + i) * 3 + k], sizeof(float));
+            if ((double)med < pr.min_median) { pr.min_median = (double)med; pr.win = p->h_ids[pr.pos + i] * 3 + k; }
+          }
+        }
+        pr.done = true;  // the whole budget was one round (or the draws ran out)
+        continue;
+      }
       for (; i < avail && pr.iter < pr.niters; i++, pr.iter++) {
         const int nm = p->h_nmod[pr.pos + i];
         for (int k = 0; k < nm; k++) {
@@ -325,22 +369,45 @@ extern "C" int urmvo_fm_plan_finish(urmvo_fm_plan* p, uint8_t* inlier, urmvo_fm_
   CU_TRY(cudaSetDevice(p->ctx->device));
   cudaStream_t s = p->ctx->stream;
   unsigned char* D = p->dev;
-  for (int b = 0; b < p->B; b++) p->h_win[b] = p->prob[b].max_good > 0 ? p->prob[b].win : -1;
-  CU_TRY(cudaMemcpyAsync(D + p->o_win, p->h_win, (size_t)p->B * sizeof(int), cudaMemcpyHostToDevice, s));
+  float* h_thr = (float*)(p->h_win + p->B);
+  for (int b = 0; b < p->B; b++) {
+    const FmProblem& pr = p->prob[b];
+    h_thr[b] = p->thr2;
+    if (pr.mode == 0) {
+      p->h_win[b] = pr.max_good > 0 ? pr.win : -1;
+    } else if (pr.mode == 2) {
+      p->h_win[b] = pr.win;
+      h_thr[b] = -1.f;  // mask.setTo(1), whether or not the solver found a model
+    } else {
+      p->h_win[b] = pr.min_median < DBL_MAX ? pr.win : -1;
+      if (pr.min_median < DBL_MAX) {
+        double sigma = 2.5 * 1.4826 * (1 + 5. / (pr.N - 7)) * std::sqrt(pr.min_median);
+        sigma = std::max(sigma, 0.001);
+        h_thr[b] = (float)(sigma * sigma);
+      }
+    }
+  }
+  CU_TRY(cudaMemcpyAsync(D + p->o_win, p->h_win, (size_t)2 * p->B * sizeof(int), cudaMemcpyHostToDevice, s));
   CU_TRY(launch_fm_mask(p->B, p->max_n, (const int*)(D + p->o_off), (const float4*)(D + p->o_pts),
-                        (const double*)(D + p->o_models), (const int*)(D + p->o_win), p->thr2, D + p->o_mask,
+                        (const double*)(D + p->o_models), (const int*)(D + p->o_win), p->thr2,
+                        p->any_small ? (const float*)(D + p->o_win) + p->B : nullptr, D + p->o_mask,
                         (double*)(D + p->o_winF), s));
   p->ctx->launches += 1;
-  if (inlier) CU_TRY(cudaMemcpyAsync(p->h_mask, D + p->o_mask, (size_t)p->total_n, cudaMemcpyDeviceToHost, s));
+  if (inlier || p->any_small) CU_TRY(cudaMemcpyAsync(p->h_mask, D + p->o_mask, (size_t)p->total_n, cudaMemcpyDeviceToHost, s));
   if (stats) CU_TRY(cudaMemcpyAsync(p->h_winF, D + p->o_winF, (size_t)p->B * 9 * sizeof(double), cudaMemcpyDeviceToHost, s));
   CU_TRY(cudaStreamSynchronize(s));
   if (inlier) std::memcpy(inlier, p->h_mask, (size_t)p->total_n);
   if (stats)
     for (int b = 0; b < p->B; b++) {
       const FmProblem& pr = p->prob[b];
-      stats[b].found = pr.max_good > 0 ? 1 : 0;
+      int good = pr.max_good;
+      if (pr.mode == 1) {  // LMedS: inliers of the winning model under its own sigma; found = at least 7 of them
+        good = 0;
+        for (int i = 0; i < pr.N; i++) good += p->h_mask[pr.base + i];
+      }
+      stats[b].found = pr.mode == 1 ? (pr.min_median < DBL_MAX && good >= 7 ? 1 : 0) : (pr.max_good > 0 ? 1 : 0);
       stats[b].iters = pr.iter;
-      stats[b].n_inliers = pr.max_good;
+      stats[b].n_inliers = pr.mode == 2 ? 7 : good;
       stats[b].n_models = pr.models;
       for (int i = 0; i < 9; i++) stats[b].F[i] = p->h_winF[(size_t)b * 9 + i];
     }

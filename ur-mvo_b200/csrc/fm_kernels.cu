@@ -254,6 +254,33 @@ struct FmThresh {
   double hi;    // tm * (1 + 1e-12)
 };
 
+// FMEstimatorCallback::computeError for one correspondence, OpenCV's expression operation by operation.
+__device__ __forceinline__ float fm_error_exact(const double* F, const float4 m) {
+  const double x1 = m.x, y1 = m.y, x2 = m.z, y2 = m.w;
+  const double a2 = F[0] * x1 + F[1] * y1 + F[2];
+  const double b2 = F[3] * x1 + F[4] * y1 + F[5];
+  const double c2 = F[6] * x1 + F[7] * y1 + F[8];
+  const double s2 = 1. / (a2 * a2 + b2 * b2);
+  const double d2 = x2 * a2 + y2 * b2 + c2;
+  const double a1 = F[0] * x2 + F[3] * y2 + F[6];
+  const double b1 = F[1] * x2 + F[4] * y2 + F[7];
+  const double c1 = F[2] * x2 + F[5] * y2 + F[8];
+  const double s1 = 1. / (a1 * a1 + b1 * b1);
+  const double d1 = x1 * a1 + y1 * b1 + c1;
+  const double e1 = d1 * d1 * s1, e2 = d2 * d2 * s2;
+  return (float)((e1 < e2) ? e2 : e1);  // std::max(e1, e2)
+}
+
+__device__ __forceinline__ FmThresh fm_make_thresh(float t) {
+  // (float)x <= t  <=>  x <= midpoint(t, nextafterf(t, +inf)) up to the tie, which the exact path decides
+  const double tm = 0.5 * ((double)t + (double)nextafterf(t, INFINITY));
+  FmThresh th;
+  th.t = t;
+  th.lo = tm * (1.0 - 1e-12);
+  th.hi = tm * (1.0 + 1e-12);
+  return th;
+}
+
 __device__ __forceinline__ bool fm_inlier(const double* F, const float4 m, const FmThresh th) {
   const double x1 = m.x, y1 = m.y, x2 = m.z, y2 = m.w;
   const double a2 = F[0] * x1 + F[1] * y1 + F[2];
@@ -298,6 +325,20 @@ fm_score_kernel(int n_hyp, const int* __restrict__ hyp_ids, int max_iters, const
     for (int e = 0; e < 9; e++) F[e] = models_all[(size_t)id * 27 + 9 * k + e];
     const int b = id / max_iters;
     const int i0 = off[b], i1 = off[b + 1];
+    if (i1 - i0 < 15) {
+      // fewer than 15 matches: cv::findFundamentalMat runs LMeDSPointSetRegistrator::run — the score of a model is
+      // the count/2-th smallest float error, ordered as integers (std::nth_element on errf.ptr<int>()).  counts[g]
+      // carries the bits of that median.
+      const int n = i1 - i0;
+      const int mine = lane < n ? __float_as_int(fm_error_exact(F, pts[i0 + lane])) : 0x7fffffff;
+      int rank = 0;
+      for (int j = 0; j < n; j++) {
+        const int other = __shfl_sync(0xffffffffu, mine, j);
+        rank += (other < mine || (other == mine && j < lane)) ? 1 : 0;
+      }
+      if (lane < n && rank == n / 2) counts[g] = mine;
+      continue;
+    }
     int good = 0;
     for (int base = i0; base < i1; base += 32) {
       const int j = base + lane;
@@ -310,21 +351,29 @@ fm_score_kernel(int n_hyp, const int* __restrict__ hyp_ids, int max_iters, const
 }
 
 // Inlier flags of the winning model of every problem; win_id[b] = hyp_id*3 + model slot or -1 (no
-// model: all flags 0).  Also gathers the winning models into win_F [B][9].
+// model: all flags 0).  Also gathers the winning models into win_F [B][9].  thr_b[b] = the problem's own squared
+// threshold as a float (the LMedS sigma^2 of problems with fewer than 15 matches); a negative value flags every
+// match (the direct 7-point branch: mask.setTo(1)); thr_b == NULL: th for all.
 __global__ void __launch_bounds__(256)
 fm_mask_kernel(int B, const int* __restrict__ off, const float4* __restrict__ pts,
                const double* __restrict__ models_all, const int* __restrict__ win_id, FmThresh th,
-               uint8_t* __restrict__ mask, double* __restrict__ win_F) {
+               const float* __restrict__ thr_b, uint8_t* __restrict__ mask, double* __restrict__ win_F) {
   const int b = blockIdx.y;
   if (b >= B) return;
   const int i0 = off[b], i1 = off[b + 1];
   const int w = win_id[b];
+  bool all = false;
+  if (thr_b) {
+    const float t = thr_b[b];
+    all = t < 0.f;
+    if (!all) th = fm_make_thresh(t);
+  }
   double F[9];
 #pragma unroll
   for (int i = 0; i < 9; i++) F[i] = w >= 0 ? models_all[(size_t)(w / 3) * 27 + 9 * (w % 3) + i] : 0.0;
   if (blockIdx.x == 0 && threadIdx.x < 9) win_F[(size_t)b * 9 + threadIdx.x] = F[threadIdx.x];
   for (int i = i0 + blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += gridDim.x * blockDim.x)
-    mask[i] = (w >= 0 && fm_inlier(F, pts[i], th)) ? 1 : 0;
+    mask[i] = (all || (w >= 0 && fm_inlier(F, pts[i], th))) ? 1 : 0;
 }
 
 }  // namespace
@@ -362,10 +411,11 @@ cudaError_t launch_fm_score(int n_hyp, const int* hyp_ids, int max_iters, const 
 }
 
 cudaError_t launch_fm_mask(int B, int max_n, const int* off, const float4* pts, const double* models_all,
-                           const int* win_id, float thr2, uint8_t* mask, double* win_F, cudaStream_t s) {
+                           const int* win_id, float thr2, const float* thr_b, uint8_t* mask, double* win_F,
+                           cudaStream_t s) {
   if (B <= 0 || max_n <= 0) return cudaSuccess;
   dim3 grid((unsigned)((max_n + 255) / 256), (unsigned)B);
-  fm_mask_kernel<<<grid, 256, 0, s>>>(B, off, pts, models_all, win_id, make_thresh(thr2), mask, win_F);
+  fm_mask_kernel<<<grid, 256, 0, s>>>(B, off, pts, models_all, win_id, make_thresh(thr2), thr_b, mask, win_F);
   return cudaGetLastError();
 }
 

@@ -111,14 +111,17 @@ cudaError_t launch_tv_motion(const TVBuffers& b, float th2, cudaStream_t stream)
 
 // ---- fm_kernels.cu (per-frame fundamental-matrix RANSAC; pts = (x0,y0,x1,y1) per match).
 // One RANSAC round evaluates n_hyp hypotheses; hyp_ids[i] = problem * max_iters + iteration addresses
-// the persistent model store models_all [B*max_iters][27]; sets / n_models / counts are per round.
+// the persistent model store models_all [B*max_iters][27]; sets / n_models / counts are per round.  Problems with
+// fewer than 15 matches are OpenCV's LMedS branch: their counts are the bits of the median float error, and
+// thr_b (per problem, may be NULL) carries their own squared threshold (negative: flag every match).
 cudaError_t launch_fm_solve(int n_hyp, const int* hyp_ids, const int* sets, const float4* pts, double* models_all,
                             int* n_models, cudaStream_t s);
 cudaError_t launch_fm_score(int n_hyp, const int* hyp_ids, int max_iters, const int* off, const float4* pts,
                             const double* models_all, const int* n_models, float thr2, int* counts, int n_sm,
                             cudaStream_t s);
 cudaError_t launch_fm_mask(int B, int max_n, const int* off, const float4* pts, const double* models_all,
-                           const int* win_id, float thr2, uint8_t* mask, double* win_F, cudaStream_t s);
+                           const int* win_id, float thr2, const float* thr_b, uint8_t* mask, double* win_F,
+                           cudaStream_t s);
 
 // ---- map_kernels.cu (device-resident map: slot-addressed keyframe / mappoint / observation arrays)
 cudaError_t launch_map_gather(double* pose_in, double* pts_in, double* uv, const double* d_kf, const double* d_pt,
