@@ -44,6 +44,7 @@ def parse_args():
     ap.add_argument("--distinct", type=int, default=37, help="distinct synthetic windows generated per GPU")
     ap.add_argument("--no-extra", action="store_true", help="skip the RANSAC / pose-only / cfg4 side measurements")
     ap.add_argument("--cpu-seconds", type=float, default=8.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--weak", type=int, default=0, help="1: also run the weak-scaling point-sharded BA (cfg5 per GPU) at N > 1")
     return ap.parse_args()
 
 
@@ -414,7 +415,7 @@ def main():
             dist.broadcast(uid, 0)
             ctx.comm_init(rank, world, uid.cpu().numpy())
         sharded = sharded_ba(ctx, stream, torch, dist, rank, world, peak, synth.cfg5(), "strong", True)
-        if world > 1:
+        if world > 1 and args.weak:
             # the same camera chain grown with the GPU count: 1000 cameras / 200k points / ~2M observations PER GPU
             # (weak scaling of the path with the collective; at one GPU this is cfg5 itself)
             sharded_weak = sharded_ba(ctx, stream, torch, dist, rank, world, peak,

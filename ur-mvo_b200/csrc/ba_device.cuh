@@ -130,21 +130,24 @@ struct PackStage {
 };
 
 // Packed-mode record access.  The record of the NEXT group is copied global -> shared with cp.async
-// (LDGSTS: no destination registers, so the compiler cannot consume it early) into the lane's 32-byte
-// cell of the warp's record buffer and read back at the top of the next iteration.
+// (LDGSTS: no destination registers, so the compiler cannot consume it early) into the warp's record buffer
+// and read back at the top of the next iteration.  The buffer holds the two 16-byte halves of the 32 records as
+// two planes ([half][lane]): every copy and every read-back touches 512 contiguous bytes (a lane stride of 32
+// bytes made four lanes share each bank group: twice the shared-memory wavefronts, measured as bank conflicts
+// of the LDGSTS path).
 struct RecRegs { int4 a, b; };
 __device__ __forceinline__ void rec_prefetch(double* buf, const ObsRec* rec, int g, int lane) {
-  const unsigned dst = (unsigned)__cvta_generic_to_shared(buf) + lane * 32;
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(buf) + lane * 16;
   const size_t src = __cvta_generic_to_global(rec + (size_t)g * 32 + lane);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16), "l"(src + 16) : "memory");
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 512), "l"(src + 16) : "memory");
 }
 __device__ __forceinline__ RecRegs rec_take(const double* buf, int lane) {
   asm volatile("cp.async.wait_all;" ::: "memory");
-  const int4* r = reinterpret_cast<const int4*>(buf) + lane * 2;
+  const int4* r = reinterpret_cast<const int4*>(buf);
   RecRegs x;
-  x.a = r[0];
-  x.b = r[1];
+  x.a = r[lane];
+  x.b = r[32 + lane];
   return x;
 }
 

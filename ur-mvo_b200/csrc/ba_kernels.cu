@@ -1479,6 +1479,8 @@ __device__ void lin_phase_packed(const Scope& sc, const BAWin& W, int cur, doubl
     {
       const int len = valid ? s1 - s0 : 0;
       const int maxlen = __reduce_max_sync(0xffffffffu, len);
+      // unrolled by four: the shared-memory loads of four observations are in flight before the (ordered) additions
+#pragma unroll 4
       for (int t = 0; t < maxlen; t++) {
         const int s = t < len ? s0 + t : kPackZero;
 #pragma unroll
@@ -1738,6 +1740,7 @@ __device__ void backsub_phase_packed(const Scope& sc, const BAWin& W, int cur, d
     {
       const int len = valid ? s1 - s0 : 0;
       const int maxlen = __reduce_max_sync(0xffffffffu, len);
+#pragma unroll 4
       for (int t = 0; t < maxlen; t++) {
         const int s = t < len ? s0 + t : kPackZero;
 #pragma unroll
