@@ -331,6 +331,7 @@ def main():
             tj = json.load(open(prof))
             roofline["traffic"] = tj.get("ba_window_cluster_kernel_bytes_per_launch")
             roofline["fp64_pipe_active_pct_ncu"] = tj.get("ba_window_cluster_kernel_fp64_pipe_active_pct")
+            roofline["lsu_wavefronts_pct_of_peak_ncu"] = tj.get("ba_window_cluster_kernel_lsu_wavefronts_pct_of_peak")
             fpi = tj.get("ba_window_cluster_kernel_fp64_flop_per_lm_iteration")
             if fpi:
                 its_launch = its_steps / args.steps
