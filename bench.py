@@ -419,8 +419,11 @@ def main():
         if world > 1 and args.weak:
             # the same camera chain grown with the GPU count: 1000 cameras / 200k points / ~2M observations PER GPU
             # (weak scaling of the path with the collective; at one GPU this is cfg5 itself)
+            # points numbered along the trajectory, as a SLAM map numbers its mappoints: every rank's contiguous range of
+            # points then belongs to its own stretch of cameras
             sharded_weak = sharded_ba(ctx, stream, torch, dist, rank, world, peak,
-                                      synth.cfg5(1005, 1000 * world, 200000 * world), "weak", world <= 2)
+                                      synth.sort_points_by_first_camera(synth.cfg5(1005, 1000 * world, 200000 * world)),
+                                      "weak", world <= 2)
 
     # ---------------------------------------------------------------- parity spot check + CPU baseline (rank 0)
     cpu_baseline = None

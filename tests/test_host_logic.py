@@ -137,3 +137,19 @@ def test_covisibility_union_over_shards_equals_global():
         acc |= ba_covisibility(shard_points(prob, r, 3))
     assert np.array_equal(acc, full)
     assert np.array_equal(full, np.triu(full)) and full.diagonal().all()
+
+
+def test_points_numbered_along_the_trajectory_is_the_same_problem(oracle):
+    """synth.sort_points_by_first_camera only renumbers the points (bench.py's weak-scaling sharded BA uses it so that a
+    rank's contiguous range of points is local to a stretch of cameras): same minimum, point-major observations."""
+    import numpy as np
+    from urmvo_b200 import synth
+    p = synth.small_ba(seed=3, n_pts=300)
+    q = synth.sort_points_by_first_camera(p)
+    assert np.all(np.diff(q["obs_pt"]) >= 0) and sorted(map(tuple, np.c_[q["uv"], q["obs_cam"]])) == sorted(map(tuple, np.c_[p["uv"], p["obs_cam"]]))
+    first = np.full(q["pts"].shape[0], 10 ** 9)
+    np.minimum.at(first, q["obs_pt"], q["obs_cam"])
+    assert np.all(np.diff(first) >= 0)
+    a, b = oracle.local_ba(p), oracle.local_ba(q)
+    assert abs(a[3].chi2_final[1] - b[3].chi2_final[1]) <= 1e-9 * a[3].chi2_final[1]
+    assert np.abs(a[0] - b[0]).max() < 1e-8

@@ -204,6 +204,31 @@ def cfg5(seed=1005, n_cams=1000, n_pts=200000):
     return make_ba(seed, n_cams, n_pts, 10.3, 16, 2, 0.01)
 
 
+def sort_points_by_first_camera(prob):
+    """Renumbers the points of a BA problem by the first camera that observes them (the order a SLAM map creates
+    its mappoints in: the generator above draws them at random along the trajectory).  The problem is the same; a
+    contiguous range of point ids is then local to a stretch of the trajectory, which is what a point-sharded solve
+    wants.  Observations stay point-major."""
+    obs_pt, obs_cam = prob["obs_pt"], prob["obs_cam"]
+    n_pts = prob["pts"].shape[0]
+    first = np.full(n_pts, np.iinfo(np.int32).max, dtype=np.int64)
+    np.minimum.at(first, obs_pt, obs_cam)
+    order = np.argsort(first, kind="stable")          # new index -> old index
+    inv = np.empty(n_pts, dtype=np.int64); inv[order] = np.arange(n_pts)
+    new_pt = inv[obs_pt]
+    o = np.lexsort((obs_cam, new_pt))
+    out = dict(prob)
+    out["pts"] = np.ascontiguousarray(prob["pts"][order])
+    if "gt_pts" in prob:
+        out["gt_pts"] = np.ascontiguousarray(prob["gt_pts"][order])
+    out["obs_pt"] = np.ascontiguousarray(new_pt[o].astype(np.int32))
+    out["obs_cam"] = np.ascontiguousarray(obs_cam[o])
+    out["uv"] = np.ascontiguousarray(prob["uv"][o])
+    if "is_outlier" in prob:
+        out["is_outlier"] = prob["is_outlier"][o]
+    return out
+
+
 def small_ba(seed=7, n_cams=6, n_pts=120, n_fixed=2, outlier_frac=0.05, **kw):
     return make_ba(seed, n_cams, n_pts, 4.5, n_cams, n_fixed, outlier_frac, **kw)
 
