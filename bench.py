@@ -44,7 +44,7 @@ def parse_args():
     ap.add_argument("--distinct", type=int, default=37, help="distinct synthetic windows generated per GPU")
     ap.add_argument("--no-extra", action="store_true", help="skip the RANSAC / pose-only / cfg4 side measurements")
     ap.add_argument("--cpu-seconds", type=float, default=8.0, help="budget of the cpu_baseline leg")
-    ap.add_argument("--weak", type=int, default=0, help="1: also run the weak-scaling point-sharded BA (cfg5 per GPU) at N > 1")
+    ap.add_argument("--weak", type=int, default=1, help="0: skip the weak-scaling point-sharded BA (cfg5 per GPU) at N > 1")
     return ap.parse_args()
 
 
