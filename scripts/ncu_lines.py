@@ -41,7 +41,12 @@ print("samples", n, "warp-instructions %.3f G" % (sum(exline.values()) / 1e9))
 print(" ".join(f"{k[6:]}={v / sum(tot.values()) * 100:.1f}%" for k, v in tot.most_common(8)))
 for ln, c in byline.most_common(top):
     t3 = ", ".join(f"{k[6:]}:{v}" for k, v in bystall[ln].most_common(3))
-    print(f"{ln:5d} {c / n * 100:5.1f}% ex={exline[ln]:9d} [{t3}] {src[ln - 1].strip()[:90] if ln > 0 else ''}")
+    print(f"{ln:5d} {c / n * 100:5.1f}% ex={exline[ln]:9d} [{t3}] {src[ln - 1].strip()[:90] if 0 < ln <= len(src) else ''}")
+if os.environ.get("BY_EXEC"):  # short kernels have too few samples: rank the lines by executed warp instructions
+    ne = sum(exline.values())
+    print("by executed warp instructions:")
+    for ln, c in exline.most_common(top):
+        print(f"{ln:5d} {c / ne * 100:5.1f}% ex={c:9d} {src[ln - 1].strip()[:100] if 0 < ln <= len(src) else ''}")
 if len(sys.argv) > 4:  # dump the SASS of the given source lines with their samples
     want = {int(x) for x in sys.argv[4].split(",")}
     for k, (d, (off, ln, txt)) in enumerate(zip(data, seq)):
