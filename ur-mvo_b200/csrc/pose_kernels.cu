@@ -33,7 +33,9 @@ __device__ __forceinline__ void pose_map(const double* R, const double* t, const
 // added in warp order by thread k.  red: >= 29 * 32 doubles.
 // (Measured and NOT adopted: evaluating the normal equations in the trial-cost pass, so that an accepted trial is
 // already linearised for the next iteration — identical results, but the heavier trial pass cost more than the saved
-// error passes: 0.278 -> 0.314 ms for one 1000-match frame.)
+// error passes: 0.278 -> 0.314 ms for one 1000-match frame.  512 threads per frame (two observations per thread and
+// pass, 128 registers): 0.281 -> 0.287 ms for one frame, 0.34 -> 0.44 ms for 100 — the spills and the longer CTA
+// reduction cost more than the shorter pass saves.)
 __device__ __forceinline__ void block_sum28(double (&v)[28], double* red) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
   double a[16];
