@@ -1,4 +1,5 @@
 """CPU: the BA / pose-only oracle against known answers and scipy."""
+import pytest
 import numpy as np
 from scipy.optimize import least_squares
 from scipy.spatial.transform import Rotation
@@ -174,3 +175,29 @@ def test_multicam_pose_only_matches_single_model_and_rejects_bad_index(oracle):
     assert np.abs(gp[:, 4:] - b["gt_poses"][:, 4:]).max() < 0.05 and (gn > 0.7 * 150).all()
     bad = dict(many, kind_model=(many["kind_model"] | 0xF0).astype(np.uint8))
     assert (oracle.pose_only_batch_multicam(bad, 10.0, 75.0)[2] < 0).all()
+
+
+def test_pose_only_final_pose_is_opencvs_least_squares_pose_over_the_inliers(oracle):
+    """An independent pin of FrameOptimization's result with the REAL OpenCV: rounds 3 and 4 run without the robust
+    kernel over the edges that survived the re-classification (src/g2o_optimization.cc:287-288), so the returned pose
+    is the plain least-squares minimum over the final inlier set.  cv2.solvePnP(ITERATIVE) + solvePnPRefineLM, started
+    from the same INPUT pose on that set, must reach the same pose."""
+    cv2 = pytest.importorskip("cv2")
+    b = synth.make_pose_batch(3, B=6, n_obs=400)
+    K = np.array([[b["intr"][0], 0, b["intr"][2]], [0, b["intr"][1], b["intr"][3]], [0, 0, 1.0]])
+    for f in range(6):
+        s = slice(b["obs_offset"][f], b["obs_offset"][f + 1])
+        pose, inl, n, _ = oracle.pose_only(b["poses"][f], b["uv"][s], b["Xw"][s], b["intr"])
+        m = inl.astype(bool)
+        R = synth.quat_to_R(pose[None, :4])[0]
+        Rcw, tcw = R.T, -R.T @ pose[4:]
+        R0 = synth.quat_to_R(b["poses"][f][None, :4])[0]
+        rvec, _ = cv2.Rodrigues(R0.T)
+        tvec = (-R0.T @ b["poses"][f][4:]).reshape(3, 1)
+        ok, rv, tv = cv2.solvePnP(b["Xw"][s][m], b["uv"][s][m], K, None, rvec.copy(), tvec.copy(), useExtrinsicGuess=True,
+                                  flags=cv2.SOLVEPNP_ITERATIVE)
+        rv, tv = cv2.solvePnPRefineLM(b["Xw"][s][m], b["uv"][s][m], K, None, rv, tv,
+                                      criteria=(cv2.TERM_CRITERIA_EPS + cv2.TERM_CRITERIA_COUNT, 100, 1e-12))
+        R2, _ = cv2.Rodrigues(rv)
+        assert ok and np.abs(R0.T - Rcw).max() > 1e-3      # the input pose is far from the answer
+        assert np.abs(R2 - Rcw).max() < 1e-6 and np.abs(tv.ravel() - tcw).max() < 1e-6
