@@ -123,6 +123,39 @@ def test_robust_first_pass_minimum_matches_scipy_huber(oracle):
     assert abs(st.chi2_final[0] - 2 * sol.cost) / (2 * sol.cost) < 1e-6
 
 
+def test_stereo_second_pass_minimum_matches_scipy_least_squares(oracle):
+    """EdgeStereoSE3ProjectXYZ next to EdgeSE3ProjectXYZ (src/g2o_optimization.cc:96-118): with it0 = 0 the graph is
+    plain least squares over 2-row mono and 3-row stereo residuals (third row u_right - (u - bf / z)); scipy finds the
+    same minimum."""
+    p = synth.add_stereo(synth.small_ba(seed=9, n_cams=4, n_pts=40, outlier_frac=0.0), 3, stereo_frac=0.5)
+    assert 10 < p["kind"].sum() < len(p["kind"]) - 10
+    poses, pts, inl, st = oracle.local_ba_stereo(p, 10.0, 75.0, it0=0, it1=40)
+    Np = p["pts"].shape[0]
+    free = np.where(p["fixed"] == 0)[0]
+    fx, bf = p["intr5"][0], p["intr5"][4]
+    stereo = p["kind"] != 0
+
+    def unpack(x):
+        P = p["poses"].copy()
+        for k, c in enumerate(free):
+            r = Rotation.from_rotvec(x[k * 6:k * 6 + 3]) * Rotation.from_quat(p["poses"][c, :4])
+            P[c, :4] = r.as_quat()
+            P[c, 4:] = p["poses"][c, 4:] + x[k * 6 + 3:k * 6 + 6]
+        return P, p["pts"] + x[len(free) * 6:].reshape(Np, 3)
+
+    def resid(x):
+        P, X = unpack(x)
+        uv, z = synth.project(P, p["obs_cam"], X[p["obs_pt"]])
+        e = (p["uv3"][:, :2] - uv).ravel()
+        er = (p["uv3"][:, 2] - (uv[:, 0] - bf / z))[stereo]
+        return np.r_[e, er]
+
+    assert fx > 0
+    sol = least_squares(resid, np.zeros(len(free) * 6 + Np * 3), method="trf", xtol=1e-15, ftol=1e-15, gtol=1e-12, max_nfev=400)
+    assert abs(st.chi2_final[1] - 2 * sol.cost) / (2 * sol.cost) < 1e-6
+    assert np.abs(unpack(sol.x)[1] - pts).max() < 1e-4
+
+
 def test_outliers_are_flagged(oracle):
     p = synth.cfg1()
     _, _, inl, st = oracle.local_ba(p)
