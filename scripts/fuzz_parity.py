@@ -34,6 +34,37 @@ for k in range(N):
 print("local BA", w)
 bad += w["cost"] > 1e-6 or w["pose"] > 1e-5 or w["flags"] > 0 or w["iters"] > 0
 
+# ---- stereo / several camera models (3-row phases), large windows in tile mode with either band solver
+m = dict(n=0, cost=0.0, pose=0.0, flags=0)
+for k in range(max(10, N // 8)):
+    base = synth.add_stereo(synth.small_ba(seed=50000 + k, n_cams=int(rng.integers(4, 11)), n_pts=int(rng.integers(60, 500)),
+                                           n_fixed=2, outlier_frac=float(rng.uniform(0, 0.15))), 50500 + k,
+                            stereo_frac=float(rng.uniform(0, 1)))
+    if k % 2:
+        p = synth.add_camera_models(base, 51000 + k, n_models=int(rng.integers(2, 6)))
+        g = ctx.local_ba_multicam(p, 10.0, 75.0); o = po.local_ba_multicam(p, 10.0, 75.0)
+    else:
+        g = ctx.local_ba_stereo(base, 10.0, 75.0); o = po.local_ba_stereo(base, 10.0, 75.0)
+    m["n"] += 1
+    m["cost"] = max(m["cost"], abs(g[3].chi2_final[1] - o[3].chi2_final[1]) / abs(o[3].chi2_final[1]))
+    m["pose"] = max(m["pose"], float(np.abs(g[0] - o[0]).max()))
+    m["flags"] += int((g[2] != o[2]).sum())
+print("stereo / camera models", m)
+bad += m["cost"] > 1e-6 or m["pose"] > 1e-5 or m["flags"] > 0
+L = dict(n=0, cost=0.0, pose=0.0, flags=0, tile=0)
+for k in range(max(6, N // 40)):
+    ncam = int(rng.integers(30, 420)); span = int(rng.integers(5, 17))
+    p = synth.make_ba(60000 + k, ncam, int(ncam * rng.integers(20, 45)), 0.6 * span, span, 2, 0.02)
+    plan = U.ShardedBAPlan(ctx, U.shard_points(p, 0, 1), covis=U.ba_covisibility(p), opts=U.BAOptions(0, 0, 0, 0, 0, 0, 0, 1 + k % 2))
+    plan.run(); L["tile"] += int(plan.phase_info()["tile_mode"]); g = plan.download(); plan.close()
+    o = po.local_ba(p)
+    L["n"] += 1
+    L["cost"] = max(L["cost"], abs(g[3].chi2_final[1] - o[3].chi2_final[1]) / abs(o[3].chi2_final[1]))
+    L["pose"] = max(L["pose"], float(np.abs(g[0] - o[0]).max()))
+    L["flags"] += int((g[2] != o[2]).sum())
+print("large windows (tile mode, band solve / cyclic reduction alternating)", L)
+bad += L["cost"] > 1e-6 or L["pose"] > 1e-5 or L["flags"] > 0
+
 # ---- pose-only frames
 b = synth.make_pose_batch(777, B=N, n_obs=int(rng.integers(60, 1200)), outlier_frac=0.15, rot_deg=3.0, trans=0.2)
 gp, gi, gn = ctx.pose_only_batch(b); op, oi, on = po.pose_only_batch(b)
