@@ -1897,6 +1897,10 @@ __device__ LMResult lm_optimize(const Scope& sc, const BAWin& W, const BARun& ru
         if (sc.blk() == 0) {
           ok2 = pcg_dense_smem(sc, W, lambda, run.pcg_tol, run.pcg_max_iter, run.dense_solver, pcg_sm, pcg_it);
           if (threadIdx.x == 0) { __stcg(flags, ok2 ? 1.0 : 0.0); __stcg(flags + 1, (double)pcg_it); }
+          // the CTA that solved also moves the (<= 16) cameras: the scope barrier below then publishes the solution
+          // flags AND the trial cameras, instead of a second barrier after a camera phase spread over the scope
+          __syncthreads();
+          if (__ldcg(flags) > 0.5) cam_update(CtaScope(), W, cur);
         }
         sc.sync();
         ok2 = __ldcg(flags) > 0.5;
@@ -1923,7 +1927,7 @@ __device__ LMResult lm_optimize(const Scope& sc, const BAWin& W, const BARun& ru
       double tempChi = 1.7976931348623157e308;
       double scale = 0.0;
       if (ok2) {
-        {
+        if (!SMEM) {
           BA_T0();
           cam_update(sc, W, cur);
           sc.sync();
