@@ -1378,7 +1378,7 @@ static int pose_plan_create_impl(urmvo_ctx* ctx, urmvo_pose_plan** out, int B, c
                                       const double* poses, const double* uv, const double* Xw,
                                       const double* intr, double chi2_thr, int rounds, int its_per_round,
                                       const uint8_t* inlier, bool borrow_ws, int uv_stride = 2,
-                                      const uint8_t* kind = nullptr, double chi2_thr_stereo = 0.0, int n_models = 0) {
+                                      const uint8_t* kind = nullptr, double chi2_thr_stereo = 0.0, int n_models = 0) try {
   // n_models > 0: intr is a table of n_models rows (fx fy cx cy bf) and kind[o] = stereo bit | camera model << 1
   // (the reference reads camera_list[mpc->id_camera] per constraint, src/g2o_optimization.cc:221-224, :243-250)
   if (!ctx || !out) return fail(URMVO_ERR_ARG, "pose_plan_create: null context / out");
@@ -1454,6 +1454,8 @@ static int pose_plan_create_impl(urmvo_ctx* ctx, urmvo_pose_plan** out, int B, c
     if (x != cudaSuccess) { urmvo_pose_plan_destroy(p); return fail(URMVO_ERR_CUDA, std::string("pose_plan_create upload: ") + cudaGetErrorString(x)); }
   *out = p;
   return URMVO_OK;
+} catch (const std::exception& e) {  // no exception crosses the C ABI
+  return fail(URMVO_ERR_ARG, std::string("pose_plan_create_impl: ") + e.what());
 }
 
 extern "C" int urmvo_pose_plan_create(urmvo_ctx* ctx, urmvo_pose_plan** out, int B, const int32_t* obs_off,
@@ -1631,8 +1633,10 @@ static int tv_plan_create_impl(urmvo_ctx* ctx, urmvo_tv_plan** out, int n1, cons
 
 extern "C" int urmvo_tv_plan_create(urmvo_ctx* ctx, urmvo_tv_plan** out, int n1, const float* keys1, int n2,
                                     const float* keys2, const int32_t* matches12, const float* K, float sigma,
-                                    int n_hyp, const int32_t* sets) {
+                                    int n_hyp, const int32_t* sets) try {
   return tv_plan_create_impl(ctx, out, n1, keys1, n2, keys2, matches12, K, sigma, n_hyp, sets, false);
+} catch (const std::exception& e) {  // no exception crosses the C ABI
+  return fail(URMVO_ERR_ARG, std::string("urmvo_tv_plan_create: ") + e.what());
 }
 
 extern "C" int urmvo_tv_plan_run_ransac(urmvo_tv_plan* p) {
@@ -1646,7 +1650,7 @@ extern "C" int urmvo_tv_plan_run_ransac(urmvo_tv_plan* p) {
   return URMVO_OK;
 }
 
-extern "C" int urmvo_tv_plan_download_hyps(urmvo_tv_plan* p, int model, float* scores, uint32_t* masks, float* models) {
+extern "C" int urmvo_tv_plan_download_hyps(urmvo_tv_plan* p, int model, float* scores, uint32_t* masks, float* models) try {
   if (!p || model < 0 || model > 1) return fail(URMVO_ERR_ARG, "tv_plan_download_hyps: bad plan / model");
   CU_TRY(cudaSetDevice(p->ctx->device));
   cudaStream_t s = p->ctx->stream;
@@ -1663,10 +1667,12 @@ extern "C" int urmvo_tv_plan_download_hyps(urmvo_tv_plan* p, int model, float* s
   if (models)
     for (size_t h = 0; h < nh; h++) std::memcpy(models + h * 9, tmp.data() + h * 18, 9 * sizeof(float));
   return URMVO_OK;
+} catch (const std::exception& e) {  // no exception crosses the C ABI
+  return fail(URMVO_ERR_ARG, std::string("urmvo_tv_plan_download_hyps: ") + e.what());
 }
 
 extern "C" int urmvo_tv_plan_reconstruct(urmvo_tv_plan* p, float* T21, float* P3D, uint8_t* triangulated,
-                                         uint8_t* mask_H, uint8_t* mask_F, urmvo_tv_stats* stats, int* success) {
+                                         uint8_t* mask_H, uint8_t* mask_F, urmvo_tv_stats* stats, int* success) try {
   if (!p || !T21 || !P3D || !triangulated || !success) return fail(URMVO_ERR_ARG, "tv_plan_reconstruct: null argument");
   if (!p->ransac_done) return fail(URMVO_ERR_ARG, "tv_plan_reconstruct: run_ransac has not been called");
   CU_TRY(cudaSetDevice(p->ctx->device));
@@ -1770,6 +1776,8 @@ extern "C" int urmvo_tv_plan_reconstruct(urmvo_tv_plan* p, float* T21, float* P3
   }
   if (stats) *stats = st;
   return URMVO_OK;
+} catch (const std::exception& e) {  // no exception crosses the C ABI
+  return fail(URMVO_ERR_ARG, std::string("urmvo_tv_plan_reconstruct: ") + e.what());
 }
 
 extern "C" int urmvo_tv_plan_set_score_mode(urmvo_tv_plan* p, int score_mode) {

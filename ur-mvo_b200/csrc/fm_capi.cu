@@ -155,7 +155,7 @@ extern "C" void urmvo_fm_plan_destroy(urmvo_fm_plan* p) {
 extern "C" int urmvo_fm_plan_hypotheses(const urmvo_fm_plan* p) { return p ? p->evaluated : 0; }
 
 static int fm_plan_create_impl(urmvo_ctx* ctx, urmvo_fm_plan** out, int B, const int32_t* off, const float* pts0,
-                               const float* pts1, double thresh, double confidence, int max_iters, bool borrow) {
+                               const float* pts1, double thresh, double confidence, int max_iters, bool borrow) try {
   if (!ctx || !out || B <= 0 || !off || !pts0 || !pts1)
     return set_error(URMVO_ERR_ARG, "fm_plan_create: null or empty input");
   *out = nullptr;
@@ -251,6 +251,8 @@ static int fm_plan_create_impl(urmvo_ctx* ctx, urmvo_fm_plan** out, int B, const
     }
   *out = p;
   return URMVO_OK;
+} catch (const std::exception& e) {  // no exception crosses the C ABI
+  return set_error(URMVO_ERR_ARG, std::string("fm_plan_create_impl: ") + e.what());
 }
 
 extern "C" int urmvo_fm_plan_create(urmvo_ctx* ctx, urmvo_fm_plan** out, int B, const int32_t* off,
@@ -262,7 +264,7 @@ extern "C" int urmvo_fm_plan_create(urmvo_ctx* ctx, urmvo_fm_plan** out, int B, 
 // The RANSAC loop of every problem, in rounds: round 1 evaluates the first kFirstRound iterations of
 // each problem, later rounds everything that is left of each problem's (shrinking) budget.  After
 // every round the host replays the sequential "better model -> new budget" logic on the counts.
-extern "C" int urmvo_fm_plan_run(urmvo_fm_plan* p) {
+extern "C" int urmvo_fm_plan_run(urmvo_fm_plan* p) try {
   if (!p) return set_error(URMVO_ERR_ARG, "fm_plan_run: null plan");
   CU_TRY(cudaSetDevice(p->ctx->device));
   cudaStream_t s = p->ctx->stream;
@@ -362,9 +364,11 @@ extern "C" int urmvo_fm_plan_run(urmvo_fm_plan* p) {
     }
   }
   return URMVO_OK;
+} catch (const std::exception& e) {  // no exception crosses the C ABI
+  return set_error(URMVO_ERR_ARG, std::string("urmvo_fm_plan_run: ") + e.what());
 }
 
-extern "C" int urmvo_fm_plan_finish(urmvo_fm_plan* p, uint8_t* inlier, urmvo_fm_stats* stats) {
+extern "C" int urmvo_fm_plan_finish(urmvo_fm_plan* p, uint8_t* inlier, urmvo_fm_stats* stats) try {
   if (!p) return set_error(URMVO_ERR_ARG, "fm_plan_finish: null plan");
   CU_TRY(cudaSetDevice(p->ctx->device));
   cudaStream_t s = p->ctx->stream;
@@ -412,6 +416,8 @@ extern "C" int urmvo_fm_plan_finish(urmvo_fm_plan* p, uint8_t* inlier, urmvo_fm_
       for (int i = 0; i < 9; i++) stats[b].F[i] = p->h_winF[(size_t)b * 9 + i];
     }
   return URMVO_OK;
+} catch (const std::exception& e) {  // no exception crosses the C ABI
+  return set_error(URMVO_ERR_ARG, std::string("urmvo_fm_plan_finish: ") + e.what());
 }
 
 extern "C" int urmvo_fm_ransac_batch(urmvo_ctx* ctx, int B, const int32_t* off, const float* pts0, const float* pts1,
