@@ -153,3 +153,25 @@ def test_points_numbered_along_the_trajectory_is_the_same_problem(oracle):
     a, b = oracle.local_ba(p), oracle.local_ba(q)
     assert abs(a[3].chi2_final[1] - b[3].chi2_final[1]) <= 1e-9 * a[3].chi2_final[1]
     assert np.abs(a[0] - b[0]).max() < 1e-8
+
+
+def test_trajectory_ordered_shards_are_camera_local():
+    """bench.py's weak-scaling sharded BA: with points numbered along the trajectory a rank's contiguous range of points
+    touches only its own stretch of cameras (plus the co-visibility halo), the union of the shards is the problem."""
+    import numpy as np
+    import urmvo_b200 as U
+    from urmvo_b200 import synth
+    p = synth.sort_points_by_first_camera(synth.make_ba(77, 200, 4000, 6.0, 12, 2, 0.01))
+    world = 4
+    shards = [U.shard_points(p, r, world) for r in range(world)]
+    assert sum(s["uv"].shape[0] for s in shards) == p["uv"].shape[0]
+    assert sum(s["pts"].shape[0] for s in shards) == p["pts"].shape[0]
+    lo = [int(s["obs_cam"].min()) for s in shards]
+    hi = [int(s["obs_cam"].max()) for s in shards]
+    assert lo == sorted(lo) and hi == sorted(hi)
+    for r in range(world):
+        assert hi[r] - lo[r] <= 200 // world + 2 * 12 + 12  # its quarter of the trajectory + the halo of the span
+    # the generator's own (random) numbering spreads every shard over the whole trajectory
+    q = synth.make_ba(77, 200, 4000, 6.0, 12, 2, 0.01)
+    s0 = U.shard_points(q, 0, world)
+    assert int(s0["obs_cam"].max()) - int(s0["obs_cam"].min()) > 150
