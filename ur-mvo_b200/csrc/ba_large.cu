@@ -188,11 +188,17 @@ k_lg_lin(const BAWin* __restrict__ wins, BARun run, const LgState* __restrict__ 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   double* red = reinterpret_cast<double*>(smem);                     // 4 * 32 doubles
   double* stage0 = red + 4 * 32;
-  unsigned char* slot0 = reinterpret_cast<unsigned char*>(stage0 + (size_t)kLgWarps * kLgStage);
-  int* s_np = reinterpret_cast<int*>(slot0 + (size_t)kLgWarps * kLgSlotBytes);
-  PackStage st;
-  st.f = stage0 + (size_t)wid * kLgStage;
-  st.slot = reinterpret_cast<signed char*>(slot0 + (size_t)wid * kLgSlotBytes);
+  // TWO staging buffers per warp: while the slower warps of the CTA still sweep round r (buffer r & 1), a warp that is
+  // done stages its group of round r + 1 into the other buffer — one CTA barrier per round instead of two, and the
+  // latency-bound staging chain of some warps overlaps the fp64-dense sweep of the others
+  unsigned char* slot0 = reinterpret_cast<unsigned char*>(stage0 + (size_t)2 * kLgWarps * kLgStage);
+  int* s_np = reinterpret_cast<int*>(slot0 + (size_t)2 * kLgWarps * kLgSlotBytes);  // [2][kLgWarps]
+  auto stage_of = [&](int buf) {
+    PackStage st;
+    st.f = stage0 + (size_t)(buf * kLgWarps + wid) * kLgStage;
+    st.slot = reinterpret_cast<signed char*>(slot0 + (size_t)(buf * kLgWarps + wid) * kLgSlotBytes);
+    return st;
+  };
   const int cur = stt->cur;
   const bool robust = stt->robust != 0;
   const double lambda = DIAG ? 0.0 : stt->lambda;
@@ -205,34 +211,16 @@ k_lg_lin(const BAWin* __restrict__ wins, BARun run, const LgState* __restrict__ 
   double* __restrict__ bl_out = W.bl;
   double chi_acc = 0.0, maxdiag_acc = 0.0;
   // the all-zero slot of every stage (absent pairs read it: they add exactly +0)
-  for (int a = lane; a < kPackFields; a += 32) st.f[a * kPackSlots + kPackZero] = 0.0;
+  for (int a = lane; a < kPackFields; a += 32) {
+    stage_of(0).f[a * kPackSlots + kPackZero] = 0.0;
+    stage_of(1).f[a * kPackSlots + kPackZero] = 0.0;
+  }
   __syncthreads();
+  int rp = 0;  // buffer of the round that is swept next (runs on across the chunks)
 
-  for (int ch = blockIdx.x; ch < W.n_chunk; ch += gridDim.x) {
-    const int g_begin = W.chunk_grp[ch], g_end = W.chunk_grp[ch + 1];
-    const int b0 = W.chunk_blk[ch], nb = W.chunk_blk[ch + 1] - b0;
-    // a chunk with <= 128 blocks is swept by several REPLICAS of the block owners (warp-aligned), each
-    // replica visiting every n_rep-th staged group; all replicas flush
-    const int nb_pad = (nb + 31) & ~31;
-    const int n_rep = nb_pad > 0 ? (kLgThreads / nb_pad > 0 ? kLgThreads / nb_pad : 1) : 1;
-    const int my_rep = nb_pad > 0 ? tid / nb_pad : 0, bidx = nb_pad > 0 ? tid - my_rep * nb_pad : tid;
-    const bool has = my_rep < n_rep && bidx < nb;
-    int cil = 0, cjl = 0, gblk = 0;
-    if (has) {
-      const int d0 = W.blk_desc[(size_t)(b0 + bidx) * 2];
-      gblk = W.blk_desc[(size_t)(b0 + bidx) * 2 + 1];
-      cil = d0 & 255; cjl = (d0 >> 8) & 255;
-    }
-    const bool diag_lane = has && cil == cjl;
-    double accS[36];
-#pragma unroll
-    for (int e = 0; e < 36; e++) accS[e] = 0.0;
-    double accb[12];
-#pragma unroll
-    for (int e = 0; e < 12; e++) accb[e] = 0.0;
-
-    for (int gb = g_begin; gb < g_end; gb += kLgWarps) {
-      // ---- stage: warp w takes group gb + w (lane = observation)
+  // ---- stage: warp w takes group gb + w of the round (lane = observation) into its buffer `buf`
+  auto stage_round = [&](int gb, int g_end, int buf) {
+    PackStage st = stage_of(buf);
       const int g = gb + wid;
       int np_mine = 0;
       if (g < g_end) {
@@ -329,15 +317,42 @@ k_lg_lin(const BAWin* __restrict__ wins, BARun run, const LgState* __restrict__ 
           }
         }
       }
-      if (lane == 0) s_np[wid] = np_mine;
-      __syncthreads();
+      if (lane == 0) s_np[buf * kLgWarps + wid] = np_mine;
+  };
+
+  for (int ch = blockIdx.x; ch < W.n_chunk; ch += gridDim.x) {
+    const int g_begin = W.chunk_grp[ch], g_end = W.chunk_grp[ch + 1];
+    const int b0 = W.chunk_blk[ch], nb = W.chunk_blk[ch + 1] - b0;
+    // a chunk with <= 128 blocks is swept by several REPLICAS of the block owners (warp-aligned), each
+    // replica visiting every n_rep-th staged group; all replicas flush
+    const int nb_pad = (nb + 31) & ~31;
+    const int n_rep = nb_pad > 0 ? (kLgThreads / nb_pad > 0 ? kLgThreads / nb_pad : 1) : 1;
+    const int my_rep = nb_pad > 0 ? tid / nb_pad : 0, bidx = nb_pad > 0 ? tid - my_rep * nb_pad : tid;
+    const bool has = my_rep < n_rep && bidx < nb;
+    int cil = 0, cjl = 0, gblk = 0;
+    if (has) {
+      const int d0 = W.blk_desc[(size_t)(b0 + bidx) * 2];
+      gblk = W.blk_desc[(size_t)(b0 + bidx) * 2 + 1];
+      cil = d0 & 255; cjl = (d0 >> 8) & 255;
+    }
+    const bool diag_lane = has && cil == cjl;
+    double accS[36];
+#pragma unroll
+    for (int e = 0; e < 36; e++) accS[e] = 0.0;
+    double accb[12];
+#pragma unroll
+    for (int e = 0; e < 12; e++) accb[e] = 0.0;
+
+    stage_round(g_begin, g_end, rp);  // first round of the chunk (its buffer was last swept two rounds ago)
+    for (int gb = g_begin; gb < g_end; gb += kLgWarps) {
+      __syncthreads();  // round gb is staged by every warp; everybody has left the sweep of the round before
       // ---- sweep: every thread visits the staged points for the camera pair of ITS block
       for (int ws = 0; ws < kLgWarps; ws++) {
-        const int np = s_np[ws];
+        const int np = s_np[rp * kLgWarps + ws];
         if (np == 0 || ws % n_rep != my_rep % n_rep) continue;
         PackStage sv;
-        sv.f = stage0 + (size_t)ws * kLgStage;
-        const unsigned char* sl = slot0 + (size_t)ws * kLgSlotBytes;
+        sv.f = stage0 + (size_t)(rp * kLgWarps + ws) * kLgStage;
+        const unsigned char* sl = slot0 + (size_t)(rp * kLgWarps + ws) * kLgSlotBytes;
         for (int q = 0; q < np; q++) {
           int si = kPackZero, sj = kPackZero;
           if (has) { si = sl[q * 32 + cil]; sj = DIAG ? si : sl[q * 32 + cjl]; }
@@ -385,7 +400,8 @@ k_lg_lin(const BAWin* __restrict__ wins, BARun run, const LgState* __restrict__ 
           }
         }
       }
-      __syncthreads();
+      if (gb + kLgWarps < g_end) stage_round(gb + kLgWarps, g_end, rp ^ 1);
+      rp ^= 1;
     }
     // ---- flush: each block of S once per chunk
     if (has) {
@@ -1018,8 +1034,8 @@ cudaError_t lg_timing_read(unsigned long long* out, bool reset) {
 int lg_band_max_m() { return kBandMaxM; }
 
 static size_t lg_lin_smem() {
-  return (size_t)4 * 32 * sizeof(double) + (size_t)kLgWarps * kLgStage * sizeof(double) +
-         (size_t)kLgWarps * kLgSlotBytes + kLgWarps * sizeof(int) + 32;
+  return (size_t)4 * 32 * sizeof(double) + (size_t)2 * kLgWarps * kLgStage * sizeof(double) +
+         (size_t)2 * kLgWarps * kLgSlotBytes + 2 * kLgWarps * sizeof(int) + 32;  // two staging buffers per warp
 }
 
 cudaError_t lg_prepare(int M, int Ncf) {
